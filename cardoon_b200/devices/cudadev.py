@@ -1,0 +1,91 @@
+"""
+Device-plugin side of the CUDA boundary.
+
+Replaces the reference's AD-tape module devices/cppaddev.py: there,
+``eval``/``eval_and_deriv`` (:134-170) taped ``eval_cqs`` with CppAD and
+replayed the tape; here they hand the port voltages and the packed
+post-``process_params`` parameter record to the forward-mode dual-number
+kernel of the model (``cdn_dev_eval`` in libcardoon_b200.so) with a batch of
+one.  The nodal engines never call these: they evaluate whole device groups
+inside the Newton kernels from the same packed records.
+
+There is deliberately no Python/CPU implementation of the model equations in
+this package: without the CUDA library and a GPU these functions raise.
+"""
+import numpy as np
+
+from .param_layout import MODEL_IDS, LAYOUTS
+
+
+class CudaModel(object):
+    """Mixin for nonlinear device classes evaluated by a CUDA kernel.
+
+    Sub-classes set ``cudaModel`` (a key of param_layout.MODEL_IDS) and
+    implement ``cuda_pack() -> (flags, params)`` where ``params`` follows
+    param_layout.LAYOUTS[cudaModel].  ``process_params``/``set_temp_vars``
+    must call ``delete_tape(self)`` (same contract as the reference,
+    cppaddev.py:99-111) so that the cached record is rebuilt.
+    """
+    cudaModel = None
+
+    def cuda_spec(self):
+        spec = self.__dict__.get('_cuda_spec')
+        if spec is None:
+            flags, params = self.cuda_pack()
+            params = np.ascontiguousarray(params, dtype=np.float64)
+            nexp = len(LAYOUTS[self.cudaModel][0])
+            if self.cudaModel != 'memr':
+                assert params.shape == (nexp,), \
+                    '{0}: packed {1} parameters, layout has {2}'.format(
+                        self.instanceName, params.shape, nexp)
+            spec = dict(model=MODEL_IDS[self.cudaModel], flags=int(flags),
+                        params=params,
+                        nxin=len(self.controlPorts) + self.nDelays,
+                        ncs=len(self.csOutPorts), nqs=len(self.qsOutPorts))
+            self._cuda_spec = spec
+        return spec
+
+    # ---- reference plugin API (batch of one) --------------------------
+    def eval_and_deriv(self, vPort):
+        return eval_and_deriv(self, vPort)
+
+    def eval(self, vPort):
+        return eval(self, vPort)
+
+    def eval_cqs(self, vPort, getOP=False):
+        """(iVec, qVec) at the control voltages ``vPort``.
+
+        Same meaning as the reference's ``eval_cqs``; computed on the GPU.
+        """
+        out = eval(self, vPort)
+        ncs = len(self.csOutPorts)
+        return (out[:ncs], out[ncs:])
+
+
+def delete_tape(dev):
+    """Invalidate the cached kernel record (reference cppaddev.py:99)."""
+    dev.__dict__.pop('_cuda_spec', None)
+
+
+def _run(dev, vPort, want_jac):
+    from .._lib import get_lib
+    spec = dev.cuda_spec()
+    vPort = np.asarray(vPort, dtype=np.float64)
+    if vPort.shape != (spec['nxin'],):
+        raise ValueError('{0}: expected {1} port voltages, got {2}'.format(
+            dev.instanceName, spec['nxin'], vPort.shape))
+    return get_lib().dev_eval_host(spec['model'], spec['flags'],
+                                   spec['params'][:, None], vPort[:, None],
+                                   spec['ncs'] + spec['nqs'], want_jac)
+
+
+def eval_and_deriv(dev, vPort):
+    """(out, Jac): out = [currents, charges], Jac[r, c] = d out_r / d vPort_c."""
+    out, jac = _run(dev, vPort, True)
+    nout = out.shape[0]
+    return out[:, 0].copy(), jac[:, 0].reshape(nout, -1).copy()
+
+
+def eval(dev, vPort):
+    out, _ = _run(dev, vPort, False)
+    return out[:, 0].copy()
