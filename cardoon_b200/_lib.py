@@ -1,0 +1,154 @@
+"""
+ctypes binding of libcardoon_b200.so (include/cardoon_b200.h).
+
+PyTorch only owns device buffers here (``tensor.data_ptr()``) and provides
+the current stream; every computation is a call into the library.  There is
+no CPU fallback: a missing library or GPU raises ``CudaUnavailable``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(_HERE, 'libcardoon_b200.so')
+
+
+class CudaUnavailable(RuntimeError):
+    pass
+
+
+class CdnError(RuntimeError):
+    pass
+
+
+_vp = C.c_void_p
+
+
+def _declare(dll):
+    dll.cdn_version.restype = C.c_int
+    dll.cdn_init.argtypes = [C.c_int, C.POINTER(_vp)]
+    dll.cdn_free.argtypes = [_vp]
+    dll.cdn_last_error.argtypes = [_vp]
+    dll.cdn_last_error.restype = C.c_char_p
+    dll.cdn_sm_count.argtypes = [_vp]
+    dll.cdn_model_nparams.argtypes = [C.c_int]
+    dll.cdn_dev_eval.argtypes = [_vp, C.c_int, C.c_uint, C.c_long, C.c_int,
+                                 _vp, C.c_long, _vp, _vp, _vp, _vp, _vp]
+    dll.cdn_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
+
+
+def load_dll():
+    """Load the shared library (no GPU needed); raises if it is not built."""
+    if not os.path.exists(LIBPATH):
+        raise CudaUnavailable(
+            'libcardoon_b200.so is not built: run '
+            '`python -c "import __graft_entry__ as g; g.build()"`')
+    dll = C.CDLL(LIBPATH)
+    _declare(dll)
+    return dll
+
+
+class Lib(object):
+    """One library context bound to one GPU."""
+
+    def __init__(self, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise CudaUnavailable(
+                'cardoon_b200 needs a CUDA GPU (B200, sm_100a); there is no '
+                'CPU implementation of the hot path in this package')
+        self.torch = torch
+        self.dll = load_dll()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device('cuda', device)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)      # make sure a context exists
+        self.ctx = _vp()
+        rc = self.dll.cdn_init(int(device), C.byref(self.ctx))
+        if rc != 0:
+            raise CdnError('cdn_init failed ({0})'.format(rc))
+
+    # ---- helpers ---------------------------------------------------------
+    def check(self, rc):
+        if rc != 0:
+            msg = self.dll.cdn_last_error(self.ctx)
+            raise CdnError('libcardoon_b200 error {0}: {1}'.format(
+                rc, msg.decode() if msg else ''))
+
+    def stream(self):
+        return _vp(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def dev(self, array, dtype=None):
+        """numpy array -> contiguous device tensor."""
+        t = self.torch.as_tensor(np.ascontiguousarray(array))
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.device)
+
+    def empty(self, shape, dtype=None):
+        return self.torch.empty(shape, dtype=dtype or self.torch.float64,
+                                device=self.device)
+
+    def zeros(self, shape, dtype=None):
+        return self.torch.zeros(shape, dtype=dtype or self.torch.float64,
+                                device=self.device)
+
+    @staticmethod
+    def ptr(t):
+        return _vp(t.data_ptr()) if t is not None else None
+
+    # ---- device evaluation -------------------------------------------------
+    def dev_eval(self, model, flags, params, xin, nout, want_jac=True,
+                 pidx=None, out=None, jac=None):
+        """Device tensors in, device tensors out.
+
+        params: [npar, ncols]; xin: [nxin, n]; returns out[nout, n] and
+        jac[nout*nxin, n] (None if not requested).
+        """
+        nxin, n = xin.shape
+        if pidx is None and params.shape[1] != n:
+            if params.shape[1] != 1:
+                raise ValueError('params must have 1 or n columns')
+            # one parameter set shared by every instance
+            pidx = self.zeros((n,), self.torch.int32)
+        if out is None:
+            out = self.empty((nout, n))
+        if want_jac and jac is None:
+            jac = self.empty((nout * nxin, n))
+        rc = self.dll.cdn_dev_eval(
+            self.ctx, int(model), int(flags), int(n), int(nxin),
+            self.ptr(params), int(params.stride(0)), self.ptr(pidx),
+            self.ptr(xin), self.ptr(out), self.ptr(jac) if want_jac else None,
+            self.stream())
+        self.check(rc)
+        return out, (jac if want_jac else None)
+
+    def dev_eval_host(self, model, flags, params, xin, nout, want_jac=True):
+        """numpy in / numpy out convenience (plugin batch-of-one path)."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        xin = np.ascontiguousarray(xin, dtype=np.float64)
+        out, jac = self.dev_eval(model, flags, self.dev(params),
+                                 self.dev(xin), nout, want_jac)
+        self.torch.cuda.synchronize(self.device)
+        return (out.cpu().numpy(),
+                jac.cpu().numpy() if jac is not None else None)
+
+    def fp64_peak(self):
+        v = C.c_double()
+        self.check(self.dll.cdn_fp64_peak(self.ctx, C.byref(v)))
+        return v.value
+
+
+_LIB = {}
+
+
+def get_lib(device=None):
+    import torch
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() \
+            else 0
+    if device not in _LIB:
+        _LIB[device] = Lib(device)
+    return _LIB[device]

@@ -1,0 +1,31 @@
+// Shared declarations of libcardoon_b200.so (context, error reporting).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <cstdio>
+
+struct cdn_ctx {
+    int device;
+    int sm_count;
+    std::string err;
+};
+
+#define CDN_OK 0
+#define CDN_ERR_ARG (-1)
+#define CDN_ERR_CUDA (-2)
+#define CDN_ERR_STATE (-3)
+#define CDN_ERR_SINGULAR (-4)
+
+#define CDN_CUDA(ctx, call)                                                    \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) {                                               \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);   \
+            return CDN_ERR_CUDA;                                               \
+        }                                                                      \
+    } while (0)
+
+static inline int cdn_fail(cdn_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}

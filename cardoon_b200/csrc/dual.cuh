@@ -1,0 +1,210 @@
+// Forward-mode dual numbers for the device-evaluation kernels.
+//
+// Replaces the reference's pycppad/CppAD tapes (devices/cppaddev.py:113-157):
+// a Dual<P> carries a value and P tangent lanes (P = number of control
+// ports), every operation propagates exact first derivatives, so one pass
+// through a model's equations yields out[] and the full Jacobian.  P = 0 is
+// the plain-double instantiation used where only values are needed
+// (charge update, reference cppaddev.eval :160).
+//
+// Semantics that the models rely on (reference cppaddev.py:56-96 and CppAD):
+//   select(b, c, d)  = (b > 0) ? c : d   strict, applied to value AND tangents
+//                      (the un-selected branch may be NaN/inf and must not
+//                      leak; never multiply by 0/1 masks)
+//   safe_exp(x)      = exp(x) for x < 50, exp(50)*(x-49) above
+//   d|x|/dx          = sign(x) with sign(0) = 0
+//   comparisons with NaN are false (=> "d" branch)
+#pragma once
+#include <math.h>
+
+#define CDN_HD __device__ __forceinline__
+
+template <int P>
+struct Dual {
+    double v;
+    double d[P > 0 ? P : 1];
+    CDN_HD Dual() {}
+    CDN_HD Dual(double x) : v(x) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) d[i] = 0.0;
+    }
+};
+
+// ---- construction -----------------------------------------------------------
+template <int P>
+CDN_HD Dual<P> make_var(double x, int lane) {
+    Dual<P> r; r.v = x;
+#pragma unroll
+    for (int i = 0; i < P; ++i) r.d[i] = (i == lane) ? 1.0 : 0.0;
+    return r;
+}
+
+// ---- addition / subtraction ---------------------------------------------------
+template <int P>
+CDN_HD Dual<P> operator-(const Dual<P>& a) {
+    Dual<P> r; r.v = -a.v;
+#pragma unroll
+    for (int i = 0; i < P; ++i) r.d[i] = -a.d[i];
+    return r;
+}
+template <int P>
+CDN_HD Dual<P> operator+(const Dual<P>& a, const Dual<P>& b) {
+    Dual<P> r; r.v = a.v + b.v;
+#pragma unroll
+    for (int i = 0; i < P; ++i) r.d[i] = a.d[i] + b.d[i];
+    return r;
+}
+template <int P>
+CDN_HD Dual<P> operator+(const Dual<P>& a, double b) {
+    Dual<P> r = a; r.v = a.v + b; return r;
+}
+template <int P>
+CDN_HD Dual<P> operator+(double a, const Dual<P>& b) { return b + a; }
+template <int P>
+CDN_HD Dual<P> operator-(const Dual<P>& a, const Dual<P>& b) {
+    Dual<P> r; r.v = a.v - b.v;
+#pragma unroll
+    for (int i = 0; i < P; ++i) r.d[i] = a.d[i] - b.d[i];
+    return r;
+}
+template <int P>
+CDN_HD Dual<P> operator-(const Dual<P>& a, double b) {
+    Dual<P> r = a; r.v = a.v - b; return r;
+}
+template <int P>
+CDN_HD Dual<P> operator-(double a, const Dual<P>& b) {
+    Dual<P> r; r.v = a - b.v;
+#pragma unroll
+    for (int i = 0; i < P; ++i) r.d[i] = -b.d[i];
+    return r;
+}
+
+// ---- multiplication ---------------------------------------------------------
+template <int P>
+CDN_HD Dual<P> operator*(const Dual<P>& a, const Dual<P>& b) {
+    Dual<P> r; r.v = a.v * b.v;
+#pragma unroll
+    for (int i = 0; i < P; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i];
+    return r;
+}
+template <int P>
+CDN_HD Dual<P> operator*(const Dual<P>& a, double b) {
+    Dual<P> r; r.v = a.v * b;
+#pragma unroll
+    for (int i = 0; i < P; ++i) r.d[i] = a.d[i] * b;
+    return r;
+}
+template <int P>
+CDN_HD Dual<P> operator*(double a, const Dual<P>& b) { return b * a; }
+
+// ---- division ---------------------------------------------------------------
+template <int P>
+CDN_HD Dual<P> operator/(const Dual<P>& a, const Dual<P>& b) {
+    Dual<P> r; r.v = a.v / b.v;
+    const double inv = 1.0 / b.v;
+#pragma unroll
+    for (int i = 0; i < P; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
+    return r;
+}
+template <int P>
+CDN_HD Dual<P> operator/(const Dual<P>& a, double b) {
+    Dual<P> r; r.v = a.v / b;
+    const double inv = 1.0 / b;
+#pragma unroll
+    for (int i = 0; i < P; ++i) r.d[i] = a.d[i] * inv;
+    return r;
+}
+template <int P>
+CDN_HD Dual<P> operator/(double a, const Dual<P>& b) {
+    Dual<P> r; r.v = a / b.v;
+    const double k = -r.v / b.v;
+#pragma unroll
+    for (int i = 0; i < P; ++i) r.d[i] = k * b.d[i];
+    return r;
+}
+
+// ---- elementary functions -----------------------------------------------------
+template <int P>
+CDN_HD Dual<P> d_scale(const Dual<P>& x, double z, double dz) {
+    Dual<P> r; r.v = z;
+#pragma unroll
+    for (int i = 0; i < P; ++i) r.d[i] = dz * x.d[i];
+    return r;
+}
+template <int P> CDN_HD Dual<P> exp(const Dual<P>& x) {
+    const double z = ::exp(x.v); return d_scale(x, z, z);
+}
+template <int P> CDN_HD Dual<P> log(const Dual<P>& x) {
+    return d_scale(x, ::log(x.v), 1.0 / x.v);
+}
+template <int P> CDN_HD Dual<P> sqrt(const Dual<P>& x) {
+    const double z = ::sqrt(x.v); return d_scale(x, z, 0.5 / z);
+}
+template <int P> CDN_HD Dual<P> tan(const Dual<P>& x) {
+    const double z = ::tan(x.v); return d_scale(x, z, 1.0 + z * z);
+}
+template <int P> CDN_HD Dual<P> tanh(const Dual<P>& x) {
+    const double z = ::tanh(x.v); return d_scale(x, z, 1.0 - z * z);
+}
+template <int P> CDN_HD Dual<P> sin(const Dual<P>& x) {
+    return d_scale(x, ::sin(x.v), ::cos(x.v));
+}
+template <int P> CDN_HD Dual<P> cos(const Dual<P>& x) {
+    return d_scale(x, ::cos(x.v), -::sin(x.v));
+}
+template <int P> CDN_HD Dual<P> cosh(const Dual<P>& x) {
+    return d_scale(x, ::cosh(x.v), ::sinh(x.v));
+}
+template <int P> CDN_HD Dual<P> dabs(const Dual<P>& x) {
+    const double s = (x.v > 0.0) ? 1.0 : ((x.v < 0.0) ? -1.0 : 0.0);
+    return d_scale(x, ::fabs(x.v), s);
+}
+// x**p, constant exponent
+template <int P> CDN_HD Dual<P> dpow(const Dual<P>& x, double p) {
+    const double z = ::pow(x.v, p); return d_scale(x, z, p * z / x.v);
+}
+template <int P> CDN_HD Dual<P> sq(const Dual<P>& x) { return x * x; }
+CDN_HD double sq(double x) { return x * x; }
+
+// ---- selection ------------------------------------------------------------------
+template <int P>
+CDN_HD Dual<P> select(double b, const Dual<P>& c, const Dual<P>& d) {
+    Dual<P> r;
+    const bool m = b > 0.0;
+    r.v = m ? c.v : d.v;
+#pragma unroll
+    for (int i = 0; i < P; ++i) r.d[i] = m ? c.d[i] : d.d[i];
+    return r;
+}
+template <int P>
+CDN_HD Dual<P> select(const Dual<P>& b, const Dual<P>& c, const Dual<P>& d) {
+    return select(b.v, c, d);
+}
+template <int P>
+CDN_HD Dual<P> select(const Dual<P>& b, const Dual<P>& c, double d) {
+    return select(b.v, c, Dual<P>(d));
+}
+template <int P>
+CDN_HD Dual<P> select(const Dual<P>& b, double c, const Dual<P>& d) {
+    return select(b.v, Dual<P>(c), d);
+}
+template <int P>
+CDN_HD Dual<P> select(double b, const Dual<P>& c, double d) {
+    return select(b, c, Dual<P>(d));
+}
+template <int P>
+CDN_HD Dual<P> select(double b, double c, const Dual<P>& d) {
+    return select(b, Dual<P>(c), d);
+}
+template <int P>
+CDN_HD double selectd(const Dual<P>& b, double c, double d) {
+    return (b.v > 0.0) ? c : d;
+}
+
+template <int P> CDN_HD Dual<P> safe_exp(const Dual<P>& x) {
+    // reference cppaddev.safe_exp: condexp_lt(x, 50, exp(x), exp(50)(x-49))
+    const double e50 = 5.184705528587072e21;   // exp(50.)
+    const Dual<P> c = exp(x);
+    const Dual<P> d = e50 * (x - 50.0 + 1.0);
+    return select(50.0 - x.v, c, d);
+}

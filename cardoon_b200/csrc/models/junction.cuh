@@ -1,0 +1,48 @@
+// P-N junction current / charge laws.
+// Reference: devices/diode.py Junction.get_id :74-80, get_qd :83-98;
+// devices/svdiode.py SVJunction.get_idvd :80-97, get_qd :99-111.
+// The record layout is param_layout.JUNCTION (J_* indexes).
+#pragma once
+#include "../dual.cuh"
+#include "../param_index.h"
+
+// Strided view of one instance's parameter column: p[k] = base[k*ld].
+struct PV {
+    const double* base;
+    long ld;
+    CDN_HD double operator[](int k) const { return __ldg(base + (long)k * ld); }
+    CDN_HD PV sub(int off) const { PV r; r.base = base + (long)off * ld; r.ld = ld; return r; }
+};
+
+template <int P>
+CDN_HD Dual<P> junction_id(const PV& j, const Dual<P>& vd) {
+    return j[J_t_is] * (safe_exp(vd / j[J_kexp]) - 1.0);
+}
+
+// Depletion charge; callers guard on the cj0 != 0 flag (the reference returns
+// 0*vd otherwise).
+template <int P>
+CDN_HD Dual<P> junction_qd(const PV& j, const Dual<P>& vd) {
+    const double fc = j[J_fc], t_vj = j[J_t_vj], k4 = j[J_k4], k5 = j[J_k5];
+    const double k6 = j[J_k6], k7 = j[J_k7], m = j[J_m];
+    const Dual<P> b = fc * t_vj - vd;
+    const Dual<P> c = k5 * (1.0 - dpow(1.0 - vd / t_vj, k4));
+    const Dual<P> d = k6 * ((1.0 - fc * (1.0 + m)) * vd
+                            + .5 * m * vd * vd / t_vj - k7)
+                      + k5 * (1.0 - ::pow(1.0 - fc, k4));
+    return select(b, c, d);
+}
+
+// State-variable junction: current and voltage as functions of x.
+template <int P>
+CDN_HD void svjunction_idvd(const PV& j, const Dual<P>& x, Dual<P>& iD, Dual<P>& vD) {
+    const double t_is = j[J_t_is], alpha = j[J_alpha], svth = j[J_svth];
+    const double kexp = j[J_kexp];
+    const Dual<P> b = svth - x;
+    const Dual<P> c = t_is * (exp(alpha * x) - 1.0);
+    const Dual<P> lin = 1.0 + alpha * (x - svth);
+    const Dual<P> d = t_is * kexp * lin - t_is;
+    iD = select(b, c, d);
+    const Dual<P> dv = svth + log(lin) / alpha;
+    vD = select(b, x, dv);
+}

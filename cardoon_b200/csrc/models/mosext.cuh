@@ -1,0 +1,48 @@
+// Extrinsic MOSFET additions: drain/source area + sidewall junctions and the
+// parallel multiplier.  Reference: devices/mosExt.py eval_cqs :281-324
+// (junction voltage is -v*tf; contributions are *subtracted* from idb/isb and
+// qd/qs; everything times m).  `base` is the index of the 'm' entry of the
+// model's parameter list; flag bits are the first 8 of the model's flags.
+#pragma once
+#include "junction.cuh"
+
+#define F_MOSEXT_AD 1u
+#define F_MOSEXT_CJ_D 2u
+#define F_MOSEXT_PD 4u
+#define F_MOSEXT_CJSW_D 8u
+#define F_MOSEXT_ASRC 16u
+#define F_MOSEXT_CJ_S 32u
+#define F_MOSEXT_PS 64u
+#define F_MOSEXT_CJSW_S 128u
+
+template <int P>
+CDN_HD void mosext_apply(const PV& p, int base, unsigned flags, double tf,
+                         const Dual<P>* v, Dual<P>* iv, Dual<P>* qv) {
+    const PV dj = p.sub(base + 1), djsw = p.sub(base + 1 + CDN_NJ);
+    const PV sj = p.sub(base + 1 + 2 * CDN_NJ), sjsw = p.sub(base + 1 + 3 * CDN_NJ);
+    if (flags & (F_MOSEXT_AD | F_MOSEXT_PD)) {
+        const Dual<P> v1 = -v[0] * tf;
+        if (flags & F_MOSEXT_AD) {
+            iv[1] = iv[1] - junction_id(dj, v1) * tf;
+            if (flags & F_MOSEXT_CJ_D) qv[0] = qv[0] - junction_qd(dj, v1) * tf;
+        }
+        if (flags & F_MOSEXT_PD) {
+            iv[1] = iv[1] - junction_id(djsw, v1) * tf;
+            if (flags & F_MOSEXT_CJSW_D) qv[0] = qv[0] - junction_qd(djsw, v1) * tf;
+        }
+    }
+    if (flags & (F_MOSEXT_ASRC | F_MOSEXT_PS)) {
+        const Dual<P> v1 = -v[2] * tf;
+        if (flags & F_MOSEXT_ASRC) {
+            iv[2] = iv[2] - junction_id(sj, v1) * tf;
+            if (flags & F_MOSEXT_CJ_S) qv[2] = qv[2] - junction_qd(sj, v1) * tf;
+        }
+        if (flags & F_MOSEXT_PS) {
+            iv[2] = iv[2] - junction_id(sjsw, v1) * tf;
+            if (flags & F_MOSEXT_CJSW_S) qv[2] = qv[2] - junction_qd(sjsw, v1) * tf;
+        }
+    }
+    const double m = p[base];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { iv[k] = iv[k] * m; qv[k] = qv[k] * m; }
+}

@@ -15,10 +15,10 @@ CUDA kernel interprets in dual-number arithmetic
 import ast
 
 OP_CONST, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_NEG, OP_ABS, \
-    OP_EXP, OP_LOG, OP_SQRT, OP_TANH, OP_SIN, OP_COS, OP_TAN = range(16)
+    OP_EXP, OP_LOG, OP_SQRT, OP_TANH, OP_SIN, OP_COS, OP_TAN, OP_COSH = range(17)
 
 _FUNCS = dict(abs=OP_ABS, exp=OP_EXP, log=OP_LOG, sqrt=OP_SQRT,
-              tanh=OP_TANH, sin=OP_SIN, cos=OP_COS, tan=OP_TAN)
+              tanh=OP_TANH, sin=OP_SIN, cos=OP_COS, tan=OP_TAN, cosh=OP_COSH)
 _BIN = {ast.Add: OP_ADD, ast.Sub: OP_SUB, ast.Mult: OP_MUL, ast.Div: OP_DIV,
         ast.Pow: OP_POW}
 

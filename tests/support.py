@@ -1,0 +1,84 @@
+"""Helpers shared by the tests, smoke() and bench.py's checker legs."""
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NETS = os.path.join(HERE, 'netlists')
+
+
+def net(name):
+    return os.path.join(NETS, name)
+
+
+def load_circuit(path, init=True):
+    """Parse a deck into a fresh main circuit; returns (ckt, analyses)."""
+    from cardoon_b200 import simulator as sim
+    from cardoon_b200 import circuit as cir
+    sim.reset_all()
+    ckt = cir.get_mainckt()
+    queue = sim.parse_net(path, ckt)
+    if init:
+        ckt.flatten()
+        ckt.init()
+    return ckt, queue
+
+
+def nonlinear_elements(ckt):
+    return [e for e in ckt.elemDict.values() if e.isNonlinear]
+
+
+def make_element(devType, nodes, model=None, **params):
+    """One initialised element in a scratch circuit."""
+    from cardoon_b200 import simulator as sim
+    from cardoon_b200 import circuit as cir
+    name = 'scratch{0}'.format(len(cir.Circuit.cktDict))
+    ckt = cir.Circuit(name)
+    elem = sim.new_elem(devType, 'e1', **params)
+    ckt.add_elem(elem, model)
+    ckt.connect(elem, [str(n) for n in nodes])
+    elem.init()
+    return elem
+
+
+def nxin_of(elem):
+    return len(elem.controlPorts) + elem.nDelays
+
+
+def cuda_eval(lib, elem, xin, want_jac=True, full=True):
+    """out[nout, n], jac[nout, nxin, n] of one element at xin[nxin, n]."""
+    spec = elem.cuda_spec()
+    nout = spec['ncs'] + spec['nqs']
+    xin = np.ascontiguousarray(xin, dtype=float)
+    out, jac = lib.dev_eval_host(spec['model'], spec['flags'],
+                                 spec['params'][:, None].repeat(
+                                     xin.shape[1] if full else 1, axis=1),
+                                 xin, nout, want_jac)
+    if jac is not None:
+        jac = jac.reshape(nout, xin.shape[0], xin.shape[1])
+    return out, jac
+
+
+def rel_err(a, b, floor):
+    """max |a-b| / (|b| + floor)"""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    with np.errstate(invalid='ignore'):
+        e = np.abs(a - b) / (np.abs(b) + floor)
+    e = np.where(np.isnan(a) & np.isnan(b), 0., e)
+    return float(np.max(e)) if e.size else 0.
+
+
+def smoke_check():
+    """BSIM3 + diode device evaluation on cuda:0 against the oracle."""
+    from cardoon_b200._lib import get_lib
+    from oracle.models import device_eval
+    lib = get_lib(0)
+    ckt, _ = load_circuit(net('ring_bsim3.net'))
+    rng = np.random.default_rng(7)
+    for elem in nonlinear_elements(ckt)[:2]:
+        xin = rng.uniform(-0.5, 3.0, size=(3, 64))
+        out, jac = cuda_eval(lib, elem, xin)
+        ro, rj = device_eval(elem, xin, True)
+        assert rel_err(out, ro, 1e-18) < 1e-9, 'BSIM3 value mismatch'
+        assert rel_err(jac, rj, 1e-12) < 1e-7, 'BSIM3 Jacobian mismatch'
