@@ -1,0 +1,70 @@
+// Host/device description of one circuit "plan": the precomputed index
+// structures that let the Newton kernels evaluate devices, assemble the MNA
+// residual and Jacobian by *gather* (no atomics), factor it with a static
+// pivot order and solve, all on the device.
+//
+// Built once per circuit and analysis kind by symbolic.cpp from the index
+// lists of the reference's make_nodal_circuit / process_nodal_element /
+// create_additional_indexes (analyses/nodal.py:113-282, nodalSP.py:111-164).
+#pragma once
+
+#define CDN_MAX_GROUPS 24
+
+// one homogeneous group of nonlinear devices (same model, flags, port counts)
+struct cdn_group_dev {
+    int model;
+    unsigned flags;
+    int n, nxin, ncs, nqs, ndelay;
+    int pad_;
+    const double* params;     // [npar][ldp] device, owned by caller
+    long ldp;
+    const int* pidx;          // [n] column of each instance in params, or NULL
+    const int* vpos;          // [nxin][n] row of + control terminal (-1 gnd)
+    const int* vneg;          // [nxin][n]
+    long out_off;             // offset of this group's out[nout][n] in dev_out
+    long jac_off;             // offset of jac[nout*nxin][n] in dev_jac
+};
+
+struct cdn_plan_dev {
+    int n;                    // unknowns
+    int nlu;                  // stored entries of L+U (static pattern)
+    int nlev_f, nlev_l, nlev_u;
+    int ngroups;
+    // ---- factorisation: entries ("slots") numbered in level order --------
+    const int* f_lvl_ptr;     // [nlev_f+1]
+    const int* e_term_ptr;    // [nlu+1]   Crout terms of entry e
+    const int* e_term_l;      // [nterms]  slot of L(i,k)
+    const int* e_term_u;      // [nterms]  slot of U(k,j)
+    const int* e_piv;         // [nlu]  L entry: slot of U(j,j); U: -1; diag: -2
+    const double* e_g;        // [nlu] linear conductance part
+    const double* e_c;        // [nlu] linear capacitance part (times a0)
+    const double* e_gones;    // [nlu] gmin-stepping pattern (times gmin)
+    const int* e_con_ptr;     // [nlu+1] device-Jacobian contributions
+    const int* e_con_src;     // [ncon]  index into dev_jac
+    const signed char* e_con_kind;  // +-1 current row, +-2 charge row (x a0)
+    // ---- triangular solves (permuted index space) --------------------------
+    const int* l_lvl_ptr;     // [nlev_l+1]
+    const int* l_rows;        // [n] rows ordered by level
+    const int* l_ptr;         // [n+1]
+    const int* l_col;         // [nnzL]
+    const int* l_slot;        // [nnzL]
+    const int* u_lvl_ptr;     // [nlev_u+1]
+    const int* u_rows;        // [n]
+    const int* u_ptr;         // [n+1]
+    const int* u_col;         // [nnzU] (strictly upper)
+    const int* u_slot;        // [nnzU]
+    const int* u_diag;        // [n] slot of U(i,i)
+    const int* rowmap;        // [n] permuted row i  <- original row rowmap[i]
+    const int* colmap;        // [n] permuted col j  -> original unknown colmap[j]
+    // ---- residual (original index space) ------------------------------------
+    const int* r_lin_ptr;     // [n+1] CSR of the linear matrices
+    const int* r_lin_col;
+    const double* r_lin_g;
+    const double* r_lin_c;
+    const double* r_lin_gones;
+    const int* r_con_ptr;     // [n+1] device-output contributions per row
+    const int* r_con_src;     // index into dev_out
+    const signed char* r_con_kind;   // +-1 current, +-2 charge
+    long dev_out_size, dev_jac_size;
+    cdn_group_dev groups[CDN_MAX_GROUPS];
+};

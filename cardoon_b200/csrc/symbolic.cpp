@@ -1,0 +1,616 @@
+// Host-side symbolic analysis for the sparse Newton engine: done once per
+// circuit (the reference re-runs COLAMD + symbolic + numeric SuperLU on every
+// Newton iteration, analyses/nodalSP.py:281-303).
+//
+//   1. pattern of J from the linear quads and every device's +/- stamp
+//      positions (nodalSP.py:45-85, 111-164)
+//   2. static pivoting: the caller supplies a row<->column matching that puts
+//      large entries on the diagonal (gyrator-built sources and inductors
+//      have structurally zero diagonals, devices/vdc.py:112-123)
+//   3. nested-dissection ordering of the symmetrised pattern (level-structure
+//      bisection; hub nodes last).  Chain-like circuits (soliton line,
+//      inverter chains) have ~n elimination levels under AMD/COLAMD but
+//      O(log n) under ND, which is what makes level scheduling pay
+//   4. symbolic factorisation (elimination tree + row patterns)
+//   5. entry-wise Crout schedule: every stored entry of L+U gets the list of
+//      (L(i,k), U(k,j)) products it subtracts and a dependency level; entries
+//      are renumbered level by level so one barrier separates levels and all
+//      arithmetic is a deterministic gather (no atomics)
+//   6. gather lists for the device Jacobian/outputs -> matrix entries / rows
+//   7. row level schedules for the two triangular solves
+#include "common.cuh"
+#include "plan.h"
+#include "plan_host.h"
+#include <vector>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <cstdint>
+
+namespace {
+
+typedef std::vector<int> ivec;
+
+// ---- nested dissection ----------------------------------------------------------
+struct Graph {
+    int n;
+    ivec ptr, adj;
+};
+
+struct NDOrder {
+    const Graph& g;
+    ivec setid;       // current subset label of each node
+    ivec level;       // BFS scratch
+    ivec order;       // output: elimination order (new -> old)
+    int next_label;
+    int leaf;
+
+    NDOrder(const Graph& g_, int leaf_) : g(g_), setid(g_.n, 0), level(g_.n, -1),
+                                          next_label(1), leaf(leaf_) {}
+
+    // BFS inside subset `lab` from `start`; returns visit order, fills level[]
+    void bfs(int start, int lab, ivec& visit) {
+        visit.clear();
+        visit.push_back(start);
+        level[start] = 0;
+        for (size_t h = 0; h < visit.size(); ++h) {
+            const int u = visit[h];
+            for (int e = g.ptr[u]; e < g.ptr[u + 1]; ++e) {
+                const int w = g.adj[e];
+                if (setid[w] == lab && level[w] < 0) {
+                    level[w] = level[u] + 1;
+                    visit.push_back(w);
+                }
+            }
+        }
+    }
+
+    void emit_by_degree(ivec& nodes) {
+        std::stable_sort(nodes.begin(), nodes.end(), [&](int a, int b) {
+            return (g.ptr[a + 1] - g.ptr[a]) < (g.ptr[b + 1] - g.ptr[b]);
+        });
+        for (int v : nodes) order.push_back(v);
+    }
+
+    void run(ivec nodes) {
+        // explicit work stack; separators are emitted after both halves, which
+        // is arranged by pushing a "emit" item below them
+        struct Item { ivec nodes; bool emit_only; };
+        std::vector<Item> stack;
+        stack.push_back(Item{std::move(nodes), false});
+        ivec visit, visit2;
+        while (!stack.empty()) {
+            Item it = std::move(stack.back());
+            stack.pop_back();
+            if (it.emit_only) { for (int v : it.nodes) order.push_back(v); continue; }
+            ivec& S = it.nodes;
+            if ((int)S.size() <= leaf) { emit_by_degree(S); continue; }
+            const int lab = next_label++;
+            for (int v : S) { setid[v] = lab; level[v] = -1; }
+            // start from a minimum-degree node
+            int start = S[0];
+            for (int v : S)
+                if (g.ptr[v + 1] - g.ptr[v] < g.ptr[start + 1] - g.ptr[start]) start = v;
+            bfs(start, lab, visit);
+            if (visit.size() < S.size()) {
+                // disconnected: peel this component off and handle both parts
+                ivec comp(visit), rest;
+                for (int v : comp) setid[v] = -lab;
+                for (int v : S) if (setid[v] == lab) rest.push_back(v);
+                stack.push_back(Item{std::move(rest), false});
+                stack.push_back(Item{std::move(comp), false});
+                continue;
+            }
+            // pseudo-peripheral node: restart from the farthest node
+            const int far = visit.back();
+            for (int v : S) level[v] = -1;
+            bfs(far, lab, visit2);
+            const int nlev = level[visit2.back()] + 1;
+            if (nlev < 3) { emit_by_degree(S); continue; }
+            ivec cnt(nlev, 0);
+            for (int v : S) cnt[level[v]]++;
+            // separator level: the interior level where the halves balance
+            const long half = (long)S.size() / 2;
+            long acc = 0;
+            int m = 1;
+            for (int l = 0; l < nlev; ++l) {
+                if (acc + cnt[l] > half) { m = l; break; }
+                acc += cnt[l];
+            }
+            if (m < 1) m = 1;
+            if (m > nlev - 2) m = nlev - 2;
+            ivec A, B, Sep;
+            for (int v : S) {
+                if (level[v] < m) A.push_back(v);
+                else if (level[v] > m) B.push_back(v);
+                else Sep.push_back(v);
+            }
+            stack.push_back(Item{std::move(Sep), true});
+            stack.push_back(Item{std::move(B), false});
+            stack.push_back(Item{std::move(A), false});
+        }
+    }
+};
+
+template <class T>
+static long put(std::vector<char>& buf, const std::vector<T>& v) {
+    long off = (long)((buf.size() + 255) / 256 * 256);
+    buf.resize(off + std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (!v.empty()) memcpy(buf.data() + off, v.data(), v.size() * sizeof(T));
+    return off;
+}
+
+}  // namespace
+
+struct cdn_plan {
+    cdn_ctx* ctx;
+    cdn_plan_dev dev;             // device pointers valid after bind
+    std::vector<char> staging;    // packed index arrays
+    struct Off {
+        long f_lvl_ptr, e_term_ptr, e_term_l, e_term_u, e_piv, e_g, e_c, e_gones, e_con_ptr,
+            e_con_src, e_con_kind, l_lvl_ptr, l_rows, l_ptr, l_col, l_slot, u_lvl_ptr, u_rows,
+            u_ptr, u_col, u_slot, u_diag, rowmap, colmap, r_lin_ptr, r_lin_col, r_lin_g,
+            r_lin_c, r_lin_gones, r_con_ptr, r_con_src, r_con_kind;
+        long gv[CDN_MAX_GROUPS][2];
+    } off;
+    long nterms, ncon, nnzA;
+    bool bound;
+    int max_terms, max_con;
+};
+
+static int find_slot(const ivec& rptr, const ivec& rcol, const ivec& rslot, int i, int j) {
+    const int* b = rcol.data() + rptr[i];
+    const int* e = rcol.data() + rptr[i + 1];
+    const int* p = std::lower_bound(b, e, j);
+    if (p == e || *p != j) return -1;
+    return rslot[p - rcol.data()];
+}
+
+extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan** out) {
+    if (!ctx || !c || !out) return CDN_ERR_ARG;
+    const int n = c->n;
+    if (n <= 0) return cdn_fail(ctx, CDN_ERR_ARG, "plan: empty circuit");
+    if (c->ngroups > CDN_MAX_GROUPS) return cdn_fail(ctx, CDN_ERR_ARG, "plan: too many device groups");
+    cdn_plan* P = new cdn_plan();
+    P->ctx = ctx;
+    P->bound = false;
+    memset(&P->dev, 0, sizeof(P->dev));
+
+    // ---- permutation from the matching: row r of A becomes row mrow[r] ----------
+    ivec mrow(n);
+    {
+        std::vector<char> seen(n, 0);
+        for (int r = 0; r < n; ++r) {
+            const int m = c->rowmatch ? c->rowmatch[r] : r;
+            if (m < 0 || m >= n || seen[m]) { delete P; return cdn_fail(ctx, CDN_ERR_ARG, "plan: rowmatch is not a permutation"); }
+            seen[m] = 1;
+            mrow[r] = m;
+        }
+    }
+
+    // ---- 1. pattern (in "B" coordinates: (mrow[r], c)) ------------------------------
+    std::vector<uint64_t> keys;
+    auto addkey = [&](int r, int col) {
+        if (r >= 0 && col >= 0) keys.push_back(((uint64_t)(uint32_t)mrow[r] << 32) | (uint32_t)col);
+    };
+    for (long k = 0; k < c->nG; ++k) addkey(c->g_row[k], c->g_col[k]);
+    for (long k = 0; k < c->nC; ++k) addkey(c->c_row[k], c->c_col[k]);
+    for (long k = 0; k < c->nE; ++k) addkey(c->e_row[k], c->e_col[k]);
+    for (int g = 0; g < c->ngroups; ++g) {
+        const cdn_group_host& G = c->groups[g];
+        for (int i = 0; i < G.n; ++i)
+            for (int o = 0; o < G.ncs + G.nqs; ++o) {
+                const int rp = (o < G.ncs) ? G.cpos[(long)o * G.n + i] : G.qpos[(long)(o - G.ncs) * G.n + i];
+                const int rn = (o < G.ncs) ? G.cneg[(long)o * G.n + i] : G.qneg[(long)(o - G.ncs) * G.n + i];
+                for (int k = 0; k < G.nxin; ++k) {
+                    const int cp = G.vpos[(long)k * G.n + i], cn = G.vneg[(long)k * G.n + i];
+                    addkey(rp, cp); addkey(rn, cn); addkey(rp, cn); addkey(rn, cp);
+                }
+            }
+    }
+    for (int i = 0; i < n; ++i) keys.push_back(((uint64_t)(uint32_t)i << 32) | (uint32_t)i);
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    P->nnzA = (long)keys.size();
+
+    // ---- 3. ordering on the symmetrised graph -----------------------------------------
+    Graph gr;
+    gr.n = n;
+    {
+        std::vector<uint64_t> ek;
+        ek.reserve(keys.size() * 2);
+        for (uint64_t k : keys) {
+            const uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)k;
+            if (a != b) { ek.push_back(((uint64_t)a << 32) | b); ek.push_back(((uint64_t)b << 32) | a); }
+        }
+        std::sort(ek.begin(), ek.end());
+        ek.erase(std::unique(ek.begin(), ek.end()), ek.end());
+        gr.ptr.assign(n + 1, 0);
+        gr.adj.resize(ek.size());
+        for (uint64_t k : ek) gr.ptr[(k >> 32) + 1]++;
+        for (int i = 0; i < n; ++i) gr.ptr[i + 1] += gr.ptr[i];
+        for (size_t q = 0; q < ek.size(); ++q) gr.adj[q] = (int)(uint32_t)ek[q];
+    }
+    ivec perm;   // new -> old (B index)
+    {
+        const int hub_deg = std::max(64, (int)(10.0 * std::sqrt((double)n)));
+        ivec normal, hubs;
+        for (int v = 0; v < n; ++v)
+            ((gr.ptr[v + 1] - gr.ptr[v]) > hub_deg ? hubs : normal).push_back(v);
+        // hubs are removed from the graph seen by ND by giving them a label no
+        // subset ever uses
+        NDOrder nd(gr, 2);
+        for (int v : hubs) nd.setid[v] = -1000000;
+        if (c->ordering == 1) {
+            for (int v : normal) nd.order.push_back(v);       // natural (debug)
+        } else {
+            nd.run(normal);
+        }
+        std::stable_sort(hubs.begin(), hubs.end(), [&](int a, int b) {
+            return (gr.ptr[a + 1] - gr.ptr[a]) < (gr.ptr[b + 1] - gr.ptr[b]);
+        });
+        perm = nd.order;
+        for (int v : hubs) perm.push_back(v);
+        if ((int)perm.size() != n) { delete P; return cdn_fail(ctx, CDN_ERR_STATE, "plan: ordering lost nodes"); }
+    }
+    ivec ip(n);
+    for (int i = 0; i < n; ++i) ip[perm[i]] = i;
+
+    // ---- symmetric pattern of M = B[perm, perm], lower part by rows ----------------
+    std::vector<ivec> low(n);    // low[i] = { k < i : M(i,k) or M(k,i) != 0 }
+    for (uint64_t k : keys) {
+        int a = ip[(uint32_t)(k >> 32)], b = ip[(uint32_t)k];
+        if (a == b) continue;
+        if (a < b) std::swap(a, b);
+        low[a].push_back(b);
+    }
+    for (int i = 0; i < n; ++i) {
+        std::sort(low[i].begin(), low[i].end());
+        low[i].erase(std::unique(low[i].begin(), low[i].end()), low[i].end());
+    }
+
+    // ---- 4. symbolic factorisation: row patterns of L via the elimination tree ------
+    std::vector<ivec> Lrow(n);
+    {
+        ivec parent(n, -1), mark(n, -1);
+        for (int i = 0; i < n; ++i) {
+            mark[i] = i;
+            for (int k : low[i]) {
+                int j = k;
+                while (mark[j] != i) {
+                    if (parent[j] < 0) parent[j] = i;
+                    Lrow[i].push_back(j);
+                    mark[j] = i;
+                    j = parent[j];
+                }
+            }
+            std::sort(Lrow[i].begin(), Lrow[i].end());
+        }
+    }
+    std::vector<ivec>().swap(low);
+    // U row patterns = transpose of L patterns
+    ivec ucount(n, 0);
+    for (int i = 0; i < n; ++i) for (int k : Lrow[i]) ucount[k]++;
+    // natural numbering: row i -> [L cols..., diag, U cols...]
+    ivec rptr(n + 1, 0);
+    for (int i = 0; i < n; ++i) rptr[i + 1] = rptr[i] + (int)Lrow[i].size() + 1 + ucount[i];
+    const long nlu = rptr[n];
+    if (nlu > 2000000000L) { delete P; return cdn_fail(ctx, CDN_ERR_STATE, "plan: fill too large"); }
+    ivec rcol(nlu);
+    {
+        ivec ufill(n, 0);
+        for (int i = 0; i < n; ++i) {
+            int q = rptr[i];
+            for (int k : Lrow[i]) rcol[q++] = k;
+            rcol[q] = i;
+        }
+        for (int i = 0; i < n; ++i)
+            for (int k : Lrow[i]) {     // (i,k) in L  =>  (k,i) in U, rows k filled in increasing i
+                const int q = rptr[k] + (int)Lrow[k].size() + 1 + ufill[k]++;
+                rcol[q] = i;
+            }
+    }
+    auto diag_id = [&](int i) { return rptr[i] + (int)Lrow[i].size(); };
+
+    // ---- 5. Crout terms and levels (natural numbering) -----------------------------------
+    ivec tcount(nlu, 0);
+    {
+        ivec pos(n, -1);
+        for (int i = 0; i < n; ++i) {
+            for (int q = rptr[i]; q < rptr[i + 1]; ++q) pos[rcol[q]] = q;
+            for (int k : Lrow[i]) {
+                const int ub = diag_id(k) + 1, ue = rptr[k + 1];
+                for (int q = ub; q < ue; ++q) tcount[pos[rcol[q]]]++;
+            }
+            for (int q = rptr[i]; q < rptr[i + 1]; ++q) pos[rcol[q]] = -1;
+        }
+    }
+    std::vector<long> tptr(nlu + 1, 0);
+    for (long e = 0; e < nlu; ++e) tptr[e + 1] = tptr[e] + tcount[e];
+    const long nterms = tptr[nlu];
+    if (nterms > 2000000000L) { delete P; return cdn_fail(ctx, CDN_ERR_STATE, "plan: too many LU terms"); }
+    ivec tl(nterms), tu(nterms), lev(nlu, 0);
+    {
+        ivec pos(n, -1);
+        std::vector<long> fillp(tptr.begin(), tptr.end() - 1);
+        for (int i = 0; i < n; ++i) {
+            for (int q = rptr[i]; q < rptr[i + 1]; ++q) pos[rcol[q]] = q;
+            int li = rptr[i];
+            for (int k : Lrow[i]) {
+                const int lid = li++;      // natural id of L(i,k)
+                const int ub = diag_id(k) + 1, ue = rptr[k + 1];
+                for (int q = ub; q < ue; ++q) {
+                    const int e = pos[rcol[q]];
+                    tl[fillp[e]] = lid;
+                    tu[fillp[e]] = q;
+                    fillp[e]++;
+                }
+            }
+            // levels of this row's entries, left to right
+            for (int q = rptr[i]; q < rptr[i + 1]; ++q) {
+                int l = 0;
+                for (long t = tptr[q]; t < tptr[q + 1]; ++t) {
+                    l = std::max(l, lev[tl[t]] + 1);
+                    l = std::max(l, lev[tu[t]] + 1);
+                }
+                const int j = rcol[q];
+                if (j < i) l = std::max(l, lev[diag_id(j)] + 1);
+                lev[q] = l;
+            }
+            for (int q = rptr[i]; q < rptr[i + 1]; ++q) pos[rcol[q]] = -1;
+        }
+    }
+    int nlev_f = 0;
+    for (long e = 0; e < nlu; ++e) nlev_f = std::max(nlev_f, lev[e] + 1);
+    // renumber by level (stable)
+    ivec f_lvl_ptr(nlev_f + 1, 0), slot(nlu);
+    for (long e = 0; e < nlu; ++e) f_lvl_ptr[lev[e] + 1]++;
+    for (int l = 0; l < nlev_f; ++l) f_lvl_ptr[l + 1] += f_lvl_ptr[l];
+    {
+        ivec cur(f_lvl_ptr.begin(), f_lvl_ptr.end() - 1);
+        for (long e = 0; e < nlu; ++e) slot[e] = cur[lev[e]]++;
+    }
+    ivec e_term_ptr(nlu + 1, 0), e_term_l(nterms), e_term_u(nterms), e_piv(nlu);
+    P->max_terms = 0;
+    for (long e = 0; e < nlu; ++e) { e_term_ptr[slot[e] + 1] = tcount[e]; P->max_terms = std::max(P->max_terms, tcount[e]); }
+    for (long s = 0; s < nlu; ++s) e_term_ptr[s + 1] += e_term_ptr[s];
+    for (int i = 0; i < n; ++i)
+        for (int q = rptr[i]; q < rptr[i + 1]; ++q) {
+            const int s = slot[q];
+            long w = e_term_ptr[s];
+            for (long t = tptr[q]; t < tptr[q + 1]; ++t, ++w) {
+                e_term_l[w] = slot[tl[t]];
+                e_term_u[w] = slot[tu[t]];
+            }
+            const int j = rcol[q];
+            e_piv[s] = (j < i) ? slot[diag_id(j)] : (j == i ? -2 : -1);
+        }
+    ivec().swap(tl); ivec().swap(tu); std::vector<long>().swap(tptr);
+    ivec rslot(nlu);
+    for (long e = 0; e < nlu; ++e) rslot[e] = slot[e];
+
+    // ---- 7. linear parts per slot -----------------------------------------------------------
+    std::vector<double> e_g(nlu, 0.0), e_c(nlu, 0.0), e_gones(nlu, 0.0);
+    auto slot_of = [&](int r, int col) { return find_slot(rptr, rcol, rslot, ip[mrow[r]], ip[col]); };
+    for (long k = 0; k < c->nG; ++k)
+        if (c->g_row[k] >= 0 && c->g_col[k] >= 0) e_g[slot_of(c->g_row[k], c->g_col[k])] += c->g_val[k];
+    for (long k = 0; k < c->nC; ++k)
+        if (c->c_row[k] >= 0 && c->c_col[k] >= 0) e_c[slot_of(c->c_row[k], c->c_col[k])] += c->c_val[k];
+    for (long k = 0; k < c->nE; ++k)
+        if (c->e_row[k] >= 0 && c->e_col[k] >= 0) e_gones[slot_of(c->e_row[k], c->e_col[k])] += c->e_val[k];
+
+    // ---- 6. device gather lists ----------------------------------------------------------------
+    long out_size = 0, jac_size = 0;
+    std::vector<long> out_off(c->ngroups), jac_off(c->ngroups);
+    for (int g = 0; g < c->ngroups; ++g) {
+        const cdn_group_host& G = c->groups[g];
+        out_off[g] = out_size;
+        jac_off[g] = jac_size;
+        out_size += (long)(G.ncs + G.nqs) * G.n;
+        jac_size += (long)(G.ncs + G.nqs) * G.nxin * G.n;
+    }
+    if (jac_size > 2000000000L) { delete P; return cdn_fail(ctx, CDN_ERR_STATE, "plan: device Jacobian buffer too large"); }
+    struct Con { int dst; int src; signed char kind; };
+    std::vector<Con> econ, rcon;
+    for (int g = 0; g < c->ngroups; ++g) {
+        const cdn_group_host& G = c->groups[g];
+        const int nout = G.ncs + G.nqs;
+        for (int i = 0; i < G.n; ++i)
+            for (int o = 0; o < nout; ++o) {
+                const bool chg = o >= G.ncs;
+                const int rp = chg ? G.qpos[(long)(o - G.ncs) * G.n + i] : G.cpos[(long)o * G.n + i];
+                const int rn = chg ? G.qneg[(long)(o - G.ncs) * G.n + i] : G.cneg[(long)o * G.n + i];
+                const signed char kp = chg ? 2 : 1, kn = chg ? -2 : -1;
+                const int osrc = (int)(out_off[g] + (long)o * G.n + i);
+                if (rp >= 0) rcon.push_back(Con{rp, osrc, kp});
+                if (rn >= 0) rcon.push_back(Con{rn, osrc, kn});
+                for (int k = 0; k < G.nxin; ++k) {
+                    const int cp = G.vpos[(long)k * G.n + i], cn = G.vneg[(long)k * G.n + i];
+                    const int jsrc = (int)(jac_off[g] + ((long)o * G.nxin + k) * G.n + i);
+                    if (rp >= 0 && cp >= 0) econ.push_back(Con{slot_of(rp, cp), jsrc, kp});
+                    if (rn >= 0 && cn >= 0) econ.push_back(Con{slot_of(rn, cn), jsrc, kp});
+                    if (rp >= 0 && cn >= 0) econ.push_back(Con{slot_of(rp, cn), jsrc, kn});
+                    if (rn >= 0 && cp >= 0) econ.push_back(Con{slot_of(rn, cp), jsrc, kn});
+                }
+            }
+    }
+    auto to_csr = [](std::vector<Con>& v, long ndst, ivec& ptr, ivec& src, std::vector<signed char>& kind, int* maxlen) {
+        ptr.assign(ndst + 1, 0);
+        for (const Con& x : v) ptr[x.dst + 1]++;
+        int mx = 0;
+        for (long d = 0; d < ndst; ++d) { mx = std::max(mx, ptr[d + 1]); ptr[d + 1] += ptr[d]; }
+        if (maxlen) *maxlen = mx;
+        src.resize(v.size());
+        kind.resize(v.size());
+        ivec cur(ptr.begin(), ptr.end() - 1);
+        for (const Con& x : v) { src[cur[x.dst]] = x.src; kind[cur[x.dst]] = x.kind; cur[x.dst]++; }
+    };
+    ivec e_con_ptr, e_con_src, r_con_ptr, r_con_src;
+    std::vector<signed char> e_con_kind, r_con_kind;
+    to_csr(econ, nlu, e_con_ptr, e_con_src, e_con_kind, &P->max_con);
+    to_csr(rcon, n, r_con_ptr, r_con_src, r_con_kind, nullptr);
+    P->ncon = (long)econ.size();
+    std::vector<Con>().swap(econ); std::vector<Con>().swap(rcon);
+
+    // residual: CSR of the linear matrices in original numbering
+    ivec r_lin_ptr(n + 1, 0), r_lin_col;
+    std::vector<double> r_lin_g, r_lin_c, r_lin_gones;
+    {
+        struct LE { uint64_t key; double g, c, e; };
+        std::vector<LE> le;
+        auto addl = [&](int r, int col, double g, double cc, double e) {
+            if (r >= 0 && col >= 0) le.push_back(LE{((uint64_t)(uint32_t)r << 32) | (uint32_t)col, g, cc, e});
+        };
+        for (long k = 0; k < c->nG; ++k) addl(c->g_row[k], c->g_col[k], c->g_val[k], 0, 0);
+        for (long k = 0; k < c->nC; ++k) addl(c->c_row[k], c->c_col[k], 0, c->c_val[k], 0);
+        for (long k = 0; k < c->nE; ++k) addl(c->e_row[k], c->e_col[k], 0, 0, c->e_val[k]);
+        std::stable_sort(le.begin(), le.end(), [](const LE& a, const LE& b) { return a.key < b.key; });
+        for (size_t q = 0; q < le.size();) {
+            size_t q2 = q;
+            double g = 0, cc = 0, e = 0;
+            while (q2 < le.size() && le[q2].key == le[q].key) { g += le[q2].g; cc += le[q2].c; e += le[q2].e; ++q2; }
+            const int r = (int)(le[q].key >> 32);
+            r_lin_ptr[r + 1]++;
+            r_lin_col.push_back((int)(uint32_t)le[q].key);
+            r_lin_g.push_back(g); r_lin_c.push_back(cc); r_lin_gones.push_back(e);
+            q = q2;
+        }
+        for (int i = 0; i < n; ++i) r_lin_ptr[i + 1] += r_lin_ptr[i];
+    }
+
+    // ---- triangular-solve schedules ---------------------------------------------------------------
+    ivec l_ptr(n + 1, 0), u_ptr(n + 1, 0), u_diag(n);
+    for (int i = 0; i < n; ++i) {
+        l_ptr[i + 1] = l_ptr[i] + (int)Lrow[i].size();
+        u_ptr[i + 1] = u_ptr[i] + ucount[i];
+    }
+    ivec l_col(l_ptr[n]), l_slot(l_ptr[n]), u_col(u_ptr[n]), u_slot(u_ptr[n]);
+    ivec levl(n, 0), levu(n, 0);
+    int nlev_l = 0, nlev_u = 0;
+    for (int i = 0; i < n; ++i) {
+        int q = rptr[i], w = l_ptr[i], l = 0;
+        for (size_t t = 0; t < Lrow[i].size(); ++t, ++q, ++w) {
+            l_col[w] = rcol[q]; l_slot[w] = rslot[q];
+            l = std::max(l, levl[rcol[q]] + 1);
+        }
+        levl[i] = l;
+        nlev_l = std::max(nlev_l, l + 1);
+        u_diag[i] = rslot[q];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        int q = diag_id(i) + 1, w = u_ptr[i], l = 0;
+        for (; q < rptr[i + 1]; ++q, ++w) {
+            u_col[w] = rcol[q]; u_slot[w] = rslot[q];
+            l = std::max(l, levu[rcol[q]] + 1);
+        }
+        levu[i] = l;
+        nlev_u = std::max(nlev_u, l + 1);
+    }
+    auto by_level = [&](const ivec& lv, int nl, ivec& lptr, ivec& rows) {
+        lptr.assign(nl + 1, 0);
+        for (int i = 0; i < n; ++i) lptr[lv[i] + 1]++;
+        for (int l = 0; l < nl; ++l) lptr[l + 1] += lptr[l];
+        rows.resize(n);
+        ivec cur(lptr.begin(), lptr.end() - 1);
+        for (int i = 0; i < n; ++i) rows[cur[lv[i]]++] = i;
+    };
+    ivec l_lvl_ptr, l_rows, u_lvl_ptr, u_rows;
+    by_level(levl, nlev_l, l_lvl_ptr, l_rows);
+    by_level(levu, nlev_u, u_lvl_ptr, u_rows);
+    // permuted row i <- original row rowmap[i]; permuted col j -> unknown colmap[j]
+    ivec rowmap(n), colmap(n);
+    for (int r = 0; r < n; ++r) rowmap[ip[mrow[r]]] = r;
+    for (int col = 0; col < n; ++col) colmap[ip[col]] = col;
+
+    // ---- pack ---------------------------------------------------------------------------------------
+    std::vector<char>& B = P->staging;
+    cdn_plan::Off& O = P->off;
+    O.f_lvl_ptr = put(B, f_lvl_ptr); O.e_term_ptr = put(B, e_term_ptr);
+    O.e_term_l = put(B, e_term_l); O.e_term_u = put(B, e_term_u); O.e_piv = put(B, e_piv);
+    O.e_g = put(B, e_g); O.e_c = put(B, e_c); O.e_gones = put(B, e_gones);
+    O.e_con_ptr = put(B, e_con_ptr); O.e_con_src = put(B, e_con_src); O.e_con_kind = put(B, e_con_kind);
+    O.l_lvl_ptr = put(B, l_lvl_ptr); O.l_rows = put(B, l_rows); O.l_ptr = put(B, l_ptr);
+    O.l_col = put(B, l_col); O.l_slot = put(B, l_slot);
+    O.u_lvl_ptr = put(B, u_lvl_ptr); O.u_rows = put(B, u_rows); O.u_ptr = put(B, u_ptr);
+    O.u_col = put(B, u_col); O.u_slot = put(B, u_slot); O.u_diag = put(B, u_diag);
+    O.rowmap = put(B, rowmap); O.colmap = put(B, colmap);
+    O.r_lin_ptr = put(B, r_lin_ptr); O.r_lin_col = put(B, r_lin_col); O.r_lin_g = put(B, r_lin_g);
+    O.r_lin_c = put(B, r_lin_c); O.r_lin_gones = put(B, r_lin_gones);
+    O.r_con_ptr = put(B, r_con_ptr); O.r_con_src = put(B, r_con_src); O.r_con_kind = put(B, r_con_kind);
+    cdn_plan_dev& D = P->dev;
+    D.n = n; D.nlu = (int)nlu; D.nlev_f = nlev_f; D.nlev_l = nlev_l; D.nlev_u = nlev_u;
+    D.ngroups = c->ngroups;
+    D.dev_out_size = out_size; D.dev_jac_size = jac_size;
+    for (int g = 0; g < c->ngroups; ++g) {
+        const cdn_group_host& G = c->groups[g];
+        cdn_group_dev& d = D.groups[g];
+        d.model = G.model; d.flags = G.flags; d.n = G.n; d.nxin = G.nxin; d.ncs = G.ncs;
+        d.nqs = G.nqs; d.ndelay = G.ndelay;
+        d.out_off = out_off[g]; d.jac_off = jac_off[g];
+        ivec vp(G.vpos, G.vpos + (long)G.nxin * G.n), vn(G.vneg, G.vneg + (long)G.nxin * G.n);
+        O.gv[g][0] = put(B, vp); O.gv[g][1] = put(B, vn);
+    }
+    P->nterms = nterms;
+    *out = P;
+    return CDN_OK;
+}
+
+extern "C" long cdn_plan_bytes(cdn_plan* P) { return P ? (long)P->staging.size() + 256 : 0; }
+
+// info[0..9] = n, nlu, nlev_f, nlev_l, nlev_u, nterms, ncon, nnzA, max_terms, max_con
+extern "C" int cdn_plan_info(cdn_plan* P, long* info) {
+    if (!P || !info) return CDN_ERR_ARG;
+    info[0] = P->dev.n; info[1] = P->dev.nlu; info[2] = P->dev.nlev_f; info[3] = P->dev.nlev_l;
+    info[4] = P->dev.nlev_u; info[5] = P->nterms; info[6] = P->ncon; info[7] = P->nnzA;
+    info[8] = P->max_terms; info[9] = P->max_con;
+    info[10] = P->dev.dev_out_size; info[11] = P->dev.dev_jac_size;
+    return CDN_OK;
+}
+
+extern "C" int cdn_plan_bind(cdn_plan* P, void* dev_ws, long bytes, void* stream) {
+    if (!P || !dev_ws) return CDN_ERR_ARG;
+    cdn_ctx* ctx = P->ctx;
+    char* base = (char*)(((uintptr_t)dev_ws + 255) / 256 * 256);
+    if ((long)(base - (char*)dev_ws) + (long)P->staging.size() > bytes)
+        return cdn_fail(ctx, CDN_ERR_ARG, "plan_bind: workspace too small");
+    CDN_CUDA(ctx, cudaMemcpyAsync(base, P->staging.data(), P->staging.size(),
+                                  cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CDN_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    cdn_plan_dev& D = P->dev;
+    const cdn_plan::Off& O = P->off;
+#define BIND(f, T) D.f = (const T*)(base + O.f)
+    BIND(f_lvl_ptr, int); BIND(e_term_ptr, int); BIND(e_term_l, int); BIND(e_term_u, int);
+    BIND(e_piv, int); BIND(e_g, double); BIND(e_c, double); BIND(e_gones, double);
+    BIND(e_con_ptr, int); BIND(e_con_src, int); BIND(e_con_kind, signed char);
+    BIND(l_lvl_ptr, int); BIND(l_rows, int); BIND(l_ptr, int); BIND(l_col, int); BIND(l_slot, int);
+    BIND(u_lvl_ptr, int); BIND(u_rows, int); BIND(u_ptr, int); BIND(u_col, int); BIND(u_slot, int);
+    BIND(u_diag, int); BIND(rowmap, int); BIND(colmap, int);
+    BIND(r_lin_ptr, int); BIND(r_lin_col, int); BIND(r_lin_g, double); BIND(r_lin_c, double);
+    BIND(r_lin_gones, double); BIND(r_con_ptr, int); BIND(r_con_src, int);
+    BIND(r_con_kind, signed char);
+#undef BIND
+    for (int g = 0; g < D.ngroups; ++g) {
+        D.groups[g].vpos = (const int*)(base + O.gv[g][0]);
+        D.groups[g].vneg = (const int*)(base + O.gv[g][1]);
+    }
+    P->bound = true;
+    return CDN_OK;
+}
+
+extern "C" int cdn_plan_set_group_params(cdn_plan* P, int g, const double* params, long ldp,
+                                         const int* pidx) {
+    if (!P || g < 0 || g >= P->dev.ngroups) return CDN_ERR_ARG;
+    P->dev.groups[g].params = params;
+    P->dev.groups[g].ldp = ldp;
+    P->dev.groups[g].pidx = pidx;
+    return CDN_OK;
+}
+
+// update the linear values of the plan in place (parameter sweeps): not needed yet
+extern "C" int cdn_plan_free(cdn_plan* P) {
+    delete P;
+    return CDN_OK;
+}
+
+const cdn_plan_dev* cdn_plan_device_view(cdn_plan* P) { return P && P->bound ? &P->dev : nullptr; }
+cdn_ctx* cdn_plan_ctx(cdn_plan* P) { return P->ctx; }
