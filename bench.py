@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""
+bench.py -- throughput of the cardoon_b200 Newton hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME]
+  python bench.py --impl reference ...     (CPU oracle arm, see below)
+
+One JSON line on stdout (rank 0).  Workloads (BASELINE.json `metric`):
+
+  deveval  device evals/s: one step = one cdn_dev_eval launch (values + full
+           Jacobian) over n BSIM3 (mosbsim3) instances with per-instance
+           parameter columns in HBM (SURVEY 8d "E").
+  mc       circuits/s: complete ring_bsim3 transients, one circuit instance
+           per Monte-Carlo sample, instances sharded across ranks (8d "M").
+  soliton  accepted timepoints/s of test/soliton.net (8d "T"), 1 GPU.
+
+`value` is measured with the inputs resident in HBM; `e2e` is the same
+metric through the public host-buffer API with the host<->device copies in
+the timed region.  `--impl reference` times the CPU oracle restatement of
+the reference's path (the reference itself is Python 2 + pycppad and cannot
+run here) on the same workload definition.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+# ---------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get('hbm_gbs', 6650.)), 'measured'
+    return 6650., 'fallback'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,'
+         'clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unsampled'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for ts, line in self.lines:
+            if t0 is not None and (ts < t0 - 0.05 or ts > t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unsampled'])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                    power_w_max=float(max(pw)), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+class Dist(object):
+    """torch.distributed plumbing (one process per GPU, NCCL)."""
+
+    def __init__(self, ngpus):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: no CUDA GPU -- the hot path has no '
+                             'CPU implementation (use --impl reference for '
+                             'the CPU oracle arm)')
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            os.environ.setdefault('MASTER_PORT', '29511')
+            dist.init_process_group('nccl', rank=self.rank,
+                                    world_size=self.world,
+                                    device_id=torch.device('cuda', self.local))
+            self.dist = dist
+        if ngpus != self.world:
+            if self.rank == 0:
+                print('bench.py: --gpus {0} but WORLD_SIZE={1}; using {1}'
+                      .format(ngpus, self.world), file=sys.stderr)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64,
+                              device='cuda')
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if self.dist is None:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64,
+                              device='cuda')
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def timed_steps(D, step, steps, warmup, flush=None):
+    """W untimed + K timed steps; device time (CUDA events), max over ranks.
+
+    Returns (total_ms, wall_t0, wall_t1).  `flush` (optional) runs between
+    steps outside the per-step event pairs.
+    """
+    torch = D.torch
+    for _ in range(warmup):
+        step()
+        if flush is not None:
+            flush()
+    D.barrier()
+    t0 = time.time()
+    if flush is None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    else:
+        ms = 0.
+        for _ in range(steps):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            flush()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+    D.barrier()
+    t1 = time.time()
+    return D.max_over_ranks(ms), t0, t1
+
+
+# ---------------------------------------------------------------------------
+# workload: device evaluation (SURVEY 8d "E")
+# ---------------------------------------------------------------------------
+def bsim3_param_columns(ncols, seed=1234):
+    """Packed mosbsim3 records of the nch and pch models of
+    inverter_chain_bsim.net with w ~ U(1u, 30u), l ~ U(0.5u, 2u).
+
+    Returns one group per channel type (their kernel flag words differ:
+    the nch card has a substrate-current term)."""
+    from tests import support as S
+    ckt, _ = S.load_circuit(S.net('inverter_chain_bsim.net'))
+    elems = S.nonlinear_elements(ckt)
+    rng = np.random.default_rng(seed)
+    groups = []
+    for tf in (1., -1.):
+        e = [x for x in elems if x._tf == tf][0]
+        cols, flags = [], None
+        for k in range(ncols):
+            e.w = float(rng.uniform(1e-6, 30e-6))
+            e.l = float(rng.uniform(0.5e-6, 2e-6))
+            e.process_params()
+            spec = e.cuda_spec()
+            flags = spec['flags'] if flags is None else flags
+            assert spec['flags'] == flags
+            cols.append(spec['params'].copy())
+        groups.append(dict(elem=e, tf=tf, model=spec['model'], flags=flags,
+                           cols=np.array(cols).T.copy()))
+    return groups
+
+
+def deveval_inputs(n, ncols=256, seed=1234):
+    """Two groups (nch, pch) of n/2 instances each."""
+    groups = bsim3_param_columns(ncols, seed)
+    rng = np.random.default_rng(seed + 1)
+    for g in groups:
+        m = n // 2
+        g['n'] = m
+        g['col'] = rng.integers(0, ncols, size=m).astype(np.int64)
+        g['xin'] = rng.uniform(-0.5, 3.5, size=(3, m)) * g['tf']
+    return dict(groups=groups, n=2 * (n // 2), nout=6, nxin=3)
+
+
+def bsim3_flops(inp, nsample=2048):
+    """Algorithmic FLOPs of one eval (oracle op counter)."""
+    from oracle import dual as OD
+    from oracle.models import device_eval
+    OD.reset_ops()
+    for g in inp['groups']:
+        device_eval(g['elem'], g['xin'][:, :nsample], True)
+    # the counter tallies one scalar operation per vectorised numpy call
+    k = float(len(inp['groups']))
+    return OD.OPS['flop'] / k, OD.OPS['trans'] / k
+
+
+def run_deveval(args, D):
+    torch = D.torch
+    from cardoon_b200._lib import get_lib
+    lib = get_lib(D.local)
+    inp = deveval_inputs(args.n or (1 << 22), seed=1234 + D.rank)
+    n, nout, nxin = inp['n'], inp['nout'], inp['nxin']
+    G = []
+    for g in inp['groups']:
+        colidx = torch.as_tensor(g['col'], device=lib.device)
+        m = g['n']
+        G.append(dict(model=g['model'], flags=g['flags'], n=m,
+                      params=lib.dev(g['cols']).index_select(1, colidx)
+                      .contiguous(),
+                      xin_h=torch.as_tensor(g['xin']).pin_memory(),
+                      xin=lib.dev(g['xin']), out=lib.empty((nout, m)),
+                      jac=lib.empty((nout * nxin, m)),
+                      out_h=torch.empty((nout, m), dtype=torch.float64)
+                      .pin_memory(),
+                      jac_h=torch.empty((nout * nxin, m),
+                                        dtype=torch.float64).pin_memory()))
+    npar = G[0]['params'].shape[0]
+    pbytes = sum(g['params'].numel() for g in G) * 8
+
+    def step():
+        for g in G:
+            lib.dev_eval(g['model'], g['flags'], g['params'], g['xin'], nout,
+                         want_jac=True, out=g['out'], jac=g['jac'])
+
+    clk = ClockSampler(D.local)
+    clk.start()
+    ms, t0, t1 = timed_steps(D, step, args.steps, args.warmup)
+    clocks = clk.stop(t0, t1)
+    timed_launches = args.steps * len(G)
+    total = D.sum_over_ranks(n) * args.steps
+    value = total / (ms * 1e-3)
+
+    # ---- end to end: host xin -> device, eval, out + jac -> host ---------
+    def e2e_step():
+        for g in G:
+            g['xin'].copy_(g['xin_h'], non_blocking=True)
+            lib.dev_eval(g['model'], g['flags'], g['params'], g['xin'], nout,
+                         want_jac=True, out=g['out'], jac=g['jac'])
+            g['out_h'].copy_(g['out'], non_blocking=True)
+            g['jac_h'].copy_(g['jac'], non_blocking=True)
+
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e, _, _ = timed_steps(D, e2e_step, e2e_steps, 1)
+    e2e = dict(value=D.sum_over_ranks(n) * e2e_steps / (ms_e * 1e-3),
+               unit='device evals/s',
+               h2d_bytes_per_step=int(n * nxin * 8),
+               d2h_bytes_per_step=int(n * (nout + nout * nxin) * 8))
+
+    line = None
+    if D.rank == 0:
+        flop, trans = bsim3_flops(inp)
+        peak = lib.fp64_peak()
+        hbm, how = measured_peaks()
+        bytes_eval = 8. * (npar + nxin + nout + nout * nxin)
+        t_step = ms * 1e-3 / args.steps
+        ach = n * flop / t_step / 1e12
+        roof = dict(bound='fp64', achieved=ach, peak=peak / 1e12,
+                    unit='TFLOP/s', frac=ach / (peak / 1e12), traffic=None,
+                    peak_source='cdn_fp64_peak (DFMA microbenchmark, this '
+                                'run)',
+                    flop_per_eval=flop, transcendental_per_eval=trans,
+                    hbm=dict(achieved=n * bytes_eval / t_step / 1e9,
+                             peak=hbm, unit='GB/s',
+                             frac=n * bytes_eval / t_step / 1e9 / hbm,
+                             bytes_per_eval=bytes_eval, peak_source=how))
+        cpu = cpu_baseline_deveval(inp)
+        line = dict(metric='device evals/s (BSIM3v3 mosbsim3, value + '
+                           'Jacobian)', value=value, unit='device evals/s',
+                    n_gpus=D.world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True,
+                    scaling='weak', vs_baseline=None, dtype='f64',
+                    data='synthetic',
+                    config=dict(workload='deveval: {0} mosbsim3 instances per '
+                                'GPU (half nch, half pch), per-instance '
+                                'parameter columns ({1} doubles each) in HBM'
+                                .format(n, npar), instances_per_gpu=n,
+                                l2='inputs larger than L2 ({0:.1f} GB of '
+                                   'parameters per step)'.format(pbytes
+                                                                 / 1e9)),
+                    clocks=clocks, e2e=e2e, gpu_launches=timed_launches,
+                    roofline=roof, cpu_baseline=cpu)
+    return line
+
+
+def cpu_baseline_deveval(inp, nsample=1 << 15, seconds=10.):
+    from oracle.models import device_eval
+    t0 = time.time()
+    reps = 0
+    while time.time() - t0 < seconds:
+        for g in inp['groups']:
+            device_eval(g['elem'], g['xin'][:, :nsample], True)
+        reps += 1
+    dt = time.time() - t0
+    return dict(value=2 * nsample * reps / dt, unit='device evals/s', cores=1,
+                kind='port',
+                sample='{0} x {1} mosbsim3 evals (numpy dual-number oracle, '
+                       'vectorised over instances)'.format(2 * reps, nsample))
+
+
+# ---------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return None
+    if args.workload == 'deveval':
+        inp = deveval_inputs(1 << 16)
+        cpu = cpu_baseline_deveval(inp)
+        v = cpu['value']
+        return dict(impl='reference', metric='device evals/s (BSIM3v3 '
+                    'mosbsim3, value + Jacobian)', value=v,
+                    unit='device evals/s', n_gpus=args.gpus,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=None,
+                    higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f64', data='synthetic',
+                    config=dict(workload='deveval'), cpu_baseline=cpu,
+                    e2e=dict(value=v, unit='device evals/s',
+                             h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    raise SystemExit('unknown workload')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native',
+                    choices=['native', 'reference'])
+    ap.add_argument('--workload', default='deveval',
+                    choices=['deveval', 'mc', 'soliton'])
+    ap.add_argument('--n', type=int, default=0,
+                    help='instances per GPU (0 = workload default)')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'native' \
+        else args.warmup
+    if args.impl == 'reference':
+        line = run_reference(args)
+        if line is not None:
+            print(json.dumps(line))
+        return
+    import __graft_entry__ as g
+    if int(os.environ.get('LOCAL_RANK', '0')) == 0:
+        g.build()
+    D = Dist(args.gpus)
+    D.barrier()
+    line = dict(deveval=run_deveval)[args.workload](args, D)
+    if D.rank == 0:
+        print(json.dumps(line))
+    D.close()
+
+
+if __name__ == '__main__':
+    main()

@@ -213,6 +213,26 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
     P->nnzA = (long)keys.size();
 
+    const bool dense = (c->ordering == 2);
+    ivec ip(n), rptr(n + 1, 0), rcol, rslot, ucount(n, 0);
+    std::vector<ivec> Lrow(n);
+    ivec f_lvl_ptr, e_term_ptr, e_term_l, e_term_u, e_piv;
+    long nlu = 0, nterms = 0;
+    int nlev_f = 0;
+    P->max_terms = 0;
+    auto diag_id = [&](int i) { return rptr[i] + (int)Lrow[i].size(); };
+    if (dense) {
+        // dense storage for the partial-pivoting small-system kernels:
+        // slot(r, c) = r*n + c in the original numbering, no schedule
+        if ((long)n * n > 16000000L) { delete P; return cdn_fail(ctx, CDN_ERR_ARG, "plan: too large for dense storage"); }
+        for (int i = 0; i < n; ++i) { ip[i] = i; mrow[i] = i; rptr[i + 1] = (i + 1) * n; }
+        nlu = (long)n * n;
+        rcol.resize(nlu); rslot.resize(nlu);
+        for (long q = 0; q < nlu; ++q) { rcol[q] = (int)(q % n); rslot[q] = (int)q; }
+        f_lvl_ptr.assign(1, 0);
+        e_term_ptr.assign(nlu + 1, 0);
+        e_piv.assign(nlu, -1);
+    } else {
     // ---- 3. ordering on the symmetrised graph -----------------------------------------
     Graph gr;
     gr.n = n;
@@ -253,7 +273,6 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
         for (int v : hubs) perm.push_back(v);
         if ((int)perm.size() != n) { delete P; return cdn_fail(ctx, CDN_ERR_STATE, "plan: ordering lost nodes"); }
     }
-    ivec ip(n);
     for (int i = 0; i < n; ++i) ip[perm[i]] = i;
 
     // ---- symmetric pattern of M = B[perm, perm], lower part by rows ----------------
@@ -270,7 +289,6 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     }
 
     // ---- 4. symbolic factorisation: row patterns of L via the elimination tree ------
-    std::vector<ivec> Lrow(n);
     {
         ivec parent(n, -1), mark(n, -1);
         for (int i = 0; i < n; ++i) {
@@ -289,14 +307,12 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     }
     std::vector<ivec>().swap(low);
     // U row patterns = transpose of L patterns
-    ivec ucount(n, 0);
     for (int i = 0; i < n; ++i) for (int k : Lrow[i]) ucount[k]++;
     // natural numbering: row i -> [L cols..., diag, U cols...]
-    ivec rptr(n + 1, 0);
     for (int i = 0; i < n; ++i) rptr[i + 1] = rptr[i] + (int)Lrow[i].size() + 1 + ucount[i];
-    const long nlu = rptr[n];
+    nlu = rptr[n];
     if (nlu > 2000000000L) { delete P; return cdn_fail(ctx, CDN_ERR_STATE, "plan: fill too large"); }
-    ivec rcol(nlu);
+    rcol.assign(nlu, 0);
     {
         ivec ufill(n, 0);
         for (int i = 0; i < n; ++i) {
@@ -310,7 +326,6 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
                 rcol[q] = i;
             }
     }
-    auto diag_id = [&](int i) { return rptr[i] + (int)Lrow[i].size(); };
 
     // ---- 5. Crout terms and levels (natural numbering) -----------------------------------
     ivec tcount(nlu, 0);
@@ -327,7 +342,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     }
     std::vector<long> tptr(nlu + 1, 0);
     for (long e = 0; e < nlu; ++e) tptr[e + 1] = tptr[e] + tcount[e];
-    const long nterms = tptr[nlu];
+    nterms = tptr[nlu];
     if (nterms > 2000000000L) { delete P; return cdn_fail(ctx, CDN_ERR_STATE, "plan: too many LU terms"); }
     ivec tl(nterms), tu(nterms), lev(nlu, 0);
     {
@@ -360,18 +375,17 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
             for (int q = rptr[i]; q < rptr[i + 1]; ++q) pos[rcol[q]] = -1;
         }
     }
-    int nlev_f = 0;
     for (long e = 0; e < nlu; ++e) nlev_f = std::max(nlev_f, lev[e] + 1);
     // renumber by level (stable)
-    ivec f_lvl_ptr(nlev_f + 1, 0), slot(nlu);
+    f_lvl_ptr.assign(nlev_f + 1, 0);
+    ivec slot(nlu);
     for (long e = 0; e < nlu; ++e) f_lvl_ptr[lev[e] + 1]++;
     for (int l = 0; l < nlev_f; ++l) f_lvl_ptr[l + 1] += f_lvl_ptr[l];
     {
         ivec cur(f_lvl_ptr.begin(), f_lvl_ptr.end() - 1);
         for (long e = 0; e < nlu; ++e) slot[e] = cur[lev[e]]++;
     }
-    ivec e_term_ptr(nlu + 1, 0), e_term_l(nterms), e_term_u(nterms), e_piv(nlu);
-    P->max_terms = 0;
+    e_term_ptr.assign(nlu + 1, 0); e_term_l.assign(nterms, 0); e_term_u.assign(nterms, 0); e_piv.assign(nlu, 0);
     for (long e = 0; e < nlu; ++e) { e_term_ptr[slot[e] + 1] = tcount[e]; P->max_terms = std::max(P->max_terms, tcount[e]); }
     for (long s = 0; s < nlu; ++s) e_term_ptr[s + 1] += e_term_ptr[s];
     for (int i = 0; i < n; ++i)
@@ -386,8 +400,9 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
             e_piv[s] = (j < i) ? slot[diag_id(j)] : (j == i ? -2 : -1);
         }
     ivec().swap(tl); ivec().swap(tu); std::vector<long>().swap(tptr);
-    ivec rslot(nlu);
+    rslot.assign(nlu, 0);
     for (long e = 0; e < nlu; ++e) rslot[e] = slot[e];
+    }  // !dense
 
     // ---- 7. linear parts per slot -----------------------------------------------------------
     std::vector<double> e_g(nlu, 0.0), e_c(nlu, 0.0), e_gones(nlu, 0.0);
