@@ -25,6 +25,52 @@ class CdnError(RuntimeError):
 _vp = C.c_void_p
 
 
+class GroupHost(C.Structure):
+    """cdn_group_host (csrc/plan_host.h)."""
+    _fields_ = [('model', C.c_int), ('flags', C.c_uint), ('n', C.c_int),
+                ('nxin', C.c_int), ('ncs', C.c_int), ('nqs', C.c_int),
+                ('ndelay', C.c_int),
+                ('vpos', _vp), ('vneg', _vp), ('cpos', _vp), ('cneg', _vp),
+                ('qpos', _vp), ('qneg', _vp)]
+
+
+class CircuitHost(C.Structure):
+    """cdn_circuit_host (csrc/plan_host.h)."""
+    _fields_ = [('n', C.c_int), ('ordering', C.c_int),
+                ('nG', C.c_long), ('g_row', _vp), ('g_col', _vp),
+                ('g_val', _vp),
+                ('nC', C.c_long), ('c_row', _vp), ('c_col', _vp),
+                ('c_val', _vp),
+                ('nE', C.c_long), ('e_row', _vp), ('e_col', _vp),
+                ('e_val', _vp),
+                ('ngroups', C.c_int), ('groups', C.POINTER(GroupHost)),
+                ('rowmatch', _vp), ('colorder', _vp)]
+
+
+class RunHost(C.Structure):
+    """cdn_run_host (csrc/engine.cu)."""
+    _fields_ = [('abstol', C.c_double), ('reltol', C.c_double),
+                ('maxdelta', C.c_double), ('a0', C.c_double),
+                ('gmin', C.c_double), ('lam', C.c_double),
+                ('maxiter', C.c_int), ('errfunc', C.c_int),
+                ('use_q', C.c_int), ('im', C.c_int),
+                ('op', C.c_int), ('B', C.c_int),
+                ('team', C.c_int), ('T', C.c_int),
+                ('x', _vp), ('sv_in', _vp), ('ws', _vp),
+                ('nsamples', C.c_int), ('first', C.c_int),
+                ('init_ic', C.c_int), ('nsrc', C.c_int), ('nsave', C.c_int),
+                ('blocks', C.c_int),
+                ('src_rows', _vp), ('src_val', _vp), ('src_dc', _vp),
+                ('save_rows', _vp), ('wave', _vp), ('iters', _vp),
+                ('res', _vp), ('status', _vp), ('red', _vp)]
+
+
+OP_NEWTON, OP_TRAN, OP_UPDATE_Q, OP_SET_IC, OP_ACCEPT, OP_RHS, OP_CHORD, \
+    OP_GET_I, OP_GET_I_JAC, OP_SOLVE = range(10)
+TEAM_AUTO, TEAM_TILE, TEAM_BLOCK, TEAM_GRID = -1, 0, 1, 2
+ORDER_ND, ORDER_NATURAL, ORDER_DENSE, ORDER_GIVEN = 0, 1, 2, 3
+
+
 def _declare(dll):
     dll.cdn_version.restype = C.c_int
     dll.cdn_init.argtypes = [C.c_int, C.POINTER(_vp)]
@@ -36,6 +82,23 @@ def _declare(dll):
     dll.cdn_dev_eval.argtypes = [_vp, C.c_int, C.c_uint, C.c_long, C.c_int,
                                  _vp, C.c_long, _vp, _vp, _vp, _vp, _vp]
     dll.cdn_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
+    dll.cdn_plan_create.argtypes = [_vp, C.POINTER(CircuitHost),
+                                    C.POINTER(_vp)]
+    dll.cdn_plan_bytes.argtypes = [_vp]
+    dll.cdn_plan_bytes.restype = C.c_long
+    dll.cdn_plan_info.argtypes = [_vp, C.POINTER(C.c_long)]
+    dll.cdn_plan_bind.argtypes = [_vp, _vp, C.c_long, _vp]
+    dll.cdn_plan_set_group_params.argtypes = [_vp, C.c_int, _vp, C.c_long,
+                                              _vp, C.c_int]
+    dll.cdn_plan_slot_coords.argtypes = [_vp, _vp, _vp]
+    dll.cdn_plan_free.argtypes = [_vp]
+    dll.cdn_plan_array.argtypes = [_vp, C.c_char_p, C.POINTER(_vp),
+                                   C.POINTER(C.c_long)]
+    dll.cdn_init_host.argtypes = [C.POINTER(_vp)]
+    dll.cdn_engine_ws_doubles.argtypes = [_vp]
+    dll.cdn_engine_ws_doubles.restype = C.c_long
+    dll.cdn_engine_layout.argtypes = [_vp, C.POINTER(C.c_long)]
+    dll.cdn_engine_run.argtypes = [_vp, C.POINTER(RunHost), _vp]
 
 
 def load_dll():

@@ -20,6 +20,17 @@ extern "C" int cdn_init(int device, cdn_ctx** out) {
     return CDN_OK;
 }
 
+// context without a GPU: host-side symbolic analysis only (cdn_plan_create,
+// cdn_plan_info, cdn_plan_array); every launch through it fails
+extern "C" int cdn_init_host(cdn_ctx** out) {
+    if (!out) return CDN_ERR_ARG;
+    cdn_ctx* c = new cdn_ctx();
+    c->device = -1;
+    c->sm_count = 0;
+    *out = c;
+    return CDN_OK;
+}
+
 extern "C" int cdn_free(cdn_ctx* ctx) {
     delete ctx;
     return CDN_OK;

@@ -1,0 +1,135 @@
+// C ABI of the device-resident Newton engine (include/cardoon_b200.h,
+// "engine" section): sizes the per-instance state, picks the thread team and
+// the model-set instantiation, and launches one kernel per operation.
+#include "engine_launch.cuh"
+#include "plan_host.h"
+#include <cstring>
+
+extern "C" {
+
+// plain-C mirror of cdn_engine_args handed in by the host (ctypes)
+typedef struct cdn_run_host {
+    double abstol, reltol, maxdelta, a0, gmin, lambda;
+    int maxiter, errfunc, use_q, im;
+    int op, B;
+    int team, T;                 // team: -1 = choose; T: 0 = choose
+    double* x;
+    const double* sv_in;
+    double* ws;                  // NULL: state in shared memory (tile team only)
+    int nsamples, first, init_ic, nsrc, nsave, blocks;
+    const int* src_rows;
+    const double* src_val;
+    const double* src_dc;
+    const int* save_rows;
+    double* wave;
+    int* iters;
+    double* res;
+    int* status;
+    double* red;                 // >= 2*blocks doubles for the grid team
+} cdn_run_host;
+
+long cdn_engine_ws_doubles(cdn_plan* P) {
+    const cdn_plan_dev* D = cdn_plan_host_view(P);
+    if (!D) return -1;
+    return ws_doubles(D->n, D->nlu, D->dev_out_size, D->dev_jac_size);
+}
+
+// offsets (in doubles) of x, dx, ivec, sv, q, qprev, dq, y, tmp, lu, out, jac, piv
+int cdn_engine_layout(cdn_plan* P, long* off) {
+    const cdn_plan_dev* D = cdn_plan_host_view(P);
+    if (!D || !off) return CDN_ERR_ARG;
+    const long n = D->n;
+    for (int k = 0; k < 9; ++k) off[k] = k * n;
+    off[9] = 9 * n;
+    off[10] = off[9] + D->nlu;
+    off[11] = off[10] + D->dev_out_size;
+    off[12] = off[11] + D->dev_jac_size;
+    return CDN_OK;
+}
+
+int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
+    if (!P || !r) return CDN_ERR_ARG;
+    cdn_ctx* ctx = cdn_plan_ctx(P);
+    const cdn_plan_dev* D = cdn_plan_host_view(P);
+    if (!D) return cdn_fail(ctx, CDN_ERR_STATE, "engine: plan is not bound");
+    cudaStream_t st = (cudaStream_t)stream;
+    const cdn_plan_dev* dplan = nullptr;
+    int rc = cdn_plan_sync_device(P, st, &dplan);
+    if (rc != CDN_OK) return rc;
+
+    // model set
+    unsigned ms = 0;
+    for (int g = 0; g < D->ngroups; ++g) {
+        if (!D->groups[g].params) return cdn_fail(ctx, CDN_ERR_STATE, "engine: group parameters not set");
+        if (D->groups[g].ndelay) return cdn_fail(ctx, CDN_ERR_ARG, "engine: delayed control ports are not supported");
+        ms |= 1u << D->groups[g].model;
+    }
+    if (ms & ~(unsigned)CDN_MS_ALL) return cdn_fail(ctx, CDN_ERR_ARG, "engine: model not available in the Newton engine");
+
+    cdn_engine_args A;
+    memset(&A, 0, sizeof(A));
+    A.plan = dplan;
+    A.o.abstol = r->abstol; A.o.reltol = r->reltol; A.o.maxdelta = r->maxdelta;
+    A.o.a0 = r->a0; A.o.gmin = r->gmin; A.o.lambda = r->lambda;
+    A.o.maxiter = r->maxiter; A.o.errfunc = r->errfunc; A.o.use_q = r->use_q; A.o.im = r->im;
+    A.op = r->op; A.B = r->B;
+    A.x = r->x; A.sv_in = r->sv_in; A.ws = r->ws;
+    const long per = ws_doubles(D->n, D->nlu, D->dev_out_size, D->dev_jac_size);
+    A.ws_stride = per;
+    A.nsamples = r->nsamples; A.first = r->first; A.init_ic = r->init_ic;
+    A.nsrc = r->nsrc; A.nsave = r->nsave;
+    A.src_rows = r->src_rows; A.src_val = r->src_val; A.src_dc = r->src_dc;
+    A.save_rows = r->save_rows; A.wave = r->wave; A.iters = r->iters; A.res = r->res;
+    A.status = r->status; A.red = r->red;
+    if (A.B <= 0) return CDN_OK;
+    if (!A.x) return cdn_fail(ctx, CDN_ERR_ARG, "engine: x is NULL");
+
+    cdn_launch_cfg c;
+    memset(&c, 0, sizeof(c));
+    c.sm_count = ctx->sm_count;
+    c.team = r->team;
+    if (c.team < 0) {
+        if (D->dense && D->n <= 64) c.team = CDN_TEAM_TILE;
+        else if (A.B > 1 || D->nlu < 200000) c.team = CDN_TEAM_BLOCK;
+        else c.team = CDN_TEAM_GRID;
+    }
+    if (c.team == CDN_TEAM_TILE) {
+        int T = r->T;
+        if (T <= 0) {
+            const int want = D->ndev > D->n ? D->ndev : D->n;
+            T = 4;
+            while (T < want && T < 32) T *= 2;
+        }
+        c.T = T;
+        c.tpb = 128;
+        if (!A.ws) {
+            // state in shared memory: shrink the CTA until it fits
+            while (c.tpb > T && (long)(c.tpb / T) * per * 8 > 200 * 1024) c.tpb /= 2;
+            c.smem = (long)(c.tpb / T) * per * 8;
+            if (c.smem > 227 * 1024) return cdn_fail(ctx, CDN_ERR_ARG, "engine: circuit state does not fit shared memory; pass a workspace");
+        }
+        const int tiles = c.tpb / T;
+        c.blocks = (A.B + tiles - 1) / tiles;
+    } else if (c.team == CDN_TEAM_BLOCK) {
+        if (!A.ws) return cdn_fail(ctx, CDN_ERR_ARG, "engine: block team needs a workspace");
+        c.blocks = A.B;
+        c.tpb = 256;
+    } else if (c.team == CDN_TEAM_GRID) {
+        if (!A.ws || !A.red) return cdn_fail(ctx, CDN_ERR_ARG, "engine: grid team needs workspace and reduction scratch");
+        if (A.B != 1) return cdn_fail(ctx, CDN_ERR_ARG, "engine: grid team runs one circuit");
+        if (D->dense) return cdn_fail(ctx, CDN_ERR_ARG, "engine: grid team needs a sparse plan");
+        c.blocks = r->blocks;
+    } else {
+        return cdn_fail(ctx, CDN_ERR_ARG, "engine: unknown team");
+    }
+
+    cudaError_t e;
+    if ((ms & ~(unsigned)CDN_MS_DIODE) == 0) e = cdn_launch_ms_diode(A, c, st);
+    else if ((ms & ~(unsigned)CDN_MS_BSIM3) == 0) e = cdn_launch_ms_bsim3(A, c, st);
+    else e = cdn_launch_ms_all(A, c, st);
+    if (e != cudaSuccess)
+        return cdn_fail(ctx, CDN_ERR_CUDA, std::string("engine launch: ") + cudaGetErrorString(e));
+    return CDN_OK;
+}
+
+}  // extern "C"

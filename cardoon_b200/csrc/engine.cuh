@@ -1,0 +1,723 @@
+// Device-resident Newton engine: device evaluation, gather assembly, LU,
+// triangular solves, damped-Newton control, integration and the fixed-step
+// time loop, all inside one kernel launch, written once over a "team" of
+// cooperating threads:
+//
+//   TileTeam<T>  T (<= 32) lanes of a warp per circuit instance, state in
+//                shared memory: batches of small circuits (Monte Carlo)
+//   BlockTeam    one CTA per circuit instance, state in global memory (L2)
+//   GridTeam     the whole cooperative grid on one circuit (large sparse)
+//
+// Reference functions restated here (cechrist/cardoon, file:line):
+//   set_xin / set_i / set_Jac            analyses/nodal.py:44-80
+//   get_i, get_i_Jac                     nodal.py:761-821, 1046-1133;
+//                                        nodalSP.py:471-523, 804-887
+//   factor_and_solve, get_chord_deltax   nodal.py:606-659, nodalSP.py:281-354
+//   fsolve_Newton                        analyses/fsolve.py:59-128
+//   update_q, accept, get_rhs, set_IC    nodalSP.py:666-802
+//   BEuler / Trapezoidal                 analyses/integration.py:13-97
+//   time loop incl. chord predictor      analyses/tran.py:171-206
+#pragma once
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "plan.h"
+#include "models.cuh"
+
+namespace cg = cooperative_groups;
+
+// ---- run description ---------------------------------------------------------------
+enum {
+    CDN_OP_NEWTON = 0,     // x <- Newton(x, sv)
+    CDN_OP_TRAN = 1,       // whole time loop from the operating point in x
+    CDN_OP_UPDATE_Q = 2,   // q <- C x + Tq q(x)
+    CDN_OP_SET_IC = 3,     // update_q + integrator init
+    CDN_OP_ACCEPT = 4,     // update_q + integrator accept
+    CDN_OP_RHS = 5,        // sv <- f_n1 + sv_in
+    CDN_OP_CHORD = 6,      // dx <- LU \ (sv - iVec) with the last factors
+    CDN_OP_GET_I = 7,      // iVec(x)
+    CDN_OP_GET_I_JAC = 8,  // iVec(x) and assembled (unfactored) Jacobian slots
+    CDN_OP_SOLVE = 9       // factor the assembled slots, dx <- LU \ y
+};
+
+struct cdn_opts {
+    double abstol, reltol, maxdelta;
+    double a0;        // integration coefficient (0 in DC)
+    double gmin;      // gmin-stepping conductance (multiplies the Gones pattern)
+    double lambda;    // source-stepping factor (1 = full sources)
+    int maxiter;
+    int errfunc;
+    int use_q;        // 0: DC (currents only); 1: transient (charges too)
+    int im;           // 0 backward Euler, 1 trapezoidal
+};
+
+struct cdn_engine_args {
+    const cdn_plan_dev* plan;   // device copy
+    cdn_opts o;
+    int op;
+    int B;                      // circuit instances in the batch
+    double* x;                  // [B][n] in/out
+    const double* sv_in;        // [n] source vector (shared by the batch)
+    double* ws;                 // [B][ws_total] global state (NULL: shared memory)
+    long ws_stride;
+    // transient
+    int nsamples, first, init_ic, nsrc, nsave, pad_;
+    const int* src_rows;        // [nsrc] rows with a time-dependent source
+    const double* src_val;      // [nsamples][nsrc] summed source value per row
+    const double* src_dc;       // [n] constant part of the source vector
+    const int* save_rows;       // [nsave]
+    double* wave;               // [B][nsamples][nsave]
+    int* iters;                 // [B][nsamples] (TRAN) or [B] (NEWTON)
+    double* res;                // same shape as iters
+    int* status;                // [B]: 0 ok, k > 0 first failed sample, -1 Newton failed
+    double* red;                // GridTeam reduction scratch
+};
+
+// status bits or'ed into the negative range are avoided: singular pivots are
+// reported as non-convergence (the NaN/inf step never passes the test).
+
+// ---- per-instance state ----------------------------------------------------------
+struct Ws {
+    double *x, *dx, *ivec, *sv, *q, *qprev, *dq, *y, *tmp, *lu, *out, *jac;
+    int* piv;
+};
+
+__host__ __device__ inline long ws_doubles(int n, long nlu, long out_size, long jac_size) {
+    return 9L * n + nlu + out_size + jac_size + (n + 1) / 2 + 2;
+}
+
+__device__ inline Ws ws_carve(double* base, int n, long nlu, long out_size, long jac_size) {
+    Ws w;
+    w.x = base; w.dx = w.x + n; w.ivec = w.dx + n; w.sv = w.ivec + n; w.q = w.sv + n;
+    w.qprev = w.q + n; w.dq = w.qprev + n; w.y = w.dq + n; w.tmp = w.y + n; w.lu = w.tmp + n;
+    w.out = w.lu + nlu; w.jac = w.out + out_size;
+    w.piv = (int*)(w.jac + jac_size);
+    return w;
+}
+
+// ---- teams ---------------------------------------------------------------------------
+template <int T>
+struct TileTeam {
+    cg::thread_block_tile<T> tile;
+    static constexpr bool kFlat = true;      // flattened device list
+    __device__ TileTeam() : tile(cg::tiled_partition<T>(cg::this_thread_block())) {}
+    __device__ int rank() const { return tile.thread_rank(); }
+    __device__ int size() const { return T; }
+    __device__ void sync() const { tile.sync(); }
+    __device__ double max(double v) const {
+#pragma unroll
+        for (int o = T / 2; o > 0; o >>= 1) v = fmax(v, tile.shfl_xor(v, o));
+        return v;
+    }
+    __device__ bool all(bool p) const { return tile.all(p); }
+    // largest v, smallest index on ties; NaN never wins
+    __device__ void argmax(double& v, int& i) const {
+#pragma unroll
+        for (int o = T / 2; o > 0; o >>= 1) {
+            const double v2 = tile.shfl_xor(v, o);
+            const int i2 = tile.shfl_xor(i, o);
+            if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+        }
+    }
+};
+
+struct BlockTeam {
+    double* sred;      // shared scratch [64]
+    int* ired;         // shared scratch [33]
+    static constexpr bool kFlat = false;
+    __device__ int rank() const { return threadIdx.x; }
+    __device__ int size() const { return blockDim.x; }
+    __device__ void sync() const { __syncthreads(); }
+    __device__ double max(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if ((threadIdx.x & 31) == 0) sred[w] = v;
+        __syncthreads();
+        double r = sred[0];
+        for (int k = 1; k < nw; ++k) r = fmax(r, sred[k]);
+        __syncthreads();
+        return r;
+    }
+    __device__ bool all(bool p) const { return __syncthreads_and(p) != 0; }
+    __device__ void argmax(double& v, int& i) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+            if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+        }
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if ((threadIdx.x & 31) == 0) { sred[w] = v; ired[w] = i; }
+        __syncthreads();
+        v = sred[0]; i = ired[0];
+        for (int k = 1; k < nw; ++k)
+            if (sred[k] > v || (sred[k] == v && ired[k] < i)) { v = sred[k]; i = ired[k]; }
+        __syncthreads();
+    }
+};
+
+struct GridTeam {
+    cg::grid_group grid;
+    double* sred;      // shared scratch [64]
+    double* gred;      // global scratch [2][gridDim.x] (+ flags)
+    int phase;
+    static constexpr bool kFlat = false;
+    __device__ GridTeam() : grid(cg::this_grid()), phase(0) {}
+    __device__ int rank() const { return blockIdx.x * blockDim.x + threadIdx.x; }
+    __device__ int size() const { return gridDim.x * blockDim.x; }
+    __device__ void sync() const { grid.sync(); }
+    __device__ double max(double v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if ((threadIdx.x & 31) == 0) sred[w] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double r = sred[0];
+            for (int k = 1; k < nw; ++k) r = fmax(r, sred[k]);
+            gred[phase * gridDim.x + blockIdx.x] = r;
+        }
+        grid.sync();
+        double r = -INFINITY;
+        for (int k = threadIdx.x & 31; k < (int)gridDim.x; k += 32)
+            r = fmax(r, __ldcg(gred + phase * gridDim.x + k));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+        phase ^= 1;
+        return r;
+    }
+    __device__ bool all(bool p) { return max(p ? 0.0 : 1.0) == 0.0; }
+    __device__ void argmax(double& v, int& i) {
+        // only used by the dense LU, which is never run grid-wide
+        v = max(v);
+    }
+};
+
+// ---- device evaluation ------------------------------------------------------------
+template <int P>
+struct WsSink {
+    double* out;
+    double* jac;
+    int ld, i, nxin;
+    CDN_HD void put(int slot, const Dual<P>& d) const {
+        out[slot * ld + i] = d.v;
+        if (P > 0) {
+#pragma unroll
+            for (int c = 0; c < P; ++c)
+                if (c < nxin) jac[(slot * nxin + c) * ld + i] = d.d[c];
+        }
+    }
+};
+
+template <int P>
+__device__ __forceinline__ void gather_xin(const cdn_group_dev& G, int i, const double* x,
+                                           Dual<P>* v) {
+#pragma unroll
+    for (int c = 0; c < CDN_MAX_XIN; ++c) {
+        double xv = 0.0;
+        if (c < G.nxin) {
+            const int a = __ldg(G.vpos + c * G.n + i), b = __ldg(G.vneg + c * G.n + i);
+            if (a >= 0) xv += x[a];
+            if (b >= 0) xv -= x[b];
+        }
+        v[c] = make_var<P>(xv, c);
+    }
+}
+
+template <int MODEL, int P>
+__device__ __forceinline__ void eval_model(const cdn_group_dev& G, const PV& p, int i,
+                                           const double* x, const Ws& w) {
+    Dual<P> v[CDN_MAX_XIN];
+    gather_xin<P>(G, i, x, v);
+    WsSink<P> sink;
+    sink.out = w.out + G.out_off; sink.jac = w.jac + G.jac_off;
+    sink.ld = G.n; sink.i = i; sink.nxin = G.nxin;
+    if (MODEL == CDN_MODEL_DIODE) diode_eval(p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_BJT) bjt_eval<P, false>(p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_SVBJT) bjt_eval<P, true>(p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_BSIM3 || MODEL == CDN_MODEL_EKV) mos_eval(MODEL, p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_MESFETC) mesfetc_eval(p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_MEMR) memr_eval(p, G.flags, v, sink);
+}
+
+#define CDN_MS(m) (1 << (m))
+#define CDN_HAS(MS, m) (((MS) >> (m)) & 1)
+
+// one device: instance i of group G of circuit instance b
+template <int MS, bool DERIV>
+__device__ __noinline__ void eval_one(const cdn_group_dev& G, int b, int i, const double* x,
+                                      const Ws& w) {
+    long col = (G.per_inst ? (long)b * G.n : 0L) + i;
+    if (G.pidx) col = __ldg(G.pidx + col);
+    PV p;
+    p.base = G.params + col;
+    p.ld = G.ldp;
+    switch (G.model) {
+    case CDN_MODEL_DIODE:
+        if (CDN_HAS(MS, CDN_MODEL_DIODE)) eval_model<CDN_MODEL_DIODE, DERIV ? 1 : 0>(G, p, i, x, w);
+        break;
+    case CDN_MODEL_BJT:
+        if (CDN_HAS(MS, CDN_MODEL_BJT)) eval_model<CDN_MODEL_BJT, DERIV ? 4 : 0>(G, p, i, x, w);
+        break;
+    case CDN_MODEL_SVBJT:
+        if (CDN_HAS(MS, CDN_MODEL_SVBJT)) eval_model<CDN_MODEL_SVBJT, DERIV ? 4 : 0>(G, p, i, x, w);
+        break;
+    case CDN_MODEL_BSIM3:
+        if (CDN_HAS(MS, CDN_MODEL_BSIM3)) eval_model<CDN_MODEL_BSIM3, DERIV ? 3 : 0>(G, p, i, x, w);
+        break;
+    case CDN_MODEL_EKV:
+        if (CDN_HAS(MS, CDN_MODEL_EKV)) eval_model<CDN_MODEL_EKV, DERIV ? 3 : 0>(G, p, i, x, w);
+        break;
+    case CDN_MODEL_MEMR:
+        if (CDN_HAS(MS, CDN_MODEL_MEMR)) eval_model<CDN_MODEL_MEMR, DERIV ? 2 : 0>(G, p, i, x, w);
+        break;
+    default: break;
+    }
+}
+
+template <int MS, bool DERIV, class Team>
+__device__ __forceinline__ void eval_devices(Team& tm, const cdn_plan_dev& P, int b,
+                                             const double* x, const Ws& w) {
+    if (Team::kFlat) {
+        for (int d = tm.rank(); d < P.ndev; d += tm.size())
+            eval_one<MS, DERIV>(P.groups[__ldg(P.dev_g + d)], b, __ldg(P.dev_i + d), x, w);
+    } else {
+        for (int g = 0; g < P.ngroups; ++g) {
+            const cdn_group_dev& G = P.groups[g];
+            for (int i = tm.rank(); i < G.n; i += tm.size()) eval_one<MS, DERIV>(G, b, i, x, w);
+        }
+    }
+    tm.sync();
+}
+
+// ---- assembly (gather; no atomics) ------------------------------------------------------
+// iVec = G'x + Ti i(x) + a0 Tq q(x) (+ gmin Gones x);  y = lambda*sv - iVec
+template <class Team>
+__device__ __forceinline__ void residual(Team& tm, const cdn_plan_dev& P, const Ws& w,
+                                         const cdn_opts& o) {
+    const double a0 = o.use_q ? o.a0 : 0.0;
+    for (int r = tm.rank(); r < P.n; r += tm.size()) {
+        double acc = 0.0;
+        for (int k = __ldg(P.r_lin_ptr + r); k < __ldg(P.r_lin_ptr + r + 1); ++k) {
+            double g = __ldg(P.r_lin_g + k);
+            if (o.use_q) g += a0 * __ldg(P.r_lin_c + k);
+            if (o.gmin != 0.0) g += o.gmin * __ldg(P.r_lin_gones + k);
+            acc += g * w.x[__ldg(P.r_lin_col + k)];
+        }
+        for (int k = __ldg(P.r_con_ptr + r); k < __ldg(P.r_con_ptr + r + 1); ++k) {
+            const int kind = __ldg(P.r_con_kind + k);
+            const double v = w.out[__ldg(P.r_con_src + k)];
+            if (kind == 1) acc += v;
+            else if (kind == -1) acc -= v;
+            else if (o.use_q) acc += (kind > 0 ? a0 : -a0) * v;
+        }
+        w.ivec[r] = acc;
+        w.y[r] = o.lambda * w.sv[r] - acc;
+    }
+}
+
+// Jacobian slots: G' + Ti J Tcv + a0 Tq Jq Tcv (+ gmin Gones)
+template <class Team>
+__device__ __forceinline__ void assemble(Team& tm, const cdn_plan_dev& P, const Ws& w,
+                                         const cdn_opts& o) {
+    const double a0 = o.use_q ? o.a0 : 0.0;
+    for (int e = tm.rank(); e < P.nlu; e += tm.size()) {
+        double v = __ldg(P.e_g + e);
+        if (o.use_q) v += a0 * __ldg(P.e_c + e);
+        if (o.gmin != 0.0) v += o.gmin * __ldg(P.e_gones + e);
+        for (int k = __ldg(P.e_con_ptr + e); k < __ldg(P.e_con_ptr + e + 1); ++k) {
+            const int kind = __ldg(P.e_con_kind + k);
+            const double j = w.jac[__ldg(P.e_con_src + k)];
+            if (kind == 1) v += j;
+            else if (kind == -1) v -= j;
+            else if (o.use_q) v += (kind > 0 ? a0 : -a0) * j;
+        }
+        w.lu[e] = v;
+    }
+}
+
+// q = C x + Tq q(x)   (device outputs must be current)
+template <class Team>
+__device__ __forceinline__ void charge(Team& tm, const cdn_plan_dev& P, const Ws& w) {
+    for (int r = tm.rank(); r < P.n; r += tm.size()) {
+        double acc = 0.0;
+        for (int k = __ldg(P.r_lin_ptr + r); k < __ldg(P.r_lin_ptr + r + 1); ++k)
+            acc += __ldg(P.r_lin_c + k) * w.x[__ldg(P.r_lin_col + k)];
+        for (int k = __ldg(P.r_con_ptr + r); k < __ldg(P.r_con_ptr + r + 1); ++k) {
+            const int kind = __ldg(P.r_con_kind + k);
+            if (kind == 2) acc += w.out[__ldg(P.r_con_src + k)];
+            else if (kind == -2) acc -= w.out[__ldg(P.r_con_src + k)];
+        }
+        w.q[r] = acc;
+    }
+}
+
+// ---- dense LU with partial pivoting (LAPACK getrf/getrs semantics) ----------------------
+template <class Team>
+__device__ __forceinline__ void dense_factor(Team& tm, double* a, int* piv, int n) {
+    for (int k = 0; k < n; ++k) {
+        double best = -1.0;
+        int bi = n;
+        for (int i = k + tm.rank(); i < n; i += tm.size()) {
+            const double v = fabs(a[i * n + k]);
+            if (v > best) { best = v; bi = i; }
+        }
+        tm.argmax(best, bi);
+        if (bi >= n) bi = k;                      // column of NaNs: keep the row
+        if (tm.rank() == 0) piv[k] = bi;
+        if (bi != k)
+            for (int j = tm.rank(); j < n; j += tm.size()) {
+                const double t = a[k * n + j];
+                a[k * n + j] = a[bi * n + j];
+                a[bi * n + j] = t;
+            }
+        tm.sync();
+        const double pinv = 1.0 / a[k * n + k];
+        for (int i = k + 1 + tm.rank(); i < n; i += tm.size()) a[i * n + k] *= pinv;
+        tm.sync();
+        const int m = n - k - 1;
+        for (int idx = tm.rank(); idx < m * m; idx += tm.size()) {
+            const int i = k + 1 + idx / m, j = k + 1 + idx % m;
+            a[i * n + j] -= a[i * n + k] * a[k * n + j];
+        }
+        tm.sync();
+    }
+}
+
+// b <- A^{-1} b
+template <class Team>
+__device__ __forceinline__ void dense_solve(Team& tm, const double* a, const int* piv,
+                                            double* b, int n) {
+    if (tm.rank() == 0)
+        for (int k = 0; k < n; ++k) {
+            const int p = piv[k];
+            if (p != k) { const double t = b[k]; b[k] = b[p]; b[p] = t; }
+        }
+    tm.sync();
+    for (int k = 0; k < n - 1; ++k) {
+        const double bk = b[k];
+        for (int i = k + 1 + tm.rank(); i < n; i += tm.size()) b[i] -= a[i * n + k] * bk;
+        tm.sync();
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        if (tm.rank() == 0) b[k] /= a[k * n + k];
+        tm.sync();
+        const double bk = b[k];
+        for (int i = tm.rank(); i < k; i += tm.size()) b[i] -= a[i * n + k] * bk;
+        tm.sync();
+    }
+}
+
+// ---- sparse LU: static pivot order, entry-wise Crout by dependency level ----------------
+template <class Team>
+__device__ __forceinline__ void sparse_factor(Team& tm, const cdn_plan_dev& P, double* lu) {
+    for (int l = 0; l < P.nlev_f; ++l) {
+        const int e0 = __ldg(P.f_lvl_ptr + l), e1 = __ldg(P.f_lvl_ptr + l + 1);
+        for (int e = e0 + tm.rank(); e < e1; e += tm.size()) {
+            double v = lu[e];
+            for (int t = __ldg(P.e_term_ptr + e); t < __ldg(P.e_term_ptr + e + 1); ++t)
+                v -= lu[__ldg(P.e_term_l + t)] * lu[__ldg(P.e_term_u + t)];
+            const int pv = __ldg(P.e_piv + e);
+            if (pv >= 0) v /= lu[pv];
+            lu[e] = v;
+        }
+        tm.sync();
+    }
+}
+
+// dx <- A^{-1} y   (y in original row order; tmp = permuted work vector)
+template <class Team>
+__device__ __forceinline__ void sparse_solve(Team& tm, const cdn_plan_dev& P, const double* lu,
+                                             const double* y, double* tmp, double* dx) {
+    for (int l = 0; l < P.nlev_l; ++l) {
+        const int r0 = __ldg(P.l_lvl_ptr + l), r1 = __ldg(P.l_lvl_ptr + l + 1);
+        for (int q = r0 + tm.rank(); q < r1; q += tm.size()) {
+            const int i = __ldg(P.l_rows + q);
+            double v = y[__ldg(P.rowmap + i)];
+            for (int k = __ldg(P.l_ptr + i); k < __ldg(P.l_ptr + i + 1); ++k)
+                v -= lu[__ldg(P.l_slot + k)] * tmp[__ldg(P.l_col + k)];
+            tmp[i] = v;
+        }
+        tm.sync();
+    }
+    for (int l = 0; l < P.nlev_u; ++l) {
+        const int r0 = __ldg(P.u_lvl_ptr + l), r1 = __ldg(P.u_lvl_ptr + l + 1);
+        for (int q = r0 + tm.rank(); q < r1; q += tm.size()) {
+            const int i = __ldg(P.u_rows + q);
+            double v = tmp[i];
+            for (int k = __ldg(P.u_ptr + i); k < __ldg(P.u_ptr + i + 1); ++k)
+                v -= lu[__ldg(P.u_slot + k)] * tmp[__ldg(P.u_col + k)];
+            v /= lu[__ldg(P.u_diag + i)];
+            tmp[i] = v;
+            dx[__ldg(P.colmap + i)] = v;
+        }
+        tm.sync();
+    }
+}
+
+template <class Team>
+__device__ __forceinline__ void factor(Team& tm, const cdn_plan_dev& P, const Ws& w) {
+    if (P.dense) dense_factor(tm, w.lu, w.piv, P.n);
+    else sparse_factor(tm, P, w.lu);
+}
+
+// dx <- J^{-1} y  (y is consumed)
+template <class Team>
+__device__ __forceinline__ void lusolve(Team& tm, const cdn_plan_dev& P, const Ws& w) {
+    if (P.dense) {
+        dense_solve(tm, w.lu, w.piv, w.y, P.n);
+        for (int r = tm.rank(); r < P.n; r += tm.size()) w.dx[r] = w.y[r];
+        tm.sync();
+    } else {
+        sparse_solve(tm, P, w.lu, w.y, w.tmp, w.dx);
+    }
+}
+
+// ---- damped Newton (fsolve.py:59-128) -------------------------------------------------
+// Returns the iteration count; *ok tells whether the tolerances were met.
+// On return w.ivec holds the residual evaluated at the LAST-BUT-ONE iterate and
+// w.lu the factors of the Jacobian there -- exactly what the reference's chord
+// predictor re-uses (tran.py:181) -- unless errfunc is set.
+template <int MS, class Team>
+__device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, const Ws& w,
+                                      const cdn_opts& o, double* res_out, bool* ok) {
+    double res = 0.0;
+    bool success = false;
+    int it = 0;
+    for (; it < o.maxiter; ++it) {
+        eval_devices<MS, true>(tm, P, b, w.x, w);
+        assemble(tm, P, w, o);
+        residual(tm, P, w, o);
+        tm.sync();
+        factor(tm, P, w);
+        lusolve(tm, P, w);
+        double m = 0.0;
+        for (int r = tm.rank(); r < P.n; r += tm.size()) m = fmax(m, fabs(w.dx[r]));
+        m = tm.max(m);
+        const bool damp = m > o.maxdelta;
+        const double scale = damp ? o.maxdelta / m : 1.0;
+        bool conv = true;
+        for (int r = tm.rank(); r < P.n; r += tm.size()) {
+            double d = w.dx[r];
+            if (damp) d *= scale;
+            const double xo = w.x[r], xn = xo + d;
+            conv = conv && (fabs(d) < o.reltol * fmax(fabs(xo), fabs(xn)) + o.abstol);
+            w.x[r] = xn;
+        }
+        res = damp ? m * scale : m;
+        const bool n1 = tm.all(conv);      // (also orders the x update)
+        tm.sync();
+        bool n2 = true;
+        if (n1 && o.errfunc) {
+            eval_devices<MS, false>(tm, P, b, w.x, w);
+            residual(tm, P, w, o);
+            tm.sync();
+            double ef = 0.0;
+            for (int r = tm.rank(); r < P.n; r += tm.size()) ef = fmax(ef, fabs(w.y[r]));
+            ef = tm.max(ef);
+            n2 = ef < o.abstol;
+            res = fmax(ef, res);
+        }
+        if (n1 && n2) { success = true; ++it; break; }
+    }
+    *res_out = res;
+    *ok = success;
+    return it;
+}
+
+// q(x) with a values-only device sweep (nodalSP.py:719-733)
+template <int MS, class Team>
+__device__ __forceinline__ void update_q(Team& tm, const cdn_plan_dev& P, int b, const Ws& w) {
+    eval_devices<MS, false>(tm, P, b, w.x, w);
+    charge(tm, P, w);
+    tm.sync();
+}
+
+template <class Team>
+__device__ __forceinline__ void integ_init(Team& tm, const cdn_plan_dev& P, const Ws& w) {
+    for (int r = tm.rank(); r < P.n; r += tm.size()) { w.qprev[r] = w.q[r]; w.dq[r] = 0.0; }
+    tm.sync();
+}
+
+// integration.py:36-38 (BE), :83-91 (trapezoidal)
+template <class Team>
+__device__ __forceinline__ void integ_accept(Team& tm, const cdn_plan_dev& P, const Ws& w,
+                                             const cdn_opts& o) {
+    for (int r = tm.rank(); r < P.n; r += tm.size()) {
+        const double q = w.q[r];
+        if (o.im == 1) w.dq[r] = -w.dq[r] + o.a0 * (q - w.qprev[r]);
+        w.qprev[r] = q;
+    }
+    tm.sync();
+}
+
+// sv = f_n1() + s   (integration.py:47-49, :93-97; nodalSP.py:792-802)
+template <class Team>
+__device__ __forceinline__ void make_rhs(Team& tm, const cdn_plan_dev& P, const Ws& w,
+                                         const cdn_opts& o, const double* s_dense,
+                                         int nsrc, const int* src_rows, const double* src_val) {
+    for (int r = tm.rank(); r < P.n; r += tm.size()) {
+        double f = o.a0 * w.qprev[r];
+        if (o.im == 1) f += w.dq[r];
+        w.sv[r] = f + (s_dense ? __ldg(s_dense + r) : 0.0);
+    }
+    tm.sync();
+    for (int k = tm.rank(); k < nsrc; k += tm.size()) w.sv[__ldg(src_rows + k)] += __ldg(src_val + k);
+    if (nsrc) tm.sync();
+}
+
+// dx = LU \ (sv - iVec) with the factors and the residual left by the last
+// Newton iteration (nodalSP.py:345-354)
+template <class Team>
+__device__ __forceinline__ void chord(Team& tm, const cdn_plan_dev& P, const Ws& w,
+                                      const cdn_opts& o) {
+    for (int r = tm.rank(); r < P.n; r += tm.size()) w.y[r] = w.sv[r] - w.ivec[r];
+    tm.sync();
+    lusolve(tm, P, w);
+}
+
+// ---- one circuit instance, one operation ------------------------------------------------
+template <int MS, class Team>
+__device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
+                                             const cdn_plan_dev& P, int b, const Ws& w) {
+    const cdn_opts& o = A.o;
+    const int n = P.n;
+    switch (A.op) {
+    case CDN_OP_NEWTON: {
+        for (int r = tm.rank(); r < n; r += tm.size()) w.sv[r] = __ldg(A.sv_in + r);
+        tm.sync();
+        double res; bool ok;
+        const int it = newton<MS>(tm, P, b, w, o, &res, &ok);
+        if (tm.rank() == 0) {
+            A.iters[b] = it; A.res[b] = res; A.status[b] = ok ? 0 : -1;
+        }
+        break;
+    }
+    case CDN_OP_TRAN: {
+        if (A.init_ic) {                         // set_IC (nodalSP.py:666-696)
+            update_q<MS>(tm, P, b, w);
+            integ_init(tm, P, w);
+        }
+        int status = 0;
+        for (int i = A.first; i < A.nsamples; ++i) {
+            update_q<MS>(tm, P, b, w);           // accept(xOld)
+            integ_accept(tm, P, w, o);
+            make_rhs(tm, P, w, o, A.src_dc, A.nsrc, A.src_rows, A.src_val + (long)i * A.nsrc);
+            if (i > 1) {                         // chord predictor (tran.py:181)
+                chord(tm, P, w, o);
+                for (int r = tm.rank(); r < n; r += tm.size()) w.x[r] += w.dx[r];
+                tm.sync();
+            }
+            double res; bool ok;
+            const int it = newton<MS>(tm, P, b, w, o, &res, &ok);
+            const long at = (long)b * A.nsamples + i;
+            if (tm.rank() == 0) { A.iters[at] = it; A.res[at] = res; }
+            if (!ok) { status = i; break; }
+            for (int k = tm.rank(); k < A.nsave; k += tm.size())
+                A.wave[at * A.nsave + k] = w.x[__ldg(A.save_rows + k)];
+        }
+        if (tm.rank() == 0) A.status[b] = status;
+        break;
+    }
+    case CDN_OP_UPDATE_Q:
+        update_q<MS>(tm, P, b, w);
+        break;
+    case CDN_OP_SET_IC:
+        update_q<MS>(tm, P, b, w);
+        integ_init(tm, P, w);
+        break;
+    case CDN_OP_ACCEPT:
+        update_q<MS>(tm, P, b, w);
+        integ_accept(tm, P, w, o);
+        break;
+    case CDN_OP_RHS:
+        make_rhs(tm, P, w, o, A.sv_in, 0, nullptr, nullptr);
+        break;
+    case CDN_OP_CHORD:
+        chord(tm, P, w, o);
+        break;
+    case CDN_OP_GET_I:
+        eval_devices<MS, false>(tm, P, b, w.x, w);
+        residual(tm, P, w, o);
+        tm.sync();
+        break;
+    case CDN_OP_GET_I_JAC:
+        eval_devices<MS, true>(tm, P, b, w.x, w);
+        assemble(tm, P, w, o);
+        residual(tm, P, w, o);
+        tm.sync();
+        break;
+    case CDN_OP_SOLVE:
+        factor(tm, P, w);
+        lusolve(tm, P, w);
+        break;
+    default: break;
+    }
+}
+
+// ---- kernels --------------------------------------------------------------------------------
+// Batches of small circuits: T lanes per instance; the state lives in shared
+// memory unless the caller wants it kept (A.ws != NULL).
+template <int MS, int T>
+__global__ void __launch_bounds__(128)
+engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
+    extern __shared__ double smem[];
+    const cdn_plan_dev& P = *A.plan;
+    TileTeam<T> tm;
+    const int tiles = blockDim.x / T;
+    const int tile_id = threadIdx.x / T;
+    const long per = ws_doubles(P.n, P.nlu, P.dev_out_size, P.dev_jac_size);
+    for (int b = blockIdx.x * tiles + tile_id; b < A.B; b += gridDim.x * tiles) {
+        double* base = A.ws ? A.ws + (long)b * A.ws_stride : smem + (long)tile_id * per;
+        const Ws w = ws_carve(base, P.n, P.nlu, P.dev_out_size, P.dev_jac_size);
+        if (!A.ws || A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN) {
+            for (int r = tm.rank(); r < P.n; r += T) w.x[r] = A.x[(long)b * P.n + r];
+            tm.sync();
+        }
+        run_instance<MS>(tm, A, P, b, w);
+        tm.sync();
+        for (int r = tm.rank(); r < P.n; r += T) A.x[(long)b * P.n + r] = w.x[r];
+        tm.sync();
+    }
+}
+
+// One CTA per circuit instance, state in global memory.
+template <int MS, int TPB>
+__global__ void __launch_bounds__(TPB)
+engine_block_kernel(const __grid_constant__ cdn_engine_args A) {
+    __shared__ double sred[64];
+    __shared__ int ired[64];
+    const cdn_plan_dev& P = *A.plan;
+    BlockTeam tm;
+    tm.sred = sred; tm.ired = ired;
+    for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+        const Ws w = ws_carve(A.ws + (long)b * A.ws_stride, P.n, P.nlu, P.dev_out_size,
+                              P.dev_jac_size);
+        if (A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN) {
+            for (int r = tm.rank(); r < P.n; r += tm.size()) w.x[r] = A.x[(long)b * P.n + r];
+            tm.sync();
+        }
+        run_instance<MS>(tm, A, P, b, w);
+        tm.sync();
+        for (int r = tm.rank(); r < P.n; r += tm.size()) A.x[(long)b * P.n + r] = w.x[r];
+        tm.sync();
+    }
+}
+
+// The whole (cooperative) grid on one circuit.
+template <int MS, int TPB>
+__global__ void __launch_bounds__(TPB)
+engine_grid_kernel(const __grid_constant__ cdn_engine_args A) {
+    __shared__ double sred[64];
+    const cdn_plan_dev& P = *A.plan;
+    GridTeam tm;
+    tm.sred = sred; tm.gred = A.red;
+    const Ws w = ws_carve(A.ws, P.n, P.nlu, P.dev_out_size, P.dev_jac_size);
+    if (A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN) {
+        for (int r = tm.rank(); r < P.n; r += tm.size()) w.x[r] = A.x[r];
+        tm.sync();
+    }
+    run_instance<MS>(tm, A, P, 0, w);
+    tm.sync();
+    for (int r = tm.rank(); r < P.n; r += tm.size()) A.x[r] = w.x[r];
+}

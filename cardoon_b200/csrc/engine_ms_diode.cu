@@ -1,0 +1,8 @@
+// Newton-engine kernels instantiated for the model set CDN_MS_DIODE
+// (one translation unit per set keeps register allocation and compile time
+// of the light circuits independent of the heavy models).
+#include "engine_launch.cuh"
+
+cudaError_t cdn_launch_ms_diode(const cdn_engine_args& A, const cdn_launch_cfg& c, cudaStream_t st) {
+    return launch_engine<CDN_MS_DIODE>(A, c, st);
+}

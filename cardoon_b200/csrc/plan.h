@@ -18,7 +18,9 @@ struct cdn_group_dev {
     int pad_;
     const double* params;     // [npar][ldp] device, owned by caller
     long ldp;
-    const int* pidx;          // [n] column of each instance in params, or NULL
+    const int* pidx;          // column of each instance in params, or NULL
+    int per_inst;             // 1: every circuit instance b of a batch has its
+    int pad2_;                //    own columns (b*n + i); 0: shared by the batch
     const int* vpos;          // [nxin][n] row of + control terminal (-1 gnd)
     const int* vneg;          // [nxin][n]
     long out_off;             // offset of this group's out[nout][n] in dev_out
@@ -30,6 +32,11 @@ struct cdn_plan_dev {
     int nlu;                  // stored entries of L+U (static pattern)
     int nlev_f, nlev_l, nlev_u;
     int ngroups;
+    int dense;                // 1: slots are a dense n*n row-major matrix
+    int ndev;                 // nonlinear devices of one circuit instance
+    int max_terms;
+    const int* dev_g;         // [ndev] group of device d (flattened list)
+    const int* dev_i;         // [ndev] index inside its group
     // ---- factorisation: entries ("slots") numbered in level order --------
     const int* f_lvl_ptr;     // [nlev_f+1]
     const int* e_term_ptr;    // [nlu+1]   Crout terms of entry e

@@ -26,6 +26,8 @@
 #include <cmath>
 #include <cstring>
 #include <cstdint>
+#include <map>
+#include <string>
 
 namespace {
 
@@ -150,12 +152,16 @@ struct cdn_plan {
         long f_lvl_ptr, e_term_ptr, e_term_l, e_term_u, e_piv, e_g, e_c, e_gones, e_con_ptr,
             e_con_src, e_con_kind, l_lvl_ptr, l_rows, l_ptr, l_col, l_slot, u_lvl_ptr, u_rows,
             u_ptr, u_col, u_slot, u_diag, rowmap, colmap, r_lin_ptr, r_lin_col, r_lin_g,
-            r_lin_c, r_lin_gones, r_con_ptr, r_con_src, r_con_kind;
+            r_lin_c, r_lin_gones, r_con_ptr, r_con_src, r_con_kind, dev_g, dev_i;
         long gv[CDN_MAX_GROUPS][2];
     } off;
     long nterms, ncon, nnzA;
     bool bound;
+    bool dirty;
+    cdn_plan_dev* dev_struct;     // device copy of `dev`
     int max_terms, max_con;
+    ivec slot_row, slot_col;      // original (row, unknown) of every slot
+    std::map<std::string, std::pair<long, long> > reg;   // name -> (offset, count) in staging
 };
 
 static int find_slot(const ivec& rptr, const ivec& rcol, const ivec& rslot, int i, int j) {
@@ -174,6 +180,8 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     cdn_plan* P = new cdn_plan();
     P->ctx = ctx;
     P->bound = false;
+    P->dirty = true;
+    P->dev_struct = nullptr;
     memset(&P->dev, 0, sizeof(P->dev));
 
     // ---- permutation from the matching: row r of A becomes row mrow[r] ----------
@@ -261,7 +269,17 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
         // subset ever uses
         NDOrder nd(gr, 2);
         for (int v : hubs) nd.setid[v] = -1000000;
-        if (c->ordering == 1) {
+        if (c->ordering == 3 && c->colorder) {
+            // explicit elimination order (pivot sequence validated on the host)
+            hubs.clear();
+            std::vector<char> seen(n, 0);
+            for (int j = 0; j < n; ++j) {
+                const int v = c->colorder[j];
+                if (v < 0 || v >= n || seen[v]) { delete P; return cdn_fail(ctx, CDN_ERR_ARG, "plan: colorder is not a permutation"); }
+                seen[v] = 1;
+                nd.order.push_back(v);
+            }
+        } else if (c->ordering == 1) {
             for (int v : normal) nd.order.push_back(v);       // natural (debug)
         } else {
             nd.run(normal);
@@ -404,6 +422,17 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     for (long e = 0; e < nlu; ++e) rslot[e] = slot[e];
     }  // !dense
 
+    P->slot_row.assign(nlu, 0); P->slot_col.assign(nlu, 0);
+    {
+        ivec rowmap0(n), colmap0(n);
+        for (int r = 0; r < n; ++r) rowmap0[ip[mrow[r]]] = r;
+        for (int col = 0; col < n; ++col) colmap0[ip[col]] = col;
+        for (int i = 0; i < n; ++i)
+            for (int q = rptr[i]; q < rptr[i + 1]; ++q) {
+                P->slot_row[rslot[q]] = rowmap0[i];
+                P->slot_col[rslot[q]] = colmap0[rcol[q]];
+            }
+    }
     // ---- 7. linear parts per slot -----------------------------------------------------------
     std::vector<double> e_g(nlu, 0.0), e_c(nlu, 0.0), e_gones(nlu, 0.0);
     auto slot_of = [&](int r, int col) { return find_slot(rptr, rcol, rslot, ip[mrow[r]], ip[col]); };
@@ -514,7 +543,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     }
     for (int i = n - 1; i >= 0; --i) {
         int q = diag_id(i) + 1, w = u_ptr[i], l = 0;
-        for (; q < rptr[i + 1]; ++q, ++w) {
+        for (; !dense && q < rptr[i + 1]; ++q, ++w) {
             u_col[w] = rcol[q]; u_slot[w] = rslot[q];
             l = std::max(l, levu[rcol[q]] + 1);
         }
@@ -540,19 +569,50 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     // ---- pack ---------------------------------------------------------------------------------------
     std::vector<char>& B = P->staging;
     cdn_plan::Off& O = P->off;
-    O.f_lvl_ptr = put(B, f_lvl_ptr); O.e_term_ptr = put(B, e_term_ptr);
-    O.e_term_l = put(B, e_term_l); O.e_term_u = put(B, e_term_u); O.e_piv = put(B, e_piv);
-    O.e_g = put(B, e_g); O.e_c = put(B, e_c); O.e_gones = put(B, e_gones);
-    O.e_con_ptr = put(B, e_con_ptr); O.e_con_src = put(B, e_con_src); O.e_con_kind = put(B, e_con_kind);
-    O.l_lvl_ptr = put(B, l_lvl_ptr); O.l_rows = put(B, l_rows); O.l_ptr = put(B, l_ptr);
-    O.l_col = put(B, l_col); O.l_slot = put(B, l_slot);
-    O.u_lvl_ptr = put(B, u_lvl_ptr); O.u_rows = put(B, u_rows); O.u_ptr = put(B, u_ptr);
-    O.u_col = put(B, u_col); O.u_slot = put(B, u_slot); O.u_diag = put(B, u_diag);
-    O.rowmap = put(B, rowmap); O.colmap = put(B, colmap);
-    O.r_lin_ptr = put(B, r_lin_ptr); O.r_lin_col = put(B, r_lin_col); O.r_lin_g = put(B, r_lin_g);
-    O.r_lin_c = put(B, r_lin_c); O.r_lin_gones = put(B, r_lin_gones);
-    O.r_con_ptr = put(B, r_con_ptr); O.r_con_src = put(B, r_con_src); O.r_con_kind = put(B, r_con_kind);
+#define PUT(name) do { O.name = put(B, name); P->reg[#name] = std::make_pair(O.name, (long)name.size()); } while (0)
+    PUT(f_lvl_ptr);
+    PUT(e_term_ptr);
+    PUT(e_term_l);
+    PUT(e_term_u);
+    PUT(e_piv);
+    PUT(e_g);
+    PUT(e_c);
+    PUT(e_gones);
+    PUT(e_con_ptr);
+    PUT(e_con_src);
+    PUT(e_con_kind);
+    PUT(l_lvl_ptr);
+    PUT(l_rows);
+    PUT(l_ptr);
+    PUT(l_col);
+    PUT(l_slot);
+    PUT(u_lvl_ptr);
+    PUT(u_rows);
+    PUT(u_ptr);
+    PUT(u_col);
+    PUT(u_slot);
+    PUT(u_diag);
+    PUT(rowmap);
+    PUT(colmap);
+    PUT(r_lin_ptr);
+    PUT(r_lin_col);
+    PUT(r_lin_g);
+    PUT(r_lin_c);
+    PUT(r_lin_gones);
+    PUT(r_con_ptr);
+    PUT(r_con_src);
+    PUT(r_con_kind);
+    {
+        ivec dg, di;
+        for (int g = 0; g < c->ngroups; ++g)
+            for (int i = 0; i < c->groups[g].n; ++i) { dg.push_back(g); di.push_back(i); }
+        ivec& dev_g = dg; ivec& dev_i = di;
+        PUT(dev_g); PUT(dev_i);
+        P->dev.ndev = (int)dg.size();
+    }
     cdn_plan_dev& D = P->dev;
+    D.dense = dense ? 1 : 0;
+    D.max_terms = P->max_terms;
     D.n = n; D.nlu = (int)nlu; D.nlev_f = nlev_f; D.nlev_l = nlev_l; D.nlev_u = nlev_u;
     D.ngroups = c->ngroups;
     D.dev_out_size = out_size; D.dev_jac_size = jac_size;
@@ -570,7 +630,9 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     return CDN_OK;
 }
 
-extern "C" long cdn_plan_bytes(cdn_plan* P) { return P ? (long)P->staging.size() + 256 : 0; }
+extern "C" long cdn_plan_bytes(cdn_plan* P) {
+    return P ? (long)P->staging.size() + 512 + (long)sizeof(cdn_plan_dev) + 256 : 0;
+}
 
 // info[0..9] = n, nlu, nlev_f, nlev_l, nlev_u, nterms, ncon, nnzA, max_terms, max_con
 extern "C" int cdn_plan_info(cdn_plan* P, long* info) {
@@ -586,7 +648,8 @@ extern "C" int cdn_plan_bind(cdn_plan* P, void* dev_ws, long bytes, void* stream
     if (!P || !dev_ws) return CDN_ERR_ARG;
     cdn_ctx* ctx = P->ctx;
     char* base = (char*)(((uintptr_t)dev_ws + 255) / 256 * 256);
-    if ((long)(base - (char*)dev_ws) + (long)P->staging.size() > bytes)
+    const long struct_off = ((long)P->staging.size() + 255) / 256 * 256;
+    if ((long)(base - (char*)dev_ws) + struct_off + (long)sizeof(cdn_plan_dev) > bytes)
         return cdn_fail(ctx, CDN_ERR_ARG, "plan_bind: workspace too small");
     CDN_CUDA(ctx, cudaMemcpyAsync(base, P->staging.data(), P->staging.size(),
                                   cudaMemcpyHostToDevice, (cudaStream_t)stream));
@@ -603,21 +666,43 @@ extern "C" int cdn_plan_bind(cdn_plan* P, void* dev_ws, long bytes, void* stream
     BIND(r_lin_ptr, int); BIND(r_lin_col, int); BIND(r_lin_g, double); BIND(r_lin_c, double);
     BIND(r_lin_gones, double); BIND(r_con_ptr, int); BIND(r_con_src, int);
     BIND(r_con_kind, signed char);
+    BIND(dev_g, int); BIND(dev_i, int);
 #undef BIND
     for (int g = 0; g < D.ngroups; ++g) {
         D.groups[g].vpos = (const int*)(base + O.gv[g][0]);
         D.groups[g].vneg = (const int*)(base + O.gv[g][1]);
     }
+    P->dev_struct = (cdn_plan_dev*)(base + struct_off);
     P->bound = true;
+    P->dirty = true;
     return CDN_OK;
 }
 
 extern "C" int cdn_plan_set_group_params(cdn_plan* P, int g, const double* params, long ldp,
-                                         const int* pidx) {
+                                         const int* pidx, int per_inst) {
     if (!P || g < 0 || g >= P->dev.ngroups) return CDN_ERR_ARG;
     P->dev.groups[g].params = params;
     P->dev.groups[g].ldp = ldp;
     P->dev.groups[g].pidx = pidx;
+    P->dev.groups[g].per_inst = per_inst;
+    P->dirty = true;
+    return CDN_OK;
+}
+
+extern "C" int cdn_plan_slot_coords(cdn_plan* P, int* rows, int* cols) {
+    if (!P || !rows || !cols) return CDN_ERR_ARG;
+    memcpy(rows, P->slot_row.data(), P->slot_row.size() * sizeof(int));
+    memcpy(cols, P->slot_col.data(), P->slot_col.size() * sizeof(int));
+    return CDN_OK;
+}
+
+// host copy of one packed index/value array by field name (tests, tooling)
+extern "C" int cdn_plan_array(cdn_plan* P, const char* name, const void** ptr, long* count) {
+    if (!P || !name || !ptr || !count) return CDN_ERR_ARG;
+    auto it = P->reg.find(name);
+    if (it == P->reg.end()) return CDN_ERR_ARG;
+    *ptr = P->staging.data() + it->second.first;
+    *count = it->second.second;
     return CDN_OK;
 }
 
@@ -627,5 +712,17 @@ extern "C" int cdn_plan_free(cdn_plan* P) {
     return CDN_OK;
 }
 
-const cdn_plan_dev* cdn_plan_device_view(cdn_plan* P) { return P && P->bound ? &P->dev : nullptr; }
+const cdn_plan_dev* cdn_plan_host_view(cdn_plan* P) { return P && P->bound ? &P->dev : nullptr; }
+
+int cdn_plan_sync_device(cdn_plan* P, cudaStream_t st, const cdn_plan_dev** out) {
+    if (!P || !P->bound) return CDN_ERR_STATE;
+    if (P->dirty) {
+        // pageable source: the copy is staged before the call returns
+        CDN_CUDA(P->ctx, cudaMemcpyAsync(P->dev_struct, &P->dev, sizeof(cdn_plan_dev),
+                                         cudaMemcpyHostToDevice, st));
+        P->dirty = false;
+    }
+    *out = P->dev_struct;
+    return CDN_OK;
+}
 cdn_ctx* cdn_plan_ctx(cdn_plan* P) { return P->ctx; }

@@ -1,0 +1,197 @@
+"""
+GPU parity of the device-resident Newton engine
+against the oracle, through the reference-facing ``nd`` interface
+(cardoon_b200.analyses.nodalCUDA) and therefore the C ABI
+(cdn_plan_create / cdn_engine_run).
+
+Bars (BASELINE.json north_star): operating-point unknowns within 1e-9
+relative / 1e-12 absolute, Newton iteration counts within +-1, transient
+waveforms within the reference's own reltol/abstol at every accepted sample.
+"""
+import numpy as np
+import pytest
+
+from tests import support as S
+from cardoon_b200.analyses import nodalCUDA as nd
+from cardoon_b200.analyses.fsolve import solve
+from cardoon_b200.analyses.integration import Trapezoidal, BEuler
+from cardoon_b200.globalVars import glVar
+from oracle import nodal_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def run_op(ckt):
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    x0 = dc.get_guess()
+    sV = dc.get_source()
+    return solve(x0, sV, dc.convergence_helpers), dc
+
+
+def check_op(x, ref_x):
+    err = np.abs(x - ref_x)
+    assert np.all(err < 1e-9 * np.abs(ref_x) + 1e-12), \
+        'max err {0:g}'.format(err.max())
+
+
+def test_op_bias_npn_kat(lib):
+    """doc/usage.rst:48-79: 17 iterations, 12-digit node voltages."""
+    ckt, _ = S.load_circuit(S.net('bias_npn.net'))
+    (x, res, it), dc = run_op(ckt)
+    ref = R.run_op(ckt, glVar)
+    assert abs(it - ref['iterations']) <= 1 and abs(it - 17) <= 1
+    check_op(x, ref['x'])
+    dc.save_OP(x)
+    kat = {'1': 3.49950994522, '10': 11.9158367321, '2': 0.800179840214,
+           '3': 10.0}
+    for name, v in kat.items():
+        assert abs(ckt.termDict[name].nD_vOP - v) < 2e-11 * abs(v)
+    assert abs(res - ref['res']) < 1e-6 * abs(ref['res']) + 1e-12
+
+
+@pytest.mark.parametrize('deck', ['ring_bsim3.net', 'oscillator.net',
+                                  'ring_osc_ahkab.net', 'memristor.net',
+                                  'rctransient.net', 'soliton.net',
+                                  'inverter_chain_bsim.net'])
+def test_op_matches_oracle(lib, deck):
+    ckt, queue = S.load_circuit(S.net(deck))
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    tran = nd.TransientNodal(ckt, Trapezoidal())
+    x0 = dc.get_guess()
+    sV = tran.get_source(0.).copy()
+    x, res, it = solve(x0, sV, dc.convergence_helpers)
+    idx = R.prepare(ckt)
+    rdc = R.RefDC(ckt, idx, R.Options(glVar))
+    rtr = R.RefTran(ckt, idx, R.Options(glVar), R.Trapezoidal())
+    xr, resr, itr = R.solve(rdc.get_guess(), rtr.get_source(0.), rdc.helpers)
+    assert abs(it - itr) <= 1, (it, itr)
+    check_op(x, xr)
+
+
+def tran_both(deck, max_samples=None):
+    ckt, queue = S.load_circuit(S.net(deck))
+    an = [a for a in queue if a.anType == 'tran'][0]
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    imo = Trapezoidal() if an.im == 'trap' else BEuler()
+    tran = nd.TransientNodal(ckt, imo)
+    x, res, it = solve(dc.get_guess(), tran.get_source(0.).copy(),
+                       dc.convergence_helpers)
+    timeVec = np.arange(start=0., stop=an.tstop, step=an.tstep, dtype=float)
+    if max_samples:
+        timeVec = timeVec[:max_samples]
+    rows = list(range(ckt.nD_dimension))
+    wave, iters, resv, status = tran.run(x, timeVec, rows)
+    ref = R.run_tran(ckt, glVar, an.tstop, an.tstep, an.im,
+                     max_samples=len(timeVec))
+    return wave, iters, status, ref, tran
+
+
+def check_tran(wave, iters, status, ref):
+    assert status == 0
+    X = ref['X']
+    assert wave.shape == X.shape
+    err = np.abs(wave - X)
+    tol = glVar.reltol * np.abs(X) + glVar.abstol
+    bad = err > tol
+    assert not bad.any(), 'worst sample {0}, err {1:g}'.format(
+        np.argwhere(bad)[0], (err / tol).max())
+    assert np.max(np.abs(iters - ref['iters'])) <= 1, \
+        (iters[:20], ref['iters'][:20])
+    return float((err / tol).max())
+
+
+def test_tran_ring_bsim3(lib):
+    """BASELINE config 3: dense 7x7, 6 mosbsim3, 401 samples (tile team)."""
+    wave, iters, status, ref, tran = tran_both('ring_bsim3.net')
+    assert wave.shape[0] == 401
+    check_tran(wave, iters, status, ref)
+    assert tran.engine.launches == 1      # the whole time loop
+
+
+def test_tran_soliton(lib):
+    """BASELINE config 2: N = 3022 sparse, 47 diodes, 500 samples
+    (block team, level-scheduled static-pivot LU)."""
+    wave, iters, status, ref, tran = tran_both('soliton.net')
+    assert wave.shape == (500, 3022)
+    check_tran(wave, iters, status, ref)
+    assert tran.engine.launches == 1
+    assert not tran.engine.dense
+    # ~1 Newton iteration per step thanks to the chord predictor
+    # (reference doc/design.rst:243-256: 505 solves for 501 steps)
+    assert iters.sum() < 1.2 * len(iters)
+
+
+@pytest.mark.parametrize('deck', ['rctransient.net', 'oscillator.net',
+                                  'ring_osc_ahkab.net', 'memristor.net',
+                                  'inverter_chain_bsim.net'])
+def test_tran_matches_oracle(lib, deck):
+    wave, iters, status, ref, tran = tran_both(deck, max_samples=150)
+    check_tran(wave, iters, status, ref)
+
+
+def test_sparse_engine_on_small_circuit(lib):
+    """Force the sparse static-pivot path and the block team on ring_bsim3;
+    results must agree with the dense tile-team path."""
+    ckt, queue = S.load_circuit(S.net('ring_bsim3.net'))
+    an = queue[0]
+    nd.make_nodal_circuit(ckt)
+    topo = nd.get_topology(ckt)
+    dc = nd.DCNodal(ckt)
+    tran = nd.TransientNodal(ckt, Trapezoidal())
+    x, res, it = solve(dc.get_guess(), tran.get_source(0.).copy(),
+                       dc.convergence_helpers)
+    timeVec = np.arange(0., an.tstop, an.tstep)[:100]
+    src = tran.source_table(timeVec)
+    rows = list(range(topo.n))
+    out = []
+    for dense in (True, False):
+        e = nd.Engine(topo, use_q=True, a0=2. / an.tstep, x_ref=x,
+                      dense=dense)
+        w, iters, resv, status = e.tran(x, src, rows)
+        assert status[0] == 0
+        out.append((w[0], iters[0]))
+    assert np.allclose(out[0][0], out[1][0], rtol=1e-7, atol=1e-9)
+    assert np.max(np.abs(out[0][1] - out[1][1])) <= 1
+
+
+def test_nd_interface_stepwise(lib):
+    """The host-driven nd interface (get_i_Jac / factor_and_solve / accept /
+    get_rhs / get_chord_deltax) reproduces the device-resident loop."""
+    ckt, queue = S.load_circuit(S.net('ring_bsim3.net'))
+    an = queue[0]
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    imo = Trapezoidal()
+    tran = nd.TransientNodal(ckt, imo)
+    x, res, it = solve(dc.get_guess(), tran.get_source(0.).copy(),
+                       dc.convergence_helpers)
+    dc.save_OP(x)
+    # Jacobian handle materialises to the oracle's matrix
+    iVec, Jac = dc.get_i_Jac(x)
+    idx = R.prepare(ckt)
+    rdc = R.RefDC(ckt, idx, R.Options(glVar))
+    iv_r, J_r = rdc.get_i_Jac(x)
+    assert np.allclose(iVec, iv_r, rtol=1e-9, atol=1e-15)
+    assert np.allclose(Jac.toarray(), J_r, rtol=1e-8, atol=1e-14)
+    dx = dc.factor_and_solve(dc.get_source() - iVec, Jac)
+    assert np.allclose(dx, np.linalg.solve(J_r, rdc.get_source() - iv_r),
+                       rtol=1e-6, atol=1e-10)
+    # stepwise transient, host loop as in tran.py:171-206
+    timeVec = np.arange(0., an.tstop, an.tstep)[:30]
+    tran.set_IC(an.tstep)
+    xOld = x.copy()
+    waves = [x.copy()]
+    for i in range(1, len(timeVec)):
+        tran.accept(xOld)
+        sV = tran.get_rhs(timeVec[i]).copy()
+        if i > 1:
+            xOld += tran.get_chord_deltax(sV)
+        xn, res, it = solve(xOld, sV, tran.convergence_helpers)
+        xOld[:] = xn
+        waves.append(xn.copy())
+    ref = R.run_tran(ckt, glVar, an.tstop, an.tstep, an.im, max_samples=30)
+    err = np.abs(np.array(waves) - ref['X'])
+    assert np.all(err < glVar.reltol * np.abs(ref['X']) + glVar.abstol)
