@@ -360,26 +360,331 @@ def cpu_baseline_deveval(inp, nsample=1 << 15, seconds=10.):
 
 
 # ---------------------------------------------------------------------------
+# workload: Monte Carlo of ring_bsim3 transients (SURVEY 8d "M", config 5)
+# ---------------------------------------------------------------------------
+MC_TERMS = ['1', '3', '4']
+
+
+def count_flops(elem, xin, deriv):
+    """Oracle op counter for one eval of ``elem`` (values only: zero tangent
+    lanes)."""
+    from oracle import dual as OD
+    from oracle import models as OM
+    xin = np.asarray(xin, dtype=float)
+    if xin.ndim == 1:
+        xin = xin[:, None]
+    P, n = xin.shape
+    OD.reset_ops()
+    with np.errstate(all='ignore'):
+        if deriv:
+            OM.eval_cqs(elem, OD.seed(xin))
+        else:
+            OM.eval_cqs(elem, [OD.Dual(xin[k].copy(), np.zeros((0, n)))
+                               for k in range(P)])
+    return float(OD.OPS['flop']), float(OD.OPS['trans'])
+
+
+def mc_setup(lib=None):
+    from tests import support as S
+    from cardoon_b200.analyses import mc
+    ckt, queue = S.load_circuit(S.net('ring_bsim3.net'))
+    an = [a for a in queue if a.anType == 'tran'][0]
+    bt = mc.BatchTransient(ckt, an.tstop, an.tstep, an.im, lib=lib)
+    return ckt, an, bt, mc
+
+
+def oracle_mc_instance(args):
+    """One Monte-Carlo instance on the CPU oracle (reference mechanism:
+    setattr + process_params, then the reference's tran loop)."""
+    j, max_samples = args
+    from tests import support as S
+    from cardoon_b200.analyses import mc
+    from cardoon_b200.globalVars import glVar
+    from oracle import nodal_ref as R
+    ckt, queue = S.load_circuit(S.net('ring_bsim3.net'))
+    an = [a for a in queue if a.anType == 'tran'][0]
+    elems = S.nonlinear_elements(ckt)
+    mc.bsim3_ring_variation()(j, elems)
+    for e in elems:
+        e.process_params()
+    t0 = time.time()
+    r = R.run_tran(ckt, glVar, an.tstop, an.tstep, an.im,
+                   max_samples=max_samples)
+    dt = time.time() - t0
+    nfull = len(np.arange(0., an.tstop, an.tstep))
+    return dt, len(r['t']), nfull, int(r['iters'].sum())
+
+
+def cpu_baseline_mc(procs=1, per_proc=1, max_samples=100):
+    """CPU oracle on a bounded sample: `procs` worker processes, each running
+    `per_proc` instances for `max_samples` of the samples; circuits/s is
+    scaled to complete transients."""
+    import multiprocessing as mp
+    jobs = [(j, max_samples) for j in range(procs * per_proc)]
+    t0 = time.time()
+    if procs > 1:
+        with mp.get_context('spawn').Pool(procs) as pool:
+            out = pool.map(oracle_mc_instance, jobs)
+    else:
+        out = [oracle_mc_instance(j) for j in jobs]
+    wall = time.time() - t0
+    busy = sum(o[0] for o in out)
+    frac = out[0][1] / float(out[0][2])
+    # complete-transient equivalents finished per second by `procs` workers
+    value = len(jobs) * frac / (busy / procs)
+    return dict(value=value, unit='circuits/s', cores=procs, kind='port',
+                sample='{0} instances x first {1} of {2} samples on {3} '
+                       'worker process(es) (numpy oracle restatement of the '
+                       'reference tran loop; scaled to complete transients; '
+                       'wall {4:.1f} s)'.format(len(jobs), out[0][1],
+                                                out[0][2], procs, wall))
+
+
+def run_mc(args, D):
+    torch = D.torch
+    from cardoon_b200._lib import get_lib
+    lib = get_lib(D.local)
+    ckt, an, bt, mc = mc_setup(lib)
+    B = args.n or 4096
+    lo = D.rank * B
+    params_h = bt.pack_instances(B, mc.bsim3_ring_variation(), first=lo)
+    pinned = [torch.as_tensor(p).pin_memory() for p in params_h]
+    params_d = [p.to(lib.device) for p in pinned]
+    rows = bt.save_rows(MC_TERMS)
+    nsamples = len(bt.timeVec)
+    dc, tr = bt.engines(B)
+    state = {}
+
+    def step():
+        state['out'] = bt.run_device(params_d, rows, B)
+
+    clk = ClockSampler(D.local)
+    clk.start()
+    l0 = dc.launches + tr.launches
+    ms, t0, t1 = timed_steps(D, step, args.steps, args.warmup)
+    launches = (dc.launches + tr.launches - l0) \
+        * args.steps // (args.steps + args.warmup)
+    clocks = clk.stop(t0, t1)
+    wave, iters, status, opit = state['out']
+    nfail = int((status != 0).sum().item())
+    total = D.sum_over_ranks(B) * args.steps
+    value = total / (ms * 1e-3)
+
+    # ---- end to end: host records -> device, run, waveforms -> host --------
+    wave_h = torch.empty(wave.shape, dtype=torch.float64).pin_memory()
+    iters_h = torch.empty(iters.shape, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        for d, h in zip(params_d, pinned):
+            d.copy_(h, non_blocking=True)
+        w, it, st, _ = bt.run_device(params_d, rows, B)
+        wave_h.copy_(w, non_blocking=True)
+        iters_h.copy_(it, non_blocking=True)
+
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e, _, _ = timed_steps(D, e2e_step, e2e_steps, 1)
+    e2e = dict(value=D.sum_over_ranks(B) * e2e_steps / (ms_e * 1e-3),
+               unit='circuits/s',
+               h2d_bytes_per_step=int(sum(p.numel() for p in pinned) * 8),
+               d2h_bytes_per_step=int(wave_h.numel() * 8
+                                      + iters_h.numel() * 4))
+    # results of all ranks gathered once (NCCL), outside the timed region
+    allw, alli, alls = mc.gather_results(wave, iters, status, D.dist)
+
+    line = None
+    if D.rank == 0:
+        elems = ckt.nD_nlinElem
+        xs = np.array([[2.5, 1.2, 0.]]).T
+        fd = np.mean([count_flops(e, xs * e._tf, True)[0] for e in elems])
+        fv = np.mean([count_flops(e, xs * e._tf, False)[0] for e in elems])
+        n = bt.topo.n
+        ndev = len(elems)
+        it_total = float(iters.sum().item()) + float(opit.sum().item())
+        lu_flop = 2. / 3. * n ** 3 + 2. * n * n
+        flop = it_total * (ndev * fd + lu_flop) \
+            + B * nsamples * (ndev * fv + 2. * n * n)
+        t_step = ms * 1e-3 / args.steps
+        peak = lib.fp64_peak()
+        ach = flop / t_step / 1e12
+        roof = dict(bound='fp64', achieved=ach, peak=peak / 1e12,
+                    unit='TFLOP/s', frac=ach / (peak / 1e12), traffic=None,
+                    kernel='engine_tile_kernel<BSIM3, 8> (whole time loop)',
+                    peak_source='cdn_fp64_peak (DFMA microbenchmark, this '
+                                'run)',
+                    flop_per_eval_jac=fd, flop_per_eval_values=fv,
+                    newton_iterations=it_total)
+        cpu = cpu_baseline_mc(procs=1, per_proc=1, max_samples=120)
+        line = dict(metric='MC circuits/s (complete ring_bsim3 transients)',
+                    value=value, unit='circuits/s', n_gpus=D.world,
+                    steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True,
+                    scaling='weak', vs_baseline=None, dtype='f64',
+                    data='synthetic',
+                    config=dict(workload='mc: Monte Carlo of workspace/'
+                                'ring_bsim3.net (N=7, 6 mosbsim3, {0} '
+                                'samples, trapezoidal), {1} instances per '
+                                'GPU with per-instance BSIM3 records; one '
+                                'step = operating points + transients of all '
+                                'instances'.format(nsamples, B),
+                                instances_per_gpu=B, samples=nsamples,
+                                failed_instances=nfail,
+                                avg_newton_iterations_per_sample=float(
+                                    iters.sum().item()) / (B * nsamples),
+                                l2='per-instance records ({0:.1f} MB) are '
+                                   'L2-resident by nature of the workload; '
+                                   'every step re-reads them'.format(
+                                       sum(p.numel() for p in pinned) * 8
+                                       / 1e6)),
+                    clocks=clocks, e2e=e2e, gpu_launches=launches,
+                    roofline=roof, cpu_baseline=cpu)
+    return line
+
+
+# ---------------------------------------------------------------------------
+# workload: soliton transient (SURVEY 8d "T", config 2)
+# ---------------------------------------------------------------------------
+def soliton_setup():
+    from tests import support as S
+    from cardoon_b200.analyses import nodalCUDA as nd
+    from cardoon_b200.analyses.fsolve import solve
+    from cardoon_b200.analyses.integration import Trapezoidal
+    ckt, queue = S.load_circuit(S.net('soliton.net'))
+    an = [a for a in queue if a.anType == 'tran'][0]
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    tran = nd.TransientNodal(ckt, Trapezoidal())
+    x, res, it = solve(dc.get_guess(), tran.get_source(0.).copy(),
+                       dc.convergence_helpers)
+    timeVec = np.arange(start=0., stop=an.tstop, step=an.tstep, dtype=float)
+    return ckt, an, tran, x, timeVec, it
+
+
+def cpu_baseline_soliton(max_samples=150):
+    from tests import support as S
+    from cardoon_b200.globalVars import glVar
+    from oracle import nodal_ref as R
+    ckt, queue = S.load_circuit(S.net('soliton.net'))
+    an = [a for a in queue if a.anType == 'tran'][0]
+    idx = R.prepare(ckt)
+    t0 = time.time()
+    r = R.run_tran(ckt, glVar, an.tstop, an.tstep, an.im, idx=idx,
+                   max_samples=max_samples)
+    dt = time.time() - t0
+    return dict(value=(len(r['t']) - 1) / dt, unit='timepoints/s', cores=1,
+                kind='port',
+                sample='first {0} samples of test/soliton.net incl. the '
+                       'operating point (numpy oracle; SuperLU refactored '
+                       'every iteration as nodalSP.py:281-303)'.format(
+                           len(r['t'])))
+
+
+def run_soliton(args, D):
+    torch = D.torch
+    ckt, an, tran, x, timeVec, op_it = soliton_setup()
+    rows = list(range(ckt.nD_dimension))
+    nsamples = len(timeVec)
+    tran._make_engine(an.tstep, x)
+    e = tran.engine
+    lib = e.lib
+    src = tran.source_table(timeVec)
+    state = {}
+
+    def step():
+        state['out'] = e.tran(x, src, rows, im='trap', sync=False)
+
+    # first pass allocates; reuse buffers afterwards
+    clk = ClockSampler(D.local)
+    clk.start()
+    l0 = e.launches
+    ms, t0, t1 = timed_steps(D, step, args.steps, args.warmup)
+    launches = (e.launches - l0) * args.steps // (args.steps + args.warmup)
+    clocks = clk.stop(t0, t1)
+    wave, iters, res, status = state['out']
+    assert int(status[0].item()) == 0, 'soliton transient did not converge'
+    value = D.world * (nsamples - 1) * args.steps / (ms * 1e-3)
+
+    def e2e_step():
+        w, it, rs, st = e.tran(x, src, rows, im='trap', sync=True)
+
+    ms_e, _, _ = timed_steps(D, e2e_step, max(2, min(args.steps, 5)), 1)
+    e2e = dict(value=D.world * (nsamples - 1) * max(2, min(args.steps, 5))
+               / (ms_e * 1e-3), unit='timepoints/s',
+               h2d_bytes_per_step=int(src.size * 8 + x.size * 8),
+               d2h_bytes_per_step=int(wave.numel() * 8 + iters.numel() * 4
+                                      + res.numel() * 8))
+    line = None
+    if D.rank == 0:
+        info = e.info
+        n, nlu, nnz = info['n'], info['nlu'], info['nnzA']
+        it_total = float(iters.sum().item())
+        b_asm = 8. * (nnz + 2 * n) + 4. * (info['ncon'] + nnz)
+        b_lu = 8. * (nnz + 2 * nlu)
+        b_solve = 8. * (nlu + 3 * n)
+        per_iter = b_asm + b_lu + b_solve
+        per_sample = b_solve + 8. * 8 * n        # chord + accept/rhs vectors
+        algo = it_total * per_iter + (nsamples - 1) * per_sample
+        t_step = ms * 1e-3 / args.steps
+        hbm, how = measured_peaks()
+        ach = algo / t_step / 1e9
+        roof = dict(bound='hbm', achieved=ach, peak=hbm, unit='GB/s',
+                    frac=ach / hbm, traffic=None,
+                    kernel='engine_block_kernel<DIODE, 256> (whole time '
+                           'loop, one CTA, state L2-resident)',
+                    peak_source=how, bytes_per_newton_iteration=per_iter,
+                    newton_iterations=it_total, nnzJ=nnz, nnzLU=nlu,
+                    levels=dict(factor=info['nlev_f'], L=info['nlev_l'],
+                                U=info['nlev_u']))
+        cpu = cpu_baseline_soliton()
+        line = dict(metric='soliton tran timepoints/s', value=value,
+                    unit='timepoints/s', n_gpus=D.world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms / args.steps,
+                    higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f64', data='synthetic',
+                    config=dict(workload='soliton: test/soliton.net transient '
+                                '(N=3022, 47 diodes, {0} samples, '
+                                'trapezoidal, h=0.1 ps); one step = the whole '
+                                'time loop after the operating point; with '
+                                '--gpus N every rank runs a replica'
+                                .format(nsamples), samples=nsamples,
+                                op_iterations=op_it,
+                                avg_newton_iterations=it_total / nsamples,
+                                l2='single-circuit state (~0.5 MB) is '
+                                   'L2-resident; latency-bound by design'),
+                    clocks=clocks, e2e=e2e, gpu_launches=launches,
+                    roofline=roof, cpu_baseline=cpu)
+    return line
+
+
+# ---------------------------------------------------------------------------
 # reference arm
 # ---------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return None
+    cores = os.cpu_count() or 1
+    common = dict(impl='reference', n_gpus=args.gpus, steps=args.steps,
+                  warmup=args.warmup, ms_per_step=None,
+                  higher_is_better=True, scaling='weak', vs_baseline=None,
+                  dtype='f64', data='synthetic')
     if args.workload == 'deveval':
-        inp = deveval_inputs(1 << 16)
-        cpu = cpu_baseline_deveval(inp)
-        v = cpu['value']
-        return dict(impl='reference', metric='device evals/s (BSIM3v3 '
-                    'mosbsim3, value + Jacobian)', value=v,
-                    unit='device evals/s', n_gpus=args.gpus,
-                    steps=args.steps, warmup=args.warmup, ms_per_step=None,
-                    higher_is_better=True, scaling='weak', vs_baseline=None,
-                    dtype='f64', data='synthetic',
-                    config=dict(workload='deveval'), cpu_baseline=cpu,
-                    e2e=dict(value=v, unit='device evals/s',
-                             h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    raise SystemExit('unknown workload')
+        cpu = cpu_baseline_deveval(deveval_inputs(1 << 16), seconds=20.)
+        metric = 'device evals/s (BSIM3v3 mosbsim3, value + Jacobian)'
+        wl = 'deveval'
+    elif args.workload == 'mc':
+        cpu = cpu_baseline_mc(procs=cores, per_proc=1, max_samples=120)
+        metric = 'MC circuits/s (complete ring_bsim3 transients)'
+        wl = 'mc: Monte Carlo of workspace/ring_bsim3.net'
+    else:
+        cpu = cpu_baseline_soliton(max_samples=300)
+        metric = 'soliton tran timepoints/s'
+        wl = 'soliton: test/soliton.net transient'
+    v = cpu['value']
+    common.update(metric=metric, value=v, unit=cpu['unit'],
+                  config=dict(workload=wl), cpu_baseline=cpu,
+                  e2e=dict(value=v, unit=cpu['unit'], h2d_bytes_per_step=0,
+                           d2h_bytes_per_step=0))
+    return common
 
 
 def main():
@@ -389,7 +694,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native',
                     choices=['native', 'reference'])
-    ap.add_argument('--workload', default='deveval',
+    ap.add_argument('--workload', default='mc',
                     choices=['deveval', 'mc', 'soliton'])
     ap.add_argument('--n', type=int, default=0,
                     help='instances per GPU (0 = workload default)')
@@ -406,7 +711,8 @@ def main():
         g.build()
     D = Dist(args.gpus)
     D.barrier()
-    line = dict(deveval=run_deveval)[args.workload](args, D)
+    line = dict(deveval=run_deveval, mc=run_mc,
+                soliton=run_soliton)[args.workload](args, D)
     if D.rank == 0:
         print(json.dumps(line))
     D.close()

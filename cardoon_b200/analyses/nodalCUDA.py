@@ -118,6 +118,19 @@ def process_nodal_element(elem, ckt):
     ckt.__dict__.pop('_cuda_topology', None)
 
 
+def get_guess(ckt):
+    """Initial guess from the devices' ``vPortGuess`` (nodal.py:723-740):
+    only the positive node of each control port is written."""
+    x0 = np.zeros(ckt.nD_dimension)
+    for elem in ckt.nD_nlinElem:
+        try:
+            for i, j in elem.nD_vpos:
+                x0[j] = elem.vPortGuess[i]
+        except AttributeError:
+            pass
+    return x0
+
+
 def set_xin(xin, posCols, negCols, xVec):
     """xin = T_cv x (nodal.py:44-52)."""
     for i, j in posCols:
@@ -801,14 +814,7 @@ class DCNodal(_NLFunction):
                              x_ref=self.get_guess())
 
     def get_guess(self):
-        x0 = np.zeros(self.ckt.nD_dimension)
-        for elem in self.ckt.nD_nlinElem:
-            try:
-                for i, j in elem.nD_vpos:
-                    x0[j] = elem.vPortGuess[i]
-            except AttributeError:
-                pass
-        return x0
+        return get_guess(self.ckt)
 
     def get_source(self):
         self.sVec.fill(0.)
