@@ -10,11 +10,7 @@ struct cdn_ctx {
     std::string err;
 };
 
-#define CDN_OK 0
-#define CDN_ERR_ARG (-1)
-#define CDN_ERR_CUDA (-2)
-#define CDN_ERR_STATE (-3)
-#define CDN_ERR_SINGULAR (-4)
+#include "cardoon_b200.h"
 
 #define CDN_CUDA(ctx, call)                                                    \
     do {                                                                       \

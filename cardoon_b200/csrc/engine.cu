@@ -7,27 +7,6 @@
 
 extern "C" {
 
-// plain-C mirror of cdn_engine_args handed in by the host (ctypes)
-typedef struct cdn_run_host {
-    double abstol, reltol, maxdelta, a0, gmin, lambda;
-    int maxiter, errfunc, use_q, im;
-    int op, B;
-    int team, T;                 // team: -1 = choose; T: 0 = choose
-    double* x;
-    const double* sv_in;
-    double* ws;                  // NULL: state in shared memory (tile team only)
-    int nsamples, first, init_ic, nsrc, nsave, blocks;
-    const int* src_rows;
-    const double* src_val;
-    const double* src_dc;
-    const int* save_rows;
-    double* wave;
-    int* iters;
-    double* res;
-    int* status;
-    double* red;                 // >= 2*blocks doubles for the grid team
-} cdn_run_host;
-
 long cdn_engine_ws_doubles(cdn_plan* P) {
     const cdn_plan_dev* D = cdn_plan_host_view(P);
     if (!D) return -1;

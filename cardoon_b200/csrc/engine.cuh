@@ -26,19 +26,7 @@
 namespace cg = cooperative_groups;
 
 // ---- run description ---------------------------------------------------------------
-enum {
-    CDN_OP_NEWTON = 0,     // x <- Newton(x, sv)
-    CDN_OP_TRAN = 1,       // whole time loop from the operating point in x
-    CDN_OP_UPDATE_Q = 2,   // q <- C x + Tq q(x)
-    CDN_OP_SET_IC = 3,     // update_q + integrator init
-    CDN_OP_ACCEPT = 4,     // update_q + integrator accept
-    CDN_OP_RHS = 5,        // sv <- f_n1 + sv_in
-    CDN_OP_CHORD = 6,      // dx <- LU \ (sv - iVec) with the last factors
-    CDN_OP_GET_I = 7,      // iVec(x)
-    CDN_OP_GET_I_JAC = 8,  // iVec(x) and assembled (unfactored) Jacobian slots
-    CDN_OP_SOLVE = 9       // factor the assembled slots, dx <- LU \ y
-};
-
+// operation codes CDN_OP_*: include/cardoon_b200.h
 struct cdn_opts {
     double abstol, reltol, maxdelta;
     double a0;        // integration coefficient (0 in DC)

@@ -47,6 +47,124 @@ int cdn_dev_eval(cdn_ctx* ctx, int model_id, unsigned flags, long n, int nxin,
                  const double* params, long ldp, const int* pidx,
                  const double* xin, double* out, double* jac, void* stream);
 
+/* ---- (a1-a4, a12) formulation plan: symbolic analysis, done once ---------
+ * Replaces what the reference redoes on every Newton iteration: COO -> CSC
+ * conversion with duplicate summing, COLAMD ordering, symbolic and numeric
+ * SuperLU factorisation (cardoon/analyses/nodalSP.py:281-303) and the
+ * per-element index bookkeeping of create_additional_indexes (:111-164).
+ * Input = the index lists of make_nodal_circuit / process_nodal_element
+ * (cardoon/analyses/nodal.py:113-282): -1 is the reference node (dropped).
+ * Port lists are k-major over the n instances of a group: vpos[k*n + i].   */
+typedef struct cdn_group_host {
+    int model;            /* CDN_MODEL_* (csrc/param_index.h)                */
+    unsigned flags;       /* model structure flags, uniform over the group   */
+    int n, nxin, ncs, nqs, ndelay;
+    const int* vpos;      /* [nxin][n] row of the + control terminal         */
+    const int* vneg;      /* [nxin][n]                                       */
+    const int* cpos;      /* [ncs][n]  row the current leaves                */
+    const int* cneg;      /* [ncs][n]                                        */
+    const int* qpos;      /* [nqs][n]                                        */
+    const int* qneg;      /* [nqs][n]                                        */
+} cdn_group_host;
+
+typedef struct cdn_circuit_host {
+    int n;                /* unknowns                                        */
+    int ordering;         /* 0 nested dissection, 1 natural, 2 dense storage
+                             (partial pivoting), 3 colorder given            */
+    long nG; const int* g_row; const int* g_col; const double* g_val; /* G   */
+    long nC; const int* c_row; const int* c_col; const double* c_val; /* C   */
+    long nE; const int* e_row; const int* e_col; const double* e_val; /* gmin
+                             stepping pattern (nodal.py:491-515)             */
+    int ngroups;
+    const cdn_group_host* groups;
+    const int* rowmatch;  /* [n] unknown whose pivot row each row is, or NULL */
+    const int* colorder;  /* [n] unknown eliminated at each position (3)     */
+} cdn_circuit_host;
+
+typedef struct cdn_plan cdn_plan;
+
+int cdn_init_host(cdn_ctx** ctx);      /* context without a GPU (plans only) */
+int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan** out);
+long cdn_plan_bytes(cdn_plan* plan);   /* device bytes cdn_plan_bind needs   */
+/* info[0..11] = n, nlu, factor levels, L levels, U levels, Crout terms,
+ * device contributions, nnz(J), longest term list, longest contribution
+ * list, doubles of device outputs, doubles of device Jacobians             */
+int cdn_plan_info(cdn_plan* plan, long* info);
+int cdn_plan_bind(cdn_plan* plan, void* dev_ws, long bytes, void* stream);
+/* params[k*ldp + col] (device); per_inst = 1: instance b of a batch reads
+ * columns b*n + i, else every instance reads column i                      */
+int cdn_plan_set_group_params(cdn_plan* plan, int group, const double* params,
+                              long ldp, const int* pidx, int per_inst);
+/* (row, unknown) of every Jacobian slot, original numbering (host arrays)  */
+int cdn_plan_slot_coords(cdn_plan* plan, int* rows, int* cols);
+/* host copy of a packed plan array by field name (csrc/plan.h)             */
+int cdn_plan_array(cdn_plan* plan, const char* name, const void** ptr,
+                   long* count);
+int cdn_plan_free(cdn_plan* plan);
+
+/* ---- (a6-a16) device-resident Newton engine ------------------------------
+ * One launch per operation; the state of every circuit instance (x, dx,
+ * iVec, sV, q, integrator history, LU factors, device outputs) lives on the
+ * device (caller-provided `ws`, or shared memory for batches of small
+ * circuits when ws == NULL).  Replaces, per operation:
+ *   CDN_OP_NEWTON     fsolve_Newton (cardoon/analyses/fsolve.py:59-128) over
+ *                     get_i_Jac + factor_and_solve (nodal.py:455-457,
+ *                     787-821, 606-627; nodalSP.py:494-523, 281-303)
+ *   CDN_OP_TRAN       the time loop of cardoon/analyses/tran.py:171-206
+ *                     (accept, get_rhs, chord predictor, solve, store)
+ *   CDN_OP_UPDATE_Q   TransientNodal.update_q   (nodalSP.py:719-733)
+ *   CDN_OP_SET_IC     TransientNodal.set_IC     (nodalSP.py:666-696)
+ *   CDN_OP_ACCEPT     TransientNodal.accept     (nodalSP.py:735-758)
+ *   CDN_OP_RHS        TransientNodal.get_rhs    (nodalSP.py:792-802)
+ *   CDN_OP_CHORD      get_chord_deltax          (nodalSP.py:345-354)
+ *   CDN_OP_GET_I      get_i                     (nodalSP.py:471-492, 804-836)
+ *   CDN_OP_GET_I_JAC  get_i_Jac                 (nodalSP.py:494-523, 838-887)
+ *   CDN_OP_SOLVE      factor_and_solve          (nodalSP.py:281-303)
+ * Non-convergence is a status, not an error: status[b] = -1 (NEWTON) or the
+ * first failed sample (TRAN); the host raises NoConvergenceError.           */
+#define CDN_OP_NEWTON 0
+#define CDN_OP_TRAN 1
+#define CDN_OP_UPDATE_Q 2
+#define CDN_OP_SET_IC 3
+#define CDN_OP_ACCEPT 4
+#define CDN_OP_RHS 5
+#define CDN_OP_CHORD 6
+#define CDN_OP_GET_I 7
+#define CDN_OP_GET_I_JAC 8
+#define CDN_OP_SOLVE 9
+
+typedef struct cdn_run_host {
+    /* .options read by Newton (cardoon/globalVars.py:44-57) */
+    double abstol, reltol, maxdelta;
+    double a0;           /* integration coefficient: 2/h trap, 1/h BE, 0 DC  */
+    double gmin;         /* gmin stepping (multiplies the E pattern)         */
+    double lambda;       /* source stepping factor (1 = full sources)        */
+    int maxiter, errfunc;
+    int use_q;           /* 0: DC (currents only), 1: transient              */
+    int im;              /* 0 backward Euler, 1 trapezoidal                  */
+    int op, B;           /* operation, circuit instances in the batch        */
+    int team, T;         /* -1 choose / 0 warp tile / 1 CTA / 2 grid; lanes  */
+    double* x;           /* [B][n] in/out (device)                           */
+    const double* sv_in; /* [n] source vector (device)                       */
+    double* ws;          /* [B][cdn_engine_ws_doubles] state, or NULL        */
+    int nsamples, first, init_ic, nsrc, nsave, blocks;
+    const int* src_rows;     /* [nsrc] rows with a time-varying source       */
+    const double* src_val;   /* [nsamples][nsrc]                             */
+    const double* src_dc;    /* [n] constant part of the source vector       */
+    const int* save_rows;    /* [nsave] unknowns to record                   */
+    double* wave;            /* [B][nsamples][nsave]                         */
+    int* iters;              /* [B][nsamples] (TRAN) or [B]                  */
+    double* res;             /* same shape as iters                          */
+    int* status;             /* [B]                                          */
+    double* red;             /* grid team: reduction scratch                 */
+} cdn_run_host;
+
+long cdn_engine_ws_doubles(cdn_plan* plan);
+/* offsets (doubles) of x, dx, ivec, sv, q, qprev, dq, y, tmp, lu, out, jac,
+ * piv inside one instance's state                                          */
+int cdn_engine_layout(cdn_plan* plan, long* off);
+int cdn_engine_run(cdn_plan* plan, const cdn_run_host* run, void* stream);
+
 /* measured FP64 FMA throughput of this GPU in FLOP/s (roofline denominator
  * for the device-evaluation kernels; none is published in MEASURED_PEAKS). */
 int cdn_fp64_peak(cdn_ctx* ctx, double* flops_per_s);
