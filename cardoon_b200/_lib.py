@@ -56,6 +56,7 @@ class RunHost(C.Structure):
                 ('use_q', C.c_int), ('im', C.c_int),
                 ('op', C.c_int), ('B', C.c_int),
                 ('team', C.c_int), ('T', C.c_int),
+                ('helpers', C.c_int), ('pad_', C.c_int),
                 ('x', _vp), ('sv_in', _vp), ('ws', _vp),
                 ('nsamples', C.c_int), ('first', C.c_int),
                 ('init_ic', C.c_int), ('nsrc', C.c_int), ('nsave', C.c_int),

@@ -128,8 +128,9 @@ class BatchTransient(object):
         dc.x.copy_(torch.as_tensor(np.broadcast_to(
             self.x0, (B, self.topo.n)).copy()))
         dc.sv.copy_(torch.as_tensor(self.src[0]))
-        dc._launch(dc._run_struct(nd.L.OP_NEWTON))
-        self._op_fallback(dc, B)
+        # plain Newton, then gmin / source stepping for the instances that
+        # need them, all inside the launch (fsolve.py:23-56 helper chain)
+        dc._launch(dc._run_struct(nd.L.OP_NEWTON, helpers=1))
         tr.x.copy_(dc.x)
         wave, iters, res, status = tr.tran(None, self.src, rows, im=self.im,
                                            sync=False)
@@ -138,53 +139,12 @@ class BatchTransient(object):
                              status)
         return wave, iters, status, dc.iters
 
-    def _op_fallback(self, dc, B):
-        """Instances whose plain Newton operating point failed go through the
-        reference's convergence-helper chain (fsolve.py:23-56: gmin stepping,
-        source stepping), one instance at a time, each inner solve a device
-        Newton launch on that instance's records."""
-        failed = np.nonzero(dc.status.cpu().numpy() != 0)[0]
-        self.op_fallbacks = len(failed)
-        if not len(failed):
-            return
-        torch = dc.lib.torch
-        single = self._engines.get('single')
-        if single is None:
-            single = _SingleDC(nd.Engine(self.topo, use_q=False, batch=1,
-                                         lib=self.lib, keep_state=False,
-                                         x_ref=self.x0))
-            self._engines['single'] = single
-        for b in failed:
-            cols = []
-            for g, p in zip(self.topo.groups, dc.params):
-                cols.append(p[:, b * g['n']:(b + 1) * g['n']].contiguous())
-            single.engine.set_params(cols)
-            for helper in single.convergence_helpers[1:]:
-                if helper is None:
-                    break
-                try:
-                    x, res, it = helper(self.x0.copy(), self.src[0])
-                except nd.NoConvergenceError:
-                    continue
-                dc.x[b].copy_(torch.as_tensor(x))
-                dc.status[b] = 0
-                dc.iters[b] = it
-                break
-
     def run(self, params, terms):
         B = params[0].shape[1] // self.topo.groups[0]['n']
         wave, iters, status, opit = self.run_device(
             params, self.save_rows(terms), B)
         return (wave.cpu().numpy(), iters.cpu().numpy(),
                 status.cpu().numpy(), opit.cpu().numpy())
-
-
-class _SingleDC(nd._NLFunction):
-    """Convergence helpers around a one-instance DC engine."""
-
-    def __init__(self, engine):
-        nd._NLFunction.__init__(self)
-        self.engine = engine
 
 
 def bsim3_ring_variation(seed=20240):

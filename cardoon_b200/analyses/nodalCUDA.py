@@ -496,10 +496,11 @@ class Engine(object):
         self.set_params(params)
         # ---- state -------------------------------------------------------------------
         self.ws_per = lib.dll.cdn_engine_ws_doubles(self.plan)
-        off = (C.c_long * 13)()
+        off = (C.c_long * 14)()
         lib.check(lib.dll.cdn_engine_layout(self.plan, off))
         self.off = dict(zip(('x', 'dx', 'ivec', 'sv', 'q', 'qprev', 'dq',
-                             'y', 'tmp', 'lu', 'out', 'jac', 'piv'), off))
+                             'y', 'tmp', 'xb', 'lu', 'out', 'jac', 'piv'),
+                            off))
         self.keep_state = keep_state
         self.ws = None
         if keep_state or not (dense and n <= DENSE_MAX):
@@ -550,8 +551,9 @@ class Engine(object):
                 self.plan, k, lib.ptr(t), int(t.stride(0)), None, per_inst))
 
     # ---- launches ---------------------------------------------------------------
-    def _run_struct(self, op, a0=None, gmin=0., lam=1.):
+    def _run_struct(self, op, a0=None, gmin=0., lam=1., helpers=0):
         r = L.RunHost()
+        r.helpers = helpers
         r.abstol, r.reltol = glVar.abstol, glVar.reltol
         r.maxdelta, r.maxiter = glVar.maxdelta, int(glVar.maxiter)
         r.errfunc = int(bool(glVar.errfunc))
@@ -650,7 +652,7 @@ class Engine(object):
                               device=lib.device)
         if first == 1:
             wave[:, 0, :] = self.x[:, self._src[3].long()]
-        r = self._run_struct(L.OP_TRAN)
+        r = self._run_struct(L.OP_TRAN, helpers=1)
         r.im = 1 if im == 'trap' else 0
         r.nsamples, r.first, r.init_ic = nsamples, first, int(init_ic)
         r.nsrc, r.nsave = len(var), nsave
@@ -717,9 +719,8 @@ class _NLFunction(object):
         stack = [0., 1.]
         step = lam
         small = 1e-4
-        x = np.copy(x0)
-        x0 = np.copy(x0)
-        success = True
+        x = np.copy(x0)           # (x0 itself is updated in place below,
+        success = True            #  as in the reference)
         totIter = 0
         res = 0.
         while stack:

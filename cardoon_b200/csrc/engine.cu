@@ -13,16 +13,16 @@ long cdn_engine_ws_doubles(cdn_plan* P) {
     return ws_doubles(D->n, D->nlu, D->dev_out_size, D->dev_jac_size);
 }
 
-// offsets (in doubles) of x, dx, ivec, sv, q, qprev, dq, y, tmp, lu, out, jac, piv
+// offsets (in doubles) of x, dx, ivec, sv, q, qprev, dq, y, tmp, xb, lu, out, jac, piv
 int cdn_engine_layout(cdn_plan* P, long* off) {
     const cdn_plan_dev* D = cdn_plan_host_view(P);
     if (!D || !off) return CDN_ERR_ARG;
     const long n = D->n;
-    for (int k = 0; k < 9; ++k) off[k] = k * n;
-    off[9] = 9 * n;
-    off[10] = off[9] + D->nlu;
-    off[11] = off[10] + D->dev_out_size;
-    off[12] = off[11] + D->dev_jac_size;
+    for (int k = 0; k < 10; ++k) off[k] = k * n;
+    off[10] = 10 * n;
+    off[11] = off[10] + D->nlu;
+    off[12] = off[11] + D->dev_out_size;
+    off[13] = off[12] + D->dev_jac_size;
     return CDN_OK;
 }
 
@@ -56,7 +56,7 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     const long per = ws_doubles(D->n, D->nlu, D->dev_out_size, D->dev_jac_size);
     A.ws_stride = per;
     A.nsamples = r->nsamples; A.first = r->first; A.init_ic = r->init_ic;
-    A.nsrc = r->nsrc; A.nsave = r->nsave;
+    A.nsrc = r->nsrc; A.nsave = r->nsave; A.helpers = r->helpers;
     A.src_rows = r->src_rows; A.src_val = r->src_val; A.src_dc = r->src_dc;
     A.save_rows = r->save_rows; A.wave = r->wave; A.iters = r->iters; A.res = r->res;
     A.status = r->status; A.red = r->red;

@@ -48,7 +48,8 @@ struct cdn_engine_args {
     double* ws;                 // [B][ws_total] global state (NULL: shared memory)
     long ws_stride;
     // transient
-    int nsamples, first, init_ic, nsrc, nsave, pad_;
+    int nsamples, first, init_ic, nsrc, nsave;
+    int helpers;                // 1: fall back to gmin / source stepping in-kernel
     const int* src_rows;        // [nsrc] rows with a time-dependent source
     const double* src_val;      // [nsamples][nsrc] summed source value per row
     const double* src_dc;       // [n] constant part of the source vector
@@ -65,18 +66,18 @@ struct cdn_engine_args {
 
 // ---- per-instance state ----------------------------------------------------------
 struct Ws {
-    double *x, *dx, *ivec, *sv, *q, *qprev, *dq, *y, *tmp, *lu, *out, *jac;
+    double *x, *dx, *ivec, *sv, *q, *qprev, *dq, *y, *tmp, *xb, *lu, *out, *jac;
     int* piv;
 };
 
 __host__ __device__ inline long ws_doubles(int n, long nlu, long out_size, long jac_size) {
-    return 9L * n + nlu + out_size + jac_size + (n + 1) / 2 + 2;
+    return 10L * n + nlu + out_size + jac_size + (n + 1) / 2 + 2;
 }
 
 __device__ inline Ws ws_carve(double* base, int n, long nlu, long out_size, long jac_size) {
     Ws w;
     w.x = base; w.dx = w.x + n; w.ivec = w.dx + n; w.sv = w.ivec + n; w.q = w.sv + n;
-    w.qprev = w.q + n; w.dq = w.qprev + n; w.y = w.dq + n; w.tmp = w.y + n; w.lu = w.tmp + n;
+    w.qprev = w.q + n; w.dq = w.qprev + n; w.y = w.dq + n; w.tmp = w.y + n; w.xb = w.tmp + n; w.lu = w.xb + n;
     w.out = w.lu + nlu; w.jac = w.out + out_size;
     w.piv = (int*)(w.jac + jac_size);
     return w;
@@ -513,6 +514,65 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
     return it;
 }
 
+// Continuation on lambda with bisection and backtracking (nodal.py:545-604):
+// mode 0 = gmin stepping on the nonlinear ports (gmin = 1e-3/lambda - 1e-3,
+// nodal.py:491-515, 535-543), mode 1 = source stepping (:517-533).  w.xb is
+// the caller's x0 and, as in the reference, is overwritten by every
+// successful intermediate solution.
+template <int MS, class Team>
+__device__ __noinline__ int homotopy(Team& tm, const cdn_plan_dev& P, int b, const Ws& w,
+                                     cdn_opts o, int mode, double* res_out, bool* ok) {
+    double stack[48];
+    int sp = 0;
+    stack[sp++] = 0.0;
+    stack[sp++] = 1.0;
+    double lam = 0.5, step = 0.5, res = 0.0;
+    const double small = 1e-4;
+    bool success = true;
+    int tot = 0;
+    for (int r = tm.rank(); r < P.n; r += tm.size()) w.x[r] = w.xb[r];
+    tm.sync();
+    while (sp > 0) {
+        if (mode == 0) o.gmin = 1e-3 / lam - 1e-3;
+        else o.lambda = lam;
+        bool ok1;
+        tot += newton<MS>(tm, P, b, w, o, &res, &ok1);
+        if (ok1) {
+            for (int r = tm.rank(); r < P.n; r += tm.size()) w.xb[r] = w.x[r];
+            step = stack[sp - 1] - lam;
+            lam = stack[--sp];
+        } else {
+            for (int r = tm.rank(); r < P.n; r += tm.size()) w.x[r] = w.xb[r];
+            if (sp < 48) stack[sp++] = lam;
+            step *= 0.5;
+            lam -= step;
+            if (lam < small || step < small) { success = false; tm.sync(); break; }
+        }
+        tm.sync();
+    }
+    *res_out = res;
+    *ok = success;
+    return tot;
+}
+
+// fsolve.solve (fsolve.py:23-56) over the helper list of the sparse engine
+// (nodalSP.py:232-235): plain Newton, gmin stepping, source stepping.  x0 is
+// taken from w.x; returns the iteration count of the helper that succeeded.
+template <int MS, class Team>
+__device__ __forceinline__ int solve_helpers(Team& tm, const cdn_plan_dev& P, int b,
+                                             const Ws& w, const cdn_opts& o, int helpers,
+                                             double* res_out, bool* ok) {
+    if (helpers) {
+        for (int r = tm.rank(); r < P.n; r += tm.size()) w.xb[r] = w.x[r];
+        tm.sync();
+    }
+    int it = newton<MS>(tm, P, b, w, o, res_out, ok);
+    if (*ok || !helpers) return it;
+    it = homotopy<MS>(tm, P, b, w, o, 0, res_out, ok);
+    if (*ok) return it;
+    return homotopy<MS>(tm, P, b, w, o, 1, res_out, ok);
+}
+
 // q(x) with a values-only device sweep (nodalSP.py:719-733)
 template <int MS, class Team>
 __device__ __forceinline__ void update_q(Team& tm, const cdn_plan_dev& P, int b, const Ws& w) {
@@ -575,7 +635,7 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
         for (int r = tm.rank(); r < n; r += tm.size()) w.sv[r] = __ldg(A.sv_in + r);
         tm.sync();
         double res; bool ok;
-        const int it = newton<MS>(tm, P, b, w, o, &res, &ok);
+        const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, &res, &ok);
         if (tm.rank() == 0) {
             A.iters[b] = it; A.res[b] = res; A.status[b] = ok ? 0 : -1;
         }
@@ -597,7 +657,7 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
                 tm.sync();
             }
             double res; bool ok;
-            const int it = newton<MS>(tm, P, b, w, o, &res, &ok);
+            const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, &res, &ok);
             const long at = (long)b * A.nsamples + i;
             if (tm.rank() == 0) { A.iters[at] = it; A.res[at] = res; }
             if (!ok) { status = i; break; }

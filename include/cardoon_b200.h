@@ -107,7 +107,8 @@ int cdn_plan_free(cdn_plan* plan);
  * iVec, sV, q, integrator history, LU factors, device outputs) lives on the
  * device (caller-provided `ws`, or shared memory for batches of small
  * circuits when ws == NULL).  Replaces, per operation:
- *   CDN_OP_NEWTON     fsolve_Newton (cardoon/analyses/fsolve.py:59-128) over
+ *   CDN_OP_NEWTON     fsolve.solve / fsolve_Newton (cardoon/analyses/fsolve.py:
+ *                     23-128) with the helper chain of nodal.py:452-604 over
  *                     get_i_Jac + factor_and_solve (nodal.py:455-457,
  *                     787-821, 606-627; nodalSP.py:494-523, 281-303)
  *   CDN_OP_TRAN       the time loop of cardoon/analyses/tran.py:171-206
@@ -144,6 +145,8 @@ typedef struct cdn_run_host {
     int im;              /* 0 backward Euler, 1 trapezoidal                  */
     int op, B;           /* operation, circuit instances in the batch        */
     int team, T;         /* -1 choose / 0 warp tile / 1 CTA / 2 grid; lanes  */
+    int helpers, pad_;   /* 1: on failure continue in-kernel with gmin and
+                            source stepping (fsolve.py:23-56 helper chain)  */
     double* x;           /* [B][n] in/out (device)                           */
     const double* sv_in; /* [n] source vector (device)                       */
     double* ws;          /* [B][cdn_engine_ws_doubles] state, or NULL        */
@@ -160,8 +163,8 @@ typedef struct cdn_run_host {
 } cdn_run_host;
 
 long cdn_engine_ws_doubles(cdn_plan* plan);
-/* offsets (doubles) of x, dx, ivec, sv, q, qprev, dq, y, tmp, lu, out, jac,
- * piv inside one instance's state                                          */
+/* offsets (doubles) of x, dx, ivec, sv, q, qprev, dq, y, tmp, xb, lu, out,
+ * jac, piv inside one instance's state                                          */
 int cdn_engine_layout(cdn_plan* plan, long* off);
 int cdn_engine_run(cdn_plan* plan, const cdn_run_host* run, void* stream);
 
