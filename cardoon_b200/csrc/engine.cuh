@@ -97,6 +97,11 @@ struct TileTeam {
         for (int o = T / 2; o > 0; o >>= 1) v = fmax(v, tile.shfl_xor(v, o));
         return v;
     }
+    __device__ double sum(double v) const {
+#pragma unroll
+        for (int o = T / 2; o > 0; o >>= 1) v += tile.shfl_xor(v, o);
+        return v;
+    }
     __device__ bool all(bool p) const { return tile.all(p); }
     // largest v, smallest index on ties; NaN never wins
     __device__ void argmax(double& v, int& i) const {
@@ -124,6 +129,17 @@ struct BlockTeam {
         __syncthreads();
         double r = sred[0];
         for (int k = 1; k < nw; ++k) r = fmax(r, sred[k]);
+        __syncthreads();
+        return r;
+    }
+    __device__ double sum(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if ((threadIdx.x & 31) == 0) sred[w] = v;
+        __syncthreads();
+        double r = sred[0];
+        for (int k = 1; k < nw; ++k) r += sred[k];
         __syncthreads();
         return r;
     }
@@ -172,6 +188,26 @@ struct GridTeam {
             r = fmax(r, __ldcg(gred + phase * gridDim.x + k));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+        phase ^= 1;
+        return r;
+    }
+    __device__ double sum(double v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if ((threadIdx.x & 31) == 0) sred[w] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double r = sred[0];
+            for (int k = 1; k < nw; ++k) r += sred[k];
+            gred[phase * gridDim.x + blockIdx.x] = r;
+        }
+        grid.sync();
+        double r = 0.0;
+        for (int k = threadIdx.x & 31; k < (int)gridDim.x; k += 32)
+            r += __ldcg(gred + phase * gridDim.x + k);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
         phase ^= 1;
         return r;
     }
@@ -281,63 +317,121 @@ __device__ __forceinline__ void eval_devices(Team& tm, const cdn_plan_dev& P, in
 
 // ---- assembly (gather; no atomics) ------------------------------------------------------
 // iVec = G'x + Ti i(x) + a0 Tq q(x) (+ gmin Gones x);  y = lambda*sv - iVec
+// Rows / slots with more than CDN_HEAVY gather terms (hub nodes such as a
+// supply rail) are summed by the whole team, everything else by one thread.
+template <class Team>
+__device__ __forceinline__ double row_sum(const cdn_plan_dev& P, const Ws& w, const cdn_opts& o,
+                                          double a0, int r, int first, int stride) {
+    double acc = 0.0;
+    const int l0 = __ldg(P.r_lin_ptr + r), l1 = __ldg(P.r_lin_ptr + r + 1);
+    for (int k = l0 + first; k < l1; k += stride) {
+        double g = __ldg(P.r_lin_g + k);
+        if (o.use_q) g += a0 * __ldg(P.r_lin_c + k);
+        if (o.gmin != 0.0) g += o.gmin * __ldg(P.r_lin_gones + k);
+        acc += g * w.x[__ldg(P.r_lin_col + k)];
+    }
+    const int c0 = __ldg(P.r_con_ptr + r), c1 = __ldg(P.r_con_ptr + r + 1);
+    for (int k = c0 + first; k < c1; k += stride) {
+        const int kind = __ldg(P.r_con_kind + k);
+        const double v = w.out[__ldg(P.r_con_src + k)];
+        if (kind == 1) acc += v;
+        else if (kind == -1) acc -= v;
+        else if (o.use_q) acc += (kind > 0 ? a0 : -a0) * v;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ bool row_heavy(const cdn_plan_dev& P, int r) {
+    return (__ldg(P.r_lin_ptr + r + 1) - __ldg(P.r_lin_ptr + r)) +
+           (__ldg(P.r_con_ptr + r + 1) - __ldg(P.r_con_ptr + r)) > CDN_HEAVY;
+}
+
 template <class Team>
 __device__ __forceinline__ void residual(Team& tm, const cdn_plan_dev& P, const Ws& w,
                                          const cdn_opts& o) {
     const double a0 = o.use_q ? o.a0 : 0.0;
     for (int r = tm.rank(); r < P.n; r += tm.size()) {
-        double acc = 0.0;
-        for (int k = __ldg(P.r_lin_ptr + r); k < __ldg(P.r_lin_ptr + r + 1); ++k) {
-            double g = __ldg(P.r_lin_g + k);
-            if (o.use_q) g += a0 * __ldg(P.r_lin_c + k);
-            if (o.gmin != 0.0) g += o.gmin * __ldg(P.r_lin_gones + k);
-            acc += g * w.x[__ldg(P.r_lin_col + k)];
-        }
-        for (int k = __ldg(P.r_con_ptr + r); k < __ldg(P.r_con_ptr + r + 1); ++k) {
-            const int kind = __ldg(P.r_con_kind + k);
-            const double v = w.out[__ldg(P.r_con_src + k)];
-            if (kind == 1) acc += v;
-            else if (kind == -1) acc -= v;
-            else if (o.use_q) acc += (kind > 0 ? a0 : -a0) * v;
-        }
+        if (P.n_r_heavy && row_heavy(P, r)) continue;
+        const double acc = row_sum<Team>(P, w, o, a0, r, 0, 1);
         w.ivec[r] = acc;
         w.y[r] = o.lambda * w.sv[r] - acc;
+    }
+    for (int h = 0; h < P.n_r_heavy; ++h) {
+        const int r = __ldg(P.r_heavy + h);
+        const double acc = tm.sum(row_sum<Team>(P, w, o, a0, r, tm.rank(), tm.size()));
+        if (tm.rank() == 0) {
+            w.ivec[r] = acc;
+            w.y[r] = o.lambda * w.sv[r] - acc;
+        }
     }
 }
 
 // Jacobian slots: G' + Ti J Tcv + a0 Tq Jq Tcv (+ gmin Gones)
 template <class Team>
+__device__ __forceinline__ double slot_sum(const cdn_plan_dev& P, const Ws& w, const cdn_opts& o,
+                                           double a0, int e, int first, int stride) {
+    double v = 0.0;
+    const int c0 = __ldg(P.e_con_ptr + e), c1 = __ldg(P.e_con_ptr + e + 1);
+    for (int k = c0 + first; k < c1; k += stride) {
+        const int kind = __ldg(P.e_con_kind + k);
+        const double j = w.jac[__ldg(P.e_con_src + k)];
+        if (kind == 1) v += j;
+        else if (kind == -1) v -= j;
+        else if (o.use_q) v += (kind > 0 ? a0 : -a0) * j;
+    }
+    return v;
+}
+
+template <class Team>
 __device__ __forceinline__ void assemble(Team& tm, const cdn_plan_dev& P, const Ws& w,
                                          const cdn_opts& o) {
     const double a0 = o.use_q ? o.a0 : 0.0;
     for (int e = tm.rank(); e < P.nlu; e += tm.size()) {
+        if (P.n_e_heavy && __ldg(P.e_con_ptr + e + 1) - __ldg(P.e_con_ptr + e) > CDN_HEAVY) continue;
         double v = __ldg(P.e_g + e);
         if (o.use_q) v += a0 * __ldg(P.e_c + e);
         if (o.gmin != 0.0) v += o.gmin * __ldg(P.e_gones + e);
-        for (int k = __ldg(P.e_con_ptr + e); k < __ldg(P.e_con_ptr + e + 1); ++k) {
-            const int kind = __ldg(P.e_con_kind + k);
-            const double j = w.jac[__ldg(P.e_con_src + k)];
-            if (kind == 1) v += j;
-            else if (kind == -1) v -= j;
-            else if (o.use_q) v += (kind > 0 ? a0 : -a0) * j;
+        w.lu[e] = v + slot_sum<Team>(P, w, o, a0, e, 0, 1);
+    }
+    for (int h = 0; h < P.n_e_heavy; ++h) {
+        const int e = __ldg(P.e_heavy + h);
+        const double t = tm.sum(slot_sum<Team>(P, w, o, a0, e, tm.rank(), tm.size()));
+        if (tm.rank() == 0) {
+            double v = __ldg(P.e_g + e);
+            if (o.use_q) v += a0 * __ldg(P.e_c + e);
+            if (o.gmin != 0.0) v += o.gmin * __ldg(P.e_gones + e);
+            w.lu[e] = v + t;
         }
-        w.lu[e] = v;
     }
 }
 
 // q = C x + Tq q(x)   (device outputs must be current)
 template <class Team>
+__device__ __forceinline__ double charge_sum(const cdn_plan_dev& P, const Ws& w, int r, int first,
+                                             int stride) {
+    double acc = 0.0;
+    const int l0 = __ldg(P.r_lin_ptr + r), l1 = __ldg(P.r_lin_ptr + r + 1);
+    for (int k = l0 + first; k < l1; k += stride)
+        acc += __ldg(P.r_lin_c + k) * w.x[__ldg(P.r_lin_col + k)];
+    const int c0 = __ldg(P.r_con_ptr + r), c1 = __ldg(P.r_con_ptr + r + 1);
+    for (int k = c0 + first; k < c1; k += stride) {
+        const int kind = __ldg(P.r_con_kind + k);
+        if (kind == 2) acc += w.out[__ldg(P.r_con_src + k)];
+        else if (kind == -2) acc -= w.out[__ldg(P.r_con_src + k)];
+    }
+    return acc;
+}
+
+template <class Team>
 __device__ __forceinline__ void charge(Team& tm, const cdn_plan_dev& P, const Ws& w) {
     for (int r = tm.rank(); r < P.n; r += tm.size()) {
-        double acc = 0.0;
-        for (int k = __ldg(P.r_lin_ptr + r); k < __ldg(P.r_lin_ptr + r + 1); ++k)
-            acc += __ldg(P.r_lin_c + k) * w.x[__ldg(P.r_lin_col + k)];
-        for (int k = __ldg(P.r_con_ptr + r); k < __ldg(P.r_con_ptr + r + 1); ++k) {
-            const int kind = __ldg(P.r_con_kind + k);
-            if (kind == 2) acc += w.out[__ldg(P.r_con_src + k)];
-            else if (kind == -2) acc -= w.out[__ldg(P.r_con_src + k)];
-        }
-        w.q[r] = acc;
+        if (P.n_r_heavy && row_heavy(P, r)) continue;
+        w.q[r] = charge_sum<Team>(P, w, r, 0, 1);
+    }
+    for (int h = 0; h < P.n_r_heavy; ++h) {
+        const int r = __ldg(P.r_heavy + h);
+        const double acc = tm.sum(charge_sum<Team>(P, w, r, tm.rank(), tm.size()));
+        if (tm.rank() == 0) w.q[r] = acc;
     }
 }
 
@@ -398,13 +492,31 @@ __device__ __forceinline__ void dense_solve(Team& tm, const double* a, const int
 }
 
 // ---- sparse LU: static pivot order, entry-wise Crout by dependency level ----------------
+// Entries (rows) with more than CDN_HEAVY terms sit at the head of their level
+// and are reduced by the whole team (hub rows/columns).
 template <class Team>
 __device__ __forceinline__ void sparse_factor(Team& tm, const cdn_plan_dev& P, double* lu) {
     for (int l = 0; l < P.nlev_f; ++l) {
         const int e0 = __ldg(P.f_lvl_ptr + l), e1 = __ldg(P.f_lvl_ptr + l + 1);
-        for (int e = e0 + tm.rank(); e < e1; e += tm.size()) {
+        const int nh = __ldg(P.f_lvl_nheavy + l);
+        for (int h = 0; h < nh; ++h) {
+            const int e = e0 + h;
+            double part = 0.0;
+            const int t1 = __ldg(P.e_term_ptr + e + 1);
+            for (int t = __ldg(P.e_term_ptr + e) + tm.rank(); t < t1; t += tm.size())
+                part += lu[__ldg(P.e_term_l + t)] * lu[__ldg(P.e_term_u + t)];
+            part = tm.sum(part);
+            if (tm.rank() == 0) {
+                double v = lu[e] - part;
+                const int pv = __ldg(P.e_piv + e);
+                if (pv >= 0) v /= lu[pv];
+                lu[e] = v;
+            }
+        }
+        for (int e = e0 + nh + tm.rank(); e < e1; e += tm.size()) {
             double v = lu[e];
-            for (int t = __ldg(P.e_term_ptr + e); t < __ldg(P.e_term_ptr + e + 1); ++t)
+            const int t1 = __ldg(P.e_term_ptr + e + 1);
+            for (int t = __ldg(P.e_term_ptr + e); t < t1; ++t)
                 v -= lu[__ldg(P.e_term_l + t)] * lu[__ldg(P.e_term_u + t)];
             const int pv = __ldg(P.e_piv + e);
             if (pv >= 0) v /= lu[pv];
@@ -420,10 +532,21 @@ __device__ __forceinline__ void sparse_solve(Team& tm, const cdn_plan_dev& P, co
                                              const double* y, double* tmp, double* dx) {
     for (int l = 0; l < P.nlev_l; ++l) {
         const int r0 = __ldg(P.l_lvl_ptr + l), r1 = __ldg(P.l_lvl_ptr + l + 1);
-        for (int q = r0 + tm.rank(); q < r1; q += tm.size()) {
+        const int nh = __ldg(P.l_lvl_nheavy + l);
+        for (int h = 0; h < nh; ++h) {
+            const int i = __ldg(P.l_rows + r0 + h);
+            double part = 0.0;
+            const int k1 = __ldg(P.l_ptr + i + 1);
+            for (int k = __ldg(P.l_ptr + i) + tm.rank(); k < k1; k += tm.size())
+                part += lu[__ldg(P.l_slot + k)] * tmp[__ldg(P.l_col + k)];
+            part = tm.sum(part);
+            if (tm.rank() == 0) tmp[i] = y[__ldg(P.rowmap + i)] - part;
+        }
+        for (int q = r0 + nh + tm.rank(); q < r1; q += tm.size()) {
             const int i = __ldg(P.l_rows + q);
             double v = y[__ldg(P.rowmap + i)];
-            for (int k = __ldg(P.l_ptr + i); k < __ldg(P.l_ptr + i + 1); ++k)
+            const int k1 = __ldg(P.l_ptr + i + 1);
+            for (int k = __ldg(P.l_ptr + i); k < k1; ++k)
                 v -= lu[__ldg(P.l_slot + k)] * tmp[__ldg(P.l_col + k)];
             tmp[i] = v;
         }
@@ -431,10 +554,25 @@ __device__ __forceinline__ void sparse_solve(Team& tm, const cdn_plan_dev& P, co
     }
     for (int l = 0; l < P.nlev_u; ++l) {
         const int r0 = __ldg(P.u_lvl_ptr + l), r1 = __ldg(P.u_lvl_ptr + l + 1);
-        for (int q = r0 + tm.rank(); q < r1; q += tm.size()) {
+        const int nh = __ldg(P.u_lvl_nheavy + l);
+        for (int h = 0; h < nh; ++h) {
+            const int i = __ldg(P.u_rows + r0 + h);
+            double part = 0.0;
+            const int k1 = __ldg(P.u_ptr + i + 1);
+            for (int k = __ldg(P.u_ptr + i) + tm.rank(); k < k1; k += tm.size())
+                part += lu[__ldg(P.u_slot + k)] * tmp[__ldg(P.u_col + k)];
+            part = tm.sum(part);
+            if (tm.rank() == 0) {
+                const double v = (tmp[i] - part) / lu[__ldg(P.u_diag + i)];
+                tmp[i] = v;
+                dx[__ldg(P.colmap + i)] = v;
+            }
+        }
+        for (int q = r0 + nh + tm.rank(); q < r1; q += tm.size()) {
             const int i = __ldg(P.u_rows + q);
             double v = tmp[i];
-            for (int k = __ldg(P.u_ptr + i); k < __ldg(P.u_ptr + i + 1); ++k)
+            const int k1 = __ldg(P.u_ptr + i + 1);
+            for (int k = __ldg(P.u_ptr + i); k < k1; ++k)
                 v -= lu[__ldg(P.u_slot + k)] * tmp[__ldg(P.u_col + k)];
             v /= lu[__ldg(P.u_diag + i)];
             tmp[i] = v;

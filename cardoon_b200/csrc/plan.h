@@ -9,6 +9,8 @@
 #pragma once
 
 #define CDN_MAX_GROUPS 24
+// gather / term lists longer than this are summed cooperatively by the team
+#define CDN_HEAVY 256
 
 // one homogeneous group of nonlinear devices (same model, flags, port counts)
 struct cdn_group_dev {
@@ -35,6 +37,12 @@ struct cdn_plan_dev {
     int dense;                // 1: slots are a dense n*n row-major matrix
     int ndev;                 // nonlinear devices of one circuit instance
     int max_terms;
+    int n_e_heavy, n_r_heavy;
+    const int* e_heavy;       // [n_e_heavy] slots with long contribution lists
+    const int* r_heavy;       // [n_r_heavy] rows with long gather lists
+    const int* f_lvl_nheavy;  // [nlev_f] heavy entries at the head of each level
+    const int* l_lvl_nheavy;  // [nlev_l]
+    const int* u_lvl_nheavy;  // [nlev_u]
     const int* dev_g;         // [ndev] group of device d (flattened list)
     const int* dev_i;         // [ndev] index inside its group
     // ---- factorisation: entries ("slots") numbered in level order --------

@@ -149,6 +149,7 @@ struct cdn_plan {
     cdn_plan_dev dev;             // device pointers valid after bind
     std::vector<char> staging;    // packed index arrays
     struct Off {
+        long f_lvl_nheavy, l_lvl_nheavy, u_lvl_nheavy, e_heavy, r_heavy;
         long f_lvl_ptr, e_term_ptr, e_term_l, e_term_u, e_piv, e_g, e_c, e_gones, e_con_ptr,
             e_con_src, e_con_kind, l_lvl_ptr, l_rows, l_ptr, l_col, l_slot, u_lvl_ptr, u_rows,
             u_ptr, u_col, u_slot, u_diag, rowmap, colmap, r_lin_ptr, r_lin_col, r_lin_g,
@@ -224,7 +225,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     const bool dense = (c->ordering == 2);
     ivec ip(n), rptr(n + 1, 0), rcol, rslot, ucount(n, 0);
     std::vector<ivec> Lrow(n);
-    ivec f_lvl_ptr, e_term_ptr, e_term_l, e_term_u, e_piv;
+    ivec f_lvl_ptr, f_lvl_nheavy, e_term_ptr, e_term_l, e_term_u, e_piv;
     long nlu = 0, nterms = 0;
     int nlev_f = 0;
     P->max_terms = 0;
@@ -399,9 +400,15 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     ivec slot(nlu);
     for (long e = 0; e < nlu; ++e) f_lvl_ptr[lev[e] + 1]++;
     for (int l = 0; l < nlev_f; ++l) f_lvl_ptr[l + 1] += f_lvl_ptr[l];
+    f_lvl_nheavy.assign(nlev_f, 0);
     {
+        // inside a level the entries with long term lists come first: the
+        // kernels reduce those cooperatively (hub rows/columns)
         ivec cur(f_lvl_ptr.begin(), f_lvl_ptr.end() - 1);
-        for (long e = 0; e < nlu; ++e) slot[e] = cur[lev[e]]++;
+        for (long e = 0; e < nlu; ++e)
+            if (tcount[e] > CDN_HEAVY) { slot[e] = cur[lev[e]]++; f_lvl_nheavy[lev[e]]++; }
+        for (long e = 0; e < nlu; ++e)
+            if (tcount[e] <= CDN_HEAVY) slot[e] = cur[lev[e]]++;
     }
     e_term_ptr.assign(nlu + 1, 0); e_term_l.assign(nterms, 0); e_term_u.assign(nterms, 0); e_piv.assign(nlu, 0);
     for (long e = 0; e < nlu; ++e) { e_term_ptr[slot[e] + 1] = tcount[e]; P->max_terms = std::max(P->max_terms, tcount[e]); }
@@ -550,17 +557,29 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
         levu[i] = l;
         nlev_u = std::max(nlev_u, l + 1);
     }
-    auto by_level = [&](const ivec& lv, int nl, ivec& lptr, ivec& rows) {
+    auto by_level = [&](const ivec& lv, int nl, const ivec& rp, ivec& lptr, ivec& rows,
+                        ivec& nheavy) {
         lptr.assign(nl + 1, 0);
+        nheavy.assign(nl, 0);
         for (int i = 0; i < n; ++i) lptr[lv[i] + 1]++;
         for (int l = 0; l < nl; ++l) lptr[l + 1] += lptr[l];
         rows.resize(n);
         ivec cur(lptr.begin(), lptr.end() - 1);
-        for (int i = 0; i < n; ++i) rows[cur[lv[i]]++] = i;
+        for (int i = 0; i < n; ++i)
+            if (rp[i + 1] - rp[i] > CDN_HEAVY) { rows[cur[lv[i]]++] = i; nheavy[lv[i]]++; }
+        for (int i = 0; i < n; ++i)
+            if (rp[i + 1] - rp[i] <= CDN_HEAVY) rows[cur[lv[i]]++] = i;
     };
-    ivec l_lvl_ptr, l_rows, u_lvl_ptr, u_rows;
-    by_level(levl, nlev_l, l_lvl_ptr, l_rows);
-    by_level(levu, nlev_u, u_lvl_ptr, u_rows);
+    ivec l_lvl_ptr, l_rows, u_lvl_ptr, u_rows, l_lvl_nheavy, u_lvl_nheavy;
+    by_level(levl, nlev_l, l_ptr, l_lvl_ptr, l_rows, l_lvl_nheavy);
+    by_level(levu, nlev_u, u_ptr, u_lvl_ptr, u_rows, u_lvl_nheavy);
+    // slots / rows whose gather lists are long enough for a cooperative sum
+    ivec e_heavy, r_heavy;
+    for (long e = 0; e < nlu; ++e)
+        if (e_con_ptr[e + 1] - e_con_ptr[e] > CDN_HEAVY) e_heavy.push_back((int)e);
+    for (int r = 0; r < n; ++r)
+        if ((r_con_ptr[r + 1] - r_con_ptr[r]) + (r_lin_ptr[r + 1] - r_lin_ptr[r]) > CDN_HEAVY)
+            r_heavy.push_back(r);
     // permuted row i <- original row rowmap[i]; permuted col j -> unknown colmap[j]
     ivec rowmap(n), colmap(n);
     for (int r = 0; r < n; ++r) rowmap[ip[mrow[r]]] = r;
@@ -571,6 +590,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     cdn_plan::Off& O = P->off;
 #define PUT(name) do { O.name = put(B, name); P->reg[#name] = std::make_pair(O.name, (long)name.size()); } while (0)
     PUT(f_lvl_ptr);
+    PUT(f_lvl_nheavy); PUT(l_lvl_nheavy); PUT(u_lvl_nheavy); PUT(e_heavy); PUT(r_heavy);
     PUT(e_term_ptr);
     PUT(e_term_l);
     PUT(e_term_u);
@@ -612,6 +632,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     }
     cdn_plan_dev& D = P->dev;
     D.dense = dense ? 1 : 0;
+    D.n_e_heavy = (int)e_heavy.size(); D.n_r_heavy = (int)r_heavy.size();
     D.max_terms = P->max_terms;
     D.n = n; D.nlu = (int)nlu; D.nlev_f = nlev_f; D.nlev_l = nlev_l; D.nlev_u = nlev_u;
     D.ngroups = c->ngroups;
@@ -657,6 +678,8 @@ extern "C" int cdn_plan_bind(cdn_plan* P, void* dev_ws, long bytes, void* stream
     cdn_plan_dev& D = P->dev;
     const cdn_plan::Off& O = P->off;
 #define BIND(f, T) D.f = (const T*)(base + O.f)
+    BIND(f_lvl_nheavy, int); BIND(l_lvl_nheavy, int); BIND(u_lvl_nheavy, int);
+    BIND(e_heavy, int); BIND(r_heavy, int);
     BIND(f_lvl_ptr, int); BIND(e_term_ptr, int); BIND(e_term_l, int); BIND(e_term_u, int);
     BIND(e_piv, int); BIND(e_g, double); BIND(e_c, double); BIND(e_gones, double);
     BIND(e_con_ptr, int); BIND(e_con_src, int); BIND(e_con_kind, signed char);

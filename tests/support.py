@@ -82,3 +82,35 @@ def smoke_check():
         ro, rj = device_eval(elem, xin, True)
         assert rel_err(out, ro, 1e-18) < 1e-9, 'BSIM3 value mismatch'
         assert rel_err(jac, rj, 1e-12) < 1e-7, 'BSIM3 Jacobian mismatch'
+
+
+def chain_netlist(K, path=None):
+    """BASELINE config 4: K `inverter` sub-circuits of the reference's
+    workspace/inverter_chain_bsim.net (:17-22) in a chain, same model cards,
+    same vpulse:vin and vdc:vdd, cap:cload on the last node, tstep 0.1 ns,
+    tstop 20 ns, `.options maxdelta=1 maxiter=30 sparse=1`.
+    Returns the path of the generated deck."""
+    import tempfile
+    src = open(net('inverter_chain_bsim.net')).read()
+    models = src[src.index('.model nch'):src.index('.end')]
+    lines = ['# synthetic {0}-stage BSIM3 inverter chain'.format(K),
+             '.options maxdelta=1. maxiter=30 sparse=1',
+             '.analysis tran tstop=20n tstep=.1n im=trap verbose=0',
+             models,
+             'vdc:vdd 1 gnd vdc=3V',
+             'vpulse:vin o0 gnd v1=0 v2=3 pw=2n per=10n tr=3n tf=3n']
+    for k in range(1, K + 1):
+        lines.append('x{0} o{1} o{0} 1 gnd inverter'.format(k, k - 1))
+    lines += ['cap:cload o{0} gnd c=20fF'.format(K),
+              '.subckt inverter in out 1 2',
+              'mosbsim3:m1 1 in out 1 model=pch ad=8p asrc=8p cj=2e-4 '
+              'cjsw=1n ps=8u m=3',
+              'mosbsim3:m2 out in 2 2 model=nch ad=8p asrc=8p cj=2e-4 '
+              'cjsw=1n ps=8u',
+              '.ends', '.end', '']
+    if path is None:
+        fd, path = tempfile.mkstemp(suffix='.net', prefix='chain{0}_'.format(K))
+        os.close(fd)
+    with open(path, 'w') as f:
+        f.write('\n'.join(lines))
+    return path

@@ -8,6 +8,8 @@ Bars (BASELINE.json north_star): operating-point unknowns within 1e-9
 relative / 1e-12 absolute, Newton iteration counts within +-1, transient
 waveforms within the reference's own reltol/abstol at every accepted sample.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -195,3 +197,31 @@ def test_nd_interface_stepwise(lib):
     ref = R.run_tran(ckt, glVar, an.tstop, an.tstep, an.im, max_samples=30)
     err = np.abs(np.array(waves) - ref['X'])
     assert np.all(err < glVar.reltol * np.abs(ref['X']) + glVar.abstol)
+
+
+@pytest.mark.parametrize('team', ['block', 'grid'])
+def test_tran_inverter_chain_synthetic(lib, team):
+    """BASELINE config 4 at reduced length (K = 300 stages, N = 304): sparse
+    plan with the supply rail as a hub (cooperatively reduced gather and
+    Crout lists), run by one CTA and by the cooperative grid."""
+    from cardoon_b200 import _lib as L
+    path = S.chain_netlist(300)
+    ckt, queue = S.load_circuit(path)
+    an = [a for a in queue if a.anType == 'tran'][0]
+    nd.make_nodal_circuit(ckt)
+    topo = nd.get_topology(ckt)
+    dc = nd.DCNodal(ckt)
+    assert not dc.engine.dense
+    tran = nd.TransientNodal(ckt, Trapezoidal())
+    x, res, it = solve(dc.get_guess(), tran.get_source(0.).copy(),
+                       dc.convergence_helpers)
+    timeVec = np.arange(0., an.tstop, an.tstep)[:40]
+    src = tran.source_table(timeVec)
+    e = nd.Engine(topo, use_q=True, a0=2. / an.tstep, x_ref=x,
+                  team=L.TEAM_BLOCK if team == 'block' else L.TEAM_GRID)
+    assert e.info['max_con'] > 256 and e.info['max_terms'] > 256
+    wave, iters, resv, status = e.tran(x, src, list(range(topo.n)))
+    ref = R.run_tran(ckt, glVar, an.tstop, an.tstep, an.im, max_samples=40)
+    assert abs(it - ref['op_iterations']) <= 1
+    check_tran(wave[0], iters[0], int(status[0]), ref)
+    os.remove(path)

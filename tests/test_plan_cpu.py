@@ -118,3 +118,19 @@ def test_sparse_plan_soliton():
     assert info['nlu'] < 40000
     info = check_plan(topo, idx, ckt, False, 0., False, x)
     assert info["nlev_l"] < 400      # DC pivot order follows SuperLU row swaps
+
+
+def test_sparse_plan_chain_with_hub():
+    """Synthetic inverter chain: the supply rail is a hub whose gather and
+    Crout lists exceed CDN_HEAVY and are ordered to the head of their
+    levels."""
+    import os
+    path = S.chain_netlist(150)
+    try:
+        ckt, queue, topo, idx = setup(path)
+        x = np.random.default_rng(5).uniform(0., 3., topo.n)
+        info = check_plan(topo, idx, ckt, True, 2. / 1e-10, False, x)
+        assert info['max_con'] > 256
+        info = check_plan(topo, idx, ckt, False, 0., False, x)
+    finally:
+        os.remove(path)
