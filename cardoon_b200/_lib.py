@@ -44,7 +44,7 @@ class CircuitHost(C.Structure):
                 ('nE', C.c_long), ('e_row', _vp), ('e_col', _vp),
                 ('e_val', _vp),
                 ('ngroups', C.c_int), ('groups', C.POINTER(GroupHost)),
-                ('rowmatch', _vp), ('colorder', _vp)]
+                ('rowmatch', _vp), ('colorder', _vp), ('heavy', C.c_int)]
 
 
 class RunHost(C.Structure):

@@ -363,6 +363,9 @@ PLAN_INFO = ('n', 'nlu', 'nlev_f', 'nlev_l', 'nlev_u', 'nterms', 'ncon',
              'nnzA', 'max_terms', 'max_con', 'dev_out', 'dev_jac')
 
 
+HEAVY = 0          # 0 = library default (tests lower it to reach the hub paths)
+
+
 def create_plan(dll, ctx, topo, use_q, dense, match=None, ordering=None,
                 check=None, colorder=None):
     """cdn_plan_create on the index lists of ``topo``: returns the plan
@@ -378,6 +381,7 @@ def create_plan(dll, ctx, topo, use_q, dense, match=None, ordering=None,
             setattr(gh, name, g[name].ctypes.data_as(L._vp))
     ch = L.CircuitHost()
     ch.n = n
+    ch.heavy = HEAVY
     if dense:
         ch.ordering = L.ORDER_DENSE
     else:

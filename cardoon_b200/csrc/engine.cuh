@@ -343,7 +343,7 @@ __device__ __forceinline__ double row_sum(const cdn_plan_dev& P, const Ws& w, co
 
 __device__ __forceinline__ bool row_heavy(const cdn_plan_dev& P, int r) {
     return (__ldg(P.r_lin_ptr + r + 1) - __ldg(P.r_lin_ptr + r)) +
-           (__ldg(P.r_con_ptr + r + 1) - __ldg(P.r_con_ptr + r)) > CDN_HEAVY;
+           (__ldg(P.r_con_ptr + r + 1) - __ldg(P.r_con_ptr + r)) > P.heavy;
 }
 
 template <class Team>
@@ -387,7 +387,7 @@ __device__ __forceinline__ void assemble(Team& tm, const cdn_plan_dev& P, const 
                                          const cdn_opts& o) {
     const double a0 = o.use_q ? o.a0 : 0.0;
     for (int e = tm.rank(); e < P.nlu; e += tm.size()) {
-        if (P.n_e_heavy && __ldg(P.e_con_ptr + e + 1) - __ldg(P.e_con_ptr + e) > CDN_HEAVY) continue;
+        if (P.n_e_heavy && __ldg(P.e_con_ptr + e + 1) - __ldg(P.e_con_ptr + e) > P.heavy) continue;
         double v = __ldg(P.e_g + e);
         if (o.use_q) v += a0 * __ldg(P.e_c + e);
         if (o.gmin != 0.0) v += o.gmin * __ldg(P.e_gones + e);

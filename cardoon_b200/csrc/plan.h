@@ -37,6 +37,7 @@ struct cdn_plan_dev {
     int dense;                // 1: slots are a dense n*n row-major matrix
     int ndev;                 // nonlinear devices of one circuit instance
     int max_terms;
+    int heavy;                // list length above which the team reduces together
     int n_e_heavy, n_r_heavy;
     const int* e_heavy;       // [n_e_heavy] slots with long contribution lists
     const int* r_heavy;       // [n_r_heavy] rows with long gather lists

@@ -223,6 +223,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     P->nnzA = (long)keys.size();
 
     const bool dense = (c->ordering == 2);
+    const int HEAVY = c->heavy > 0 ? c->heavy : CDN_HEAVY;
     ivec ip(n), rptr(n + 1, 0), rcol, rslot, ucount(n, 0);
     std::vector<ivec> Lrow(n);
     ivec f_lvl_ptr, f_lvl_nheavy, e_term_ptr, e_term_l, e_term_u, e_piv;
@@ -406,9 +407,9 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
         // kernels reduce those cooperatively (hub rows/columns)
         ivec cur(f_lvl_ptr.begin(), f_lvl_ptr.end() - 1);
         for (long e = 0; e < nlu; ++e)
-            if (tcount[e] > CDN_HEAVY) { slot[e] = cur[lev[e]]++; f_lvl_nheavy[lev[e]]++; }
+            if (tcount[e] > HEAVY) { slot[e] = cur[lev[e]]++; f_lvl_nheavy[lev[e]]++; }
         for (long e = 0; e < nlu; ++e)
-            if (tcount[e] <= CDN_HEAVY) slot[e] = cur[lev[e]]++;
+            if (tcount[e] <= HEAVY) slot[e] = cur[lev[e]]++;
     }
     e_term_ptr.assign(nlu + 1, 0); e_term_l.assign(nterms, 0); e_term_u.assign(nterms, 0); e_piv.assign(nlu, 0);
     for (long e = 0; e < nlu; ++e) { e_term_ptr[slot[e] + 1] = tcount[e]; P->max_terms = std::max(P->max_terms, tcount[e]); }
@@ -566,9 +567,9 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
         rows.resize(n);
         ivec cur(lptr.begin(), lptr.end() - 1);
         for (int i = 0; i < n; ++i)
-            if (rp[i + 1] - rp[i] > CDN_HEAVY) { rows[cur[lv[i]]++] = i; nheavy[lv[i]]++; }
+            if (rp[i + 1] - rp[i] > HEAVY) { rows[cur[lv[i]]++] = i; nheavy[lv[i]]++; }
         for (int i = 0; i < n; ++i)
-            if (rp[i + 1] - rp[i] <= CDN_HEAVY) rows[cur[lv[i]]++] = i;
+            if (rp[i + 1] - rp[i] <= HEAVY) rows[cur[lv[i]]++] = i;
     };
     ivec l_lvl_ptr, l_rows, u_lvl_ptr, u_rows, l_lvl_nheavy, u_lvl_nheavy;
     by_level(levl, nlev_l, l_ptr, l_lvl_ptr, l_rows, l_lvl_nheavy);
@@ -576,9 +577,9 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     // slots / rows whose gather lists are long enough for a cooperative sum
     ivec e_heavy, r_heavy;
     for (long e = 0; e < nlu; ++e)
-        if (e_con_ptr[e + 1] - e_con_ptr[e] > CDN_HEAVY) e_heavy.push_back((int)e);
+        if (e_con_ptr[e + 1] - e_con_ptr[e] > HEAVY) e_heavy.push_back((int)e);
     for (int r = 0; r < n; ++r)
-        if ((r_con_ptr[r + 1] - r_con_ptr[r]) + (r_lin_ptr[r + 1] - r_lin_ptr[r]) > CDN_HEAVY)
+        if ((r_con_ptr[r + 1] - r_con_ptr[r]) + (r_lin_ptr[r + 1] - r_lin_ptr[r]) > HEAVY)
             r_heavy.push_back(r);
     // permuted row i <- original row rowmap[i]; permuted col j -> unknown colmap[j]
     ivec rowmap(n), colmap(n);
@@ -632,6 +633,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     }
     cdn_plan_dev& D = P->dev;
     D.dense = dense ? 1 : 0;
+    D.heavy = HEAVY;
     D.n_e_heavy = (int)e_heavy.size(); D.n_r_heavy = (int)r_heavy.size();
     D.max_terms = P->max_terms;
     D.n = n; D.nlu = (int)nlu; D.nlev_f = nlev_f; D.nlev_l = nlev_l; D.nlev_u = nlev_u;

@@ -79,6 +79,8 @@ typedef struct cdn_circuit_host {
     const cdn_group_host* groups;
     const int* rowmatch;  /* [n] unknown whose pivot row each row is, or NULL */
     const int* colorder;  /* [n] unknown eliminated at each position (3)     */
+    int heavy;            /* gather/Crout lists longer than this are reduced by
+                             the whole thread team (0 = default 256)         */
 } cdn_circuit_host;
 
 typedef struct cdn_plan cdn_plan;

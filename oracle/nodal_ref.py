@@ -723,14 +723,17 @@ def run_op(ckt, glVar, idx=None):
     return dict(x=x, res=res, iterations=it, idx=idx, dc=dc)
 
 
-def run_tran(ckt, glVar, tstop, tstep, im='trap', idx=None, max_samples=None):
-    """Fixed-step transient: dict(t, X[nsamples, N], iters, res, idx)."""
+def run_tran(ckt, glVar, tstop, tstep, im='trap', idx=None, max_samples=None,
+             x0=None):
+    """Fixed-step transient: dict(t, X[nsamples, N], iters, res, idx).
+    ``x0`` overrides the devices' initial guess of the operating-point solve
+    (a nodeset; the reference always starts from get_guess())."""
     idx = idx or prepare(ckt)
     opt = Options(glVar)
     imo = Trapezoidal() if im == 'trap' else BEuler()
     dc = RefDC(ckt, idx, opt)
     tran = RefTran(ckt, idx, opt, imo)
-    x = dc.get_guess()
+    x = dc.get_guess() if x0 is None else np.array(x0, dtype=float)
     sV = tran.get_source(0.)
     x, res, it = solve(x, sV, dc.helpers)
     op_iters = it

@@ -92,7 +92,7 @@ def chain_netlist(K, path=None):
     Returns the path of the generated deck."""
     import tempfile
     src = open(net('inverter_chain_bsim.net')).read()
-    models = src[src.index('.model nch'):src.index('.end')]
+    models = src[src.index('.model nch'):src.index('#.plot dc')]
     lines = ['# synthetic {0}-stage BSIM3 inverter chain'.format(K),
              '.options maxdelta=1. maxiter=30 sparse=1',
              '.analysis tran tstop=20n tstep=.1n im=trap verbose=0',
@@ -114,3 +114,18 @@ def chain_netlist(K, path=None):
     with open(path, 'w') as f:
         f.write('\n'.join(lines))
     return path
+
+
+def chain_nodeset(ckt, K, vdd=3.):
+    """Initial guess for the operating point of the synthetic chain with the
+    input low: inverter outputs alternate vdd / 0.  (From the all-zero guess
+    the reference's Newton needs O(K) iterations to propagate through the
+    chain and gives up at maxiter; its SuperLU path then meets exactly
+    singular matrices during source stepping.)"""
+    import numpy as np
+    x0 = np.zeros(ckt.nD_dimension)
+    x0[ckt.termDict['1'].nD_namRC] = vdd
+    for k in range(1, K + 1):
+        if k % 2:
+            x0[ckt.termDict['o{0}'.format(k)].nD_namRC] = vdd
+    return x0

@@ -200,28 +200,38 @@ def test_nd_interface_stepwise(lib):
 
 
 @pytest.mark.parametrize('team', ['block', 'grid'])
-def test_tran_inverter_chain_synthetic(lib, team):
-    """BASELINE config 4 at reduced length (K = 300 stages, N = 304): sparse
-    plan with the supply rail as a hub (cooperatively reduced gather and
-    Crout lists), run by one CTA and by the cooperative grid."""
+def test_tran_inverter_chain_synthetic(lib, team, monkeypatch):
+    """BASELINE config 4 at reduced length (K = 40 stages): sparse plan with
+    the supply rail as a hub -- its gather and Crout lists are reduced by the
+    whole team (threshold lowered so that this length reaches those paths)
+    -- run by one CTA and by the cooperative grid.  The operating point
+    starts from the alternating nodeset (see support.chain_nodeset)."""
     from cardoon_b200 import _lib as L
-    path = S.chain_netlist(300)
-    ckt, queue = S.load_circuit(path)
-    an = [a for a in queue if a.anType == 'tran'][0]
-    nd.make_nodal_circuit(ckt)
-    topo = nd.get_topology(ckt)
-    dc = nd.DCNodal(ckt)
-    assert not dc.engine.dense
-    tran = nd.TransientNodal(ckt, Trapezoidal())
-    x, res, it = solve(dc.get_guess(), tran.get_source(0.).copy(),
-                       dc.convergence_helpers)
-    timeVec = np.arange(0., an.tstop, an.tstep)[:40]
-    src = tran.source_table(timeVec)
-    e = nd.Engine(topo, use_q=True, a0=2. / an.tstep, x_ref=x,
-                  team=L.TEAM_BLOCK if team == 'block' else L.TEAM_GRID)
-    assert e.info['max_con'] > 256 and e.info['max_terms'] > 256
-    wave, iters, resv, status = e.tran(x, src, list(range(topo.n)))
-    ref = R.run_tran(ckt, glVar, an.tstop, an.tstep, an.im, max_samples=40)
-    assert abs(it - ref['op_iterations']) <= 1
-    check_tran(wave[0], iters[0], int(status[0]), ref)
-    os.remove(path)
+    K, nsamp = 40, 25
+    path = S.chain_netlist(K)
+    try:
+        ckt, queue = S.load_circuit(path)
+        an = [a for a in queue if a.anType == 'tran'][0]
+        nd.make_nodal_circuit(ckt)
+        topo = nd.get_topology(ckt)
+        monkeypatch.setattr(nd, 'HEAVY', 16)
+        monkeypatch.setattr(nd, 'DENSE_MAX', 8)
+        x0 = S.chain_nodeset(ckt, K)
+        dc = nd.DCNodal(ckt)
+        assert not dc.engine.dense
+        tran = nd.TransientNodal(ckt, Trapezoidal())
+        x, res, it = solve(x0.copy(), tran.get_source(0.).copy(),
+                           dc.convergence_helpers)
+        timeVec = np.arange(0., an.tstop, an.tstep)[:nsamp]
+        src = tran.source_table(timeVec)
+        e = nd.Engine(topo, use_q=True, a0=2. / an.tstep, x_ref=x,
+                      team=L.TEAM_BLOCK if team == 'block' else L.TEAM_GRID)
+        assert not e.dense
+        assert e.info['max_con'] > 16 and e.info['max_terms'] > 16
+        wave, iters, resv, status = e.tran(x, src, list(range(topo.n)))
+        ref = R.run_tran(ckt, glVar, an.tstop, an.tstep, an.im,
+                         max_samples=nsamp, x0=x0)
+        assert abs(it - ref['op_iterations']) <= 1
+        check_tran(wave[0], iters[0], int(status[0]), ref)
+    finally:
+        os.remove(path)

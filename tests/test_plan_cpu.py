@@ -120,17 +120,19 @@ def test_sparse_plan_soliton():
     assert info["nlev_l"] < 400      # DC pivot order follows SuperLU row swaps
 
 
-def test_sparse_plan_chain_with_hub():
+def test_sparse_plan_chain_with_hub(monkeypatch):
     """Synthetic inverter chain: the supply rail is a hub whose gather and
-    Crout lists exceed CDN_HEAVY and are ordered to the head of their
-    levels."""
+    Crout lists exceed the cooperative-reduction threshold and are ordered to
+    the head of their levels."""
     import os
-    path = S.chain_netlist(150)
+    monkeypatch.setattr(nd, 'HEAVY', 16)
+    K = 40
+    path = S.chain_netlist(K)
     try:
         ckt, queue, topo, idx = setup(path)
-        x = np.random.default_rng(5).uniform(0., 3., topo.n)
+        x = S.chain_nodeset(ckt, K) \
+            + np.random.default_rng(5).uniform(-.2, .2, topo.n)
         info = check_plan(topo, idx, ckt, True, 2. / 1e-10, False, x)
-        assert info['max_con'] > 256
-        info = check_plan(topo, idx, ckt, False, 0., False, x)
+        assert info['max_con'] > 16 and info['max_terms'] > 16
     finally:
         os.remove(path)
