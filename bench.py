@@ -628,8 +628,8 @@ def run_soliton(args, D):
         ach = algo / t_step / 1e9
         roof = dict(bound='hbm', achieved=ach, peak=hbm, unit='GB/s',
                     frac=ach / hbm, traffic=None,
-                    kernel='engine_block_kernel<DIODE, 256> (whole time '
-                           'loop, one CTA, state L2-resident)',
+                    kernel='engine_{0}_kernel<DIODE, 256> (whole time loop, '
+                           'state L2-resident)'.format(e.last_team()),
                     peak_source=how, bytes_per_newton_iteration=per_iter,
                     newton_iterations=it_total, nnzJ=nnz, nnzLU=nlu,
                     levels=dict(factor=info['nlev_f'], L=info['nlev_l'],
@@ -656,6 +656,159 @@ def run_soliton(args, D):
 
 
 # ---------------------------------------------------------------------------
+# workload: synthetic BSIM3 inverter chain
+# ---------------------------------------------------------------------------
+def chain_setup(K):
+    import io
+    import contextlib
+    from tests import support as S
+    from cardoon_b200.analyses import nodalCUDA as nd
+    path = S.chain_netlist(K)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ckt, queue = S.load_circuit(path)
+    finally:
+        os.remove(path)
+    an = [a for a in queue if a.anType == 'tran'][0]
+    nd.make_nodal_circuit(ckt)
+    return ckt, an, nd, S.chain_nodeset(ckt, K)
+
+
+def cpu_baseline_chain(K_full, K=150, max_samples=8):
+    from tests import support as S
+    from cardoon_b200.globalVars import glVar
+    from oracle import nodal_ref as R
+    import io
+    import contextlib
+    path = S.chain_netlist(K)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ckt, queue = S.load_circuit(path)
+    finally:
+        os.remove(path)
+    an = [a for a in queue if a.anType == 'tran'][0]
+    idx = R.prepare(ckt)
+    x0 = np.zeros(idx.dimension)
+    rows = idx.name_to_row()
+    x0[rows['1']] = 3.
+    for k in range(1, K + 1, 2):
+        x0[rows['o{0}'.format(k)]] = 3.
+    t0 = time.time()
+    r = R.run_tran(ckt, glVar, an.tstop, an.tstep, an.im, idx=idx,
+                   max_samples=max_samples, x0=x0)
+    dt = time.time() - t0
+    tps_small = (len(r['t']) - 1) / dt
+    return dict(value=tps_small * K / float(K_full), unit='timepoints/s',
+                cores=1, kind='port',
+                sample='{0}-stage chain, first {1} samples: {2:.3f} '
+                       'timepoints/s, scaled by {0}/{3} (the oracle\'s cost '
+                       'is linear in the number of devices)'.format(
+                           K, len(r['t']), tps_small, K_full))
+
+
+def run_chain(args, D):
+    torch = D.torch
+    K = args.n or 100000
+    t_setup = time.time()
+    ckt, an, nd, x0 = chain_setup(K)
+    from cardoon_b200.analyses.integration import Trapezoidal
+    from cardoon_b200.analyses.fsolve import NoConvergenceError
+    topo = nd.get_topology(ckt)
+    helper = nd.TransientNodal(ckt, Trapezoidal())
+    timeVec = np.arange(start=0., stop=an.tstop, step=an.tstep, dtype=float)
+    src = helper.source_table(timeVec)
+    dc = nd.Engine(topo, use_q=False, x_ref=x0)
+    r = dc._run_struct(nd.L.OP_NEWTON, helpers=1)
+    dc.x.copy_(torch.as_tensor(x0[None, :]))
+    dc.sv.copy_(torch.as_tensor(src[0]))
+    dc._launch(r)
+    if int(dc.status[0].item()) != 0:
+        raise NoConvergenceError('chain operating point did not converge')
+    op_it = int(dc.iters[0].item())
+    x = dc.x[0].cpu().numpy()
+    e = nd.Engine(topo, use_q=True, a0=2. / an.tstep, x_ref=x)
+    del dc
+    t_setup = time.time() - t_setup
+    rows = [ckt.termDict[nm].nD_namRC
+            for nm in ('o1', 'o2', 'o{0}'.format(K // 2), 'o{0}'.format(K))]
+    nsamples = len(timeVec)
+    state = {}
+
+    def step():
+        state['out'] = e.tran(x, src, rows, im='trap', sync=False)
+
+    clk = ClockSampler(D.local)
+    clk.start()
+    l0 = e.launches
+    ms, t0, t1 = timed_steps(D, step, args.steps, args.warmup)
+    launches = (e.launches - l0) * args.steps // (args.steps + args.warmup)
+    clocks = clk.stop(t0, t1)
+    wave, iters, res, status = state['out']
+    assert int(status[0].item()) == 0, 'chain transient did not converge'
+    value = D.world * (nsamples - 1) * args.steps / (ms * 1e-3)
+
+    def e2e_step():
+        e.tran(x, src, rows, im='trap', sync=True)
+
+    ne = max(1, min(args.steps, 2))
+    ms_e, _, _ = timed_steps(D, e2e_step, ne, 1)
+    e2e = dict(value=D.world * (nsamples - 1) * ne / (ms_e * 1e-3),
+               unit='timepoints/s',
+               h2d_bytes_per_step=int(src.size * 8 + x.size * 8),
+               d2h_bytes_per_step=int(wave.numel() * 8 + iters.numel() * 4
+                                      + res.numel() * 8))
+    line = None
+    if D.rank == 0:
+        info = e.info
+        n, nlu, nnz = info['n'], info['nlu'], info['nnzA']
+        it_total = float(iters.sum().item())
+        ndev = sum(g['n'] for g in topo.groups)
+        npar = len(topo.groups[0]['elems'][0].cuda_spec()['params'])
+        b_eval = 8. * ndev * (npar + 3)
+        b_asm = 8. * (nnz + 2 * n) + 4. * (info['ncon'] + nnz)
+        b_lu = 8. * (nnz + 2 * nlu)
+        b_solve = 8. * (nlu + 3 * n)
+        per_iter = b_eval + b_asm + b_lu + b_solve
+        per_sample = b_eval + b_solve + 8. * 8 * n
+        algo = it_total * per_iter + (nsamples - 1) * per_sample
+        t_step = ms * 1e-3 / args.steps
+        hbm, how = measured_peaks()
+        ach = algo / t_step / 1e9
+        roof = dict(bound='hbm', achieved=ach, peak=hbm, unit='GB/s',
+                    frac=ach / hbm, traffic=None,
+                    kernel='engine_{0}_kernel<BSIM3, 256> (whole time loop)'
+                    .format(e.last_team()),
+                    peak_source=how, bytes_per_newton_iteration=per_iter,
+                    newton_iterations=it_total, nnzJ=nnz, nnzLU=nlu,
+                    devices=ndev,
+                    levels=dict(factor=info['nlev_f'], L=info['nlev_l'],
+                                U=info['nlev_u']))
+        cpu = cpu_baseline_chain(K)
+        line = dict(metric='inverter-chain tran timepoints/s', value=value,
+                    unit='timepoints/s', n_gpus=D.world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms / args.steps,
+                    higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f64', data='synthetic',
+                    config=dict(workload='chain: synthetic {0}-stage BSIM3v3 '
+                                'inverter chain (N={1}, {2} mosbsim3, {3} '
+                                'samples, trapezoidal, h=0.1 ns), operating '
+                                'point from the alternating nodeset; one step '
+                                '= the whole time loop'.format(
+                                    K, n, ndev, nsamples),
+                                stages=K, samples=nsamples,
+                                op_iterations=op_it,
+                                avg_newton_iterations=it_total / nsamples,
+                                host_setup_s=t_setup,
+                                l2='state {0:.0f} MB + records {1:.0f} MB per '
+                                   'iteration: larger than L2 for the full '
+                                   'size'.format(e.ws_per * 8 / 1e6,
+                                                 ndev * npar * 8 / 1e6)),
+                    clocks=clocks, e2e=e2e, gpu_launches=launches,
+                    roofline=roof, cpu_baseline=cpu)
+    return line
+
+
+# ---------------------------------------------------------------------------
 # reference arm
 # ---------------------------------------------------------------------------
 def run_reference(args):
@@ -675,6 +828,10 @@ def run_reference(args):
         cpu = cpu_baseline_mc(procs=cores, per_proc=1, max_samples=120)
         metric = 'MC circuits/s (complete ring_bsim3 transients)'
         wl = 'mc: Monte Carlo of workspace/ring_bsim3.net'
+    elif args.workload == 'chain':
+        cpu = cpu_baseline_chain(args.n or 100000, K=300, max_samples=10)
+        metric = 'inverter-chain tran timepoints/s'
+        wl = 'chain: synthetic BSIM3v3 inverter chain'
     else:
         cpu = cpu_baseline_soliton(max_samples=300)
         metric = 'soliton tran timepoints/s'
@@ -695,7 +852,7 @@ def main():
     ap.add_argument('--impl', default='native',
                     choices=['native', 'reference'])
     ap.add_argument('--workload', default='mc',
-                    choices=['deveval', 'mc', 'soliton'])
+                    choices=['deveval', 'mc', 'soliton', 'chain'])
     ap.add_argument('--n', type=int, default=0,
                     help='instances per GPU (0 = workload default)')
     args = ap.parse_args()
@@ -711,8 +868,8 @@ def main():
         g.build()
     D = Dist(args.gpus)
     D.barrier()
-    line = dict(deveval=run_deveval, mc=run_mc,
-                soliton=run_soliton)[args.workload](args, D)
+    line = dict(deveval=run_deveval, mc=run_mc, soliton=run_soliton,
+                chain=run_chain)[args.workload](args, D)
     if D.rank == 0:
         print(json.dumps(line))
     D.close()

@@ -581,6 +581,12 @@ class Engine(object):
                                          lib.stream()))
         self.launches += 1
 
+    def last_team(self):
+        """Thread team of the last launch: 'tile', 'block' or 'grid'."""
+        info = (C.c_long * 16)()
+        self.lib.dll.cdn_plan_info(self.plan, info)
+        return {0: 'tile', 1: 'block', 2: 'grid'}.get(info[12], 'none')
+
     def view(self, name, b=0):
         """Slice of the kept state of instance ``b`` (device tensor)."""
         names = list(self.off)

@@ -69,7 +69,7 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     c.team = r->team;
     if (c.team < 0) {
         if (D->dense && D->n <= 64) c.team = CDN_TEAM_TILE;
-        else if (A.B > 1 || D->nlu < 200000) c.team = CDN_TEAM_BLOCK;
+        else if (A.B > 1 || D->dense || (D->nlu < 50000 && D->ndev < 2048)) c.team = CDN_TEAM_BLOCK;
         else c.team = CDN_TEAM_GRID;
     }
     if (c.team == CDN_TEAM_TILE) {
@@ -102,6 +102,7 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
         return cdn_fail(ctx, CDN_ERR_ARG, "engine: unknown team");
     }
 
+    cdn_plan_note_team(P, c.team);
     cudaError_t e;
     if ((ms & ~(unsigned)CDN_MS_DIODE) == 0) e = cdn_launch_ms_diode(A, c, st);
     else if ((ms & ~(unsigned)CDN_MS_BSIM3) == 0) e = cdn_launch_ms_bsim3(A, c, st);

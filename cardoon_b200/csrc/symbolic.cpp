@@ -159,6 +159,7 @@ struct cdn_plan {
     long nterms, ncon, nnzA;
     bool bound;
     bool dirty;
+    int last_team;
     cdn_plan_dev* dev_struct;     // device copy of `dev`
     int max_terms, max_con;
     ivec slot_row, slot_col;      // original (row, unknown) of every slot
@@ -182,6 +183,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     P->ctx = ctx;
     P->bound = false;
     P->dirty = true;
+    P->last_team = -1;
     P->dev_struct = nullptr;
     memset(&P->dev, 0, sizeof(P->dev));
 
@@ -664,6 +666,7 @@ extern "C" int cdn_plan_info(cdn_plan* P, long* info) {
     info[4] = P->dev.nlev_u; info[5] = P->nterms; info[6] = P->ncon; info[7] = P->nnzA;
     info[8] = P->max_terms; info[9] = P->max_con;
     info[10] = P->dev.dev_out_size; info[11] = P->dev.dev_jac_size;
+    info[12] = P->last_team;
     return CDN_OK;
 }
 
@@ -751,3 +754,4 @@ int cdn_plan_sync_device(cdn_plan* P, cudaStream_t st, const cdn_plan_dev** out)
     return CDN_OK;
 }
 cdn_ctx* cdn_plan_ctx(cdn_plan* P) { return P->ctx; }
+void cdn_plan_note_team(cdn_plan* P, int team) { P->last_team = team; }

@@ -90,7 +90,8 @@ int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan** out);
 long cdn_plan_bytes(cdn_plan* plan);   /* device bytes cdn_plan_bind needs   */
 /* info[0..11] = n, nlu, factor levels, L levels, U levels, Crout terms,
  * device contributions, nnz(J), longest term list, longest contribution
- * list, doubles of device outputs, doubles of device Jacobians             */
+ * list, doubles of device outputs, doubles of device Jacobians, thread team
+ * of the last cdn_engine_run (-1 none, 0 tile, 1 CTA, 2 grid); 16 longs    */
 int cdn_plan_info(cdn_plan* plan, long* info);
 int cdn_plan_bind(cdn_plan* plan, void* dev_ws, long bytes, void* stream);
 /* params[k*ldp + col] (device); per_inst = 1: instance b of a batch reads
