@@ -261,6 +261,7 @@ def run_deveval(args, D):
     from cardoon_b200._lib import get_lib
     lib = get_lib(D.local)
     inp = deveval_inputs(args.n or (1 << 22), seed=1234 + D.rank)
+    lib.dll.cdn_set_tuning(0, args.minblocks)
     n, nout, nxin = inp['n'], inp['nout'], inp['nxin']
     G = []
     for g in inp['groups']:
@@ -853,6 +854,8 @@ def main():
                     choices=['native', 'reference'])
     ap.add_argument('--workload', default='mc',
                     choices=['deveval', 'mc', 'soliton', 'chain'])
+    ap.add_argument('--minblocks', type=int, default=0,
+                    help='deveval tuning: CTAs/SM register limit (0 = default)')
     ap.add_argument('--n', type=int, default=0,
                     help='instances per GPU (0 = workload default)')
     args = ap.parse_args()

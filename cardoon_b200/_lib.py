@@ -83,6 +83,7 @@ def _declare(dll):
     dll.cdn_dev_eval.argtypes = [_vp, C.c_int, C.c_uint, C.c_long, C.c_int,
                                  _vp, C.c_long, _vp, _vp, _vp, _vp, _vp]
     dll.cdn_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
+    dll.cdn_set_tuning.argtypes = [C.c_int, C.c_int]
     dll.cdn_plan_create.argtypes = [_vp, C.POINTER(CircuitHost),
                                     C.POINTER(_vp)]
     dll.cdn_plan_bytes.argtypes = [_vp]

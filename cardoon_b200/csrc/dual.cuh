@@ -98,26 +98,53 @@ template <int P>
 CDN_HD Dual<P> operator*(double a, const Dual<P>& b) { return b * a; }
 
 // ---- division ---------------------------------------------------------------
+// One reciprocal per dual division: MUFU seed + two Newton steps (~1 ulp), then
+// the quotient gets the usual residual correction, which makes it the
+// correctly rounded a/b in all but rare half-way cases.  Zero, denormal,
+// huge, infinite and NaN divisors take the IEEE path so that special values
+// propagate exactly as in the host arithmetic the models were written for.
+CDN_HD double cdn_rcp(double x) {
+    const unsigned ex = (unsigned)__double2hiint(x) & 0x7ff00000u;
+    if (ex - 0x00100000u >= 0x7fc00000u) return 1.0 / x;     // rare, divergent
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+// a/b given inv ~ 1/b
+CDN_HD double cdn_div(double a, double b, double inv) {
+    double q = a * inv;
+    const double rem = fma(-b, q, a);
+    if (fabs(rem) <= 1.79769313486231570815e308) q = fma(rem, inv, q);   // finite
+    return q;
+}
 template <int P>
 CDN_HD Dual<P> operator/(const Dual<P>& a, const Dual<P>& b) {
-    Dual<P> r; r.v = a.v / b.v;
-    const double inv = 1.0 / b.v;
+    Dual<P> r;
+    const double inv = cdn_rcp(b.v);
+    r.v = cdn_div(a.v, b.v, inv);
 #pragma unroll
     for (int i = 0; i < P; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
     return r;
 }
 template <int P>
 CDN_HD Dual<P> operator/(const Dual<P>& a, double b) {
-    Dual<P> r; r.v = a.v / b;
-    const double inv = 1.0 / b;
+    Dual<P> r;
+    const double inv = cdn_rcp(b);
+    r.v = cdn_div(a.v, b, inv);
 #pragma unroll
     for (int i = 0; i < P; ++i) r.d[i] = a.d[i] * inv;
     return r;
 }
 template <int P>
 CDN_HD Dual<P> operator/(double a, const Dual<P>& b) {
-    Dual<P> r; r.v = a / b.v;
-    const double k = -r.v / b.v;
+    Dual<P> r;
+    const double inv = cdn_rcp(b.v);
+    r.v = cdn_div(a, b.v, inv);
+    const double k = -r.v * inv;
 #pragma unroll
     for (int i = 0; i < P; ++i) r.d[i] = k * b.d[i];
     return r;
@@ -135,10 +162,10 @@ template <int P> CDN_HD Dual<P> exp(const Dual<P>& x) {
     const double z = ::exp(x.v); return d_scale(x, z, z);
 }
 template <int P> CDN_HD Dual<P> log(const Dual<P>& x) {
-    return d_scale(x, ::log(x.v), 1.0 / x.v);
+    return d_scale(x, ::log(x.v), cdn_rcp(x.v));
 }
 template <int P> CDN_HD Dual<P> sqrt(const Dual<P>& x) {
-    const double z = ::sqrt(x.v); return d_scale(x, z, 0.5 / z);
+    const double z = ::sqrt(x.v); return d_scale(x, z, 0.5 * cdn_rcp(z));
 }
 template <int P> CDN_HD Dual<P> tan(const Dual<P>& x) {
     const double z = ::tan(x.v); return d_scale(x, z, 1.0 + z * z);
@@ -161,7 +188,7 @@ template <int P> CDN_HD Dual<P> dabs(const Dual<P>& x) {
 }
 // x**p, constant exponent
 template <int P> CDN_HD Dual<P> dpow(const Dual<P>& x, double p) {
-    const double z = ::pow(x.v, p); return d_scale(x, z, p * z / x.v);
+    const double z = ::pow(x.v, p); return d_scale(x, z, p * z * cdn_rcp(x.v));
 }
 template <int P> CDN_HD Dual<P> sq(const Dual<P>& x) { return x * x; }
 CDN_HD double sq(double x) { return x * x; }

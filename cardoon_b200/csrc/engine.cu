@@ -80,7 +80,9 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
             while (T < want && T < 32) T *= 2;
         }
         c.T = T;
-        c.tpb = 128;
+        // one CTA of 8 warps per SM when the batch fills the GPU: its tiles run
+        // in lockstep and share the instruction cache
+        c.tpb = ((long)A.B * T >= (long)ctx->sm_count * 128) ? 256 : 128;
         if (!A.ws) {
             // state in shared memory: shrink the CTA until it fits
             while (c.tpb > T && (long)(c.tpb / T) * per * 8 > 200 * 1024) c.tpb /= 2;

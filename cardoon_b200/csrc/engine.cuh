@@ -103,6 +103,11 @@ struct TileTeam {
         return v;
     }
     __device__ bool all(bool p) const { return tile.all(p); }
+    // True if p holds for any tile of the CTA.  Called by every thread of the
+    // CTA the same number of times: the tiles of a CTA iterate in lockstep so
+    // that their warps run the (large) device-evaluation code at the same time
+    // and share instruction-cache lines.
+    __device__ bool cta_any(bool p) const { return __syncthreads_or(p) != 0; }
     // largest v, smallest index on ties; NaN never wins
     __device__ void argmax(double& v, int& i) const {
 #pragma unroll
@@ -144,6 +149,7 @@ struct BlockTeam {
         return r;
     }
     __device__ bool all(bool p) const { return __syncthreads_and(p) != 0; }
+    __device__ bool cta_any(bool p) const { return p; }       // p is team-uniform
     __device__ void argmax(double& v, int& i) const {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -212,6 +218,7 @@ struct GridTeam {
         return r;
     }
     __device__ bool all(bool p) { return max(p ? 0.0 : 1.0) == 0.0; }
+    __device__ bool cta_any(bool p) const { return p; }       // p is team-uniform
     __device__ void argmax(double& v, int& i) {
         // only used by the dense LU, which is never run grid-wide
         v = max(v);
@@ -582,17 +589,80 @@ __device__ __forceinline__ void sparse_solve(Team& tm, const cdn_plan_dev& P, co
     }
 }
 
+// Same factorisation for n <= team size, one lane per matrix column: no
+// integer division, no shuffles, two barriers per pivot step.  Every lane
+// scans the pivot column itself (shared-memory broadcast reads).
+template <class Team>
+__device__ __forceinline__ void dense_factor_cols(Team& tm, double* a, int* piv, int n) {
+    const int j = tm.rank();
+    for (int k = 0; k < n; ++k) {
+        double best = fabs(a[k * n + k]);
+        int bi = k;
+        if (!(best >= 0.0)) best = -1.0;               // NaN never wins
+        for (int i = k + 1; i < n; ++i) {
+            const double v = fabs(a[i * n + k]);
+            if (v > best) { best = v; bi = i; }
+        }
+        tm.sync();                                     // all lanes have read column k
+        if (j < n && bi != k) {
+            const double t = a[k * n + j];
+            a[k * n + j] = a[bi * n + j];
+            a[bi * n + j] = t;
+        }
+        if (j == 0) piv[k] = bi;
+        tm.sync();
+        const double pinv = 1.0 / a[k * n + k];
+        if (j > k && j < n) {
+            const double akj = a[k * n + j];
+            for (int i = k + 1; i < n; ++i) a[i * n + j] -= (a[i * n + k] * pinv) * akj;
+        }
+        tm.sync();                                     // column k read by everybody
+        if (j == k)
+            for (int i = k + 1; i < n; ++i) a[i * n + k] *= pinv;
+    }
+    tm.sync();
+}
+
+// b <- A^{-1} b by one lane (tiny systems: the barriers of the cooperative
+// version cost more than the 2 n^2 flops)
+template <class Team>
+__device__ __forceinline__ void dense_solve_serial(Team& tm, const double* a, const int* piv,
+                                                   double* b, int n) {
+    if (tm.rank() == 0) {
+        for (int k = 0; k < n; ++k) {
+            const int p = piv[k];
+            if (p != k) { const double t = b[k]; b[k] = b[p]; b[p] = t; }
+        }
+        for (int i = 1; i < n; ++i) {
+            double v = b[i];
+            for (int k = 0; k < i; ++k) v -= a[i * n + k] * b[k];
+            b[i] = v;
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double v = b[i];
+            for (int k = i + 1; k < n; ++k) v -= a[i * n + k] * b[k];
+            b[i] = v / a[i * n + i];
+        }
+    }
+    tm.sync();
+}
+
 template <class Team>
 __device__ __forceinline__ void factor(Team& tm, const cdn_plan_dev& P, const Ws& w) {
-    if (P.dense) dense_factor(tm, w.lu, w.piv, P.n);
-    else sparse_factor(tm, P, w.lu);
+    if (P.dense) {
+        if (Team::kFlat && P.n <= tm.size()) dense_factor_cols(tm, w.lu, w.piv, P.n);
+        else dense_factor(tm, w.lu, w.piv, P.n);
+    } else {
+        sparse_factor(tm, P, w.lu);
+    }
 }
 
 // dx <- J^{-1} y  (y is consumed)
 template <class Team>
 __device__ __forceinline__ void lusolve(Team& tm, const cdn_plan_dev& P, const Ws& w) {
     if (P.dense) {
-        dense_solve(tm, w.lu, w.piv, w.y, P.n);
+        if (Team::kFlat && P.n <= 16) dense_solve_serial(tm, w.lu, w.piv, w.y, P.n);
+        else dense_solve(tm, w.lu, w.piv, w.y, P.n);
         for (int r = tm.rank(); r < P.n; r += tm.size()) w.dx[r] = w.y[r];
         tm.sync();
     } else {
@@ -607,11 +677,15 @@ __device__ __forceinline__ void lusolve(Team& tm, const cdn_plan_dev& P, const W
 // predictor re-uses (tran.py:181) -- unless errfunc is set.
 template <int MS, class Team>
 __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, const Ws& w,
-                                      const cdn_opts& o, double* res_out, bool* ok) {
+                                      const cdn_opts& o, bool active, double* res_out, bool* ok) {
     double res = 0.0;
     bool success = false;
     int it = 0;
-    for (; it < o.maxiter; ++it) {
+    // `active` teams iterate; the others only keep the CTA-level count of
+    // cta_any() calls in step (tile teams; see TileTeam::cta_any)
+    bool run = active;
+    while (tm.cta_any(run && it < o.maxiter)) {
+        if (!(run && it < o.maxiter)) continue;
         eval_devices<MS, true>(tm, P, b, w.x, w);
         assemble(tm, P, w, o);
         residual(tm, P, w, o);
@@ -645,7 +719,8 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
             n2 = ef < o.abstol;
             res = fmax(ef, res);
         }
-        if (n1 && n2) { success = true; ++it; break; }
+        ++it;
+        if (n1 && n2) { success = true; run = false; }
     }
     *res_out = res;
     *ok = success;
@@ -659,7 +734,8 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
 // successful intermediate solution.
 template <int MS, class Team>
 __device__ __noinline__ int homotopy(Team& tm, const cdn_plan_dev& P, int b, const Ws& w,
-                                     cdn_opts o, int mode, double* res_out, bool* ok) {
+                                     cdn_opts o, int mode, bool active, double* res_out,
+                                     bool* ok) {
     double stack[48];
     int sp = 0;
     stack[sp++] = 0.0;
@@ -668,13 +744,18 @@ __device__ __noinline__ int homotopy(Team& tm, const cdn_plan_dev& P, int b, con
     const double small = 1e-4;
     bool success = true;
     int tot = 0;
-    for (int r = tm.rank(); r < P.n; r += tm.size()) w.x[r] = w.xb[r];
-    tm.sync();
-    while (sp > 0) {
+    if (active) {
+        for (int r = tm.rank(); r < P.n; r += tm.size()) w.x[r] = w.xb[r];
+        tm.sync();
+    }
+    bool run = active;
+    while (tm.cta_any(run && sp > 0)) {
+        const bool go = run && sp > 0;
         if (mode == 0) o.gmin = 1e-3 / lam - 1e-3;
         else o.lambda = lam;
-        bool ok1;
-        tot += newton<MS>(tm, P, b, w, o, &res, &ok1);
+        bool ok1 = false;
+        tot += newton<MS>(tm, P, b, w, o, go, &res, &ok1);
+        if (!go) continue;
         if (ok1) {
             for (int r = tm.rank(); r < P.n; r += tm.size()) w.xb[r] = w.x[r];
             step = stack[sp - 1] - lam;
@@ -684,12 +765,12 @@ __device__ __noinline__ int homotopy(Team& tm, const cdn_plan_dev& P, int b, con
             if (sp < 48) stack[sp++] = lam;
             step *= 0.5;
             lam -= step;
-            if (lam < small || step < small) { success = false; tm.sync(); break; }
+            if (lam < small || step < small) { success = false; run = false; }
         }
         tm.sync();
     }
     *res_out = res;
-    *ok = success;
+    *ok = success && active;
     return tot;
 }
 
@@ -699,16 +780,24 @@ __device__ __noinline__ int homotopy(Team& tm, const cdn_plan_dev& P, int b, con
 template <int MS, class Team>
 __device__ __forceinline__ int solve_helpers(Team& tm, const cdn_plan_dev& P, int b,
                                              const Ws& w, const cdn_opts& o, int helpers,
-                                             double* res_out, bool* ok) {
-    if (helpers) {
+                                             bool active, double* res_out, bool* ok) {
+    if (helpers && active) {
         for (int r = tm.rank(); r < P.n; r += tm.size()) w.xb[r] = w.x[r];
         tm.sync();
     }
-    int it = newton<MS>(tm, P, b, w, o, res_out, ok);
-    if (*ok || !helpers) return it;
-    it = homotopy<MS>(tm, P, b, w, o, 0, res_out, ok);
-    if (*ok) return it;
-    return homotopy<MS>(tm, P, b, w, o, 1, res_out, ok);
+    int it = newton<MS>(tm, P, b, w, o, active, res_out, ok);
+    if (!helpers) return it;
+    bool need = active && !*ok;
+    if (!tm.cta_any(need)) return it;
+    double res2 = 0.0;
+    bool ok2 = false;
+    int it2 = homotopy<MS>(tm, P, b, w, o, 0, need, &res2, &ok2);
+    if (need) { it = it2; *res_out = res2; *ok = ok2; }
+    need = need && !ok2;
+    if (!tm.cta_any(need)) return it;
+    it2 = homotopy<MS>(tm, P, b, w, o, 1, need, &res2, &ok2);
+    if (need) { it = it2; *res_out = res2; *ok = ok2; }
+    return it;
 }
 
 // q(x) with a values-only device sweep (nodalSP.py:719-733)
@@ -763,77 +852,96 @@ __device__ __forceinline__ void chord(Team& tm, const cdn_plan_dev& P, const Ws&
 }
 
 // ---- one circuit instance, one operation ------------------------------------------------
+// `active` is false for the padding tiles of a ragged batch: they only take
+// part in the CTA-level lockstep (TileTeam::cta_any).
 template <int MS, class Team>
 __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
-                                             const cdn_plan_dev& P, int b, const Ws& w) {
+                                             const cdn_plan_dev& P, int b, const Ws& w,
+                                             bool active) {
     const cdn_opts& o = A.o;
     const int n = P.n;
     switch (A.op) {
     case CDN_OP_NEWTON: {
-        for (int r = tm.rank(); r < n; r += tm.size()) w.sv[r] = __ldg(A.sv_in + r);
-        tm.sync();
+        if (active) {
+            for (int r = tm.rank(); r < n; r += tm.size()) w.sv[r] = __ldg(A.sv_in + r);
+            tm.sync();
+        }
         double res; bool ok;
-        const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, &res, &ok);
-        if (tm.rank() == 0) {
+        const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, active, &res, &ok);
+        if (active && tm.rank() == 0) {
             A.iters[b] = it; A.res[b] = res; A.status[b] = ok ? 0 : -1;
         }
         break;
     }
     case CDN_OP_TRAN: {
-        if (A.init_ic) {                         // set_IC (nodalSP.py:666-696)
+        if (active && A.init_ic) {               // set_IC (nodalSP.py:666-696)
             update_q<MS>(tm, P, b, w);
             integ_init(tm, P, w);
         }
         int status = 0;
+        bool run = active;
         for (int i = A.first; i < A.nsamples; ++i) {
-            update_q<MS>(tm, P, b, w);           // accept(xOld)
-            integ_accept(tm, P, w, o);
-            make_rhs(tm, P, w, o, A.src_dc, A.nsrc, A.src_rows, A.src_val + (long)i * A.nsrc);
-            if (i > 1) {                         // chord predictor (tran.py:181)
-                chord(tm, P, w, o);
-                for (int r = tm.rank(); r < n; r += tm.size()) w.x[r] += w.dx[r];
-                tm.sync();
+            if (!tm.cta_any(run)) break;
+            if (run) {
+                update_q<MS>(tm, P, b, w);       // accept(xOld)
+                integ_accept(tm, P, w, o);
+                make_rhs(tm, P, w, o, A.src_dc, A.nsrc, A.src_rows,
+                         A.src_val + (long)i * A.nsrc);
+                if (i > 1) {                     // chord predictor (tran.py:181)
+                    chord(tm, P, w, o);
+                    for (int r = tm.rank(); r < n; r += tm.size()) w.x[r] += w.dx[r];
+                    tm.sync();
+                }
             }
             double res; bool ok;
-            const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, &res, &ok);
+            const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, run, &res, &ok);
+            if (!run) continue;
             const long at = (long)b * A.nsamples + i;
             if (tm.rank() == 0) { A.iters[at] = it; A.res[at] = res; }
-            if (!ok) { status = i; break; }
+            if (!ok) { status = i; run = false; continue; }
             for (int k = tm.rank(); k < A.nsave; k += tm.size())
                 A.wave[at * A.nsave + k] = w.x[__ldg(A.save_rows + k)];
         }
-        if (tm.rank() == 0) A.status[b] = status;
+        if (active && tm.rank() == 0) A.status[b] = status;
         break;
     }
     case CDN_OP_UPDATE_Q:
+        if (!active) break;
         update_q<MS>(tm, P, b, w);
         break;
     case CDN_OP_SET_IC:
+        if (!active) break;
         update_q<MS>(tm, P, b, w);
         integ_init(tm, P, w);
         break;
     case CDN_OP_ACCEPT:
+        if (!active) break;
         update_q<MS>(tm, P, b, w);
         integ_accept(tm, P, w, o);
         break;
     case CDN_OP_RHS:
+        if (!active) break;
         make_rhs(tm, P, w, o, A.sv_in, 0, nullptr, nullptr);
         break;
     case CDN_OP_CHORD:
+        if (!active) break;
         chord(tm, P, w, o);
         break;
     case CDN_OP_GET_I:
+        if (!active) break;
         eval_devices<MS, false>(tm, P, b, w.x, w);
         residual(tm, P, w, o);
         tm.sync();
         break;
     case CDN_OP_GET_I_JAC:
+        if (!active) break;
         eval_devices<MS, true>(tm, P, b, w.x, w);
         assemble(tm, P, w, o);
         residual(tm, P, w, o);
         tm.sync();
         break;
     case CDN_OP_SOLVE:
+        if (!active) break;
         factor(tm, P, w);
         lusolve(tm, P, w);
         break;
@@ -845,7 +953,7 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
 // Batches of small circuits: T lanes per instance; the state lives in shared
 // memory unless the caller wants it kept (A.ws != NULL).
 template <int MS, int T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
     extern __shared__ double smem[];
     const cdn_plan_dev& P = *A.plan;
@@ -853,17 +961,23 @@ engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
     const int tiles = blockDim.x / T;
     const int tile_id = threadIdx.x / T;
     const long per = ws_doubles(P.n, P.nlu, P.dev_out_size, P.dev_jac_size);
-    for (int b = blockIdx.x * tiles + tile_id; b < A.B; b += gridDim.x * tiles) {
-        double* base = A.ws ? A.ws + (long)b * A.ws_stride : smem + (long)tile_id * per;
+    // the loop bounds are CTA-uniform: padding tiles run along inactive
+    for (int b0 = blockIdx.x * tiles; b0 < A.B; b0 += gridDim.x * tiles) {
+        const int b = b0 + tile_id;
+        const bool active = b < A.B;
+        double* base = A.ws ? A.ws + (long)(active ? b : 0) * A.ws_stride
+                            : smem + (long)tile_id * per;
         const Ws w = ws_carve(base, P.n, P.nlu, P.dev_out_size, P.dev_jac_size);
-        if (!A.ws || A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN) {
+        if (active && (!A.ws || A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN)) {
             for (int r = tm.rank(); r < P.n; r += T) w.x[r] = A.x[(long)b * P.n + r];
             tm.sync();
         }
-        run_instance<MS>(tm, A, P, b, w);
-        tm.sync();
-        for (int r = tm.rank(); r < P.n; r += T) A.x[(long)b * P.n + r] = w.x[r];
-        tm.sync();
+        run_instance<MS>(tm, A, P, b, w, active);
+        if (active) {
+            tm.sync();
+            for (int r = tm.rank(); r < P.n; r += T) A.x[(long)b * P.n + r] = w.x[r];
+            tm.sync();
+        }
     }
 }
 
@@ -883,7 +997,7 @@ engine_block_kernel(const __grid_constant__ cdn_engine_args A) {
             for (int r = tm.rank(); r < P.n; r += tm.size()) w.x[r] = A.x[(long)b * P.n + r];
             tm.sync();
         }
-        run_instance<MS>(tm, A, P, b, w);
+        run_instance<MS>(tm, A, P, b, w, true);
         tm.sync();
         for (int r = tm.rank(); r < P.n; r += tm.size()) A.x[(long)b * P.n + r] = w.x[r];
         tm.sync();
@@ -903,7 +1017,7 @@ engine_grid_kernel(const __grid_constant__ cdn_engine_args A) {
         for (int r = tm.rank(); r < P.n; r += tm.size()) w.x[r] = A.x[r];
         tm.sync();
     }
-    run_instance<MS>(tm, A, P, 0, w);
+    run_instance<MS>(tm, A, P, 0, w, true);
     tm.sync();
     for (int r = tm.rank(); r < P.n; r += tm.size()) A.x[r] = w.x[r];
 }

@@ -171,6 +171,10 @@ long cdn_engine_ws_doubles(cdn_plan* plan);
 int cdn_engine_layout(cdn_plan* plan, long* off);
 int cdn_engine_run(cdn_plan* plan, const cdn_run_host* run, void* stream);
 
+/* tuning knobs for experiments (key 0: resident CTAs per SM the BSIM3
+ * evaluation kernel is register-limited for; 0 = default)                    */
+int cdn_set_tuning(int key, int value);
+
 /* measured FP64 FMA throughput of this GPU in FLOP/s (roofline denominator
  * for the device-evaluation kernels; none is published in MEASURED_PEAKS). */
 int cdn_fp64_peak(cdn_ctx* ctx, double* flops_per_s);
