@@ -44,7 +44,8 @@ class CircuitHost(C.Structure):
                 ('nE', C.c_long), ('e_row', _vp), ('e_col', _vp),
                 ('e_val', _vp),
                 ('ngroups', C.c_int), ('groups', C.POINTER(GroupHost)),
-                ('rowmatch', _vp), ('colorder', _vp), ('heavy', C.c_int)]
+                ('rowmatch', _vp), ('colorder', _vp), ('heavy', C.c_int),
+                ('skip_q', C.c_int)]
 
 
 class RunHost(C.Structure):

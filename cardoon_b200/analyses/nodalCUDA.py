@@ -382,6 +382,7 @@ def create_plan(dll, ctx, topo, use_q, dense, match=None, ordering=None,
     ch = L.CircuitHost()
     ch.n = n
     ch.heavy = HEAVY
+    ch.skip_q = 0 if use_q else 1
     if dense:
         ch.ordering = L.ORDER_DENSE
     else:
@@ -437,7 +438,8 @@ def sparse_plan(dll, ctx, topo, use_q, A_ref, ordering=None, check=None):
 _ARRAY_TYPES = dict(e_g=np.float64, e_c=np.float64, e_gones=np.float64,
                     r_lin_g=np.float64, r_lin_c=np.float64,
                     r_lin_gones=np.float64, e_con_kind=np.int8,
-                    r_con_kind=np.int8)
+                    r_con_kind=np.int8, e_con_pk=np.uint32,
+                    r_con_pk=np.uint32)
 
 
 def plan_array(dll, plan, name):
@@ -539,9 +541,22 @@ class Engine(object):
         if params is None:
             params = self.topo.pack_params()
         self.params = []
+        self.pidx = []
         for k, (g, p) in enumerate(zip(self.topo.groups, params)):
+            pidx = None
+            if not hasattr(p, 'data_ptr') and p.shape[1] >= 64:
+                # identical records (devices sharing a model card and
+                # geometry) are stored once and addressed through an index:
+                # a warp then reads one address per parameter
+                uniq, inv = np.unique(p, axis=1, return_inverse=True)
+                if uniq.shape[1] * 4 <= p.shape[1]:
+                    pidx = lib.dev(np.ascontiguousarray(
+                        inv.reshape(-1).astype(np.int32)))
+                    ncol = p.shape[1]
+                    p = np.ascontiguousarray(uniq)
             t = p if hasattr(p, 'data_ptr') else lib.dev(p)
-            ncol = t.shape[1]
+            if pidx is None:
+                ncol = t.shape[1]
             if ncol == g['n']:
                 per_inst = 0
             elif ncol == g['n'] * self.B:
@@ -551,8 +566,10 @@ class Engine(object):
                                  'devices x {3} instances'.format(
                                      k, ncol, g['n'], self.B))
             self.params.append(t)
+            self.pidx.append(pidx)
             lib.check(lib.dll.cdn_plan_set_group_params(
-                self.plan, k, lib.ptr(t), int(t.stride(0)), None, per_inst))
+                self.plan, k, lib.ptr(t), int(t.stride(0)), lib.ptr(pidx),
+                per_inst))
 
     # ---- launches ---------------------------------------------------------------
     def _run_struct(self, op, a0=None, gmin=0., lam=1., helpers=0):

@@ -50,6 +50,7 @@ struct cdn_engine_args {
     // transient
     int nsamples, first, init_ic, nsrc, nsave;
     int helpers;                // 1: fall back to gmin / source stepping in-kernel
+    int smem_lu;                // block team: LU values + solve vectors in shared memory
     const int* src_rows;        // [nsrc] rows with a time-dependent source
     const double* src_val;      // [nsamples][nsrc] summed source value per row
     const double* src_dc;       // [n] constant part of the source vector
@@ -337,13 +338,15 @@ __device__ __forceinline__ double row_sum(const cdn_plan_dev& P, const Ws& w, co
         if (o.gmin != 0.0) g += o.gmin * __ldg(P.r_lin_gones + k);
         acc += g * w.x[__ldg(P.r_lin_col + k)];
     }
+    // device outputs: branch-free, the sign and the a0 factor of charge rows
+    // are decoded from the packed entry (DC plans hold no charge entries)
     const int c0 = __ldg(P.r_con_ptr + r), c1 = __ldg(P.r_con_ptr + r + 1);
+#pragma unroll 4
     for (int k = c0 + first; k < c1; k += stride) {
-        const int kind = __ldg(P.r_con_kind + k);
-        const double v = w.out[__ldg(P.r_con_src + k)];
-        if (kind == 1) acc += v;
-        else if (kind == -1) acc -= v;
-        else if (o.use_q) acc += (kind > 0 ? a0 : -a0) * v;
+        const unsigned pk = __ldg(P.r_con_pk + k);
+        double c = (pk & (1u << 30)) ? a0 : 1.0;
+        if (pk & (1u << 29)) c = -c;
+        acc = fma(c, w.out[pk & 0x1fffffffu], acc);
     }
     return acc;
 }
@@ -379,12 +382,12 @@ __device__ __forceinline__ double slot_sum(const cdn_plan_dev& P, const Ws& w, c
                                            double a0, int e, int first, int stride) {
     double v = 0.0;
     const int c0 = __ldg(P.e_con_ptr + e), c1 = __ldg(P.e_con_ptr + e + 1);
+#pragma unroll 4
     for (int k = c0 + first; k < c1; k += stride) {
-        const int kind = __ldg(P.e_con_kind + k);
-        const double j = w.jac[__ldg(P.e_con_src + k)];
-        if (kind == 1) v += j;
-        else if (kind == -1) v -= j;
-        else if (o.use_q) v += (kind > 0 ? a0 : -a0) * j;
+        const unsigned pk = __ldg(P.e_con_pk + k);
+        double c = (pk & (1u << 30)) ? a0 : 1.0;
+        if (pk & (1u << 29)) c = -c;
+        v = fma(c, w.jac[pk & 0x1fffffffu], v);
     }
     return v;
 }
@@ -422,9 +425,11 @@ __device__ __forceinline__ double charge_sum(const cdn_plan_dev& P, const Ws& w,
         acc += __ldg(P.r_lin_c + k) * w.x[__ldg(P.r_lin_col + k)];
     const int c0 = __ldg(P.r_con_ptr + r), c1 = __ldg(P.r_con_ptr + r + 1);
     for (int k = c0 + first; k < c1; k += stride) {
-        const int kind = __ldg(P.r_con_kind + k);
-        if (kind == 2) acc += w.out[__ldg(P.r_con_src + k)];
-        else if (kind == -2) acc -= w.out[__ldg(P.r_con_src + k)];
+        const unsigned pk = __ldg(P.r_con_pk + k);
+        if (pk & (1u << 30)) {
+            const double v = w.out[pk & 0x1fffffffu];
+            acc += (pk & (1u << 29)) ? -v : v;
+        }
     }
     return acc;
 }
@@ -981,25 +986,41 @@ engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
     }
 }
 
-// One CTA per circuit instance, state in global memory.
+// One CTA per circuit instance, state in global memory (L2).  When the caller
+// provides enough dynamic shared memory (A.smem_lu), the LU values and the two
+// work vectors of the triangular solves live there for the whole launch: the
+// level-scheduled factorisation and solves are chains of short dependent
+// loads, and their latency, not bandwidth, is what a time step costs.
 template <int MS, int TPB>
 __global__ void __launch_bounds__(TPB)
 engine_block_kernel(const __grid_constant__ cdn_engine_args A) {
+    extern __shared__ double dsm[];
     __shared__ double sred[64];
     __shared__ int ired[64];
     const cdn_plan_dev& P = *A.plan;
     BlockTeam tm;
     tm.sred = sred; tm.ired = ired;
     for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
-        const Ws w = ws_carve(A.ws + (long)b * A.ws_stride, P.n, P.nlu, P.dev_out_size,
-                              P.dev_jac_size);
+        Ws w = ws_carve(A.ws + (long)b * A.ws_stride, P.n, P.nlu, P.dev_out_size,
+                        P.dev_jac_size);
+        double* const g_lu = w.lu;
+        double* const g_y = w.y;
+        if (A.smem_lu) {
+            w.lu = dsm; w.tmp = dsm + P.nlu; w.y = w.tmp + P.n;
+            for (int e = tm.rank(); e < P.nlu; e += tm.size()) w.lu[e] = g_lu[e];
+            for (int r = tm.rank(); r < P.n; r += tm.size()) w.y[r] = g_y[r];
+        }
         if (A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN) {
             for (int r = tm.rank(); r < P.n; r += tm.size()) w.x[r] = A.x[(long)b * P.n + r];
-            tm.sync();
         }
+        tm.sync();
         run_instance<MS>(tm, A, P, b, w, true);
         tm.sync();
         for (int r = tm.rank(); r < P.n; r += tm.size()) A.x[(long)b * P.n + r] = w.x[r];
+        if (A.smem_lu) {
+            for (int e = tm.rank(); e < P.nlu; e += tm.size()) g_lu[e] = w.lu[e];
+            for (int r = tm.rank(); r < P.n; r += tm.size()) g_y[r] = w.y[r];
+        }
         tm.sync();
     }
 }

@@ -14,6 +14,11 @@ struct cdn_launch_cfg {
     int sm_count;
 };
 
+#define CDN_MS_DIODE (CDN_MS(CDN_MODEL_DIODE))
+#define CDN_MS_BSIM3 (CDN_MS(CDN_MODEL_BSIM3))
+#define CDN_MS_ALL (CDN_MS(CDN_MODEL_DIODE) | CDN_MS(CDN_MODEL_BJT) | CDN_MS(CDN_MODEL_SVBJT) | \
+                    CDN_MS(CDN_MODEL_BSIM3) | CDN_MS(CDN_MODEL_EKV) | CDN_MS(CDN_MODEL_MEMR))
+
 template <class K>
 static cudaError_t set_smem(K kernel, long smem) {
     if (smem > 48 * 1024)
@@ -40,9 +45,20 @@ static cudaError_t launch_engine(const cdn_engine_args& A, cdn_launch_cfg c, cud
         case 32: return launch_tile<MS, 32>(A, c, st);
         default: return cudaErrorInvalidValue;
         }
-    case CDN_TEAM_BLOCK:
-        engine_block_kernel<MS, 256><<<c.blocks, 256, 0, st>>>(A);
+    case CDN_TEAM_BLOCK: {
+        // light model sets run 1024 threads per CTA (64 registers each); the
+        // heavy models need their 255 registers
+        if (MS == CDN_MS_DIODE && c.tpb == 1024) {
+            cudaError_t e = set_smem(engine_block_kernel<MS, (MS == CDN_MS_DIODE ? 1024 : 256)>, c.smem);
+            if (e != cudaSuccess) return e;
+            engine_block_kernel<MS, (MS == CDN_MS_DIODE ? 1024 : 256)><<<c.blocks, 1024, c.smem, st>>>(A);
+            return cudaGetLastError();
+        }
+        cudaError_t e = set_smem(engine_block_kernel<MS, 256>, c.smem);
+        if (e != cudaSuccess) return e;
+        engine_block_kernel<MS, 256><<<c.blocks, 256, c.smem, st>>>(A);
         return cudaGetLastError();
+    }
     case CDN_TEAM_GRID: {
         int per_sm = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
@@ -58,11 +74,6 @@ static cudaError_t launch_engine(const cdn_engine_args& A, cdn_launch_cfg c, cud
     default: return cudaErrorInvalidValue;
     }
 }
-
-#define CDN_MS_DIODE (CDN_MS(CDN_MODEL_DIODE))
-#define CDN_MS_BSIM3 (CDN_MS(CDN_MODEL_BSIM3))
-#define CDN_MS_ALL (CDN_MS(CDN_MODEL_DIODE) | CDN_MS(CDN_MODEL_BJT) | CDN_MS(CDN_MODEL_SVBJT) | \
-                    CDN_MS(CDN_MODEL_BSIM3) | CDN_MS(CDN_MODEL_EKV) | CDN_MS(CDN_MODEL_MEMR))
 
 cudaError_t cdn_launch_ms_diode(const cdn_engine_args& A, const cdn_launch_cfg& c, cudaStream_t st);
 cudaError_t cdn_launch_ms_bsim3(const cdn_engine_args& A, const cdn_launch_cfg& c, cudaStream_t st);

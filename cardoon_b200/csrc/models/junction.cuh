@@ -26,10 +26,12 @@ CDN_HD Dual<P> junction_qd(const PV& j, const Dual<P>& vd) {
     const double fc = j[J_fc], t_vj = j[J_t_vj], k4 = j[J_k4], k5 = j[J_k5];
     const double k6 = j[J_k6], k7 = j[J_k7], m = j[J_m];
     const Dual<P> b = fc * t_vj - vd;
-    const Dual<P> c = k5 * (1.0 - dpow(1.0 - vd / t_vj, k4));
+    const Dual<P> u = 1.0 - vd / t_vj;
+    // (1 - vd/vj)**(1 - m): the default grading m = 1/2 is a square root
+    const Dual<P> c = k5 * (1.0 - ((k4 == 0.5) ? sqrt(u) : dpow(u, k4)));
     const Dual<P> d = k6 * ((1.0 - fc * (1.0 + m)) * vd
                             + .5 * m * vd * vd / t_vj - k7)
-                      + k5 * (1.0 - ::pow(1.0 - fc, k4));
+                      + j[J_k8];          // k5 (1 - (1-fc)**k4), folded on the host
     return select(b, c, d);
 }
 

@@ -58,6 +58,8 @@ struct cdn_plan_dev {
     const int* e_con_ptr;     // [nlu+1] device-Jacobian contributions
     const int* e_con_src;     // [ncon]  index into dev_jac
     const signed char* e_con_kind;  // +-1 current row, +-2 charge row (x a0)
+    const unsigned* e_con_pk;  // src | minus << 29 | charge << 30 (what the kernels read)
+    const unsigned* r_con_pk;
     // ---- triangular solves (permuted index space) --------------------------
     const int* l_lvl_ptr;     // [nlev_l+1]
     const int* l_rows;        // [n] rows ordered by level

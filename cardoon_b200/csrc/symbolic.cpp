@@ -153,7 +153,8 @@ struct cdn_plan {
         long f_lvl_ptr, e_term_ptr, e_term_l, e_term_u, e_piv, e_g, e_c, e_gones, e_con_ptr,
             e_con_src, e_con_kind, l_lvl_ptr, l_rows, l_ptr, l_col, l_slot, u_lvl_ptr, u_rows,
             u_ptr, u_col, u_slot, u_diag, rowmap, colmap, r_lin_ptr, r_lin_col, r_lin_g,
-            r_lin_c, r_lin_gones, r_con_ptr, r_con_src, r_con_kind, dev_g, dev_i;
+            r_lin_c, r_lin_gones, r_con_ptr, r_con_src, r_con_kind, dev_g, dev_i, e_con_pk,
+            r_con_pk;
         long gv[CDN_MAX_GROUPS][2];
     } off;
     long nterms, ncon, nnzA;
@@ -463,7 +464,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
         out_size += (long)(G.ncs + G.nqs) * G.n;
         jac_size += (long)(G.ncs + G.nqs) * G.nxin * G.n;
     }
-    if (jac_size > 2000000000L) { delete P; return cdn_fail(ctx, CDN_ERR_STATE, "plan: device Jacobian buffer too large"); }
+    if (jac_size > 500000000L || out_size > 500000000L) { delete P; return cdn_fail(ctx, CDN_ERR_STATE, "plan: device Jacobian buffer too large"); }
     struct Con { int dst; int src; signed char kind; };
     std::vector<Con> econ, rcon;
     for (int g = 0; g < c->ngroups; ++g) {
@@ -472,6 +473,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
         for (int i = 0; i < G.n; ++i)
             for (int o = 0; o < nout; ++o) {
                 const bool chg = o >= G.ncs;
+                if (chg && c->skip_q) continue;
                 const int rp = chg ? G.qpos[(long)(o - G.ncs) * G.n + i] : G.cpos[(long)o * G.n + i];
                 const int rn = chg ? G.qneg[(long)(o - G.ncs) * G.n + i] : G.cneg[(long)o * G.n + i];
                 const signed char kp = chg ? 2 : 1, kn = chg ? -2 : -1;
@@ -503,6 +505,17 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     std::vector<signed char> e_con_kind, r_con_kind;
     to_csr(econ, nlu, e_con_ptr, e_con_src, e_con_kind, &P->max_con);
     to_csr(rcon, n, r_con_ptr, r_con_src, r_con_kind, nullptr);
+    // packed gather entries: source index in the low 29 bits, bit 29 = minus
+    // sign, bit 30 = charge row (scaled by a0)
+    auto pack = [](const ivec& src, const std::vector<signed char>& kind) {
+        std::vector<unsigned> pk(src.size());
+        for (size_t k = 0; k < src.size(); ++k) {
+            const int kd = kind[k];
+            pk[k] = (unsigned)src[k] | ((kd < 0) ? (1u << 29) : 0u) | ((kd == 2 || kd == -2) ? (1u << 30) : 0u);
+        }
+        return pk;
+    };
+    std::vector<unsigned> e_con_pk = pack(e_con_src, e_con_kind), r_con_pk = pack(r_con_src, r_con_kind);
     P->ncon = (long)econ.size();
     std::vector<Con>().swap(econ); std::vector<Con>().swap(rcon);
 
@@ -625,6 +638,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     PUT(r_con_ptr);
     PUT(r_con_src);
     PUT(r_con_kind);
+    PUT(e_con_pk); PUT(r_con_pk);
     {
         ivec dg, di;
         for (int g = 0; g < c->ngroups; ++g)
@@ -695,6 +709,7 @@ extern "C" int cdn_plan_bind(cdn_plan* P, void* dev_ws, long bytes, void* stream
     BIND(r_lin_gones, double); BIND(r_con_ptr, int); BIND(r_con_src, int);
     BIND(r_con_kind, signed char);
     BIND(dev_g, int); BIND(dev_i, int);
+    BIND(e_con_pk, unsigned); BIND(r_con_pk, unsigned);
 #undef BIND
     for (int g = 0; g < D.ngroups; ++g) {
         D.groups[g].vpos = (const int*)(base + O.gv[g][0]);

@@ -60,6 +60,9 @@ class Junction:
             rec[2:7] = (self._t_vj, self._k4, self._k5, self._k6, self._k7)
             rec[7] = self.fc
             rec[8] = self.m
+            # constant term of the forward-bias branch of get_qd (reference
+            # diode.py:93-96), folded with the reference's own arithmetic
+            rec[11] = self._k5 * (1. - pow(1. - self.fc, self._k4))
         if self.stateVariable:
             rec[9] = self._alpha
             rec[10] = self._svth

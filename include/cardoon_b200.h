@@ -81,6 +81,7 @@ typedef struct cdn_circuit_host {
     const int* colorder;  /* [n] unknown eliminated at each position (3)     */
     int heavy;            /* gather/Crout lists longer than this are reduced by
                              the whole thread team (0 = default 256)         */
+    int skip_q;           /* 1: DC plan, charge outputs contribute nothing   */
 } cdn_circuit_host;
 
 typedef struct cdn_plan cdn_plan;
