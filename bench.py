@@ -846,6 +846,16 @@ def run_reference(args):
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON result): everything else any
+    # library prints (NCCL banner, netlist warnings) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + '\n').encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -864,7 +874,7 @@ def main():
     if args.impl == 'reference':
         line = run_reference(args)
         if line is not None:
-            print(json.dumps(line))
+            emit(line)
         return
     import __graft_entry__ as g
     if int(os.environ.get('LOCAL_RANK', '0')) == 0:
@@ -874,7 +884,7 @@ def main():
     line = dict(deveval=run_deveval, mc=run_mc, soliton=run_soliton,
                 chain=run_chain)[args.workload](args, D)
     if D.rank == 0:
-        print(json.dumps(line))
+        emit(line)
     D.close()
 
 
