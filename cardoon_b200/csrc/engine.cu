@@ -94,7 +94,7 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     } else if (c.team == CDN_TEAM_BLOCK) {
         if (!A.ws) return cdn_fail(ctx, CDN_ERR_ARG, "engine: block team needs a workspace");
         c.blocks = A.B;
-        c.tpb = ((ms & ~(unsigned)CDN_MS_DIODE) == 0 && D->n >= 1024) ? 512 : 256;
+        c.tpb = ((ms & ~(unsigned)CDN_MS_DIODE) == 0 && D->n >= 1024) ? 1024 : 256;
         // LU values + two work vectors in shared memory when they fit
         const long need = ((long)D->nlu + 2L * D->n) * 8;
         if (!D->dense && need <= 220 * 1024) { c.smem = need; A.smem_lu = 1; }

@@ -504,54 +504,13 @@ __device__ __forceinline__ void dense_solve(Team& tm, const double* a, const int
 }
 
 // ---- sparse LU: static pivot order, entry-wise Crout by dependency level ----------------
-// Entries (rows) with more than P.heavy terms sit at the head of their level
+// Entries (rows) with more than CDN_HEAVY terms sit at the head of their level
 // and are reduced by the whole team (hub rows/columns).
-//
-// A level is a short chain of dependent loads followed by a barrier, and the
-// chain -- not bandwidth -- is what a level costs.  Everything in it that
-// depends only on the plan (which entry, where its term list starts, the first
-// CDN_PRE operand indexes) is therefore fetched one level ahead into registers,
-// so that between two barriers a thread only touches the LU values and work
-// vectors (shared memory on the block team) for its first entry of the level.
-#define CDN_PRE 4
-
-struct EntPre {            // one Crout entry, fetched ahead
-    int e, t0, t1, pv;
-    int tl[CDN_PRE], tu[CDN_PRE];
-};
-
-__device__ __forceinline__ void pre_entry(const cdn_plan_dev& P, int e, int e1, EntPre& p) {
-    p.e = -1;
-    if (e < e1) {
-        p.e = e;
-        p.t0 = __ldg(P.e_term_ptr + e);
-        p.t1 = __ldg(P.e_term_ptr + e + 1);
-        p.pv = __ldg(P.e_piv + e);
-#pragma unroll
-        for (int u = 0; u < CDN_PRE; ++u)
-            if (p.t0 + u < p.t1) {
-                p.tl[u] = __ldg(P.e_term_l + p.t0 + u);
-                p.tu[u] = __ldg(P.e_term_u + p.t0 + u);
-            }
-    }
-}
-
 template <class Team>
 __device__ __forceinline__ void sparse_factor(Team& tm, const cdn_plan_dev& P, double* lu) {
-    if (P.nlev_f <= 0) return;
-    int e0 = __ldg(P.f_lvl_ptr), e1 = __ldg(P.f_lvl_ptr + 1), nh = __ldg(P.f_lvl_nheavy);
-    EntPre cur;
-    pre_entry(P, e0 + nh + tm.rank(), e1, cur);
     for (int l = 0; l < P.nlev_f; ++l) {
-        // next level's bookkeeping: in flight during this level's work
-        int e0n = e1, e1n = e1, nhn = 0;
-        EntPre nxt;
-        nxt.e = -1;
-        if (l + 1 < P.nlev_f) {
-            e1n = __ldg(P.f_lvl_ptr + l + 2);
-            nhn = __ldg(P.f_lvl_nheavy + l + 1);
-            pre_entry(P, e0n + nhn + tm.rank(), e1n, nxt);
-        }
+        const int e0 = __ldg(P.f_lvl_ptr + l), e1 = __ldg(P.f_lvl_ptr + l + 1);
+        const int nh = __ldg(P.f_lvl_nheavy + l);
         for (int h = 0; h < nh; ++h) {
             const int e = e0 + h;
             double part = 0.0;
@@ -566,17 +525,7 @@ __device__ __forceinline__ void sparse_factor(Team& tm, const cdn_plan_dev& P, d
                 lu[e] = v;
             }
         }
-        if (cur.e >= 0) {
-            double v = lu[cur.e];
-#pragma unroll
-            for (int u = 0; u < CDN_PRE; ++u)
-                if (cur.t0 + u < cur.t1) v -= lu[cur.tl[u]] * lu[cur.tu[u]];
-            for (int t = cur.t0 + CDN_PRE; t < cur.t1; ++t)
-                v -= lu[__ldg(P.e_term_l + t)] * lu[__ldg(P.e_term_u + t)];
-            if (cur.pv >= 0) v /= lu[cur.pv];
-            lu[cur.e] = v;
-        }
-        for (int e = e0 + nh + tm.rank() + tm.size(); e < e1; e += tm.size()) {
+        for (int e = e0 + nh + tm.rank(); e < e1; e += tm.size()) {
             double v = lu[e];
             const int t1 = __ldg(P.e_term_ptr + e + 1);
             for (int t = __ldg(P.e_term_ptr + e); t < t1; ++t)
@@ -586,31 +535,6 @@ __device__ __forceinline__ void sparse_factor(Team& tm, const cdn_plan_dev& P, d
             lu[e] = v;
         }
         tm.sync();
-        cur = nxt;
-        e0 = e0n; e1 = e1n; nh = nhn;
-    }
-}
-
-struct RowPre {            // one row of a triangular solve, fetched ahead
-    int i, rm, k0, k1, dg;
-    int s[CDN_PRE], c[CDN_PRE];
-};
-
-__device__ __forceinline__ void pre_row(const int* __restrict__ rows, const int* __restrict__ ptr,
-                                        const int* __restrict__ slot, const int* __restrict__ col,
-                                        const int* __restrict__ aux, int q, int r1, RowPre& p) {
-    p.i = -1;
-    if (q < r1) {
-        p.i = __ldg(rows + q);
-        p.k0 = __ldg(ptr + p.i);
-        p.k1 = __ldg(ptr + p.i + 1);
-        p.rm = __ldg(aux + p.i);          // rowmap (L solve) / colmap (U solve)
-#pragma unroll
-        for (int u = 0; u < CDN_PRE; ++u)
-            if (p.k0 + u < p.k1) {
-                p.s[u] = __ldg(slot + p.k0 + u);
-                p.c[u] = __ldg(col + p.k0 + u);
-            }
     }
 }
 
@@ -618,106 +542,55 @@ __device__ __forceinline__ void pre_row(const int* __restrict__ rows, const int*
 template <class Team>
 __device__ __forceinline__ void sparse_solve(Team& tm, const cdn_plan_dev& P, const double* lu,
                                              const double* y, double* tmp, double* dx) {
-    if (P.nlev_l <= 0) return;
-    {
-        int r0 = __ldg(P.l_lvl_ptr), r1 = __ldg(P.l_lvl_ptr + 1), nh = __ldg(P.l_lvl_nheavy);
-        RowPre cur;
-        pre_row(P.l_rows, P.l_ptr, P.l_slot, P.l_col, P.rowmap, r0 + nh + tm.rank(), r1, cur);
-        for (int l = 0; l < P.nlev_l; ++l) {
-            int r0n = r1, r1n = r1, nhn = 0;
-            RowPre nxt;
-            nxt.i = -1;
-            if (l + 1 < P.nlev_l) {
-                r1n = __ldg(P.l_lvl_ptr + l + 2);
-                nhn = __ldg(P.l_lvl_nheavy + l + 1);
-                pre_row(P.l_rows, P.l_ptr, P.l_slot, P.l_col, P.rowmap, r0n + nhn + tm.rank(),
-                        r1n, nxt);
-            }
-            for (int h = 0; h < nh; ++h) {
-                const int i = __ldg(P.l_rows + r0 + h);
-                double part = 0.0;
-                const int k1 = __ldg(P.l_ptr + i + 1);
-                for (int k = __ldg(P.l_ptr + i) + tm.rank(); k < k1; k += tm.size())
-                    part += lu[__ldg(P.l_slot + k)] * tmp[__ldg(P.l_col + k)];
-                part = tm.sum(part);
-                if (tm.rank() == 0) tmp[i] = y[__ldg(P.rowmap + i)] - part;
-            }
-            if (cur.i >= 0) {
-                double v = y[cur.rm];
-#pragma unroll
-                for (int u = 0; u < CDN_PRE; ++u)
-                    if (cur.k0 + u < cur.k1) v -= lu[cur.s[u]] * tmp[cur.c[u]];
-                for (int k = cur.k0 + CDN_PRE; k < cur.k1; ++k)
-                    v -= lu[__ldg(P.l_slot + k)] * tmp[__ldg(P.l_col + k)];
-                tmp[cur.i] = v;
-            }
-            for (int q = r0 + nh + tm.rank() + tm.size(); q < r1; q += tm.size()) {
-                const int i = __ldg(P.l_rows + q);
-                double v = y[__ldg(P.rowmap + i)];
-                const int k1 = __ldg(P.l_ptr + i + 1);
-                for (int k = __ldg(P.l_ptr + i); k < k1; ++k)
-                    v -= lu[__ldg(P.l_slot + k)] * tmp[__ldg(P.l_col + k)];
-                tmp[i] = v;
-            }
-            tm.sync();
-            cur = nxt;
-            r0 = r0n; r1 = r1n; nh = nhn;
+    for (int l = 0; l < P.nlev_l; ++l) {
+        const int r0 = __ldg(P.l_lvl_ptr + l), r1 = __ldg(P.l_lvl_ptr + l + 1);
+        const int nh = __ldg(P.l_lvl_nheavy + l);
+        for (int h = 0; h < nh; ++h) {
+            const int i = __ldg(P.l_rows + r0 + h);
+            double part = 0.0;
+            const int k1 = __ldg(P.l_ptr + i + 1);
+            for (int k = __ldg(P.l_ptr + i) + tm.rank(); k < k1; k += tm.size())
+                part += lu[__ldg(P.l_slot + k)] * tmp[__ldg(P.l_col + k)];
+            part = tm.sum(part);
+            if (tm.rank() == 0) tmp[i] = y[__ldg(P.rowmap + i)] - part;
         }
+        for (int q = r0 + nh + tm.rank(); q < r1; q += tm.size()) {
+            const int i = __ldg(P.l_rows + q);
+            double v = y[__ldg(P.rowmap + i)];
+            const int k1 = __ldg(P.l_ptr + i + 1);
+            for (int k = __ldg(P.l_ptr + i); k < k1; ++k)
+                v -= lu[__ldg(P.l_slot + k)] * tmp[__ldg(P.l_col + k)];
+            tmp[i] = v;
+        }
+        tm.sync();
     }
-    {
-        int r0 = __ldg(P.u_lvl_ptr), r1 = __ldg(P.u_lvl_ptr + 1), nh = __ldg(P.u_lvl_nheavy);
-        RowPre cur;
-        pre_row(P.u_rows, P.u_ptr, P.u_slot, P.u_col, P.colmap, r0 + nh + tm.rank(), r1, cur);
-        if (cur.i >= 0) cur.dg = __ldg(P.u_diag + cur.i);
-        for (int l = 0; l < P.nlev_u; ++l) {
-            int r0n = r1, r1n = r1, nhn = 0;
-            RowPre nxt;
-            nxt.i = -1;
-            if (l + 1 < P.nlev_u) {
-                r1n = __ldg(P.u_lvl_ptr + l + 2);
-                nhn = __ldg(P.u_lvl_nheavy + l + 1);
-                pre_row(P.u_rows, P.u_ptr, P.u_slot, P.u_col, P.colmap, r0n + nhn + tm.rank(),
-                        r1n, nxt);
-                if (nxt.i >= 0) nxt.dg = __ldg(P.u_diag + nxt.i);
-            }
-            for (int h = 0; h < nh; ++h) {
-                const int i = __ldg(P.u_rows + r0 + h);
-                double part = 0.0;
-                const int k1 = __ldg(P.u_ptr + i + 1);
-                for (int k = __ldg(P.u_ptr + i) + tm.rank(); k < k1; k += tm.size())
-                    part += lu[__ldg(P.u_slot + k)] * tmp[__ldg(P.u_col + k)];
-                part = tm.sum(part);
-                if (tm.rank() == 0) {
-                    const double v = (tmp[i] - part) / lu[__ldg(P.u_diag + i)];
-                    tmp[i] = v;
-                    dx[__ldg(P.colmap + i)] = v;
-                }
-            }
-            if (cur.i >= 0) {
-                double v = tmp[cur.i];
-#pragma unroll
-                for (int u = 0; u < CDN_PRE; ++u)
-                    if (cur.k0 + u < cur.k1) v -= lu[cur.s[u]] * tmp[cur.c[u]];
-                for (int k = cur.k0 + CDN_PRE; k < cur.k1; ++k)
-                    v -= lu[__ldg(P.u_slot + k)] * tmp[__ldg(P.u_col + k)];
-                v /= lu[cur.dg];
-                tmp[cur.i] = v;
-                dx[cur.rm] = v;
-            }
-            for (int q = r0 + nh + tm.rank() + tm.size(); q < r1; q += tm.size()) {
-                const int i = __ldg(P.u_rows + q);
-                double v = tmp[i];
-                const int k1 = __ldg(P.u_ptr + i + 1);
-                for (int k = __ldg(P.u_ptr + i); k < k1; ++k)
-                    v -= lu[__ldg(P.u_slot + k)] * tmp[__ldg(P.u_col + k)];
-                v /= lu[__ldg(P.u_diag + i)];
+    for (int l = 0; l < P.nlev_u; ++l) {
+        const int r0 = __ldg(P.u_lvl_ptr + l), r1 = __ldg(P.u_lvl_ptr + l + 1);
+        const int nh = __ldg(P.u_lvl_nheavy + l);
+        for (int h = 0; h < nh; ++h) {
+            const int i = __ldg(P.u_rows + r0 + h);
+            double part = 0.0;
+            const int k1 = __ldg(P.u_ptr + i + 1);
+            for (int k = __ldg(P.u_ptr + i) + tm.rank(); k < k1; k += tm.size())
+                part += lu[__ldg(P.u_slot + k)] * tmp[__ldg(P.u_col + k)];
+            part = tm.sum(part);
+            if (tm.rank() == 0) {
+                const double v = (tmp[i] - part) / lu[__ldg(P.u_diag + i)];
                 tmp[i] = v;
                 dx[__ldg(P.colmap + i)] = v;
             }
-            tm.sync();
-            cur = nxt;
-            r0 = r0n; r1 = r1n; nh = nhn;
         }
+        for (int q = r0 + nh + tm.rank(); q < r1; q += tm.size()) {
+            const int i = __ldg(P.u_rows + q);
+            double v = tmp[i];
+            const int k1 = __ldg(P.u_ptr + i + 1);
+            for (int k = __ldg(P.u_ptr + i); k < k1; ++k)
+                v -= lu[__ldg(P.u_slot + k)] * tmp[__ldg(P.u_col + k)];
+            v /= lu[__ldg(P.u_diag + i)];
+            tmp[i] = v;
+            dx[__ldg(P.colmap + i)] = v;
+        }
+        tm.sync();
     }
 }
 

@@ -46,12 +46,12 @@ static cudaError_t launch_engine(const cdn_engine_args& A, cdn_launch_cfg c, cud
         default: return cudaErrorInvalidValue;
         }
     case CDN_TEAM_BLOCK: {
-        // light model sets run 512 threads per CTA (128 registers each); the
+        // light model sets run 1024 threads per CTA (64 registers each); the
         // heavy models need their 255 registers
-        if (MS == CDN_MS_DIODE && c.tpb == 512) {
-            cudaError_t e = set_smem(engine_block_kernel<MS, (MS == CDN_MS_DIODE ? 512 : 256)>, c.smem);
+        if (MS == CDN_MS_DIODE && c.tpb == 1024) {
+            cudaError_t e = set_smem(engine_block_kernel<MS, (MS == CDN_MS_DIODE ? 1024 : 256)>, c.smem);
             if (e != cudaSuccess) return e;
-            engine_block_kernel<MS, (MS == CDN_MS_DIODE ? 512 : 256)><<<c.blocks, 512, c.smem, st>>>(A);
+            engine_block_kernel<MS, (MS == CDN_MS_DIODE ? 1024 : 256)><<<c.blocks, 1024, c.smem, st>>>(A);
             return cudaGetLastError();
         }
         cudaError_t e = set_smem(engine_block_kernel<MS, 256>, c.smem);
