@@ -31,7 +31,7 @@ class GroupHost(C.Structure):
                 ('nxin', C.c_int), ('ncs', C.c_int), ('nqs', C.c_int),
                 ('ndelay', C.c_int),
                 ('vpos', _vp), ('vneg', _vp), ('cpos', _vp), ('cneg', _vp),
-                ('qpos', _vp), ('qneg', _vp)]
+                ('qpos', _vp), ('qneg', _vp), ('delay', _vp)]
 
 
 class CircuitHost(C.Structure):
@@ -45,7 +45,7 @@ class CircuitHost(C.Structure):
                 ('e_val', _vp),
                 ('ngroups', C.c_int), ('groups', C.POINTER(GroupHost)),
                 ('rowmatch', _vp), ('colorder', _vp), ('heavy', C.c_int),
-                ('skip_q', C.c_int)]
+                ('skip_q', C.c_int), ('nhist', C.c_int)]
 
 
 class RunHost(C.Structure):
@@ -53,6 +53,7 @@ class RunHost(C.Structure):
     _fields_ = [('abstol', C.c_double), ('reltol', C.c_double),
                 ('maxdelta', C.c_double), ('a0', C.c_double),
                 ('gmin', C.c_double), ('lam', C.c_double),
+                ('h', C.c_double),
                 ('maxiter', C.c_int), ('errfunc', C.c_int),
                 ('use_q', C.c_int), ('im', C.c_int),
                 ('op', C.c_int), ('B', C.c_int),

@@ -104,7 +104,8 @@ class BatchTransient(object):
             dc = nd.Engine(self.topo, use_q=False, batch=B, lib=self.lib,
                            keep_state=False, x_ref=self.x0)
             tr = nd.Engine(self.topo, use_q=True, a0=a0, batch=B,
-                           lib=self.lib, keep_state=False, x_ref=self.x0)
+                           lib=self.lib, keep_state=False, x_ref=self.x0,
+                           h=self.tstep)
             self._engines[B] = (dc, tr)
         return self._engines[B]
 

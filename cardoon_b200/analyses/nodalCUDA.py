@@ -221,6 +221,11 @@ class Topology(object):
             g['vpos'], g['vneg'] = kmajor(vp, nxin), kmajor(vn, nxin)
             g['cpos'], g['cneg'] = kmajor(cp, ncs), kmajor(cn, ncs)
             g['qpos'], g['qneg'] = kmajor(qp, nqs), kmajor(qn, nqs)
+            g['delay'] = None
+            if ndelay:
+                # [ndelay][n] delays of the delayed control ports
+                g['delay'] = np.ascontiguousarray(np.array(
+                    [e.nD_delay for e in elems], dtype=np.float64).T)
             self.groups.append(g)
 
     def pack_params(self):
@@ -367,7 +372,7 @@ HEAVY = 0          # 0 = library default (tests lower it to reach the hub paths)
 
 
 def create_plan(dll, ctx, topo, use_q, dense, match=None, ordering=None,
-                check=None, colorder=None):
+                check=None, colorder=None, nhist=0):
     """cdn_plan_create on the index lists of ``topo``: returns the plan
     handle and its size figures.  Host-only (works without a GPU)."""
     n = topo.n
@@ -379,9 +384,12 @@ def create_plan(dll, ctx, topo, use_q, dense, match=None, ordering=None,
         gh.ndelay = g['ndelay']
         for name in ('vpos', 'vneg', 'cpos', 'cneg', 'qpos', 'qneg'):
             setattr(gh, name, g[name].ctypes.data_as(L._vp))
+        if g['delay'] is not None:
+            gh.delay = g['delay'].ctypes.data_as(L._vp)
     ch = L.CircuitHost()
     ch.n = n
     ch.heavy = HEAVY
+    ch.nhist = nhist
     ch.skip_q = 0 if use_q else 1
     if dense:
         ch.ordering = L.ORDER_DENSE
@@ -417,13 +425,14 @@ def create_plan(dll, ctx, topo, use_q, dense, match=None, ordering=None,
     return plan, dict(zip(PLAN_INFO, info[:12]))
 
 
-def sparse_plan(dll, ctx, topo, use_q, A_ref, ordering=None, check=None):
+def sparse_plan(dll, ctx, topo, use_q, A_ref, ordering=None, check=None,
+                nhist=0):
     """Static-pivot sparse plan validated numerically at the reference
     matrix ``A_ref``: matching + nested dissection, then the pivot sequence
     is corrected with the row interchanges SuperLU needs in that order."""
     match = static_pivot_matching(A_ref)
     plan, info = create_plan(dll, ctx, topo, use_q, False, match, ordering,
-                             check)
+                             check, nhist=nhist)
     rowmap = plan_array(dll, plan, 'rowmap')
     colmap = plan_array(dll, plan, 'colmap')
     match2 = refine_pivots(A_ref, rowmap, colmap)
@@ -431,7 +440,7 @@ def sparse_plan(dll, ctx, topo, use_q, A_ref, ordering=None, check=None):
         dll.cdn_plan_free(plan)
         match = match2
         plan, info = create_plan(dll, ctx, topo, use_q, False, match, None,
-                                 check, colorder=colmap)
+                                 check, colorder=colmap, nhist=nhist)
     return plan, info, match
 
 
@@ -470,7 +479,7 @@ class Engine(object):
 
     def __init__(self, topo, use_q, a0=0., x_ref=None, batch=1, params=None,
                  lib=None, keep_state=True, dense=None, team=L.TEAM_AUTO,
-                 ordering=None):
+                 ordering=None, h=0.):
         self.lib = lib or L.get_lib()
         lib = self.lib
         torch = lib.torch
@@ -479,6 +488,15 @@ class Engine(object):
         self.B = batch
         self.use_q = bool(use_q)
         self.a0 = float(a0)
+        self.h = float(h)
+        # history samples kept per delayed control port (nodalSP.py:686-696)
+        maxDelay = max([g['delay'].max() for g in topo.groups
+                        if g['delay'] is not None] + [0.])
+        self.nhist = 0
+        if use_q and maxDelay > 0.:
+            if not h > 0.:
+                raise ValueError('delayed control ports need the time step')
+            self.nhist = int(np.ceil(maxDelay / h)) + 2
         if dense is None:
             dense = (n <= DENSE_MAX) or (not glVar.sparse and n <= 2000)
         self.dense = dense
@@ -486,13 +504,15 @@ class Engine(object):
         self.match = None
         if dense:
             self.plan, self.info = create_plan(
-                lib.dll, lib.ctx, topo, use_q, True, check=lib.check)
+                lib.dll, lib.ctx, topo, use_q, True, check=lib.check,
+                nhist=self.nhist)
         else:
             xr = np.zeros(n) if x_ref is None else np.asarray(x_ref)
             stamps = topo.device_stamps(topo.device_jacobians(lib, xr))
             A_ref = reference_matrix(topo, use_q, a0, stamps)
             self.plan, self.info, self.match = sparse_plan(
-                lib.dll, lib.ctx, topo, use_q, A_ref, ordering, lib.check)
+                lib.dll, lib.ctx, topo, use_q, A_ref, ordering, lib.check,
+                nhist=self.nhist)
         nbytes = lib.dll.cdn_plan_bytes(self.plan)
         self._planbuf = torch.empty(nbytes, dtype=torch.uint8,
                                     device=lib.device)
@@ -502,11 +522,11 @@ class Engine(object):
         self.set_params(params)
         # ---- state -------------------------------------------------------------------
         self.ws_per = lib.dll.cdn_engine_ws_doubles(self.plan)
-        off = (C.c_long * 14)()
+        off = (C.c_long * 15)()
         lib.check(lib.dll.cdn_engine_layout(self.plan, off))
         self.off = dict(zip(('x', 'dx', 'ivec', 'sv', 'q', 'qprev', 'dq',
-                             'y', 'tmp', 'xb', 'lu', 'out', 'jac', 'piv'),
-                            off))
+                             'y', 'tmp', 'xb', 'lu', 'out', 'jac', 'hist',
+                             'piv'), off))
         self.keep_state = keep_state
         self.ws = None
         if keep_state or not (dense and n <= DENSE_MAX):
@@ -580,6 +600,7 @@ class Engine(object):
         r.errfunc = int(bool(glVar.errfunc))
         r.a0 = self.a0 if a0 is None else a0
         r.gmin, r.lam = gmin, lam
+        r.h = self.h
         r.use_q = int(self.use_q)
         r.im = 1
         r.op, r.B = op, self.B
@@ -876,10 +897,6 @@ class TransientNodal(_NLFunction):
         self.im = im
         self.sVec = np.zeros(ckt.nD_dimension)
         self.engine = None
-        if ckt.nD_delayElem:
-            raise NotImplementedError(
-                'transient analysis with delayed control ports (mesfetc) is '
-                'not available in the CUDA engine yet')
 
     def _imcode(self):
         return 1 if type(self.im).__name__ == 'Trapezoidal' else 0
@@ -888,7 +905,7 @@ class TransientNodal(_NLFunction):
         a0 = (2. / h) if self._imcode() else (1. / h)
         self.h = h
         self.engine = Engine(get_topology(self.ckt), use_q=True, a0=a0,
-                             x_ref=x_ref)
+                             x_ref=x_ref, h=h)
 
     def refresh(self):
         self.ckt.__dict__.pop('_cuda_topology', None)

@@ -10,10 +10,10 @@ extern "C" {
 long cdn_engine_ws_doubles(cdn_plan* P) {
     const cdn_plan_dev* D = cdn_plan_host_view(P);
     if (!D) return -1;
-    return ws_doubles(D->n, D->nlu, D->dev_out_size, D->dev_jac_size);
+    return ws_doubles(D->n, D->nlu, D->dev_out_size, D->dev_jac_size, D->hist_size);
 }
 
-// offsets (in doubles) of x, dx, ivec, sv, q, qprev, dq, y, tmp, xb, lu, out, jac, piv
+// offsets (in doubles) of x, dx, ivec, sv, q, qprev, dq, y, tmp, xb, lu, out, jac, hist, piv
 int cdn_engine_layout(cdn_plan* P, long* off) {
     const cdn_plan_dev* D = cdn_plan_host_view(P);
     if (!D || !off) return CDN_ERR_ARG;
@@ -23,6 +23,7 @@ int cdn_engine_layout(cdn_plan* P, long* off) {
     off[11] = off[10] + D->nlu;
     off[12] = off[11] + D->dev_out_size;
     off[13] = off[12] + D->dev_jac_size;
+    off[14] = off[13] + D->hist_size;
     return CDN_OK;
 }
 
@@ -40,7 +41,6 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     unsigned ms = 0;
     for (int g = 0; g < D->ngroups; ++g) {
         if (!D->groups[g].params) return cdn_fail(ctx, CDN_ERR_STATE, "engine: group parameters not set");
-        if (D->groups[g].ndelay) return cdn_fail(ctx, CDN_ERR_ARG, "engine: delayed control ports are not supported");
         ms |= 1u << D->groups[g].model;
     }
     if (ms & ~(unsigned)CDN_MS_ALL) return cdn_fail(ctx, CDN_ERR_ARG, "engine: model not available in the Newton engine");
@@ -49,11 +49,11 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     memset(&A, 0, sizeof(A));
     A.plan = dplan;
     A.o.abstol = r->abstol; A.o.reltol = r->reltol; A.o.maxdelta = r->maxdelta;
-    A.o.a0 = r->a0; A.o.gmin = r->gmin; A.o.lambda = r->lambda;
+    A.o.a0 = r->a0; A.o.gmin = r->gmin; A.o.lambda = r->lambda; A.o.h = r->h;
     A.o.maxiter = r->maxiter; A.o.errfunc = r->errfunc; A.o.use_q = r->use_q; A.o.im = r->im;
     A.op = r->op; A.B = r->B;
     A.x = r->x; A.sv_in = r->sv_in; A.ws = r->ws;
-    const long per = ws_doubles(D->n, D->nlu, D->dev_out_size, D->dev_jac_size);
+    const long per = ws_doubles(D->n, D->nlu, D->dev_out_size, D->dev_jac_size, D->hist_size);
     A.ws_stride = per;
     A.nsamples = r->nsamples; A.first = r->first; A.init_ic = r->init_ic;
     A.nsrc = r->nsrc; A.nsave = r->nsave; A.helpers = r->helpers;

@@ -32,6 +32,7 @@ struct cdn_opts {
     double a0;        // integration coefficient (0 in DC)
     double gmin;      // gmin-stepping conductance (multiplies the Gones pattern)
     double lambda;    // source-stepping factor (1 = full sources)
+    double h;         // time step (delayed control ports)
     int maxiter;
     int errfunc;
     int use_q;        // 0: DC (currents only); 1: transient (charges too)
@@ -67,20 +68,23 @@ struct cdn_engine_args {
 
 // ---- per-instance state ----------------------------------------------------------
 struct Ws {
-    double *x, *dx, *ivec, *sv, *q, *qprev, *dq, *y, *tmp, *xb, *lu, *out, *jac;
-    int* piv;
+    double *x, *dx, *ivec, *sv, *q, *qprev, *dq, *y, *tmp, *xb, *lu, *out, *jac, *hist;
+    int* piv;       // [n] pivot rows (dense LU); piv[n + 1] = head of the history rings
 };
 
-__host__ __device__ inline long ws_doubles(int n, long nlu, long out_size, long jac_size) {
-    return 10L * n + nlu + out_size + jac_size + (n + 1) / 2 + 2;
+__host__ __device__ inline long ws_doubles(int n, long nlu, long out_size, long jac_size,
+                                           long hist_size = 0) {
+    return 10L * n + nlu + out_size + jac_size + hist_size + (n + 1) / 2 + 2;
 }
 
-__device__ inline Ws ws_carve(double* base, int n, long nlu, long out_size, long jac_size) {
+__device__ inline Ws ws_carve(double* base, int n, long nlu, long out_size, long jac_size,
+                              long hist_size = 0) {
     Ws w;
     w.x = base; w.dx = w.x + n; w.ivec = w.dx + n; w.sv = w.ivec + n; w.q = w.sv + n;
     w.qprev = w.q + n; w.dq = w.qprev + n; w.y = w.dq + n; w.tmp = w.y + n; w.xb = w.tmp + n; w.lu = w.xb + n;
     w.out = w.lu + nlu; w.jac = w.out + out_size;
-    w.piv = (int*)(w.jac + jac_size);
+    w.hist = w.jac + jac_size;
+    w.piv = (int*)(w.hist + hist_size);
     return w;
 }
 
@@ -232,15 +236,47 @@ struct WsSink {
     double* out;
     double* jac;
     int ld, i, nxin;
+    int ndel;            // the last ndel control ports are delayed:
+    double coef[2];      // d v(t - tau) / d v(t) of each (nodalSP.py:872-875)
     CDN_HD void put(int slot, const Dual<P>& d) const {
         out[slot * ld + i] = d.v;
         if (P > 0) {
 #pragma unroll
             for (int c = 0; c < P; ++c)
-                if (c < nxin) jac[(slot * nxin + c) * ld + i] = d.d[c];
+                if (c < nxin) {
+                    double t = d.d[c];
+                    if (ndel > 0 && c >= nxin - ndel) t *= coef[c - (nxin - ndel)];
+                    jac[(slot * nxin + c) * ld + i] = t;
+                }
         }
     }
 };
+
+// v(t - td) by linear interpolation over the stored history of a port voltage
+// (reference nodal.py:82-108 with a fixed step h).  ring[pos(back)] is the
+// value `back` accepted samples ago (back = 0: last accepted sample); vp is the
+// value at the time point being solved.  Returns the interpolated value and
+// sets *coeff to its derivative with respect to vp.
+__device__ __forceinline__ double delay_interp(double td, double vp, double h,
+                                               const double* ring, int R, int head,
+                                               double* coeff) {
+    int p0 = head;
+    if (td <= h) {
+        const double c = (h - td) / h;
+        *coeff = c;
+        return ring[p0] + (vp - ring[p0]) * c;
+    }
+    *coeff = 0.0;
+    double timeacc = h;
+    for (int k = 0; k < R - 1; ++k) {
+        timeacc += h;
+        int p1 = p0 - 1;
+        if (p1 < 0) p1 += R;
+        if (td < timeacc) return ring[p1] + (ring[p0] - ring[p1]) * (timeacc - td) / h;
+        p0 = p1;
+    }
+    return ring[p0];
+}
 
 template <int P>
 __device__ __forceinline__ void gather_xin(const cdn_group_dev& G, int i, const double* x,
@@ -259,12 +295,26 @@ __device__ __forceinline__ void gather_xin(const cdn_group_dev& G, int i, const 
 
 template <int MODEL, int P>
 __device__ __forceinline__ void eval_model(const cdn_group_dev& G, const PV& p, int i,
-                                           const double* x, const Ws& w) {
+                                           const double* x, const Ws& w, int nhist, double h,
+                                           int head) {
     Dual<P> v[CDN_MAX_XIN];
     gather_xin<P>(G, i, x, v);
     WsSink<P> sink;
     sink.out = w.out + G.out_off; sink.jac = w.jac + G.jac_off;
     sink.ld = G.n; sink.i = i; sink.nxin = G.nxin;
+    sink.ndel = 0;
+    if (MODEL == CDN_MODEL_MESFETC && nhist > 0 && G.ndelay > 0) {
+        // delayed copies of control voltages (nodalSP.py:860-875)
+        sink.ndel = G.ndelay;
+#pragma unroll
+        for (int d = 0; d < 2; ++d)
+            if (d < G.ndelay) {
+                const int c = G.nxin - G.ndelay + d;
+                const double* ring = w.hist + G.hist_off + ((long)d * G.n + i) * nhist;
+                v[c].v = delay_interp(__ldg(G.delay + d * G.n + i), v[c].v, h, ring, nhist, head,
+                                      &sink.coef[d]);
+            }
+    }
     if (MODEL == CDN_MODEL_DIODE) diode_eval(p, G.flags, v, sink);
     else if (MODEL == CDN_MODEL_BJT) bjt_eval<P, false>(p, G.flags, v, sink);
     else if (MODEL == CDN_MODEL_SVBJT) bjt_eval<P, true>(p, G.flags, v, sink);
@@ -279,7 +329,7 @@ __device__ __forceinline__ void eval_model(const cdn_group_dev& G, const PV& p, 
 // one device: instance i of group G of circuit instance b
 template <int MS, bool DERIV>
 __device__ __noinline__ void eval_one(const cdn_group_dev& G, int b, int i, const double* x,
-                                      const Ws& w) {
+                                      const Ws& w, int nhist, double h, int head) {
     long col = (G.per_inst ? (long)b * G.n : 0L) + i;
     if (G.pidx) col = __ldg(G.pidx + col);
     PV p;
@@ -287,39 +337,79 @@ __device__ __noinline__ void eval_one(const cdn_group_dev& G, int b, int i, cons
     p.ld = G.ldp;
     switch (G.model) {
     case CDN_MODEL_DIODE:
-        if (CDN_HAS(MS, CDN_MODEL_DIODE)) eval_model<CDN_MODEL_DIODE, DERIV ? 1 : 0>(G, p, i, x, w);
+        if (CDN_HAS(MS, CDN_MODEL_DIODE)) eval_model<CDN_MODEL_DIODE, DERIV ? 1 : 0>(G, p, i, x, w, 0, h, 0);
         break;
     case CDN_MODEL_BJT:
-        if (CDN_HAS(MS, CDN_MODEL_BJT)) eval_model<CDN_MODEL_BJT, DERIV ? 4 : 0>(G, p, i, x, w);
+        if (CDN_HAS(MS, CDN_MODEL_BJT)) eval_model<CDN_MODEL_BJT, DERIV ? 4 : 0>(G, p, i, x, w, 0, h, 0);
         break;
     case CDN_MODEL_SVBJT:
-        if (CDN_HAS(MS, CDN_MODEL_SVBJT)) eval_model<CDN_MODEL_SVBJT, DERIV ? 4 : 0>(G, p, i, x, w);
+        if (CDN_HAS(MS, CDN_MODEL_SVBJT)) eval_model<CDN_MODEL_SVBJT, DERIV ? 4 : 0>(G, p, i, x, w, 0, h, 0);
         break;
     case CDN_MODEL_BSIM3:
-        if (CDN_HAS(MS, CDN_MODEL_BSIM3)) eval_model<CDN_MODEL_BSIM3, DERIV ? 3 : 0>(G, p, i, x, w);
+        if (CDN_HAS(MS, CDN_MODEL_BSIM3)) eval_model<CDN_MODEL_BSIM3, DERIV ? 3 : 0>(G, p, i, x, w, 0, h, 0);
         break;
     case CDN_MODEL_EKV:
-        if (CDN_HAS(MS, CDN_MODEL_EKV)) eval_model<CDN_MODEL_EKV, DERIV ? 3 : 0>(G, p, i, x, w);
+        if (CDN_HAS(MS, CDN_MODEL_EKV)) eval_model<CDN_MODEL_EKV, DERIV ? 3 : 0>(G, p, i, x, w, 0, h, 0);
         break;
     case CDN_MODEL_MEMR:
-        if (CDN_HAS(MS, CDN_MODEL_MEMR)) eval_model<CDN_MODEL_MEMR, DERIV ? 2 : 0>(G, p, i, x, w);
+        if (CDN_HAS(MS, CDN_MODEL_MEMR)) eval_model<CDN_MODEL_MEMR, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0);
+        break;
+    case CDN_MODEL_MESFETC:
+        if (CDN_HAS(MS, CDN_MODEL_MESFETC))
+            eval_model<CDN_MODEL_MESFETC, DERIV ? 4 : 0>(G, p, i, x, w, nhist, h, head);
         break;
     default: break;
     }
 }
 
+// `delayed`: evaluate the delayed control ports at t - tau (Newton, get_i);
+// update_q evaluates them at the present voltages (nodalSP.py:719-733)
 template <int MS, bool DERIV, class Team>
 __device__ __forceinline__ void eval_devices(Team& tm, const cdn_plan_dev& P, int b,
-                                             const double* x, const Ws& w) {
+                                             const double* x, const Ws& w, bool delayed = false,
+                                             double h = 0.0) {
+    const int nhist = delayed ? P.nhist : 0;
+    const int head = nhist ? w.piv[P.n + 1] : 0;
     if (Team::kFlat) {
         for (int d = tm.rank(); d < P.ndev; d += tm.size())
-            eval_one<MS, DERIV>(P.groups[__ldg(P.dev_g + d)], b, __ldg(P.dev_i + d), x, w);
+            eval_one<MS, DERIV>(P.groups[__ldg(P.dev_g + d)], b, __ldg(P.dev_i + d), x, w, nhist,
+                                h, head);
     } else {
         for (int g = 0; g < P.ngroups; ++g) {
             const cdn_group_dev& G = P.groups[g];
-            for (int i = tm.rank(); i < G.n; i += tm.size()) eval_one<MS, DERIV>(G, b, i, x, w);
+            for (int i = tm.rank(); i < G.n; i += tm.size())
+                eval_one<MS, DERIV>(G, b, i, x, w, nhist, h, head);
         }
     }
+    tm.sync();
+}
+
+// Port-voltage history of the delayed control ports (nodalSP.py:686-696,
+// 741-758): a ring of P.nhist accepted samples per port, head in piv[n + 1].
+template <class Team>
+__device__ __forceinline__ void hist_store(Team& tm, const cdn_plan_dev& P, const Ws& w,
+                                           bool fill) {
+    if (P.nhist <= 0) return;
+    const int R = P.nhist;
+    int head = fill ? 0 : w.piv[P.n + 1] + 1;
+    if (head >= R) head = 0;
+    for (int g = 0; g < P.ngroups; ++g) {
+        const cdn_group_dev& G = P.groups[g];
+        if (G.ndelay <= 0) continue;
+        for (int t = tm.rank(); t < G.ndelay * G.n; t += tm.size()) {
+            const int d = t / G.n, i = t - d * G.n;
+            const int c = G.nxin - G.ndelay + d;
+            const int a = __ldg(G.vpos + c * G.n + i), bb = __ldg(G.vneg + c * G.n + i);
+            double v = 0.0;
+            if (a >= 0) v += w.x[a];
+            if (bb >= 0) v -= w.x[bb];
+            double* ring = w.hist + G.hist_off + ((long)d * G.n + i) * R;
+            if (fill) for (int k = 0; k < R; ++k) ring[k] = v;
+            else ring[head] = v;
+        }
+    }
+    tm.sync();
+    if (tm.rank() == 0) w.piv[P.n + 1] = head;
     tm.sync();
 }
 
@@ -691,7 +781,7 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
     bool run = active;
     while (tm.cta_any(run && it < o.maxiter)) {
         if (!(run && it < o.maxiter)) continue;
-        eval_devices<MS, true>(tm, P, b, w.x, w);
+        eval_devices<MS, true>(tm, P, b, w.x, w, true, o.h);
         assemble(tm, P, w, o);
         residual(tm, P, w, o);
         tm.sync();
@@ -715,7 +805,7 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
         tm.sync();
         bool n2 = true;
         if (n1 && o.errfunc) {
-            eval_devices<MS, false>(tm, P, b, w.x, w);
+            eval_devices<MS, false>(tm, P, b, w.x, w, true, o.h);
             residual(tm, P, w, o);
             tm.sync();
             double ef = 0.0;
@@ -882,6 +972,7 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
         if (active && A.init_ic) {               // set_IC (nodalSP.py:666-696)
             update_q<MS>(tm, P, b, w);
             integ_init(tm, P, w);
+            hist_store(tm, P, w, true);
         }
         int status = 0;
         bool run = active;
@@ -890,6 +981,7 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
             if (run) {
                 update_q<MS>(tm, P, b, w);       // accept(xOld)
                 integ_accept(tm, P, w, o);
+                hist_store(tm, P, w, false);
                 make_rhs(tm, P, w, o, A.src_dc, A.nsrc, A.src_rows,
                          A.src_val + (long)i * A.nsrc);
                 if (i > 1) {                     // chord predictor (tran.py:181)
@@ -918,11 +1010,13 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
         if (!active) break;
         update_q<MS>(tm, P, b, w);
         integ_init(tm, P, w);
+        hist_store(tm, P, w, true);
         break;
     case CDN_OP_ACCEPT:
         if (!active) break;
         update_q<MS>(tm, P, b, w);
         integ_accept(tm, P, w, o);
+        hist_store(tm, P, w, false);
         break;
     case CDN_OP_RHS:
         if (!active) break;
@@ -934,13 +1028,13 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
         break;
     case CDN_OP_GET_I:
         if (!active) break;
-        eval_devices<MS, false>(tm, P, b, w.x, w);
+        eval_devices<MS, false>(tm, P, b, w.x, w, true, o.h);
         residual(tm, P, w, o);
         tm.sync();
         break;
     case CDN_OP_GET_I_JAC:
         if (!active) break;
-        eval_devices<MS, true>(tm, P, b, w.x, w);
+        eval_devices<MS, true>(tm, P, b, w.x, w, true, o.h);
         assemble(tm, P, w, o);
         residual(tm, P, w, o);
         tm.sync();
@@ -965,14 +1059,14 @@ engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
     TileTeam<T> tm;
     const int tiles = blockDim.x / T;
     const int tile_id = threadIdx.x / T;
-    const long per = ws_doubles(P.n, P.nlu, P.dev_out_size, P.dev_jac_size);
+    const long per = ws_doubles(P.n, P.nlu, P.dev_out_size, P.dev_jac_size, P.hist_size);
     // the loop bounds are CTA-uniform: padding tiles run along inactive
     for (int b0 = blockIdx.x * tiles; b0 < A.B; b0 += gridDim.x * tiles) {
         const int b = b0 + tile_id;
         const bool active = b < A.B;
         double* base = A.ws ? A.ws + (long)(active ? b : 0) * A.ws_stride
                             : smem + (long)tile_id * per;
-        const Ws w = ws_carve(base, P.n, P.nlu, P.dev_out_size, P.dev_jac_size);
+        const Ws w = ws_carve(base, P.n, P.nlu, P.dev_out_size, P.dev_jac_size, P.hist_size);
         if (active && (!A.ws || A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN)) {
             for (int r = tm.rank(); r < P.n; r += T) w.x[r] = A.x[(long)b * P.n + r];
             tm.sync();
@@ -1002,7 +1096,7 @@ engine_block_kernel(const __grid_constant__ cdn_engine_args A) {
     tm.sred = sred; tm.ired = ired;
     for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
         Ws w = ws_carve(A.ws + (long)b * A.ws_stride, P.n, P.nlu, P.dev_out_size,
-                        P.dev_jac_size);
+                        P.dev_jac_size, P.hist_size);
         double* const g_lu = w.lu;
         double* const g_y = w.y;
         if (A.smem_lu) {
@@ -1033,7 +1127,7 @@ engine_grid_kernel(const __grid_constant__ cdn_engine_args A) {
     const cdn_plan_dev& P = *A.plan;
     GridTeam tm;
     tm.sred = sred; tm.gred = A.red;
-    const Ws w = ws_carve(A.ws, P.n, P.nlu, P.dev_out_size, P.dev_jac_size);
+    const Ws w = ws_carve(A.ws, P.n, P.nlu, P.dev_out_size, P.dev_jac_size, P.hist_size);
     if (A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN) {
         for (int r = tm.rank(); r < P.n; r += tm.size()) w.x[r] = A.x[r];
         tm.sync();

@@ -27,6 +27,8 @@ struct cdn_group_dev {
     const int* vneg;          // [nxin][n]
     long out_off;             // offset of this group's out[nout][n] in dev_out
     long jac_off;             // offset of jac[nout*nxin][n] in dev_jac
+    const double* delay;      // [ndelay][n] delays of the last ndelay control ports
+    long hist_off;            // offset of hist[ndelay][n][nhist] in the history buffer
 };
 
 struct cdn_plan_dev {
@@ -38,6 +40,8 @@ struct cdn_plan_dev {
     int ndev;                 // nonlinear devices of one circuit instance
     int max_terms;
     int heavy;                // list length above which the team reduces together
+    int nhist;                // history samples per delayed port (0: no delays)
+    long hist_size;           // doubles of port-voltage history per circuit instance
     int n_e_heavy, n_r_heavy;
     const int* e_heavy;       // [n_e_heavy] slots with long contribution lists
     const int* r_heavy;       // [n_r_heavy] rows with long gather lists

@@ -156,6 +156,7 @@ struct cdn_plan {
             r_lin_c, r_lin_gones, r_con_ptr, r_con_src, r_con_kind, dev_g, dev_i, e_con_pk,
             r_con_pk;
         long gv[CDN_MAX_GROUPS][2];
+        long gd[CDN_MAX_GROUPS];
     } off;
     long nterms, ncon, nnzA;
     bool bound;
@@ -649,6 +650,8 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     }
     cdn_plan_dev& D = P->dev;
     D.dense = dense ? 1 : 0;
+    D.nhist = c->nhist > 0 ? c->nhist : 0;
+    D.hist_size = 0;
     D.heavy = HEAVY;
     D.n_e_heavy = (int)e_heavy.size(); D.n_r_heavy = (int)r_heavy.size();
     D.max_terms = P->max_terms;
@@ -663,6 +666,16 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
         d.out_off = out_off[g]; d.jac_off = jac_off[g];
         ivec vp(G.vpos, G.vpos + (long)G.nxin * G.n), vn(G.vneg, G.vneg + (long)G.nxin * G.n);
         O.gv[g][0] = put(B, vp); O.gv[g][1] = put(B, vn);
+        O.gd[g] = -1;
+        d.hist_off = 0;
+        if (G.ndelay > 0 && G.delay) {
+            std::vector<double> dl(G.delay, G.delay + (long)G.ndelay * G.n);
+            O.gd[g] = put(B, dl);
+            if (c->nhist > 0) {
+                d.hist_off = D.hist_size;
+                D.hist_size += (long)G.ndelay * G.n * c->nhist;
+            }
+        }
     }
     P->nterms = nterms;
     *out = P;
@@ -681,6 +694,7 @@ extern "C" int cdn_plan_info(cdn_plan* P, long* info) {
     info[8] = P->max_terms; info[9] = P->max_con;
     info[10] = P->dev.dev_out_size; info[11] = P->dev.dev_jac_size;
     info[12] = P->last_team;
+    info[13] = P->dev.hist_size;
     return CDN_OK;
 }
 
@@ -714,6 +728,7 @@ extern "C" int cdn_plan_bind(cdn_plan* P, void* dev_ws, long bytes, void* stream
     for (int g = 0; g < D.ngroups; ++g) {
         D.groups[g].vpos = (const int*)(base + O.gv[g][0]);
         D.groups[g].vneg = (const int*)(base + O.gv[g][1]);
+        D.groups[g].delay = O.gd[g] >= 0 ? (const double*)(base + O.gd[g]) : nullptr;
     }
     P->dev_struct = (cdn_plan_dev*)(base + struct_off);
     P->bound = true;

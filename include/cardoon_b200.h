@@ -65,6 +65,8 @@ typedef struct cdn_group_host {
     const int* cneg;      /* [ncs][n]                                        */
     const int* qpos;      /* [nqs][n]                                        */
     const int* qneg;      /* [nqs][n]                                        */
+    const double* delay;  /* [ndelay][n] delay of the last ndelay control
+                             ports (delayedContPorts), or NULL               */
 } cdn_group_host;
 
 typedef struct cdn_circuit_host {
@@ -82,6 +84,9 @@ typedef struct cdn_circuit_host {
     int heavy;            /* gather/Crout lists longer than this are reduced by
                              the whole thread team (0 = default 256)         */
     int skip_q;           /* 1: DC plan, charge outputs contribute nothing   */
+    int nhist;            /* transient with delayed ports: samples of port-
+                             voltage history kept per delayed port (>= ceil(
+                             max delay / h) + 2); 0 = ports are not delayed  */
 } cdn_circuit_host;
 
 typedef struct cdn_plan cdn_plan;
@@ -144,6 +149,7 @@ typedef struct cdn_run_host {
     double a0;           /* integration coefficient: 2/h trap, 1/h BE, 0 DC  */
     double gmin;         /* gmin stepping (multiplies the E pattern)         */
     double lambda;       /* source stepping factor (1 = full sources)        */
+    double h;            /* time step (delayed-port interpolation)           */
     int maxiter, errfunc;
     int use_q;           /* 0: DC (currents only), 1: transient              */
     int im;              /* 0 backward Euler, 1 trapezoidal                  */
@@ -168,7 +174,7 @@ typedef struct cdn_run_host {
 
 long cdn_engine_ws_doubles(cdn_plan* plan);
 /* offsets (doubles) of x, dx, ivec, sv, q, qprev, dq, y, tmp, xb, lu, out,
- * jac, piv inside one instance's state                                          */
+ * jac, hist, piv inside one instance's state (15 longs)                                          */
 int cdn_engine_layout(cdn_plan* plan, long* off);
 int cdn_engine_run(cdn_plan* plan, const cdn_run_host* run, void* stream);
 

@@ -72,9 +72,11 @@ def test_op_matches_oracle(lib, deck):
     check_op(x, xr)
 
 
-def tran_both(deck, max_samples=None):
+def tran_both(deck, max_samples=None, tstep=None):
     ckt, queue = S.load_circuit(S.net(deck))
     an = [a for a in queue if a.anType == 'tran'][0]
+    if tstep is not None:
+        an.tstep = tstep
     nd.make_nodal_circuit(ckt)
     dc = nd.DCNodal(ckt)
     imo = Trapezoidal() if an.im == 'trap' else BEuler()
@@ -131,6 +133,18 @@ def test_tran_soliton(lib):
                                   'inverter_chain_bsim.net'])
 def test_tran_matches_oracle(lib, deck):
     wave, iters, status, ref, tran = tran_both(deck, max_samples=150)
+    check_tran(wave, iters, status, ref)
+
+
+@pytest.mark.parametrize('tstep', [None, 2e-12, 1.7e-12])
+def test_tran_mesfetc_delayed_ports(lib, tstep):
+    """Curtice MESFET: two delayed control ports (tau = 5 ps) interpolated
+    from the port-voltage history (reference nodal.py:82-108).  tstep = 5 ps
+    is the deck's own (tau <= h branch: derivative coefficient (h-tau)/h);
+    the smaller steps take the history-walk branch."""
+    wave, iters, status, ref, tran = tran_both('mesfetc_plain.net',
+                                               max_samples=300, tstep=tstep)
+    assert tran.engine.nhist >= 3
     check_tran(wave, iters, status, ref)
 
 
