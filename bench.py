@@ -47,6 +47,16 @@ def measured_peaks():
     return 6650., 'fallback'
 
 
+def measured_traffic(workload):
+    """DRAM bytes of the dominant kernel from the committed ncu capture."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        with open(p) as f:
+            return json.load(f).get(workload)
+    except (OSError, ValueError):
+        return None
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,'
@@ -317,8 +327,12 @@ def run_deveval(args, D):
         bytes_eval = 8. * (npar + nxin + nout + nout * nxin)
         t_step = ms * 1e-3 / args.steps
         ach = n * flop / t_step / 1e12
+        tr = measured_traffic('deveval')
         roof = dict(bound='fp64', achieved=ach, peak=peak / 1e12,
-                    unit='TFLOP/s', frac=ach / (peak / 1e12), traffic=None,
+                    unit='TFLOP/s', frac=ach / (peak / 1e12),
+                    traffic=(tr['bytes_per_instance'] * n / len(G)
+                             if tr else None),
+                    traffic_source=(tr or {}).get('source'),
                     peak_source='cdn_fp64_peak (DFMA microbenchmark, this '
                                 'run)',
                     flop_per_eval=flop, transcendental_per_eval=trans,
@@ -507,8 +521,11 @@ def run_mc(args, D):
         t_step = ms * 1e-3 / args.steps
         peak = lib.fp64_peak()
         ach = flop / t_step / 1e12
+        tr = measured_traffic('mc')
         roof = dict(bound='fp64', achieved=ach, peak=peak / 1e12,
-                    unit='TFLOP/s', frac=ach / (peak / 1e12), traffic=None,
+                    unit='TFLOP/s', frac=ach / (peak / 1e12),
+                    traffic=tr['bytes_per_instance'] * B if tr else None,
+                    traffic_source=(tr or {}).get('source'),
                     kernel='engine_tile_kernel<BSIM3, 8> (whole time loop)',
                     peak_source='cdn_fp64_peak (DFMA microbenchmark, this '
                                 'run)',
@@ -627,8 +644,11 @@ def run_soliton(args, D):
         t_step = ms * 1e-3 / args.steps
         hbm, how = measured_peaks()
         ach = algo / t_step / 1e9
+        tr = measured_traffic('soliton')
         roof = dict(bound='hbm', achieved=ach, peak=hbm, unit='GB/s',
-                    frac=ach / hbm, traffic=None,
+                    frac=ach / hbm,
+                    traffic=tr['bytes_per_launch'] if tr else None,
+                    traffic_source=(tr or {}).get('source'),
                     kernel='engine_{0}_kernel<DIODE, 256> (whole time loop, '
                            'state L2-resident)'.format(e.last_team()),
                     peak_source=how, bytes_per_newton_iteration=per_iter,

@@ -3,7 +3,7 @@ Analysis registry (``anClass``) and output requests.
 
 Mirror of the reference's cardoon/analyses/__init__.py (:21-70).  This
 back-end provides the two analyses on the Newton hot path, ``op`` and
-``tran``; the other reference analyses (``dc``, ``ac``, ``testdev``) are
+``tran`` and the ``dc`` sweep; the other reference analyses (``ac``, ``testdev``) are
 registered as placeholders that report they are not available, so netlists
 that request them still load and run the rest.
 """
@@ -59,9 +59,9 @@ class _AnyParams(dict):
 anClass = {}
 validReqTypes = ['tran', 'dc', 'ac_mag', 'ac_phase', 'ac_dB']
 
-from . import op, tran          # noqa: E402
+from . import op, tran, dc      # noqa: E402
 
-for _module in (op, tran):
+for _module in (op, tran, dc):
     anClass[_module.aClass.anType] = _module.aClass
-for _name in ('dc', 'ac', 'testdev'):
+for _name in ('ac', 'testdev'):
     anClass[_name] = _placeholder(_name, _AnyParams())

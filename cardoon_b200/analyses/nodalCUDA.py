@@ -228,6 +228,23 @@ class Topology(object):
                     [e.nD_delay for e in elems], dtype=np.float64).T)
             self.groups.append(g)
 
+    def same_formulation(self, other):
+        """True if ``other`` has the same linear stamps, device groups and
+        port rows (then a plan built for one serves the other)."""
+        if self.n != other.n or len(self.groups) != len(other.groups):
+            return False
+        for a, b in zip(self.G + self.C + self.E, other.G + other.C + other.E):
+            if a.shape != b.shape or not np.array_equal(a, b):
+                return False
+        keys = ('model', 'flags', 'nxin', 'ncs', 'nqs', 'ndelay', 'n')
+        arrs = ('vpos', 'vneg', 'cpos', 'cneg', 'qpos', 'qneg')
+        for g, h in zip(self.groups, other.groups):
+            if any(g[k] != h[k] for k in keys):
+                return False
+            if any(not np.array_equal(g[k], h[k]) for k in arrs):
+                return False
+        return True
+
     def pack_params(self):
         """[npar, n] packed records per group (post-process_params)."""
         return [np.ascontiguousarray(
@@ -859,6 +876,13 @@ class DCNodal(_NLFunction):
         changes (dc.py:179-188 pattern)."""
         self.ckt.__dict__.pop('_cuda_topology', None)
         topo = get_topology(self.ckt)
+        old = getattr(self, 'engine', None)
+        if old is not None and old.topo.same_formulation(topo):
+            # only device records (or source values) changed: the symbolic
+            # plan stays, the records are uploaded again
+            old.topo = topo
+            old.set_params(None)
+            return
         self.engine = Engine(topo, use_q=False, a0=0.,
                              x_ref=self.get_guess())
 

@@ -723,6 +723,29 @@ def run_op(ckt, glVar, idx=None):
     return dict(x=x, res=res, iterations=it, idx=idx, dc=dc)
 
 
+def run_dc(ckt, glVar, device, param, start, stop, num):
+    """DC sweep of one device parameter (dc.py:141-205): dict(sweep,
+    X[num, N], iters, idx).  The circuit's element is left at the last
+    value; callers reload the deck."""
+    idx = prepare(ckt)
+    opt = Options(glVar)
+    dev = ckt.elemDict[device]
+    sweep = np.linspace(start=start, stop=stop, num=num)
+    x = RefDC(ckt, idx, opt).get_guess()
+    X = np.zeros((num, idx.dimension))
+    iters = np.zeros(num, dtype=int)
+    for i, value in enumerate(sweep):
+        setattr(dev, param, value)
+        dev.process_params()
+        idx = NodalIndex(ckt)                   # restore + re-process
+        dc = RefDC(ckt, idx, opt)               # refresh()
+        sV = dc.get_source()
+        x, res, it = solve(x, sV, dc.helpers)
+        X[i] = x
+        iters[i] = it
+    return dict(sweep=sweep, X=X, iters=iters, idx=idx)
+
+
 def run_tran(ckt, glVar, tstop, tstep, im='trap', idx=None, max_samples=None,
              x0=None):
     """Fixed-step transient: dict(t, X[nsamples, N], iters, res, idx).

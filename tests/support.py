@@ -70,9 +70,17 @@ def rel_err(a, b, floor):
 
 
 def smoke_check():
-    """BSIM3 + diode device evaluation on cuda:0 against the oracle."""
+    """One small invocation of the hot path on cuda:0 against the oracle:
+    BSIM3 device evaluation, the bias_npn operating point (the reference's
+    printed known answer: 17 iterations) and 40 samples of the ring_bsim3
+    transient, all through the C ABI."""
     from cardoon_b200._lib import get_lib
+    from cardoon_b200.analyses import nodalCUDA as nd
+    from cardoon_b200.analyses.fsolve import solve
+    from cardoon_b200.analyses.integration import Trapezoidal
+    from cardoon_b200.globalVars import glVar
     from oracle.models import device_eval
+    from oracle import nodal_ref as R
     lib = get_lib(0)
     ckt, _ = load_circuit(net('ring_bsim3.net'))
     rng = np.random.default_rng(7)
@@ -82,6 +90,31 @@ def smoke_check():
         ro, rj = device_eval(elem, xin, True)
         assert rel_err(out, ro, 1e-18) < 1e-9, 'BSIM3 value mismatch'
         assert rel_err(jac, rj, 1e-12) < 1e-7, 'BSIM3 Jacobian mismatch'
+    # operating point of bias_npn.net
+    ckt, _ = load_circuit(net('bias_npn.net'))
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    x, res, it = solve(dc.get_guess(), dc.get_source(),
+                       dc.convergence_helpers)
+    ref = R.run_op(ckt, glVar)
+    assert abs(it - 17) <= 1 and abs(it - ref['iterations']) <= 1
+    assert np.all(np.abs(x - ref['x']) < 1e-9 * np.abs(ref['x']) + 1e-12)
+    # device-resident transient
+    ckt, queue = load_circuit(net('ring_bsim3.net'))
+    an = queue[0]
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    tran = nd.TransientNodal(ckt, Trapezoidal())
+    x, res, it = solve(dc.get_guess(), tran.get_source(0.).copy(),
+                       dc.convergence_helpers)
+    timeVec = np.arange(0., an.tstop, an.tstep)[:40]
+    wave, iters, resv, status = tran.run(x, timeVec,
+                                         list(range(ckt.nD_dimension)))
+    ref = R.run_tran(ckt, glVar, an.tstop, an.tstep, an.im, max_samples=40)
+    assert status == 0
+    assert np.all(np.abs(wave - ref['X'])
+                  < glVar.reltol * np.abs(ref['X']) + glVar.abstol)
+    assert np.max(np.abs(iters - ref['iters'])) <= 1
 
 
 def chain_netlist(K, path=None):

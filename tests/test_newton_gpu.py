@@ -249,3 +249,48 @@ def test_tran_inverter_chain_synthetic(lib, team, monkeypatch):
         check_tran(wave[0], iters[0], int(status[0]), ref)
     finally:
         os.remove(path)
+
+
+def test_dc_sweep_bias_npn(lib, capsys):
+    """`.analysis dc` of the reference's test/bias_npn.net (dc.py:89-242):
+    50-point sweep of a source value, each point starting from the previous
+    solution."""
+    ckt, queue = S.load_circuit(S.net('bias_npn.net'))
+    an = [a for a in queue if a.anType == 'dc'][0]
+    ckt.saveReqList = []
+    ckt.plotReqList = []
+    an.run(ckt)
+    got = np.array([t.dC_v for t in ckt.nD_termList]).T
+    assert got.shape == (an.num, ckt.nD_dimension)
+    ckt2, _ = S.load_circuit(S.net('bias_npn.net'))
+    ref = R.run_dc(ckt2, glVar, an.device, an.param, an.start, an.stop,
+                   an.num)
+    err = np.abs(got - ref['X'])
+    assert np.all(err < 1e-9 * np.abs(ref['X']) + 1e-12), err.max()
+    assert np.max(np.abs(an.iterations - ref['iters'])) <= 1
+    # the swept element is restored to its netlist value
+    assert ckt.elemDict[an.device].vdc == 10.
+    assert 'Average iterations' in capsys.readouterr().out
+
+
+def test_dc_sweep_device_parameter(lib):
+    """Sweep of a MOSFET parameter (vth0 of one transistor of the BSIM3
+    inverter chain): only device records change, the plan is kept."""
+    from cardoon_b200.analyses.dc import DCSweep
+    ckt, _ = S.load_circuit(S.net('inverter_chain_bsim.net'))
+    ckt.saveReqList = []
+    ckt.plotReqList = []
+    an = DCSweep()
+    an.set_param('device', 'x2:mosbsim3:m2')
+    an.set_param('param', 'w')
+    an.set_param('start', 1e-6)
+    an.set_param('stop', 2e-5)
+    an.set_param('num', 12)
+    an.set_attributes()
+    an.run(ckt)
+    got = np.array([t.dC_v for t in ckt.nD_termList]).T
+    ckt2, _ = S.load_circuit(S.net('inverter_chain_bsim.net'))
+    ref = R.run_dc(ckt2, glVar, 'x2:mosbsim3:m2', 'w', 1e-6, 2e-5, 12)
+    err = np.abs(got - ref['X'])
+    assert np.all(err < 1e-9 * np.abs(ref['X']) + 1e-12), err.max()
+    assert np.max(np.abs(an.iterations - ref['iters'])) <= 1
