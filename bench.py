@@ -174,6 +174,19 @@ class Dist(object):
             self.dist.destroy_process_group()
 
 
+def phase_shares(D, engine, step):
+    """One extra, untimed step with the in-kernel phase timers on: share of
+    instance 0's cycles per phase of the time loop."""
+    engine.profile = True
+    engine.phase_cycles()
+    step()
+    D.torch.cuda.synchronize()
+    c = engine.phase_cycles()
+    engine.profile = False
+    tot = float(sum(c.values())) or 1.
+    return {k: round(v / tot, 4) for k, v in c.items()}
+
+
 def timed_steps(D, step, steps, warmup, flush=None):
     """W untimed + K timed steps; device time (CUDA events), max over ranks.
 
@@ -272,6 +285,7 @@ def run_deveval(args, D):
     lib = get_lib(D.local)
     inp = deveval_inputs(args.n or (1 << 22), seed=1234 + D.rank)
     lib.dll.cdn_set_tuning(0, args.minblocks)
+    lib.dll.cdn_set_tuning(1, args.npre)
     n, nout, nxin = inp['n'], inp['nout'], inp['nxin']
     G = []
     for g in inp['groups']:
@@ -482,6 +496,7 @@ def run_mc(args, D):
     clocks = clk.stop(t0, t1)
     wave, iters, status, opit = state['out']
     nfail = int((status != 0).sum().item())
+    phases = phase_shares(D, tr, step)
     total = D.sum_over_ranks(B) * args.steps
     value = total / (ms * 1e-3)
 
@@ -546,6 +561,7 @@ def run_mc(args, D):
                                 'instances'.format(nsamples, B),
                                 instances_per_gpu=B, samples=nsamples,
                                 failed_instances=nfail,
+                                phase_shares_instance0=phases,
                                 avg_newton_iterations_per_sample=float(
                                     iters.sum().item()) / (B * nsamples),
                                 l2='per-instance records ({0:.1f} MB) are '
@@ -619,6 +635,7 @@ def run_soliton(args, D):
     clocks = clk.stop(t0, t1)
     wave, iters, res, status = state['out']
     assert int(status[0].item()) == 0, 'soliton transient did not converge'
+    phases = phase_shares(D, e, step)
     value = D.world * (nsamples - 1) * args.steps / (ms * 1e-3)
 
     def e2e_step():
@@ -669,6 +686,7 @@ def run_soliton(args, D):
                                 .format(nsamples), samples=nsamples,
                                 op_iterations=op_it,
                                 avg_newton_iterations=it_total / nsamples,
+                                phase_shares=phases,
                                 l2='single-circuit state (~0.5 MB) is '
                                    'L2-resident; latency-bound by design'),
                     clocks=clocks, e2e=e2e, gpu_launches=launches,
@@ -766,6 +784,7 @@ def run_chain(args, D):
     clocks = clk.stop(t0, t1)
     wave, iters, res, status = state['out']
     assert int(status[0].item()) == 0, 'chain transient did not converge'
+    phases = phase_shares(D, e, step)
     value = D.world * (nsamples - 1) * args.steps / (ms * 1e-3)
 
     def e2e_step():
@@ -819,6 +838,7 @@ def run_chain(args, D):
                                 stages=K, samples=nsamples,
                                 op_iterations=op_it,
                                 avg_newton_iterations=it_total / nsamples,
+                                phase_shares=phases,
                                 host_setup_s=t_setup,
                                 l2='state {0:.0f} MB + records {1:.0f} MB per '
                                    'iteration: larger than L2 for the full '
@@ -886,6 +906,8 @@ def main():
                     choices=['deveval', 'mc', 'soliton', 'chain'])
     ap.add_argument('--minblocks', type=int, default=0,
                     help='deveval tuning: CTAs/SM register limit (0 = default)')
+    ap.add_argument('--npre', type=int, default=-1,
+                    help='deveval tuning: record rows prefetched to L1')
     ap.add_argument('--n', type=int, default=0,
                     help='instances per GPU (0 = workload default)')
     args = ap.parse_args()

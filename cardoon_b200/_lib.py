@@ -65,7 +65,7 @@ class RunHost(C.Structure):
                 ('blocks', C.c_int),
                 ('src_rows', _vp), ('src_val', _vp), ('src_dc', _vp),
                 ('save_rows', _vp), ('wave', _vp), ('iters', _vp),
-                ('res', _vp), ('status', _vp), ('red', _vp)]
+                ('res', _vp), ('status', _vp), ('red', _vp), ('prof', _vp)]
 
 
 OP_NEWTON, OP_TRAN, OP_UPDATE_Q, OP_SET_IC, OP_ACCEPT, OP_RHS, OP_CHORD, \

@@ -550,6 +550,8 @@ class Engine(object):
             self.ws = torch.zeros((batch, self.ws_per), dtype=torch.float64,
                                   device=lib.device)
         keep = []
+        self.profile = False
+        self.prof = torch.zeros(8, dtype=torch.int64, device=lib.device)
         self.red = torch.zeros(4096, dtype=torch.float64, device=lib.device)
         self.x = torch.zeros((batch, n), dtype=torch.float64,
                              device=lib.device)
@@ -628,6 +630,7 @@ class Engine(object):
         r.ws = lib.ptr(self.ws)
         r.iters, r.res = lib.ptr(self.iters), lib.ptr(self.res)
         r.status, r.red = lib.ptr(self.status), lib.ptr(self.red)
+        r.prof = lib.ptr(self.prof) if self.profile else None
         return r
 
     def _launch(self, r):
@@ -635,6 +638,17 @@ class Engine(object):
         lib.check(lib.dll.cdn_engine_run(self.plan, C.byref(r),
                                          lib.stream()))
         self.launches += 1
+
+    PHASES = ('device_sweep', 'assembly', 'factor', 'solve', 'update',
+              'accept_rhs', 'chord')
+
+    def phase_cycles(self, reset=True):
+        """SM cycles instance 0 spent per phase since the last reset (set
+        ``engine.profile = True`` before launching)."""
+        c = self.prof.cpu().numpy()
+        if reset:
+            self.prof.zero_()
+        return dict(zip(self.PHASES, (int(v) for v in c)))
 
     def last_team(self):
         """Thread team of the last launch: 'tile', 'block' or 'grid'."""

@@ -59,7 +59,7 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     A.nsrc = r->nsrc; A.nsave = r->nsave; A.helpers = r->helpers;
     A.src_rows = r->src_rows; A.src_val = r->src_val; A.src_dc = r->src_dc;
     A.save_rows = r->save_rows; A.wave = r->wave; A.iters = r->iters; A.res = r->res;
-    A.status = r->status; A.red = r->red;
+    A.status = r->status; A.red = r->red; A.prof = r->prof;
     if (A.B <= 0) return CDN_OK;
     if (!A.x) return cdn_fail(ctx, CDN_ERR_ARG, "engine: x is NULL");
 
@@ -87,6 +87,13 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
             // state in shared memory: shrink the CTA until it fits
             while (c.tpb > T && (long)(c.tpb / T) * per * 8 > 200 * 1024) c.tpb /= 2;
             c.smem = (long)(c.tpb / T) * per * 8;
+            // room for the shared-memory copy of the plan's gather lists
+            const long pb = plan_smem_bytes(*D);
+            if (D->dense && !D->n_e_heavy && !D->n_r_heavy && pb <= 32 * 1024 &&
+                c.smem + pb <= 200 * 1024) {
+                A.plan_smem = (int)pb;
+                c.smem += pb;
+            }
             if (c.smem > 227 * 1024) return cdn_fail(ctx, CDN_ERR_ARG, "engine: circuit state does not fit shared memory; pass a workspace");
         }
         const int tiles = c.tpb / T;

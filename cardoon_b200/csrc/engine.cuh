@@ -25,6 +25,11 @@
 
 namespace cg = cooperative_groups;
 
+// Plan arrays are read with generic loads: the tile kernels keep a copy of the
+// (small) plan of a dense circuit in shared memory, the other teams read the
+// global copy.
+#define CDN_LD(p) (*(p))
+
 // ---- run description ---------------------------------------------------------------
 // operation codes CDN_OP_*: include/cardoon_b200.h
 struct cdn_opts {
@@ -61,6 +66,10 @@ struct cdn_engine_args {
     double* res;                // same shape as iters
     int* status;                // [B]: 0 ok, k > 0 first failed sample, -1 Newton failed
     double* red;                // GridTeam reduction scratch
+    int plan_smem;              // tile kernels: bytes reserved for a shared-memory copy
+                                // of the plan's gather lists (0: read the global copy)
+    long long* prof;            // optional [8]: cycles of instance 0 per phase (device
+                                // sweep, assembly, factor, solve, update, accept, chord)
 };
 
 // status bits or'ed into the negative range are avoided: singular pivots are
@@ -285,7 +294,7 @@ __device__ __forceinline__ void gather_xin(const cdn_group_dev& G, int i, const 
     for (int c = 0; c < CDN_MAX_XIN; ++c) {
         double xv = 0.0;
         if (c < G.nxin) {
-            const int a = __ldg(G.vpos + c * G.n + i), b = __ldg(G.vneg + c * G.n + i);
+            const int a = CDN_LD(G.vpos + c * G.n + i), b = CDN_LD(G.vneg + c * G.n + i);
             if (a >= 0) xv += x[a];
             if (b >= 0) xv -= x[b];
         }
@@ -311,7 +320,7 @@ __device__ __forceinline__ void eval_model(const cdn_group_dev& G, const PV& p, 
             if (d < G.ndelay) {
                 const int c = G.nxin - G.ndelay + d;
                 const double* ring = w.hist + G.hist_off + ((long)d * G.n + i) * nhist;
-                v[c].v = delay_interp(__ldg(G.delay + d * G.n + i), v[c].v, h, ring, nhist, head,
+                v[c].v = delay_interp(CDN_LD(G.delay + d * G.n + i), v[c].v, h, ring, nhist, head,
                                       &sink.coef[d]);
             }
     }
@@ -331,7 +340,7 @@ template <int MS, bool DERIV>
 __device__ __noinline__ void eval_one(const cdn_group_dev& G, int b, int i, const double* x,
                                       const Ws& w, int nhist, double h, int head) {
     long col = (G.per_inst ? (long)b * G.n : 0L) + i;
-    if (G.pidx) col = __ldg(G.pidx + col);
+    if (G.pidx) col = CDN_LD(G.pidx + col);
     PV p;
     p.base = G.params + col;
     p.ld = G.ldp;
@@ -372,7 +381,7 @@ __device__ __forceinline__ void eval_devices(Team& tm, const cdn_plan_dev& P, in
     const int head = nhist ? w.piv[P.n + 1] : 0;
     if (Team::kFlat) {
         for (int d = tm.rank(); d < P.ndev; d += tm.size())
-            eval_one<MS, DERIV>(P.groups[__ldg(P.dev_g + d)], b, __ldg(P.dev_i + d), x, w, nhist,
+            eval_one<MS, DERIV>(P.groups[CDN_LD(P.dev_g + d)], b, CDN_LD(P.dev_i + d), x, w, nhist,
                                 h, head);
     } else {
         for (int g = 0; g < P.ngroups; ++g) {
@@ -399,7 +408,7 @@ __device__ __forceinline__ void hist_store(Team& tm, const cdn_plan_dev& P, cons
         for (int t = tm.rank(); t < G.ndelay * G.n; t += tm.size()) {
             const int d = t / G.n, i = t - d * G.n;
             const int c = G.nxin - G.ndelay + d;
-            const int a = __ldg(G.vpos + c * G.n + i), bb = __ldg(G.vneg + c * G.n + i);
+            const int a = CDN_LD(G.vpos + c * G.n + i), bb = CDN_LD(G.vneg + c * G.n + i);
             double v = 0.0;
             if (a >= 0) v += w.x[a];
             if (bb >= 0) v -= w.x[bb];
@@ -414,6 +423,13 @@ __device__ __forceinline__ void hist_store(Team& tm, const cdn_plan_dev& P, cons
 }
 
 // ---- assembly (gather; no atomics) ------------------------------------------------------
+// coefficient of a packed gather entry: +-1 for a current row, +-a0 for a
+// charge row (DC plans hold no charge entries)
+__device__ __forceinline__ double pk_coef(unsigned pk, double a0) {
+    const double c = (pk & (1u << 30)) ? a0 : 1.0;
+    return (pk & (1u << 29)) ? -c : c;
+}
+
 // iVec = G'x + Ti i(x) + a0 Tq q(x) (+ gmin Gones x);  y = lambda*sv - iVec
 // Rows / slots with more than CDN_HEAVY gather terms (hub nodes such as a
 // supply rail) are summed by the whole team, everything else by one thread.
@@ -421,29 +437,41 @@ template <class Team>
 __device__ __forceinline__ double row_sum(const cdn_plan_dev& P, const Ws& w, const cdn_opts& o,
                                           double a0, int r, int first, int stride) {
     double acc = 0.0;
-    const int l0 = __ldg(P.r_lin_ptr + r), l1 = __ldg(P.r_lin_ptr + r + 1);
+    const int l0 = CDN_LD(P.r_lin_ptr + r), l1 = CDN_LD(P.r_lin_ptr + r + 1);
     for (int k = l0 + first; k < l1; k += stride) {
-        double g = __ldg(P.r_lin_g + k);
-        if (o.use_q) g += a0 * __ldg(P.r_lin_c + k);
-        if (o.gmin != 0.0) g += o.gmin * __ldg(P.r_lin_gones + k);
-        acc += g * w.x[__ldg(P.r_lin_col + k)];
+        double g = CDN_LD(P.r_lin_g + k);
+        if (o.use_q) g += a0 * CDN_LD(P.r_lin_c + k);
+        if (o.gmin != 0.0) g += o.gmin * CDN_LD(P.r_lin_gones + k);
+        acc += g * w.x[CDN_LD(P.r_lin_col + k)];
     }
     // device outputs: branch-free, the sign and the a0 factor of charge rows
     // are decoded from the packed entry (DC plans hold no charge entries)
-    const int c0 = __ldg(P.r_con_ptr + r), c1 = __ldg(P.r_con_ptr + r + 1);
-#pragma unroll 4
-    for (int k = c0 + first; k < c1; k += stride) {
-        const unsigned pk = __ldg(P.r_con_pk + k);
-        double c = (pk & (1u << 30)) ? a0 : 1.0;
-        if (pk & (1u << 29)) c = -c;
-        acc = fma(c, w.out[pk & 0x1fffffffu], acc);
+    const int c0 = CDN_LD(P.r_con_ptr + r), c1 = CDN_LD(P.r_con_ptr + r + 1);
+    int k = c0 + first;
+    if (stride == 1) {
+        double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (; k + 3 < c1; k += 4) {
+            const unsigned p0 = CDN_LD(P.r_con_pk + k), p1 = CDN_LD(P.r_con_pk + k + 1);
+            const unsigned p2 = CDN_LD(P.r_con_pk + k + 2), p3 = CDN_LD(P.r_con_pk + k + 3);
+            const double o0 = w.out[p0 & 0x1fffffffu], o1 = w.out[p1 & 0x1fffffffu];
+            const double o2 = w.out[p2 & 0x1fffffffu], o3 = w.out[p3 & 0x1fffffffu];
+            acc = fma(pk_coef(p0, a0), o0, acc);
+            a1 = fma(pk_coef(p1, a0), o1, a1);
+            a2 = fma(pk_coef(p2, a0), o2, a2);
+            a3 = fma(pk_coef(p3, a0), o3, a3);
+        }
+        acc += (a1 + a2) + a3;
+    }
+    for (; k < c1; k += stride) {
+        const unsigned pk = CDN_LD(P.r_con_pk + k);
+        acc = fma(pk_coef(pk, a0), w.out[pk & 0x1fffffffu], acc);
     }
     return acc;
 }
 
 __device__ __forceinline__ bool row_heavy(const cdn_plan_dev& P, int r) {
-    return (__ldg(P.r_lin_ptr + r + 1) - __ldg(P.r_lin_ptr + r)) +
-           (__ldg(P.r_con_ptr + r + 1) - __ldg(P.r_con_ptr + r)) > P.heavy;
+    return (CDN_LD(P.r_lin_ptr + r + 1) - CDN_LD(P.r_lin_ptr + r)) +
+           (CDN_LD(P.r_con_ptr + r + 1) - CDN_LD(P.r_con_ptr + r)) > P.heavy;
 }
 
 template <class Team>
@@ -457,7 +485,7 @@ __device__ __forceinline__ void residual(Team& tm, const cdn_plan_dev& P, const 
         w.y[r] = o.lambda * w.sv[r] - acc;
     }
     for (int h = 0; h < P.n_r_heavy; ++h) {
-        const int r = __ldg(P.r_heavy + h);
+        const int r = CDN_LD(P.r_heavy + h);
         const double acc = tm.sum(row_sum<Team>(P, w, o, a0, r, tm.rank(), tm.size()));
         if (tm.rank() == 0) {
             w.ivec[r] = acc;
@@ -471,13 +499,26 @@ template <class Team>
 __device__ __forceinline__ double slot_sum(const cdn_plan_dev& P, const Ws& w, const cdn_opts& o,
                                            double a0, int e, int first, int stride) {
     double v = 0.0;
-    const int c0 = __ldg(P.e_con_ptr + e), c1 = __ldg(P.e_con_ptr + e + 1);
-#pragma unroll 4
-    for (int k = c0 + first; k < c1; k += stride) {
-        const unsigned pk = __ldg(P.e_con_pk + k);
-        double c = (pk & (1u << 30)) ? a0 : 1.0;
-        if (pk & (1u << 29)) c = -c;
-        v = fma(c, w.jac[pk & 0x1fffffffu], v);
+    const int c0 = CDN_LD(P.e_con_ptr + e), c1 = CDN_LD(P.e_con_ptr + e + 1);
+    int k = c0 + first;
+    if (stride == 1) {
+        // four independent accumulators: the loads of a group overlap
+        double v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        for (; k + 3 < c1; k += 4) {
+            const unsigned p0 = CDN_LD(P.e_con_pk + k), p1 = CDN_LD(P.e_con_pk + k + 1);
+            const unsigned p2 = CDN_LD(P.e_con_pk + k + 2), p3 = CDN_LD(P.e_con_pk + k + 3);
+            const double j0 = w.jac[p0 & 0x1fffffffu], j1 = w.jac[p1 & 0x1fffffffu];
+            const double j2 = w.jac[p2 & 0x1fffffffu], j3 = w.jac[p3 & 0x1fffffffu];
+            v = fma(pk_coef(p0, a0), j0, v);
+            v1 = fma(pk_coef(p1, a0), j1, v1);
+            v2 = fma(pk_coef(p2, a0), j2, v2);
+            v3 = fma(pk_coef(p3, a0), j3, v3);
+        }
+        v += (v1 + v2) + v3;
+    }
+    for (; k < c1; k += stride) {
+        const unsigned pk = CDN_LD(P.e_con_pk + k);
+        v = fma(pk_coef(pk, a0), w.jac[pk & 0x1fffffffu], v);
     }
     return v;
 }
@@ -486,20 +527,21 @@ template <class Team>
 __device__ __forceinline__ void assemble(Team& tm, const cdn_plan_dev& P, const Ws& w,
                                          const cdn_opts& o) {
     const double a0 = o.use_q ? o.a0 : 0.0;
-    for (int e = tm.rank(); e < P.nlu; e += tm.size()) {
-        if (P.n_e_heavy && __ldg(P.e_con_ptr + e + 1) - __ldg(P.e_con_ptr + e) > P.heavy) continue;
-        double v = __ldg(P.e_g + e);
-        if (o.use_q) v += a0 * __ldg(P.e_c + e);
-        if (o.gmin != 0.0) v += o.gmin * __ldg(P.e_gones + e);
+    for (int q = tm.rank(); q < P.nlu; q += tm.size()) {
+        const int e = P.dense ? CDN_LD(P.e_bal + q) : q;
+        if (P.n_e_heavy && CDN_LD(P.e_con_ptr + e + 1) - CDN_LD(P.e_con_ptr + e) > P.heavy) continue;
+        double v = CDN_LD(P.e_g + e);
+        if (o.use_q) v += a0 * CDN_LD(P.e_c + e);
+        if (o.gmin != 0.0) v += o.gmin * CDN_LD(P.e_gones + e);
         w.lu[e] = v + slot_sum<Team>(P, w, o, a0, e, 0, 1);
     }
     for (int h = 0; h < P.n_e_heavy; ++h) {
-        const int e = __ldg(P.e_heavy + h);
+        const int e = CDN_LD(P.e_heavy + h);
         const double t = tm.sum(slot_sum<Team>(P, w, o, a0, e, tm.rank(), tm.size()));
         if (tm.rank() == 0) {
-            double v = __ldg(P.e_g + e);
-            if (o.use_q) v += a0 * __ldg(P.e_c + e);
-            if (o.gmin != 0.0) v += o.gmin * __ldg(P.e_gones + e);
+            double v = CDN_LD(P.e_g + e);
+            if (o.use_q) v += a0 * CDN_LD(P.e_c + e);
+            if (o.gmin != 0.0) v += o.gmin * CDN_LD(P.e_gones + e);
             w.lu[e] = v + t;
         }
     }
@@ -510,12 +552,12 @@ template <class Team>
 __device__ __forceinline__ double charge_sum(const cdn_plan_dev& P, const Ws& w, int r, int first,
                                              int stride) {
     double acc = 0.0;
-    const int l0 = __ldg(P.r_lin_ptr + r), l1 = __ldg(P.r_lin_ptr + r + 1);
+    const int l0 = CDN_LD(P.r_lin_ptr + r), l1 = CDN_LD(P.r_lin_ptr + r + 1);
     for (int k = l0 + first; k < l1; k += stride)
-        acc += __ldg(P.r_lin_c + k) * w.x[__ldg(P.r_lin_col + k)];
-    const int c0 = __ldg(P.r_con_ptr + r), c1 = __ldg(P.r_con_ptr + r + 1);
+        acc += CDN_LD(P.r_lin_c + k) * w.x[CDN_LD(P.r_lin_col + k)];
+    const int c0 = CDN_LD(P.r_con_ptr + r), c1 = CDN_LD(P.r_con_ptr + r + 1);
     for (int k = c0 + first; k < c1; k += stride) {
-        const unsigned pk = __ldg(P.r_con_pk + k);
+        const unsigned pk = CDN_LD(P.r_con_pk + k);
         if (pk & (1u << 30)) {
             const double v = w.out[pk & 0x1fffffffu];
             acc += (pk & (1u << 29)) ? -v : v;
@@ -531,7 +573,7 @@ __device__ __forceinline__ void charge(Team& tm, const cdn_plan_dev& P, const Ws
         w.q[r] = charge_sum<Team>(P, w, r, 0, 1);
     }
     for (int h = 0; h < P.n_r_heavy; ++h) {
-        const int r = __ldg(P.r_heavy + h);
+        const int r = CDN_LD(P.r_heavy + h);
         const double acc = tm.sum(charge_sum<Team>(P, w, r, tm.rank(), tm.size()));
         if (tm.rank() == 0) w.q[r] = acc;
     }
@@ -599,28 +641,28 @@ __device__ __forceinline__ void dense_solve(Team& tm, const double* a, const int
 template <class Team>
 __device__ __forceinline__ void sparse_factor(Team& tm, const cdn_plan_dev& P, double* lu) {
     for (int l = 0; l < P.nlev_f; ++l) {
-        const int e0 = __ldg(P.f_lvl_ptr + l), e1 = __ldg(P.f_lvl_ptr + l + 1);
-        const int nh = __ldg(P.f_lvl_nheavy + l);
+        const int e0 = CDN_LD(P.f_lvl_ptr + l), e1 = CDN_LD(P.f_lvl_ptr + l + 1);
+        const int nh = CDN_LD(P.f_lvl_nheavy + l);
         for (int h = 0; h < nh; ++h) {
             const int e = e0 + h;
             double part = 0.0;
-            const int t1 = __ldg(P.e_term_ptr + e + 1);
-            for (int t = __ldg(P.e_term_ptr + e) + tm.rank(); t < t1; t += tm.size())
-                part += lu[__ldg(P.e_term_l + t)] * lu[__ldg(P.e_term_u + t)];
+            const int t1 = CDN_LD(P.e_term_ptr + e + 1);
+            for (int t = CDN_LD(P.e_term_ptr + e) + tm.rank(); t < t1; t += tm.size())
+                part += lu[CDN_LD(P.e_term_l + t)] * lu[CDN_LD(P.e_term_u + t)];
             part = tm.sum(part);
             if (tm.rank() == 0) {
                 double v = lu[e] - part;
-                const int pv = __ldg(P.e_piv + e);
+                const int pv = CDN_LD(P.e_piv + e);
                 if (pv >= 0) v /= lu[pv];
                 lu[e] = v;
             }
         }
         for (int e = e0 + nh + tm.rank(); e < e1; e += tm.size()) {
             double v = lu[e];
-            const int t1 = __ldg(P.e_term_ptr + e + 1);
-            for (int t = __ldg(P.e_term_ptr + e); t < t1; ++t)
-                v -= lu[__ldg(P.e_term_l + t)] * lu[__ldg(P.e_term_u + t)];
-            const int pv = __ldg(P.e_piv + e);
+            const int t1 = CDN_LD(P.e_term_ptr + e + 1);
+            for (int t = CDN_LD(P.e_term_ptr + e); t < t1; ++t)
+                v -= lu[CDN_LD(P.e_term_l + t)] * lu[CDN_LD(P.e_term_u + t)];
+            const int pv = CDN_LD(P.e_piv + e);
             if (pv >= 0) v /= lu[pv];
             lu[e] = v;
         }
@@ -633,52 +675,52 @@ template <class Team>
 __device__ __forceinline__ void sparse_solve(Team& tm, const cdn_plan_dev& P, const double* lu,
                                              const double* y, double* tmp, double* dx) {
     for (int l = 0; l < P.nlev_l; ++l) {
-        const int r0 = __ldg(P.l_lvl_ptr + l), r1 = __ldg(P.l_lvl_ptr + l + 1);
-        const int nh = __ldg(P.l_lvl_nheavy + l);
+        const int r0 = CDN_LD(P.l_lvl_ptr + l), r1 = CDN_LD(P.l_lvl_ptr + l + 1);
+        const int nh = CDN_LD(P.l_lvl_nheavy + l);
         for (int h = 0; h < nh; ++h) {
-            const int i = __ldg(P.l_rows + r0 + h);
+            const int i = CDN_LD(P.l_rows + r0 + h);
             double part = 0.0;
-            const int k1 = __ldg(P.l_ptr + i + 1);
-            for (int k = __ldg(P.l_ptr + i) + tm.rank(); k < k1; k += tm.size())
-                part += lu[__ldg(P.l_slot + k)] * tmp[__ldg(P.l_col + k)];
+            const int k1 = CDN_LD(P.l_ptr + i + 1);
+            for (int k = CDN_LD(P.l_ptr + i) + tm.rank(); k < k1; k += tm.size())
+                part += lu[CDN_LD(P.l_slot + k)] * tmp[CDN_LD(P.l_col + k)];
             part = tm.sum(part);
-            if (tm.rank() == 0) tmp[i] = y[__ldg(P.rowmap + i)] - part;
+            if (tm.rank() == 0) tmp[i] = y[CDN_LD(P.rowmap + i)] - part;
         }
         for (int q = r0 + nh + tm.rank(); q < r1; q += tm.size()) {
-            const int i = __ldg(P.l_rows + q);
-            double v = y[__ldg(P.rowmap + i)];
-            const int k1 = __ldg(P.l_ptr + i + 1);
-            for (int k = __ldg(P.l_ptr + i); k < k1; ++k)
-                v -= lu[__ldg(P.l_slot + k)] * tmp[__ldg(P.l_col + k)];
+            const int i = CDN_LD(P.l_rows + q);
+            double v = y[CDN_LD(P.rowmap + i)];
+            const int k1 = CDN_LD(P.l_ptr + i + 1);
+            for (int k = CDN_LD(P.l_ptr + i); k < k1; ++k)
+                v -= lu[CDN_LD(P.l_slot + k)] * tmp[CDN_LD(P.l_col + k)];
             tmp[i] = v;
         }
         tm.sync();
     }
     for (int l = 0; l < P.nlev_u; ++l) {
-        const int r0 = __ldg(P.u_lvl_ptr + l), r1 = __ldg(P.u_lvl_ptr + l + 1);
-        const int nh = __ldg(P.u_lvl_nheavy + l);
+        const int r0 = CDN_LD(P.u_lvl_ptr + l), r1 = CDN_LD(P.u_lvl_ptr + l + 1);
+        const int nh = CDN_LD(P.u_lvl_nheavy + l);
         for (int h = 0; h < nh; ++h) {
-            const int i = __ldg(P.u_rows + r0 + h);
+            const int i = CDN_LD(P.u_rows + r0 + h);
             double part = 0.0;
-            const int k1 = __ldg(P.u_ptr + i + 1);
-            for (int k = __ldg(P.u_ptr + i) + tm.rank(); k < k1; k += tm.size())
-                part += lu[__ldg(P.u_slot + k)] * tmp[__ldg(P.u_col + k)];
+            const int k1 = CDN_LD(P.u_ptr + i + 1);
+            for (int k = CDN_LD(P.u_ptr + i) + tm.rank(); k < k1; k += tm.size())
+                part += lu[CDN_LD(P.u_slot + k)] * tmp[CDN_LD(P.u_col + k)];
             part = tm.sum(part);
             if (tm.rank() == 0) {
-                const double v = (tmp[i] - part) / lu[__ldg(P.u_diag + i)];
+                const double v = (tmp[i] - part) / lu[CDN_LD(P.u_diag + i)];
                 tmp[i] = v;
-                dx[__ldg(P.colmap + i)] = v;
+                dx[CDN_LD(P.colmap + i)] = v;
             }
         }
         for (int q = r0 + nh + tm.rank(); q < r1; q += tm.size()) {
-            const int i = __ldg(P.u_rows + q);
+            const int i = CDN_LD(P.u_rows + q);
             double v = tmp[i];
-            const int k1 = __ldg(P.u_ptr + i + 1);
-            for (int k = __ldg(P.u_ptr + i); k < k1; ++k)
-                v -= lu[__ldg(P.u_slot + k)] * tmp[__ldg(P.u_col + k)];
-            v /= lu[__ldg(P.u_diag + i)];
+            const int k1 = CDN_LD(P.u_ptr + i + 1);
+            for (int k = CDN_LD(P.u_ptr + i); k < k1; ++k)
+                v -= lu[CDN_LD(P.u_slot + k)] * tmp[CDN_LD(P.u_col + k)];
+            v /= lu[CDN_LD(P.u_diag + i)];
             tmp[i] = v;
-            dx[__ldg(P.colmap + i)] = v;
+            dx[CDN_LD(P.colmap + i)] = v;
         }
         tm.sync();
     }
@@ -742,10 +784,130 @@ __device__ __forceinline__ void dense_solve_serial(Team& tm, const double* a, co
     tm.sync();
 }
 
+// n <= 8 on a warp tile: the whole matrix lives in registers, lane j holding
+// column j; the pivot column is broadcast with shuffles, so the factorisation
+// has no barrier and no shared-memory round trip inside (same arithmetic and
+// pivot choice as above).  The factors are written back for the solves.
+template <int T>
+__device__ __forceinline__ void dense_factor_reg8(TileTeam<T>& tm, double* a, int* piv, int n) {
+    const int j = tm.rank();
+    double col[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) col[i] = (i < n && j < n) ? a[i * n + j] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k < n) {
+            double v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (i >= k) ? tm.tile.shfl(col[i], k) : 0.0;
+            double best = fabs(v[k]);
+            int bi = k;
+            if (!(best >= 0.0)) best = -1.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i > k && i < n) {
+                    const double t = fabs(v[i]);
+                    if (t > best) { best = t; bi = i; }
+                }
+            if (j == 0) piv[k] = bi;
+            // swap rows k and bi (own column and the broadcast pivot column)
+            const double ck = col[k], vk = v[k];
+            double cb = ck, vb = vk;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i > k && i == bi) { cb = col[i]; vb = v[i]; col[i] = ck; v[i] = vk; }
+            col[k] = cb;
+            const double pinv = 1.0 / vb;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i > k && i < n) {
+                    const double l = v[i] * pinv;
+                    if (j > k) col[i] -= l * cb;
+                    else if (j == k) col[i] = l;
+                }
+        }
+    }
+    if (j < n) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < n) a[i * n + j] = col[i];
+    }
+    tm.sync();
+}
+
+// b <- A^{-1} b with the factors of dense_factor_reg8: every lane carries the
+// whole right-hand side in registers, the L and U entries come from the lane
+// that owns their column.
+template <int T>
+__device__ __forceinline__ void dense_solve_reg8(TileTeam<T>& tm, const double* a, const int* piv,
+                                                 double* b, int n) {
+    const int j = tm.rank();
+    double col[8], x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        col[i] = (i < n && j < n) ? a[i * n + j] : 0.0;
+        x[i] = (i < n) ? b[i] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < n) {
+            const int p = piv[k];
+            if (p != k) {
+                const double t = x[k];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i > k && i == p) { x[k] = x[i]; x[i] = t; }
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)            // L y = P b (unit diagonal)
+        if (k + 1 < n) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i > k && i < n) x[i] -= tm.tile.shfl(col[i], k) * x[k];
+        }
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {       // U x = y
+        const int k = 7 - kk;
+        if (k < n) {
+            x[k] = x[k] / tm.tile.shfl(col[k], k);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < k) x[i] -= tm.tile.shfl(col[i], k) * x[k];
+        }
+    }
+    tm.sync();                              // everybody has read b
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i == j && i < n) b[i] = x[i];
+    tm.sync();
+}
+
+template <class Team>
+__device__ __forceinline__ void factor_small(Team& tm, double* a, int* piv, int n) {
+    dense_factor_cols(tm, a, piv, n);
+}
+template <int T>
+__device__ __forceinline__ void factor_small(TileTeam<T>& tm, double* a, int* piv, int n) {
+    if (T >= 8 && n <= 8) dense_factor_reg8(tm, a, piv, n);
+    else dense_factor_cols(tm, a, piv, n);
+}
+template <class Team>
+__device__ __forceinline__ void solve_small(Team& tm, const double* a, const int* piv, double* b,
+                                            int n) {
+    dense_solve_serial(tm, a, piv, b, n);
+}
+template <int T>
+__device__ __forceinline__ void solve_small(TileTeam<T>& tm, const double* a, const int* piv,
+                                            double* b, int n) {
+    if (T >= 8 && n <= 8) dense_solve_reg8(tm, a, piv, b, n);
+    else dense_solve_serial(tm, a, piv, b, n);
+}
+
 template <class Team>
 __device__ __forceinline__ void factor(Team& tm, const cdn_plan_dev& P, const Ws& w) {
     if (P.dense) {
-        if (Team::kFlat && P.n <= tm.size()) dense_factor_cols(tm, w.lu, w.piv, P.n);
+        if (Team::kFlat && P.n <= tm.size()) factor_small(tm, w.lu, w.piv, P.n);
         else dense_factor(tm, w.lu, w.piv, P.n);
     } else {
         sparse_factor(tm, P, w.lu);
@@ -756,7 +918,7 @@ __device__ __forceinline__ void factor(Team& tm, const cdn_plan_dev& P, const Ws
 template <class Team>
 __device__ __forceinline__ void lusolve(Team& tm, const cdn_plan_dev& P, const Ws& w) {
     if (P.dense) {
-        if (Team::kFlat && P.n <= 16) dense_solve_serial(tm, w.lu, w.piv, w.y, P.n);
+        if (Team::kFlat && P.n <= 16) solve_small(tm, w.lu, w.piv, w.y, P.n);
         else dense_solve(tm, w.lu, w.piv, w.y, P.n);
         for (int r = tm.rank(); r < P.n; r += tm.size()) w.dx[r] = w.y[r];
         tm.sync();
@@ -770,9 +932,21 @@ __device__ __forceinline__ void lusolve(Team& tm, const cdn_plan_dev& P, const W
 // On return w.ivec holds the residual evaluated at the LAST-BUT-ONE iterate and
 // w.lu the factors of the Jacobian there -- exactly what the reference's chord
 // predictor re-uses (tran.py:181) -- unless errfunc is set.
+// phase timers (instance 0, thread 0 of the team): where a Newton iteration goes
+#define CDN_PROF_T0 long long pt_ = prof ? clock64() : 0
+#define CDN_PROF(k)                                                     \
+    do {                                                                \
+        if (prof) {                                                     \
+            const long long t_ = clock64();                             \
+            if (tm.rank() == 0) prof[k] += t_ - pt_;                    \
+            pt_ = t_;                                                   \
+        }                                                               \
+    } while (0)
+
 template <int MS, class Team>
 __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, const Ws& w,
-                                      const cdn_opts& o, bool active, double* res_out, bool* ok) {
+                                      const cdn_opts& o, bool active, double* res_out, bool* ok,
+                                      long long* prof = nullptr) {
     double res = 0.0;
     bool success = false;
     int it = 0;
@@ -781,12 +955,17 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
     bool run = active;
     while (tm.cta_any(run && it < o.maxiter)) {
         if (!(run && it < o.maxiter)) continue;
+        CDN_PROF_T0;
         eval_devices<MS, true>(tm, P, b, w.x, w, true, o.h);
+        CDN_PROF(0);
         assemble(tm, P, w, o);
         residual(tm, P, w, o);
         tm.sync();
+        CDN_PROF(1);
         factor(tm, P, w);
+        CDN_PROF(2);
         lusolve(tm, P, w);
+        CDN_PROF(3);
         double m = 0.0;
         for (int r = tm.rank(); r < P.n; r += tm.size()) m = fmax(m, fabs(w.dx[r]));
         m = tm.max(m);
@@ -816,6 +995,7 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
         }
         ++it;
         if (n1 && n2) { success = true; run = false; }
+        CDN_PROF(4);
     }
     *res_out = res;
     *ok = success;
@@ -875,12 +1055,13 @@ __device__ __noinline__ int homotopy(Team& tm, const cdn_plan_dev& P, int b, con
 template <int MS, class Team>
 __device__ __forceinline__ int solve_helpers(Team& tm, const cdn_plan_dev& P, int b,
                                              const Ws& w, const cdn_opts& o, int helpers,
-                                             bool active, double* res_out, bool* ok) {
+                                             bool active, double* res_out, bool* ok,
+                                             long long* prof = nullptr) {
     if (helpers && active) {
         for (int r = tm.rank(); r < P.n; r += tm.size()) w.xb[r] = w.x[r];
         tm.sync();
     }
-    int it = newton<MS>(tm, P, b, w, o, active, res_out, ok);
+    int it = newton<MS>(tm, P, b, w, o, active, res_out, ok, prof);
     if (!helpers) return it;
     bool need = active && !*ok;
     if (!tm.cta_any(need)) return it;
@@ -962,7 +1143,8 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
             tm.sync();
         }
         double res; bool ok;
-        const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, active, &res, &ok);
+        const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, active, &res, &ok,
+                                         b == 0 ? A.prof : nullptr);
         if (active && tm.rank() == 0) {
             A.iters[b] = it; A.res[b] = res; A.status[b] = ok ? 0 : -1;
         }
@@ -978,20 +1160,24 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
         bool run = active;
         for (int i = A.first; i < A.nsamples; ++i) {
             if (!tm.cta_any(run)) break;
+            long long* prof = (b == 0) ? A.prof : nullptr;
             if (run) {
+                CDN_PROF_T0;
                 update_q<MS>(tm, P, b, w);       // accept(xOld)
                 integ_accept(tm, P, w, o);
                 hist_store(tm, P, w, false);
                 make_rhs(tm, P, w, o, A.src_dc, A.nsrc, A.src_rows,
                          A.src_val + (long)i * A.nsrc);
+                CDN_PROF(5);
                 if (i > 1) {                     // chord predictor (tran.py:181)
                     chord(tm, P, w, o);
                     for (int r = tm.rank(); r < n; r += tm.size()) w.x[r] += w.dx[r];
                     tm.sync();
                 }
+                CDN_PROF(6);
             }
             double res; bool ok;
-            const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, run, &res, &ok);
+            const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, run, &res, &ok, prof);
             if (!run) continue;
             const long at = (long)b * A.nsamples + i;
             if (tm.rank() == 0) { A.iters[at] = it; A.res[at] = res; }
@@ -1048,6 +1234,71 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
     }
 }
 
+// ---- shared-memory copy of a small (dense) plan ------------------------------------------
+__host__ __device__ inline long plan_smem_bytes(const cdn_plan_dev& P) {
+    long b = 0;
+    b += 3L * P.nlu * 8;                         // e_g, e_c, e_gones
+    b += (2L * P.nlu + 1L) * 4 + (long)P.ncon * 4;    // e_con_ptr, e_bal, e_con_pk
+    b += (P.n + 1L) * 4 * 2;                     // r_lin_ptr, r_con_ptr
+    b += (long)P.nrlin * (4 + 3 * 8);            // r_lin_col, r_lin_g/c/gones
+    b += (long)P.nrcon * 4;                      // r_con_pk
+    b += (long)P.ndev * 8;                       // dev_g, dev_i
+    for (int g = 0; g < P.ngroups; ++g) b += 2L * P.groups[g].nxin * P.groups[g].n * 4;
+    return b + 16 * 16;                          // alignment slack
+}
+
+template <class T>
+__device__ __forceinline__ const T* smem_copy(const T* src, long count, char*& cur) {
+    cur = (char*)(((unsigned long long)cur + 15ull) & ~15ull);
+    T* dst = (T*)cur;
+    for (long k = threadIdx.x; k < count; k += blockDim.x) dst[k] = src[k];
+    cur += count * (long)sizeof(T);
+    return dst;
+}
+
+// all threads of the CTA; ends with a CTA barrier
+__device__ __forceinline__ void plan_to_smem(const cdn_plan_dev& G, cdn_plan_dev& S, char* buf) {
+    {   // the struct itself
+        const int* s = (const int*)&G;
+        int* d = (int*)&S;
+        for (int k = threadIdx.x; k < (int)(sizeof(cdn_plan_dev) / 4); k += blockDim.x) d[k] = s[k];
+    }
+    __syncthreads();
+    char* cur = buf;
+    const double* e_g = smem_copy(G.e_g, G.nlu, cur);
+    const double* e_c = smem_copy(G.e_c, G.nlu, cur);
+    const double* e_gones = smem_copy(G.e_gones, G.nlu, cur);
+    const double* r_lin_g = smem_copy(G.r_lin_g, G.nrlin, cur);
+    const double* r_lin_c = smem_copy(G.r_lin_c, G.nrlin, cur);
+    const double* r_lin_gones = smem_copy(G.r_lin_gones, G.nrlin, cur);
+    const int* e_con_ptr = smem_copy(G.e_con_ptr, G.nlu + 1L, cur);
+    const unsigned* e_con_pk = smem_copy(G.e_con_pk, G.ncon, cur);
+    const int* r_lin_ptr = smem_copy(G.r_lin_ptr, G.n + 1L, cur);
+    const int* r_lin_col = smem_copy(G.r_lin_col, G.nrlin, cur);
+    const int* r_con_ptr = smem_copy(G.r_con_ptr, G.n + 1L, cur);
+    const unsigned* r_con_pk = smem_copy(G.r_con_pk, G.nrcon, cur);
+    const int* e_bal = smem_copy(G.e_bal, G.nlu, cur);
+    const int* dev_g = smem_copy(G.dev_g, G.ndev, cur);
+    const int* dev_i = smem_copy(G.dev_i, G.ndev, cur);
+    const int* vp[CDN_MAX_GROUPS];
+    const int* vn[CDN_MAX_GROUPS];
+    for (int g = 0; g < G.ngroups; ++g) {
+        const long cnt = (long)G.groups[g].nxin * G.groups[g].n;
+        vp[g] = smem_copy(G.groups[g].vpos, cnt, cur);
+        vn[g] = smem_copy(G.groups[g].vneg, cnt, cur);
+    }
+    if (threadIdx.x == 0) {
+        S.e_g = e_g; S.e_c = e_c; S.e_gones = e_gones;
+        S.r_lin_g = r_lin_g; S.r_lin_c = r_lin_c; S.r_lin_gones = r_lin_gones;
+        S.e_con_ptr = e_con_ptr; S.e_con_pk = e_con_pk;
+        S.r_lin_ptr = r_lin_ptr; S.r_lin_col = r_lin_col;
+        S.r_con_ptr = r_con_ptr; S.r_con_pk = r_con_pk; S.e_bal = e_bal;
+        S.dev_g = dev_g; S.dev_i = dev_i;
+        for (int g = 0; g < G.ngroups; ++g) { S.groups[g].vpos = vp[g]; S.groups[g].vneg = vn[g]; }
+    }
+    __syncthreads();
+}
+
 // ---- kernels --------------------------------------------------------------------------------
 // Batches of small circuits: T lanes per instance; the state lives in shared
 // memory unless the caller wants it kept (A.ws != NULL).
@@ -1055,10 +1306,20 @@ template <int MS, int T>
 __global__ void __launch_bounds__(256)
 engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
     extern __shared__ double smem[];
-    const cdn_plan_dev& P = *A.plan;
     TileTeam<T> tm;
     const int tiles = blockDim.x / T;
     const int tile_id = threadIdx.x / T;
+    // The gather lists of a dense plan are a few KB and are read by every
+    // instance in every Newton iteration: keep a copy in shared memory (the
+    // per-instance device records streaming through L1 evict the global copy).
+    __shared__ cdn_plan_dev Ps;
+    const bool shadow = A.plan_smem > 0;
+    if (shadow) {
+        const long per0 = ws_doubles(A.plan->n, A.plan->nlu, A.plan->dev_out_size,
+                                     A.plan->dev_jac_size, A.plan->hist_size);
+        plan_to_smem(*A.plan, Ps, (char*)(smem + (long)tiles * per0));
+    }
+    const cdn_plan_dev& P = shadow ? Ps : *A.plan;
     const long per = ws_doubles(P.n, P.nlu, P.dev_out_size, P.dev_jac_size, P.hist_size);
     // the loop bounds are CTA-uniform: padding tiles run along inactive
     for (int b0 = blockIdx.x * tiles; b0 < A.B; b0 += gridDim.x * tiles) {

@@ -39,6 +39,7 @@ struct cdn_plan_dev {
     int dense;                // 1: slots are a dense n*n row-major matrix
     int ndev;                 // nonlinear devices of one circuit instance
     int max_terms;
+    int ncon, nrcon, nrlin;   // lengths of e_con_*, r_con_*, r_lin_*
     int heavy;                // list length above which the team reduces together
     int nhist;                // history samples per delayed port (0: no delays)
     long hist_size;           // doubles of port-voltage history per circuit instance
@@ -64,6 +65,8 @@ struct cdn_plan_dev {
     const signed char* e_con_kind;  // +-1 current row, +-2 charge row (x a0)
     const unsigned* e_con_pk;  // src | minus << 29 | charge << 30 (what the kernels read)
     const unsigned* r_con_pk;
+    const int* e_bal;         // [nlu] dense plans: slots by decreasing gather length, so
+                              // that a strided walk gives every lane the same work
     // ---- triangular solves (permuted index space) --------------------------
     const int* l_lvl_ptr;     // [nlev_l+1]
     const int* l_rows;        // [n] rows ordered by level

@@ -154,7 +154,7 @@ struct cdn_plan {
             e_con_src, e_con_kind, l_lvl_ptr, l_rows, l_ptr, l_col, l_slot, u_lvl_ptr, u_rows,
             u_ptr, u_col, u_slot, u_diag, rowmap, colmap, r_lin_ptr, r_lin_col, r_lin_g,
             r_lin_c, r_lin_gones, r_con_ptr, r_con_src, r_con_kind, dev_g, dev_i, e_con_pk,
-            r_con_pk;
+            r_con_pk, e_bal;
         long gv[CDN_MAX_GROUPS][2];
         long gd[CDN_MAX_GROUPS];
     } off;
@@ -640,6 +640,13 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     PUT(r_con_src);
     PUT(r_con_kind);
     PUT(e_con_pk); PUT(r_con_pk);
+    ivec e_bal(nlu);
+    for (long e = 0; e < nlu; ++e) e_bal[e] = (int)e;
+    if (dense)
+        std::stable_sort(e_bal.begin(), e_bal.end(), [&](int a, int b) {
+            return (e_con_ptr[a + 1] - e_con_ptr[a]) > (e_con_ptr[b + 1] - e_con_ptr[b]);
+        });
+    PUT(e_bal);
     {
         ivec dg, di;
         for (int g = 0; g < c->ngroups; ++g)
@@ -655,6 +662,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     D.heavy = HEAVY;
     D.n_e_heavy = (int)e_heavy.size(); D.n_r_heavy = (int)r_heavy.size();
     D.max_terms = P->max_terms;
+    D.ncon = (int)e_con_pk.size(); D.nrcon = (int)r_con_pk.size(); D.nrlin = (int)r_lin_col.size();
     D.n = n; D.nlu = (int)nlu; D.nlev_f = nlev_f; D.nlev_l = nlev_l; D.nlev_u = nlev_u;
     D.ngroups = c->ngroups;
     D.dev_out_size = out_size; D.dev_jac_size = jac_size;
@@ -723,7 +731,7 @@ extern "C" int cdn_plan_bind(cdn_plan* P, void* dev_ws, long bytes, void* stream
     BIND(r_lin_gones, double); BIND(r_con_ptr, int); BIND(r_con_src, int);
     BIND(r_con_kind, signed char);
     BIND(dev_g, int); BIND(dev_i, int);
-    BIND(e_con_pk, unsigned); BIND(r_con_pk, unsigned);
+    BIND(e_con_pk, unsigned); BIND(r_con_pk, unsigned); BIND(e_bal, int);
 #undef BIND
     for (int g = 0; g < D.ngroups; ++g) {
         D.groups[g].vpos = (const int*)(base + O.gv[g][0]);
