@@ -76,10 +76,11 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
         int T = r->T;
         if (T <= 0) {
             const int want = D->ndev > D->n ? D->ndev : D->n;
-            T = 4;
+            T = 8;
             while (T < want && T < 32) T *= 2;
         }
-        c.T = T;
+        c.T = (T <= 8) ? 8 : (T <= 16) ? 16 : 32;
+        T = c.T;
         // one CTA of 8 warps per SM when the batch fills the GPU: its tiles run
         // in lockstep and share the instruction cache
         c.tpb = ((long)A.B * T >= (long)ctx->sm_count * 128) ? 256 : 128;
@@ -115,10 +116,20 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     }
 
     cdn_plan_note_team(P, c.team);
-    cudaError_t e;
-    if ((ms & ~(unsigned)CDN_MS_DIODE) == 0) e = cdn_launch_ms_diode(A, c, st);
-    else if ((ms & ~(unsigned)CDN_MS_BSIM3) == 0) e = cdn_launch_ms_bsim3(A, c, st);
-    else e = cdn_launch_ms_all(A, c, st);
+    static const cdn_launch_fn table[CDN_NSET][CDN_NKIND] = {
+        {cdn_launch_diode_tile8, cdn_launch_diode_tile16, cdn_launch_diode_tile32,
+         cdn_launch_diode_block, cdn_launch_diode_grid},
+        {cdn_launch_bsim3_tile8, cdn_launch_bsim3_tile16, cdn_launch_bsim3_tile32,
+         cdn_launch_bsim3_block, cdn_launch_bsim3_grid},
+        {cdn_launch_all_tile8, cdn_launch_all_tile16, cdn_launch_all_tile32, cdn_launch_all_block,
+         cdn_launch_all_grid}};
+    const int set = ((ms & ~(unsigned)CDN_MS_DIODE) == 0) ? CDN_SET_DIODE
+                    : ((ms & ~(unsigned)CDN_MS_BSIM3) == 0) ? CDN_SET_BSIM3 : CDN_SET_ALL;
+    int kind = CDN_KIND_GRID;
+    if (c.team == CDN_TEAM_BLOCK) kind = CDN_KIND_BLOCK;
+    else if (c.team == CDN_TEAM_TILE)
+        kind = (c.T <= 8) ? CDN_KIND_TILE8 : (c.T <= 16) ? CDN_KIND_TILE16 : CDN_KIND_TILE32;
+    const cudaError_t e = table[set][kind](A, c, st);
     if (e != cudaSuccess)
         return cdn_fail(ctx, CDN_ERR_CUDA, std::string("engine launch: ") + cudaGetErrorString(e));
     return CDN_OK;

@@ -27,6 +27,12 @@ static cudaError_t set_smem(K kernel, long smem) {
     return cudaSuccess;
 }
 
+// One translation unit per (model set, kernel kind): the big kernels compile in
+// parallel and a light circuit never pays for the heavy models.
+enum { CDN_KIND_TILE8 = 0, CDN_KIND_TILE16, CDN_KIND_TILE32, CDN_KIND_BLOCK, CDN_KIND_GRID,
+       CDN_NKIND };
+enum { CDN_SET_DIODE = 0, CDN_SET_BSIM3, CDN_SET_ALL, CDN_NSET };
+
 template <int MS, int T>
 static cudaError_t launch_tile(const cdn_engine_args& A, const cdn_launch_cfg& c, cudaStream_t st) {
     cudaError_t e = set_smem(engine_tile_kernel<MS, T>, c.smem);
@@ -35,32 +41,25 @@ static cudaError_t launch_tile(const cdn_engine_args& A, const cdn_launch_cfg& c
     return cudaGetLastError();
 }
 
-template <int MS>
-static cudaError_t launch_engine(const cdn_engine_args& A, cdn_launch_cfg c, cudaStream_t st) {
-    switch (c.team) {
-    case CDN_TEAM_TILE:
-        switch (c.T) {
-        case 4: return launch_tile<MS, 4>(A, c, st);
-        case 8: return launch_tile<MS, 8>(A, c, st);
-        case 16: return launch_tile<MS, 16>(A, c, st);
-        case 32: return launch_tile<MS, 32>(A, c, st);
-        default: return cudaErrorInvalidValue;
-        }
-    case CDN_TEAM_BLOCK: {
+template <int MS, int KIND>
+static cudaError_t launch_kind(const cdn_engine_args& A, const cdn_launch_cfg& c, cudaStream_t st) {
+    // (if constexpr: a translation unit instantiates exactly one kernel)
+    if constexpr (KIND == CDN_KIND_TILE8) {
+        return launch_tile<MS, 8>(A, c, st);
+    } else if constexpr (KIND == CDN_KIND_TILE16) {
+        return launch_tile<MS, 16>(A, c, st);
+    } else if constexpr (KIND == CDN_KIND_TILE32) {
+        return launch_tile<MS, 32>(A, c, st);
+    } else if constexpr (KIND == CDN_KIND_BLOCK) {
         // light model sets run 1024 threads per CTA (64 registers each); the
         // heavy models need their 255 registers
-        if (MS == CDN_MS_DIODE && c.tpb == 1024) {
-            cudaError_t e = set_smem(engine_block_kernel<MS, (MS == CDN_MS_DIODE ? 1024 : 256)>, c.smem);
-            if (e != cudaSuccess) return e;
-            engine_block_kernel<MS, (MS == CDN_MS_DIODE ? 1024 : 256)><<<c.blocks, 1024, c.smem, st>>>(A);
-            return cudaGetLastError();
-        }
-        cudaError_t e = set_smem(engine_block_kernel<MS, 256>, c.smem);
+        constexpr int TPB = (MS == CDN_MS_DIODE) ? 1024 : 256;
+        cudaError_t e = set_smem(engine_block_kernel<MS, TPB>, c.smem);
         if (e != cudaSuccess) return e;
-        engine_block_kernel<MS, 256><<<c.blocks, 256, c.smem, st>>>(A);
+        engine_block_kernel<MS, TPB><<<c.blocks, TPB, c.smem, st>>>(A);
         return cudaGetLastError();
-    }
-    case CDN_TEAM_GRID: {
+    } else {
+        // cooperative grid
         int per_sm = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
             &per_sm, engine_grid_kernel<MS, 256>, 256, 0);
@@ -72,10 +71,27 @@ static cudaError_t launch_engine(const cdn_engine_args& A, cdn_launch_cfg c, cud
         return cudaLaunchCooperativeKernel((void*)engine_grid_kernel<MS, 256>, dim3(blocks),
                                            dim3(256), args, 0, st);
     }
-    default: return cudaErrorInvalidValue;
-    }
 }
 
-cudaError_t cdn_launch_ms_diode(const cdn_engine_args& A, const cdn_launch_cfg& c, cudaStream_t st);
-cudaError_t cdn_launch_ms_bsim3(const cdn_engine_args& A, const cdn_launch_cfg& c, cudaStream_t st);
-cudaError_t cdn_launch_ms_all(const cdn_engine_args& A, const cdn_launch_cfg& c, cudaStream_t st);
+typedef cudaError_t (*cdn_launch_fn)(const cdn_engine_args&, const cdn_launch_cfg&, cudaStream_t);
+#define CDN_DEFINE_LAUNCH(name, MS, KIND)                                                    \
+    cudaError_t name(const cdn_engine_args& A, const cdn_launch_cfg& c, cudaStream_t st) {   \
+        return launch_kind<MS, KIND>(A, c, st);                                              \
+    }
+#define CDN_DECLARE_LAUNCH(name) \
+    cudaError_t name(const cdn_engine_args& A, const cdn_launch_cfg& c, cudaStream_t st);
+CDN_DECLARE_LAUNCH(cdn_launch_diode_tile8)
+CDN_DECLARE_LAUNCH(cdn_launch_diode_tile16)
+CDN_DECLARE_LAUNCH(cdn_launch_diode_tile32)
+CDN_DECLARE_LAUNCH(cdn_launch_diode_block)
+CDN_DECLARE_LAUNCH(cdn_launch_diode_grid)
+CDN_DECLARE_LAUNCH(cdn_launch_bsim3_tile8)
+CDN_DECLARE_LAUNCH(cdn_launch_bsim3_tile16)
+CDN_DECLARE_LAUNCH(cdn_launch_bsim3_tile32)
+CDN_DECLARE_LAUNCH(cdn_launch_bsim3_block)
+CDN_DECLARE_LAUNCH(cdn_launch_bsim3_grid)
+CDN_DECLARE_LAUNCH(cdn_launch_all_tile8)
+CDN_DECLARE_LAUNCH(cdn_launch_all_tile16)
+CDN_DECLARE_LAUNCH(cdn_launch_all_tile32)
+CDN_DECLARE_LAUNCH(cdn_launch_all_block)
+CDN_DECLARE_LAUNCH(cdn_launch_all_grid)
