@@ -294,3 +294,78 @@ def test_dc_sweep_device_parameter(lib):
     err = np.abs(got - ref['X'])
     assert np.all(err < 1e-9 * np.abs(ref['X']) + 1e-12), err.max()
     assert np.max(np.abs(an.iterations - ref['iters'])) <= 1
+
+
+def test_no_convergence_is_raised(lib, capsys):
+    """Failure is reported the reference's way: the helpers raise
+    NoConvergenceError (fsolve.py:42-54), the kernels only return a status."""
+    from cardoon_b200.analyses.fsolve import NoConvergenceError
+    ckt, _ = S.load_circuit(S.net('bias_npn.net'))
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    old = glVar.maxiter
+    glVar.maxiter = 3
+    try:
+        with pytest.raises(NoConvergenceError):
+            dc.solve_simple(dc.get_guess(), dc.get_source())
+        # the device-side helper chain reports it as a status
+        x, res, it, ok = dc.engine.newton(dc.get_guess(), dc.get_source())
+        assert not ok[0] and it[0] == 3
+    finally:
+        glVar.maxiter = old
+    x, res, it = solve(dc.get_guess(), dc.get_source(),
+                       dc.convergence_helpers)
+    assert abs(it - 17) <= 1
+
+
+def test_homotopy_helpers_on_device(lib):
+    """gmin and source stepping (nodal.py:491-604) run inside one launch and
+    reach the same operating point as the host-driven helper chain."""
+    ckt, _ = S.load_circuit(S.net('bias_npn.net'))
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    old = glVar.maxiter
+    glVar.maxiter = 8          # plain Newton needs 17: force the helpers
+    try:
+        x0, sV = dc.get_guess(), dc.get_source()
+        xh, resh, ith = dc.solve_homotopy_gmin2(x0.copy(), sV)
+        e = dc.engine
+        r = e._run_struct(nd.L.OP_NEWTON, helpers=1)
+        e.x.copy_(e.lib.torch.as_tensor(x0[None, :]))
+        e.sv.copy_(e.lib.torch.as_tensor(sV))
+        e._launch(r)
+        assert int(e.status[0].item()) == 0
+        xd = e.x[0].cpu().numpy()
+        assert np.allclose(xd, xh, rtol=1e-6, atol=1e-9)
+        assert int(e.iters[0].item()) == ith
+        idx = R.prepare(ckt)
+        rdc = R.RefDC(ckt, idx, R.Options(glVar))
+        xr, resr, itr = rdc.solve_homotopy_gmin2(rdc.get_guess(),
+                                                 rdc.get_source())
+        assert abs(ith - itr) <= 2
+        assert np.allclose(xh, xr, rtol=1e-6, atol=1e-9)
+    finally:
+        glVar.maxiter = old
+
+
+def test_sparse_nd_interface_soliton(lib):
+    """get_i_Jac / factor_and_solve of the sparse engine against the
+    oracle's assembled matrix and SuperLU solve (N = 3022)."""
+    ckt, queue = S.load_circuit(S.net('soliton.net'))
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    assert not dc.engine.dense
+    x = np.random.default_rng(11).uniform(-0.5, 0.3, ckt.nD_dimension)
+    iVec, Jac = dc.get_i_Jac(x)
+    idx = R.prepare(ckt)
+    rdc = R.RefDC(ckt, idx, R.Options(glVar))
+    iv_r, J_r = rdc.get_i_Jac(x)
+    J_r = J_r.tocsc()
+    assert np.allclose(iVec, iv_r, rtol=1e-9, atol=1e-14)
+    d = abs(Jac.tocsc() - J_r)
+    assert d.max() < 1e-9 * abs(J_r).max()
+    rhs = dc.get_source() - iVec
+    dx = dc.factor_and_solve(rhs, Jac)
+    import scipy.sparse.linalg as spla
+    ref = spla.splu(J_r).solve(rhs)
+    assert np.allclose(dx, ref, rtol=1e-6, atol=1e-9 * np.abs(ref).max())
