@@ -33,9 +33,6 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     const cdn_plan_dev* D = cdn_plan_host_view(P);
     if (!D) return cdn_fail(ctx, CDN_ERR_STATE, "engine: plan is not bound");
     cudaStream_t st = (cudaStream_t)stream;
-    const cdn_plan_dev* dplan = nullptr;
-    int rc = cdn_plan_sync_device(P, st, &dplan);
-    if (rc != CDN_OK) return rc;
 
     // model set
     unsigned ms = 0;
@@ -47,7 +44,8 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
 
     cdn_engine_args A;
     memset(&A, 0, sizeof(A));
-    A.plan = dplan;
+    A.plan = *D;
+    static_assert(sizeof(cdn_engine_args) <= 4000, "kernel parameter space");
     A.o.abstol = r->abstol; A.o.reltol = r->reltol; A.o.maxdelta = r->maxdelta;
     A.o.a0 = r->a0; A.o.gmin = r->gmin; A.o.lambda = r->lambda; A.o.h = r->h;
     A.o.maxiter = r->maxiter; A.o.errfunc = r->errfunc; A.o.use_q = r->use_q; A.o.im = r->im;
@@ -104,8 +102,13 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
         c.blocks = A.B;
         c.tpb = ((ms & ~(unsigned)CDN_MS_DIODE) == 0 && D->n >= 1024) ? 1024 : 256;
         // LU values + two work vectors in shared memory when they fit
-        const long need = ((long)D->nlu + 2L * D->n) * 8;
-        if (!D->dense && need <= 220 * 1024) { c.smem = need; A.smem_lu = 1; }
+        const long need = ((long)D->nlu + D->n) * 8;
+        if (!D->dense && need <= 220 * 1024) {
+            c.smem = need;
+            A.smem_lu = 1;
+            const long st = compact_stage_bytes(*D);
+            if (D->compact && need + st <= 226 * 1024) { c.smem = need + st; A.smem_lu = 2; }
+        }
     } else if (c.team == CDN_TEAM_GRID) {
         if (!A.ws || !A.red) return cdn_fail(ctx, CDN_ERR_ARG, "engine: grid team needs workspace and reduction scratch");
         if (A.B != 1) return cdn_fail(ctx, CDN_ERR_ARG, "engine: grid team runs one circuit");

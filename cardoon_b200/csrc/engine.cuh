@@ -45,7 +45,9 @@ struct cdn_opts {
 };
 
 struct cdn_engine_args {
-    const cdn_plan_dev* plan;   // device copy
+    cdn_plan_dev plan;          // by value: kernel parameters live in the constant bank, so
+                                // the plan's scalars and array pointers are uniform loads that
+                                // never have to be re-read after a barrier
     cdn_opts o;
     int op;
     int B;                      // circuit instances in the batch
@@ -56,7 +58,8 @@ struct cdn_engine_args {
     // transient
     int nsamples, first, init_ic, nsrc, nsave;
     int helpers;                // 1: fall back to gmin / source stepping in-kernel
-    int smem_lu;                // block team: LU values + solve vectors in shared memory
+    int smem_lu;                // block team: 1 = LU values + solve work vector in shared
+                                // memory, 2 = also a staging area for compact programs
     const int* src_rows;        // [nsrc] rows with a time-dependent source
     const double* src_val;      // [nsamples][nsrc] summed source value per row
     const double* src_dc;       // [n] constant part of the source vector
@@ -79,6 +82,7 @@ struct cdn_engine_args {
 struct Ws {
     double *x, *dx, *ivec, *sv, *q, *qprev, *dq, *y, *tmp, *xb, *lu, *out, *jac, *hist;
     int* piv;       // [n] pivot rows (dense LU); piv[n + 1] = head of the history rings
+    unsigned* stage;   // block team: shared-memory staging area for compact solve programs
 };
 
 __host__ __device__ inline long ws_doubles(int n, long nlu, long out_size, long jac_size,
@@ -94,6 +98,7 @@ __device__ inline Ws ws_carve(double* base, int n, long nlu, long out_size, long
     w.out = w.lu + nlu; w.jac = w.out + out_size;
     w.hist = w.jac + jac_size;
     w.piv = (int*)(w.hist + hist_size);
+    w.stage = nullptr;
     return w;
 }
 
@@ -914,6 +919,91 @@ __device__ __forceinline__ void factor(Team& tm, const cdn_plan_dev& P, const Ws
     }
 }
 
+// Triangular solves from shared memory (block team, compact plans): the LU
+// values and the work vector are resident; the 16-bit program of each sweep
+// (row records, column and slot streams, level pointers) is staged next to
+// them, so that between two barriers a thread touches shared memory only.
+__host__ __device__ inline long compact_stage_bytes(const cdn_plan_dev& P) {
+    const long nnz = P.nnzl > P.nnzu ? P.nnzl : P.nnzu;
+    const int nlev = P.nlev_l > P.nlev_u ? P.nlev_l : P.nlev_u;
+    return 8L * P.n + 4L * ((nnz + 1) / 2) * 2 + 4L * (nlev + 2) + 64;
+}
+
+__device__ __forceinline__ void stage_words(unsigned* dst, const unsigned* src, long nwords) {
+    for (long k = threadIdx.x; k < nwords; k += blockDim.x) dst[k] = src[k];
+}
+
+__device__ __forceinline__ void staged_solve(BlockTeam& tm, const cdn_plan_dev& P, const Ws& w) {
+    const int n = P.n;
+    double* lu = w.lu;
+    double* tmp = w.tmp;
+    unsigned* rec = w.stage;                               // [2n]
+    // ---- L sweep -------------------------------------------------------------------
+    {
+        const long wc = (P.nnzl + 1) / 2;                  // 16-bit streams as words
+        unsigned* colw = rec + 2L * n;
+        unsigned* slotw = colw + wc;
+        int* lvl = (int*)(slotw + wc);
+        stage_words(rec, P.cl_rec, 2L * n);
+        stage_words(colw, (const unsigned*)P.cl_col, wc);
+        stage_words(slotw, (const unsigned*)P.cl_slot, wc);
+        for (int k = threadIdx.x; k <= P.nlev_l; k += blockDim.x) lvl[k] = P.l_lvl_ptr[k];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) tmp[i] = w.y[P.rowmap[i]];
+        __syncthreads();
+        const unsigned short* col = (const unsigned short*)colw;
+        const unsigned short* slot = (const unsigned short*)slotw;
+        for (int l = 0; l < P.nlev_l; ++l) {
+            const int r1 = lvl[l + 1];
+            for (int q = lvl[l] + threadIdx.x; q < r1; q += blockDim.x) {
+                const unsigned w0 = rec[2 * q], k0 = rec[2 * q + 1];
+                const int i = w0 & 0xffffu, cnt = w0 >> 16;
+                double v = tmp[i];
+                for (int k = 0; k < cnt; ++k) v -= lu[slot[k0 + k]] * tmp[col[k0 + k]];
+                tmp[i] = v;
+            }
+            __syncthreads();
+        }
+    }
+    // ---- U sweep -------------------------------------------------------------------
+    {
+        const long wc = (P.nnzu + 1) / 2;
+        unsigned* colw = rec + 2L * n;
+        unsigned* slotw = colw + wc;
+        int* lvl = (int*)(slotw + wc);
+        stage_words(rec, P.cu_rec, 2L * n);
+        stage_words(colw, (const unsigned*)P.cu_col, wc);
+        stage_words(slotw, (const unsigned*)P.cu_slot, wc);
+        for (int k = threadIdx.x; k <= P.nlev_u; k += blockDim.x) lvl[k] = P.u_lvl_ptr[k];
+        __syncthreads();
+        const unsigned short* col = (const unsigned short*)colw;
+        const unsigned short* slot = (const unsigned short*)slotw;
+        for (int l = 0; l < P.nlev_u; ++l) {
+            const int r1 = lvl[l + 1];
+            for (int q = lvl[l] + threadIdx.x; q < r1; q += blockDim.x) {
+                const unsigned w0 = rec[2 * q], w1 = rec[2 * q + 1];
+                const int i = w0 & 0xffffu, cnt = w0 >> 16;
+                const int k0 = w1 & 0xffffu, dg = w1 >> 16;
+                double v = tmp[i];
+                for (int k = 0; k < cnt; ++k) v -= lu[slot[k0 + k]] * tmp[col[k0 + k]];
+                tmp[i] = v / lu[dg];
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) w.dx[P.colmap[i]] = tmp[i];
+        __syncthreads();
+    }
+}
+
+template <class Team>
+__device__ __forceinline__ bool try_staged_solve(Team&, const cdn_plan_dev&, const Ws&) {
+    return false;
+}
+__device__ __forceinline__ bool try_staged_solve(BlockTeam& tm, const cdn_plan_dev& P, const Ws& w) {
+    if (!w.stage || !P.compact) return false;
+    staged_solve(tm, P, w);
+    return true;
+}
+
 // dx <- J^{-1} y  (y is consumed)
 template <class Team>
 __device__ __forceinline__ void lusolve(Team& tm, const cdn_plan_dev& P, const Ws& w) {
@@ -922,7 +1012,7 @@ __device__ __forceinline__ void lusolve(Team& tm, const cdn_plan_dev& P, const W
         else dense_solve(tm, w.lu, w.piv, w.y, P.n);
         for (int r = tm.rank(); r < P.n; r += tm.size()) w.dx[r] = w.y[r];
         tm.sync();
-    } else {
+    } else if (!try_staged_solve(tm, P, w)) {
         sparse_solve(tm, P, w.lu, w.y, w.tmp, w.dx);
     }
 }
@@ -1315,11 +1405,11 @@ engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
     __shared__ cdn_plan_dev Ps;
     const bool shadow = A.plan_smem > 0;
     if (shadow) {
-        const long per0 = ws_doubles(A.plan->n, A.plan->nlu, A.plan->dev_out_size,
-                                     A.plan->dev_jac_size, A.plan->hist_size);
-        plan_to_smem(*A.plan, Ps, (char*)(smem + (long)tiles * per0));
+        const long per0 = ws_doubles(A.plan.n, A.plan.nlu, A.plan.dev_out_size,
+                                     A.plan.dev_jac_size, A.plan.hist_size);
+        plan_to_smem(A.plan, Ps, (char*)(smem + (long)tiles * per0));
     }
-    const cdn_plan_dev& P = shadow ? Ps : *A.plan;
+    const cdn_plan_dev& P = shadow ? Ps : A.plan;
     const long per = ws_doubles(P.n, P.nlu, P.dev_out_size, P.dev_jac_size, P.hist_size);
     // the loop bounds are CTA-uniform: padding tiles run along inactive
     for (int b0 = blockIdx.x * tiles; b0 < A.B; b0 += gridDim.x * tiles) {
@@ -1352,18 +1442,17 @@ engine_block_kernel(const __grid_constant__ cdn_engine_args A) {
     extern __shared__ double dsm[];
     __shared__ double sred[64];
     __shared__ int ired[64];
-    const cdn_plan_dev& P = *A.plan;
+    const cdn_plan_dev& P = A.plan;
     BlockTeam tm;
     tm.sred = sred; tm.ired = ired;
     for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
         Ws w = ws_carve(A.ws + (long)b * A.ws_stride, P.n, P.nlu, P.dev_out_size,
                         P.dev_jac_size, P.hist_size);
         double* const g_lu = w.lu;
-        double* const g_y = w.y;
         if (A.smem_lu) {
-            w.lu = dsm; w.tmp = dsm + P.nlu; w.y = w.tmp + P.n;
+            w.lu = dsm; w.tmp = dsm + P.nlu;
+            if (A.smem_lu > 1) w.stage = (unsigned*)(w.tmp + P.n);
             for (int e = tm.rank(); e < P.nlu; e += tm.size()) w.lu[e] = g_lu[e];
-            for (int r = tm.rank(); r < P.n; r += tm.size()) w.y[r] = g_y[r];
         }
         if (A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN) {
             for (int r = tm.rank(); r < P.n; r += tm.size()) w.x[r] = A.x[(long)b * P.n + r];
@@ -1372,10 +1461,8 @@ engine_block_kernel(const __grid_constant__ cdn_engine_args A) {
         run_instance<MS>(tm, A, P, b, w, true);
         tm.sync();
         for (int r = tm.rank(); r < P.n; r += tm.size()) A.x[(long)b * P.n + r] = w.x[r];
-        if (A.smem_lu) {
+        if (A.smem_lu)
             for (int e = tm.rank(); e < P.nlu; e += tm.size()) g_lu[e] = w.lu[e];
-            for (int r = tm.rank(); r < P.n; r += tm.size()) g_y[r] = w.y[r];
-        }
         tm.sync();
     }
 }
@@ -1385,7 +1472,7 @@ template <int MS, int TPB>
 __global__ void __launch_bounds__(TPB)
 engine_grid_kernel(const __grid_constant__ cdn_engine_args A) {
     __shared__ double sred[64];
-    const cdn_plan_dev& P = *A.plan;
+    const cdn_plan_dev& P = A.plan;
     GridTeam tm;
     tm.sred = sred; tm.gred = A.red;
     const Ws w = ws_carve(A.ws, P.n, P.nlu, P.dev_out_size, P.dev_jac_size, P.hist_size);

@@ -8,7 +8,7 @@
 // create_additional_indexes (analyses/nodal.py:113-282, nodalSP.py:111-164).
 #pragma once
 
-#define CDN_MAX_GROUPS 24
+#define CDN_MAX_GROUPS 16
 // gather / term lists longer than this are summed cooperatively by the team
 #define CDN_HEAVY 256
 
@@ -65,6 +65,17 @@ struct cdn_plan_dev {
     const signed char* e_con_kind;  // +-1 current row, +-2 charge row (x a0)
     const unsigned* e_con_pk;  // src | minus << 29 | charge << 30 (what the kernels read)
     const unsigned* r_con_pk;
+    // compact triangular-solve programs (n, nlu < 65536, no hub rows): per
+    // level-ordered row two words {row | count << 16, first entry | diag slot
+    // << 16} and 16-bit column / slot streams; small enough to be staged in
+    // shared memory next to the LU values (block team)
+    int compact, nnzl, nnzu;
+    const unsigned* cl_rec;   // [2n]
+    const unsigned short* cl_col;   // [nnzl]
+    const unsigned short* cl_slot;  // [nnzl]
+    const unsigned* cu_rec;   // [2n]
+    const unsigned short* cu_col;   // [nnzu]
+    const unsigned short* cu_slot;  // [nnzu]
     const int* e_bal;         // [nlu] dense plans: slots by decreasing gather length, so
                               // that a strided walk gives every lane the same work
     // ---- triangular solves (permuted index space) --------------------------

@@ -154,7 +154,7 @@ struct cdn_plan {
             e_con_src, e_con_kind, l_lvl_ptr, l_rows, l_ptr, l_col, l_slot, u_lvl_ptr, u_rows,
             u_ptr, u_col, u_slot, u_diag, rowmap, colmap, r_lin_ptr, r_lin_col, r_lin_g,
             r_lin_c, r_lin_gones, r_con_ptr, r_con_src, r_con_kind, dev_g, dev_i, e_con_pk,
-            r_con_pk, e_bal;
+            r_con_pk, e_bal, cl_rec, cl_col, cl_slot, cu_rec, cu_col, cu_slot;
         long gv[CDN_MAX_GROUPS][2];
         long gd[CDN_MAX_GROUPS];
     } off;
@@ -602,6 +602,25 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     for (int r = 0; r < n; ++r) rowmap[ip[mrow[r]]] = r;
     for (int col = 0; col < n; ++col) colmap[ip[col]] = col;
 
+    // compact solve programs
+    std::vector<unsigned> cl_rec, cu_rec;
+    std::vector<unsigned short> cl_col, cl_slot, cu_col, cu_slot;
+    bool compact = !dense && n < 65536 && nlu < 65536;
+    for (int l = 0; compact && l < nlev_l; ++l) if (l_lvl_nheavy[l]) compact = false;
+    for (int l = 0; compact && l < nlev_u; ++l) if (u_lvl_nheavy[l]) compact = false;
+    if (compact) {
+        cl_rec.resize(2 * (size_t)n); cu_rec.resize(2 * (size_t)n);
+        for (int q = 0; q < n; ++q) {
+            const int i = l_rows[q];
+            cl_rec[2 * q] = (unsigned)i | ((unsigned)(l_ptr[i + 1] - l_ptr[i]) << 16);
+            cl_rec[2 * q + 1] = (unsigned)l_ptr[i];
+            const int j = u_rows[q];
+            cu_rec[2 * q] = (unsigned)j | ((unsigned)(u_ptr[j + 1] - u_ptr[j]) << 16);
+            cu_rec[2 * q + 1] = (unsigned)u_ptr[j] | ((unsigned)u_diag[j] << 16);
+        }
+        cl_col.assign(l_col.begin(), l_col.end()); cl_slot.assign(l_slot.begin(), l_slot.end());
+        cu_col.assign(u_col.begin(), u_col.end()); cu_slot.assign(u_slot.begin(), u_slot.end());
+    }
     // ---- pack ---------------------------------------------------------------------------------------
     std::vector<char>& B = P->staging;
     cdn_plan::Off& O = P->off;
@@ -640,6 +659,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     PUT(r_con_src);
     PUT(r_con_kind);
     PUT(e_con_pk); PUT(r_con_pk);
+    PUT(cl_rec); PUT(cl_col); PUT(cl_slot); PUT(cu_rec); PUT(cu_col); PUT(cu_slot);
     ivec e_bal(nlu);
     for (long e = 0; e < nlu; ++e) e_bal[e] = (int)e;
     if (dense)
@@ -657,6 +677,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     }
     cdn_plan_dev& D = P->dev;
     D.dense = dense ? 1 : 0;
+    D.compact = compact ? 1 : 0; D.nnzl = (int)l_col.size(); D.nnzu = (int)u_col.size();
     D.nhist = c->nhist > 0 ? c->nhist : 0;
     D.hist_size = 0;
     D.heavy = HEAVY;
@@ -732,6 +753,8 @@ extern "C" int cdn_plan_bind(cdn_plan* P, void* dev_ws, long bytes, void* stream
     BIND(r_con_kind, signed char);
     BIND(dev_g, int); BIND(dev_i, int);
     BIND(e_con_pk, unsigned); BIND(r_con_pk, unsigned); BIND(e_bal, int);
+    BIND(cl_rec, unsigned); BIND(cl_col, unsigned short); BIND(cl_slot, unsigned short);
+    BIND(cu_rec, unsigned); BIND(cu_col, unsigned short); BIND(cu_slot, unsigned short);
 #undef BIND
     for (int g = 0; g < D.ngroups; ++g) {
         D.groups[g].vpos = (const int*)(base + O.gv[g][0]);
