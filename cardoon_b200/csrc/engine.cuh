@@ -919,44 +919,48 @@ __device__ __forceinline__ void factor(Team& tm, const cdn_plan_dev& P, const Ws
     }
 }
 
-// Triangular solves from shared memory (block team, compact plans): the LU
-// values and the work vector are resident; the 16-bit program of each sweep
-// (row records, column and slot streams, level pointers) is staged next to
-// them, so that between two barriers a thread touches shared memory only.
+// Sweeps from shared memory (block team, compact plans): the LU values and
+// the work vector are resident; the program of each sweep (level pointers,
+// packed row / entry records, 16-bit index streams; see plan.h) is one blob that
+// is staged next to them with 16-byte copies, so that between two barriers a
+// thread touches shared memory only.
 __host__ __device__ inline long compact_stage_bytes(const cdn_plan_dev& P) {
-    const long nnz = P.nnzl > P.nnzu ? P.nnzl : P.nnzu;
-    const int nlev = P.nlev_l > P.nlev_u ? P.nlev_l : P.nlev_u;
-    return 8L * P.n + 4L * ((nnz + 1) / 2) * 2 + 4L * (nlev + 2) + 64;
+    int w = P.cl_words > P.cu_words ? P.cl_words : P.cu_words;
+    if (P.cf_words > w) w = P.cf_words;
+    return 4L * w + 32;
 }
 
-__device__ __forceinline__ void stage_words(unsigned* dst, const unsigned* src, long nwords) {
-    for (long k = threadIdx.x; k < nwords; k += blockDim.x) dst[k] = src[k];
+__device__ __forceinline__ void stage_blob(unsigned* dst, const unsigned* src, int nwords) {
+    const uint4* s4 = (const uint4*)src;
+    uint4* d4 = (uint4*)dst;
+    const int n4 = nwords >> 2;                    // blobs are padded to 16 bytes
+    // (batching several loads per thread before the stores was measured slower:
+    // the 1024-thread CTA has 64 registers per thread)
+    for (int k = threadIdx.x; k < n4; k += blockDim.x) d4[k] = s4[k];
 }
 
 __device__ __forceinline__ void staged_solve(BlockTeam& tm, const cdn_plan_dev& P, const Ws& w) {
     const int n = P.n;
     double* lu = w.lu;
     double* tmp = w.tmp;
-    unsigned* rec = w.stage;                               // [2n]
+    unsigned* blob = w.stage;
     // ---- L sweep -------------------------------------------------------------------
     {
-        const long wc = (P.nnzl + 1) / 2;                  // 16-bit streams as words
-        unsigned* colw = rec + 2L * n;
-        unsigned* slotw = colw + wc;
-        int* lvl = (int*)(slotw + wc);
-        stage_words(rec, P.cl_rec, 2L * n);
-        stage_words(colw, (const unsigned*)P.cl_col, wc);
-        stage_words(slotw, (const unsigned*)P.cl_slot, wc);
-        for (int k = threadIdx.x; k <= P.nlev_l; k += blockDim.x) lvl[k] = P.l_lvl_ptr[k];
-        for (int i = threadIdx.x; i < n; i += blockDim.x) tmp[i] = w.y[P.rowmap[i]];
+        stage_blob(blob, P.cl_prog, P.cl_words);
         __syncthreads();
-        const unsigned short* col = (const unsigned short*)colw;
-        const unsigned short* slot = (const unsigned short*)slotw;
-        for (int l = 0; l < P.nlev_l; ++l) {
+        const int* lvl = (const int*)(blob + P.cl_off[0]);
+        const uint2* rec = (const uint2*)(blob + P.cl_off[1]);
+        const unsigned short* col = (const unsigned short*)(blob + P.cl_off[2]);
+        const unsigned short* slot = (const unsigned short*)(blob + P.cl_off[3]);
+        const unsigned short* rmap = (const unsigned short*)(blob + P.cl_off[4]);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) tmp[i] = w.y[rmap[i]];
+        __syncthreads();
+        const int nlev = P.nlev_l;
+        for (int l = 0; l < nlev; ++l) {
             const int r1 = lvl[l + 1];
             for (int q = lvl[l] + threadIdx.x; q < r1; q += blockDim.x) {
-                const unsigned w0 = rec[2 * q], k0 = rec[2 * q + 1];
-                const int i = w0 & 0xffffu, cnt = w0 >> 16;
+                const uint2 r = rec[q];
+                const int i = r.x & 0xffffu, cnt = r.x >> 16, k0 = r.y;
                 double v = tmp[i];
                 for (int k = 0; k < cnt; ++k) v -= lu[slot[k0 + k]] * tmp[col[k0 + k]];
                 tmp[i] = v;
@@ -966,30 +970,27 @@ __device__ __forceinline__ void staged_solve(BlockTeam& tm, const cdn_plan_dev& 
     }
     // ---- U sweep -------------------------------------------------------------------
     {
-        const long wc = (P.nnzu + 1) / 2;
-        unsigned* colw = rec + 2L * n;
-        unsigned* slotw = colw + wc;
-        int* lvl = (int*)(slotw + wc);
-        stage_words(rec, P.cu_rec, 2L * n);
-        stage_words(colw, (const unsigned*)P.cu_col, wc);
-        stage_words(slotw, (const unsigned*)P.cu_slot, wc);
-        for (int k = threadIdx.x; k <= P.nlev_u; k += blockDim.x) lvl[k] = P.u_lvl_ptr[k];
+        stage_blob(blob, P.cu_prog, P.cu_words);
         __syncthreads();
-        const unsigned short* col = (const unsigned short*)colw;
-        const unsigned short* slot = (const unsigned short*)slotw;
-        for (int l = 0; l < P.nlev_u; ++l) {
+        const int* lvl = (const int*)(blob + P.cu_off[0]);
+        const uint2* rec = (const uint2*)(blob + P.cu_off[1]);
+        const unsigned short* col = (const unsigned short*)(blob + P.cu_off[2]);
+        const unsigned short* slot = (const unsigned short*)(blob + P.cu_off[3]);
+        const unsigned short* cmap = (const unsigned short*)(blob + P.cu_off[4]);
+        const int nlev = P.nlev_u;
+        for (int l = 0; l < nlev; ++l) {
             const int r1 = lvl[l + 1];
             for (int q = lvl[l] + threadIdx.x; q < r1; q += blockDim.x) {
-                const unsigned w0 = rec[2 * q], w1 = rec[2 * q + 1];
-                const int i = w0 & 0xffffu, cnt = w0 >> 16;
-                const int k0 = w1 & 0xffffu, dg = w1 >> 16;
+                const uint2 r = rec[q];
+                const int i = r.x & 0xffffu, cnt = r.x >> 16;
+                const int k0 = r.y & 0xffffu, dg = r.y >> 16;
                 double v = tmp[i];
                 for (int k = 0; k < cnt; ++k) v -= lu[slot[k0 + k]] * tmp[col[k0 + k]];
                 tmp[i] = v / lu[dg];
             }
             __syncthreads();
         }
-        for (int i = threadIdx.x; i < n; i += blockDim.x) w.dx[P.colmap[i]] = tmp[i];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) w.dx[cmap[i]] = tmp[i];
         __syncthreads();
     }
 }
@@ -1001,6 +1002,72 @@ __device__ __forceinline__ bool try_staged_solve(Team&, const cdn_plan_dev&, con
 __device__ __forceinline__ bool try_staged_solve(BlockTeam& tm, const cdn_plan_dev& P, const Ws& w) {
     if (!w.stage || !P.compact) return false;
     staged_solve(tm, P, w);
+    return true;
+}
+
+// Partial refactorisation (block team, compact plans).  Between two Newton
+// iterations only the device contributions change: an entry of L+U changes only
+// if it receives one, or if an operand of its Crout update or its pivot does.
+// That closure is computed once on the host; all other entries keep the values
+// of the last full factorisation (same a0 and gmin).  The affected entries are
+// re-assembled from the linear parts and re-eliminated level by level from a
+// staged program.
+__device__ __forceinline__ void staged_refactor(BlockTeam& tm, const cdn_plan_dev& P, const Ws& w,
+                                                const cdn_opts& o) {
+    double* lu = w.lu;
+    unsigned* blob = w.stage;
+    stage_blob(blob, P.cf_prog, P.cf_words);
+    __syncthreads();
+    const int* lvl = (const int*)(blob + P.cf_off[0]);
+    const uint2* rec = (const uint2*)(blob + P.cf_off[1]);
+    const unsigned* term = blob + P.cf_off[2];
+    const double a0 = o.use_q ? o.a0 : 0.0;
+    // assembly of the affected slots
+    for (int q = threadIdx.x; q < P.naff; q += blockDim.x) {
+        const int e = rec[q].x & 0xffffu;
+        double v = P.e_g[e];
+        if (o.use_q) v += a0 * P.e_c[e];
+        if (o.gmin != 0.0) v += o.gmin * P.e_gones[e];
+        lu[e] = v + slot_sum<BlockTeam>(P, w, o, a0, e, 0, 1);
+    }
+    __syncthreads();
+    const int nlev = P.nlev_f;
+    for (int l = 0; l < nlev; ++l) {
+        const int q0 = lvl[l], q1 = lvl[l + 1];
+        if (q0 == q1) continue;                    // nothing changes on this level
+        for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+            const uint2 r = rec[q];
+            const int e = r.x & 0xffffu, cnt = r.x >> 16;
+            const int t0 = r.y & 0xffffu, pv = r.y >> 16;
+            double v = lu[e];
+            for (int t = 0; t < cnt; ++t) {
+                const unsigned tt = term[t0 + t];
+                v -= lu[tt & 0xffffu] * lu[tt >> 16];
+            }
+            if (pv != 0xffff) v /= lu[pv];
+            lu[e] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// state of the factors held in w.lu during one launch
+struct FactState {
+    bool valid;
+    double a0, gmin;
+};
+
+template <class Team>
+__device__ __forceinline__ bool try_staged_refactor(Team&, const cdn_plan_dev&, const Ws&,
+                                                    const cdn_opts&, const FactState&) {
+    return false;
+}
+__device__ __forceinline__ bool try_staged_refactor(BlockTeam& tm, const cdn_plan_dev& P,
+                                                    const Ws& w, const cdn_opts& o,
+                                                    const FactState& fs) {
+    const double a0 = o.use_q ? o.a0 : 0.0;
+    if (!w.stage || !P.compact || !fs.valid || fs.a0 != a0 || fs.gmin != o.gmin) return false;
+    staged_refactor(tm, P, w, o);
     return true;
 }
 
@@ -1036,7 +1103,7 @@ __device__ __forceinline__ void lusolve(Team& tm, const cdn_plan_dev& P, const W
 template <int MS, class Team>
 __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, const Ws& w,
                                       const cdn_opts& o, bool active, double* res_out, bool* ok,
-                                      long long* prof = nullptr) {
+                                      long long* prof = nullptr, FactState* fs = nullptr) {
     double res = 0.0;
     bool success = false;
     int it = 0;
@@ -1048,12 +1115,17 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
         CDN_PROF_T0;
         eval_devices<MS, true>(tm, P, b, w.x, w, true, o.h);
         CDN_PROF(0);
-        assemble(tm, P, w, o);
         residual(tm, P, w, o);
-        tm.sync();
-        CDN_PROF(1);
-        factor(tm, P, w);
-        CDN_PROF(2);
+        if (fs && try_staged_refactor(tm, P, w, o, *fs)) {
+            CDN_PROF(2);
+        } else {
+            assemble(tm, P, w, o);
+            tm.sync();
+            CDN_PROF(1);
+            factor(tm, P, w);
+            if (fs) { fs->valid = true; fs->a0 = o.use_q ? o.a0 : 0.0; fs->gmin = o.gmin; }
+            CDN_PROF(2);
+        }
         lusolve(tm, P, w);
         CDN_PROF(3);
         double m = 0.0;
@@ -1146,15 +1218,16 @@ template <int MS, class Team>
 __device__ __forceinline__ int solve_helpers(Team& tm, const cdn_plan_dev& P, int b,
                                              const Ws& w, const cdn_opts& o, int helpers,
                                              bool active, double* res_out, bool* ok,
-                                             long long* prof = nullptr) {
+                                             long long* prof = nullptr, FactState* fs = nullptr) {
     if (helpers && active) {
         for (int r = tm.rank(); r < P.n; r += tm.size()) w.xb[r] = w.x[r];
         tm.sync();
     }
-    int it = newton<MS>(tm, P, b, w, o, active, res_out, ok, prof);
+    int it = newton<MS>(tm, P, b, w, o, active, res_out, ok, prof, fs);
     if (!helpers) return it;
     bool need = active && !*ok;
     if (!tm.cta_any(need)) return it;
+    if (fs) fs->valid = false;              // the helpers refactor in full
     double res2 = 0.0;
     bool ok2 = false;
     int it2 = homotopy<MS>(tm, P, b, w, o, 0, need, &res2, &ok2);
@@ -1248,6 +1321,8 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
         }
         int status = 0;
         bool run = active;
+        FactState fs;
+        fs.valid = false; fs.a0 = 0.0; fs.gmin = 0.0;
         for (int i = A.first; i < A.nsamples; ++i) {
             if (!tm.cta_any(run)) break;
             long long* prof = (b == 0) ? A.prof : nullptr;
@@ -1267,7 +1342,8 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
                 CDN_PROF(6);
             }
             double res; bool ok;
-            const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, run, &res, &ok, prof);
+            const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, run, &res, &ok, prof,
+                                             &fs);
             if (!run) continue;
             const long at = (long)b * A.nsamples + i;
             if (tm.rank() == 0) { A.iters[at] = it; A.res[at] = res; }
@@ -1451,7 +1527,8 @@ engine_block_kernel(const __grid_constant__ cdn_engine_args A) {
         double* const g_lu = w.lu;
         if (A.smem_lu) {
             w.lu = dsm; w.tmp = dsm + P.nlu;
-            if (A.smem_lu > 1) w.stage = (unsigned*)(w.tmp + P.n);
+            if (A.smem_lu > 1)      // 16-byte aligned: blobs are copied as uint4
+                w.stage = (unsigned*)(((unsigned long long)(w.tmp + P.n) + 15ull) & ~15ull);
             for (int e = tm.rank(); e < P.nlu; e += tm.size()) w.lu[e] = g_lu[e];
         }
         if (A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN) {

@@ -70,12 +70,18 @@ struct cdn_plan_dev {
     // << 16} and 16-bit column / slot streams; small enough to be staged in
     // shared memory next to the LU values (block team)
     int compact, nnzl, nnzu;
-    const unsigned* cl_rec;   // [2n]
-    const unsigned short* cl_col;   // [nnzl]
-    const unsigned short* cl_slot;  // [nnzl]
-    const unsigned* cu_rec;   // [2n]
-    const unsigned short* cu_col;   // [nnzu]
-    const unsigned short* cu_slot;  // [nnzu]
+    // one contiguous blob of 32-bit words per sweep (copied with 16-byte loads):
+    //   L / U solve: [level ptr | row records (2 words) | columns (16 bit) |
+    //                 slots (16 bit) | rowmap / colmap (16 bit)]
+    //   partial refactorisation: [level ptr | entry records (2 words: slot |
+    //                 terms << 16, first term | pivot slot << 16) | terms
+    //                 (L slot | U slot << 16)] over the entries that depend on a
+    //                 device contribution; all other entries keep the values of the
+    //                 last full factorisation
+    const unsigned* cl_prog;  int cl_words; int cl_off[5];
+    const unsigned* cu_prog;  int cu_words; int cu_off[5];
+    const unsigned* cf_prog;  int cf_words; int cf_off[3];
+    int naff;                 // entries in the partial refactorisation
     const int* e_bal;         // [nlu] dense plans: slots by decreasing gather length, so
                               // that a strided walk gives every lane the same work
     // ---- triangular solves (permuted index space) --------------------------

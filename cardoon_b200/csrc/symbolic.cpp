@@ -154,7 +154,7 @@ struct cdn_plan {
             e_con_src, e_con_kind, l_lvl_ptr, l_rows, l_ptr, l_col, l_slot, u_lvl_ptr, u_rows,
             u_ptr, u_col, u_slot, u_diag, rowmap, colmap, r_lin_ptr, r_lin_col, r_lin_g,
             r_lin_c, r_lin_gones, r_con_ptr, r_con_src, r_con_kind, dev_g, dev_i, e_con_pk,
-            r_con_pk, e_bal, cl_rec, cl_col, cl_slot, cu_rec, cu_col, cu_slot;
+            r_con_pk, e_bal, cl_prog, cu_prog, cf_prog;
         long gv[CDN_MAX_GROUPS][2];
         long gd[CDN_MAX_GROUPS];
     } off;
@@ -602,25 +602,83 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     for (int r = 0; r < n; ++r) rowmap[ip[mrow[r]]] = r;
     for (int col = 0; col < n; ++col) colmap[ip[col]] = col;
 
-    // compact solve programs
-    std::vector<unsigned> cl_rec, cu_rec;
-    std::vector<unsigned short> cl_col, cl_slot, cu_col, cu_slot;
-    bool compact = !dense && n < 65536 && nlu < 65536;
+    // compact programs (see plan.h)
+    std::vector<unsigned> cl_prog, cu_prog, cf_prog;
+    int cl_off[5] = {0, 0, 0, 0, 0}, cu_off[5] = {0, 0, 0, 0, 0}, cf_off[3] = {0, 0, 0};
+    int naff = 0;
+    bool compact = !dense && n < 65535 && nlu < 65535;
     for (int l = 0; compact && l < nlev_l; ++l) if (l_lvl_nheavy[l]) compact = false;
     for (int l = 0; compact && l < nlev_u; ++l) if (u_lvl_nheavy[l]) compact = false;
+    for (int l = 0; compact && l < nlev_f; ++l) if (f_lvl_nheavy[l]) compact = false;
     if (compact) {
-        cl_rec.resize(2 * (size_t)n); cu_rec.resize(2 * (size_t)n);
-        for (int q = 0; q < n; ++q) {
-            const int i = l_rows[q];
-            cl_rec[2 * q] = (unsigned)i | ((unsigned)(l_ptr[i + 1] - l_ptr[i]) << 16);
-            cl_rec[2 * q + 1] = (unsigned)l_ptr[i];
-            const int j = u_rows[q];
-            cu_rec[2 * q] = (unsigned)j | ((unsigned)(u_ptr[j + 1] - u_ptr[j]) << 16);
-            cu_rec[2 * q + 1] = (unsigned)u_ptr[j] | ((unsigned)u_diag[j] << 16);
+        auto pad4 = [](std::vector<unsigned>& v) { while (v.size() % 4) v.push_back(0u); };
+        auto push16 = [&](std::vector<unsigned>& v, const ivec& a) {
+            for (size_t k = 0; k < a.size(); k += 2)
+                v.push_back((unsigned)a[k] | ((k + 1 < a.size() ? (unsigned)a[k + 1] : 0u) << 16));
+            pad4(v);
+        };
+        // L and U sweeps
+        for (int pass = 0; pass < 2; ++pass) {
+            std::vector<unsigned>& pr = pass ? cu_prog : cl_prog;
+            int* off = pass ? cu_off : cl_off;
+            const ivec& lvl = pass ? u_lvl_ptr : l_lvl_ptr;
+            const ivec& rows = pass ? u_rows : l_rows;
+            const ivec& ptr = pass ? u_ptr : l_ptr;
+            off[0] = 0;
+            for (int v : lvl) pr.push_back((unsigned)v);
+            pad4(pr);
+            off[1] = (int)pr.size();
+            for (int q = 0; q < n; ++q) {
+                const int i = rows[q];
+                pr.push_back((unsigned)i | ((unsigned)(ptr[i + 1] - ptr[i]) << 16));
+                pr.push_back((unsigned)ptr[i] | (pass ? ((unsigned)u_diag[i] << 16) : 0u));
+            }
+            pad4(pr);
+            off[2] = (int)pr.size();
+            push16(pr, pass ? u_col : l_col);
+            off[3] = (int)pr.size();
+            push16(pr, pass ? u_slot : l_slot);
+            off[4] = (int)pr.size();
+            push16(pr, pass ? colmap : rowmap);
         }
-        cl_col.assign(l_col.begin(), l_col.end()); cl_slot.assign(l_slot.begin(), l_slot.end());
-        cu_col.assign(u_col.begin(), u_col.end()); cu_slot.assign(u_slot.begin(), u_slot.end());
+        // partial refactorisation: closure of the slots with device contributions
+        std::vector<char> aff(nlu, 0);
+        for (long e = 0; e < nlu; ++e) {
+            bool f = e_con_ptr[e + 1] > e_con_ptr[e];
+            for (int t = e_term_ptr[e]; !f && t < e_term_ptr[e + 1]; ++t)
+                f = aff[e_term_l[t]] || aff[e_term_u[t]];
+            if (!f && e_piv[e] >= 0) f = aff[e_piv[e]];
+            aff[e] = f ? 1 : 0;
+        }
+        ivec flvl(nlev_f + 1, 0);
+        std::vector<unsigned> frec, fterm;
+        for (int l = 0; l < nlev_f; ++l) {
+            for (int e = f_lvl_ptr[l]; e < f_lvl_ptr[l + 1]; ++e) {
+                if (!aff[e]) continue;
+                const int cnt = e_term_ptr[e + 1] - e_term_ptr[e];
+                frec.push_back((unsigned)e | ((unsigned)cnt << 16));
+                frec.push_back((unsigned)fterm.size() |
+                               ((unsigned)(e_piv[e] >= 0 ? e_piv[e] : 0xffff) << 16));
+                for (int t = e_term_ptr[e]; t < e_term_ptr[e + 1]; ++t)
+                    fterm.push_back((unsigned)e_term_l[t] | ((unsigned)e_term_u[t] << 16));
+                ++naff;
+            }
+            flvl[l + 1] = naff;
+        }
+        if (fterm.size() >= 65535) {
+            compact = false;             // first-term offsets are 16 bit
+        } else {
+            for (int v : flvl) cf_prog.push_back((unsigned)v);
+            pad4(cf_prog);
+            cf_off[1] = (int)cf_prog.size();
+            cf_prog.insert(cf_prog.end(), frec.begin(), frec.end());
+            pad4(cf_prog);
+            cf_off[2] = (int)cf_prog.size();
+            cf_prog.insert(cf_prog.end(), fterm.begin(), fterm.end());
+            pad4(cf_prog);
+        }
     }
+    if (!compact) { cl_prog.clear(); cu_prog.clear(); cf_prog.clear(); naff = 0; }
     // ---- pack ---------------------------------------------------------------------------------------
     std::vector<char>& B = P->staging;
     cdn_plan::Off& O = P->off;
@@ -659,7 +717,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     PUT(r_con_src);
     PUT(r_con_kind);
     PUT(e_con_pk); PUT(r_con_pk);
-    PUT(cl_rec); PUT(cl_col); PUT(cl_slot); PUT(cu_rec); PUT(cu_col); PUT(cu_slot);
+    PUT(cl_prog); PUT(cu_prog); PUT(cf_prog);
     ivec e_bal(nlu);
     for (long e = 0; e < nlu; ++e) e_bal[e] = (int)e;
     if (dense)
@@ -678,6 +736,10 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     cdn_plan_dev& D = P->dev;
     D.dense = dense ? 1 : 0;
     D.compact = compact ? 1 : 0; D.nnzl = (int)l_col.size(); D.nnzu = (int)u_col.size();
+    D.cl_words = (int)cl_prog.size(); D.cu_words = (int)cu_prog.size();
+    D.cf_words = (int)cf_prog.size(); D.naff = naff;
+    for (int k = 0; k < 5; ++k) { D.cl_off[k] = cl_off[k]; D.cu_off[k] = cu_off[k]; }
+    for (int k = 0; k < 3; ++k) D.cf_off[k] = cf_off[k];
     D.nhist = c->nhist > 0 ? c->nhist : 0;
     D.hist_size = 0;
     D.heavy = HEAVY;
@@ -753,8 +815,7 @@ extern "C" int cdn_plan_bind(cdn_plan* P, void* dev_ws, long bytes, void* stream
     BIND(r_con_kind, signed char);
     BIND(dev_g, int); BIND(dev_i, int);
     BIND(e_con_pk, unsigned); BIND(r_con_pk, unsigned); BIND(e_bal, int);
-    BIND(cl_rec, unsigned); BIND(cl_col, unsigned short); BIND(cl_slot, unsigned short);
-    BIND(cu_rec, unsigned); BIND(cu_col, unsigned short); BIND(cu_slot, unsigned short);
+    BIND(cl_prog, unsigned); BIND(cu_prog, unsigned); BIND(cf_prog, unsigned);
 #undef BIND
     for (int g = 0; g < D.ngroups; ++g) {
         D.groups[g].vpos = (const int*)(base + O.gv[g][0]);
