@@ -369,3 +369,30 @@ def test_sparse_nd_interface_soliton(lib):
     import scipy.sparse.linalg as spla
     ref = spla.splu(J_r).solve(rhs)
     assert np.allclose(dx, ref, rtol=1e-6, atol=1e-9 * np.abs(ref).max())
+
+
+def test_tran_backward_euler_and_errfunc(lib):
+    """Backward Euler (integration.py:13-49) and the optional error-function
+    test of the Newton loop (fsolve.py:113-118, `.options errfunc=1`; it also
+    changes which residual the chord predictor re-uses, tran.py:181)."""
+    for im, errfunc in (('BE', False), ('trap', True), ('BE', True)):
+        ckt, queue = S.load_circuit(S.net('ring_osc_ahkab.net'))
+        an = [a for a in queue if a.anType == 'tran'][0]
+        an.im = im
+        old = glVar.errfunc
+        glVar.errfunc = errfunc
+        try:
+            nd.make_nodal_circuit(ckt)
+            dc = nd.DCNodal(ckt)
+            imo = Trapezoidal() if im == 'trap' else BEuler()
+            tran = nd.TransientNodal(ckt, imo)
+            x, res, it = solve(dc.get_guess(), tran.get_source(0.).copy(),
+                               dc.convergence_helpers)
+            timeVec = np.arange(0., an.tstop, an.tstep)[:120]
+            wave, iters, resv, status = tran.run(
+                x, timeVec, list(range(ckt.nD_dimension)))
+            ref = R.run_tran(ckt, glVar, an.tstop, an.tstep, im,
+                             max_samples=120)
+            check_tran(wave, iters, status, ref)
+        finally:
+            glVar.errfunc = old
