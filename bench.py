@@ -347,6 +347,8 @@ def run_deveval(args, D):
                     traffic=(tr['bytes_per_instance'] * n / len(G)
                              if tr else None),
                     traffic_source=(tr or {}).get('source'),
+                    pipe_fp64_active_pct_ncu=(tr or {}).get(
+                        'pipe_fp64_active_pct'),
                     peak_source='cdn_fp64_peak (DFMA microbenchmark, this '
                                 'run)',
                     flop_per_eval=flop, transcendental_per_eval=trans,
@@ -541,6 +543,8 @@ def run_mc(args, D):
                     unit='TFLOP/s', frac=ach / (peak / 1e12),
                     traffic=tr['bytes_per_instance'] * B if tr else None,
                     traffic_source=(tr or {}).get('source'),
+                    pipe_fp64_active_pct_ncu=(tr or {}).get(
+                        'pipe_fp64_active_pct'),
                     kernel='engine_tile_kernel<BSIM3, 8> (whole time loop)',
                     peak_source='cdn_fp64_peak (DFMA microbenchmark, this '
                                 'run)',
