@@ -183,8 +183,9 @@ def phase_shares(D, engine, step):
     D.torch.cuda.synchronize()
     c = engine.phase_cycles()
     engine.profile = False
-    tot = float(sum(c.values())) or 1.
-    return {k: round(v / tot, 4) for k, v in c.items()}
+    main = {k: v for k, v in c.items() if k in engine.PHASES[:7]}
+    tot = float(sum(main.values())) or 1.
+    return {k: round(v / tot, 4) for k, v in main.items()}
 
 
 def timed_steps(D, step, steps, warmup, flush=None):

@@ -551,7 +551,7 @@ class Engine(object):
                                   device=lib.device)
         keep = []
         self.profile = False
-        self.prof = torch.zeros(8, dtype=torch.int64, device=lib.device)
+        self.prof = torch.zeros(16, dtype=torch.int64, device=lib.device)
         self.red = torch.zeros(4096, dtype=torch.float64, device=lib.device)
         self.x = torch.zeros((batch, n), dtype=torch.float64,
                              device=lib.device)
@@ -640,7 +640,8 @@ class Engine(object):
         self.launches += 1
 
     PHASES = ('device_sweep', 'assembly', 'factor', 'solve', 'update',
-              'accept_rhs', 'chord')
+              'accept_rhs', 'chord', 'spare', 'stage_L', 'permute_rhs',
+              'levels_L', 'stage_U', 'levels_U', 'scatter_dx')
 
     def phase_cycles(self, reset=True):
         """SM cycles instance 0 spent per phase since the last reset (set

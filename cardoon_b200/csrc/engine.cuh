@@ -71,7 +71,7 @@ struct cdn_engine_args {
     double* red;                // GridTeam reduction scratch
     int plan_smem;              // tile kernels: bytes reserved for a shared-memory copy
                                 // of the plan's gather lists (0: read the global copy)
-    long long* prof;            // optional [8]: cycles of instance 0 per phase (device
+    long long* prof;            // optional [16]: cycles of instance 0 per phase (device
                                 // sweep, assembly, factor, solve, update, accept, chord)
 };
 
@@ -83,6 +83,7 @@ struct Ws {
     double *x, *dx, *ivec, *sv, *q, *qprev, *dq, *y, *tmp, *xb, *lu, *out, *jac, *hist;
     int* piv;       // [n] pivot rows (dense LU); piv[n + 1] = head of the history rings
     unsigned* stage;   // block team: shared-memory staging area for compact solve programs
+    long long* dprof;  // optional fine-grained timers of the staged sweeps (slots 8..15)
 };
 
 __host__ __device__ inline long ws_doubles(int n, long nlu, long out_size, long jac_size,
@@ -99,6 +100,7 @@ __device__ inline Ws ws_carve(double* base, int n, long nlu, long out_size, long
     w.hist = w.jac + jac_size;
     w.piv = (int*)(w.hist + hist_size);
     w.stage = nullptr;
+    w.dprof = nullptr;
     return w;
 }
 
@@ -944,10 +946,14 @@ __device__ __forceinline__ void staged_solve(BlockTeam& tm, const cdn_plan_dev& 
     double* lu = w.lu;
     double* tmp = w.tmp;
     unsigned* blob = w.stage;
+    long long* dp = w.dprof;
+    long long tt = dp ? clock64() : 0;
+#define CDN_DP(k) do { if (dp) { const long long t_ = clock64(); if (threadIdx.x == 0) dp[k] += t_ - tt; tt = t_; } } while (0)
     // ---- L sweep -------------------------------------------------------------------
     {
         stage_blob(blob, P.cl_prog, P.cl_words);
         __syncthreads();
+        CDN_DP(8);
         const int* lvl = (const int*)(blob + P.cl_off[0]);
         const uint2* rec = (const uint2*)(blob + P.cl_off[1]);
         const unsigned short* col = (const unsigned short*)(blob + P.cl_off[2]);
@@ -955,6 +961,7 @@ __device__ __forceinline__ void staged_solve(BlockTeam& tm, const cdn_plan_dev& 
         const unsigned short* rmap = (const unsigned short*)(blob + P.cl_off[4]);
         for (int i = threadIdx.x; i < n; i += blockDim.x) tmp[i] = w.y[rmap[i]];
         __syncthreads();
+        CDN_DP(9);
         const int nlev = P.nlev_l;
         for (int l = 0; l < nlev; ++l) {
             const int r1 = lvl[l + 1];
@@ -968,10 +975,12 @@ __device__ __forceinline__ void staged_solve(BlockTeam& tm, const cdn_plan_dev& 
             __syncthreads();
         }
     }
+    CDN_DP(10);
     // ---- U sweep -------------------------------------------------------------------
     {
         stage_blob(blob, P.cu_prog, P.cu_words);
         __syncthreads();
+        CDN_DP(11);
         const int* lvl = (const int*)(blob + P.cu_off[0]);
         const uint2* rec = (const uint2*)(blob + P.cu_off[1]);
         const unsigned short* col = (const unsigned short*)(blob + P.cu_off[2]);
@@ -990,9 +999,12 @@ __device__ __forceinline__ void staged_solve(BlockTeam& tm, const cdn_plan_dev& 
             }
             __syncthreads();
         }
+        CDN_DP(12);
         for (int i = threadIdx.x; i < n; i += blockDim.x) w.dx[cmap[i]] = tmp[i];
         __syncthreads();
+        CDN_DP(13);
     }
+#undef CDN_DP
 }
 
 template <class Team>
@@ -1527,6 +1539,7 @@ engine_block_kernel(const __grid_constant__ cdn_engine_args A) {
         double* const g_lu = w.lu;
         if (A.smem_lu) {
             w.lu = dsm; w.tmp = dsm + P.nlu;
+            w.dprof = A.prof;
             if (A.smem_lu > 1)      // 16-byte aligned: blobs are copied as uint4
                 w.stage = (unsigned*)(((unsigned long long)(w.tmp + P.n) + 15ull) & ~15ull);
             for (int e = tm.rank(); e < P.nlu; e += tm.size()) w.lu[e] = g_lu[e];

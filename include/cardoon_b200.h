@@ -170,7 +170,7 @@ typedef struct cdn_run_host {
     double* res;             /* same shape as iters                          */
     int* status;             /* [B]                                          */
     double* red;             /* grid team: reduction scratch                 */
-    long long* prof;         /* optional [8] (device): SM cycles instance 0
+    long long* prof;         /* optional [16] (device): SM cycles instance 0
                                 spent per phase: device sweep, assembly, factor,
                                 solve, update, accept (+rhs), chord            */
 } cdn_run_host;

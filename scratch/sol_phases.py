@@ -18,4 +18,5 @@ it0 = int(iters[0].sum().item()); ns = iters.shape[1]
 print('ms', e0.elapsed_time(e1), 'iters', it0, 'samples', ns, e.info)
 for k, v in c.items():
     per = v / (it0 if k in ('device_sweep', 'assembly', 'factor', 'solve', 'update') else ns)
+    if k in ('stage_L', 'permute_rhs', 'levels_L', 'stage_U', 'levels_U', 'scatter_dx'): per = v / (it0 + ns)
     print('%-14s total %12d  per call %9.0f cycles = %.1f us' % (k, v, per, per / 1965.))
