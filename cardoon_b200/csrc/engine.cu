@@ -70,6 +70,8 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
         else if (A.B > 1 || D->dense || (D->nlu < 50000 && D->ndev < 2048)) c.team = CDN_TEAM_BLOCK;
         else c.team = CDN_TEAM_GRID;
     }
+    // the tile kernels keep the state in shared memory only
+    if (c.team == CDN_TEAM_TILE && A.ws) c.team = CDN_TEAM_BLOCK;
     if (c.team == CDN_TEAM_TILE) {
         int T = r->T;
         if (T <= 0) {

@@ -941,11 +941,20 @@ __device__ __forceinline__ void stage_blob(unsigned* dst, const unsigned* src, i
     for (int k = threadIdx.x; k < n4; k += blockDim.x) d4[k] = s4[k];
 }
 
+// (The shared-memory pointers are derived from the kernel's dynamic shared array
+// here, not taken from the generic pointers in Ws: the compiler then emits
+// LDS/STS instead of generic loads and stores.)
+__device__ __forceinline__ unsigned* stage_area(double* dsm, const cdn_plan_dev& P) {
+    // same layout as engine_block_kernel: lu[nlu] | tmp[n] | 16-byte aligned blob
+    return (unsigned*)(dsm + ((P.nlu + P.n + 1) & ~1));
+}
+
 __device__ __forceinline__ void staged_solve(BlockTeam& tm, const cdn_plan_dev& P, const Ws& w) {
+    extern __shared__ double dsm[];
     const int n = P.n;
-    double* lu = w.lu;
-    double* tmp = w.tmp;
-    unsigned* blob = w.stage;
+    double* lu = dsm;
+    double* tmp = dsm + P.nlu;
+    unsigned* blob = stage_area(dsm, P);
     long long* dp = w.dprof;
     long long tt = dp ? clock64() : 0;
 #define CDN_DP(k) do { if (dp) { const long long t_ = clock64(); if (threadIdx.x == 0) dp[k] += t_ - tt; tt = t_; } } while (0)
@@ -1026,8 +1035,9 @@ __device__ __forceinline__ bool try_staged_solve(BlockTeam& tm, const cdn_plan_d
 // staged program.
 __device__ __forceinline__ void staged_refactor(BlockTeam& tm, const cdn_plan_dev& P, const Ws& w,
                                                 const cdn_opts& o) {
-    double* lu = w.lu;
-    unsigned* blob = w.stage;
+    extern __shared__ double dsm[];
+    double* lu = dsm;
+    unsigned* blob = stage_area(dsm, P);
     stage_blob(blob, P.cf_prog, P.cf_words);
     __syncthreads();
     const int* lvl = (const int*)(blob + P.cf_off[0]);
@@ -1503,10 +1513,12 @@ engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
     for (int b0 = blockIdx.x * tiles; b0 < A.B; b0 += gridDim.x * tiles) {
         const int b = b0 + tile_id;
         const bool active = b < A.B;
-        double* base = A.ws ? A.ws + (long)(active ? b : 0) * A.ws_stride
-                            : smem + (long)tile_id * per;
+        // always shared memory (callers that keep the state between launches are
+        // routed to the block kernel): with the address space known at compile
+        // time the state is accessed with LDS/STS, not generic loads and stores
+        double* base = smem + (long)tile_id * per;
         const Ws w = ws_carve(base, P.n, P.nlu, P.dev_out_size, P.dev_jac_size, P.hist_size);
-        if (active && (!A.ws || A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN)) {
+        if (active) {
             for (int r = tm.rank(); r < P.n; r += T) w.x[r] = A.x[(long)b * P.n + r];
             tm.sync();
         }
@@ -1540,8 +1552,7 @@ engine_block_kernel(const __grid_constant__ cdn_engine_args A) {
         if (A.smem_lu) {
             w.lu = dsm; w.tmp = dsm + P.nlu;
             w.dprof = A.prof;
-            if (A.smem_lu > 1)      // 16-byte aligned: blobs are copied as uint4
-                w.stage = (unsigned*)(((unsigned long long)(w.tmp + P.n) + 15ull) & ~15ull);
+            if (A.smem_lu > 1) w.stage = stage_area(dsm, P);   // 16-byte aligned
             for (int e = tm.rank(); e < P.nlu; e += tm.size()) w.lu[e] = g_lu[e];
         }
         if (A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN) {
