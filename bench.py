@@ -287,6 +287,7 @@ def run_deveval(args, D):
     inp = deveval_inputs(args.n or (1 << 22), seed=1234 + D.rank)
     lib.dll.cdn_set_tuning(0, args.minblocks)
     lib.dll.cdn_set_tuning(1, args.npre)
+    lib.dll.cdn_set_tuning(2, args.ring)
     n, nout, nxin = inp['n'], inp['nout'], inp['nxin']
     G = []
     for g in inp['groups']:
@@ -913,6 +914,9 @@ def main():
                     help='deveval tuning: CTAs/SM register limit (0 = default)')
     ap.add_argument('--npre', type=int, default=-1,
                     help='deveval tuning: record rows prefetched to L1')
+    ap.add_argument('--ring', type=int, default=1,
+                    help='deveval tuning: BSIM3 record through the '
+                         'shared-memory ring (0 = on-demand loads)')
     ap.add_argument('--n', type=int, default=0,
                     help='instances per GPU (0 = workload default)')
     args = ap.parse_args()

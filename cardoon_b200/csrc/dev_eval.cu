@@ -42,8 +42,80 @@ CDN_HD void eval_any(int model, const PV& p, unsigned flags, const Dual<P>* v, S
     }
 }
 
-// MINB = resident CTAs per SM the register allocation is limited for
-template <int MODEL, int P, int MINB = 1>
+// Ring-staged record accessor of the BSIM3 evaluation kernel.  The record
+// (78 intrinsic rows, sorted by first use) is streamed through a shared-memory
+// ring of R rows with per-thread 8-byte cp.async copies: every thread copies
+// and reads only its own column, so no barrier is needed, and the copies of
+// the rows two code sections ahead are in flight while the current section
+// computes -- the HBM latency of the on-demand __ldg of each row (45 % of the
+// stall samples of the on-demand kernel) is taken off the dependent chain
+// without holding the rows in registers.  mark(first) is called by the model
+// code at section boundaries: rows below `first` are dead and their slots are
+// refilled.  All bookkeeping is compile-time after inlining (row numbers are
+// literals); a row outside the resident window falls back to __ldg, so
+// correctness does not depend on the placement of the marks.
+template <int R, int NROWS, int TPB, int DEPTH>
+struct PVRing {
+    const double* base;
+    long ld;
+    double* sm;            // this thread's column: row k at sm[(k % R) * TPB]
+    int lo, ok, hi;        // rows [lo, ok) resident, [ok, hi) in flight
+    int h1;                // `hi` before the previous mark's copies
+    __device__ __forceinline__ void issue(int upto) {
+        const int h0 = hi;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int k = h0 + j;
+            if (k < upto && k < NROWS) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + (k % R) * TPB);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst),
+                             "l"(base + (long)k * ld) : "memory");
+            }
+        }
+        // one commit group per mark (an empty group completes at once)
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (upto > hi) hi = (upto < NROWS) ? upto : NROWS;
+    }
+    // fill the ring and wait for it (kernel start)
+    __device__ __forceinline__ void start() {
+        lo = 0; hi = 0;
+        issue(R);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        ok = h1 = hi;
+    }
+    // Rows below `first` are dead: refill their slots.  The copies issued by
+    // the last DEPTH marks may still be in flight afterwards, so a row has
+    // DEPTH code sections to arrive.
+    __device__ __forceinline__ void mark(int first) {
+        const int before = hi;
+        issue(first + R);
+        if (DEPTH == 2) {          // all but the groups of this and the previous mark
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
+            ok = h1;
+        } else {                   // all but this mark's group
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            ok = before;
+        }
+        h1 = before;
+        lo = first;
+    }
+    __device__ __forceinline__ double operator[](int k) const {
+        if (k >= lo && k < ok) return sm[(k % R) * TPB];
+        return __ldg(base + (long)k * ld);
+    }
+    // view of a sub-record (junction) that follows the ring's state
+    struct Sub {
+        const PVRing* r;
+        int off;
+        __device__ __forceinline__ double operator[](int k) const { return (*r)[off + k]; }
+    };
+    __device__ __forceinline__ Sub sub(int off) const { Sub v; v.r = this; v.off = off; return v; }
+};
+
+// MINB = resident CTAs per SM the register allocation is limited for;
+// RING = rows of the shared-memory ring the BSIM3 record is streamed through
+// (0 = on-demand loads)
+template <int MODEL, int P, int MINB = 1, int RING = 0>
 __global__ void __launch_bounds__(128, MINB)
 dev_eval_kernel(long n, unsigned flags, const double* __restrict__ params, long ldp,
                 const int* __restrict__ pidx, const double* __restrict__ xin,
@@ -58,6 +130,26 @@ dev_eval_kernel(long n, unsigned flags, const double* __restrict__ params, long 
     // row), so that those reads are cache hits instead of HBM round trips
     for (int k = 0; k < npre; ++k)
         asm volatile("prefetch.global.L1 [%0];" ::"l"(p.base + (long)k * ldp));
+    if constexpr (RING && MODEL == CDN_MODEL_BSIM3) {
+        __shared__ double ring[RING * 128];
+        PVRing<RING, NP_BSIM3, 128, (RING >= 48) ? 2 : 1> pr;
+        pr.base = p.base; pr.ld = ldp; pr.sm = ring + threadIdx.x;
+        pr.start();                // overlaps with the xin loads below
+        Dual<P> v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = make_var<P>(xin[(long)c * n + i], c);
+        GlobalSink<P> sink;
+        sink.out = out; sink.jac = jac; sink.ld = n; sink.i = i; sink.nxin = nxin;
+        Dual<P> iv[3], qv[3];
+        const double tf = pr[P_BSIM3_tf];
+        bsim3_intrinsic(pr, flags, v, iv, qv);
+        mosext_apply(pr, P_BSIM3_m, flags, tf, v, iv, qv);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sink.put(k, iv[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sink.put(3 + k, qv[k]);
+        return;
+    }
     Dual<P> v[CDN_MAX_XIN];
 #pragma unroll
     for (int c = 0; c < CDN_MAX_XIN; ++c)
@@ -69,10 +161,12 @@ dev_eval_kernel(long n, unsigned flags, const double* __restrict__ params, long 
 
 static int g_minblocks = 0;      // tuning: 0 = default register allocation
 static int g_npre = -1;          // tuning: record rows prefetched to L1 (-1 = default)
+static int g_ring = 1;           // tuning: BSIM3 record through the shared-memory ring
 
 extern "C" int cdn_set_tuning(int key, int value) {
     if (key == 0) { g_minblocks = value; return CDN_OK; }
     if (key == 1) { g_npre = value; return CDN_OK; }
+    if (key == 2) { g_ring = value; return CDN_OK; }
     return CDN_ERR_ARG;
 }
 
@@ -85,20 +179,25 @@ static cudaError_t launch_one(long n, unsigned flags, const double* params, long
     // BSIM3 with Jacobian: 228 registers unconstrained (8 warps/SM).  Limiting
     // the allocation to 128 registers (16 warps/SM, ~200 B of spills) measured
     // +50 % throughput on B200: the kernel is latency-bound, not pipe-bound.
-    const int mb = (MODEL == CDN_MODEL_BSIM3 && P == 3) ? (g_minblocks ? g_minblocks : 4) : 1;
+    const int mb = (MODEL == CDN_MODEL_BSIM3 && P == 3) ? (g_minblocks ? g_minblocks : 3) : 1;
     const int npre = (g_npre >= 0) ? g_npre : 0;
-#define CDN_LAUNCH_MB(M) dev_eval_kernel<MODEL, P, M><<<(unsigned)blocks, tpb, 0, st>>>( \
+#define CDN_LAUNCH_MB(M, R) dev_eval_kernel<MODEL, P, M, R><<<(unsigned)blocks, tpb, 0, st>>>( \
         n, flags, params, ldp, pidx, xin, out, jac, nxin, npre)
-    if (MODEL == CDN_MODEL_BSIM3 && P == 3) {
-        switch (mb) {
-        case 2: CDN_LAUNCH_MB(2); break;
-        case 3: CDN_LAUNCH_MB(3); break;
-        case 5: CDN_LAUNCH_MB(5); break;
-        case 6: CDN_LAUNCH_MB(6); break;
-        default: CDN_LAUNCH_MB(4); break;
+    if constexpr (MODEL == CDN_MODEL_BSIM3 && P == 3) {
+      if (g_ring && nxin == 3) {
+        // ring-staged record; (CTAs/SM, ring rows) variants kept for tuning
+        const int key = mb * 100 + (g_ring == 1 ? 48 : g_ring);
+        switch (key) {
+        case 248: CDN_LAUNCH_MB(2, 48); break;
+        case 332: CDN_LAUNCH_MB(3, 32); break;
+        case 448: CDN_LAUNCH_MB(4, 48); break;
+        default: CDN_LAUNCH_MB(3, 48); break;
         }
+      } else {
+        CDN_LAUNCH_MB(4, 0);
+      }
     } else {
-        CDN_LAUNCH_MB(1);
+        CDN_LAUNCH_MB(1, 0);
     }
 #undef CDN_LAUNCH_MB
     return cudaGetLastError();

@@ -100,19 +100,25 @@ CDN_HD Dual<P> operator*(double a, const Dual<P>& b) { return b * a; }
 // ---- division ---------------------------------------------------------------
 // One reciprocal per dual division: MUFU seed + two Newton steps (~1 ulp), then
 // the quotient gets the usual residual correction, which makes it the
-// correctly rounded a/b in all but rare half-way cases.  Zero, denormal,
-// huge, infinite and NaN divisors take the IEEE path so that special values
-// propagate exactly as in the host arithmetic the models were written for.
+// correctly rounded a/b in all but rare half-way cases.  Branch-free: for a
+// zero, denormal, huge, infinite or NaN divisor the refinement would turn the
+// seed into NaN, so the seed itself is returned -- it is the IEEE result for
+// 0, inf and NaN (+-inf, +-0, NaN propagate exactly as in the host arithmetic
+// the models were written for); a denormal divisor gives inf and one above
+// 2^1022 gives 0, off from IEEE by less than 2^-1022 absolute.  (An IEEE
+// `1.0 / x` slow path behind a branch was measured first: ptxas lays it out
+// as the fall-through, so each of the ~110 divisions of a BSIM3 evaluation
+// took a jump over 20 dead instructions -- 20 % of the stall samples.)
 CDN_HD double cdn_rcp(double x) {
     const unsigned ex = (unsigned)__double2hiint(x) & 0x7ff00000u;
-    if (ex - 0x00100000u >= 0x7fc00000u) return 1.0 / x;     // rare, divergent
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
+    const bool special = ex - 0x00100000u >= 0x7fc00000u;
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    double e = fma(-x, r0, 1.0);
+    double r = fma(r0, e, r0);
     e = fma(-x, r, 1.0);
     r = fma(r, e, r);
-    return r;
+    return special ? r0 : r;
 }
 // a/b given inv ~ 1/b
 CDN_HD double cdn_div(double a, double b, double inv) {

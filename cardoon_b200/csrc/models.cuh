@@ -14,8 +14,9 @@
 #define CDN_MAX_OUT 12
 
 template <int P, class S>
-CDN_HD void mos_eval(int model, const PV& p, unsigned flags, const Dual<P>* v, S& out) {
+CDN_HD void mos_eval(int model, const PV& p0, unsigned flags, const Dual<P>* v, S& out) {
     Dual<P> iv[3], qv[3];
+    PV p = p0;
     if (model == CDN_MODEL_BSIM3) {
         bsim3_intrinsic(p, flags, v, iv, qv);
         mosext_apply(p, P_BSIM3_m, flags, p[P_BSIM3_tf], v, iv, qv);

@@ -25,10 +25,15 @@ CDN_HD Dual<P> log1pexp(const Dual<P>& x) {           // :24-33
     return select(-x.v - BSIM3_EXP_THRESHOLD, ex, y1);
 }
 
-template <int P>
-CDN_HD void bsim3_intrinsic(const PV& p, unsigned flags, const Dual<P>* v,
+// `A` is the record accessor: PV (on-demand loads) or the evaluation kernel's
+// PVRing, which streams the rows through shared memory in layout order; the
+// p.mark(r) calls tell it that rows below r have been consumed (the BSIM3 list
+// of param_layout.py is sorted by first use in this function).
+template <int P, class A>
+CDN_HD void bsim3_intrinsic(A& p, unsigned flags, const Dual<P>* v,
                             Dual<P>* iv, Dual<P>* qv) {
     typedef Dual<P> D;
+    p.mark(0);
     const double tf = p[P_BSIM3_tf];
     const D vd0 = tf * v[0], vg = tf * v[1], vs0 = tf * v[2];
     // ---- D/S swap (:418-423)
@@ -73,6 +78,7 @@ CDN_HD void bsim3_intrinsic(const PV& p, unsigned flags, const Dual<P>* v,
         T2 = T2 * (1.0 + 2.0 * T2);
         const D T0 = p[P_BSIM3_dvt0w] * T2;
         T2 = T0 * V0;
+        p.mark(P_BSIM3_t1a);
         T1 = p[P_BSIM3_t1a] + (p[P_BSIM3_kt1eff] + p[P_BSIM3_kt2] * Vbseff) * p[P_BSIM3_ToTnm1];
         const D T3b = p[P_BSIM3_eta0] + p[P_BSIM3_etab] * Vbseff;
         const D DIBL_Sft = (T3b * p[P_BSIM3_theta0vb0]) * VDS;
@@ -81,6 +87,7 @@ CDN_HD void bsim3_intrinsic(const PV& p, unsigned flags, const Dual<P>* v,
               + (p[P_BSIM3_k3] + p[P_BSIM3_k3b] * Vbseff) * p[P_BSIM3_tmp2] + T1 - DIBL_Sft;
     }
     // ---- subthreshold slope factor n (:502-509)
+    p.mark(P_BSIM3_cox);
     const double cox = p[P_BSIM3_cox], Vt = p[P_BSIM3_Vt];
     D n;
     {
@@ -104,6 +111,7 @@ CDN_HD void bsim3_intrinsic(const PV& p, unsigned flags, const Dual<P>* v,
                          T1 / T2);
     }
     // ---- effective channel geometry, Rds (:539-551)
+    p.mark(P_BSIM3_weff);
     const double weff = p[P_BSIM3_weff], leff = p[P_BSIM3_leff];
     D Weff, Rds;
     {
@@ -134,6 +142,7 @@ CDN_HD void bsim3_intrinsic(const PV& p, unsigned flags, const Dual<P>* v,
         Abulk0 = Abulk0 * T0;
     }
     // ---- mobility, Esat (:575-584)
+    p.mark(P_BSIM3_tox);
     const double tox = p[P_BSIM3_tox], vsattemp = p[P_BSIM3_vsattemp];
     D ueff, Esat;
     {
@@ -175,6 +184,7 @@ CDN_HD void bsim3_intrinsic(const PV& p, unsigned flags, const Dual<P>* v,
     // ---- VACLM, VADIBL, Va (:619-668)
     D Va;
     {
+        p.mark(P_BSIM3_pclm);
         const double pclm = p[P_BSIM3_pclm], litl = p[P_BSIM3_litl];
         const D VACLM = select((diffVds - 1.0e-10) * pclm,
                                leff * (Abulk + Vgsteff / EsatL) * diffVds / (pclm * Abulk * litl),
@@ -227,6 +237,7 @@ CDN_HD void bsim3_intrinsic(const PV& p, unsigned flags, const Dual<P>* v,
     iv[1] = select(swap, Isub, 0.0) * tf;
     iv[2] = select(swap, D(0.0), Isub) * tf;
     // ---- charges (:738-907)
+    p.mark(P_BSIM3_vfbzb);
     const double vfbzb = p[P_BSIM3_vfbzb], Tox = p[P_BSIM3_Tox];
     const double ldeb = p[P_BSIM3_ldeb], epSi = p[P_BSIM3_epSi];
     const double k1ox = p[P_BSIM3_k1ox];

@@ -12,17 +12,20 @@ struct PV {
     long ld;
     CDN_HD double operator[](int k) const { return __ldg(base + (long)k * ld); }
     CDN_HD PV sub(int off) const { PV r; r.base = base + (long)off * ld; r.ld = ld; return r; }
+    // streaming hint of the ring-staged accessor (dev_eval.cu PVRing): "rows
+    // below `first` are not read any more"; nothing to do for on-demand loads
+    CDN_HD void mark(int) {}
 };
 
-template <int P>
-CDN_HD Dual<P> junction_id(const PV& j, const Dual<P>& vd) {
+template <int P, class A>
+CDN_HD Dual<P> junction_id(const A& j, const Dual<P>& vd) {
     return j[J_t_is] * (safe_exp(vd / j[J_kexp]) - 1.0);
 }
 
 // Depletion charge; callers guard on the cj0 != 0 flag (the reference returns
 // 0*vd otherwise).
-template <int P>
-CDN_HD Dual<P> junction_qd(const PV& j, const Dual<P>& vd) {
+template <int P, class A>
+CDN_HD Dual<P> junction_qd(const A& j, const Dual<P>& vd) {
     const double fc = j[J_fc], t_vj = j[J_t_vj], k4 = j[J_k4], k5 = j[J_k5];
     const double k6 = j[J_k6], k7 = j[J_k7], m = j[J_m];
     const Dual<P> b = fc * t_vj - vd;

@@ -15,34 +15,35 @@
 #define F_MOSEXT_PS 64u
 #define F_MOSEXT_CJSW_S 128u
 
-template <int P>
-CDN_HD void mosext_apply(const PV& p, int base, unsigned flags, double tf,
+// `A` is the record accessor (see bsim3.cuh); the marks sit outside the flag
+// tests so that the ring-staged accessor's bookkeeping stays compile-time.
+template <int P, class A>
+CDN_HD void mosext_apply(A& p, int base, unsigned flags, double tf,
                          const Dual<P>* v, Dual<P>* iv, Dual<P>* qv) {
-    const PV dj = p.sub(base + 1), djsw = p.sub(base + 1 + CDN_NJ);
-    const PV sj = p.sub(base + 1 + 2 * CDN_NJ), sjsw = p.sub(base + 1 + 3 * CDN_NJ);
-    if (flags & (F_MOSEXT_AD | F_MOSEXT_PD)) {
-        const Dual<P> v1 = -v[0] * tf;
-        if (flags & F_MOSEXT_AD) {
-            iv[1] = iv[1] - junction_id(dj, v1) * tf;
-            if (flags & F_MOSEXT_CJ_D) qv[0] = qv[0] - junction_qd(dj, v1) * tf;
-        }
-        if (flags & F_MOSEXT_PD) {
-            iv[1] = iv[1] - junction_id(djsw, v1) * tf;
-            if (flags & F_MOSEXT_CJSW_D) qv[0] = qv[0] - junction_qd(djsw, v1) * tf;
-        }
-    }
-    if (flags & (F_MOSEXT_ASRC | F_MOSEXT_PS)) {
-        const Dual<P> v1 = -v[2] * tf;
-        if (flags & F_MOSEXT_ASRC) {
-            iv[2] = iv[2] - junction_id(sj, v1) * tf;
-            if (flags & F_MOSEXT_CJ_S) qv[2] = qv[2] - junction_qd(sj, v1) * tf;
-        }
-        if (flags & F_MOSEXT_PS) {
-            iv[2] = iv[2] - junction_id(sjsw, v1) * tf;
-            if (flags & F_MOSEXT_CJSW_S) qv[2] = qv[2] - junction_qd(sjsw, v1) * tf;
-        }
-    }
+    p.mark(base);
     const double m = p[base];
+    const auto dj = p.sub(base + 1), djsw = p.sub(base + 1 + CDN_NJ);
+    const auto sj = p.sub(base + 1 + 2 * CDN_NJ), sjsw = p.sub(base + 1 + 3 * CDN_NJ);
+    const Dual<P> vdj = -v[0] * tf, vsj = -v[2] * tf;
+    if (flags & F_MOSEXT_AD) {
+        iv[1] = iv[1] - junction_id(dj, vdj) * tf;
+        if (flags & F_MOSEXT_CJ_D) qv[0] = qv[0] - junction_qd(dj, vdj) * tf;
+    }
+    p.mark(base + 1 + CDN_NJ);
+    if (flags & F_MOSEXT_PD) {
+        iv[1] = iv[1] - junction_id(djsw, vdj) * tf;
+        if (flags & F_MOSEXT_CJSW_D) qv[0] = qv[0] - junction_qd(djsw, vdj) * tf;
+    }
+    p.mark(base + 1 + 2 * CDN_NJ);
+    if (flags & F_MOSEXT_ASRC) {
+        iv[2] = iv[2] - junction_id(sj, vsj) * tf;
+        if (flags & F_MOSEXT_CJ_S) qv[2] = qv[2] - junction_qd(sj, vsj) * tf;
+    }
+    p.mark(base + 1 + 3 * CDN_NJ);
+    if (flags & F_MOSEXT_PS) {
+        iv[2] = iv[2] - junction_id(sjsw, vsj) * tf;
+        if (flags & F_MOSEXT_CJSW_S) qv[2] = qv[2] - junction_qd(sjsw, vsj) * tf;
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) { iv[k] = iv[k] * m; qv[k] = qv[k] * m; }
 }
