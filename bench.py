@@ -268,6 +268,54 @@ def deveval_inputs(n, ncols=256, seed=1234):
     return dict(groups=groups, n=2 * (n // 2), nout=6, nxin=3)
 
 
+def gp_inputs(n, seed=4321):
+    """Gummel-Poon `bjt` of test/oscillator.net (model t122), one shared
+    record; biases vbe ~ U(-1, 0.9), vbc ~ U(-5, 0.9), other ports ~ U(-1, 1)
+    (SURVEY 8d "E")."""
+    from tests import support as S
+    ckt, _ = S.load_circuit(S.net('oscillator.net'))
+    e = [x for x in S.nonlinear_elements(ckt) if x.devType == 'bjt'][0]
+    spec = e.cuda_spec()
+    rng = np.random.default_rng(seed)
+    nxin = spec['nxin']
+    xin = rng.uniform(-1., 1., size=(nxin, n))
+    xin[0] = rng.uniform(-1., 0.9, size=n)
+    xin[1] = rng.uniform(-5., 0.9, size=n)
+    return dict(elem=e, spec=spec, xin=xin, n=n, nxin=nxin,
+                nout=spec['ncs'] + spec['nqs'])
+
+
+def run_gp_leg(lib, torch, n, steps, warmup, D):
+    """Second half of BASELINE.json's device-eval metric: GP evals/s with
+    the same timing rules; reported inside the deveval line's config."""
+    g = gp_inputs(n)
+    spec = g['spec']
+    # per-instance records in HBM like the BSIM3 leg (identical columns)
+    params = lib.dev(spec['params'].reshape(-1, 1)).expand(-1, n).contiguous()
+    xin = lib.dev(g['xin'])
+    out = lib.empty((g['nout'], n))
+    jac = lib.empty((g['nout'] * g['nxin'], n))
+
+    def step():
+        lib.dev_eval(spec['model'], spec['flags'], params, xin, g['nout'],
+                     want_jac=True, out=out, jac=jac)
+
+    ms, _, _ = timed_steps(D, step, steps, warmup)
+    from oracle import dual as OD
+    from oracle.models import device_eval
+    OD.reset_ops()
+    o_ref, j_ref = device_eval(g['elem'], g['xin'][:, :2048], True)
+    flop, trans = OD.OPS['flop'], OD.OPS['trans']
+    torch.cuda.synchronize()
+    o = out[:, :2048].cpu().numpy()
+    err = float(np.max(np.abs(o - o_ref) / (np.abs(o_ref) + 1e-30)))
+    return dict(model='bjt (Gummel-Poon, oscillator.net t122)', instances=n,
+                nxin=g['nxin'], nout=g['nout'],
+                evals_per_s=n * steps / (ms * 1e-3), ms_per_step=ms / steps,
+                flop_per_eval=flop, transcendental_per_eval=trans,
+                max_rel_err_vs_oracle_first_2048=err)
+
+
 def bsim3_flops(inp, nsample=2048):
     """Algorithmic FLOPs of one eval (oracle op counter)."""
     from oracle import dual as OD
@@ -335,30 +383,50 @@ def run_deveval(args, D):
                h2d_bytes_per_step=int(n * nxin * 8),
                d2h_bytes_per_step=int(n * (nout + nout * nxin) * 8))
 
+    # every rank runs the Gummel-Poon leg (it holds a barrier)
+    gp = run_gp_leg(lib, torch, n, args.steps, args.warmup, D)
     line = None
     if D.rank == 0:
         flop, trans = bsim3_flops(inp)
         peak = lib.fp64_peak()
         hbm, how = measured_peaks()
-        bytes_eval = 8. * (npar + nxin + nout + nout * nxin)
+        # rows the evaluation reads: junction records whose mosExt flag
+        # (AD, PD, ASRC, PS) is off are not touched
+        from cardoon_b200.devices.param_layout import NJ, flag_bits
+        fb = flag_bits('bsim3')
+        nrows = np.mean([npar - NJ * sum(1 for f in ('AD', 'PD', 'ASRC', 'PS')
+                                         if not g['flags'] & fb[f])
+                         for g in G])
+        bytes_eval = 8. * (nrows + nxin + nout + nout * nxin)
         t_step = ms * 1e-3 / args.steps
         ach = n * flop / t_step / 1e12
         tr = measured_traffic('deveval')
-        roof = dict(bound='fp64', achieved=ach, peak=peak / 1e12,
-                    unit='TFLOP/s', frac=ach / (peak / 1e12),
+        # roofline: the algorithmic intensity F / bytes_eval decides which
+        # roof binds (ridge = FP64 peak / HBM peak)
+        ach_bw = n * bytes_eval / t_step / 1e9
+        fp64 = dict(achieved=ach, peak=peak / 1e12, unit='TFLOP/s',
+                    frac=ach / (peak / 1e12),
+                    peak_source='cdn_fp64_peak (DFMA microbenchmark, this '
+                                'run)', flop_per_eval=flop,
+                    transcendental_per_eval=trans,
+                    pipe_fp64_active_pct_ncu=(tr or {}).get(
+                        'pipe_fp64_active_pct'))
+        hbm_r = dict(achieved=ach_bw, peak=hbm, unit='GB/s',
+                     frac=ach_bw / hbm, bytes_per_eval=bytes_eval,
+                     peak_source=how)
+        intensity = flop / bytes_eval
+        ridge = peak / (hbm * 1e9)
+        bound = 'hbm' if intensity < ridge else 'fp64'
+        roof = dict(hbm_r if bound == 'hbm' else fp64)
+        roof.update(bound=bound, intensity_flop_per_byte=intensity,
+                    ridge_flop_per_byte=ridge,
                     traffic=(tr['bytes_per_instance'] * n / len(G)
                              if tr else None),
                     traffic_source=(tr or {}).get('source'),
-                    pipe_fp64_active_pct_ncu=(tr or {}).get(
-                        'pipe_fp64_active_pct'),
-                    peak_source='cdn_fp64_peak (DFMA microbenchmark, this '
-                                'run)',
-                    flop_per_eval=flop, transcendental_per_eval=trans,
-                    hbm=dict(achieved=n * bytes_eval / t_step / 1e9,
-                             peak=hbm, unit='GB/s',
-                             frac=n * bytes_eval / t_step / 1e9 / hbm,
-                             bytes_per_eval=bytes_eval, peak_source=how))
+                    kernel='bsim3_ring_kernel<128,3,48> (one launch per '
+                           'channel type)', fp64=fp64, hbm=hbm_r)
         cpu = cpu_baseline_deveval(inp)
+        gp['fp64_frac'] = gp['evals_per_s'] * gp['flop_per_eval'] / peak
         line = dict(metric='device evals/s (BSIM3v3 mosbsim3, value + '
                            'Jacobian)', value=value, unit='device evals/s',
                     n_gpus=D.world, steps=args.steps, warmup=args.warmup,
@@ -369,6 +437,7 @@ def run_deveval(args, D):
                                 'GPU (half nch, half pch), per-instance '
                                 'parameter columns ({1} doubles each) in HBM'
                                 .format(n, npar), instances_per_gpu=n,
+                                gummel_poon=gp,
                                 l2='inputs larger than L2 ({0:.1f} GB of '
                                    'parameters per step)'.format(pbytes
                                                                  / 1e9)),

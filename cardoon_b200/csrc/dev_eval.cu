@@ -54,19 +54,24 @@ CDN_HD void eval_any(int model, const PV& p, unsigned flags, const Dual<P>* v, S
 // refilled.  All bookkeeping is compile-time after inlining (row numbers are
 // literals); a row outside the resident window falls back to __ldg, so
 // correctness does not depend on the placement of the marks.
-template <int R, int NROWS, int TPB, int DEPTH>
+template <int R, int NROWS, int TPB, int DEPTH, bool SYNC = false>
 struct PVRing {
     const double* base;
     long ld;
     double* sm;            // this thread's column: row k at sm[(k % R) * TPB]
     int lo, ok, hi;        // rows [lo, ok) resident, [ok, hi) in flight
     int h1;                // `hi` before the previous mark's copies
+    int jbase;             // first row of the trailing junction records
+    unsigned jskip;        // bit j set: junction record j is not read (flags)
     __device__ __forceinline__ void issue(int upto) {
         const int h0 = hi;
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const int k = h0 + j;
-            if (k < upto && k < NROWS) {
+            // (k is a literal after unrolling: the junction test is one
+            // warp-uniform predicate per row)
+            if (k < upto && k < NROWS
+                && !(k >= jbase && ((jskip >> ((k - jbase) / CDN_NJ)) & 1u))) {
                 const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + (k % R) * TPB);
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst),
                              "l"(base + (long)k * ld) : "memory");
@@ -87,6 +92,9 @@ struct PVRing {
     // the last DEPTH marks may still be in flight afterwards, so a row has
     // DEPTH code sections to arrive.
     __device__ __forceinline__ void mark(int first) {
+        // SYNC: the warps of the CTA walk the model code section by section
+        // together, so that they share the instruction cache lines
+        if (SYNC) __syncthreads();
         const int before = hi;
         issue(first + R);
         if (DEPTH == 2) {          // all but the groups of this and the previous mark
@@ -112,10 +120,63 @@ struct PVRing {
     __device__ __forceinline__ Sub sub(int off) const { Sub v; v.r = this; v.off = off; return v; }
 };
 
-// MINB = resident CTAs per SM the register allocation is limited for;
-// RING = rows of the shared-memory ring the BSIM3 record is streamed through
-// (0 = on-demand loads)
-template <int MODEL, int P, int MINB = 1, int RING = 0>
+// BSIM3 value + Jacobian with the record streamed through the ring.
+// TPB threads per CTA, MINB CTAs per SM (register limit), R ring rows.
+template <int TPB, int MINB, int R, bool SYNC>
+__global__ void __launch_bounds__(TPB, MINB)
+bsim3_ring_kernel(long n, unsigned flags, const double* __restrict__ params, long ldp,
+                  const int* __restrict__ pidx, const double* __restrict__ xin,
+                  double* __restrict__ out, double* __restrict__ jac) {
+    extern __shared__ double ring[];                  // [R][TPB]
+    long i = (long)blockIdx.x * TPB + threadIdx.x;
+    const bool live = i < n;
+    if (!live) {
+        if (!SYNC) return;
+        i = n - 1;                 // keeps the barriers; nothing is stored
+    }
+    PVRing<R, NP_BSIM3, TPB, (R >= 48) ? 2 : 1, SYNC> pr;
+    pr.base = params + (pidx ? (long)pidx[i] : i);
+    pr.ld = ldp;
+    pr.sm = ring + threadIdx.x;
+    // junction records whose flag is off are never read: leave them in HBM
+    pr.jbase = P_BSIM3_m + 1;
+    pr.jskip = ((flags & F_MOSEXT_AD) ? 0u : 1u) | ((flags & F_MOSEXT_PD) ? 0u : 2u)
+               | ((flags & F_MOSEXT_ASRC) ? 0u : 4u) | ((flags & F_MOSEXT_PS) ? 0u : 8u);
+    pr.start();
+    Dual<3> v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = make_var<3>(xin[(long)c * n + i], c);
+    Dual<3> iv[3], qv[3];
+    const double tf = pr[P_BSIM3_tf];
+    bsim3_intrinsic(pr, flags, v, iv, qv);
+    mosext_apply(pr, P_BSIM3_m, flags, tf, v, iv, qv);
+    if (!live) return;
+    GlobalSink<3> sink;
+    sink.out = out; sink.jac = jac; sink.ld = n; sink.i = i; sink.nxin = 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sink.put(k, iv[k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sink.put(3 + k, qv[k]);
+}
+
+template <int TPB, int MINB, int R, bool SYNC>
+static void launch_ring(long n, unsigned flags, const double* params, long ldp,
+                        const int* pidx, const double* xin, double* out, double* jac,
+                        cudaStream_t st) {
+    static bool configured = false;
+    const int smem = R * TPB * (int)sizeof(double);
+    if (!configured) {
+        cudaFuncSetAttribute(bsim3_ring_kernel<TPB, MINB, R, SYNC>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    const long blocks = (n + TPB - 1) / TPB;
+    bsim3_ring_kernel<TPB, MINB, R, SYNC><<<(unsigned)blocks, TPB, smem, st>>>(
+        n, flags, params, ldp, pidx, xin, out, jac);
+}
+
+// MINB = resident CTAs per SM the register allocation is limited for
+template <int MODEL, int P, int MINB = 1>
 __global__ void __launch_bounds__(128, MINB)
 dev_eval_kernel(long n, unsigned flags, const double* __restrict__ params, long ldp,
                 const int* __restrict__ pidx, const double* __restrict__ xin,
@@ -130,26 +191,6 @@ dev_eval_kernel(long n, unsigned flags, const double* __restrict__ params, long 
     // row), so that those reads are cache hits instead of HBM round trips
     for (int k = 0; k < npre; ++k)
         asm volatile("prefetch.global.L1 [%0];" ::"l"(p.base + (long)k * ldp));
-    if constexpr (RING && MODEL == CDN_MODEL_BSIM3) {
-        __shared__ double ring[RING * 128];
-        PVRing<RING, NP_BSIM3, 128, (RING >= 48) ? 2 : 1> pr;
-        pr.base = p.base; pr.ld = ldp; pr.sm = ring + threadIdx.x;
-        pr.start();                // overlaps with the xin loads below
-        Dual<P> v[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = make_var<P>(xin[(long)c * n + i], c);
-        GlobalSink<P> sink;
-        sink.out = out; sink.jac = jac; sink.ld = n; sink.i = i; sink.nxin = nxin;
-        Dual<P> iv[3], qv[3];
-        const double tf = pr[P_BSIM3_tf];
-        bsim3_intrinsic(pr, flags, v, iv, qv);
-        mosext_apply(pr, P_BSIM3_m, flags, tf, v, iv, qv);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) sink.put(k, iv[k]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) sink.put(3 + k, qv[k]);
-        return;
-    }
     Dual<P> v[CDN_MAX_XIN];
 #pragma unroll
     for (int c = 0; c < CDN_MAX_XIN; ++c)
@@ -179,25 +220,27 @@ static cudaError_t launch_one(long n, unsigned flags, const double* params, long
     // BSIM3 with Jacobian: 228 registers unconstrained (8 warps/SM).  Limiting
     // the allocation to 128 registers (16 warps/SM, ~200 B of spills) measured
     // +50 % throughput on B200: the kernel is latency-bound, not pipe-bound.
-    const int mb = (MODEL == CDN_MODEL_BSIM3 && P == 3) ? (g_minblocks ? g_minblocks : 3) : 1;
     const int npre = (g_npre >= 0) ? g_npre : 0;
-#define CDN_LAUNCH_MB(M, R) dev_eval_kernel<MODEL, P, M, R><<<(unsigned)blocks, tpb, 0, st>>>( \
+#define CDN_LAUNCH_MB(M) dev_eval_kernel<MODEL, P, M><<<(unsigned)blocks, tpb, 0, st>>>( \
         n, flags, params, ldp, pidx, xin, out, jac, nxin, npre)
     if constexpr (MODEL == CDN_MODEL_BSIM3 && P == 3) {
-      if (g_ring && nxin == 3) {
-        // ring-staged record; (CTAs/SM, ring rows) variants kept for tuning
-        const int key = mb * 100 + (g_ring == 1 ? 48 : g_ring);
-        switch (key) {
-        case 248: CDN_LAUNCH_MB(2, 48); break;
-        case 332: CDN_LAUNCH_MB(3, 32); break;
-        case 448: CDN_LAUNCH_MB(4, 48); break;
-        default: CDN_LAUNCH_MB(3, 48); break;
+      if (g_ring && nxin == 3 && jac) {
+#define CDN_RING(T, M, R, S) launch_ring<T, M, R, S>(n, flags, params, ldp, pidx, xin, out, jac, st)
+        // tuning variants (bench.py --ring): measured on B200 3.44 / 3.48 /
+        // 3.24 / 2.96 G evals/s -- more warps cost spills, a CTA-wide
+        // lockstep costs more at the CTA ramps than it saves in fetches
+        switch (g_ring) {
+        case 2: CDN_RING(128, 3, 32, false); break;
+        case 3: CDN_RING(128, 4, 48, false); break;
+        case 4: CDN_RING(384, 1, 48, true); break;
+        default: CDN_RING(128, 3, 48, false); break;
         }
+#undef CDN_RING
       } else {
-        CDN_LAUNCH_MB(4, 0);
+        CDN_LAUNCH_MB(4);
       }
     } else {
-        CDN_LAUNCH_MB(1, 0);
+        CDN_LAUNCH_MB(1);
     }
 #undef CDN_LAUNCH_MB
     return cudaGetLastError();
