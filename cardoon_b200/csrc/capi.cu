@@ -51,6 +51,7 @@ extern "C" int cdn_model_nparams(int model_id) {
     case CDN_MODEL_EKV: return NP_EKV;
     case CDN_MODEL_MESFETC: return NP_MESFETC;
     case CDN_MODEL_MEMR: return NP_MEMR;
+    case CDN_MODEL_DIODE_T: return NP_DIODE_T;
     default: return -1;
     }
 }

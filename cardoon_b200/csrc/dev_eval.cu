@@ -38,6 +38,7 @@ CDN_HD void eval_any(int model, const PV& p, unsigned flags, const Dual<P>* v, S
     case CDN_MODEL_BSIM3: case CDN_MODEL_EKV: mos_eval(model, p, flags, v, sink); break;
     case CDN_MODEL_MESFETC: mesfetc_eval(p, flags, v, sink); break;
     case CDN_MODEL_MEMR: memr_eval(p, flags, v, sink); break;
+    case CDN_MODEL_DIODE_T: diode_t_eval(p, flags, v, sink); break;
     default: break;
     }
 }
@@ -278,6 +279,8 @@ static cudaError_t launch_model(int model, int lanes, long n, unsigned flags,
         return lanes ? LAUNCH(CDN_MODEL_MESFETC, 4) : LAUNCH(CDN_MODEL_MESFETC, 0);
     case CDN_MODEL_MEMR:
         return lanes ? LAUNCH(CDN_MODEL_MEMR, 2) : LAUNCH(CDN_MODEL_MEMR, 0);
+    case CDN_MODEL_DIODE_T:
+        return lanes ? LAUNCH(CDN_MODEL_DIODE_T, 2) : LAUNCH(CDN_MODEL_DIODE_T, 0);
     default:
         return cudaErrorInvalidValue;
     }
@@ -291,7 +294,7 @@ extern "C" int cdn_dev_eval(cdn_ctx* ctx, int model_id, unsigned flags, long n, 
     if (nxin < 1 || nxin > CDN_MAX_XIN) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_dev_eval: bad nxin");
     cudaStream_t st = (cudaStream_t)stream;
     const int lanes = jac ? nxin : 0;
-    if (model_id < 0 || model_id > CDN_MODEL_MEMR)
+    if (model_id < 0 || model_id > CDN_MODEL_DIODE_T || model_id == CDN_MODEL_SVDIODE)
         return cdn_fail(ctx, CDN_ERR_ARG, "cdn_dev_eval: unknown model id");
     const cudaError_t e = launch_model(model_id, lanes, n, flags, params, ldp, pidx, xin,
                                        out, jac, nxin, st);

@@ -197,6 +197,10 @@ template <int P> CDN_HD Dual<P> dpow(const Dual<P>& x, double p) {
     const double z = ::pow(x.v, p); return d_scale(x, z, p * z * cdn_rcp(x.v));
 }
 template <int P> CDN_HD Dual<P> sq(const Dual<P>& x) { return x * x; }
+// value of a record entry that is a double (isothermal record) or a dual
+// (electro-thermal record, models/thermal.cuh)
+CDN_HD double val(double x) { return x; }
+template <int P> CDN_HD double val(const Dual<P>& x) { return x.v; }
 CDN_HD double sq(double x) { return x * x; }
 
 // ---- selection ------------------------------------------------------------------

@@ -337,6 +337,7 @@ __device__ __forceinline__ void eval_model(const cdn_group_dev& G, const PV& p, 
     else if (MODEL == CDN_MODEL_BSIM3 || MODEL == CDN_MODEL_EKV) mos_eval(MODEL, p, G.flags, v, sink);
     else if (MODEL == CDN_MODEL_MESFETC) mesfetc_eval(p, G.flags, v, sink);
     else if (MODEL == CDN_MODEL_MEMR) memr_eval(p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_DIODE_T) diode_t_eval(p, G.flags, v, sink);
 }
 
 #define CDN_MS(m) (1 << (m))
@@ -369,6 +370,10 @@ __device__ __noinline__ void eval_one(const cdn_group_dev& G, int b, int i, cons
         break;
     case CDN_MODEL_MEMR:
         if (CDN_HAS(MS, CDN_MODEL_MEMR)) eval_model<CDN_MODEL_MEMR, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0);
+        break;
+    case CDN_MODEL_DIODE_T:
+        if (CDN_HAS(MS, CDN_MODEL_DIODE_T))
+            eval_model<CDN_MODEL_DIODE_T, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0);
         break;
     case CDN_MODEL_MESFETC:
         if (CDN_HAS(MS, CDN_MODEL_MESFETC))

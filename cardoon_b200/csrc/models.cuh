@@ -9,6 +9,7 @@
 #include "models/ekv.cuh"
 #include "models/mesfetc.cuh"
 #include "models/exprvm.cuh"
+#include "models/thermal.cuh"
 
 #define CDN_MAX_XIN 4
 #define CDN_MAX_OUT 12
@@ -34,6 +35,7 @@ CDN_HD void mos_eval(int model, const PV& p0, unsigned flags, const Dual<P>* v, 
 __host__ __device__ inline int model_lanes(int model) {
     switch (model) {
     case CDN_MODEL_DIODE: return 1;
+    case CDN_MODEL_DIODE_T: return 2;
     case CDN_MODEL_BSIM3: case CDN_MODEL_EKV: return 3;
     case CDN_MODEL_MEMR: return 2;
     default: return 4;

@@ -3,17 +3,25 @@
 #pragma once
 #include "junction.cuh"
 
-template <int P, class S>
-CDN_HD void diode_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
-    const PV jtn = p.sub(P_DIODE_jtn_t_is);
-    const Dual<P> vd = v[0];
-    Dual<P> iD = junction_id(jtn, vd);
-    Dual<P> qD(0.0);
+// `A`: PV (packed isothermal record) or DualRec (thermal.cuh)
+template <int P, class A>
+CDN_HD void diode_core(const A& p, unsigned flags, const Dual<P>& vd, Dual<P>& iD, Dual<P>& qD) {
+    const auto jtn = p.sub(P_DIODE_jtn_t_is);
+    iD = junction_id(jtn, vd);
+    qD = Dual<P>(0.0);
     if (flags & F_DIODE_CJ0) qD = junction_qd(jtn, vd);
     if (flags & F_DIODE_TT) qD = qD + p[P_DIODE_tt] * iD;
     if (flags & F_DIODE_BV)
         iD = iD - p[P_DIODE_ibv] * safe_exp(-(vd + p[P_DIODE_bv]) / p[P_DIODE_n] / p[P_DIODE_vt]);
-    const double area = p[P_DIODE_area];
-    out.put(0, iD * area);
-    if (flags & F_DIODE_QD) out.put(1, qD * area);
+    const auto area = p[P_DIODE_area];
+    iD = iD * area;
+    qD = qD * area;
+}
+
+template <int P, class S>
+CDN_HD void diode_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
+    Dual<P> iD, qD;
+    diode_core(p, flags, v[0], iD, qD);
+    out.put(0, iD);
+    if (flags & F_DIODE_QD) out.put(1, qD);
 }

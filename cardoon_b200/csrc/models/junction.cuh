@@ -26,8 +26,11 @@ CDN_HD Dual<P> junction_id(const A& j, const Dual<P>& vd) {
 // 0*vd otherwise).
 template <int P, class A>
 CDN_HD Dual<P> junction_qd(const A& j, const Dual<P>& vd) {
-    const double fc = j[J_fc], t_vj = j[J_t_vj], k4 = j[J_k4], k5 = j[J_k5];
-    const double k6 = j[J_k6], k7 = j[J_k7], m = j[J_m];
+    // `auto`: doubles for the packed isothermal record, duals (d/dT lane) for
+    // the electro-thermal one
+    const auto fc = j[J_fc], t_vj = j[J_t_vj], k5 = j[J_k5];
+    const auto k6 = j[J_k6], k7 = j[J_k7], m = j[J_m];
+    const double k4 = val(j[J_k4]);               // 1 - m: never temperature dependent
     const Dual<P> b = fc * t_vj - vd;
     const Dual<P> u = 1.0 - vd / t_vj;
     // (1 - vd/vj)**(1 - m): the default grading m = 1/2 is a square root

@@ -4,16 +4,23 @@ Electro-thermal wrapping of nonlinear devices (``<dev>_t``).
 Class factory with the interface of the reference's devices/autoThermal.py
 (thermal_device :25-138): adds a thermal port pair after the regular
 terminals, appends the thermal port to ``controlPorts`` and a power output to
-``csOutPorts``.  The kernels need a second instantiation per model in which
-``set_temp_vars`` runs on the device in dual arithmetic with the temperature
-as an extra input; that instantiation is scheduled after the isothermal path
-(SURVEY section 8f, rank 3), so for now ``cuda_pack`` of a ``_t`` device
-raises.  Netlists and catalogs that only *name* ``_t`` devices keep parsing.
+``csOutPorts``.  The reference's ``eval_cqs`` (:97-124) calls the base
+class's ``set_temp_vars`` with the AD-typed port temperature before every
+evaluation; here that happens inside the model's electro-thermal kernel
+(csrc/models/thermal.cuh): the base class provides ``cuda_pack_thermal()``,
+which returns the base record followed by the raw, temperature-independent
+inputs of ``set_temp_vars``, and the kernel recomputes the temperature
+dependent entries as duals (one more derivative lane for the temperature).
+Base classes without ``cuda_pack_thermal`` (so far every model except
+``diode``) still parse and build their ports, but raise when a kernel record
+is requested.
 """
 import numpy as np
 
 from ..globalVars import glVar
 from .. import circuit as cir
+from . import cudadev as ad
+from .param_layout import MODEL_IDS
 
 
 def thermal_device(nle):
@@ -53,10 +60,21 @@ def thermal_device(nle):
                     len(guess) < len(self.controlPorts) + self.nDelays:
                 self.vPortGuess = np.insert(guess, self._tpn, 0.)
 
+            # ambient temperature the port temperature is added to
+            # (autoThermal.py:110: vPort[tpn] + glVar.temp)
+            self._tamb = glVar.temp
+            ad.delete_tape(self)
+
+        cudaModel = (nle.cudaModel + '_t') \
+            if getattr(nle, 'cudaModel', None) else None
+
         def cuda_pack(self):
-            raise cir.CircuitError(
-                '{0}: electro-thermal kernels ({1}) are not built yet'
-                .format(self.instanceName, self.devType))
+            if not hasattr(nle, 'cuda_pack_thermal') \
+                    or self.cudaModel not in MODEL_IDS:
+                raise cir.CircuitError(
+                    '{0}: no electro-thermal kernel for {1} yet'
+                    .format(self.instanceName, self.devType))
+            return nle.cuda_pack_thermal(self)
 
         def power(self, vPort, ioutV):
             return ioutV[self._ton]

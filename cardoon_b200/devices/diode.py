@@ -116,6 +116,18 @@ class Device(ad.CudaModel, cir.Element):
         head = [self.area, bv, self.ibv, self.n, self.vt, self.tt]
         return flags, np.concatenate((head, self.jtn.pack()))
 
+    def cuda_pack_thermal(self):
+        """diode_t record (param_layout.DIODE_T): the diode record -- its
+        temperature-dependent entries (vt, jtn_t_is, jtn_kexp, jtn_t_vj,
+        jtn_k5..k8) are placeholders evaluated at ambient, the kernel
+        recomputes them from the port temperature -- plus the raw inputs of
+        set_temp_vars (reference diode.py:254-272, :53-72)."""
+        from ..globalVars import glVar
+        self.set_temp_vars(glVar.temp)
+        flags, base = Device.cuda_pack(self)
+        extra = [glVar.temp, self.Tnomabs, self.egapn, self.eg0]
+        return flags, np.concatenate((base, extra, self.jtn.pack_raw()))
+
     def power(self, vPort, ioutV):
         return vPort[0] * ioutV[0]
 

@@ -69,6 +69,20 @@ class Junction:
         return rec
 
 
+def _pack_raw(self):
+    """Raw record of the electro-thermal kernels (param_layout.JRAW): the
+    temperature-independent inputs of set_temp_vars."""
+    c6 = c8 = 0.
+    if self.cj0 != 0.:
+        c6 = pow(1. - self.fc, - self.m - 1.)
+        c8 = 1. - pow(1. - self.fc, self._k4)
+    return np.array([self.isat, self.n, self._k1, self._k2, self._k3,
+                     self._k4, self.vj, self.cj0, self.m, self.fc, c6, c8])
+
+
+Junction.pack_raw = _pack_raw
+
+
 class SVJunction(Junction):
     """State-variable junction: i and v are both functions of x."""
     stateVariable = True

@@ -605,9 +605,70 @@ def memr_cqs(s, v):
     return [dev_gyr()**2 * M * v[0]], []
 
 
+# ---- electro-thermal wrapping (autoThermal.py:97-124) -------------------------
+K_BOLTZ = 1.3806488e-23     # globalVars.py:26-39
+Q_ELEC = 1.602176565e-19
+T_ZERO = 273.15
+
+
+class _Proxy(object):
+    """Copy of a device / junction whose temperature-dependent attributes
+    are replaced by Dual values (what the reference gets by calling
+    set_temp_vars with an AD-typed temperature)."""
+
+    def __init__(self, obj):
+        self.__dict__.update(obj.__dict__)
+
+
+def junction_temp_vars(j, Tabs, Tnomabs, vt, egapn, egap_t):
+    """Junction.set_temp_vars, diode.py:53-72."""
+    jt = _Proxy(j)
+    tnratio = Tabs / Tnomabs
+    jt._t_is = j.isat * D.power(tnratio, j._k1) * exp(j._k2 - j._k3 / Tabs)
+    jt._kexp = vt * j.n
+    if j.cj0 != 0.:
+        jt._t_vj = j.vj * tnratio - 3. * vt * log(tnratio) \
+            - tnratio * egapn + egap_t
+        jt._t_cj0 = j.cj0 * (1. + j.m * (.0004 * (Tabs - Tnomabs)
+                                         + 1. - jt._t_vj / j.vj))
+        jt._k5 = jt._t_vj * jt._t_cj0 / j._k4
+        jt._k6 = jt._t_cj0 * pow(1. - j.fc, - j.m - 1.)
+        jt._k7 = ((1. - j.fc * (1. + j.m)) * jt._t_vj * j.fc
+                  + .5 * j.m * jt._t_vj * j.fc * j.fc)
+    return jt
+
+
+def diode_temp_vars(dev, temp):
+    """Device.set_temp_vars of the diode, diode.py:254-272."""
+    d = _Proxy(dev)
+    Tabs = temp + T_ZERO
+    d.vt = K_BOLTZ * Tabs / Q_ELEC
+    egap_t = dev.eg0 - .000702 * (Tabs * Tabs) / (Tabs + 1108.)
+    d.jtn = junction_temp_vars(dev.jtn, Tabs, dev.Tnomabs, d.vt, dev.egapn,
+                               egap_t)
+    return d
+
+
+_THERMAL = {}       # base devType -> (set_temp_vars, eval_cqs, power)
+
+
+def thermal_cqs(dev, v):
+    """ThermalDevice.eval_cqs, autoThermal.py:97-124: the last regular
+    control port is the temperature rise; outputs get the power appended."""
+    tempvars, base_cqs, power = _THERMAL[dev.devType[:-2]]
+    tpn = dev._tpn
+    temp = v[tpn] + dev._tamb
+    d = tempvars(dev, temp)
+    v1 = [x for k, x in enumerate(v) if k != tpn]
+    iV, qV = base_cqs(d, v1)
+    return list(iV) + [power(d, v1, iV)], qV
+
+
 # ---- dispatch ---------------------------------------------------------------
 def eval_cqs(dev, v):
     t = dev.devType
+    if t.endswith('_t') and t[:-2] in _THERMAL:
+        return thermal_cqs(dev, v)
     if t == 'diode':
         return diode_cqs(dev, v)
     if t == 'bjt':
@@ -627,6 +688,10 @@ def eval_cqs(dev, v):
     if t == 'memr':
         return memr_cqs(dev, v)
     raise NotImplementedError('oracle: no model for ' + t)
+
+
+_THERMAL['diode'] = (diode_temp_vars, diode_cqs,
+                     lambda d, v, i: v[0] * i[0])       # diode.py:310-316
 
 
 def device_eval(dev, xin, deriv=True, gyr=1e-3):

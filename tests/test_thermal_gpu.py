@@ -1,0 +1,76 @@
+"""
+GPU parity of the electro-thermal diode (`diode_t`, reference
+devices/autoThermal.py + diode.py) against the oracle: the evaluation kernel
+through cdn_dev_eval, and operating point / DC sweep / transient through the
+device-resident Newton engine.
+"""
+import numpy as np
+import pytest
+
+from tests import support as S
+from tests.test_dev_eval_gpu import check
+from tests.test_newton_gpu import tran_both, check_tran, check_op
+from cardoon_b200.analyses import nodalCUDA as nd
+from cardoon_b200.analyses.fsolve import solve
+from cardoon_b200.globalVars import glVar
+from oracle import nodal_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def test_diode_t_kernel(lib):
+    rng = np.random.default_rng(11)
+    n = 2048
+    xin = np.vstack([rng.uniform(-5., 0.9, n), rng.uniform(-60., 150., n)])
+    for kw in (dict(), dict(cj0=1e-12), dict(tt=1e-9),
+               dict(cj0=2e-12, tt=1e-9, bv=4., rs=10.),
+               dict(isat=1e-15, n=1.5, area=3., cj0=1e-12, m=0.33, fc=0.6)):
+        elem = S.make_element('diode_t', [1, 0, 2, 0], **kw)
+        check(lib, elem, xin)
+
+
+def test_diode_t_plugin_batch_of_one(lib):
+    """Device-plugin interface (eval_and_deriv / eval_cqs / power) of a `_t`
+    device: batch of one through the same kernel."""
+    from oracle.models import device_eval
+    elem = S.make_element('diode_t', [1, 0, 2, 0], cj0=1e-12, rs=3.)
+    v = np.array([0.71, 35.])
+    out, jac = elem.eval_and_deriv(v)
+    ro, rj = device_eval(elem, v[:, None], True)
+    assert np.allclose(out, ro[:, 0], rtol=1e-10)
+    assert np.allclose(jac, rj[:, :, 0], rtol=1e-8)
+    iV, qV = elem.eval_cqs(v)
+    assert len(iV) == 2 and len(qV) == 1
+    assert elem.power(v[:1], iV) == iV[1]
+    assert abs(iV[1] - v[0] * iV[0]) < 1e-12 * abs(iV[1])
+
+
+def test_op_and_dc_sweep_diode_thermal(lib):
+    ckt, queue = S.load_circuit(S.net('diode_thermal.net'))
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    x, res, it = solve(dc.get_guess(), dc.get_source(), dc.convergence_helpers)
+    ref = R.run_op(ckt, glVar)
+    assert abs(it - ref['iterations']) <= 1
+    check_op(x, ref['x'])
+    # `.analysis dc device=res:rth param=r` of the deck (dc.py:89-242)
+    ckt, queue = S.load_circuit(S.net('diode_thermal.net'))
+    an = [a for a in queue if a.anType == 'dc'][0]
+    ckt.saveReqList = []
+    ckt.plotReqList = []
+    an.run(ckt)
+    got = np.array([t.dC_v for t in ckt.nD_termList]).T
+    ckt2, _ = S.load_circuit(S.net('diode_thermal.net'))
+    r2 = R.run_dc(ckt2, glVar, an.device, an.param, an.start, an.stop, an.num)
+    err = np.abs(got - r2['X'])
+    assert np.all(err < 1e-9 * np.abs(r2['X']) + 1e-12), err.max()
+    assert np.max(np.abs(an.iterations - r2['iters'])) <= 1
+
+
+def test_tran_self_heating(lib):
+    wave, iters, status, ref, tran = tran_both('diode_thermal_tran.net')
+    check_tran(wave, iters, status, ref)
+    rows = ref['idx'].name_to_row()
+    # the junction really heats up (tens of degrees) and cools down again
+    dT = wave[:, rows['1000']]
+    assert dT.max() > 5. and dT[-1] < dT.max()
