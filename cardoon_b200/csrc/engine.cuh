@@ -338,6 +338,8 @@ __device__ __forceinline__ void eval_model(const cdn_group_dev& G, const PV& p, 
     else if (MODEL == CDN_MODEL_MESFETC) mesfetc_eval(p, G.flags, v, sink);
     else if (MODEL == CDN_MODEL_MEMR) memr_eval(p, G.flags, v, sink);
     else if (MODEL == CDN_MODEL_DIODE_T) diode_t_eval(p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_BJT_T) bjt_t_eval<P, false>(p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_SVBJT_T) bjt_t_eval<P, true>(p, G.flags, v, sink);
 }
 
 #define CDN_MS(m) (1 << (m))
@@ -374,6 +376,14 @@ __device__ __noinline__ void eval_one(const cdn_group_dev& G, int b, int i, cons
     case CDN_MODEL_DIODE_T:
         if (CDN_HAS(MS, CDN_MODEL_DIODE_T))
             eval_model<CDN_MODEL_DIODE_T, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0);
+        break;
+    case CDN_MODEL_BJT_T:
+        if (CDN_HAS(MS, CDN_MODEL_BJT_T))
+            eval_model<CDN_MODEL_BJT_T, DERIV ? 5 : 0>(G, p, i, x, w, 0, h, 0);
+        break;
+    case CDN_MODEL_SVBJT_T:
+        if (CDN_HAS(MS, CDN_MODEL_SVBJT_T))
+            eval_model<CDN_MODEL_SVBJT_T, DERIV ? 5 : 0>(G, p, i, x, w, 0, h, 0);
         break;
     case CDN_MODEL_MESFETC:
         if (CDN_HAS(MS, CDN_MODEL_MESFETC))

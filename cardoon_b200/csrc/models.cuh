@@ -9,10 +9,11 @@
 #include "models/ekv.cuh"
 #include "models/mesfetc.cuh"
 #include "models/exprvm.cuh"
-#include "models/thermal.cuh"
 
-#define CDN_MAX_XIN 4
+#define CDN_MAX_XIN 5
 #define CDN_MAX_OUT 12
+#define CDN_MAX_OUT_BUF 11          // base-model outputs of a `_t` device
+#include "models/thermal.cuh"
 
 template <int P, class S>
 CDN_HD void mos_eval(int model, const PV& p0, unsigned flags, const Dual<P>* v, S& out) {
@@ -36,6 +37,7 @@ __host__ __device__ inline int model_lanes(int model) {
     switch (model) {
     case CDN_MODEL_DIODE: return 1;
     case CDN_MODEL_DIODE_T: return 2;
+    case CDN_MODEL_BJT_T: case CDN_MODEL_SVBJT_T: return 5;
     case CDN_MODEL_BSIM3: case CDN_MODEL_EKV: return 3;
     case CDN_MODEL_MEMR: return 2;
     default: return 4;

@@ -13,10 +13,14 @@
 #pragma once
 #include "junction.cuh"
 
-template <int P, bool SV, class S>
-CDN_HD int bjt_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
-    const double typef = p[P_BJT_typef], area = p[P_BJT_area], gyr = p[P_BJT_gyr];
-    const PV jif = p.sub(P_BJT_jif_t_is), jir = p.sub(P_BJT_jir_t_is);
+//
+// `A` is the record accessor: PV (packed isothermal record) or the dual
+// record of the electro-thermal variant (thermal.cuh); entries that never
+// depend on temperature are read through val().
+template <int P, bool SV, class S, class A>
+CDN_HD int bjt_eval(const A& p, unsigned flags, const Dual<P>* v, S& out) {
+    const double typef = val(p[P_BJT_typef]), area = val(p[P_BJT_area]), gyr = val(p[P_BJT_gyr]);
+    const auto jif = p.sub(P_BJT_jif_t_is), jir = p.sub(P_BJT_jir_t_is);
     const Dual<P> x1 = typef * v[0];
     const Dual<P> x2 = typef * v[1];
     Dual<P> ibf, ibr, vbe, vbc;
@@ -32,13 +36,13 @@ CDN_HD int bjt_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
     if (flags & F_BJT_ISE) ile = junction_id(p.sub(P_BJT_jile_t_is), vbe);
     if (flags & F_BJT_ISC) ilc = junction_id(p.sub(P_BJT_jilc_t_is), vbc);
     Dual<P> q1m1(1.0);
-    if (flags & F_BJT_VAR) q1m1 = q1m1 - vbe / p[P_BJT_var];
-    if (flags & F_BJT_VAF) q1m1 = q1m1 - vbc / p[P_BJT_vaf];
+    if (flags & F_BJT_VAR) q1m1 = q1m1 - vbe / val(p[P_BJT_var]);
+    if (flags & F_BJT_VAF) q1m1 = q1m1 - vbc / val(p[P_BJT_vaf]);
     Dual<P> kqb = 1.0 / q1m1;
     if (flags & (F_BJT_IKF | F_BJT_IKR)) {
         Dual<P> q2(0.0);
-        if (flags & F_BJT_IKF) q2 = q2 + ibf / p[P_BJT_ikf];
-        if (flags & F_BJT_IKR) q2 = q2 + ibr / p[P_BJT_ikr];
+        if (flags & F_BJT_IKF) q2 = q2 + ibf / val(p[P_BJT_ikf]);
+        if (flags & F_BJT_IKR) q2 = q2 + ibr / val(p[P_BJT_ikr]);
         kqb = kqb * (.5 * (1.0 + sqrt(1.0 + 4.0 * q2)));
     }
     const double k = area * typef;
@@ -54,11 +58,11 @@ CDN_HD int bjt_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
         const Dual<P> ib = (typef * v[2]) * gyr;
         nv = 3;
         Dual<P> rb;
-        const double rb0 = p[P_BJT_rb], rbm = p[P_BJT_rbm];
+        const double rb0 = val(p[P_BJT_rb]), rbm = val(p[P_BJT_rbm]);
         if (flags & F_BJT_IRB) {
             const Dual<P> ib1 = dabs(ib);
-            Dual<P> x = sqrt(1.0 + p[P_BJT_ck1] * ib1) - 1.0;
-            x = x * (p[P_BJT_ck2] / sqrt(ib1));
+            Dual<P> x = sqrt(1.0 + val(p[P_BJT_ck1]) * ib1) - 1.0;
+            x = x * (val(p[P_BJT_ck2]) / sqrt(ib1));
             const Dual<P> tx = tan(x);
             const Dual<P> c = rbm + 3.0 * (rb0 - rbm) * (tx - x) / (x * tx * tx);
             rb = select(ib1, c, rb0);
@@ -69,7 +73,7 @@ CDN_HD int bjt_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
         vbcx = ib * rb / area + vbc;
     }
     if (flags & F_BJT_SUB) {
-        const PV cbj = p.sub(P_BJT_cbj_t_is);
+        const auto cbj = p.sub(P_BJT_cbj_t_is);
         const Dual<P> vs = v[nv] * typef;
         out.put(n++, junction_id(cbj, vs) * area * typef);
     }
@@ -77,12 +81,12 @@ CDN_HD int bjt_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
     if (flags & F_BJT_QBE) {
         Dual<P> qbe(0.0);
         if (flags & F_BJT_TF) {
-            Dual<P> tfeff(p[P_BJT_tf]);
+            Dual<P> tfeff(val(p[P_BJT_tf]));
             if (flags & F_BJT_VTF) {
-                const Dual<P> x = ibf / (ibf + p[P_BJT_itf]);
-                const Dual<P> arg = vbc / 1.44 / p[P_BJT_vtf];
+                const Dual<P> x = ibf / (ibf + val(p[P_BJT_itf]));
+                const Dual<P> arg = vbc / 1.44 / val(p[P_BJT_vtf]);
                 const Dual<P> ex = SV ? exp(arg) : safe_exp(arg);
-                tfeff = tfeff * (1.0 + p[P_BJT_xtf] * x * x * ex);
+                tfeff = tfeff * (1.0 + val(p[P_BJT_xtf]) * x * x * ex);
             }
             qbe = tfeff * ibf;
         }
@@ -91,9 +95,9 @@ CDN_HD int bjt_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
     }
     if (flags & F_BJT_QBC) {
         Dual<P> qbc(0.0);
-        if (flags & F_BJT_TR) qbc = p[P_BJT_tr] * ibr;
+        if (flags & F_BJT_TR) qbc = val(p[P_BJT_tr]) * ibr;
         if (flags & F_BJT_QBX) {
-            const double xcjc = p[P_BJT_xcjc];
+            const double xcjc = val(p[P_BJT_xcjc]);
             Dual<P> qbx(0.0);
             if (flags & F_BJT_CJC) {
                 qbc = qbc + junction_qd(jir, vbc) * xcjc;
@@ -107,7 +111,7 @@ CDN_HD int bjt_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
         }
     }
     if ((flags & F_BJT_SUB) && (flags & F_BJT_CJS)) {
-        const PV cbj = p.sub(P_BJT_cbj_t_is);
+        const auto cbj = p.sub(P_BJT_cbj_t_is);
         const Dual<P> vs = v[nv] * typef;
         out.put(n++, junction_qd(cbj, vs) * area * typef);
     }

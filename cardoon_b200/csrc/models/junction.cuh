@@ -42,10 +42,10 @@ CDN_HD Dual<P> junction_qd(const A& j, const Dual<P>& vd) {
 }
 
 // State-variable junction: current and voltage as functions of x.
-template <int P>
-CDN_HD void svjunction_idvd(const PV& j, const Dual<P>& x, Dual<P>& iD, Dual<P>& vD) {
-    const double t_is = j[J_t_is], alpha = j[J_alpha], svth = j[J_svth];
-    const double kexp = j[J_kexp];
+template <int P, class A>
+CDN_HD void svjunction_idvd(const A& j, const Dual<P>& x, Dual<P>& iD, Dual<P>& vD) {
+    const auto t_is = j[J_t_is], alpha = j[J_alpha], svth = j[J_svth];
+    const auto kexp = j[J_kexp];
     const Dual<P> b = svth - x;
     const Dual<P> c = t_is * (exp(alpha * x) - 1.0);
     const Dual<P> lin = 1.0 + alpha * (x - svth);

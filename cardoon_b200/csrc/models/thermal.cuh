@@ -11,6 +11,7 @@
 // record (the model functions are templates over the record accessor).
 #pragma once
 #include "diode.cuh"
+#include "bjt.cuh"
 
 #define CDN_CONST_K 1.3806488e-23        // globalVars.py:26-39
 #define CDN_CONST_Q 1.602176565e-19
@@ -54,12 +55,21 @@ CDN_HD TempState<P> temp_state(const Dual<P>& dT, double temp_amb, double Tnomab
 
 // Junction.set_temp_vars (diode.py:53-72) on the raw record `raw` (JR_*),
 // written into the J_* entries of `rec` starting at `off`
-template <int P, class R>
+// (SV: SVJunction.set_temp_vars, svdiode.py:53-78)
+template <bool SV, int P, class R>
 CDN_HD void junction_tempvars(const PV& raw, const TempState<P>& t, bool cap, R& rec, int off) {
     typedef Dual<P> D;
     rec.r[off + J_t_is] = raw[JR_isat] * dpow(t.tnratio, raw[JR_k1])
                           * exp(raw[JR_k2] - raw[JR_k3] / t.Tabs);
-    rec.r[off + J_kexp] = t.vt * raw[JR_n];
+    if (SV) {
+        const double n = raw[JR_n];
+        const D alpha = 1. / n / t.vt;
+        rec.r[off + J_alpha] = alpha;
+        rec.r[off + J_svth] = log(5e10 / alpha) / alpha;
+        rec.r[off + J_kexp] = n * t.vt * 5e10;
+    } else {
+        rec.r[off + J_kexp] = t.vt * raw[JR_n];
+    }
     if (cap) {
         const double vj = raw[JR_vj], m = raw[JR_m], fc = raw[JR_fc];
         const D t_vj = vj * t.tnratio - 3. * t.vt * log(t.tnratio) - t.tnratio * t.egapn + t.egap_t;
@@ -83,11 +93,79 @@ CDN_HD void diode_t_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) 
     const TempState<P> t = temp_state(v[1], p[P_DIODE_T_temp_amb], p[P_DIODE_T_Tnomabs],
                                       p[P_DIODE_T_egapn], p[P_DIODE_T_eg0]);
     rec.r[P_DIODE_vt] = t.vt;
-    junction_tempvars(p.sub(P_DIODE_T_jraw_isat), t, (flags & F_DIODE_CJ0) != 0, rec,
+    junction_tempvars<false>(p.sub(P_DIODE_T_jraw_isat), t, (flags & F_DIODE_CJ0) != 0, rec,
                       P_DIODE_jtn_t_is);
     Dual<P> iD, qD;
     diode_core(rec, flags, v[0], iD, qD);
     out.put(0, iD);
     out.put(1, v[0] * iD);
     if (flags & F_DIODE_QD) out.put(2, qD);
+}
+
+// collects the base model's outputs so that the power can be inserted between
+// currents and charges (autoThermal.py:121-123)
+template <int P>
+struct BufSink {
+    Dual<P> o[CDN_MAX_OUT_BUF];
+    CDN_HD void put(int slot, const Dual<P>& d) { o[slot] = d; }
+};
+
+template <int P>
+CDN_HD Dual<P> pick(const Dual<P>* v, int idx) {       // v[idx] without local memory
+    Dual<P> r = v[0];
+#pragma unroll
+    for (int c = 1; c < CDN_MAX_XIN; ++c)
+        if (c == idx) r = v[c];
+    return r;
+}
+
+// bjt_t / svbjt_t: in [vbe|x1, vbc|x2, (v_ib), (v_sub), dT]; out = the base
+// model's currents, the power, then the charges.  set_temp_vars: bjt.py:453-482,
+// svbjt.py:276-305, extrinsic :170-180; power: bjt.py:607-625, svbjt.py:438-458,
+// extrinsic :208-222 (RE, RC not counted).
+template <int P, bool SV, class S>
+CDN_HD void bjt_t_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
+    typedef Dual<P> D;
+    DualRec<P, NP_BJT> rec;
+#pragma unroll
+    for (int k = 0; k < NP_BJT; ++k) rec.r[k] = D(p[k]);
+    const int nrb = (flags & F_BJT_RB) ? 1 : 0, nsub = (flags & F_BJT_SUB) ? 1 : 0;
+    const D dT = pick(v, 2 + nrb + nsub);
+    const TempState<P> t = temp_state(dT, p[P_BJT_T_temp_amb], p[P_BJT_T_Tnomabs],
+                                      p[P_BJT_T_egapn], p[P_BJT_T_eg]);
+    const D tnXTB = dpow(t.tnratio, p[P_BJT_T_xtb]);
+    junction_tempvars<SV>(p.sub(P_BJT_T_rawjif_isat), t, (flags & F_BJT_CJE) != 0, rec,
+                          P_BJT_jif_t_is);
+    junction_tempvars<SV>(p.sub(P_BJT_T_rawjir_isat), t, (flags & F_BJT_CJC) != 0, rec,
+                          P_BJT_jir_t_is);
+    if (flags & F_BJT_ISE) {
+        junction_tempvars<false>(p.sub(P_BJT_T_rawjile_isat), t, false, rec, P_BJT_jile_t_is);
+        rec.r[P_BJT_jile_t_is] = rec.r[P_BJT_jile_t_is] / tnXTB;
+    }
+    if (flags & F_BJT_ISC) {
+        junction_tempvars<false>(p.sub(P_BJT_T_rawjilc_isat), t, false, rec, P_BJT_jilc_t_is);
+        rec.r[P_BJT_jilc_t_is] = rec.r[P_BJT_jilc_t_is] / tnXTB;
+    }
+    if (nsub)
+        junction_tempvars<false>(p.sub(P_BJT_T_rawcbj_isat), t, (flags & F_BJT_CJS) != 0, rec,
+                                 P_BJT_cbj_t_is);
+    rec.r[P_BJT_bf_t] = p[P_BJT_T_bf] * tnXTB;
+    rec.r[P_BJT_br_t] = p[P_BJT_T_br] * tnXTB;
+    BufSink<P> buf;
+    const int n = bjt_eval<P, SV>(rec, flags, v, buf);
+    const int ncur = (SV ? 5 : 3) + nrb + nsub;
+    D pout;
+    if (SV)
+        pout = (buf.o[0] * buf.o[1] + buf.o[2] * buf.o[3] + buf.o[4] * (buf.o[1] - buf.o[3]))
+               / p[P_BJT_gyr];
+    else
+        pout = buf.o[0] * v[0] + buf.o[1] * v[1] + buf.o[2] * (v[0] - v[1]);
+    if (nrb) pout = pout + buf.o[SV ? 5 : 3] * v[2];
+    if (nsub) pout = pout + pick(v, 2 + nrb) * buf.o[ncur - 1];
+#pragma unroll
+    for (int k = 0; k < CDN_MAX_OUT_BUF; ++k) {
+        if (k < ncur) out.put(k, buf.o[k]);
+        else if (k < n) out.put(k + 1, buf.o[k]);
+    }
+    out.put(ncur, pout);
 }

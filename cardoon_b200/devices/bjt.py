@@ -372,6 +372,22 @@ def extrinsic_bjt(IBJT):
                 return f, np.concatenate((p, self.cbjtn.pack()))
             return f, np.concatenate((p, EMPTY))
 
+        def cuda_pack_thermal(self):
+            """bjt_t / svbjt_t record (param_layout.BJT_T): the BJT record
+            (temperature-dependent entries are placeholders at the device's
+            own temp, recomputed by the kernel from the thermal port) plus
+            the raw inputs of set_temp_vars (reference bjt.py:453-482,
+            :170-180)."""
+            f, base = BJT.cuda_pack(self)
+            raw_empty = EMPTY
+            extra = [glVar.temp, self.Tnomabs, self.egapn, self.eg, self.xtb,
+                     self.bf, self.br]
+            recs = [self.jif.pack_raw(), self.jir.pack_raw(),
+                    self.jile.pack_raw() if self.ise != 0. else raw_empty,
+                    self.jilc.pack_raw() if self.isc != 0. else raw_empty,
+                    self.cbjtn.pack_raw() if self._addCBjtn else raw_empty]
+            return f, np.concatenate([base, extra] + recs)
+
         def power(self, vPort, currV):
             pout = IBJT.power(self, vPort, currV)
             if self._addCBjtn:

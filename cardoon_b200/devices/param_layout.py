@@ -21,7 +21,7 @@ def _junc(prefix):
 
 
 MODEL_IDS = dict(diode=0, bjt=1, svbjt=2, bsim3=3, ekv=4, mesfetc=5,
-                 memr=6, svdiode=7, diode_t=8)
+                 memr=6, svdiode=7, diode_t=8, bjt_t=9, svbjt_t=10)
 
 # raw (temperature-independent) junction record of the electro-thermal
 # variants: the inputs of Junction.set_temp_vars (reference diode.py:53-72);
@@ -46,6 +46,16 @@ BJT = (['typef', 'area', 'bf_t', 'br_t', 'ikf', 'ikr', 'var', 'vaf', 'rb',
        + _junc('cbj'))
 BJT_FLAGS = ['ISE', 'ISC', 'VAR', 'VAF', 'IKF', 'IKR', 'RB', 'IRB', 'TF',
              'VTF', 'CJE', 'CJC', 'TR', 'QBX', 'QBE', 'QBC', 'SUB', 'CJS']
+
+def _jraw(prefix):
+    return [prefix + '_' + n for n in JRAW]
+
+
+# bjt_t / svbjt_t: the BJT record followed by the raw inputs of set_temp_vars
+# (reference bjt.py:453-482, extrinsic :170-180)
+BJT_T = BJT + ['temp_amb', 'Tnomabs', 'egapn', 'eg', 'xtb', 'bf', 'br'] \
+    + _jraw('rawjif') + _jraw('rawjir') + _jraw('rawjile') \
+    + _jraw('rawjilc') + _jraw('rawcbj')
 
 # mosExt wrapper (reference mosExt.py:281-324) appended to both MOS models
 MOSEXT = ['m'] + _junc('dj') + _junc('djsw') + _junc('sj') + _junc('sjsw')
@@ -88,7 +98,8 @@ MEMR = ['c', 'gyr']
 MEMR_FLAGS = []
 
 LAYOUTS = dict(diode=(DIODE, DIODE_FLAGS), svdiode=(SVDIODE, SVDIODE_FLAGS),
-               diode_t=(DIODE_T, DIODE_FLAGS),
+               diode_t=(DIODE_T, DIODE_FLAGS), bjt_t=(BJT_T, BJT_FLAGS),
+               svbjt_t=(BJT_T, BJT_FLAGS),
                bjt=(BJT, BJT_FLAGS), svbjt=(BJT, BJT_FLAGS),
                bsim3=(BSIM3, BSIM3_FLAGS), ekv=(EKV, EKV_FLAGS),
                mesfetc=(MESFETC, MESFETC_FLAGS), memr=(MEMR, MEMR_FLAGS))
@@ -115,7 +126,8 @@ def write_header(path):
         lines.append('#define JR_{0} {1}'.format(n, i))
     done = set()
     for model, (names, flags) in LAYOUTS.items():
-        tag = 'BJT' if model in ('bjt', 'svbjt') else model.upper()
+        tag = 'BJT' if model in ('bjt', 'svbjt') else \
+            'BJT_T' if model in ('bjt_t', 'svbjt_t') else model.upper()
         if tag in done:
             continue
         done.add(tag)

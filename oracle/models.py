@@ -649,6 +649,61 @@ def diode_temp_vars(dev, temp):
     return d
 
 
+def svjunction_temp_vars(j, Tabs, Tnomabs, vt, egapn, egap_t):
+    """SVJunction.set_temp_vars, svdiode.py:53-78."""
+    jt = junction_temp_vars(j, Tabs, Tnomabs, vt, egapn, egap_t)
+    jt._alpha = 1. / j.n / vt
+    max_exp_arg = 5e10
+    jt._svth = log(max_exp_arg / jt._alpha) / jt._alpha
+    jt._kexp = j.n * vt * max_exp_arg
+    return jt
+
+
+def bjt_temp_vars(dev, temp):
+    """set_temp_vars of the intrinsic models (bjt.py:453-482,
+    svbjt.py:276-305) and of the extrinsic wrapper (bjt.py:170-180)."""
+    d = _Proxy(dev)
+    sv = dev.devType.startswith('svbjt')
+    jtv = svjunction_temp_vars if sv else junction_temp_vars
+    Tabs = T_ZERO + temp
+    tnratio = Tabs / dev.Tnomabs
+    tnXTB = D.power(tnratio, dev.xtb)
+    d.vt = K_BOLTZ * Tabs / Q_ELEC
+    egap_t = dev.eg - .000702 * (Tabs * Tabs) / (Tabs + 1108.)
+    args = (Tabs, dev.Tnomabs, d.vt, dev.egapn, egap_t)
+    d.jif = jtv(dev.jif, *args)
+    d.jir = jtv(dev.jir, *args)
+    if dev.ise != 0.:
+        d.jile = junction_temp_vars(dev.jile, *args)
+        d.jile._t_is = d.jile._t_is / tnXTB
+    if dev.isc != 0.:
+        d.jilc = junction_temp_vars(dev.jilc, *args)
+        d.jilc._t_is = d.jilc._t_is / tnXTB
+    d._bf_t = dev.bf * tnXTB
+    d._br_t = dev.br * tnXTB
+    d.cbjtn = junction_temp_vars(dev.cbjtn, *args)
+    return d
+
+
+def bjt_power(d, v, i):
+    """bjt.py:607-625 + extrinsic :208-222."""
+    pRb = i[3] * v[2] if d.rb != 0. else 0.
+    pout = i[0] * v[0] + i[1] * v[1] + i[2] * (v[0] - v[1]) + pRb
+    if d._addCBjtn:
+        pout = pout + v[d._bccn] * i[d._bcon]
+    return pout
+
+
+def svbjt_power(d, v, i):
+    """svbjt.py:438-458 + extrinsic bjt.py:208-222."""
+    gyrvce = i[1] - i[3]
+    pRb = i[5] * v[2] if d.rb != 0. else 0.
+    pout = (i[0] * i[1] + i[2] * i[3] + i[4] * gyrvce) / dev_gyr() + pRb
+    if d._addCBjtn:
+        pout = pout + v[d._bccn] * i[d._bcon]
+    return pout
+
+
 _THERMAL = {}       # base devType -> (set_temp_vars, eval_cqs, power)
 
 
@@ -692,6 +747,11 @@ def eval_cqs(dev, v):
 
 _THERMAL['diode'] = (diode_temp_vars, diode_cqs,
                      lambda d, v, i: v[0] * i[0])       # diode.py:310-316
+_THERMAL['bjt'] = (bjt_temp_vars,
+                   lambda d, v: extrinsic_bjt_cqs(d, v, bjt_cqs), bjt_power)
+_THERMAL['svbjt'] = (bjt_temp_vars,
+                     lambda d, v: extrinsic_bjt_cqs(d, v, svbjt_cqs),
+                     svbjt_power)
 
 
 def device_eval(dev, xin, deriv=True, gyr=1e-3):

@@ -734,6 +734,7 @@ def run_dc(ckt, glVar, device, param, start, stop, num):
     x = RefDC(ckt, idx, opt).get_guess()
     X = np.zeros((num, idx.dimension))
     iters = np.zeros(num, dtype=int)
+    resv = np.zeros(num)
     for i, value in enumerate(sweep):
         setattr(dev, param, value)
         dev.process_params()
@@ -743,7 +744,8 @@ def run_dc(ckt, glVar, device, param, start, stop, num):
         x, res, it = solve(x, sV, dc.helpers)
         X[i] = x
         iters[i] = it
-    return dict(sweep=sweep, X=X, iters=iters, idx=idx)
+        resv[i] = res
+    return dict(sweep=sweep, X=X, iters=iters, res=resv, idx=idx)
 
 
 def run_tran(ckt, glVar, tstop, tstep, im='trap', idx=None, max_samples=None,

@@ -104,3 +104,117 @@ def test_diode_thermal_operating_point_self_consistent():
         ckt2, _ = S.load_circuit(path)
         r2 = R.run_op(ckt2, glVar)
     assert abs(r2['x'][r2['idx'].name_to_row()['3']] - v3) < 1e-6
+
+
+# ---- Gummel-Poon: bjt_t / svbjt_t -------------------------------------------
+BJT_KW = [dict(bf=200., vaf=100., ikf=10e-3, rb=1e3),
+          dict(isat=5e-17, bf=147., vaf=80., ikf=4.3e-3, ise=8e-18, ne=1.233,
+               br=1.9, var=11., ikr=6e-4, isc=5e-16, nc=1.08, re=12.,
+               rb=1200., rbm=200., rc=25., cje=58e-15, vje=0.83, mje=0.35,
+               cjc=133e-15, vjc=0.6, mjc=0.44, xcjc=0.8, fc=0.85, tf=60e-12,
+               xtf=48., itf=3e-2, vtf=2., tr=10e-9, eg=1.16, xti=3.,
+               xtb=1.6),
+          dict(type='pnp', bf=49., xtb=1.5, cjs=1e-13, iss=2e-14,
+               cje=54e-15)]
+
+
+def bjt_pair(dev, dT, nterm, **kw):
+    nodes = [1, 2, 3, 4][:nterm]
+    dt = S.make_element(dev + '_t', nodes + [9, 0], **kw)
+    d = S.make_element(dev, nodes, temp=glVar.temp + dT, **kw)
+    return dt, d
+
+
+def bjt_xin(elem, n, rng, sv):
+    nx = len(elem.controlPorts)
+    x = rng.uniform(-1., 1., size=(nx, n))
+    if sv:
+        x[0] = rng.uniform(-50., 400., n)
+        x[1] = rng.uniform(-50., 50., n)
+    else:
+        x[0] = rng.uniform(-1., 0.85, n)
+        x[1] = rng.uniform(-5., 0.85, n)
+    return x
+
+
+def test_bjt_thermal_equals_isothermal_at_port_temperature():
+    rng = np.random.default_rng(5)
+    for dev in ('bjt', 'svbjt'):
+        for kw in BJT_KW:
+            for nterm in (3, 4):
+                for dT in (0., 41.):
+                    dt, d = bjt_pair(dev, dT, nterm, **kw)
+                    assert len(dt.controlPorts) == len(d.controlPorts) + 1
+                    x = bjt_xin(d, 256, rng, dev == 'svbjt')
+                    xt = np.vstack([x, np.full((1, x.shape[1]), dT)])
+                    ot, jt = device_eval(dt, xt, True)
+                    oi, ji = device_eval(d, x, True)
+                    ncs = len(d.csOutPorts)
+                    assert ot.shape[0] == oi.shape[0] + 1
+                    assert np.allclose(ot[:ncs], oi[:ncs], rtol=1e-11,
+                                       atol=1e-300)
+                    assert np.allclose(ot[ncs + 1:], oi[ncs:], rtol=1e-11,
+                                       atol=1e-300)
+                    # power output = the device's own power() of the currents
+                    pw = np.array([d.power(x[:, k], oi[:ncs, k])
+                                   for k in range(x.shape[1])])
+                    assert np.allclose(ot[ncs], pw, rtol=1e-10, atol=1e-300)
+                    assert np.allclose(jt[:ncs, :-1], ji[:ncs], rtol=1e-10,
+                                       atol=1e-300)
+
+
+def test_bjt_temperature_derivative_matches_finite_difference():
+    rng = np.random.default_rng(6)
+    for dev in ('bjt', 'svbjt'):
+        dt, d = bjt_pair(dev, 0., 4, **BJT_KW[1])
+        x = bjt_xin(d, 64, rng, dev == 'svbjt')
+        if dev == 'svbjt':
+            x[0] = rng.uniform(-5., 40., 64)
+            x[1] = rng.uniform(-50., 20., 64)
+        T0, h = 30., 1e-3
+        xt = np.vstack([x, np.full((1, 64), T0)])
+        e = np.zeros_like(xt)
+        e[-1] = h
+        o, j = device_eval(dt, xt, True)
+        op, _ = device_eval(dt, xt + e, False)
+        om, _ = device_eval(dt, xt - e, False)
+        fd = (op - om) / (2. * h)
+        scale = np.abs(j[:, -1]).max(axis=1, keepdims=True)
+        assert np.all(np.abs(fd - j[:, -1])
+                      <= 2e-6 * np.abs(j[:, -1]) + 1e-8 * scale)
+
+
+def test_npn_thermal_dc_sweep_kat():
+    """doc/examples/examples.rst:122-165: electro-thermal svbjt_t DC sweep --
+    system dimension 11, "Average iterations: 5" (dc.py:208 divides two ints
+    under Python 2: 295 // 50), "Average residual: 0.0114478106429".  The
+    oracle reproduces the residual to 8 digits (release 0.4.1 of the docs vs.
+    the current sources), which pins svbjt_t: SVJunction.set_temp_vars in
+    dual arithmetic, the power output and the thermal port stamps."""
+    import json
+    import os
+    import tempfile
+    with open(os.path.join(S.HERE, 'golden', 'reference_kat.json')) as f:
+        k = json.load(f)['npn_thermal_dc']
+    deck = open(S.net('npn_thermal.net')).read()
+    assert '.options temp=25' in deck
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, 'npn_thermal_doc.net')
+        open(path, 'w').write(deck.replace('.options temp=25', ''))
+        ckt, queue = S.load_circuit(path)
+        an = [a for a in queue if a.anType == 'dc'][0]
+        r = R.run_dc(ckt, glVar, an.device, an.param, an.start, an.stop,
+                     an.num)
+    assert an.num == k['points']
+    assert r['idx'].dimension == k['dimension']
+    assert int(r['iters'].sum()) // an.num \
+        == k['average_iterations_py2_integer_division']
+    assert abs(r['res'].mean() - k['average_residual']) \
+        < 1e-7 * k['average_residual']
+    rows = r['idx'].name_to_row()
+    X = r['X']
+    # self-heating: T rise = 100 K/W * dissipated power, grows with the bias
+    t1 = X[:, rows['t1']]
+    assert t1[-1] > t1[0] and 0.5 < t1[-1] < 20.
+    ic = (X[:, rows['10']] - X[:, rows['1']]) / 1e3
+    assert np.all(np.diff(ic) > -1e-9) and 5e-3 < ic[-1] < 12e-3

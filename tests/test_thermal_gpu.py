@@ -74,3 +74,41 @@ def test_tran_self_heating(lib):
     # the junction really heats up (tens of degrees) and cools down again
     dT = wave[:, rows['1000']]
     assert dT.max() > 5. and dT[-1] < dT.max()
+
+
+# ---- Gummel-Poon: bjt_t / svbjt_t -------------------------------------------
+from tests.test_thermal_cpu import BJT_KW, bjt_pair, bjt_xin   # noqa: E402
+
+
+@pytest.mark.parametrize('dev', ['bjt', 'svbjt'])
+def test_bjt_t_kernel(lib, dev):
+    rng = np.random.default_rng(21)
+    for kw in BJT_KW:
+        for nterm in (3, 4):
+            dt, d = bjt_pair(dev, 0., nterm, **kw)
+            x = bjt_xin(d, 1024, rng, dev == 'svbjt')
+            if dev == 'svbjt':
+                x[0] = rng.uniform(-20., 45., 1024)
+                x[1] = rng.uniform(-50., 30., 1024)
+            xt = np.vstack([x, rng.uniform(-40., 120., (1, 1024))])
+            if kw.get('rb'):
+                xt[2, :8] = 0.          # ib = 0: |x| derivative convention
+            check(lib, dt, xt, jtol=1e-7)
+
+
+def test_npn_thermal_dc_sweep(lib):
+    """`.analysis dc` of test/npn_thermal.net on the device engine against
+    the oracle (which reproduces the documented run, test_thermal_cpu)."""
+    ckt, queue = S.load_circuit(S.net('npn_thermal.net'))
+    an = [a for a in queue if a.anType == 'dc'][0]
+    ckt.saveReqList = []
+    ckt.plotReqList = []
+    an.run(ckt)
+    assert ckt.nD_dimension == 11
+    got = np.array([t.dC_v for t in ckt.nD_termList]).T
+    ckt2, _ = S.load_circuit(S.net('npn_thermal.net'))
+    ref = R.run_dc(ckt2, glVar, an.device, an.param, an.start, an.stop,
+                   an.num)
+    err = np.abs(got - ref['X'])
+    assert np.all(err < 1e-9 * np.abs(ref['X']) + 1e-12), err.max()
+    assert np.max(np.abs(an.iterations - ref['iters'])) <= 1
