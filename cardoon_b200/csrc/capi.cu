@@ -53,6 +53,7 @@ extern "C" int cdn_model_nparams(int model_id) {
     case CDN_MODEL_MEMR: return NP_MEMR;
     case CDN_MODEL_DIODE_T: return NP_DIODE_T;
     case CDN_MODEL_BJT_T: case CDN_MODEL_SVBJT_T: return NP_BJT_T;
+    case CDN_MODEL_MESFETC_T: return NP_MESFETC_T;
     default: return -1;
     }
 }

@@ -319,7 +319,7 @@ __device__ __forceinline__ void eval_model(const cdn_group_dev& G, const PV& p, 
     sink.out = w.out + G.out_off; sink.jac = w.jac + G.jac_off;
     sink.ld = G.n; sink.i = i; sink.nxin = G.nxin;
     sink.ndel = 0;
-    if (MODEL == CDN_MODEL_MESFETC && nhist > 0 && G.ndelay > 0) {
+    if ((MODEL == CDN_MODEL_MESFETC || MODEL == CDN_MODEL_MESFETC_T) && nhist > 0 && G.ndelay > 0) {
         // delayed copies of control voltages (nodalSP.py:860-875)
         sink.ndel = G.ndelay;
 #pragma unroll
@@ -340,6 +340,7 @@ __device__ __forceinline__ void eval_model(const cdn_group_dev& G, const PV& p, 
     else if (MODEL == CDN_MODEL_DIODE_T) diode_t_eval(p, G.flags, v, sink);
     else if (MODEL == CDN_MODEL_BJT_T) bjt_t_eval<P, false>(p, G.flags, v, sink);
     else if (MODEL == CDN_MODEL_SVBJT_T) bjt_t_eval<P, true>(p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_MESFETC_T) mesfetc_t_eval(p, G.flags, v, sink);
 }
 
 #define CDN_MS(m) (1 << (m))
@@ -384,6 +385,10 @@ __device__ __noinline__ void eval_one(const cdn_group_dev& G, int b, int i, cons
     case CDN_MODEL_SVBJT_T:
         if (CDN_HAS(MS, CDN_MODEL_SVBJT_T))
             eval_model<CDN_MODEL_SVBJT_T, DERIV ? 5 : 0>(G, p, i, x, w, 0, h, 0);
+        break;
+    case CDN_MODEL_MESFETC_T:
+        if (CDN_HAS(MS, CDN_MODEL_MESFETC_T))
+            eval_model<CDN_MODEL_MESFETC_T, DERIV ? 5 : 0>(G, p, i, x, w, nhist, h, head);
         break;
     case CDN_MODEL_MESFETC:
         if (CDN_HAS(MS, CDN_MODEL_MESFETC))

@@ -7,7 +7,6 @@
 #include "models/mosext.cuh"
 #include "models/bsim3.cuh"
 #include "models/ekv.cuh"
-#include "models/mesfetc.cuh"
 #include "models/exprvm.cuh"
 
 #define CDN_MAX_XIN 5
@@ -37,7 +36,7 @@ __host__ __device__ inline int model_lanes(int model) {
     switch (model) {
     case CDN_MODEL_DIODE: return 1;
     case CDN_MODEL_DIODE_T: return 2;
-    case CDN_MODEL_BJT_T: case CDN_MODEL_SVBJT_T: return 5;
+    case CDN_MODEL_BJT_T: case CDN_MODEL_SVBJT_T: case CDN_MODEL_MESFETC_T: return 5;
     case CDN_MODEL_BSIM3: case CDN_MODEL_EKV: return 3;
     case CDN_MODEL_MEMR: return 2;
     default: return 4;

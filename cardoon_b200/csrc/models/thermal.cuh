@@ -12,6 +12,7 @@
 #pragma once
 #include "diode.cuh"
 #include "bjt.cuh"
+#include "mesfetc.cuh"
 
 #define CDN_CONST_K 1.3806488e-23        // globalVars.py:26-39
 #define CDN_CONST_Q 1.602176565e-19
@@ -168,4 +169,40 @@ CDN_HD void bjt_t_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
         else if (k < n) out.put(k + 1, buf.o[k]);
     }
     out.put(ncur, pout);
+}
+
+// mesfetc_t: in [vgs, vgd, dT, vgs(t-tau), vgd(t-tau)] (the thermal port sits
+// before the delayed copies, autoThermal.py:114-116); out [igs, igd, ids,
+// power], q [qgs, qgd].  set_temp_vars: mesfetc.py:160-189; power :233-242.
+template <int P, class S>
+CDN_HD void mesfetc_t_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
+    typedef Dual<P> D;
+    DualRec<P, NP_MESFETC> rec;
+#pragma unroll
+    for (int k = 0; k < NP_MESFETC; ++k) rec.r[k] = D(p[k]);
+    const double temp_amb = p[P_MESFETC_T_temp_amb];
+    const TempState<P> t = temp_state(v[2], temp_amb, p[P_MESFETC_T_Tnomabs],
+                                      p[P_MESFETC_T_egapn], p[P_MESFETC_T_eg0]);
+    junction_tempvars<false>(p.sub(P_MESFETC_T_rawgs_isat), t, (flags & F_MESFETC_CGS0) != 0, rec,
+                             P_MESFETC_diogs_t_is);
+    junction_tempvars<false>(p.sub(P_MESFETC_T_rawgd_isat), t, (flags & F_MESFETC_CGD0) != 0, rec,
+                             P_MESFETC_diogd_t_is);
+    const D delta_T = (v[2] + temp_amb) - p[P_MESFETC_T_tnom];
+    rec.r[P_MESFETC_k6] = p[P_MESFETC_T_nr] * t.vt;
+    rec.r[P_MESFETC_Vt0] = p[P_MESFETC_T_vt0] * (1. + (delta_T * p[P_MESFETC_T_avt0])
+                                               + (delta_T * delta_T * p[P_MESFETC_T_bvt0]));
+    const double tbet = p[P_MESFETC_T_tbet], tm = p[P_MESFETC_T_tm], tme = p[P_MESFETC_T_tme];
+    if (tbet != 0.)          // beta * 1.01 ** (delta_T * tbet)
+        rec.r[P_MESFETC_Beta] = p[P_MESFETC_T_beta] * exp((delta_T * tbet) * 0.009950330853168083);
+    if (tme * tm != 0.)
+        rec.r[P_MESFETC_idsFac] = dpow(1. + delta_T * tm, tme);
+    const D v1[4] = {v[0], v[1], v[3], v[4]};
+    BufSink<P> buf;
+    mesfetc_eval(rec, flags, v1, buf);
+    const D pout = (v[0] - v[1]) * buf.o[2] + v[0] * buf.o[0] + v[1] * buf.o[1];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out.put(k, buf.o[k]);
+    out.put(3, pout);
+    out.put(4, buf.o[3]);
+    out.put(5, buf.o[4]);
 }

@@ -141,6 +141,19 @@ class Device(ad.CudaModel, cir.Element):
         return flags, np.concatenate((head, self.diogs.pack(),
                                       self.diogd.pack()))
 
+    def cuda_pack_thermal(self):
+        """mesfetc_t record (param_layout.MESFETC_T): base record with
+        placeholders at ambient + raw inputs of set_temp_vars
+        (reference mesfetc.py:160-189)."""
+        from ..globalVars import glVar
+        self.set_temp_vars(glVar.temp)
+        flags, base = Device.cuda_pack(self)
+        extra = [glVar.temp, self.Tnomabs, self.egapn, self.eg0, self.tnom,
+                 self.nr, self.vt0, self.avt0, self.bvt0, self.beta,
+                 float(self.tbet), self.tm, self.tme]
+        return flags, np.concatenate((base, extra, self.diogs.pack_raw(),
+                                      self.diogd.pack_raw()))
+
     def power(self, vPort, currV):
         vds = vPort[0] - vPort[1]
         return vds * currV[2] + vPort[0] * currV[0] + vPort[1] * currV[1]

@@ -21,7 +21,8 @@ def _junc(prefix):
 
 
 MODEL_IDS = dict(diode=0, bjt=1, svbjt=2, bsim3=3, ekv=4, mesfetc=5,
-                 memr=6, svdiode=7, diode_t=8, bjt_t=9, svbjt_t=10)
+                 memr=6, svdiode=7, diode_t=8, bjt_t=9, svbjt_t=10,
+                 mesfetc_t=11)
 
 # raw (temperature-independent) junction record of the electro-thermal
 # variants: the inputs of Junction.set_temp_vars (reference diode.py:53-72);
@@ -92,6 +93,10 @@ EKV_FLAGS = MOSEXT_FLAGS + ['SIMPLE']
 MESFETC = ['area', 'ib0', 'vbd', 'k6', 'Beta', 'vds0', 'a0', 'a1', 'a2',
            'a3', 'gama', 'idsFac', 'Vt0'] + _junc('diogs') + _junc('diogd')
 MESFETC_FLAGS = ['CGS0', 'CGD0']
+# mesfetc_t: raw inputs of set_temp_vars (reference mesfetc.py:160-189)
+MESFETC_T = MESFETC + ['temp_amb', 'Tnomabs', 'egapn', 'eg0', 'tnom', 'nr',
+                       'vt0', 'avt0', 'bvt0', 'beta', 'tbet', 'tm', 'tme'] \
+    + _jraw('rawgs') + _jraw('rawgd')
 
 # memristor: c, gyr, then the byte-code of M(q) (see memristor.py)
 MEMR = ['c', 'gyr']
@@ -100,6 +105,7 @@ MEMR_FLAGS = []
 LAYOUTS = dict(diode=(DIODE, DIODE_FLAGS), svdiode=(SVDIODE, SVDIODE_FLAGS),
                diode_t=(DIODE_T, DIODE_FLAGS), bjt_t=(BJT_T, BJT_FLAGS),
                svbjt_t=(BJT_T, BJT_FLAGS),
+               mesfetc_t=(MESFETC_T, MESFETC_FLAGS),
                bjt=(BJT, BJT_FLAGS), svbjt=(BJT, BJT_FLAGS),
                bsim3=(BSIM3, BSIM3_FLAGS), ekv=(EKV, EKV_FLAGS),
                mesfetc=(MESFETC, MESFETC_FLAGS), memr=(MEMR, MEMR_FLAGS))

@@ -704,6 +704,31 @@ def svbjt_power(d, v, i):
     return pout
 
 
+def mesfetc_temp_vars(dev, temp):
+    """mesfetc.py:160-189."""
+    d = _Proxy(dev)
+    Tabs = T_ZERO + temp
+    d.vt = K_BOLTZ * Tabs / Q_ELEC
+    egap_t = dev.eg0 - .000702 * (Tabs * Tabs) / (Tabs + 1108.)
+    args = (Tabs, dev.Tnomabs, d.vt, dev.egapn, egap_t)
+    d.diogs = junction_temp_vars(dev.diogs, *args)
+    d.diogd = junction_temp_vars(dev.diogd, *args)
+    delta_T = temp - dev.tnom
+    d._k6 = dev.nr * d.vt
+    d._Vt0 = dev.vt0 * (1. + (delta_T * dev.avt0)
+                        + (delta_T * delta_T * dev.bvt0))
+    d._Beta = dev.beta * pow(1.01, (delta_T * dev.tbet)) if dev.tbet \
+        else dev.beta
+    d._idsFac = D.power(1. + delta_T * dev.tm, dev.tme) \
+        if dev.tme * dev.tm != 0. else 1.
+    return d
+
+
+def mesfetc_power(d, v, i):
+    """mesfetc.py:233-242."""
+    return (v[0] - v[1]) * i[2] + v[0] * i[0] + v[1] * i[1]
+
+
 _THERMAL = {}       # base devType -> (set_temp_vars, eval_cqs, power)
 
 
@@ -747,6 +772,7 @@ def eval_cqs(dev, v):
 
 _THERMAL['diode'] = (diode_temp_vars, diode_cqs,
                      lambda d, v, i: v[0] * i[0])       # diode.py:310-316
+_THERMAL['mesfetc'] = (mesfetc_temp_vars, mesfetc_cqs, mesfetc_power)
 _THERMAL['bjt'] = (bjt_temp_vars,
                    lambda d, v: extrinsic_bjt_cqs(d, v, bjt_cqs), bjt_power)
 _THERMAL['svbjt'] = (bjt_temp_vars,

@@ -218,3 +218,40 @@ def test_npn_thermal_dc_sweep_kat():
     assert t1[-1] > t1[0] and 0.5 < t1[-1] < 20.
     ic = (X[:, rows['10']] - X[:, rows['1']]) / 1e3
     assert np.all(np.diff(ic) > -1e-9) and 5e-3 < ic[-1] < 12e-3
+
+
+# ---- Curtice MESFET: mesfetc_t ----------------------------------------------
+MES_KW = dict(a0=.016542, a1=.0500214, a2=.02012, a3=-.00806592,
+              gama=2.16505, tau=5e-12, beta=-.0394707, isat=1e-9, vbd=15.,
+              nr=10., ib0=1e-9, cgs0=.52785e-12, cgd0=.087e-12, avt0=1e-3,
+              bvt0=1e-6, tbet=0.3, tm=2e-3, tme=1.5)
+
+
+def test_mesfetc_thermal_equals_isothermal_at_port_temperature():
+    rng = np.random.default_rng(8)
+    for dT in (0., 37.):
+        dt = S.make_element('mesfetc_t', [1, 2, 3, 9, 0], **MES_KW)
+        d = S.make_element('mesfetc', [1, 2, 3], temp=glVar.temp + dT,
+                           **MES_KW)
+        assert dt.nDelays == 2 and len(dt.controlPorts) == 3
+        x = rng.uniform(-1.2, 0.6, size=(4, 256))
+        x[1] = rng.uniform(-4., 0.6, 256)
+        x[3] = x[1] + rng.uniform(-.1, .1, 256)
+        # thermal port sits before the delayed copies (autoThermal.py:114)
+        xt = np.vstack([x[:2], np.full((1, 256), dT), x[2:]])
+        ot, jt = device_eval(dt, xt, True)
+        oi, ji = device_eval(d, x, True)
+        assert np.allclose(ot[:3], oi[:3], rtol=1e-11, atol=1e-300)
+        assert np.allclose(ot[4:], oi[3:], rtol=1e-11, atol=1e-300)
+        pw = np.array([d.power(x[:, k], oi[:3, k]) for k in range(256)])
+        assert np.allclose(ot[3], pw, rtol=1e-10, atol=1e-300)
+    # d/dT against finite differences
+    h = 1e-3
+    e = np.zeros_like(xt)
+    e[2] = h
+    o, j = device_eval(dt, xt, True)
+    fd = (device_eval(dt, xt + e, False)[0]
+          - device_eval(dt, xt - e, False)[0]) / (2. * h)
+    scale = np.abs(j[:, 2]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(fd - j[:, 2]) <= 2e-6 * np.abs(j[:, 2])
+                  + 1e-8 * scale)

@@ -112,3 +112,26 @@ def test_npn_thermal_dc_sweep(lib):
     err = np.abs(got - ref['X'])
     assert np.all(err < 1e-9 * np.abs(ref['X']) + 1e-12), err.max()
     assert np.max(np.abs(an.iterations - ref['iters'])) <= 1
+
+
+# ---- Curtice MESFET: mesfetc_t ----------------------------------------------
+from tests.test_thermal_cpu import MES_KW                      # noqa: E402
+
+
+def test_mesfetc_t_kernel(lib):
+    rng = np.random.default_rng(31)
+    n = 1024
+    dt = S.make_element('mesfetc_t', [1, 2, 3, 9, 0], **MES_KW)
+    x = rng.uniform(-1.2, 0.6, size=(5, n))
+    x[1] = rng.uniform(-4., 0.6, n)
+    x[2] = rng.uniform(-30., 90., n)
+    x[4] = x[1] + rng.uniform(-.1, .1, n)
+    check(lib, dt, x, jtol=1e-7)
+
+
+def test_tran_mesfetc_thermal(lib):
+    """test/mesfetc_thermal.net: delayed control ports next to the thermal
+    port, thermal RC sub-circuit (first 150 samples)."""
+    wave, iters, status, ref, tran = tran_both('mesfetc_thermal.net',
+                                               max_samples=150)
+    check_tran(wave, iters, status, ref)
