@@ -54,6 +54,9 @@ extern "C" int cdn_model_nparams(int model_id) {
     case CDN_MODEL_DIODE_T: return NP_DIODE_T;
     case CDN_MODEL_BJT_T: case CDN_MODEL_SVBJT_T: return NP_BJT_T;
     case CDN_MODEL_MESFETC_T: return NP_MESFETC_T;
+    case CDN_MODEL_SVDIODE: return NP_SVDIODE;
+    case CDN_MODEL_SVDIODE_T: return NP_SVDIODE_T;
+    case CDN_MODEL_RES_T: return NP_RES_T;
     default: return -1;
     }
 }

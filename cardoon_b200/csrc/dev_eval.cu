@@ -42,6 +42,9 @@ CDN_HD void eval_any(int model, const PV& p, unsigned flags, const Dual<P>* v, S
     case CDN_MODEL_BJT_T: bjt_t_eval<P, false>(p, flags, v, sink); break;
     case CDN_MODEL_SVBJT_T: bjt_t_eval<P, true>(p, flags, v, sink); break;
     case CDN_MODEL_MESFETC_T: mesfetc_t_eval(p, flags, v, sink); break;
+    case CDN_MODEL_SVDIODE: svdiode_eval(p, flags, v, sink); break;
+    case CDN_MODEL_SVDIODE_T: svdiode_t_eval(p, flags, v, sink); break;
+    case CDN_MODEL_RES_T: res_t_eval(p, flags, v, sink); break;
     default: break;
     }
 }
@@ -290,6 +293,12 @@ static cudaError_t launch_model(int model, int lanes, long n, unsigned flags,
         return lanes ? LAUNCH(CDN_MODEL_SVBJT_T, 5) : LAUNCH(CDN_MODEL_SVBJT_T, 0);
     case CDN_MODEL_MESFETC_T:
         return lanes ? LAUNCH(CDN_MODEL_MESFETC_T, 5) : LAUNCH(CDN_MODEL_MESFETC_T, 0);
+    case CDN_MODEL_SVDIODE:
+        return lanes ? LAUNCH(CDN_MODEL_SVDIODE, 1) : LAUNCH(CDN_MODEL_SVDIODE, 0);
+    case CDN_MODEL_SVDIODE_T:
+        return lanes ? LAUNCH(CDN_MODEL_SVDIODE_T, 2) : LAUNCH(CDN_MODEL_SVDIODE_T, 0);
+    case CDN_MODEL_RES_T:
+        return lanes ? LAUNCH(CDN_MODEL_RES_T, 2) : LAUNCH(CDN_MODEL_RES_T, 0);
     default:
         return cudaErrorInvalidValue;
     }
@@ -303,7 +312,7 @@ extern "C" int cdn_dev_eval(cdn_ctx* ctx, int model_id, unsigned flags, long n, 
     if (nxin < 1 || nxin > CDN_MAX_XIN) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_dev_eval: bad nxin");
     cudaStream_t st = (cudaStream_t)stream;
     const int lanes = jac ? nxin : 0;
-    if (model_id < 0 || model_id > CDN_MODEL_MESFETC_T || model_id == CDN_MODEL_SVDIODE)
+    if (model_id < 0 || model_id > CDN_MODEL_RES_T)
         return cdn_fail(ctx, CDN_ERR_ARG, "cdn_dev_eval: unknown model id");
     const cudaError_t e = launch_model(model_id, lanes, n, flags, params, ldp, pidx, xin,
                                        out, jac, nxin, st);

@@ -341,6 +341,9 @@ __device__ __forceinline__ void eval_model(const cdn_group_dev& G, const PV& p, 
     else if (MODEL == CDN_MODEL_BJT_T) bjt_t_eval<P, false>(p, G.flags, v, sink);
     else if (MODEL == CDN_MODEL_SVBJT_T) bjt_t_eval<P, true>(p, G.flags, v, sink);
     else if (MODEL == CDN_MODEL_MESFETC_T) mesfetc_t_eval(p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_SVDIODE) svdiode_eval(p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_SVDIODE_T) svdiode_t_eval(p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_RES_T) res_t_eval(p, G.flags, v, sink);
 }
 
 #define CDN_MS(m) (1 << (m))
@@ -389,6 +392,18 @@ __device__ __noinline__ void eval_one(const cdn_group_dev& G, int b, int i, cons
     case CDN_MODEL_MESFETC_T:
         if (CDN_HAS(MS, CDN_MODEL_MESFETC_T))
             eval_model<CDN_MODEL_MESFETC_T, DERIV ? 5 : 0>(G, p, i, x, w, nhist, h, head);
+        break;
+    case CDN_MODEL_SVDIODE:
+        if (CDN_HAS(MS, CDN_MODEL_SVDIODE))
+            eval_model<CDN_MODEL_SVDIODE, DERIV ? 1 : 0>(G, p, i, x, w, 0, h, 0);
+        break;
+    case CDN_MODEL_SVDIODE_T:
+        if (CDN_HAS(MS, CDN_MODEL_SVDIODE_T))
+            eval_model<CDN_MODEL_SVDIODE_T, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0);
+        break;
+    case CDN_MODEL_RES_T:
+        if (CDN_HAS(MS, CDN_MODEL_RES_T))
+            eval_model<CDN_MODEL_RES_T, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0);
         break;
     case CDN_MODEL_MESFETC:
         if (CDN_HAS(MS, CDN_MODEL_MESFETC))

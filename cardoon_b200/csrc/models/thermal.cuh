@@ -206,3 +206,37 @@ CDN_HD void mesfetc_t_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out
     out.put(4, buf.o[3]);
     out.put(5, buf.o[4]);
 }
+
+// svdiode_t: in [x, dT]; out [id, gyr*vd, power] (+ [qd]).  svdiode.py:280-295
+// (set_temp_vars), :336-345 (power = id * (gyr vd) / gyr).
+template <int P, class S>
+CDN_HD void svdiode_t_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
+    DualRec<P, NP_SVDIODE> rec;
+#pragma unroll
+    for (int k = 0; k < NP_SVDIODE; ++k) rec.r[k] = Dual<P>(p[k]);
+    const TempState<P> t = temp_state(v[1], p[P_SVDIODE_T_temp_amb], p[P_SVDIODE_T_Tnomabs],
+                                      p[P_SVDIODE_T_egapn], p[P_SVDIODE_T_eg0]);
+    rec.r[P_SVDIODE_vt] = t.vt;
+    junction_tempvars<true>(p.sub(P_SVDIODE_T_jraw_isat), t, (flags & F_SVDIODE_CJ0) != 0, rec,
+                            P_SVDIODE_jtn_t_is);
+    Dual<P> iD, vD, qD;
+    svdiode_core(rec, flags, v[0], iD, vD, qD);
+    out.put(0, iD);
+    out.put(1, vD);
+    out.put(2, iD * vD / p[P_SVDIODE_gyr]);
+    if (flags & F_SVDIODE_QD) out.put(3, qD);
+}
+
+// res_t: in [v, dT]; out [i, power].  resistor.py:107-131: the conductance
+// 1/r (or the sheet-resistance value) divided by 1 + (tc1 + tc2 dT') dT',
+// dT' = temp - tnom.  (The reference's `self.g /= ...` compounds on repeated
+// calls; it is executed once, while the AD tape is recorded, which is what is
+// restated here.)
+template <int P, class S>
+CDN_HD void res_t_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
+    const Dual<P> deltaT = (v[1] + p[P_RES_T_temp_amb]) - p[P_RES_T_tnom];
+    const Dual<P> g = p[P_RES_T_g0] / (1. + (p[P_RES_T_tc1] + p[P_RES_T_tc2] * deltaT) * deltaT);
+    const Dual<P> i = g * v[0];
+    out.put(0, i);
+    out.put(1, v[0] * i);
+}

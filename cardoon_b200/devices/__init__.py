@@ -10,7 +10,8 @@ import importlib
 
 from . import autoThermal
 
-netElemList = ['linear', 'memristor', 'diode', 'bjt', 'svbjt', 'mosEKV',
+netElemList = ['linear', 'memristor', 'diode', 'svdiode', 'bjt', 'svbjt',
+               'mosEKV',
                'mosBSIM3v3', 'mesfetc', 'tlinpy4']
 
 devClass = {}
@@ -18,7 +19,9 @@ devClass = {}
 
 def add_device(device):
     devClass[device.devType] = device
-    if device.makeAutoThermal and device.isNonlinear:
+    # (reference devices/__init__.py:59-63: also for the linear resistor,
+    # whose electro-thermal version is nonlinear)
+    if device.makeAutoThermal:
         tDevice = autoThermal.thermal_device(device)
         devClass[tDevice.devType] = tDevice
 

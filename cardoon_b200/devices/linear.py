@@ -15,9 +15,10 @@ import numpy as np
 
 from ..globalVars import const, glVar
 from .. import circuit as cir
+from . import cudadev as ad
 
 
-class Resistor(cir.Element):
+class Resistor(ad.CudaModel, cir.Element):
     """
     Resistor
     --------
@@ -25,9 +26,14 @@ class Resistor(cir.Element):
     Netlist example::
 
         res:r1 1 2 r=1e3 tc1=10e-3
+
+    ``res_t`` (electro-thermal, autoThermal) is nonlinear: its conductance
+    follows the thermal port (kernel ``res_t_eval``, csrc/models/thermal.cuh).
     """
     category = "Basic components"
     devType = "res"
+    cudaModel = 'res'
+    makeAutoThermal = True
     numTerms = 2
     csOutPorts = [(0, 1)]
     noisePorts = [(0, 1)]
@@ -63,6 +69,17 @@ class Resistor(cir.Element):
         self.g /= (1. + (self.tc1 + self.tc2 * deltaT) * deltaT)
         self._St = 4. * const.k * (temp + const.T0) * self.g
         self.linearVCCS = [((0, 1), (0, 1), self.g)]
+
+    def cuda_pack_thermal(self):
+        """res_t record (param_layout.RES_T); reference resistor.py:107-131:
+        process_params(thermal=True) leaves ``g`` uncorrected and the taped
+        eval_cqs divides it once by the temperature polynomial."""
+        from ..globalVars import glVar
+        return 0, np.array([self.g, self.tnom, self.tc1, self.tc2,
+                            glVar.temp])
+
+    def power(self, vPort, ioutV):
+        return vPort[0] * ioutV[0]
 
     def get_noise(self, f):
         return np.array([self._St])

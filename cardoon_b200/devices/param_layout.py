@@ -22,7 +22,7 @@ def _junc(prefix):
 
 MODEL_IDS = dict(diode=0, bjt=1, svbjt=2, bsim3=3, ekv=4, mesfetc=5,
                  memr=6, svdiode=7, diode_t=8, bjt_t=9, svbjt_t=10,
-                 mesfetc_t=11)
+                 mesfetc_t=11, svdiode_t=12, res_t=13)
 
 # raw (temperature-independent) junction record of the electro-thermal
 # variants: the inputs of Junction.set_temp_vars (reference diode.py:53-72);
@@ -40,6 +40,12 @@ DIODE_T = DIODE + ['temp_amb', 'Tnomabs', 'egapn', 'eg0'] \
 
 SVDIODE = ['area', 'bv', 'ibv', 'n', 'vt', 'tt', 'gyr'] + _junc('jtn')
 SVDIODE_FLAGS = ['CJ0', 'TT', 'BV', 'QD']
+SVDIODE_T = SVDIODE + ['temp_amb', 'Tnomabs', 'egapn', 'eg0'] \
+    + ['jraw_' + n for n in JRAW]
+
+# res_t (reference resistor.py:107-131): conductance before the temperature
+# correction and the coefficients of the correction
+RES_T = ['g0', 'tnom', 'tc1', 'tc2', 'temp_amb']
 
 BJT = (['typef', 'area', 'bf_t', 'br_t', 'ikf', 'ikr', 'var', 'vaf', 'rb',
         'rbm', 'ck1', 'ck2', 'tf', 'xtf', 'vtf', 'itf', 'tr', 'xcjc', 'gyr']
@@ -106,6 +112,7 @@ LAYOUTS = dict(diode=(DIODE, DIODE_FLAGS), svdiode=(SVDIODE, SVDIODE_FLAGS),
                diode_t=(DIODE_T, DIODE_FLAGS), bjt_t=(BJT_T, BJT_FLAGS),
                svbjt_t=(BJT_T, BJT_FLAGS),
                mesfetc_t=(MESFETC_T, MESFETC_FLAGS),
+               svdiode_t=(SVDIODE_T, SVDIODE_FLAGS), res_t=(RES_T, []),
                bjt=(BJT, BJT_FLAGS), svbjt=(BJT, BJT_FLAGS),
                bsim3=(BSIM3, BSIM3_FLAGS), ekv=(EKV, EKV_FLAGS),
                mesfetc=(MESFETC, MESFETC_FLAGS), memr=(MEMR, MEMR_FLAGS))

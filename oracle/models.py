@@ -63,6 +63,21 @@ def diode_cqs(dev, v):
     return [iD], []
 
 
+# ---- state-variable diode (svdiode.py:300-333) ------------------------------
+def svdiode_cqs(dev, v):
+    iD, vD = svjunction_idvd(dev.jtn, v[0])
+    qD = junction_qd(dev.jtn, vD, guarded=False) if dev.cj0 != 0. else 0.
+    if dev.tt != 0.:
+        qD = qD + dev.tt * iD
+    if dev.bv < np.inf:
+        iD = iD - dev.ibv * safe_exp(-(vD + dev.bv) / dev.n / dev.vt)
+    iD = iD * dev.area
+    vD = vD * dev_gyr()
+    if dev._qd:
+        return [iD, vD], [qD * dev.area]
+    return [iD, vD], []
+
+
 # ---- Gummel-Poon (bjt.py:485-607) and state-variable GP (svbjt.py:308-435)
 def _gp_core(dev, ibf, ibr, vbe, vbc, vib, sv):
     """Common part once junction currents/voltages are known."""
@@ -704,6 +719,26 @@ def svbjt_power(d, v, i):
     return pout
 
 
+def svdiode_temp_vars(dev, temp):
+    """svdiode.py:280-295."""
+    d = _Proxy(dev)
+    Tabs = temp + T_ZERO
+    d.vt = K_BOLTZ * Tabs / Q_ELEC
+    egap_t = dev.eg0 - .000702 * (Tabs * Tabs) / (Tabs + 1108.)
+    d.jtn = svjunction_temp_vars(dev.jtn, Tabs, dev.Tnomabs, d.vt, dev.egapn,
+                                 egap_t)
+    return d
+
+
+def res_temp_vars(dev, temp):
+    """resistor.py:107-120 as executed once while the tape is recorded:
+    g = g(process_params) / (1 + (tc1 + tc2 dT) dT)."""
+    d = _Proxy(dev)
+    deltaT = temp - dev.tnom
+    d.g = dev.g / (1. + (dev.tc1 + dev.tc2 * deltaT) * deltaT)
+    return d
+
+
 def mesfetc_temp_vars(dev, temp):
     """mesfetc.py:160-189."""
     d = _Proxy(dev)
@@ -751,6 +786,8 @@ def eval_cqs(dev, v):
         return thermal_cqs(dev, v)
     if t == 'diode':
         return diode_cqs(dev, v)
+    if t == 'svdiode':
+        return svdiode_cqs(dev, v)
     if t == 'bjt':
         return extrinsic_bjt_cqs(dev, v, bjt_cqs)
     if t == 'svbjt':
@@ -772,6 +809,10 @@ def eval_cqs(dev, v):
 
 _THERMAL['diode'] = (diode_temp_vars, diode_cqs,
                      lambda d, v, i: v[0] * i[0])       # diode.py:310-316
+_THERMAL['svdiode'] = (svdiode_temp_vars, svdiode_cqs,
+                       lambda d, v, i: i[0] * i[1] / dev_gyr())
+_THERMAL['res'] = (res_temp_vars, lambda d, v: ([d.g * v[0]], []),
+                   lambda d, v, i: v[0] * i[0])           # resistor.py:123-138
 _THERMAL['mesfetc'] = (mesfetc_temp_vars, mesfetc_cqs, mesfetc_power)
 _THERMAL['bjt'] = (bjt_temp_vars,
                    lambda d, v: extrinsic_bjt_cqs(d, v, bjt_cqs), bjt_power)

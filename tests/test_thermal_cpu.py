@@ -255,3 +255,48 @@ def test_mesfetc_thermal_equals_isothermal_at_port_temperature():
     scale = np.abs(j[:, 2]).max(axis=1, keepdims=True)
     assert np.all(np.abs(fd - j[:, 2]) <= 2e-6 * np.abs(j[:, 2])
                   + 1e-8 * scale)
+
+
+# ---- svdiode, svdiode_t, res_t -----------------------------------------------
+def test_svdiode_behaves_like_diode():
+    """svdiode.py docstring: 'Externally it behaves exactly like the regular
+    diode device' -- same current, voltage and charge as `diode` once the
+    state variable is mapped to the junction voltage."""
+    kw = dict(isat=2e-14, n=1.2, cj0=3e-12, tt=1e-9, m=0.4, area=2.)
+    sv = S.make_element('svdiode', [1, 0], **kw)
+    d = S.make_element('diode', [1, 0], **kw)
+    x = np.linspace(-3., 60., 300)[None, :]
+    osv, jsv = device_eval(sv, x, True)
+    vd = osv[1] / 1e-3                                  # gyr = 1e-3
+    od, jd = device_eval(d, vd[None, :], True)
+    assert np.allclose(osv[0], od[0], rtol=1e-9, atol=1e-22)
+    assert np.allclose(osv[2], od[1], rtol=1e-9, atol=1e-30)
+    # chain rule: di/dvd = (di/dx) / (dvd/dx)
+    assert np.allclose(jsv[0, 0] / (jsv[1, 0] / 1e-3), jd[0, 0], rtol=1e-8)
+
+
+def test_svdiode_and_resistor_thermal_equal_isothermal():
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-5., 45., (1, 256))
+    for dT in (0., 55.):
+        kw = dict(cj0=2e-12, tt=1e-9, bv=7., rs=4.)
+        dt = S.make_element('svdiode_t', [1, 0, 9, 0], **kw)
+        d = S.make_element('svdiode', [1, 0], temp=glVar.temp + dT, **kw)
+        xt = np.vstack([x, np.full((1, 256), dT)])
+        ot, jt = device_eval(dt, xt, True)
+        oi, ji = device_eval(d, x, True)
+        assert np.allclose(ot[:2], oi[:2], rtol=1e-11, atol=1e-300)
+        assert np.allclose(ot[3], oi[2], rtol=1e-11, atol=1e-300)
+        assert np.allclose(ot[2], oi[0] * oi[1] / 1e-3, rtol=1e-11)
+        # resistor: i = v / (r (1 + (tc1 + tc2 dT') dT')), dT' = temp - tnom
+        rt = S.make_element('res_t', [1, 0, 9, 0], r=330., tc1=4e-3,
+                            tc2=1e-5, tnom=20.)
+        assert rt.isNonlinear and len(rt.controlPorts) == 2
+        v = rng.uniform(-5., 5., (1, 256))
+        o, j = device_eval(rt, np.vstack([v, np.full((1, 256), dT)]), True)
+        d_ = glVar.temp + dT - 20.
+        g = 1. / 330. / (1. + (4e-3 + 1e-5 * d_) * d_)
+        assert np.allclose(o[0], g * v[0], rtol=1e-13)
+        assert np.allclose(o[1], g * v[0] * v[0], rtol=1e-13)
+        dg = -g * (4e-3 + 2e-5 * d_) / (1. + (4e-3 + 1e-5 * d_) * d_)
+        assert np.allclose(j[0, 1], dg * v[0], rtol=1e-10)

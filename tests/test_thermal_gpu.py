@@ -135,3 +135,31 @@ def test_tran_mesfetc_thermal(lib):
     wave, iters, status, ref, tran = tran_both('mesfetc_thermal.net',
                                                max_samples=150)
     check_tran(wave, iters, status, ref)
+
+
+# ---- svdiode, svdiode_t, res_t ------------------------------------------------
+def test_svdiode_and_res_t_kernels(lib):
+    rng = np.random.default_rng(41)
+    n = 1024
+    x = rng.uniform(-8., 60., (1, n))
+    for kw in (dict(), dict(cj0=2e-12, tt=1e-9, bv=7., rs=4.),
+               dict(isat=1e-15, n=1.5, area=3., cj0=1e-12, m=0.33, fc=0.6)):
+        check(lib, S.make_element('svdiode', [1, 0], **kw), x)
+        xt = np.vstack([x, rng.uniform(-40., 120., (1, n))])
+        check(lib, S.make_element('svdiode_t', [1, 0, 9, 0], **kw), xt)
+    rt = S.make_element('res_t', [1, 0, 9, 0], r=330., tc1=4e-3, tc2=1e-5,
+                        tnom=20.)
+    check(lib, rt, np.vstack([rng.uniform(-5., 5., (1, n)),
+                              rng.uniform(-40., 120., (1, n))]))
+
+
+def test_op_thermal_mix(lib):
+    ckt, queue = S.load_circuit(S.net('thermal_mix.net'))
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    x, res, it = solve(dc.get_guess(), dc.get_source(), dc.convergence_helpers)
+    ref = R.run_op(ckt, glVar)
+    assert abs(it - ref['iterations']) <= 1
+    check_op(x, ref['x'])
+    rows = ref['idx'].name_to_row()
+    assert 5. < x[rows['th']] < 80.          # tens of degrees of self-heating
