@@ -84,6 +84,9 @@ def _declare(dll):
     dll.cdn_model_nparams.argtypes = [C.c_int]
     dll.cdn_dev_eval.argtypes = [_vp, C.c_int, C.c_uint, C.c_long, C.c_int,
                                  _vp, C.c_long, _vp, _vp, _vp, _vp, _vp]
+    dll.cdn_ac_solve.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp]
     dll.cdn_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
     dll.cdn_set_tuning.argtypes = [C.c_int, C.c_int]
     dll.cdn_plan_create.argtypes = [_vp, C.POINTER(CircuitHost),
@@ -201,6 +204,44 @@ class Lib(object):
         self.torch.cuda.synchronize(self.device)
         return (out.cpu().numpy(),
                 jac.cpu().numpy() if jac is not None else None)
+
+    def ac_solve(self, G, Cm, delayed, freqs, sVec):
+        """x[nf, n] (complex) with Y(w) x = s for every frequency;
+        Y = G + j w C + sum (g + j w c) exp(-j w tau) over the `delayed`
+        entries (row, col, g, c, tau).  numpy in / numpy out."""
+        torch = self.torch
+        n = G.shape[0]
+        freqs = np.ascontiguousarray(freqs, dtype=np.float64)
+        nf = freqs.shape[0]
+        ndel = len(delayed)
+        d = np.array(delayed, dtype=np.float64).reshape(ndel, 5)
+        s2 = np.ascontiguousarray(
+            np.stack([sVec.real, sVec.imag], axis=1), dtype=np.float64)
+        ti = lambda a: torch.as_tensor(
+            np.ascontiguousarray(a, dtype=np.int32), device=self.device)
+        work = self.empty((nf * n * n * 2,)) if n > 56 else None
+        x = self.empty((nf, n, 2))
+        status = self.zeros((1,), torch.int32)
+        args = [self.dev(np.ascontiguousarray(G, dtype=np.float64)),
+                self.dev(np.ascontiguousarray(Cm, dtype=np.float64)),
+                ti(d[:, 0]), ti(d[:, 1]), self.dev(d[:, 2].copy()),
+                self.dev(d[:, 3].copy()), self.dev(d[:, 4].copy()),
+                self.dev(freqs), self.dev(s2)]
+        rc = self.dll.cdn_ac_solve(
+            self.ctx, int(n), int(nf), self.ptr(args[0]), self.ptr(args[1]),
+            int(ndel), self.ptr(args[2]), self.ptr(args[3]),
+            self.ptr(args[4]), self.ptr(args[5]), self.ptr(args[6]),
+            self.ptr(args[7]), self.ptr(args[8]), self.ptr(work),
+            self.ptr(x), self.ptr(status), self.stream())
+        self.check(rc)
+        torch.cuda.synchronize(self.device)
+        bad = int(status.item())
+        if bad:
+            raise np.linalg.LinAlgError(
+                'AC: singular matrix at frequency {0} Hz'.format(
+                    freqs[bad - 1]))
+        xh = x.cpu().numpy()
+        return xh[:, :, 0] + 1j * xh[:, :, 1]
 
     def fp64_peak(self):
         v = C.c_double()

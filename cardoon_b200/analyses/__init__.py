@@ -3,9 +3,9 @@ Analysis registry (``anClass``) and output requests.
 
 Mirror of the reference's cardoon/analyses/__init__.py (:21-70).  This
 back-end provides the two analyses on the Newton hot path, ``op`` and
-``tran`` and the ``dc`` sweep; the other reference analyses (``ac``, ``testdev``) are
-registered as placeholders that report they are not available, so netlists
-that request them still load and run the rest.
+``tran``, the ``dc`` sweep and the ``ac`` sweep; ``testdev`` is registered as
+a placeholder that reports it is not available, so netlists that request it
+still load and run the rest.
 """
 from .analysis import AnalysisError
 from ..paramset import ParamSet
@@ -57,11 +57,11 @@ class _AnyParams(dict):
 
 
 anClass = {}
-validReqTypes = ['tran', 'dc', 'ac_mag', 'ac_phase', 'ac_dB']
+validReqTypes = ['tran', 'dc', 'ac', 'ac_mag', 'ac_phase', 'ac_dB']
 
-from . import op, tran, dc      # noqa: E402
+from . import op, tran, dc, ac      # noqa: E402
 
-for _module in (op, tran, dc):
+for _module in (op, tran, dc, ac):
     anClass[_module.aClass.anType] = _module.aClass
-for _name in ('ac', 'testdev'):
+for _name in ('testdev',):
     anClass[_name] = _placeholder(_name, _AnyParams())

@@ -118,6 +118,104 @@ def process_nodal_element(elem, ckt):
     ckt.__dict__.pop('_cuda_topology', None)
 
 
+def _set_quad(M, row1, col1, row2, col2, g):
+    """nodal.py:24-41."""
+    if col1 >= 0:
+        if row1 >= 0:
+            M[row1, col1] += g
+        if row2 >= 0:
+            M[row2, col1] -= g
+    if col2 >= 0:
+        if row1 >= 0:
+            M[row1, col2] -= g
+        if row2 >= 0:
+            M[row2, col2] += g
+
+
+def _jac_entries(prow, nrow, pcol, ncol, Jac):
+    """(row, col, value, jacobian column) of T_out Jac T_in, in the order of
+    set_Jac (nodal.py:66-80)."""
+    out = []
+    for i1, i in prow:
+        for j1, j in pcol:
+            out.append((i, j, Jac[i1, j1], j1))
+        for j1, j in ncol:
+            out.append((i, j, -Jac[i1, j1], j1))
+    for i1, i in nrow:
+        for j1, j in ncol:
+            out.append((i, j, Jac[i1, j1], j1))
+        for j1, j in pcol:
+            out.append((i, j, -Jac[i1, j1], j1))
+    return out
+
+
+def run_AC(ckt, fvec):
+    """Set up and solve the small-signal AC equations (reference
+    nodal.py:286-381).
+
+    ckt: nodal-ready circuit with the operating point saved (``save_OP``);
+    fvec: frequencies, all different from zero.  Results are stored in the
+    terminals as ``aC_V``; returns the matrix (nvars x nfreq).
+
+    The reference assembles and solves ``Y = G + j w C + device Jacobians``
+    once per frequency in Python.  Here the frequency-independent part (linear
+    stamps, dI/dv into G, dQ/dv into C) is assembled once on the host from the
+    device Jacobians at the operating point (one ``cdn_dev_eval`` per
+    element), the columns of delayed control ports go to a triplet list that
+    gets its ``exp(-j w tau)`` factor per frequency, and all frequencies are
+    factored and solved in one launch (``cdn_ac_solve``, one CTA per
+    frequency).
+    """
+    from .._lib import get_lib
+    n = ckt.nD_dimension
+    if ckt.nD_freqDefinedElem:
+        raise NotImplementedError(
+            'AC: frequency-defined elements ({0}) are not supported by this '
+            'back-end'.format(ckt.nD_freqDefinedElem[0].instanceName))
+    G = np.zeros((n, n))
+    Cm = np.zeros((n, n))
+    for elem in ckt.nD_elemList:
+        for vccs in elem.nD_linVCCS:
+            _set_quad(G, *vccs)
+        for vcqs in elem.nD_linVCQS:
+            _set_quad(Cm, *vcqs)
+    delayed = []
+    for elem in ckt.nD_nlinElem:
+        (outV, outJac) = elem.eval_and_deriv(elem.nD_xOP)
+        ncs = len(elem.csOutPorts)
+        first_delayed = outJac.shape[1] - elem.nDelays
+        for rows, M, J in (((elem.nD_cpos, elem.nD_cneg), G, outJac[:ncs]),
+                           ((elem.nD_qpos, elem.nD_qneg), Cm, outJac[ncs:])):
+            if J.shape[0] == 0:
+                continue
+            for i, j, v, j1 in _jac_entries(rows[0], rows[1], elem.nD_vpos,
+                                            elem.nD_vneg, J):
+                if j1 >= first_delayed:
+                    tau = elem.nD_delay[j1 - first_delayed]
+                    delayed.append((i, j, v, 0., tau) if M is G
+                                   else (i, j, 0., v, tau))
+                else:
+                    M[i, j] += v
+    sVec = np.zeros(n, dtype=complex)
+    for source in ckt.nD_sourceFDElem:
+        try:
+            current = source.get_AC()
+        except AttributeError:
+            continue                 # AC routine not implemented: ignored
+        outTerm = source.nD_sourceOut
+        if outTerm[0] >= 0:
+            sVec[outTerm[0]] -= current
+        if outTerm[1] >= 0:
+            sVec[outTerm[1]] += current
+    x = get_lib().ac_solve(G, Cm, delayed, np.asarray(fvec, dtype=float),
+                           sVec)
+    xVec = np.ascontiguousarray(x.T)
+    ckt.nD_ref.aC_V = 0.
+    for k, term in enumerate(ckt.nD_termList):
+        term.aC_V = xVec[k, :]
+    return xVec
+
+
 def get_guess(ckt):
     """Initial guess from the devices' ``vPortGuess`` (nodal.py:723-740):
     only the positive node of each control port is written."""

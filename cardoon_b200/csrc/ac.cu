@@ -1,0 +1,166 @@
+// Small-signal AC sweep: for every frequency f_k solve
+//     Y(w_k) x_k = s,   Y(w) = G + j w C + sum_d (g_d + j w c_d) exp(-j w tau_d)
+// Replaces the per-frequency loop of the reference's run_AC
+// (analyses/nodal.py:286-381: Y[:] = G + jomega*C, set_Jac of every device
+// Jacobian with exp(-jomega*tau) on delayed columns, linalg.solve).
+//
+// Frequencies are independent, so they are the batch dimension: one CTA
+// assembles and factors one Y (dense complex LU with partial pivoting on
+// |re|+|im|, the LAPACK zgetrf pivot rule) and solves for the source vector.
+// G and C already contain the frequency-independent device stamps
+// (dI/dv into G, dQ/dv into C); only delayed control ports are applied per
+// frequency from the triplet list.  Matrices of up to 56x56 live in shared
+// memory, larger ones in the caller's workspace (L2-resident).
+#include "common.cuh"
+
+struct cplx { double re, im; };
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    cplx r; r.re = a.re * b.re - a.im * b.im; r.im = a.re * b.im + a.im * b.re; return r;
+}
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { cplx r; r.re = a.re - b.re; r.im = a.im - b.im; return r; }
+__device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
+    // Smith's algorithm (what the C99 / numpy complex division does)
+    cplx r;
+    if (fabs(b.re) >= fabs(b.im)) {
+        const double t = b.im / b.re, d = b.re + b.im * t;
+        r.re = (a.re + a.im * t) / d; r.im = (a.im - a.re * t) / d;
+    } else {
+        const double t = b.re / b.im, d = b.re * t + b.im;
+        r.re = (a.re * t + a.im) / d; r.im = (a.im * t - a.re) / d;
+    }
+    return r;
+}
+
+#define AC_TPB 256
+#define AC_SMEM_N 56
+
+__global__ void __launch_bounds__(AC_TPB)
+ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __restrict__ C,
+                int ndel, const int* __restrict__ drow, const int* __restrict__ dcol,
+                const double* __restrict__ dg, const double* __restrict__ dc,
+                const double* __restrict__ dtau, const double* __restrict__ freqs,
+                const double* __restrict__ s, cplx* __restrict__ work, cplx* __restrict__ xout,
+                int* __restrict__ status) {
+    extern __shared__ double ac_sm[];
+    __shared__ double red_v[AC_TPB / 32];
+    __shared__ int red_i[AC_TPB / 32];
+    __shared__ int piv;
+    const int tid = threadIdx.x;
+    const bool in_smem = n <= AC_SMEM_N;
+    for (int f = blockIdx.x; f < nf; f += gridDim.x) {
+        cplx* Y = in_smem ? (cplx*)ac_sm : work + (long)f * n * n;
+        cplx* x = xout + (long)f * n;
+        const double w = 6.283185307179586476925287 * freqs[f];      // 2 pi f
+        for (int e = tid; e < n * n; e += AC_TPB) {
+            cplx y; y.re = G[e]; y.im = w * C[e];
+            Y[e] = y;
+        }
+        for (int r = tid; r < n; r += AC_TPB) { cplx v; v.re = s[2 * r]; v.im = s[2 * r + 1]; x[r] = v; }
+        __syncthreads();
+        if (tid == 0) {
+            // delayed control ports: (g + j w c) exp(-j w tau); entries may repeat
+            for (int d = 0; d < ndel; ++d) {
+                double sn, cs;
+                sincos(-w * dtau[d], &sn, &cs);
+                cplx a; a.re = dg[d]; a.im = w * dc[d];
+                cplx ph; ph.re = cs; ph.im = sn;
+                const cplx v = cmul(a, ph);
+                cplx* y = Y + (long)drow[d] * n + dcol[d];
+                y->re += v.re; y->im += v.im;
+            }
+        }
+        __syncthreads();
+        bool singular = false;
+        for (int k = 0; k < n; ++k) {
+            // ---- pivot: first row with the largest |re| + |im| in column k
+            double bv = -1.0; int bi = n;
+            for (int i = k + tid; i < n; i += AC_TPB) {
+                const cplx y = Y[(long)i * n + k];
+                const double a = fabs(y.re) + fabs(y.im);
+                if (a > bv) { bv = a; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int q = 1; q < AC_TPB / 32; ++q)
+                    if (red_v[q] > bv || (red_v[q] == bv && red_i[q] < bi)) { bv = red_v[q]; bi = red_i[q]; }
+                piv = (bv > 0.0) ? bi : -1;
+            }
+            __syncthreads();
+            const int p = piv;
+            if (p < 0) { singular = true; break; }
+            if (p != k) {
+                for (int j = tid; j < n; j += AC_TPB) {
+                    const cplx t = Y[(long)k * n + j];
+                    Y[(long)k * n + j] = Y[(long)p * n + j];
+                    Y[(long)p * n + j] = t;
+                }
+                if (tid == 0) { const cplx t = x[k]; x[k] = x[p]; x[p] = t; }
+                __syncthreads();
+            }
+            // ---- multipliers, right-hand side
+            const cplx ykk = Y[(long)k * n + k];
+            const cplx xk = x[k];
+            for (int i = k + 1 + tid; i < n; i += AC_TPB) {
+                const cplx l = cdiv(Y[(long)i * n + k], ykk);
+                Y[(long)i * n + k] = l;
+                x[i] = csub(x[i], cmul(l, xk));
+            }
+            __syncthreads();
+            // ---- rank-1 update of the trailing block
+            const int m = n - k - 1;
+            for (int e = tid; e < m * m; e += AC_TPB) {
+                const int i = k + 1 + e / m, j = k + 1 + e % m;
+                Y[(long)i * n + j] = csub(Y[(long)i * n + j], cmul(Y[(long)i * n + k], Y[(long)k * n + j]));
+            }
+            __syncthreads();
+        }
+        if (singular) {
+            if (tid == 0) atomicExch(status, f + 1);
+            __syncthreads();
+            continue;
+        }
+        // ---- back substitution
+        for (int k = n - 1; k >= 0; --k) {
+            if (tid == 0) x[k] = cdiv(x[k], Y[(long)k * n + k]);
+            __syncthreads();
+            const cplx xk = x[k];
+            for (int i = tid; i < k; i += AC_TPB) x[i] = csub(x[i], cmul(Y[(long)i * n + k], xk));
+            __syncthreads();
+        }
+    }
+}
+
+// Reference: run_AC (analyses/nodal.py:286-381).  All pointers are device
+// pointers.  G, C: [n*n] row-major; delayed entries (drow, dcol, dg, dc,
+// dtau)[ndel]; freqs[nf]; s[n][2] (re, im); work: nf*n*n complex when
+// n > 56 (else unused); x: [nf][n][2]; status: 0 or 1 + index of a frequency
+// whose matrix is singular.
+extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const double* C, int ndel,
+                            const int* drow, const int* dcol, const double* dg, const double* dc,
+                            const double* dtau, const double* freqs, const double* s, double* work,
+                            double* x, int* status, void* stream) {
+    if (!ctx) return CDN_ERR_ARG;
+    if (n <= 0 || nf <= 0) return CDN_OK;
+    if (!G || !C || !freqs || !s || !x || !status || (ndel > 0 && (!drow || !dcol || !dg || !dc || !dtau)))
+        return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: null argument");
+    if (n > AC_SMEM_N && !work) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: workspace required");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smem = (n <= AC_SMEM_N) ? n * n * (int)sizeof(cplx) : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ac_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cdn_fail(ctx, CDN_ERR_CUDA, std::string("cdn_ac_solve: ") + cudaGetErrorString(e));
+    }
+    const int blocks = nf < 8 * ctx->sm_count ? nf : 8 * ctx->sm_count;
+    ac_solve_kernel<<<blocks, AC_TPB, smem, st>>>(n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, freqs, s,
+                                                  (cplx*)work, (cplx*)x, status);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cdn_fail(ctx, CDN_ERR_CUDA, std::string("cdn_ac_solve launch: ") + cudaGetErrorString(e));
+    return CDN_OK;
+}

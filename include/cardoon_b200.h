@@ -47,6 +47,22 @@ int cdn_dev_eval(cdn_ctx* ctx, int model_id, unsigned flags, long n, int nxin,
                  const double* params, long ldp, const int* pidx,
                  const double* xin, double* out, double* jac, void* stream);
 
+/* ---- (f2) small-signal AC sweep -------------------------------------------
+ * Replaces the per-frequency loop of run_AC (cardoon/analyses/nodal.py:286-381):
+ * Y = G + j w C, set_Jac of the device Jacobians with exp(-j w tau) on
+ * delayed columns, linalg.solve(Y, sVec).  One CTA per frequency.
+ *   G, C        [n*n] row-major, with the frequency-independent device stamps
+ *   (drow, dcol, dg, dc, dtau)[ndel]   Y[drow,dcol] += (dg + j w dc) exp(-j w dtau)
+ *   freqs[nf] (Hz); s[n][2] (re, im); x[nf][n][2]
+ *   work        nf*n*n*16 bytes when n > 56 (else may be NULL)
+ *   status      int: 0, or 1 + index of a frequency with a singular matrix
+ * All pointers are device pointers.                                          */
+int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const double* C,
+                 int ndel, const int* drow, const int* dcol, const double* dg,
+                 const double* dc, const double* dtau, const double* freqs,
+                 const double* s, double* work, double* x, int* status,
+                 void* stream);
+
 /* ---- (a1-a4, a12) formulation plan: symbolic analysis, done once ---------
  * Replaces what the reference redoes on every Newton iteration: COO -> CSC
  * conversion with duplicate summing, COLAMD ordering, symbolic and numeric

@@ -723,6 +723,65 @@ def run_op(ckt, glVar, idx=None):
     return dict(x=x, res=res, iterations=it, idx=idx, dc=dc)
 
 
+def run_ac(ckt, glVar, fvec, idx=None):
+    """AC sweep (ac.py:69-146 + run_AC nodal.py:286-381): operating point,
+    then per frequency Y = G + jwC + device Jacobians (delayed columns times
+    exp(-jw tau)) and a dense complex solve.  dict(f, X[nvars, nfreq], x_op,
+    idx)."""
+    from scipy import linalg
+    op = run_op(ckt, glVar, idx)
+    idx = op['idx']
+    x_op = op['x']
+    opt = Options(glVar)
+    n = idx.dimension
+    G = np.zeros((n, n))
+    C = np.zeros((n, n))
+    for elem in idx.elemList:
+        inf = idx.info[id(elem)]
+        for q in inf['vccs']:
+            _set_quad(G, *q)
+        for q in inf['vcqs']:
+            _set_quad(C, *q)
+    jacs = []
+    for elem in idx.nlin:
+        inf = idx.info[id(elem)]
+        xin = _set_xin(inf, x_op)
+        out, jac = device_eval(elem, xin[:, None], True, gyr=opt.gyr)
+        jacs.append(jac[:, :, 0])
+    sVec = np.zeros(n, dtype=complex)
+    for elem in idx.elemList:
+        if not elem.isFDSource:
+            continue
+        try:
+            current = elem.get_AC()
+        except AttributeError:
+            continue                         # nodal.py:331-343
+        n1 = idx.row(elem.connection[elem.sourceOutput[0]])
+        n2 = idx.row(elem.connection[elem.sourceOutput[1]])
+        if n1 >= 0:
+            sVec[n1] -= current
+        if n2 >= 0:
+            sVec[n2] += current
+    fvec = np.asarray(fvec, dtype=float)
+    X = np.zeros((n, len(fvec)), dtype=complex)
+    for k, jomega in enumerate(2j * np.pi * fvec):
+        Y = G + jomega * C
+        for elem, jac in zip(idx.nlin, jacs):
+            inf = idx.info[id(elem)]
+            work = jac.astype(complex)
+            if elem.nDelays:
+                for i in range(-elem.nDelays, 0):
+                    work[:, i] *= np.exp(-jomega * inf['delay'][i])
+            ncs = inf['ncs']
+            _set_Jac(Y, inf['cpos'], inf['cneg'], inf['vpos'], inf['vneg'],
+                     work)
+            if len(elem.qsOutPorts):
+                _set_Jac(Y, inf['qpos'], inf['qneg'], inf['vpos'],
+                         inf['vneg'], jomega * work[ncs:, :])
+        X[:, k] = linalg.solve(Y, sVec)
+    return dict(f=fvec, X=X, x_op=x_op, idx=idx)
+
+
 def run_dc(ckt, glVar, device, param, start, stop, num):
     """DC sweep of one device parameter (dc.py:141-205): dict(sweep,
     X[num, N], iters, idx).  The circuit's element is left at the last
