@@ -85,8 +85,8 @@ def _declare(dll):
     dll.cdn_dev_eval.argtypes = [_vp, C.c_int, C.c_uint, C.c_long, C.c_int,
                                  _vp, C.c_long, _vp, _vp, _vp, _vp, _vp]
     dll.cdn_ac_solve.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int,
-                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                 _vp, _vp]
+                                 _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     dll.cdn_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
     dll.cdn_set_tuning.argtypes = [C.c_int, C.c_int]
     dll.cdn_plan_create.argtypes = [_vp, C.POINTER(CircuitHost),
@@ -205,10 +205,12 @@ class Lib(object):
         return (out.cpu().numpy(),
                 jac.cpu().numpy() if jac is not None else None)
 
-    def ac_solve(self, G, Cm, delayed, freqs, sVec):
+    def ac_solve(self, G, Cm, delayed, freqs, sVec, fd_rc=(), fd_val=()):
         """x[nf, n] (complex) with Y(w) x = s for every frequency;
         Y = G + j w C + sum (g + j w c) exp(-j w tau) over the `delayed`
-        entries (row, col, g, c, tau).  numpy in / numpy out."""
+        entries (row, col, g, c, tau), plus fd_val[e][k] at (row, col) =
+        fd_rc[e] for frequency k (frequency-defined elements).  numpy in /
+        numpy out."""
         torch = self.torch
         n = G.shape[0]
         freqs = np.ascontiguousarray(freqs, dtype=np.float64)
@@ -219,6 +221,14 @@ class Lib(object):
             np.stack([sVec.real, sVec.imag], axis=1), dtype=np.float64)
         ti = lambda a: torch.as_tensor(
             np.ascontiguousarray(a, dtype=np.int32), device=self.device)
+        nfd = len(fd_rc)
+        frc = np.array(fd_rc, dtype=np.int32).reshape(nfd, 2)
+        fv = np.zeros((nf, nfd, 2))
+        for e, v in enumerate(fd_val):
+            v = np.broadcast_to(np.asarray(v, dtype=complex), (nf,))
+            fv[:, e, 0] = v.real
+            fv[:, e, 1] = v.imag
+        fdev = [ti(frc[:, 0]), ti(frc[:, 1]), self.dev(fv)]
         work = self.empty((nf * n * n * 2,)) if n > 56 else None
         x = self.empty((nf, n, 2))
         status = self.zeros((1,), torch.int32)
@@ -231,6 +241,7 @@ class Lib(object):
             self.ctx, int(n), int(nf), self.ptr(args[0]), self.ptr(args[1]),
             int(ndel), self.ptr(args[2]), self.ptr(args[3]),
             self.ptr(args[4]), self.ptr(args[5]), self.ptr(args[6]),
+            int(nfd), self.ptr(fdev[0]), self.ptr(fdev[1]), self.ptr(fdev[2]),
             self.ptr(args[7]), self.ptr(args[8]), self.ptr(work),
             self.ptr(x), self.ptr(status), self.stream())
         self.check(rc)

@@ -168,10 +168,6 @@ def run_AC(ckt, fvec):
     """
     from .._lib import get_lib
     n = ckt.nD_dimension
-    if ckt.nD_freqDefinedElem:
-        raise NotImplementedError(
-            'AC: frequency-defined elements ({0}) are not supported by this '
-            'back-end'.format(ckt.nD_freqDefinedElem[0].instanceName))
     G = np.zeros((n, n))
     Cm = np.zeros((n, n))
     for elem in ckt.nD_elemList:
@@ -207,8 +203,19 @@ def run_AC(ckt, fvec):
             sVec[outTerm[0]] -= current
         if outTerm[1] >= 0:
             sVec[outTerm[1]] += current
-    x = get_lib().ac_solve(G, Cm, delayed, np.asarray(fvec, dtype=float),
-                           sVec)
+    # frequency-defined elements: Y parameters for the whole sweep at once
+    # (get_Y_matrix is vectorised over frequency, nodal.py:366-370)
+    fvec = np.asarray(fvec, dtype=float)
+    fd_rc, fd_val = [], []
+    for elem in ckt.nD_freqDefinedElem:
+        Ym = elem.get_Y_matrix(fvec)
+        for sa, rows in ((1., elem.nD_fpos), (-1., elem.nD_fneg)):
+            for a, i in rows:
+                for sb, cols in ((1., elem.nD_fpos), (-1., elem.nD_fneg)):
+                    for b, j in cols:
+                        fd_rc.append((i, j))
+                        fd_val.append(sa * sb * Ym[a, b])
+    x = get_lib().ac_solve(G, Cm, delayed, fvec, sVec, fd_rc, fd_val)
     xVec = np.ascontiguousarray(x.T)
     ckt.nD_ref.aC_V = 0.
     for k, term in enumerate(ckt.nD_termList):
@@ -283,7 +290,19 @@ class Topology(object):
             rc = elem.nD_rcList
             for (p, q) in elem.nD_extPorts:
                 quadsE.append([rc[p], rc[p], rc[q], rc[q], 1.])
+        # frequency-defined elements enter the DC equations through their DC
+        # Y parameters (nodal.py:719-721, nodalSP.py:403-407) and are absent
+        # from the transient ones (nodal.py:921, commented out there)
+        quadsFD = []
+        for elem in ckt.nD_freqDefinedElem:
+            rc = [t.nD_namRC for t in elem.connection]
+            Gm = elem.get_G_matrix()
+            for a, pa in enumerate(elem.fPortsDefinition):
+                for b, pb in enumerate(elem.fPortsDefinition):
+                    quadsFD.append([rc[pa[0]], rc[pb[0]], rc[pa[1]],
+                                    rc[pb[1]], Gm[a, b]])
         self.G = _quads_to_coo(quadsG)
+        self.Gdc = _quads_to_coo(quadsG + quadsFD) if quadsFD else self.G
         self.C = _quads_to_coo(quadsC)
         self.E = _quads_to_coo(quadsE)
         # device groups
@@ -408,7 +427,7 @@ def reference_matrix(topo, use_q, a0, stamps):
     """Numeric Jacobian G + a0 C + device stamps at the reference point
     (scipy CSR, duplicates summed; structural entries kept)."""
     import scipy.sparse as sp
-    Gr, Gc, Gv = topo.G
+    Gr, Gc, Gv = topo.G if use_q else topo.Gdc
     Cr, Cc, Cv = topo.C
     dr, dc_, di, dq = stamps
     r = [Gr, dr]
@@ -511,7 +530,8 @@ def create_plan(dll, ctx, topo, use_q, dense, match=None, ordering=None,
     else:
         ch.ordering = L.ORDER_ND if ordering is None else ordering
     empty = (np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0))
-    for nm, (r, c, v) in (('G', topo.G), ('C', topo.C if use_q else empty),
+    for nm, (r, c, v) in (('G', topo.G if use_q else topo.Gdc),
+                          ('C', topo.C if use_q else empty),
                           ('E', topo.E)):
         low = nm.lower()
         setattr(ch, 'n' + nm, len(v))

@@ -1,5 +1,6 @@
 // Small-signal AC sweep: for every frequency f_k solve
 //     Y(w_k) x_k = s,   Y(w) = G + j w C + sum_d (g_d + j w c_d) exp(-j w tau_d)
+//                               + Y_fd(w_k)
 // Replaces the per-frequency loop of the reference's run_AC
 // (analyses/nodal.py:286-381: Y[:] = G + jomega*C, set_Jac of every device
 // Jacobian with exp(-jomega*tau) on delayed columns, linalg.solve).
@@ -9,7 +10,9 @@
 // |re|+|im|, the LAPACK zgetrf pivot rule) and solves for the source vector.
 // G and C already contain the frequency-independent device stamps
 // (dI/dv into G, dQ/dv into C); only delayed control ports are applied per
-// frequency from the triplet list.  Matrices of up to 56x56 live in shared
+// frequency from the triplet list, and the Y parameters of frequency-defined
+// elements (get_Y_matrix, nodal.py:366-370; evaluated on the host for the whole
+// sweep) are added from a per-frequency value table.  Matrices of up to 56x56 live in shared
 // memory, larger ones in the caller's workspace (L2-resident).
 #include "common.cuh"
 
@@ -38,7 +41,9 @@ __global__ void __launch_bounds__(AC_TPB)
 ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __restrict__ C,
                 int ndel, const int* __restrict__ drow, const int* __restrict__ dcol,
                 const double* __restrict__ dg, const double* __restrict__ dc,
-                const double* __restrict__ dtau, const double* __restrict__ freqs,
+                const double* __restrict__ dtau, int nfd, const int* __restrict__ frow,
+                const int* __restrict__ fcol, const double* __restrict__ fval,
+                const double* __restrict__ freqs,
                 const double* __restrict__ s, cplx* __restrict__ work, cplx* __restrict__ xout,
                 int* __restrict__ status) {
     extern __shared__ double ac_sm[];
@@ -67,6 +72,12 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
                 const cplx v = cmul(a, ph);
                 cplx* y = Y + (long)drow[d] * n + dcol[d];
                 y->re += v.re; y->im += v.im;
+            }
+            // frequency-defined elements: fval[f][e] = (re, im)
+            for (int e = 0; e < nfd; ++e) {
+                cplx* y = Y + (long)frow[e] * n + fcol[e];
+                y->re += fval[((long)f * nfd + e) * 2];
+                y->im += fval[((long)f * nfd + e) * 2 + 1];
             }
         }
         __syncthreads();
@@ -139,16 +150,19 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
 
 // Reference: run_AC (analyses/nodal.py:286-381).  All pointers are device
 // pointers.  G, C: [n*n] row-major; delayed entries (drow, dcol, dg, dc,
-// dtau)[ndel]; freqs[nf]; s[n][2] (re, im); work: nf*n*n complex when
+// dtau)[ndel]; frequency-defined entries (frow, fcol)[nfd] with
+// fval[nf][nfd][2]; freqs[nf]; s[n][2] (re, im); work: nf*n*n complex when
 // n > 56 (else unused); x: [nf][n][2]; status: 0 or 1 + index of a frequency
 // whose matrix is singular.
 extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const double* C, int ndel,
                             const int* drow, const int* dcol, const double* dg, const double* dc,
-                            const double* dtau, const double* freqs, const double* s, double* work,
+                            const double* dtau, int nfd, const int* frow, const int* fcol,
+                            const double* fval, const double* freqs, const double* s, double* work,
                             double* x, int* status, void* stream) {
     if (!ctx) return CDN_ERR_ARG;
     if (n <= 0 || nf <= 0) return CDN_OK;
-    if (!G || !C || !freqs || !s || !x || !status || (ndel > 0 && (!drow || !dcol || !dg || !dc || !dtau)))
+    if (!G || !C || !freqs || !s || !x || !status || (ndel > 0 && (!drow || !dcol || !dg || !dc || !dtau))
+        || (nfd > 0 && (!frow || !fcol || !fval)))
         return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: null argument");
     if (n > AC_SMEM_N && !work) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: workspace required");
     cudaStream_t st = (cudaStream_t)stream;
@@ -158,7 +172,8 @@ extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const 
         if (e != cudaSuccess) return cdn_fail(ctx, CDN_ERR_CUDA, std::string("cdn_ac_solve: ") + cudaGetErrorString(e));
     }
     const int blocks = nf < 8 * ctx->sm_count ? nf : 8 * ctx->sm_count;
-    ac_solve_kernel<<<blocks, AC_TPB, smem, st>>>(n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, freqs, s,
+    ac_solve_kernel<<<blocks, AC_TPB, smem, st>>>(n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow,
+                                                  fcol, fval, freqs, s,
                                                   (cplx*)work, (cplx*)x, status);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cdn_fail(ctx, CDN_ERR_CUDA, std::string("cdn_ac_solve launch: ") + cudaGetErrorString(e));

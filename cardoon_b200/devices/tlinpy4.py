@@ -49,10 +49,13 @@ class Device(cir.Element):
         self.l = (self.z0mag * self.z0mag) * self.c
         self.alpha_nepers = self.alpha / const.Np2dB
         if not self.nsect:
-            raise cir.CircuitError(
-                self.instanceName + ': frequency-defined mode (nsect=0) is '
-                'only meaningful in AC analysis, which this back-end does '
-                'not provide')
+            # frequency-defined model (reference tlinpy4.py:114-118): Y
+            # parameters in AC (get_Y_matrix), DC conductances in OP
+            # (get_G_matrix); ignored in transient like in the reference
+            self.isFreqDefined = True
+            self.linearVCCS = []
+            self.linearVCQS = []
+            return
         self.isFreqDefined = False
         if self.connection[1] != self.connection[3]:
             raise cir.CircuitError(
@@ -98,3 +101,31 @@ class Device(cir.Element):
                 vccs.append(((cnn, 1), (cnn, 1), G))
         self.linearVCCS = vccs
         self.linearVCQS = vcqs
+
+    # ---- linear frequency-defined device methods (nsect = 0) ---------------
+    def get_Y_matrix(self, freq):
+        """Y parameters [[y11, y12], [y12, y11]] at ``freq`` (scalar or
+        vector, never zero); reference tlinpy4.py:235-271."""
+        omega = 2. * np.pi * freq
+        if self.fscale != 0.:
+            alphaf = self.alpha_nepers * np.sqrt(freq / self.fscale)
+        else:
+            alphaf = self.alpha_nepers
+        r = 2.0 * alphaf * self.z0mag
+        g = self.tand * omega * self.c
+        z1 = r + 1j * self.l * omega
+        y1 = g + 1j * self.c * omega
+        Z0 = np.sqrt(z1 / y1)
+        gamma = np.sqrt(z1 * y1)
+        ctemp = gamma * self.length
+        y11 = np.cosh(ctemp) / Z0 / np.sinh(ctemp)
+        y12 = -1. / Z0 / np.sinh(ctemp)
+        return np.array([[y11, y12], [y12, y11]])
+
+    def get_G_matrix(self):
+        """DC Y parameters (reference tlinpy4.py:274-293): attenuation
+        alpha * length, floored at 1e-5."""
+        ctemp = max(self.alpha_nepers * self.length, 1e-5)
+        y11 = np.cosh(ctemp) / self.z0mag / np.sinh(ctemp)
+        y12 = -1. / self.z0mag / np.sinh(ctemp)
+        return np.array([[y11, y12], [y12, y11]])

@@ -53,13 +53,16 @@ int cdn_dev_eval(cdn_ctx* ctx, int model_id, unsigned flags, long n, int nxin,
  * delayed columns, linalg.solve(Y, sVec).  One CTA per frequency.
  *   G, C        [n*n] row-major, with the frequency-independent device stamps
  *   (drow, dcol, dg, dc, dtau)[ndel]   Y[drow,dcol] += (dg + j w dc) exp(-j w dtau)
+ *   (frow, fcol)[nfd], fval[nf][nfd][2]   Y_k[frow,fcol] += fval[k] (Y parameters
+ *               of frequency-defined elements, get_Y_matrix, nodal.py:366-370)
  *   freqs[nf] (Hz); s[n][2] (re, im); x[nf][n][2]
  *   work        nf*n*n*16 bytes when n > 56 (else may be NULL)
  *   status      int: 0, or 1 + index of a frequency with a singular matrix
  * All pointers are device pointers.                                          */
 int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const double* C,
                  int ndel, const int* drow, const int* dcol, const double* dg,
-                 const double* dc, const double* dtau, const double* freqs,
+                 const double* dc, const double* dtau, int nfd, const int* frow,
+                 const int* fcol, const double* fval, const double* freqs,
                  const double* s, double* work, double* x, int* status,
                  void* stream);
 

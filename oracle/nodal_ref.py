@@ -101,6 +101,8 @@ class NodalIndex(object):
             inf['epos'], inf['eneg'] = plist([(i, nports)
                                               for i in range(nports)])
             inf['ncs'] = len(elem.csOutPorts)
+        if getattr(elem, 'isFreqDefined', False):
+            inf['fpos'], inf['fneg'] = plist(elem.fPortsDefinition)
         if elem.isDCSource or elem.isTDSource:
             inf['srcOut'] = (rcList[elem.sourceOutput[0]],
                              rcList[elem.sourceOutput[1]])
@@ -444,6 +446,17 @@ class RefDC(_NLFunction):
             for elem in idx.elemList:
                 for q in idx.info[id(elem)]['vccs']:
                     _triplet_quad(T, *q)
+            for elem in idx.elemList:           # nodalSP.py:403-407
+                inf = idx.info[id(elem)]
+                if 'fpos' in inf:
+                    Gm = elem.get_G_matrix()
+                    D_ = np.zeros((self.n, self.n))
+                    _set_Jac(D_, inf['fpos'], inf['fneg'], inf['fpos'],
+                             inf['fneg'], Gm)
+                    for r_, c_ in zip(*np.nonzero(D_)):
+                        T[0].append(D_[r_, c_])
+                        T[1].append(r_)
+                        T[2].append(c_)
             self.G = sp.coo_matrix((T[0], (T[1], T[2])),
                                    (self.n, self.n)).tocsr()
             self._mbaseLin = len(T[0])
@@ -459,6 +472,10 @@ class RefDC(_NLFunction):
             for elem in idx.elemList:
                 for q in idx.info[id(elem)]['vccs']:
                     _set_quad(self.G, *q)
+                inf = idx.info[id(elem)]
+                if 'fpos' in inf:               # nodal.py:719-721
+                    _set_Jac(self.G, inf['fpos'], inf['fneg'], inf['fpos'],
+                             inf['fneg'], elem.get_G_matrix())
             self.Jac = np.zeros((self.n, self.n))
 
     def get_guess(self):                        # nodal.py:723-740
@@ -778,6 +795,11 @@ def run_ac(ckt, glVar, fvec, idx=None):
             if len(elem.qsOutPorts):
                 _set_Jac(Y, inf['qpos'], inf['qneg'], inf['vpos'],
                          inf['vneg'], jomega * work[ncs:, :])
+        for elem in idx.elemList:            # nodal.py:366-370
+            inf = idx.info[id(elem)]
+            if 'fpos' in inf:
+                _set_Jac(Y, inf['fpos'], inf['fneg'], inf['fpos'],
+                         inf['fneg'], elem.get_Y_matrix(fvec[k]))
         X[:, k] = linalg.solve(Y, sVec)
     return dict(f=fvec, X=X, x_op=x_op, idx=idx)
 

@@ -72,3 +72,36 @@ def test_delay_phase_factor():
     assert np.max(np.abs(r0['X'][rows['4']] - r['X'][rows['4']])
                   / np.abs(r['X'][rows['4']])) > 1e-3
     assert tau == 5e-12
+
+
+TLINE = """# matched, lossless frequency-defined line (nsect = 0)
+vsin:vs 1 gnd mag=1. acmag=2. freq=1GHz rint=50.
+tlinpy4:tl1 1 gnd 2 gnd z0mag=50. k=4. alpha=0. length=0.03
+res:rl 2 gnd r=50.
+res:rdc 2 3 r=1k
+vdc:vb 3 gnd vdc=1.
+.end
+"""
+
+
+def test_frequency_defined_line_closed_form():
+    """tlinpy4 with nsect=0 (tlinpy4.py:235-271): a matched lossless line
+    delays the wave by length*sqrt(k)/c0 and leaves its magnitude alone; at
+    DC it is a near-short (get_G_matrix)."""
+    ckt, _ = load_text(TLINE)
+    tl = [e for e in ckt.elemDict.values() if e.devType == 'tlinpy4'][0]
+    assert tl.isFreqDefined and not tl.linearVCCS
+    f = np.linspace(1e8, 5e9, 30)
+    r = R.run_ac(ckt, glVar, f)
+    rows = r['idx'].name_to_row()
+    # load = 50 || 1k (the DC source is an AC short)
+    zl = 1. / (1. / 50. + 1. / 1e3)
+    gam = (zl - 50.) / (zl + 50.)
+    td = 0.03 * 2. / 299792458.
+    ph = np.exp(-2j * np.pi * f * td)
+    # incident wave of amplitude acmag/2 at the input of a line matched at
+    # the source end: V2 = V+ (1 + gamma) exp(-j w td)
+    v2 = 1. * (1. + gam) * ph
+    assert np.allclose(r['X'][rows['2']], v2, rtol=1e-6)
+    # operating point: 1 V behind 1k into (50 + line) || 50
+    assert abs(r['x_op'][rows['2']] - r['x_op'][rows['1']]) < 1e-3

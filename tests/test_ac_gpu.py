@@ -82,3 +82,15 @@ def test_ac_large_dense_system(lib):
     X, ref = ac_both(ckt, np.logspace(7., 10., 24))
     assert ckt.nD_dimension > 200
     check_ac(X, ref)
+
+
+def test_ac_frequency_defined_line(lib):
+    """tlinpy4 nsect=0: DC Y parameters in the operating point, get_Y_matrix
+    per frequency in the sweep (dense and sparse OP formulations)."""
+    from tests.test_ac_cpu import TLINE
+    for opts in ('', '.options sparse=1\n'):
+        ckt, _ = load_text(opts + TLINE)
+        X, ref = ac_both(ckt, np.linspace(1e8, 5e9, 48))
+        check_ac(X, ref)
+        x_op = np.array([t.nD_vOP for t in ckt.nD_termList])
+        assert np.allclose(x_op, ref['x_op'], rtol=1e-9, atol=1e-12)
