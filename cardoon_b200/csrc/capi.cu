@@ -57,6 +57,7 @@ extern "C" int cdn_model_nparams(int model_id) {
     case CDN_MODEL_SVDIODE: return NP_SVDIODE;
     case CDN_MODEL_SVDIODE_T: return NP_SVDIODE_T;
     case CDN_MODEL_RES_T: return NP_RES_T;
+    case CDN_MODEL_EKV_T: return NP_EKV_T;
     default: return -1;
     }
 }

@@ -45,6 +45,7 @@ CDN_HD void eval_any(int model, const PV& p, unsigned flags, const Dual<P>* v, S
     case CDN_MODEL_SVDIODE: svdiode_eval(p, flags, v, sink); break;
     case CDN_MODEL_SVDIODE_T: svdiode_t_eval(p, flags, v, sink); break;
     case CDN_MODEL_RES_T: res_t_eval(p, flags, v, sink); break;
+    case CDN_MODEL_EKV_T: ekv_t_eval(p, flags, v, sink); break;
     default: break;
     }
 }
@@ -299,6 +300,8 @@ static cudaError_t launch_model(int model, int lanes, long n, unsigned flags,
         return lanes ? LAUNCH(CDN_MODEL_SVDIODE_T, 2) : LAUNCH(CDN_MODEL_SVDIODE_T, 0);
     case CDN_MODEL_RES_T:
         return lanes ? LAUNCH(CDN_MODEL_RES_T, 2) : LAUNCH(CDN_MODEL_RES_T, 0);
+    case CDN_MODEL_EKV_T:
+        return lanes ? LAUNCH(CDN_MODEL_EKV_T, 4) : LAUNCH(CDN_MODEL_EKV_T, 0);
     default:
         return cudaErrorInvalidValue;
     }
@@ -312,7 +315,7 @@ extern "C" int cdn_dev_eval(cdn_ctx* ctx, int model_id, unsigned flags, long n, 
     if (nxin < 1 || nxin > CDN_MAX_XIN) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_dev_eval: bad nxin");
     cudaStream_t st = (cudaStream_t)stream;
     const int lanes = jac ? nxin : 0;
-    if (model_id < 0 || model_id > CDN_MODEL_RES_T)
+    if (model_id < 0 || model_id > CDN_MODEL_EKV_T)
         return cdn_fail(ctx, CDN_ERR_ARG, "cdn_dev_eval: unknown model id");
     const cudaError_t e = launch_model(model_id, lanes, n, flags, params, ldp, pidx, xin,
                                        out, jac, nxin, st);

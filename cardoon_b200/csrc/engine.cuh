@@ -344,6 +344,7 @@ __device__ __forceinline__ void eval_model(const cdn_group_dev& G, const PV& p, 
     else if (MODEL == CDN_MODEL_SVDIODE) svdiode_eval(p, G.flags, v, sink);
     else if (MODEL == CDN_MODEL_SVDIODE_T) svdiode_t_eval(p, G.flags, v, sink);
     else if (MODEL == CDN_MODEL_RES_T) res_t_eval(p, G.flags, v, sink);
+    else if (MODEL == CDN_MODEL_EKV_T) ekv_t_eval(p, G.flags, v, sink);
 }
 
 #define CDN_MS(m) (1 << (m))
@@ -404,6 +405,10 @@ __device__ __noinline__ void eval_one(const cdn_group_dev& G, int b, int i, cons
     case CDN_MODEL_RES_T:
         if (CDN_HAS(MS, CDN_MODEL_RES_T))
             eval_model<CDN_MODEL_RES_T, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0);
+        break;
+    case CDN_MODEL_EKV_T:
+        if (CDN_HAS(MS, CDN_MODEL_EKV_T))
+            eval_model<CDN_MODEL_EKV_T, DERIV ? 4 : 0>(G, p, i, x, w, 0, h, 0);
         break;
     case CDN_MODEL_MESFETC:
         if (CDN_HAS(MS, CDN_MODEL_MESFETC))

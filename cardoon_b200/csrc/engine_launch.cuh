@@ -21,7 +21,8 @@ struct cdn_launch_cfg {
                     CDN_MS(CDN_MODEL_MESFETC) | CDN_MS(CDN_MODEL_DIODE_T) | \
                     CDN_MS(CDN_MODEL_BJT_T) | CDN_MS(CDN_MODEL_SVBJT_T) | \
                     CDN_MS(CDN_MODEL_MESFETC_T) | CDN_MS(CDN_MODEL_SVDIODE) | \
-                    CDN_MS(CDN_MODEL_SVDIODE_T) | CDN_MS(CDN_MODEL_RES_T))
+                    CDN_MS(CDN_MODEL_SVDIODE_T) | CDN_MS(CDN_MODEL_RES_T) | \
+                    CDN_MS(CDN_MODEL_EKV_T))
 
 template <class K>
 static cudaError_t set_smem(K kernel, long smem) {

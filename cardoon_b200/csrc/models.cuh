@@ -37,6 +37,7 @@ __host__ __device__ inline int model_lanes(int model) {
     case CDN_MODEL_DIODE: return 1;
     case CDN_MODEL_DIODE_T: case CDN_MODEL_SVDIODE_T: case CDN_MODEL_RES_T: return 2;
     case CDN_MODEL_SVDIODE: return 1;
+    case CDN_MODEL_EKV_T: return 4;
     case CDN_MODEL_BJT_T: case CDN_MODEL_SVBJT_T: case CDN_MODEL_MESFETC_T: return 5;
     case CDN_MODEL_BSIM3: case CDN_MODEL_EKV: return 3;
     case CDN_MODEL_MEMR: return 2;

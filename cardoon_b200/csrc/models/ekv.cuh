@@ -32,37 +32,39 @@ CDN_HD Dual<P> ekv_interp(const Dual<P>& v, bool simple) {
     return simple ? ekv_f_simple(v) : ekv_f_accurate(v);
 }
 
-template <int P>
-CDN_HD void ekv_intrinsic(const PV& p, unsigned flags, const Dual<P>* v,
+// `A`: PV or the dual record of the electro-thermal variant (thermal.cuh);
+// temperature-independent entries are read through val().
+template <int P, class A>
+CDN_HD void ekv_intrinsic(const A& p, unsigned flags, const Dual<P>* v,
                           Dual<P>* iv, Dual<P>* qv) {
     typedef Dual<P> D;
     const bool simple = (flags & F_EKV_SIMPLE) != 0;
-    const double tf = p[P_EKV_tf];
+    const double tf = val(p[P_EKV_tf]);
     const D vd0 = tf * v[0], vg = tf * v[1], vs0 = tf * v[2];
     const double swap = ((vd0.v - vs0.v) > 0.0) ? 1.0 : -1.0;
     const D vd = select(swap, vd0, vs0);
     const D vs = select(swap, vs0, vd0);
-    const double Vt = p[P_EKV_Vt], phiT = p[P_EKV_phiT], ga = p[P_EKV_gammaa];
-    const double go2 = p[P_EKV_go2];
+    const auto Vt = p[P_EKV_Vt], phiT = p[P_EKV_phiT];
+    const double ga = val(p[P_EKV_gammaa]), go2 = val(p[P_EKV_go2]);
     // effective gate voltage, pinch-off voltage (:409-439)
-    const D vgprime = vg - p[P_EKV_vt0a] - p[P_EKV_deltavRSCE] + phiT + p[P_EKV_gsqphi];
-    D vp0 = vgprime - phiT - ga * (sqrt(vgprime + p[P_EKV_g2o4]) - go2);
+    const D vgprime = vg - p[P_EKV_vt0a] - val(p[P_EKV_deltavRSCE]) + phiT + p[P_EKV_gsqphi];
+    D vp0 = vgprime - phiT - ga * (sqrt(vgprime + val(p[P_EKV_g2o4])) - go2);
     vp0 = select(vgprime, vp0, D(-phiT));
-    const double vt16 = p[P_EKV_vt16];
+    const auto vt16 = p[P_EKV_vt16];
     const D vsprime = 0.5 * (vs + phiT + sqrt(sq(vs + phiT) + vt16));
     const D vdprime = 0.5 * (vd + phiT + sqrt(sq(vd + phiT) + vt16));
-    D tmp = p[P_EKV_letaleff] * (sqrt(vsprime) + sqrt(vdprime));
-    tmp = tmp - p[P_EKV_weta3] * sqrt(vp0 + phiT) / p[P_EKV_weff];
-    const D gammao = ga - p[P_EKV_epscox] * tmp;
+    D tmp = val(p[P_EKV_letaleff]) * (sqrt(vsprime) + sqrt(vdprime));
+    tmp = tmp - val(p[P_EKV_weta3]) * sqrt(vp0 + phiT) / val(p[P_EKV_weff]);
+    const D gammao = ga - val(p[P_EKV_epscox]) * tmp;
     const D gammaprime = 0.5 * (gammao + sqrt(gammao * gammao + p[P_EKV_vt01]));
     D vp = vgprime - phiT;
     vp = vp - gammaprime * (sqrt(vgprime + sq(.5 * gammaprime)) - gammaprime / 2.0);
     vp = select(vgprime, vp, D(-phiT));
-    const double vt4 = p[P_EKV_vt4];
+    const auto vt4 = p[P_EKV_vt4];
     const D n = 1.0 + ga / (2.0 * sqrt(vp + phiT + vt4));
     // forward current, saturation voltages (:441-449)
     const D i_f = ekv_interp((vp - vs) / Vt, simple);
-    const double vc = p[P_EKV_vc];
+    const auto vc = p[P_EKV_vc];
     const D sqif = sqrt(i_f);
     D vdss = sqrt(0.25 + Vt * sqif / vc) - 0.5;
     vdss = vdss * vc;
@@ -71,7 +73,8 @@ CDN_HD void ekv_intrinsic(const PV& p, unsigned flags, const Dual<P>* v,
     vdssprime = vdssprime * vc;
     vdssprime = vdssprime + p[P_EKV_vdsslog];
     // channel-length modulation (:450-463)
-    const double Lambda = p[P_EKV_Lambda], lc = p[P_EKV_lc], ucrit = p[P_EKV_t_ucrit];
+    const double Lambda = val(p[P_EKV_Lambda]), lc = val(p[P_EKV_lc]);
+    const auto ucrit = p[P_EKV_t_ucrit];
     tmp = sqif - vdss / Vt;
     D deltav = sqrt(Lambda * tmp + 1.0 / 64);
     deltav = deltav * vt4;
@@ -79,9 +82,9 @@ CDN_HD void ekv_intrinsic(const PV& p, unsigned flags, const Dual<P>* v,
     D vip = sqrt(vdss * vdss + deltav * deltav);
     vip = vip - sqrt(sq(vds - vdss) + deltav * deltav);
     D deltal = log(1.0 + (vds - vip) / lc / ucrit);
-    deltal = deltal * p[P_EKV_lamlc];
-    const D lprime = p[P_EKV_nsleff] - deltal + (vds + vip) / ucrit;
-    const D leq = 0.5 * (lprime + sqrt(lprime * lprime + p[P_EKV_lmin2]));
+    deltal = deltal * val(p[P_EKV_lamlc]);
+    const D lprime = val(p[P_EKV_nsleff]) - deltal + (vds + vip) / ucrit;
+    const D leq = 0.5 * (lprime + sqrt(lprime * lprime + val(p[P_EKV_lmin2])));
     // reverse currents (:464-471)
     tmp = vp - vds - vs;
     tmp = tmp - sqrt(vdssprime * vdssprime + deltav * deltav);
@@ -104,21 +107,21 @@ CDN_HD void ekv_intrinsic(const PV& p, unsigned flags, const Dual<P>* v,
     D qb1 = -ga * sqvpphi / Vt;
     qb1 = qb1 - (nq - 1.0) * qi / nq;
     const D qb = select(vgprime, qb1, -vgprime / Vt);
-    const D qg = -qi - qb - p[P_EKV_qox];
+    const D qg = -qi - qb - val(p[P_EKV_qox]);
     // mobility reduction, drain current (:495-526)
     const D betao = p[P_EKV_kpanpw] / leq;
     const D betaoprime = p[P_EKV_bop] * betao;
-    tmp = dabs(qb + p[P_EKV_eta] * qi);
-    tmp = 1.0 + p[P_EKV_coxvt] * tmp / p[P_EKV_e0] / p[P_EKV_epSi];
+    tmp = dabs(qb + val(p[P_EKV_eta]) * qi);
+    tmp = 1.0 + p[P_EKV_coxvt] * tmp / val(p[P_EKV_e0]) / val(p[P_EKV_epSi]);
     const D beta = betaoprime / tmp;
     const D IS = 2.0 * n * beta * Vt * Vt;
     const D ids = IS * (i_f - irprime);
     // impact ionisation (:529-533)
-    const D vib = vd - vs - p[P_EKV_ibn2] * vdss;
-    D idb1 = ids * p[P_EKV_iba] * vib / p[P_EKV_t_ibb];
+    const D vib = vd - vs - val(p[P_EKV_ibn2]) * vdss;
+    D idb1 = ids * val(p[P_EKV_iba]) * vib / p[P_EKV_t_ibb];
     idb1 = idb1 * safe_exp(p[P_EKV_ntibblc] / vib);
     const D idb = select(vib, idb1, 0.0);
-    const double qscale = p[P_EKV_qscale];
+    const auto qscale = p[P_EKV_qscale];
     qv[0] = select(swap, qd, qs) * qscale;
     qv[1] = qg * qscale;
     qv[2] = select(swap, qs, qd) * qscale;

@@ -21,7 +21,7 @@ template <int P, class A>
 CDN_HD void mosext_apply(A& p, int base, unsigned flags, double tf,
                          const Dual<P>* v, Dual<P>* iv, Dual<P>* qv) {
     p.mark(base);
-    const double m = p[base];
+    const double m = val(p[base]);
     const auto dj = p.sub(base + 1), djsw = p.sub(base + 1 + CDN_NJ);
     const auto sj = p.sub(base + 1 + 2 * CDN_NJ), sjsw = p.sub(base + 1 + 3 * CDN_NJ);
     const Dual<P> vdj = -v[0] * tf, vsj = -v[2] * tf;

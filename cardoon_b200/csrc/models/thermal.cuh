@@ -13,6 +13,8 @@
 #include "diode.cuh"
 #include "bjt.cuh"
 #include "mesfetc.cuh"
+#include "mosext.cuh"
+#include "ekv.cuh"
 
 #define CDN_CONST_K 1.3806488e-23        // globalVars.py:26-39
 #define CDN_CONST_Q 1.602176565e-19
@@ -239,4 +241,71 @@ CDN_HD void res_t_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
     const Dual<P> i = g * v[0];
     out.put(0, i);
     out.put(1, v[0] * i);
+}
+
+// mosekv_t: in [vdb, vgb, vsb, dT]; out [ids, idb, isb, power], q [qd, qg, qs].
+// set_temp_vars: mosEKV.py:329-357 and the extrinsic wrapper mosExt.py:252-278;
+// the folded record entries (mosEKV.IntEKV.cuda_pack) are rebuilt from them.
+// power: mosEKV.py:586-595.
+template <int P, class S>
+CDN_HD void ekv_t_eval(const PV& p, unsigned flags, const Dual<P>* v, S& out) {
+    typedef Dual<P> D;
+    DualRec<P, NP_EKV> rec;
+#pragma unroll
+    for (int k = 0; k < NP_EKV; ++k) rec.r[k] = D(p[k]);
+    const D temp = v[3] + p[P_EKV_T_temp_amb];
+    const D T = CDN_CONST_T0 + temp;
+    const D Vt = CDN_CONST_K * T / CDN_CONST_Q;
+    const double Tn = p[P_EKV_T_Tn], Tref = p[P_EKV_T_Tref], sga = p[P_EKV_T_sga];
+    const double tf = p[P_EKV_tf], gammaa = p[P_EKV_gammaa], cox = p[P_EKV_T_cox];
+    const D vt0T = p[P_EKV_T_vt0] - p[P_EKV_T_tcv] * (T - Tn);
+    const D kpT = p[P_EKV_T_kp] * dpow(T / Tn, p[P_EKV_T_bex]);
+    D kpa = kpT * (1. + p[P_EKV_T_akp] / sga);
+    kpa = select(kpa, kpa, 0.0);
+    const D t_ucrit = p[P_EKV_T_ucrit] * dpow(T / Tn, p[P_EKV_T_ucex]);
+    const D egT = 1.16 - 0.000702 * T * T / (T + 1108.);
+    const D phiT = p[P_EKV_T_phi] * T / Tref - 3. * Vt * log(T / Tref)
+                   - p[P_EKV_T_egTref] * T / Tref + egT;
+    const D t_ibb = p[P_EKV_T_ibb] * (1. + p[P_EKV_T_ibbt] * (T - Tref));
+    const D vc = t_ucrit * p[P_EKV_T_leff] * p[P_EKV_T_ns];
+    const D qb0 = gammaa * sqrt(phiT);
+    rec.r[P_EKV_Vt] = Vt;
+    rec.r[P_EKV_vt0a] = vt0T + p[P_EKV_T_avto] / sga;
+    rec.r[P_EKV_phiT] = phiT;
+    rec.r[P_EKV_vc] = vc;
+    rec.r[P_EKV_t_ucrit] = t_ucrit;
+    rec.r[P_EKV_t_ibb] = t_ibb;
+    rec.r[P_EKV_gsqphi] = gammaa * sqrt(phiT);
+    rec.r[P_EKV_vt16] = 16. * Vt * Vt;
+    rec.r[P_EKV_vt01] = 0.1 * Vt;
+    rec.r[P_EKV_vt4] = 4. * Vt;
+    rec.r[P_EKV_vdsslog] = Vt * (log(vc / (2. * Vt)) - 0.6);
+    rec.r[P_EKV_kpanpw] = kpa * p[P_EKV_T_np] * p[P_EKV_weff];
+    rec.r[P_EKV_bop] = 1. + cox * qb0 / p[P_EKV_e0] / p[P_EKV_epSi];
+    rec.r[P_EKV_coxvt] = cox * Vt;
+    rec.r[P_EKV_ntibblc] = -t_ibb * p[P_EKV_lc];
+    rec.r[P_EKV_qscale] = p[P_EKV_T_Cox] * Vt * tf;
+    // extrinsic junctions (mosExt.py:260-278)
+    const TempState<P> t = temp_state(v[3], p[P_EKV_T_temp_amb], p[P_EKV_T_Tnabs],
+                                      p[P_EKV_T_egapn], p[P_EKV_T_eg0]);
+    if (flags & F_MOSEXT_AD)
+        junction_tempvars<false>(p.sub(P_EKV_T_rawdj_isat), t, (flags & F_MOSEXT_CJ_D) != 0, rec,
+                                 P_EKV_dj_t_is);
+    if (flags & F_MOSEXT_PD)
+        junction_tempvars<false>(p.sub(P_EKV_T_rawdjsw_isat), t, (flags & F_MOSEXT_CJSW_D) != 0,
+                                 rec, P_EKV_djsw_t_is);
+    if (flags & F_MOSEXT_ASRC)
+        junction_tempvars<false>(p.sub(P_EKV_T_rawsj_isat), t, (flags & F_MOSEXT_CJ_S) != 0, rec,
+                                 P_EKV_sj_t_is);
+    if (flags & F_MOSEXT_PS)
+        junction_tempvars<false>(p.sub(P_EKV_T_rawsjsw_isat), t, (flags & F_MOSEXT_CJSW_S) != 0,
+                                 rec, P_EKV_sjsw_t_is);
+    D iv[3], qv[3];
+    ekv_intrinsic(rec, flags, v, iv, qv);
+    mosext_apply(rec, P_EKV_m, flags, tf, v, iv, qv);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out.put(k, iv[k]);
+    out.put(3, (v[0] - v[2]) * iv[0] + v[0] * iv[1] + v[2] * iv[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out.put(4 + k, qv[k]);
 }

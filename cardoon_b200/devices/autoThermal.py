@@ -11,9 +11,8 @@ evaluation; here that happens inside the model's electro-thermal kernel
 which returns the base record followed by the raw, temperature-independent
 inputs of ``set_temp_vars``, and the kernel recomputes the temperature
 dependent entries as duals (one more derivative lane for the temperature).
-Base classes without ``cuda_pack_thermal`` (so far every model except
-``diode``) still parse and build their ports, but raise when a kernel record
-is requested.
+A base class without ``cuda_pack_thermal`` still parses and builds its
+ports, but raises when a kernel record is requested.
 """
 import numpy as np
 

@@ -227,6 +227,15 @@ class IntEKV(ad.CudaModel, cir.Element):
         rec = [v[n] for n in names[:nint]]
         return flags, np.concatenate([rec, [1.]] + 4 * [EMPTY])
 
+    def thermal_raw(self):
+        """Raw inputs of set_temp_vars for the mosekv_t record
+        (param_layout.EKV_T; reference mosEKV.py:329-357)."""
+        from ..globalVars import glVar
+        return [glVar.temp, self._vt0, self._tcv, self._Tn, self.avto,
+                self._sga, self.kp, self.bex, self.akp, self.ucrit,
+                self.ucex, self.phi, self.Tref, self.egTref, self.ibb,
+                self.ibbt, self._leff, self.ns, self.np, self.cox, self._Cox]
+
     def power(self, vPort, currV):
         vds = vPort[0] - vPort[2]
         return vds * currV[0] + vPort[0] * currV[1] + vPort[2] * currV[2]

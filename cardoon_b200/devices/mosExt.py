@@ -155,6 +155,20 @@ def extrinsic_mos(IMOS):
                 recs.append(j.pack())
             return flags, np.concatenate([p, [self.m]] + recs)
 
+        def cuda_pack_thermal(self):
+            """Electro-thermal record: the isothermal record (placeholders at
+            ambient for the temperature-dependent entries) followed by the
+            raw inputs of the intrinsic model's and of this wrapper's
+            set_temp_vars (reference mosExt.py:252-278)."""
+            from ..globalVars import glVar
+            self.set_temp_vars(glVar.temp)
+            flags, base = ExtMOS.cuda_pack(self)
+            raw = [j.pack_raw() if j is not None else EMPTY
+                   for j in (self.dj, self.djsw, self.sj, self.sjsw)]
+            extra = list(IMOS.thermal_raw(self)) \
+                + [self._Tnabs, self._egapn, self.eg0]
+            return flags, np.concatenate([base, extra] + raw)
+
         def power(self, vPort, currV):
             return IMOS.power(self, vPort, currV)
 

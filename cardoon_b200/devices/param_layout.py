@@ -22,7 +22,7 @@ def _junc(prefix):
 
 MODEL_IDS = dict(diode=0, bjt=1, svbjt=2, bsim3=3, ekv=4, mesfetc=5,
                  memr=6, svdiode=7, diode_t=8, bjt_t=9, svbjt_t=10,
-                 mesfetc_t=11, svdiode_t=12, res_t=13)
+                 mesfetc_t=11, svdiode_t=12, res_t=13, ekv_t=14)
 
 # raw (temperature-independent) junction record of the electro-thermal
 # variants: the inputs of Junction.set_temp_vars (reference diode.py:53-72);
@@ -95,6 +95,12 @@ EKV = ['tf', 'vt0a', 'deltavRSCE', 'phiT', 'gsqphi', 'gammaa', 'g2o4', 'go2',
        'lmin2', 'kpanpw', 'bop', 'coxvt', 'e0', 'epSi', 'eta', 'ibn2', 'iba',
        't_ibb', 'ntibblc', 'qscale', 'qox'] + MOSEXT
 EKV_FLAGS = MOSEXT_FLAGS + ['SIMPLE']
+# mosekv_t: raw inputs of set_temp_vars (reference mosEKV.py:329-357,
+# mosExt.py:252-278)
+EKV_T = EKV + ['temp_amb', 'vt0', 'tcv', 'Tn', 'avto', 'sga', 'kp', 'bex',
+               'akp', 'ucrit', 'ucex', 'phi', 'Tref', 'egTref', 'ibb', 'ibbt',
+               'leff', 'ns', 'np', 'cox', 'Cox', 'Tnabs', 'egapn', 'eg0'] \
+    + _jraw('rawdj') + _jraw('rawdjsw') + _jraw('rawsj') + _jraw('rawsjsw')
 
 MESFETC = ['area', 'ib0', 'vbd', 'k6', 'Beta', 'vds0', 'a0', 'a1', 'a2',
            'a3', 'gama', 'idsFac', 'Vt0'] + _junc('diogs') + _junc('diogd')
@@ -113,6 +119,7 @@ LAYOUTS = dict(diode=(DIODE, DIODE_FLAGS), svdiode=(SVDIODE, SVDIODE_FLAGS),
                svbjt_t=(BJT_T, BJT_FLAGS),
                mesfetc_t=(MESFETC_T, MESFETC_FLAGS),
                svdiode_t=(SVDIODE_T, SVDIODE_FLAGS), res_t=(RES_T, []),
+               ekv_t=(EKV_T, EKV_FLAGS),
                bjt=(BJT, BJT_FLAGS), svbjt=(BJT, BJT_FLAGS),
                bsim3=(BSIM3, BSIM3_FLAGS), ekv=(EKV, EKV_FLAGS),
                mesfetc=(MESFETC, MESFETC_FLAGS), memr=(MEMR, MEMR_FLAGS))

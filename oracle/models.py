@@ -506,7 +506,7 @@ def ekv_cqs(s, v):
     vd, vs = condassign(swap, vd, vs), condassign(swap, vs, vd)
     Vt = s._Vt
     ga = s._gammaa
-    vgprime = vg - s._vt0a - s._deltavRSCE + s.phiT + ga * np.sqrt(s.phiT)
+    vgprime = vg - s._vt0a - s._deltavRSCE + s.phiT + ga * sqrt(s.phiT)
     vp0 = vgprime - s.phiT - ga * (sqrt(vgprime + ga * ga / 4.) - ga / 2.)
     vp0 = condassign(vgprime, vp0, -s.phiT)
     tmp = 16. * Vt * Vt
@@ -527,7 +527,7 @@ def ekv_cqs(s, v):
     tmp = sqrt(i_f) - 0.75 * log(i_f)
     vdssprime = sqrt(0.25 + Vt * tmp / s._vc) - 0.5
     vdssprime = vdssprime * s._vc
-    vdssprime = vdssprime + Vt * (np.log(s._vc / (2. * Vt)) - 0.6)
+    vdssprime = vdssprime + Vt * (log(s._vc / (2. * Vt)) - 0.6)
     tmp = sqrt(i_f) - vdss / Vt
     deltav = sqrt(s.Lambda * tmp + 1. / 64)
     deltav = deltav * (4. * Vt)
@@ -739,6 +739,37 @@ def res_temp_vars(dev, temp):
     return d
 
 
+def ekv_temp_vars(dev, temp):
+    """mosEKV.py:329-357 + extrinsic wrapper mosExt.py:252-278."""
+    d = _Proxy(dev)
+    T = T_ZERO + temp
+    d._Vt = K_BOLTZ * T / Q_ELEC
+    vt0T = dev._vt0 - dev._tcv * (T - dev._Tn)
+    d._vt0a = vt0T + dev.avto / dev._sga
+    kpT = dev.kp * D.power(T / dev._Tn, dev.bex)
+    kpa = kpT * (1 + dev.akp / dev._sga)
+    d.kpa = condassign(kpa, kpa, 0.)
+    d._t_ucrit = dev.ucrit * D.power(T / dev._Tn, dev.ucex)
+    egT = 1.16 - 0.000702 * T * T / (T + 1108.)
+    d.phiT = dev.phi * T / dev.Tref - 3. * d._Vt * log(T / dev.Tref) \
+        - dev.egTref * T / dev.Tref + egT
+    d._t_ibb = dev.ibb * (1. + dev.ibbt * (T - dev.Tref))
+    d._vc = d._t_ucrit * dev._leff * dev.ns
+    d._qb0 = dev._gammaa * sqrt(d.phiT)
+    egap_t = dev.eg0 - .000702 * (T * T) / (T + 1108.)
+    for name in ('dj', 'djsw', 'sj', 'sjsw'):
+        j = getattr(dev, name)
+        if j is not None:
+            setattr(d, name, junction_temp_vars(j, T, dev._Tnabs, d._Vt,
+                                                dev._egapn, egap_t))
+    return d
+
+
+def ekv_power(d, v, i):
+    """mosEKV.py:586-595."""
+    return (v[0] - v[2]) * i[0] + v[0] * i[1] + v[2] * i[2]
+
+
 def mesfetc_temp_vars(dev, temp):
     """mesfetc.py:160-189."""
     d = _Proxy(dev)
@@ -813,6 +844,8 @@ _THERMAL['svdiode'] = (svdiode_temp_vars, svdiode_cqs,
                        lambda d, v, i: i[0] * i[1] / dev_gyr())
 _THERMAL['res'] = (res_temp_vars, lambda d, v: ([d.g * v[0]], []),
                    lambda d, v, i: v[0] * i[0])           # resistor.py:123-138
+_THERMAL['mosekv'] = (ekv_temp_vars,
+                      lambda d, v: mosext_cqs(d, v, ekv_cqs), ekv_power)
 _THERMAL['mesfetc'] = (mesfetc_temp_vars, mesfetc_cqs, mesfetc_power)
 _THERMAL['bjt'] = (bjt_temp_vars,
                    lambda d, v: extrinsic_bjt_cqs(d, v, bjt_cqs), bjt_power)

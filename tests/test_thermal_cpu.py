@@ -300,3 +300,39 @@ def test_svdiode_and_resistor_thermal_equal_isothermal():
         assert np.allclose(o[1], g * v[0] * v[0], rtol=1e-13)
         dg = -g * (4e-3 + 2e-5 * d_) / (1. + (4e-3 + 1e-5 * d_) * d_)
         assert np.allclose(j[0, 1], dg * v[0], rtol=1e-10)
+
+
+# ---- EKV: mosekv_t -----------------------------------------------------------
+EKV_KW = dict(w=30e-6, l=1e-6, ad=5e-11, asrc=5e-11, pd=4e-5, ps=4e-5,
+              cj=3e-4, cjsw=2e-10, js=1e-3, tcv=1.5e-3, bex=-1.4, ucex=0.9,
+              ibbt=8e-4, iba=2e8, ibb=4e8)
+
+
+def test_mosekv_thermal_equals_isothermal_at_port_temperature():
+    rng = np.random.default_rng(12)
+    for typ in ('n', 'p'):
+        sgn = 1. if typ == 'n' else -1.
+        for dT in (0., 45.):
+            dt = S.make_element('mosekv_t', [1, 2, 3, 4, 9, 0], type=typ,
+                                **EKV_KW)
+            d = S.make_element('mosekv', [1, 2, 3, 4], type=typ,
+                               temp=glVar.temp + dT, **EKV_KW)
+            assert len(dt.controlPorts) == 4 and len(dt.csOutPorts) == 4
+            x = sgn * rng.uniform(-0.3, 3.3, size=(3, 256))
+            xt = np.vstack([x, np.full((1, 256), dT)])
+            ot, jt = device_eval(dt, xt, True)
+            oi, ji = device_eval(d, x, True)
+            assert np.allclose(ot[:3], oi[:3], rtol=1e-10, atol=1e-300)
+            assert np.allclose(ot[4:], oi[3:], rtol=1e-10, atol=1e-300)
+            pw = np.array([d.power(x[:, k], oi[:3, k]) for k in range(256)])
+            assert np.allclose(ot[3], pw, rtol=1e-10, atol=1e-300)
+            assert np.allclose(jt[:3, :3], ji[:3], rtol=1e-9, atol=1e-300)
+    h = 1e-3
+    e = np.zeros_like(xt)
+    e[3] = h
+    o, j = device_eval(dt, xt, True)
+    fd = (device_eval(dt, xt + e, False)[0]
+          - device_eval(dt, xt - e, False)[0]) / (2. * h)
+    scale = np.abs(j[:, 3]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(fd - j[:, 3]) <= 5e-6 * np.abs(j[:, 3])
+                  + 1e-8 * scale)

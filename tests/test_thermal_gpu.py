@@ -163,3 +163,38 @@ def test_op_thermal_mix(lib):
     check_op(x, ref['x'])
     rows = ref['idx'].name_to_row()
     assert 5. < x[rows['th']] < 80.          # tens of degrees of self-heating
+
+
+# ---- EKV: mosekv_t -----------------------------------------------------------
+from tests.test_thermal_cpu import EKV_KW                      # noqa: E402
+
+EKV_T_DECK = """# self-heating EKV inverter stage
+.options temp=30
+vdc:vdd 1 gnd vdc=3.3
+vdc:vg 2 gnd vdc=1.4
+res:rd 1 3 r=2k
+mosekv_t:m1 3 2 gnd gnd th gnd w=30e-6 l=1e-6 ad=5e-11 asrc=5e-11 cj=3e-4 js=1e-3 tcv=1.5e-3 bex=-1.4
+res:rth th gnd r=2k
+.end
+"""
+
+
+def test_mosekv_t_kernel_and_op(lib):
+    from tests.test_ac_cpu import load_text
+    rng = np.random.default_rng(51)
+    n = 1024
+    for typ in ('n', 'p'):
+        sgn = 1. if typ == 'n' else -1.
+        dt = S.make_element('mosekv_t', [1, 2, 3, 4, 9, 0], type=typ,
+                            **EKV_KW)
+        x = np.vstack([sgn * rng.uniform(-0.3, 3.3, size=(3, n)),
+                       rng.uniform(-40., 120., (1, n))])
+        check(lib, dt, x, jtol=1e-7)
+    ckt, _ = load_text(EKV_T_DECK)
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    x, res, it = solve(dc.get_guess(), dc.get_source(), dc.convergence_helpers)
+    ref = R.run_op(ckt, glVar)
+    assert abs(it - ref['iterations']) <= 1
+    check_op(x, ref['x'])
+    assert x[ref['idx'].name_to_row()['th']] > 0.5
