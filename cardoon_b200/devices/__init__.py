@@ -12,7 +12,7 @@ from . import autoThermal
 
 netElemList = ['linear', 'memristor', 'diode', 'svdiode', 'bjt', 'svbjt',
                'mosEKV',
-               'mosBSIM3v3', 'mesfetc', 'tlinpy4']
+               'mosBSIM3v3', 'mesfetc', 'tlinpy4', 'tlinps4']
 
 devClass = {}
 

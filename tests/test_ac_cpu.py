@@ -105,3 +105,24 @@ def test_frequency_defined_line_closed_form():
     assert np.allclose(r['X'][rows['2']], v2, rtol=1e-6)
     # operating point: 1 V behind 1k into (50 + line) || 50
     assert abs(r['x_op'][rows['2']] - r['x_op'][rows['1']]) < 1e-3
+
+
+def test_sparameter_line_equals_y_parameter_line():
+    """tlinps4 (waves on internal ports) and tlinpy4 with nsect=0 (plain Y
+    parameters) describe the same line: identical AC node voltages."""
+    deck = """
+isin:i1 gnd 4 idc=2m acmag=1.
+res:r1 4 2 r=100
+tlin{0}:t1 2 gnd 3 gnd tand=1e-3 z0mag=50 alpha=2. k=3. length=0.07
+res:r2 3 gnd r=75
+.end
+"""
+    f = np.linspace(1e9, 5e9, 40)
+    res = []
+    for kind in ('py4', 'ps4'):
+        ckt, _ = load_text(deck.format(kind))
+        r = R.run_ac(ckt, glVar, f)
+        rows = r['idx'].name_to_row()
+        res.append((r['X'][rows['2']], r['X'][rows['3']]))
+    assert np.allclose(res[0][0], res[1][0], rtol=1e-9)
+    assert np.allclose(res[0][1], res[1][1], rtol=1e-9)

@@ -7,8 +7,8 @@ test/run_tests.py runs them (parse_net + run_analyses + the .npz files of the
 from the oracle (tests/regress.py) -- the reference's *_ref.npz files are not
 in its tree.
 
-15 of the 18 decks run; the other three need devices this repository does not
-build (ACM MOSFETs, the S-parameter line tlinps4).
+16 of the 18 decks run; the other two need the ACM MOSFET models, which this
+repository does not build.
 """
 import os
 
@@ -22,8 +22,9 @@ DECKS = ['bias_npn.net', 'diode_thermal.net', 'inv_EKV.net',
          'inverter_chain.net', 'lma411_cascade.net', 'mesfetc_plain.net',
          'mesfetc_thermal.net', 'npn_thermal.net', 'oscillator.net',
          'rctransient.net', 'ring_osc_ahkab.net', 'soliton.net',
-         'sum741_profile.net', 'thermal_mixer.net', 'thermal_rf_amp.net']
-UNSUPPORTED = ['current_source.net', 'inv_ACM.net', 'tlinpy.net']
+         'sum741_profile.net', 'thermal_mixer.net', 'thermal_rf_amp.net',
+         'tlinpy.net']
+UNSUPPORTED = ['current_source.net', 'inv_ACM.net']
 
 
 @pytest.mark.parametrize('deck', DECKS)
