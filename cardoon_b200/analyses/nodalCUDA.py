@@ -223,6 +223,19 @@ def run_AC(ckt, fvec):
     return xVec
 
 
+def add_to_diagonal(M, vec):
+    """Adds vec to the leading diagonal entries of the dense matrix M
+    (nodal.py:405-416)."""
+    n = len(vec)
+    M[0:n, 0:n] += np.diag(vec)
+    return M
+
+
+def get_submatrix(M, n):
+    """Copy of the n first columns of M (nodal.py:418-426)."""
+    return M[:, 0:n].copy()
+
+
 def get_guess(ckt):
     """Initial guess from the devices' ``vPortGuess`` (nodal.py:723-740):
     only the positive node of each control port is written."""
@@ -963,6 +976,35 @@ class _NLFunction(object):
         e.simple_op(L.OP_SOLVE)
         self.deltaxVec = e.view('dx').cpu().numpy()
         return self.deltaxVec
+
+    def solve_linear_system(self, b):
+        """Solve ``Jac x = b`` with the factors of the last
+        ``factor_and_solve`` (reference nodal.py:629-646, nodalSP.py:305-332);
+        ``b`` may be a matrix, solved column by column.  The residual vector
+        the chord predictor relies on is left untouched."""
+        e = self.engine
+        torch = e.lib.torch
+        b = np.asarray(b, dtype=float)
+        keep = e.view('ivec').clone()
+        cols = b.reshape(b.shape[0], -1)
+        x = np.zeros_like(cols)
+        for k in range(cols.shape[1]):
+            if np.any(cols[:, k] != 0.):          # zero rhs: skipped
+                e.view('ivec').zero_()
+                e.view('sv').copy_(torch.as_tensor(
+                    np.ascontiguousarray(cols[:, k])))
+                e.simple_op(L.OP_CHORD)
+                x[:, k] = e.view('dx').cpu().numpy()
+        e.view('ivec').copy_(keep)
+        return x.reshape(b.shape)
+
+    def get_adjoint_voltages(self, d):
+        """Transposed solve for sensitivities (nodal.py:661-670).  No
+        analysis of the reference's main tree calls it and the device engine
+        keeps no transposed triangular schedules."""
+        raise NotImplementedError(
+            'get_adjoint_voltages: transposed solves are not provided by the '
+            'CUDA back-end')
 
     def get_chord_deltax(self, sV, iVec=None):
         e = self.engine

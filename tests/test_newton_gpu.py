@@ -195,6 +195,21 @@ def test_nd_interface_stepwise(lib):
     dx = dc.factor_and_solve(dc.get_source() - iVec, Jac)
     assert np.allclose(dx, np.linalg.solve(J_r, rdc.get_source() - iv_r),
                        rtol=1e-6, atol=1e-10)
+    # further solves with the same factors (nodal.py:629-646): vector and
+    # matrix right-hand sides, zero columns skipped, residual vector kept
+    rng = np.random.default_rng(3)
+    B = rng.normal(size=(len(x), 3))
+    B[:, 1] = 0.
+    X = dc.solve_linear_system(B)
+    assert np.allclose(X, np.linalg.solve(J_r, B), rtol=1e-6, atol=1e-10)
+    xb = dc.solve_linear_system(B[:, 0])
+    assert np.allclose(xb, X[:, 0], rtol=0, atol=0)
+    assert np.array_equal(dc.engine.view('ivec').cpu().numpy(), iVec)
+    assert np.array_equal(nd.get_submatrix(J_r, 2), J_r[:, :2])
+    assert np.allclose(nd.add_to_diagonal(np.zeros((3, 3)), [1., 2.]),
+                       np.diag([1., 2., 0.]))
+    with pytest.raises(NotImplementedError):
+        dc.get_adjoint_voltages(B[:, 0])
     # stepwise transient, host loop as in tran.py:171-206
     timeVec = np.arange(0., an.tstop, an.tstep)[:30]
     tran.set_IC(an.tstep)
