@@ -485,11 +485,40 @@ __device__ __forceinline__ double row_sum(const cdn_plan_dev& P, const Ws& w, co
                                           double a0, int r, int first, int stride) {
     double acc = 0.0;
     const int l0 = CDN_LD(P.r_lin_ptr + r), l1 = CDN_LD(P.r_lin_ptr + r + 1);
-    for (int k = l0 + first; k < l1; k += stride) {
-        double g = CDN_LD(P.r_lin_g + k);
-        if (o.use_q) g += a0 * CDN_LD(P.r_lin_c + k);
-        if (o.gmin != 0.0) g += o.gmin * CDN_LD(P.r_lin_gones + k);
-        acc += g * w.x[CDN_LD(P.r_lin_col + k)];
+    if (stride == 1) {
+        // groups of four entries with independent loads (short rows are the
+        // rule: the index -> coefficient -> x chain of one entry is three
+        // dependent loads, and four of them overlap); lanes past the end of
+        // the row re-read its first entry with a zero coefficient
+        double b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        for (int k = l0; k < l1; k += 4) {
+            const int k1 = (k + 1 < l1) ? k + 1 : l0, k2 = (k + 2 < l1) ? k + 2 : l0;
+            const int k3 = (k + 3 < l1) ? k + 3 : l0;
+            double g0 = CDN_LD(P.r_lin_g + k), g1 = CDN_LD(P.r_lin_g + k1);
+            double g2 = CDN_LD(P.r_lin_g + k2), g3 = CDN_LD(P.r_lin_g + k3);
+            if (o.use_q) {
+                g0 += a0 * CDN_LD(P.r_lin_c + k); g1 += a0 * CDN_LD(P.r_lin_c + k1);
+                g2 += a0 * CDN_LD(P.r_lin_c + k2); g3 += a0 * CDN_LD(P.r_lin_c + k3);
+            }
+            if (o.gmin != 0.0) {
+                g0 += o.gmin * CDN_LD(P.r_lin_gones + k); g1 += o.gmin * CDN_LD(P.r_lin_gones + k1);
+                g2 += o.gmin * CDN_LD(P.r_lin_gones + k2); g3 += o.gmin * CDN_LD(P.r_lin_gones + k3);
+            }
+            const double x0 = w.x[CDN_LD(P.r_lin_col + k)], x1 = w.x[CDN_LD(P.r_lin_col + k1)];
+            const double x2 = w.x[CDN_LD(P.r_lin_col + k2)], x3 = w.x[CDN_LD(P.r_lin_col + k3)];
+            acc = fma(g0, x0, acc);
+            b1 = fma((k + 1 < l1) ? g1 : 0.0, x1, b1);
+            b2 = fma((k + 2 < l1) ? g2 : 0.0, x2, b2);
+            b3 = fma((k + 3 < l1) ? g3 : 0.0, x3, b3);
+        }
+        acc += (b1 + b2) + b3;
+    } else {
+        for (int k = l0 + first; k < l1; k += stride) {
+            double g = CDN_LD(P.r_lin_g + k);
+            if (o.use_q) g += a0 * CDN_LD(P.r_lin_c + k);
+            if (o.gmin != 0.0) g += o.gmin * CDN_LD(P.r_lin_gones + k);
+            acc += g * w.x[CDN_LD(P.r_lin_col + k)];
+        }
     }
     // device outputs: branch-free, the sign and the a0 factor of charge rows
     // are decoded from the packed entry (DC plans hold no charge entries)
