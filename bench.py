@@ -285,10 +285,29 @@ def gp_inputs(n, seed=4321):
                 nout=spec['ncs'] + spec['nqs'])
 
 
-def run_gp_leg(lib, torch, n, steps, warmup, D):
+def thermal_inputs(n, seed=987):
+    """Electro-thermal svbjt_t of test/npn_thermal.net (x1, x2, v_ib, v_sub,
+    dT): the `_t` kernels rebuild the temperature laws per evaluation."""
+    from tests import support as S
+    ckt, _ = S.load_circuit(S.net('npn_thermal.net'))
+    e = S.nonlinear_elements(ckt)[0]
+    spec = e.cuda_spec()
+    rng = np.random.default_rng(seed)
+    xin = rng.uniform(-1., 1., size=(spec['nxin'], n))
+    xin[0] = rng.uniform(-20., 45., size=n)
+    xin[1] = rng.uniform(-50., 30., size=n)
+    xin[-1] = rng.uniform(-20., 100., size=n)
+    return dict(elem=e, spec=spec, xin=xin, n=n, nxin=spec['nxin'],
+                nout=spec['ncs'] + spec['nqs'],
+                label='svbjt_t (electro-thermal state-variable Gummel-Poon, '
+                      'npn_thermal.net)')
+
+
+def run_gp_leg(lib, torch, n, steps, warmup, D, g=None):
     """Second half of BASELINE.json's device-eval metric: GP evals/s with
-    the same timing rules; reported inside the deveval line's config."""
-    g = gp_inputs(n)
+    the same timing rules; reported inside the deveval line's config.  Also
+    used for the electro-thermal leg (g = thermal_inputs(n))."""
+    g = g or gp_inputs(n)
     spec = g['spec']
     # per-instance records in HBM like the BSIM3 leg (identical columns)
     params = lib.dev(spec['params'].reshape(-1, 1)).expand(-1, n).contiguous()
@@ -309,7 +328,8 @@ def run_gp_leg(lib, torch, n, steps, warmup, D):
     torch.cuda.synchronize()
     o = out[:, :2048].cpu().numpy()
     err = float(np.max(np.abs(o - o_ref) / (np.abs(o_ref) + 1e-30)))
-    return dict(model='bjt (Gummel-Poon, oscillator.net t122)', instances=n,
+    return dict(model=g.get('label', 'bjt (Gummel-Poon, oscillator.net t122)'),
+                instances=n,
                 nxin=g['nxin'], nout=g['nout'],
                 evals_per_s=n * steps / (ms * 1e-3), ms_per_step=ms / steps,
                 flop_per_eval=flop, transcendental_per_eval=trans,
@@ -385,6 +405,8 @@ def run_deveval(args, D):
 
     # every rank runs the Gummel-Poon leg (it holds a barrier)
     gp = run_gp_leg(lib, torch, n, args.steps, args.warmup, D)
+    th = run_gp_leg(lib, torch, n // 4, args.steps, args.warmup, D,
+                    thermal_inputs(n // 4))
     line = None
     if D.rank == 0:
         flop, trans = bsim3_flops(inp)
@@ -427,6 +449,7 @@ def run_deveval(args, D):
                            'channel type)', fp64=fp64, hbm=hbm_r)
         cpu = cpu_baseline_deveval(inp)
         gp['fp64_frac'] = gp['evals_per_s'] * gp['flop_per_eval'] / peak
+        th['fp64_frac'] = th['evals_per_s'] * th['flop_per_eval'] / peak
         line = dict(metric='device evals/s (BSIM3v3 mosbsim3, value + '
                            'Jacobian)', value=value, unit='device evals/s',
                     n_gpus=D.world, steps=args.steps, warmup=args.warmup,
@@ -437,11 +460,110 @@ def run_deveval(args, D):
                                 'GPU (half nch, half pch), per-instance '
                                 'parameter columns ({1} doubles each) in HBM'
                                 .format(n, npar), instances_per_gpu=n,
-                                gummel_poon=gp,
+                                gummel_poon=gp, electro_thermal=th,
                                 l2='inputs larger than L2 ({0:.1f} GB of '
                                    'parameters per step)'.format(pbytes
                                                                  / 1e9)),
                     clocks=clocks, e2e=e2e, gpu_launches=timed_launches,
+                    roofline=roof, cpu_baseline=cpu)
+    return line
+
+
+# ---------------------------------------------------------------------------
+# workload: AC sweep
+# ---------------------------------------------------------------------------
+def ac_setup(nf):
+    """test/sum741_profile.net (741 op-amp summing amplifier, 26 svbjt, 189
+    unknowns): operating point on the device, then the operands of a
+    log sweep of nf points from 100 Hz to 1 MHz."""
+    from tests import support as S
+    from cardoon_b200.analyses import nodalCUDA as nd
+    from cardoon_b200.analyses.fsolve import solve
+    path = os.path.join(os.path.dirname(S.net('x')), 'reference_tests',
+                        'sum741_profile.net')
+    ckt, _ = S.load_circuit(path)
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    x, res, it = solve(dc.get_guess(), dc.get_source(), dc.convergence_helpers)
+    dc.save_OP(x)
+    f = np.logspace(2., 6., nf)
+    return ckt, path, f, nd.ac_operands(ckt, f)
+
+
+def run_ac(args, D):
+    torch = D.torch
+    from cardoon_b200._lib import get_lib
+    lib = get_lib(D.local)
+    nf = args.n or 2048
+    ckt, path, f, ops = ac_setup(nf)
+    n = ckt.nD_dimension
+    st = lib.ac_prepare(*ops)
+
+    def step():
+        lib.ac_launch(st)
+
+    clk = ClockSampler(D.local)
+    clk.start()
+    ms, t0, t1 = timed_steps(D, step, args.steps, args.warmup)
+    clocks = clk.stop(t0, t1)
+    x = lib.ac_fetch(st)
+    value = D.world * nf * args.steps / (ms * 1e-3)
+
+    def e2e_step():
+        lib.ac_solve(*ops)          # host operands in, host result out
+
+    ne = max(2, min(args.steps, 5))
+    ms_e, _, _ = timed_steps(D, e2e_step, ne, 1)
+    e2e = dict(value=D.world * nf * ne / (ms_e * 1e-3),
+               unit='frequency points/s',
+               h2d_bytes_per_step=int(2 * n * n * 8 + nf * 8 + n * 16),
+               d2h_bytes_per_step=int(nf * n * 16))
+    line = None
+    if D.rank == 0:
+        peak = lib.fp64_peak()
+        # complex LU: n^3/3 multiply-adds of 8 real flops, two triangular
+        # solves of n^2 / 2 each
+        flop = 8. * (n ** 3 / 3. + n ** 2)
+        t_step = ms * 1e-3 / args.steps
+        ach = nf * flop / t_step / 1e12
+        roof = dict(bound='fp64', achieved=ach, peak=peak / 1e12,
+                    unit='TFLOP/s', frac=ach / (peak / 1e12), traffic=None,
+                    kernel='ac_solve_kernel (one CTA per frequency, matrix '
+                           'in the L2-resident workspace)',
+                    peak_source='cdn_fp64_peak (DFMA microbenchmark, this '
+                                'run)', flop_per_frequency=flop,
+                    workspace_bytes=int(nf * n * n * 16))
+        # CPU: the oracle's per-frequency loop on a sample of the sweep
+        from oracle import nodal_ref as R
+        from tests import support as S
+        from cardoon_b200.globalVars import glVar
+        ckt2, _ = S.load_circuit(path)
+        ns = 64
+        tc = time.time()
+        ref = R.run_ac(ckt2, glVar, f[:: nf // ns][:ns])
+        tc = time.time() - tc
+        err = float(np.max(np.abs(x[:: nf // ns][:ns].T - ref['X']))
+                    / np.max(np.abs(ref['X'])))
+        cpu = dict(value=ns / tc, unit='frequency points/s', cores=1,
+                   kind='port',
+                   sample='{0} of the {1} frequencies incl. the operating '
+                          'point (numpy oracle: per-frequency assembly + '
+                          'scipy.linalg.solve as nodal.py:346-372)'.format(
+                              ns, nf))
+        line = dict(metric='AC frequency points/s', value=value,
+                    unit='frequency points/s', n_gpus=D.world,
+                    steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True,
+                    scaling='weak', vs_baseline=None, dtype='c128',
+                    data='synthetic',
+                    config=dict(workload='ac: test/sum741_profile.net '
+                                '(N={0}), {1}-point log sweep 100 Hz - 1 MHz '
+                                'per GPU; one step = one cdn_ac_solve launch'
+                                .format(n, nf), unknowns=n, frequencies=nf,
+                                max_rel_err_vs_oracle=err,
+                                l2='per-frequency matrices ({0:.2f} GB) '
+                                   'exceed L2'.format(nf * n * n * 16 / 1e9)),
+                    clocks=clocks, e2e=e2e, gpu_launches=args.steps,
                     roofline=roof, cpu_baseline=cpu)
     return line
 
@@ -948,6 +1070,23 @@ def run_reference(args):
         cpu = cpu_baseline_chain(args.n or 100000, K=300, max_samples=10)
         metric = 'inverter-chain tran timepoints/s'
         wl = 'chain: synthetic BSIM3v3 inverter chain'
+    elif args.workload == 'ac':
+        from oracle import nodal_ref as R
+        from tests import support as S
+        from cardoon_b200.globalVars import glVar
+        path = os.path.join(os.path.dirname(S.net('x')), 'reference_tests',
+                            'sum741_profile.net')
+        ckt, _ = S.load_circuit(path)
+        ns = 256
+        t0 = time.time()
+        R.run_ac(ckt, glVar, np.logspace(2., 6., ns))
+        cpu = dict(value=ns / (time.time() - t0), unit='frequency points/s',
+                   cores=1, kind='port',
+                   sample='{0}-point log sweep incl. the operating point '
+                          '(numpy oracle, one scipy.linalg.solve per '
+                          'frequency as nodal.py:346-372)'.format(ns))
+        metric = 'AC frequency points/s'
+        wl = 'ac: test/sum741_profile.net'
     else:
         cpu = cpu_baseline_soliton(max_samples=300)
         metric = 'soliton tran timepoints/s'
@@ -978,7 +1117,7 @@ def main():
     ap.add_argument('--impl', default='native',
                     choices=['native', 'reference'])
     ap.add_argument('--workload', default='mc',
-                    choices=['deveval', 'mc', 'soliton', 'chain'])
+                    choices=['deveval', 'mc', 'soliton', 'chain', 'ac'])
     ap.add_argument('--minblocks', type=int, default=0,
                     help='deveval tuning: CTAs/SM register limit (0 = default)')
     ap.add_argument('--npre', type=int, default=-1,
@@ -1001,7 +1140,7 @@ def main():
         g.build()
     D = Dist(args.gpus)
     D.barrier()
-    line = dict(deveval=run_deveval, mc=run_mc, soliton=run_soliton,
+    line = dict(deveval=run_deveval, mc=run_mc, soliton=run_soliton, ac=run_ac,
                 chain=run_chain)[args.workload](args, D)
     if D.rank == 0:
         emit(line)

@@ -205,12 +205,9 @@ class Lib(object):
         return (out.cpu().numpy(),
                 jac.cpu().numpy() if jac is not None else None)
 
-    def ac_solve(self, G, Cm, delayed, freqs, sVec, fd_rc=(), fd_val=()):
-        """x[nf, n] (complex) with Y(w) x = s for every frequency;
-        Y = G + j w C + sum (g + j w c) exp(-j w tau) over the `delayed`
-        entries (row, col, g, c, tau), plus fd_val[e][k] at (row, col) =
-        fd_rc[e] for frequency k (frequency-defined elements).  numpy in /
-        numpy out."""
+    def ac_prepare(self, G, Cm, delayed, freqs, sVec, fd_rc=(), fd_val=()):
+        """Upload the operands of an AC sweep; returns the launch state
+        (device tensors + sizes) for ``ac_launch`` / ``ac_fetch``."""
         torch = self.torch
         n = G.shape[0]
         freqs = np.ascontiguousarray(freqs, dtype=np.float64)
@@ -219,8 +216,10 @@ class Lib(object):
         d = np.array(delayed, dtype=np.float64).reshape(ndel, 5)
         s2 = np.ascontiguousarray(
             np.stack([sVec.real, sVec.imag], axis=1), dtype=np.float64)
-        ti = lambda a: torch.as_tensor(
-            np.ascontiguousarray(a, dtype=np.int32), device=self.device)
+
+        def ti(a):
+            return torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32),
+                                   device=self.device)
         nfd = len(fd_rc)
         frc = np.array(fd_rc, dtype=np.int32).reshape(nfd, 2)
         fv = np.zeros((nf, nfd, 2))
@@ -228,31 +227,51 @@ class Lib(object):
             v = np.broadcast_to(np.asarray(v, dtype=complex), (nf,))
             fv[:, e, 0] = v.real
             fv[:, e, 1] = v.imag
-        fdev = [ti(frc[:, 0]), ti(frc[:, 1]), self.dev(fv)]
-        work = self.empty((nf * n * n * 2,)) if n > 56 else None
-        x = self.empty((nf, n, 2))
-        status = self.zeros((1,), torch.int32)
-        args = [self.dev(np.ascontiguousarray(G, dtype=np.float64)),
-                self.dev(np.ascontiguousarray(Cm, dtype=np.float64)),
-                ti(d[:, 0]), ti(d[:, 1]), self.dev(d[:, 2].copy()),
-                self.dev(d[:, 3].copy()), self.dev(d[:, 4].copy()),
-                self.dev(freqs), self.dev(s2)]
+        st = dict(n=int(n), nf=int(nf), ndel=int(ndel), nfd=int(nfd),
+                  freqs_h=freqs,
+                  G=self.dev(np.ascontiguousarray(G, dtype=np.float64)),
+                  C=self.dev(np.ascontiguousarray(Cm, dtype=np.float64)),
+                  drow=ti(d[:, 0]), dcol=ti(d[:, 1]),
+                  dg=self.dev(d[:, 2].copy()), dc=self.dev(d[:, 3].copy()),
+                  dtau=self.dev(d[:, 4].copy()), frow=ti(frc[:, 0]),
+                  fcol=ti(frc[:, 1]), fval=self.dev(fv),
+                  freqs=self.dev(freqs), s=self.dev(s2),
+                  work=self.empty((nf * n * n * 2,)) if n > 56 else None,
+                  x=self.empty((nf, n, 2)),
+                  status=self.zeros((1,), torch.int32))
+        return st
+
+    def ac_launch(self, st):
+        """One ``cdn_ac_solve`` launch on the prepared operands (no sync)."""
         rc = self.dll.cdn_ac_solve(
-            self.ctx, int(n), int(nf), self.ptr(args[0]), self.ptr(args[1]),
-            int(ndel), self.ptr(args[2]), self.ptr(args[3]),
-            self.ptr(args[4]), self.ptr(args[5]), self.ptr(args[6]),
-            int(nfd), self.ptr(fdev[0]), self.ptr(fdev[1]), self.ptr(fdev[2]),
-            self.ptr(args[7]), self.ptr(args[8]), self.ptr(work),
-            self.ptr(x), self.ptr(status), self.stream())
+            self.ctx, st['n'], st['nf'], self.ptr(st['G']), self.ptr(st['C']),
+            st['ndel'], self.ptr(st['drow']), self.ptr(st['dcol']),
+            self.ptr(st['dg']), self.ptr(st['dc']), self.ptr(st['dtau']),
+            st['nfd'], self.ptr(st['frow']), self.ptr(st['fcol']),
+            self.ptr(st['fval']), self.ptr(st['freqs']), self.ptr(st['s']),
+            self.ptr(st['work']), self.ptr(st['x']), self.ptr(st['status']),
+            self.stream())
         self.check(rc)
-        torch.cuda.synchronize(self.device)
-        bad = int(status.item())
+
+    def ac_fetch(self, st):
+        self.torch.cuda.synchronize(self.device)
+        bad = int(st['status'].item())
         if bad:
             raise np.linalg.LinAlgError(
                 'AC: singular matrix at frequency {0} Hz'.format(
-                    freqs[bad - 1]))
-        xh = x.cpu().numpy()
+                    st['freqs_h'][bad - 1]))
+        xh = st['x'].cpu().numpy()
         return xh[:, :, 0] + 1j * xh[:, :, 1]
+
+    def ac_solve(self, G, Cm, delayed, freqs, sVec, fd_rc=(), fd_val=()):
+        """x[nf, n] (complex) with Y(w) x = s for every frequency;
+        Y = G + j w C + sum (g + j w c) exp(-j w tau) over the `delayed`
+        entries (row, col, g, c, tau), plus fd_val[e][k] at (row, col) =
+        fd_rc[e] for frequency k (frequency-defined elements).  numpy in /
+        numpy out."""
+        st = self.ac_prepare(G, Cm, delayed, freqs, sVec, fd_rc, fd_val)
+        self.ac_launch(st)
+        return self.ac_fetch(st)
 
     def fp64_peak(self):
         v = C.c_double()

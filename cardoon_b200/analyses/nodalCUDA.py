@@ -149,6 +149,12 @@ def _jac_entries(prow, nrow, pcol, ncol, Jac):
     return out
 
 
+def ac_operands(ckt, fvec):
+    """Operands of the AC sweep (see run_AC): (G, C, delayed, fvec, sVec,
+    fd_rc, fd_val)."""
+    return _ac_operands(ckt, fvec)
+
+
 def run_AC(ckt, fvec):
     """Set up and solve the small-signal AC equations (reference
     nodal.py:286-381).
@@ -167,6 +173,15 @@ def run_AC(ckt, fvec):
     frequency).
     """
     from .._lib import get_lib
+    x = get_lib().ac_solve(*_ac_operands(ckt, fvec))
+    xVec = np.ascontiguousarray(x.T)
+    ckt.nD_ref.aC_V = 0.
+    for k, term in enumerate(ckt.nD_termList):
+        term.aC_V = xVec[k, :]
+    return xVec
+
+
+def _ac_operands(ckt, fvec):
     n = ckt.nD_dimension
     G = np.zeros((n, n))
     Cm = np.zeros((n, n))
@@ -215,12 +230,7 @@ def run_AC(ckt, fvec):
                     for b, j in cols:
                         fd_rc.append((i, j))
                         fd_val.append(sa * sb * Ym[a, b])
-    x = get_lib().ac_solve(G, Cm, delayed, fvec, sVec, fd_rc, fd_val)
-    xVec = np.ascontiguousarray(x.T)
-    ckt.nD_ref.aC_V = 0.
-    for k, term in enumerate(ckt.nD_termList):
-        term.aC_V = xVec[k, :]
-    return xVec
+    return G, Cm, delayed, fvec, sVec, fd_rc, fd_val
 
 
 def add_to_diagonal(M, vec):

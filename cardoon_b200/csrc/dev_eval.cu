@@ -208,12 +208,11 @@ dev_eval_kernel(long n, unsigned flags, const double* __restrict__ params, long 
     eval_any<P>(MODEL, p, flags, v, sink);
 }
 
-static int g_minblocks = 0;      // tuning: 0 = default register allocation
 static int g_npre = -1;          // tuning: record rows prefetched to L1 (-1 = default)
 static int g_ring = 1;           // tuning: BSIM3 record through the shared-memory ring
 
 extern "C" int cdn_set_tuning(int key, int value) {
-    if (key == 0) { g_minblocks = value; return CDN_OK; }
+    if (key == 0) return CDN_OK;          // (retired: register-limit variants, see git history)
     if (key == 1) { g_npre = value; return CDN_OK; }
     if (key == 2) { g_ring = value; return CDN_OK; }
     return CDN_ERR_ARG;
