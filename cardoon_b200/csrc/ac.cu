@@ -34,10 +34,14 @@ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
     return r;
 }
 
-#define AC_TPB 256
 #define AC_SMEM_N 56
+#define AC_MAX_N 2048          // pivot row staged in shared memory: 32 KB
 
-__global__ void __launch_bounds__(AC_TPB)
+// AC_TPB threads per CTA: 256 for the shared-memory path, 512 for matrices in
+// the workspace (every CTA reuses one workspace slot for all its frequencies,
+// so the matrices in flight stay L2-resident)
+template <int AC_TPB>
+__global__ void __launch_bounds__(AC_TPB, 1024 / AC_TPB)
 ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __restrict__ C,
                 int ndel, const int* __restrict__ drow, const int* __restrict__ dcol,
                 const double* __restrict__ dg, const double* __restrict__ dc,
@@ -53,7 +57,9 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
     const int tid = threadIdx.x;
     const bool in_smem = n <= AC_SMEM_N;
     for (int f = blockIdx.x; f < nf; f += gridDim.x) {
-        cplx* Y = in_smem ? (cplx*)ac_sm : work + (long)f * n * n;
+        // one workspace slot per CTA, reused for all its frequencies: the
+        // matrices in flight stay L2-resident
+        cplx* Y = in_smem ? (cplx*)ac_sm : work + (long)blockIdx.x * n * n;
         cplx* x = xout + (long)f * n;
         const double w = 6.283185307179586476925287 * freqs[f];      // 2 pi f
         for (int e = tid; e < n * n; e += AC_TPB) {
@@ -124,11 +130,30 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
                 x[i] = csub(x[i], cmul(l, xk));
             }
             __syncthreads();
-            // ---- rank-1 update of the trailing block
-            const int m = n - k - 1;
-            for (int e = tid; e < m * m; e += AC_TPB) {
-                const int i = k + 1 + e / m, j = k + 1 + e % m;
-                Y[(long)i * n + j] = csub(Y[(long)i * n + j], cmul(Y[(long)i * n + k], Y[(long)k * n + j]));
+            // ---- rank-1 update of the trailing block.  The pivot row is staged
+            // in shared memory; a warp takes four rows at a time with its lanes
+            // along the (contiguous) columns, so that four independent L2
+            // loads are in flight per lane (latency, not bandwidth, is what
+            // the L2-resident matrix costs)
+            cplx* rowk = (cplx*)ac_sm + (in_smem ? (long)n * n : 0);
+            for (int j2 = k + 1 + tid; j2 < n; j2 += AC_TPB) rowk[j2] = Y[(long)k * n + j2];
+            __syncthreads();
+            for (int i0 = k + 1 + 4 * (tid >> 5); i0 < n; i0 += 4 * (AC_TPB / 32)) {
+                const int i1 = (i0 + 1 < n) ? i0 + 1 : i0, i2 = (i0 + 2 < n) ? i0 + 2 : i0;
+                const int i3 = (i0 + 3 < n) ? i0 + 3 : i0;
+                cplx* y0 = Y + (long)i0 * n;
+                cplx* y1 = Y + (long)i1 * n;
+                cplx* y2 = Y + (long)i2 * n;
+                cplx* y3 = Y + (long)i3 * n;
+                const cplx l0 = y0[k], l1 = y1[k], l2 = y2[k], l3 = y3[k];
+                for (int j2 = k + 1 + (tid & 31); j2 < n; j2 += 32) {
+                    const cplx b = rowk[j2];
+                    const cplx a0 = y0[j2], a1 = y1[j2], a2 = y2[j2], a3 = y3[j2];
+                    y0[j2] = csub(a0, cmul(l0, b));
+                    if (i1 != i0) y1[j2] = csub(a1, cmul(l1, b));
+                    if (i2 != i0) y2[j2] = csub(a2, cmul(l2, b));
+                    if (i3 != i0) y3[j2] = csub(a3, cmul(l3, b));
+                }
             }
             __syncthreads();
         }
@@ -153,7 +178,8 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
 // dtau)[ndel]; frequency-defined entries (frow, fcol)[nfd] with
 // fval[nf][nfd][2]; freqs[nf]; s[n][2] (re, im); work: nf*n*n complex when
 // n > 56 (else unused); x: [nf][n][2]; status: 0 or 1 + index of a frequency
-// whose matrix is singular.
+// whose matrix is singular.  (Only the first min(nf, 2 * SMs) matrices of
+// `work` are used.)
 extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const double* C, int ndel,
                             const int* drow, const int* dcol, const double* dg, const double* dc,
                             const double* dtau, int nfd, const int* frow, const int* fcol,
@@ -165,16 +191,33 @@ extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const 
         || (nfd > 0 && (!frow || !fcol || !fval)))
         return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: null argument");
     if (n > AC_SMEM_N && !work) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: workspace required");
+    if (n > AC_MAX_N) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: more than 2048 unknowns");
     cudaStream_t st = (cudaStream_t)stream;
-    const int smem = (n <= AC_SMEM_N) ? n * n * (int)sizeof(cplx) : 0;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ac_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return cdn_fail(ctx, CDN_ERR_CUDA, std::string("cdn_ac_solve: ") + cudaGetErrorString(e));
+    if (n <= AC_SMEM_N) {
+        const int smem = (n * n + n) * (int)sizeof(cplx);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(ac_solve_kernel<256>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return cdn_fail(ctx, CDN_ERR_CUDA, std::string("cdn_ac_solve: ") + cudaGetErrorString(e));
+        }
+        const int blocks = nf < 8 * ctx->sm_count ? nf : 8 * ctx->sm_count;
+        ac_solve_kernel<256><<<blocks, 256, smem, st>>>(n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd,
+                                                        frow, fcol, fval, freqs, s, (cplx*)work,
+                                                        (cplx*)x, status);
+    } else {
+        // exactly the resident CTAs, each looping over its share of the
+        // frequencies (a second wave would only start when the first has
+        // finished all of its matrices);
+        // two resident 512-thread CTAs per SM (64 registers per thread): the
+        // L2 round trips of one matrix's column step overlap with the other's
+        // (measured on B200, N = 189: 1 x 1024 threads 66.1 k, 2 x 512 76.8 k,
+        // 4 x 256 71.0 k frequency points/s)
+        long blocks = 2L * ctx->sm_count;
+        if (blocks > nf) blocks = nf;
+        ac_solve_kernel<512><<<(int)blocks, 512, n * (int)sizeof(cplx), st>>>(
+            n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow, fcol, fval, freqs, s, (cplx*)work,
+            (cplx*)x, status);
     }
-    const int blocks = nf < 8 * ctx->sm_count ? nf : 8 * ctx->sm_count;
-    ac_solve_kernel<<<blocks, AC_TPB, smem, st>>>(n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow,
-                                                  fcol, fval, freqs, s,
-                                                  (cplx*)work, (cplx*)x, status);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cdn_fail(ctx, CDN_ERR_CUDA, std::string("cdn_ac_solve launch: ") + cudaGetErrorString(e));
     return CDN_OK;
