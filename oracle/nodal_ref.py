@@ -810,15 +810,24 @@ def run_dc(ckt, glVar, device, param, start, stop, num):
     value; callers reload the deck."""
     idx = prepare(ckt)
     opt = Options(glVar)
-    dev = ckt.elemDict[device]
+    # no device: global temperature sweep (dc.py:137-140, 167-177)
+    dev = ckt.elemDict[device] if device else None
     sweep = np.linspace(start=start, stop=stop, num=num)
     x = RefDC(ckt, idx, opt).get_guess()
     X = np.zeros((num, idx.dimension))
     iters = np.zeros(num, dtype=int)
     resv = np.zeros(num)
     for i, value in enumerate(sweep):
-        setattr(dev, param, value)
-        dev.process_params()
+        if dev is None:
+            for elem in idx.elemList:
+                if not elem.is_set('temp'):
+                    try:
+                        elem.set_temp_vars(value)
+                    except AttributeError:
+                        pass            # element independent of temperature
+        else:
+            setattr(dev, param, value)
+            dev.process_params()
         idx = NodalIndex(ckt)                   # restore + re-process
         dc = RefDC(ckt, idx, opt)               # refresh()
         sV = dc.get_source()

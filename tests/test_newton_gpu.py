@@ -311,6 +311,32 @@ def test_dc_sweep_device_parameter(lib):
     assert np.max(np.abs(an.iterations - ref['iters'])) <= 1
 
 
+def test_dc_global_temperature_sweep(lib):
+    """`.analysis dc param=temp` without a device (dc.py:137-140, 167-177):
+    every element whose temp is not set gets set_temp_vars(value); only the
+    device records change between points."""
+    from cardoon_b200.analyses.dc import DCSweep
+    for deck in ('ac_amp.net', 'ring_osc_ahkab.net'):
+        ckt, _ = S.load_circuit(S.net(deck))
+        ckt.saveReqList = []
+        ckt.plotReqList = []
+        an = DCSweep()
+        an.set_param('param', 'temp')
+        an.set_param('start', -20.)
+        an.set_param('stop', 90.)
+        an.set_param('num', 12)
+        an.set_attributes()
+        an.run(ckt)
+        got = np.array([t.dC_v for t in ckt.nD_termList]).T
+        ckt2, _ = S.load_circuit(S.net(deck))
+        ref = R.run_dc(ckt2, glVar, None, 'temp', -20., 90., 12)
+        err = np.abs(got - ref['X'])
+        assert np.all(err < 1e-9 * np.abs(ref['X']) + 1e-12), err.max()
+        assert np.max(np.abs(an.iterations - ref['iters'])) <= 1
+        # the operating point really moves with temperature
+        assert np.max(np.abs(ref['X'][0] - ref['X'][-1])) > 1e-6
+
+
 def test_no_convergence_is_raised(lib, capsys):
     """Failure is reported the reference's way: the helpers raise
     NoConvergenceError (fsolve.py:42-54), the kernels only return a status."""
