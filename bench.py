@@ -669,6 +669,7 @@ def run_mc(args, D):
     from cardoon_b200._lib import get_lib
     lib = get_lib(D.local)
     ckt, an, bt, mc = mc_setup(lib)
+    lib.dll.cdn_set_tuning(3, args.tile_tpb)
     B = args.n or 4096
     lo = D.rank * B
     params_h = bt.pack_instances(B, mc.bsim3_ring_variation(), first=lo)
@@ -1125,6 +1126,9 @@ def main():
     ap.add_argument('--ring', type=int, default=1,
                     help='deveval tuning: BSIM3 record through the '
                          'shared-memory ring (0 = on-demand loads)')
+    ap.add_argument('--tile-tpb', type=int, default=0,
+                    help='mc tuning: threads per CTA of the tile kernel '
+                         '(128 | 256, 0 = automatic)')
     ap.add_argument('--n', type=int, default=0,
                     help='instances per GPU (0 = workload default)')
     args = ap.parse_args()

@@ -27,6 +27,9 @@ int cdn_engine_layout(cdn_plan* P, long* off) {
     return CDN_OK;
 }
 
+// tuning (cdn_set_tuning key 3): threads per CTA of the tile team, 0 = automatic
+int cdn_tune_tile_tpb = 0;
+
 int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     if (!P || !r) return CDN_ERR_ARG;
     cdn_ctx* ctx = cdn_plan_ctx(P);
@@ -84,6 +87,7 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
         // one CTA of 8 warps per SM when the batch fills the GPU: its tiles run
         // in lockstep and share the instruction cache
         c.tpb = ((long)A.B * T >= (long)ctx->sm_count * 128) ? 256 : 128;
+        if (cdn_tune_tile_tpb == 128 || cdn_tune_tile_tpb == 256) c.tpb = cdn_tune_tile_tpb;
         if (!A.ws) {
             // state in shared memory: shrink the CTA until it fits
             while (c.tpb > T && (long)(c.tpb / T) * per * 8 > 200 * 1024) c.tpb /= 2;
