@@ -495,6 +495,8 @@ def run_ac(args, D):
     from cardoon_b200._lib import get_lib
     lib = get_lib(D.local)
     nf = args.n or 2048
+    lib.dll.cdn_set_tuning(4, args.ac_blocks)
+    lib.dll.cdn_set_tuning(5, args.ac_tpb)
     ckt, path, f, ops = ac_setup(nf)
     n = ckt.nD_dimension
     st = lib.ac_prepare(*ops)
@@ -1126,6 +1128,10 @@ def main():
     ap.add_argument('--ring', type=int, default=1,
                     help='deveval tuning: BSIM3 record through the '
                          'shared-memory ring (0 = on-demand loads)')
+    ap.add_argument('--ac-blocks', type=int, default=0,
+                    help='ac tuning: CTAs (matrices) in flight, 0 = automatic')
+    ap.add_argument('--ac-tpb', type=int, default=0,
+                    help='ac tuning: threads per CTA (512 | 1024)')
     ap.add_argument('--tile-tpb', type=int, default=0,
                     help='mc tuning: threads per CTA of the tile kernel '
                          '(128 | 256, 0 = automatic)')

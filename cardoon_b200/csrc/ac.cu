@@ -173,6 +173,10 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
     }
 }
 
+// tuning (cdn_set_tuning keys 4, 5): CTAs in flight / threads per CTA of the
+// workspace path
+extern "C" { int cdn_tune_ac_blocks = 0; int cdn_tune_ac_tpb = 0; }
+
 // Reference: run_AC (analyses/nodal.py:286-381).  All pointers are device
 // pointers.  G, C: [n*n] row-major; delayed entries (drow, dcol, dg, dc,
 // dtau)[ndel]; frequency-defined entries (frow, fcol)[nfd] with
@@ -213,10 +217,16 @@ extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const 
         // (measured on B200, N = 189: 1 x 1024 threads 66.1 k, 2 x 512 76.8 k,
         // 4 x 256 71.0 k frequency points/s)
         long blocks = 2L * ctx->sm_count;
+        if (cdn_tune_ac_blocks > 0) blocks = cdn_tune_ac_blocks;
         if (blocks > nf) blocks = nf;
-        ac_solve_kernel<512><<<(int)blocks, 512, n * (int)sizeof(cplx), st>>>(
-            n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow, fcol, fval, freqs, s, (cplx*)work,
-            (cplx*)x, status);
+        if (cdn_tune_ac_tpb == 1024)
+            ac_solve_kernel<1024><<<(int)blocks, 1024, n * (int)sizeof(cplx), st>>>(
+                n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow, fcol, fval, freqs, s,
+                (cplx*)work, (cplx*)x, status);
+        else
+            ac_solve_kernel<512><<<(int)blocks, 512, n * (int)sizeof(cplx), st>>>(
+                n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow, fcol, fval, freqs, s,
+                (cplx*)work, (cplx*)x, status);
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cdn_fail(ctx, CDN_ERR_CUDA, std::string("cdn_ac_solve launch: ") + cudaGetErrorString(e));

@@ -212,12 +212,16 @@ static int g_npre = -1;          // tuning: record rows prefetched to L1 (-1 = d
 static int g_ring = 1;           // tuning: BSIM3 record through the shared-memory ring
 
 extern "C" int cdn_tune_tile_tpb;     // engine.cu
+extern "C" int cdn_tune_ac_blocks;    // ac.cu
+extern "C" int cdn_tune_ac_tpb;
 
 extern "C" int cdn_set_tuning(int key, int value) {
     if (key == 0) return CDN_OK;          // (retired: register-limit variants, see git history)
     if (key == 1) { g_npre = value; return CDN_OK; }
     if (key == 2) { g_ring = value; return CDN_OK; }
     if (key == 3) { cdn_tune_tile_tpb = value; return CDN_OK; }
+    if (key == 4) { cdn_tune_ac_blocks = value; return CDN_OK; }
+    if (key == 5) { cdn_tune_ac_tpb = value; return CDN_OK; }
     return CDN_ERR_ARG;
 }
 
