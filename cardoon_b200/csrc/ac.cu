@@ -35,7 +35,7 @@ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
 }
 
 #define AC_SMEM_N 56
-#define AC_MAX_N 2048          // pivot row staged in shared memory: 32 KB
+#define AC_MAX_N 1024          // multipliers + right-hand side in shared memory: 32 KB
 
 // AC_TPB threads per CTA: 256 for the shared-memory path, 512 for matrices in
 // the workspace (every CTA reuses one workspace slot for all its frequencies,
@@ -60,13 +60,20 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
         // one workspace slot per CTA, reused for all its frequencies: the
         // matrices in flight stay L2-resident
         cplx* Y = in_smem ? (cplx*)ac_sm : work + (long)blockIdx.x * n * n;
-        cplx* x = xout + (long)f * n;
         const double w = 6.283185307179586476925287 * freqs[f];      // 2 pi f
+        // column-major storage (AT(r, c)): the pivot search, the multipliers,
+        // the rank-1 update (lanes along the rows) and the column-oriented
+        // back substitution all walk contiguous memory; only the row swaps
+        // are strided
+#define AT(r, c) Y[(long)(c) * n + (r)]
         for (int e = tid; e < n * n; e += AC_TPB) {
-            cplx y; y.re = G[e]; y.im = w * C[e];
+            const int c = e / n, r = e - c * n;
+            cplx y; y.re = G[(long)r * n + c]; y.im = w * C[(long)r * n + c];
             Y[e] = y;
         }
-        for (int r = tid; r < n; r += AC_TPB) { cplx v; v.re = s[2 * r]; v.im = s[2 * r + 1]; x[r] = v; }
+        cplx* colk = (cplx*)ac_sm + (in_smem ? (long)n * n : 0);      // [n] multipliers
+        cplx* xs = colk + n;                                           // [n] right-hand side
+        for (int r = tid; r < n; r += AC_TPB) { cplx v; v.re = s[2 * r]; v.im = s[2 * r + 1]; xs[r] = v; }
         __syncthreads();
         if (tid == 0) {
             // delayed control ports: (g + j w c) exp(-j w tau); entries may repeat
@@ -76,12 +83,12 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
                 cplx a; a.re = dg[d]; a.im = w * dc[d];
                 cplx ph; ph.re = cs; ph.im = sn;
                 const cplx v = cmul(a, ph);
-                cplx* y = Y + (long)drow[d] * n + dcol[d];
+                cplx* y = &AT(drow[d], dcol[d]);
                 y->re += v.re; y->im += v.im;
             }
             // frequency-defined elements: fval[f][e] = (re, im)
             for (int e = 0; e < nfd; ++e) {
-                cplx* y = Y + (long)frow[e] * n + fcol[e];
+                cplx* y = &AT(frow[e], fcol[e]);
                 y->re += fval[((long)f * nfd + e) * 2];
                 y->im += fval[((long)f * nfd + e) * 2 + 1];
             }
@@ -92,7 +99,7 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
             // ---- pivot: first row with the largest |re| + |im| in column k
             double bv = -1.0; int bi = n;
             for (int i = k + tid; i < n; i += AC_TPB) {
-                const cplx y = Y[(long)i * n + k];
+                const cplx y = AT(i, k);
                 const double a = fabs(y.re) + fabs(y.im);
                 if (a > bv) { bv = a; bi = i; }
             }
@@ -114,62 +121,60 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
             if (p < 0) { singular = true; break; }
             if (p != k) {
                 for (int j = tid; j < n; j += AC_TPB) {
-                    const cplx t = Y[(long)k * n + j];
-                    Y[(long)k * n + j] = Y[(long)p * n + j];
-                    Y[(long)p * n + j] = t;
+                    const cplx t = AT(k, j);
+                    AT(k, j) = AT(p, j);
+                    AT(p, j) = t;
                 }
-                if (tid == 0) { const cplx t = x[k]; x[k] = x[p]; x[p] = t; }
+                if (tid == 0) { const cplx t = xs[k]; xs[k] = xs[p]; xs[p] = t; }
                 __syncthreads();
             }
-            // ---- multipliers, right-hand side
-            const cplx ykk = Y[(long)k * n + k];
-            const cplx xk = x[k];
+            // ---- multipliers (kept in shared memory for the update), right-hand side
+            const cplx ykk = AT(k, k);
+            const cplx xk = xs[k];
             for (int i = k + 1 + tid; i < n; i += AC_TPB) {
-                const cplx l = cdiv(Y[(long)i * n + k], ykk);
-                Y[(long)i * n + k] = l;
-                x[i] = csub(x[i], cmul(l, xk));
+                const cplx l = cdiv(AT(i, k), ykk);
+                AT(i, k) = l;
+                colk[i] = l;
+                xs[i] = csub(xs[i], cmul(l, xk));
             }
             __syncthreads();
-            // ---- rank-1 update of the trailing block.  The pivot row is staged
-            // in shared memory; a warp takes four rows at a time with its lanes
-            // along the (contiguous) columns, so that four independent L2
-            // loads are in flight per lane (latency, not bandwidth, is what
-            // the L2-resident matrix costs)
-            cplx* rowk = (cplx*)ac_sm + (in_smem ? (long)n * n : 0);
-            for (int j2 = k + 1 + tid; j2 < n; j2 += AC_TPB) rowk[j2] = Y[(long)k * n + j2];
-            __syncthreads();
-            for (int i0 = k + 1 + 4 * (tid >> 5); i0 < n; i0 += 4 * (AC_TPB / 32)) {
-                const int i1 = (i0 + 1 < n) ? i0 + 1 : i0, i2 = (i0 + 2 < n) ? i0 + 2 : i0;
-                const int i3 = (i0 + 3 < n) ? i0 + 3 : i0;
-                cplx* y0 = Y + (long)i0 * n;
-                cplx* y1 = Y + (long)i1 * n;
-                cplx* y2 = Y + (long)i2 * n;
-                cplx* y3 = Y + (long)i3 * n;
-                const cplx l0 = y0[k], l1 = y1[k], l2 = y2[k], l3 = y3[k];
-                for (int j2 = k + 1 + (tid & 31); j2 < n; j2 += 32) {
-                    const cplx b = rowk[j2];
-                    const cplx a0 = y0[j2], a1 = y1[j2], a2 = y2[j2], a3 = y3[j2];
-                    y0[j2] = csub(a0, cmul(l0, b));
-                    if (i1 != i0) y1[j2] = csub(a1, cmul(l1, b));
-                    if (i2 != i0) y2[j2] = csub(a2, cmul(l2, b));
-                    if (i3 != i0) y3[j2] = csub(a3, cmul(l3, b));
+            // ---- rank-1 update of the trailing block: a warp takes four columns
+            // at a time with its lanes along the (contiguous) rows, four
+            // independent loads in flight per lane
+            for (int j0 = k + 1 + 4 * (tid >> 5); j0 < n; j0 += 4 * (AC_TPB / 32)) {
+                const int j1 = (j0 + 1 < n) ? j0 + 1 : j0, j2 = (j0 + 2 < n) ? j0 + 2 : j0;
+                const int j3 = (j0 + 3 < n) ? j0 + 3 : j0;
+                cplx* y0 = Y + (long)j0 * n;
+                cplx* y1 = Y + (long)j1 * n;
+                cplx* y2 = Y + (long)j2 * n;
+                cplx* y3 = Y + (long)j3 * n;
+                const cplx u0 = y0[k], u1 = y1[k], u2 = y2[k], u3 = y3[k];
+                for (int i = k + 1 + (tid & 31); i < n; i += 32) {
+                    const cplx l = colk[i];
+                    const cplx a0 = y0[i], a1 = y1[i], a2 = y2[i], a3 = y3[i];
+                    y0[i] = csub(a0, cmul(l, u0));
+                    if (j1 != j0) y1[i] = csub(a1, cmul(l, u1));
+                    if (j2 != j0) y2[i] = csub(a2, cmul(l, u2));
+                    if (j3 != j0) y3[i] = csub(a3, cmul(l, u3));
                 }
             }
             __syncthreads();
         }
+        cplx* x = xout + (long)f * n;
         if (singular) {
             if (tid == 0) atomicExch(status, f + 1);
             __syncthreads();
             continue;
         }
-        // ---- back substitution
+        // ---- back substitution, column oriented: every thread forms x_k itself
+        // (one barrier per step), the column of U is contiguous
         for (int k = n - 1; k >= 0; --k) {
-            if (tid == 0) x[k] = cdiv(x[k], Y[(long)k * n + k]);
-            __syncthreads();
-            const cplx xk = x[k];
-            for (int i = tid; i < k; i += AC_TPB) x[i] = csub(x[i], cmul(Y[(long)i * n + k], xk));
+            const cplx xk = cdiv(xs[k], AT(k, k));
+            if (tid == 0) x[k] = xk;
+            for (int i = tid; i < k; i += AC_TPB) xs[i] = csub(xs[i], cmul(AT(i, k), xk));
             __syncthreads();
         }
+#undef AT
     }
 }
 
@@ -195,10 +200,10 @@ extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const 
         || (nfd > 0 && (!frow || !fcol || !fval)))
         return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: null argument");
     if (n > AC_SMEM_N && !work) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: workspace required");
-    if (n > AC_MAX_N) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: more than 2048 unknowns");
+    if (n > AC_MAX_N) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: more than 1024 unknowns");
     cudaStream_t st = (cudaStream_t)stream;
     if (n <= AC_SMEM_N) {
-        const int smem = (n * n + n) * (int)sizeof(cplx);
+        const int smem = (n * n + 2 * n) * (int)sizeof(cplx);
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(ac_solve_kernel<256>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -220,11 +225,11 @@ extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const 
         if (cdn_tune_ac_blocks > 0) blocks = cdn_tune_ac_blocks;
         if (blocks > nf) blocks = nf;
         if (cdn_tune_ac_tpb == 1024)
-            ac_solve_kernel<1024><<<(int)blocks, 1024, n * (int)sizeof(cplx), st>>>(
+            ac_solve_kernel<1024><<<(int)blocks, 1024, 2 * n * (int)sizeof(cplx), st>>>(
                 n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow, fcol, fval, freqs, s,
                 (cplx*)work, (cplx*)x, status);
         else
-            ac_solve_kernel<512><<<(int)blocks, 512, n * (int)sizeof(cplx), st>>>(
+            ac_solve_kernel<512><<<(int)blocks, 512, 2 * n * (int)sizeof(cplx), st>>>(
                 n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow, fcol, fval, freqs, s,
                 (cplx*)work, (cplx*)x, status);
     }
