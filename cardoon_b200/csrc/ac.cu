@@ -34,8 +34,36 @@ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
     return r;
 }
 
+// first row (>= k) with the largest |re| + |im| in column k of the column-major
+// matrix; -1 if the column is zero.  Two barriers.
+template <int TPB>
+__device__ __forceinline__ int ac_pivot(const cplx* Y, int n, int k, double* red_v, int* red_i, int* piv) {
+    const int tid = threadIdx.x;
+    double bv = -1.0; int bi = n;
+    for (int i = k + tid; i < n; i += TPB) {
+        const cplx y = Y[(long)k * n + i];
+        const double a = fabs(y.re) + fabs(y.im);
+        if (a > bv) { bv = a; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 1; q < TPB / 32; ++q)
+            if (red_v[q] > bv || (red_v[q] == bv && red_i[q] < bi)) { bv = red_v[q]; bi = red_i[q]; }
+        *piv = (bv > 0.0) ? bi : -1;
+    }
+    __syncthreads();
+    return *piv;
+}
+
 #define AC_SMEM_N 56
-#define AC_MAX_N 1024          // multipliers + right-hand side in shared memory: 32 KB
+#define AC_MAX_N 1024          // two multiplier columns + right-hand side in shared memory: 48 KB
 
 // AC_TPB threads per CTA: 256 for the shared-memory path, 512 for matrices in
 // the workspace (every CTA reuses one workspace slot for all its frequencies,
@@ -95,70 +123,84 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
         }
         __syncthreads();
         bool singular = false;
-        for (int k = 0; k < n; ++k) {
-            // ---- pivot: first row with the largest |re| + |im| in column k
-            double bv = -1.0; int bi = n;
-            for (int i = k + tid; i < n; i += AC_TPB) {
-                const cplx y = AT(i, k);
-                const double a = fabs(y.re) + fabs(y.im);
-                if (a > bv) { bv = a; bi = i; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
-            __syncthreads();
-            if (tid == 0) {
-                for (int q = 1; q < AC_TPB / 32; ++q)
-                    if (red_v[q] > bv || (red_v[q] == bv && red_i[q] < bi)) { bv = red_v[q]; bi = red_i[q]; }
-                piv = (bv > 0.0) ? bi : -1;
-            }
-            __syncthreads();
-            const int p = piv;
+        cplx* colk2 = xs + n;                                          // [n] second multipliers
+        // Two pivots per pass over the trailing block (rank-2 update): the
+        // block is loaded and stored once for two eliminated columns, which
+        // halves the L2 traffic per multiply-add of the unblocked algorithm.
+        for (int k = 0; k < n;) {
+            const int k1 = k + 1;
+            // ---- pivot k (column k is up to date)
+            int p = ac_pivot<AC_TPB>(Y, n, k, red_v, red_i, &piv);
             if (p < 0) { singular = true; break; }
             if (p != k) {
-                for (int j = tid; j < n; j += AC_TPB) {
-                    const cplx t = AT(k, j);
-                    AT(k, j) = AT(p, j);
-                    AT(p, j) = t;
-                }
+                for (int j = tid; j < n; j += AC_TPB) { const cplx t = AT(k, j); AT(k, j) = AT(p, j); AT(p, j) = t; }
                 if (tid == 0) { const cplx t = xs[k]; xs[k] = xs[p]; xs[p] = t; }
                 __syncthreads();
             }
-            // ---- multipliers (kept in shared memory for the update), right-hand side
-            const cplx ykk = AT(k, k);
-            const cplx xk = xs[k];
-            for (int i = k + 1 + tid; i < n; i += AC_TPB) {
-                const cplx l = cdiv(AT(i, k), ykk);
-                AT(i, k) = l;
-                colk[i] = l;
-                xs[i] = csub(xs[i], cmul(l, xk));
-            }
-            __syncthreads();
-            // ---- rank-1 update of the trailing block: a warp takes four columns
-            // at a time with its lanes along the (contiguous) rows, four
-            // independent loads in flight per lane
-            for (int j0 = k + 1 + 4 * (tid >> 5); j0 < n; j0 += 4 * (AC_TPB / 32)) {
-                const int j1 = (j0 + 1 < n) ? j0 + 1 : j0, j2 = (j0 + 2 < n) ? j0 + 2 : j0;
-                const int j3 = (j0 + 3 < n) ? j0 + 3 : j0;
-                cplx* y0 = Y + (long)j0 * n;
-                cplx* y1 = Y + (long)j1 * n;
-                cplx* y2 = Y + (long)j2 * n;
-                cplx* y3 = Y + (long)j3 * n;
-                const cplx u0 = y0[k], u1 = y1[k], u2 = y2[k], u3 = y3[k];
-                for (int i = k + 1 + (tid & 31); i < n; i += 32) {
-                    const cplx l = colk[i];
-                    const cplx a0 = y0[i], a1 = y1[i], a2 = y2[i], a3 = y3[i];
-                    y0[i] = csub(a0, cmul(l, u0));
-                    if (j1 != j0) y1[i] = csub(a1, cmul(l, u1));
-                    if (j2 != j0) y2[i] = csub(a2, cmul(l, u2));
-                    if (j3 != j0) y3[i] = csub(a3, cmul(l, u3));
+            {
+                const cplx ykk = AT(k, k);
+                const cplx xk = xs[k];
+                for (int i = k1 + tid; i < n; i += AC_TPB) {
+                    const cplx l = cdiv(AT(i, k), ykk);
+                    AT(i, k) = l;
+                    colk[i] = l;
+                    xs[i] = csub(xs[i], cmul(l, xk));
                 }
             }
             __syncthreads();
+            if (k1 == n) break;
+            // ---- bring column k+1 up to date with pivot k
+            {
+                const cplx u = AT(k, k1);
+                for (int i = k1 + tid; i < n; i += AC_TPB) AT(i, k1) = csub(AT(i, k1), cmul(colk[i], u));
+            }
+            __syncthreads();
+            // ---- pivot k+1; the pending update of the other columns commutes
+            // with the row swap as long as the multipliers are swapped too
+            p = ac_pivot<AC_TPB>(Y, n, k1, red_v, red_i, &piv);
+            if (p < 0) { singular = true; break; }
+            if (p != k1) {
+                for (int j = tid; j < n; j += AC_TPB) { const cplx t = AT(k1, j); AT(k1, j) = AT(p, j); AT(p, j) = t; }
+                if (tid == 0) {
+                    cplx t = xs[k1]; xs[k1] = xs[p]; xs[p] = t;
+                    t = colk[k1]; colk[k1] = colk[p]; colk[p] = t;
+                }
+                __syncthreads();
+            }
+            {
+                const cplx ykk = AT(k1, k1);
+                const cplx xk = xs[k1];
+                for (int i = k1 + 1 + tid; i < n; i += AC_TPB) {
+                    const cplx l = cdiv(AT(i, k1), ykk);
+                    AT(i, k1) = l;
+                    colk2[i] = l;
+                    xs[i] = csub(xs[i], cmul(l, xk));
+                }
+            }
+            __syncthreads();
+            // ---- rank-2 update of columns j >= k+2: a warp takes two columns
+            // at a time, lanes along the contiguous rows
+            const cplx lk1 = colk[k1];
+            for (int j0 = k + 2 + 2 * (tid >> 5); j0 < n; j0 += 2 * (AC_TPB / 32)) {
+                const int j1 = (j0 + 1 < n) ? j0 + 1 : j0;
+                cplx* y0 = Y + (long)j0 * n;
+                cplx* y1 = Y + (long)j1 * n;
+                const cplx u10 = y0[k], u11 = y1[k];
+                const cplx u20 = csub(y0[k1], cmul(lk1, u10)), u21 = csub(y1[k1], cmul(lk1, u11));
+                for (int i = k + 2 + (tid & 31); i < n; i += 32) {
+                    const cplx l1 = colk[i], l2 = colk2[i];
+                    const cplx a0 = y0[i], a1 = y1[i];
+                    y0[i] = csub(csub(a0, cmul(l1, u10)), cmul(l2, u20));
+                    if (j1 != j0) y1[i] = csub(csub(a1, cmul(l1, u11)), cmul(l2, u21));
+                }
+                __syncwarp();
+                if ((tid & 31) == 0) {
+                    y0[k1] = u20;
+                    if (j1 != j0) y1[k1] = u21;
+                }
+            }
+            __syncthreads();
+            k += 2;
         }
         cplx* x = xout + (long)f * n;
         if (singular) {
@@ -203,7 +245,7 @@ extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const 
     if (n > AC_MAX_N) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: more than 1024 unknowns");
     cudaStream_t st = (cudaStream_t)stream;
     if (n <= AC_SMEM_N) {
-        const int smem = (n * n + 2 * n) * (int)sizeof(cplx);
+        const int smem = (n * n + 3 * n) * (int)sizeof(cplx);
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(ac_solve_kernel<256>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -225,11 +267,11 @@ extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const 
         if (cdn_tune_ac_blocks > 0) blocks = cdn_tune_ac_blocks;
         if (blocks > nf) blocks = nf;
         if (cdn_tune_ac_tpb == 1024)
-            ac_solve_kernel<1024><<<(int)blocks, 1024, 2 * n * (int)sizeof(cplx), st>>>(
+            ac_solve_kernel<1024><<<(int)blocks, 1024, 3 * n * (int)sizeof(cplx), st>>>(
                 n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow, fcol, fval, freqs, s,
                 (cplx*)work, (cplx*)x, status);
         else
-            ac_solve_kernel<512><<<(int)blocks, 512, 2 * n * (int)sizeof(cplx), st>>>(
+            ac_solve_kernel<512><<<(int)blocks, 512, 3 * n * (int)sizeof(cplx), st>>>(
                 n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow, fcol, fval, freqs, s,
                 (cplx*)work, (cplx*)x, status);
     }
