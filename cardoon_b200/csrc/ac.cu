@@ -63,7 +63,8 @@ __device__ __forceinline__ int ac_pivot(const cplx* Y, int n, int k, double* red
 }
 
 #define AC_SMEM_N 56
-#define AC_MAX_N 1024          // two multiplier columns + right-hand side in shared memory: 48 KB
+#define AC_R 4                   // pivots per pass over the trailing block
+#define AC_MAX_N 600           // panel multipliers + right-hand side in shared memory: 48 KB
 
 // AC_TPB threads per CTA: 256 for the shared-memory path, 512 for matrices in
 // the workspace (every CTA reuses one workspace slot for all its frequencies,
@@ -100,7 +101,7 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
             Y[e] = y;
         }
         cplx* colk = (cplx*)ac_sm + (in_smem ? (long)n * n : 0);      // [n] multipliers
-        cplx* xs = colk + n;                                           // [n] right-hand side
+        cplx* xs = colk + (long)AC_R * n;                              // [n] right-hand side
         for (int r = tid; r < n; r += AC_TPB) { cplx v; v.re = s[2 * r]; v.im = s[2 * r + 1]; xs[r] = v; }
         __syncthreads();
         if (tid == 0) {
@@ -123,84 +124,102 @@ ac_solve_kernel(int n, int nf, const double* __restrict__ G, const double* __res
         }
         __syncthreads();
         bool singular = false;
-        cplx* colk2 = xs + n;                                          // [n] second multipliers
-        // Two pivots per pass over the trailing block (rank-2 update): the
-        // block is loaded and stored once for two eliminated columns, which
-        // halves the L2 traffic per multiply-add of the unblocked algorithm.
-        for (int k = 0; k < n;) {
-            const int k1 = k + 1;
-            // ---- pivot k (column k is up to date)
-            int p = ac_pivot<AC_TPB>(Y, n, k, red_v, red_i, &piv);
-            if (p < 0) { singular = true; break; }
-            if (p != k) {
-                for (int j = tid; j < n; j += AC_TPB) { const cplx t = AT(k, j); AT(k, j) = AT(p, j); AT(p, j) = t; }
-                if (tid == 0) { const cplx t = xs[k]; xs[k] = xs[p]; xs[p] = t; }
-                __syncthreads();
-            }
-            {
-                const cplx ykk = AT(k, k);
-                const cplx xk = xs[k];
-                for (int i = k1 + tid; i < n; i += AC_TPB) {
-                    const cplx l = cdiv(AT(i, k), ykk);
-                    AT(i, k) = l;
-                    colk[i] = l;
+        // AC_R pivots per pass over the trailing block (rank-AC_R update): the
+        // block is loaded and stored once for AC_R eliminated columns, which
+        // divides the L2 traffic per multiply-add of the unblocked algorithm
+        // by AC_R.  The multipliers of the panel stay in shared memory:
+        // Lq[q * n + i] = L(i, k + q).
+        cplx* Lq = colk;                         // [AC_R][n] (colk is its first column)
+        for (int k = 0; k < n && !singular;) {
+            const int R = (n - k < AC_R) ? n - k : AC_R;
+            for (int m = 0; m < R; ++m) {
+                const int km = k + m;
+                if (m > 0) {
+                    // bring column km up to date with the panel's earlier pivots:
+                    // u_q = U(k+q, km) by a tiny forward substitution every
+                    // thread repeats for itself, then one pass over the rows
+                    cplx u[AC_R];
+#pragma unroll
+                    for (int q = 0; q < AC_R - 1; ++q) {
+                        if (q < m) {
+                            cplx v = AT(k + q, km);
+#pragma unroll
+                            for (int q2 = 0; q2 < AC_R - 1; ++q2)
+                                if (q2 < q) v = csub(v, cmul(Lq[(long)q2 * n + k + q], u[q2]));
+                            u[q] = v;
+                        }
+                    }
+                    __syncthreads();            // everybody has read rows k..km-1 of the column
+                    for (int i = km + tid; i < n; i += AC_TPB) {
+                        cplx a = AT(i, km);
+#pragma unroll
+                        for (int q = 0; q < AC_R - 1; ++q)
+                            if (q < m) a = csub(a, cmul(Lq[(long)q * n + i], u[q]));
+                        AT(i, km) = a;
+                    }
+                    if (tid < m) AT(k + tid, km) = u[tid];
+                    __syncthreads();
+                }
+                const int p = ac_pivot<AC_TPB>(Y, n, km, red_v, red_i, &piv);
+                if (p < 0) { singular = true; break; }
+                if (p != km) {
+                    // (the pending update of the columns right of the panel
+                    // commutes with the row swap because the panel's
+                    // multipliers are swapped too)
+                    for (int j = tid; j < n; j += AC_TPB) { const cplx t = AT(km, j); AT(km, j) = AT(p, j); AT(p, j) = t; }
+                    if (tid == 0) { const cplx t = xs[km]; xs[km] = xs[p]; xs[p] = t; }
+                    if (tid < m) {
+                        const cplx t = Lq[(long)tid * n + km];
+                        Lq[(long)tid * n + km] = Lq[(long)tid * n + p];
+                        Lq[(long)tid * n + p] = t;
+                    }
+                    __syncthreads();
+                }
+                const cplx ykk = AT(km, km);
+                const cplx xk = xs[km];
+                for (int i = km + 1 + tid; i < n; i += AC_TPB) {
+                    const cplx l = cdiv(AT(i, km), ykk);
+                    AT(i, km) = l;
+                    Lq[(long)m * n + i] = l;
                     xs[i] = csub(xs[i], cmul(l, xk));
                 }
-            }
-            __syncthreads();
-            if (k1 == n) break;
-            // ---- bring column k+1 up to date with pivot k
-            {
-                const cplx u = AT(k, k1);
-                for (int i = k1 + tid; i < n; i += AC_TPB) AT(i, k1) = csub(AT(i, k1), cmul(colk[i], u));
-            }
-            __syncthreads();
-            // ---- pivot k+1; the pending update of the other columns commutes
-            // with the row swap as long as the multipliers are swapped too
-            p = ac_pivot<AC_TPB>(Y, n, k1, red_v, red_i, &piv);
-            if (p < 0) { singular = true; break; }
-            if (p != k1) {
-                for (int j = tid; j < n; j += AC_TPB) { const cplx t = AT(k1, j); AT(k1, j) = AT(p, j); AT(p, j) = t; }
-                if (tid == 0) {
-                    cplx t = xs[k1]; xs[k1] = xs[p]; xs[p] = t;
-                    t = colk[k1]; colk[k1] = colk[p]; colk[p] = t;
-                }
                 __syncthreads();
             }
-            {
-                const cplx ykk = AT(k1, k1);
-                const cplx xk = xs[k1];
-                for (int i = k1 + 1 + tid; i < n; i += AC_TPB) {
-                    const cplx l = cdiv(AT(i, k1), ykk);
-                    AT(i, k1) = l;
-                    colk2[i] = l;
-                    xs[i] = csub(xs[i], cmul(l, xk));
-                }
-            }
-            __syncthreads();
-            // ---- rank-2 update of columns j >= k+2: a warp takes two columns
-            // at a time, lanes along the contiguous rows
-            const cplx lk1 = colk[k1];
-            for (int j0 = k + 2 + 2 * (tid >> 5); j0 < n; j0 += 2 * (AC_TPB / 32)) {
-                const int j1 = (j0 + 1 < n) ? j0 + 1 : j0;
-                cplx* y0 = Y + (long)j0 * n;
-                cplx* y1 = Y + (long)j1 * n;
-                const cplx u10 = y0[k], u11 = y1[k];
-                const cplx u20 = csub(y0[k1], cmul(lk1, u10)), u21 = csub(y1[k1], cmul(lk1, u11));
-                for (int i = k + 2 + (tid & 31); i < n; i += 32) {
-                    const cplx l1 = colk[i], l2 = colk2[i];
-                    const cplx a0 = y0[i], a1 = y1[i];
-                    y0[i] = csub(csub(a0, cmul(l1, u10)), cmul(l2, u20));
-                    if (j1 != j0) y1[i] = csub(csub(a1, cmul(l1, u11)), cmul(l2, u21));
+            if (singular) break;
+            // ---- rank-R update of the columns right of the panel: a warp per
+            // column, lanes along the contiguous rows
+            const int kR = k + R;
+            for (int j = kR + (tid >> 5); j < n; j += AC_TPB / 32) {
+                cplx* yj = Y + (long)j * n;
+                cplx u[AC_R];
+#pragma unroll
+                for (int q = 0; q < AC_R; ++q) {
+                    if (q < R) {
+                        cplx v = yj[k + q];
+#pragma unroll
+                        for (int q2 = 0; q2 < AC_R; ++q2)
+                            if (q2 < q) v = csub(v, cmul(Lq[(long)q2 * n + k + q], u[q2]));
+                        u[q] = v;
+                    }
                 }
                 __syncwarp();
-                if ((tid & 31) == 0) {
-                    y0[k1] = u20;
-                    if (j1 != j0) y1[k1] = u21;
+                for (int i = kR + (tid & 31); i < n; i += 32) {
+                    cplx a = yj[i];
+#pragma unroll
+                    for (int q = 0; q < AC_R; ++q)
+                        if (q < R) a = csub(a, cmul(Lq[(long)q * n + i], u[q]));
+                    yj[i] = a;
+                }
+                if ((tid & 31) < R) {
+                    const int q = tid & 31;
+                    cplx v = u[0];
+#pragma unroll
+                    for (int q2 = 1; q2 < AC_R; ++q2) if (q2 == q) v = u[q2];
+                    yj[k + q] = v;
                 }
             }
             __syncthreads();
-            k += 2;
+            k = kR;
         }
         cplx* x = xout + (long)f * n;
         if (singular) {
@@ -242,10 +261,10 @@ extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const 
         || (nfd > 0 && (!frow || !fcol || !fval)))
         return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: null argument");
     if (n > AC_SMEM_N && !work) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: workspace required");
-    if (n > AC_MAX_N) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: more than 1024 unknowns");
+    if (n > AC_MAX_N) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: more than 600 unknowns");
     cudaStream_t st = (cudaStream_t)stream;
     if (n <= AC_SMEM_N) {
-        const int smem = (n * n + 3 * n) * (int)sizeof(cplx);
+        const int smem = (n * n + (AC_R + 1) * n) * (int)sizeof(cplx);
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(ac_solve_kernel<256>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -267,11 +286,11 @@ extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const 
         if (cdn_tune_ac_blocks > 0) blocks = cdn_tune_ac_blocks;
         if (blocks > nf) blocks = nf;
         if (cdn_tune_ac_tpb == 1024)
-            ac_solve_kernel<1024><<<(int)blocks, 1024, 3 * n * (int)sizeof(cplx), st>>>(
+            ac_solve_kernel<1024><<<(int)blocks, 1024, (AC_R + 1) * n * (int)sizeof(cplx), st>>>(
                 n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow, fcol, fval, freqs, s,
                 (cplx*)work, (cplx*)x, status);
         else
-            ac_solve_kernel<512><<<(int)blocks, 512, 3 * n * (int)sizeof(cplx), st>>>(
+            ac_solve_kernel<512><<<(int)blocks, 512, (AC_R + 1) * n * (int)sizeof(cplx), st>>>(
                 n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow, fcol, fval, freqs, s,
                 (cplx*)work, (cplx*)x, status);
     }
