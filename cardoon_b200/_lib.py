@@ -236,7 +236,9 @@ class Lib(object):
                   dtau=self.dev(d[:, 4].copy()), frow=ti(frc[:, 0]),
                   fcol=ti(frc[:, 1]), fval=self.dev(fv),
                   freqs=self.dev(freqs), s=self.dev(s2),
-                  work=self.empty((nf * n * n * 2,)) if n > 56 else None,
+                  # one matrix per CTA in flight (at most two CTAs per SM)
+                  work=self.empty((min(nf, 2 * self.dll.cdn_sm_count(self.ctx))
+                                   * n * n * 2,)) if n > 56 else None,
                   x=self.empty((nf, n, 2)),
                   status=self.zeros((1,), torch.int32))
         return st

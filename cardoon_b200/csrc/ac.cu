@@ -64,7 +64,7 @@ __device__ __forceinline__ int ac_pivot(const cplx* Y, int n, int k, double* red
 
 #define AC_SMEM_N 56
 #define AC_R 4                   // pivots per pass over the trailing block
-#define AC_MAX_N 600           // panel multipliers + right-hand side in shared memory: 48 KB
+#define AC_MAX_N 2048          // panel multipliers + right-hand side in shared memory: 160 KB
 
 // AC_TPB threads per CTA: 256 for the shared-memory path, 512 for matrices in
 // the workspace (every CTA reuses one workspace slot for all its frequencies,
@@ -261,7 +261,7 @@ extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const 
         || (nfd > 0 && (!frow || !fcol || !fval)))
         return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: null argument");
     if (n > AC_SMEM_N && !work) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: workspace required");
-    if (n > AC_MAX_N) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: more than 600 unknowns");
+    if (n > AC_MAX_N) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: more than 2048 unknowns");
     cudaStream_t st = (cudaStream_t)stream;
     if (n <= AC_SMEM_N) {
         const int smem = (n * n + (AC_R + 1) * n) * (int)sizeof(cplx);
@@ -285,12 +285,20 @@ extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const 
         long blocks = 2L * ctx->sm_count;
         if (cdn_tune_ac_blocks > 0) blocks = cdn_tune_ac_blocks;
         if (blocks > nf) blocks = nf;
-        if (cdn_tune_ac_tpb == 1024)
-            ac_solve_kernel<1024><<<(int)blocks, 1024, (AC_R + 1) * n * (int)sizeof(cplx), st>>>(
+        const int smem = (AC_R + 1) * n * (int)sizeof(cplx);
+        const bool big = cdn_tune_ac_tpb == 1024;
+        if (smem > 48 * 1024) {
+            const cudaError_t e = big
+                ? cudaFuncSetAttribute(ac_solve_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                : cudaFuncSetAttribute(ac_solve_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return cdn_fail(ctx, CDN_ERR_CUDA, std::string("cdn_ac_solve: ") + cudaGetErrorString(e));
+        }
+        if (big)
+            ac_solve_kernel<1024><<<(int)blocks, 1024, smem, st>>>(
                 n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow, fcol, fval, freqs, s,
                 (cplx*)work, (cplx*)x, status);
         else
-            ac_solve_kernel<512><<<(int)blocks, 512, (AC_R + 1) * n * (int)sizeof(cplx), st>>>(
+            ac_solve_kernel<512><<<(int)blocks, 512, smem, st>>>(
                 n, nf, G, C, ndel, drow, dcol, dg, dc, dtau, nfd, frow, fcol, fval, freqs, s,
                 (cplx*)work, (cplx*)x, status);
     }

@@ -56,7 +56,8 @@ int cdn_dev_eval(cdn_ctx* ctx, int model_id, unsigned flags, long n, int nxin,
  *   (frow, fcol)[nfd], fval[nf][nfd][2]   Y_k[frow,fcol] += fval[k] (Y parameters
  *               of frequency-defined elements, get_Y_matrix, nodal.py:366-370)
  *   freqs[nf] (Hz); s[n][2] (re, im); x[nf][n][2]
- *   work        nf*n*n*16 bytes when n > 56 (else may be NULL)
+ *   work        min(nf, 2 * SMs)*n*n*16 bytes when n > 56 (else may be NULL);
+ *               n <= 2048
  *   status      int: 0, or 1 + index of a frequency with a singular matrix
  * All pointers are device pointers.                                          */
 int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const double* C,

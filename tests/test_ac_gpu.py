@@ -84,6 +84,22 @@ def test_ac_large_dense_system(lib):
     check_ac(X, ref)
 
 
+def test_ac_panel_smem_opt_in(lib):
+    """More than 600 unknowns: the panel's multipliers need more than 48 KB of
+    shared memory (opt-in attribute); more frequencies than workspace slots."""
+    lines = ['vsin:vs 1 gnd mag=1. acmag=1. freq=1GHz rint=50.']
+    for k in range(1, 330):
+        lines.append('ind:l{0} {0} {1} l=2n'.format(k, k + 1))
+        lines.append('cap:c{0} {1} gnd c=1p'.format(k, k + 1))
+        lines.append('res:r{0} {1} gnd r=5k'.format(k, k + 1))
+    lines.append('res:rl 330 gnd r=50.')
+    lines.append('.end')
+    ckt, _ = load_text('\n'.join(lines) + '\n')
+    X, ref = ac_both(ckt, np.logspace(7., 9.5, 12))
+    assert ckt.nD_dimension > 600
+    check_ac(X, ref)
+
+
 def test_ac_frequency_defined_line(lib):
     """tlinpy4 nsect=0: DC Y parameters in the operating point, get_Y_matrix
     per frequency in the sweep (dense and sparse OP formulations)."""
