@@ -170,8 +170,39 @@ template <int P> CDN_HD Dual<P> exp(const Dual<P>& x) {
 template <int P> CDN_HD Dual<P> log(const Dual<P>& x) {
     return d_scale(x, ::log(x.v), cdn_rcp(x.v));
 }
+// sqrt(x) and its derivative 1/(2 sqrt(x)) from ONE reciprocal square root:
+// MUFU seed + two Newton steps, z = x*y with a residual correction (within
+// 1 ulp of the IEEE result).  Branch-free like cdn_rcp: +-0, denormals (treated
+// as 0), +inf, negative and NaN arguments take the values of the host
+// arithmetic through selects (sqrt: 0 / inf / NaN, derivative: inf / 0 / NaN);
+// CUDA's ::sqrt carries an out-of-line slow path per call site and the
+// derivative needed a second reciprocal sequence.
+CDN_HD void cdn_sqrt_rsqrt(double x, double& z, double& half_y) {
+    const int hi = __double2hiint(x);
+    const bool normal = (unsigned)(hi - 0x00100000) < 0x7fe00000u;      // positive, normal, finite
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    // y <- y (1.5 - 0.5 x y^2), twice
+    const double hx = 0.5 * x;
+    double t = fma(-hx * y, y, 0.5);
+    y = fma(y, t, y);
+    t = fma(-hx * y, y, 0.5);
+    y = fma(y, t, y);
+    double zz = x * y;
+    const double hy = 0.5 * y;
+    zz = fma(fma(-zz, zz, x), hy, zz);
+    // special arguments
+    const bool zero = (hi & 0x7ff00000) == 0;                          // +-0 or denormal
+    const bool pinf = (hi == 0x7ff00000) && (__double2loint(x) == 0);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    z = normal ? zz : (zero ? 0.0 * x : (pinf ? x : nan));
+    half_y = normal ? hy : (zero ? inf : (pinf ? 0.0 : nan));
+}
 template <int P> CDN_HD Dual<P> sqrt(const Dual<P>& x) {
-    const double z = ::sqrt(x.v); return d_scale(x, z, 0.5 * cdn_rcp(z));
+    double z, dz;
+    cdn_sqrt_rsqrt(x.v, z, dz);
+    return d_scale(x, z, dz);
 }
 template <int P> CDN_HD Dual<P> tan(const Dual<P>& x) {
     const double z = ::tan(x.v); return d_scale(x, z, 1.0 + z * z);
