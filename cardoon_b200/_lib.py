@@ -52,20 +52,22 @@ class RunHost(C.Structure):
     """cdn_run_host (csrc/engine.cu)."""
     _fields_ = [('abstol', C.c_double), ('reltol', C.c_double),
                 ('maxdelta', C.c_double), ('a0', C.c_double),
-                ('gmin', C.c_double), ('lam', C.c_double),
+                ('gmin', C.c_double), ('gmin_ext', C.c_double),
+                ('lam', C.c_double),
                 ('h', C.c_double),
                 ('maxiter', C.c_int), ('errfunc', C.c_int),
                 ('use_q', C.c_int), ('im', C.c_int),
                 ('op', C.c_int), ('B', C.c_int),
                 ('team', C.c_int), ('T', C.c_int),
-                ('helpers', C.c_int), ('pad_', C.c_int),
+                ('helpers', C.c_int), ('n_ext', C.c_int),
                 ('x', _vp), ('sv_in', _vp), ('ws', _vp),
                 ('nsamples', C.c_int), ('first', C.c_int),
                 ('init_ic', C.c_int), ('nsrc', C.c_int), ('nsave', C.c_int),
                 ('blocks', C.c_int),
                 ('src_rows', _vp), ('src_val', _vp), ('src_dc', _vp),
                 ('save_rows', _vp), ('wave', _vp), ('iters', _vp),
-                ('res', _vp), ('status', _vp), ('red', _vp), ('prof', _vp)]
+                ('res', _vp), ('status', _vp), ('red', _vp), ('prof', _vp),
+                ('info', _vp)]
 
 
 OP_NEWTON, OP_TRAN, OP_UPDATE_Q, OP_SET_IC, OP_ACCEPT, OP_RHS, OP_CHORD, \
@@ -86,7 +88,9 @@ def _declare(dll):
                                  _vp, C.c_long, _vp, _vp, _vp, _vp, _vp]
     dll.cdn_ac_solve.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int,
                                  _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp,
-                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+                                 _vp, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp]
+    dll.cdn_ac_work_matrices.argtypes = [_vp, C.c_int]
+    dll.cdn_ac_work_matrices.restype = C.c_long
     dll.cdn_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
     dll.cdn_set_tuning.argtypes = [C.c_int, C.c_int]
     dll.cdn_plan_create.argtypes = [_vp, C.POINTER(CircuitHost),
@@ -236,9 +240,10 @@ class Lib(object):
                   dtau=self.dev(d[:, 4].copy()), frow=ti(frc[:, 0]),
                   fcol=ti(frc[:, 1]), fval=self.dev(fv),
                   freqs=self.dev(freqs), s=self.dev(s2),
-                  # one matrix per CTA in flight (at most two CTAs per SM)
-                  work=self.empty((min(nf, 2 * self.dll.cdn_sm_count(self.ctx))
-                                   * n * n * 2,)) if n > 56 else None,
+                  # one matrix per CTA in flight
+                  nwork=int(self.dll.cdn_ac_work_matrices(self.ctx, int(nf))),
+                  work=self.empty((int(self.dll.cdn_ac_work_matrices(
+                      self.ctx, int(nf))) * n * n * 2,)) if n > 56 else None,
                   x=self.empty((nf, n, 2)),
                   status=self.zeros((1,), torch.int32))
         return st
@@ -251,7 +256,8 @@ class Lib(object):
             self.ptr(st['dg']), self.ptr(st['dc']), self.ptr(st['dtau']),
             st['nfd'], self.ptr(st['frow']), self.ptr(st['fcol']),
             self.ptr(st['fval']), self.ptr(st['freqs']), self.ptr(st['s']),
-            self.ptr(st['work']), self.ptr(st['x']), self.ptr(st['status']),
+            self.ptr(st['work']), st['nwork'], self.ptr(st['x']),
+            self.ptr(st['status']),
             self.stream())
         self.check(rc)
 

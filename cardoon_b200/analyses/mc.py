@@ -48,8 +48,72 @@ class BatchTransient(object):
         self._engines = {}
 
     # ---- host: per-instance device records ------------------------------------
-    def pack_instances(self, B, vary, first=0):
-        """Records of instances ``first .. first+B-1``.
+    def pack_batch(self, overrides):
+        """Records of B instances in one vectorised pass.
+
+        ``overrides``: one dict per nonlinear element (order of
+        ``ckt.nD_nlinElem``) mapping attribute names to arrays of shape (B,).
+        The arrays are set on the element (the ``setattr`` of dc.py:179-188)
+        and ``process_params`` / ``cuda_pack`` run once in batch mode
+        (devices/cudadev.py): every column is bit-identical to what
+        ``pack_instances`` computes for that instance, at a few milliseconds
+        per thousand instances instead of Python per-element calls.  Raises
+        ``NotImplementedError`` when a device class or the variation cannot
+        be vectorised (callers fall back to ``pack_instances``).
+        """
+        ckt, topo = self.ckt, self.topo
+        elems = ckt.nD_nlinElem
+        B = max(np.size(v) for o in overrides for v in o.values())
+        saved = [dict(e.__dict__) for e in elems]
+        out = [None] * len(topo.groups)
+        where = {}
+        for gi, g in enumerate(topo.groups):
+            npar = len(g['elems'][0].cuda_spec()['params'])
+            out[gi] = np.empty((npar, B, g['n']))
+            for i, e in enumerate(g['elems']):
+                where[id(e)] = (gi, i)
+        try:
+            for e, over in zip(elems, overrides):
+                lin = (list(e.linearVCCS), list(e.linearVCQS))
+                nterm = len(e.connection)
+                for name, val in over.items():
+                    setattr(e, name, np.asarray(val, dtype=np.float64))
+                try:
+                    e.process_params()
+                    flags, params = e.cuda_pack()
+                except (ValueError, TypeError) as err:
+                    # an ``if`` on a varied value that is not batch-aware
+                    raise NotImplementedError(
+                        '{0}: not vectorisable: {1}'.format(
+                            e.instanceName, err))
+                if (list(e.linearVCCS), list(e.linearVCQS)) != lin \
+                        or len(e.connection) != nterm or any(
+                            np.ndim(q[2]) for q in e.linearVCCS
+                            + e.linearVCQS):
+                    raise NotImplementedError(
+                        '{0}: the variation changes linear stamps; '
+                        'per-instance linear matrices are not supported'
+                        .format(e.instanceName))
+                gi, i = where[id(e)]
+                if int(flags) != topo.groups[gi]['flags']:
+                    raise NotImplementedError(
+                        '{0}: the variation changes the model structure '
+                        '(kernel flags)'.format(e.instanceName))
+                params = np.asarray(params)
+                out[gi][:, :, i] = params if params.ndim == 2 \
+                    else params[:, None]
+        finally:
+            for e, d in zip(elems, saved):
+                e.__dict__.clear()
+                e.__dict__.update(d)
+        # columns instance-major: b * n_g + i
+        return [o.reshape(o.shape[0], -1) for o in out]
+
+    def pack_instances(self, B, vary, first=0, instances=None):
+        """Records of instances ``first .. first+B-1`` (or of the listed
+        ``instances``), one Python ``process_params`` per element and
+        instance: the reference mechanism, kept as the definition that
+        ``pack_batch`` is tested against.
 
         ``vary(j, elems)`` sets attributes on the nonlinear elements for
         instance ``j`` (plain ``setattr``, as dc.py:179-188 does); each
@@ -68,9 +132,11 @@ class BatchTransient(object):
         for gi, g in enumerate(topo.groups):
             for i, e in enumerate(g['elems']):
                 where[id(e)] = (gi, i)
+        ids = list(instances) if instances is not None \
+            else range(first, first + B)
         try:
-            for b in range(B):
-                vary(first + b, elems)
+            for b, j in enumerate(ids):
+                vary(j, elems)
                 for e, lin in zip(elems, lin0):
                     e.process_params()
                     nd.restore_RCnumbers(e)
@@ -116,6 +182,26 @@ class BatchTransient(object):
             rows.append(term.nD_namRC)
         return rows
 
+    def operating_points(self, params, B):
+        """Batched operating points (sources at t = 0, tran.py:112-117):
+        plain Newton, then the convergence helpers for the instances that
+        need them, all inside one launch (fsolve.py:23-56 helper chain).
+        Returns the DC engine: ``x`` [B, n], ``iters``, ``status`` and
+        ``info[:, 0]`` (helper used) are device tensors."""
+        dc, tr = self.engines(B)
+        torch = dc.lib.torch
+        dc.set_params(params)
+        if getattr(self, '_x0_dev', None) is None or \
+                self._x0_dev.shape[0] != B:
+            self._x0_dev = torch.as_tensor(np.broadcast_to(
+                self.x0, (B, self.topo.n)).copy()).to(dc.lib.device)
+            self._sv0_dev = torch.as_tensor(self.src[0].copy()).to(
+                dc.lib.device)
+        dc.x.copy_(self._x0_dev)
+        dc.sv.copy_(self._sv0_dev)
+        dc._launch(dc._run_struct(nd.L.OP_NEWTON, helpers=1))
+        return dc
+
     def run_device(self, params, rows, B):
         """Operating points + transients of B instances; everything stays on
         the device.  ``params``: per group ``[npar, B*n_g]`` device tensors
@@ -123,21 +209,17 @@ class BatchTransient(object):
         iters[B, nsamples], status[B], op_iters[B])."""
         dc, tr = self.engines(B)
         torch = dc.lib.torch
-        dc.set_params(params)
+        self.operating_points(params, B)
         tr.set_params(dc.params)
-        # batched operating point (sources at t = 0, tran.py:112-117)
-        dc.x.copy_(torch.as_tensor(np.broadcast_to(
-            self.x0, (B, self.topo.n)).copy()))
-        dc.sv.copy_(torch.as_tensor(self.src[0]))
-        # plain Newton, then gmin / source stepping for the instances that
-        # need them, all inside the launch (fsolve.py:23-56 helper chain)
-        dc._launch(dc._run_struct(nd.L.OP_NEWTON, helpers=1))
         tr.x.copy_(dc.x)
         wave, iters, res, status = tr.tran(None, self.src, rows, im=self.im,
                                            sync=False)
         # an instance whose operating point failed is flagged at sample 0
         status = torch.where(dc.status != 0, torch.full_like(status, -1),
                              status)
+        # highest convergence helper each instance needed (operating point,
+        # transient): 0 = plain Newton only
+        self.helper_used = (dc.info[:, 0], tr.info[:, 0])
         return wave, iters, status, dc.iters
 
     def run(self, params, terms):
@@ -146,6 +228,34 @@ class BatchTransient(object):
             params, self.save_rows(terms), B)
         return (wave.cpu().numpy(), iters.cpu().numpy(),
                 status.cpu().numpy(), opit.cpu().numpy())
+
+
+def bsim3_ring_samples(instances, nelem=6, seed=20240):
+    """The standard-normal draws of the config-5 variation, z[B, nelem, 5]
+    clipped to +-4: instance j uses ``default_rng([seed, j])`` and draws five
+    numbers per MOSFET in element order (SURVEY 8d "M")."""
+    z = np.empty((len(instances), nelem, 5))
+    for b, j in enumerate(instances):
+        rng = np.random.default_rng([seed, int(j)])
+        for k in range(nelem):
+            z[b, k] = np.clip(rng.standard_normal(5), -4., 4.)
+    return z
+
+
+def bsim3_ring_overrides(z, elems):
+    """Per-element attribute arrays of ``bsim3_ring_variation`` for the draws
+    ``z`` [B, nelem, 5] (input of ``BatchTransient.pack_batch``)."""
+    out = []
+    for k, e in enumerate(elems):
+        ntype = e._tf > 0
+        zk = z[:, k, :]
+        out.append(dict(
+            vfb=-1. * (1. + 0.03 * zk[:, 0]),
+            u0=(670. if ntype else 250.) * (1. + 0.05 * zk[:, 1]),
+            tox=1.5e-8 * (1. + 0.02 * zk[:, 2]),
+            l=1e-6 * (1. + 0.02 * zk[:, 3]),
+            w=(1e-6 if ntype else 3e-6) * (1. + 0.02 * zk[:, 4])))
+    return out
 
 
 def bsim3_ring_variation(seed=20240):
@@ -182,9 +292,21 @@ def gather_results(wave, iters, status, dist=None):
             dist.get_world_size() == 1:
         return wave, iters, status
     import torch
+    world = dist.get_world_size()
+    # shards may be unequal (total % world != 0) or empty: exchange the
+    # counts, pad to the largest, gather, cut back
+    cnt = torch.tensor([wave.shape[0]], dtype=torch.int64,
+                       device=wave.device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    cnts = [int(c.item()) for c in cnts]
+    bmax = max(cnts)
     outs = []
     for t in (wave, iters, status):
-        parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
-        dist.all_gather(parts, t.contiguous())
-        outs.append(torch.cat(parts, dim=0))
+        pad = torch.zeros((bmax,) + tuple(t.shape[1:]), dtype=t.dtype,
+                          device=t.device)
+        pad[:t.shape[0]] = t
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        outs.append(torch.cat([p[:c] for p, c in zip(parts, cnts)], dim=0))
     return tuple(outs)

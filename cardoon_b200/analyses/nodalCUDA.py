@@ -373,7 +373,10 @@ class Topology(object):
         port rows (then a plan built for one serves the other)."""
         if self.n != other.n or len(self.groups) != len(other.groups):
             return False
-        for a, b in zip(self.G + self.C + self.E, other.G + other.C + other.E):
+        # (Gdc: the DC Y parameters of frequency-defined elements are part of
+        # the DC plan's linear values, nodal.py:719-721)
+        for a, b in zip(self.G + self.C + self.E + self.Gdc,
+                        other.G + other.C + other.E + other.Gdc):
             if a.shape != b.shape or not np.array_equal(a, b):
                 return False
         keys = ('model', 'flags', 'nxin', 'ncs', 'nqs', 'ndelay', 'n')
@@ -382,6 +385,10 @@ class Topology(object):
             if any(g[k] != h[k] for k in keys):
                 return False
             if any(not np.array_equal(g[k], h[k]) for k in arrs):
+                return False
+            if (g['delay'] is None) != (h['delay'] is None) or (
+                    g['delay'] is not None
+                    and not np.array_equal(g['delay'], h['delay'])):
                 return False
         return True
 
@@ -656,7 +663,7 @@ class Engine(object):
                 raise ValueError('delayed control ports need the time step')
             self.nhist = int(np.ceil(maxDelay / h)) + 2
         if dense is None:
-            dense = (n <= DENSE_MAX) or (not glVar.sparse and n <= 2000)
+            dense = uses_dense(n)
         self.dense = dense
         self.team = team
         self.match = None
@@ -700,6 +707,11 @@ class Engine(object):
         self.res = torch.zeros(batch, dtype=torch.float64, device=lib.device)
         self.status = torch.zeros(batch, dtype=torch.int32,
                                   device=lib.device)
+        # [:, 0] highest convergence helper used, [:, 1] pivot-trouble flag
+        self.info = torch.zeros((batch, 2), dtype=torch.int32,
+                                device=lib.device)
+        # external terminals come first in the unknown vector (nodal.py:472)
+        self.n_ext = int(getattr(topo.ckt, 'nD_nterms', 0)) if dense else 0
         self.sv = torch.zeros(n, dtype=torch.float64, device=lib.device)
         self._keep = keep
         self.launches = 0
@@ -752,9 +764,13 @@ class Engine(object):
                 per_inst))
 
     # ---- launches ---------------------------------------------------------------
-    def _run_struct(self, op, a0=None, gmin=0., lam=1., helpers=0):
+    def _run_struct(self, op, a0=None, gmin=0., lam=1., helpers=0,
+                    gmin_ext=0.):
         r = L.RunHost()
         r.helpers = helpers
+        r.n_ext = self.n_ext
+        r.gmin_ext = gmin_ext
+        r.info = self.lib.ptr(self.info)
         r.abstol, r.reltol = glVar.abstol, glVar.reltol
         r.maxdelta, r.maxiter = glVar.maxdelta, int(glVar.maxiter)
         r.errfunc = int(bool(glVar.errfunc))
@@ -806,7 +822,7 @@ class Engine(object):
         hi = self.off[names[k + 1]] if k + 1 < len(names) else self.ws_per
         return self.ws[b, lo:hi]
 
-    def newton(self, x0, sV, gmin=0., lam=1.):
+    def newton(self, x0, sV, gmin=0., lam=1., gmin_ext=0.):
         """Damped Newton on the device from ``x0`` [n] or [B, n] with source
         vector ``sV`` [n].  Returns numpy (x, res, iters, ok) per batch."""
         torch = self.lib.torch
@@ -814,7 +830,8 @@ class Engine(object):
         self.x.copy_(torch.as_tensor(np.broadcast_to(
             x0, (self.B, self.n)).copy()))
         self.sv.copy_(torch.as_tensor(np.ascontiguousarray(sV)))
-        r = self._run_struct(L.OP_NEWTON, gmin=gmin, lam=lam)
+        r = self._run_struct(L.OP_NEWTON, gmin=gmin, lam=lam,
+                             gmin_ext=gmin_ext)
         self._launch(r)
         x = self.x.cpu().numpy()
         return (x, self.res.cpu().numpy(), self.iters.cpu().numpy(),
@@ -890,15 +907,47 @@ class Engine(object):
 # ---------------------------------------------------------------------------
 # nonlinear-function base: convergence helpers (nodal.py:433-604)
 # ---------------------------------------------------------------------------
-class _NLFunction(object):
-    def __init__(self):
-        self.convergence_helpers = [self.solve_simple,
-                                    self.solve_homotopy_gmin2,
-                                    self.solve_homotopy_source, None]
+def uses_dense(n):
+    """Storage rule of the engines: dense LU with partial pivoting for small
+    systems or ``sparse=0`` (the reference's nodal.py engine), else the
+    static-pivot sparse LU (nodalSP.py)."""
+    return (n <= DENSE_MAX) or (not glVar.sparse and n <= 2000)
 
-    def _newton(self, x0, sV, gmin=0., lam=1.):
-        x, res, it, ok = self.engine.newton(x0, sV, gmin=gmin, lam=lam)
+
+class _NLFunction(object):
+    @property
+    def convergence_helpers(self):
+        """Helper list of the engine in use: the dense engine has a fourth
+        helper (nodal.py:443-447), the sparse one does not
+        (nodalSP.py:232-235)."""
+        helpers = [self.solve_simple, self.solve_homotopy_gmin2,
+                   self.solve_homotopy_source]
+        engine = getattr(self, 'engine', None)
+        dense = engine.dense if engine is not None \
+            else uses_dense(self.ckt.nD_dimension)
+        if dense:
+            helpers.append(self.solve_homotopy_gmin)
+        return helpers + [None]
+
+    def __init__(self):
+        pass
+
+    def _newton(self, x0, sV, gmin=0., lam=1., gmin_ext=0.):
+        x, res, it, ok = self.engine.newton(x0, sV, gmin=gmin, lam=lam,
+                                            gmin_ext=gmin_ext)
+        if not ok[0] and int(self.engine.info[0, 1].item()):
+            # a static pivot of the sparse plan degraded on the way (the
+            # reference re-pivots on every iteration, nodalSP.py:281-303):
+            # build a new plan validated at the starting point of this solve
+            # and repeat it once
+            if self._replan(x0):
+                x, res, it, ok = self.engine.newton(
+                    x0, sV, gmin=gmin, lam=lam, gmin_ext=gmin_ext)
         return x[0], float(res[0]), int(it[0]), bool(ok[0])
+
+    def _replan(self, x_ref):
+        """Hook: rebuild the sparse plan at ``x_ref``; True if done."""
+        return False
 
     def solve_simple(self, x0, sV):
         # no docstring: the driver prints helper docstrings (fsolve.py:47)
@@ -917,6 +966,21 @@ class _NLFunction(object):
             state['gmin'] = gbase / lam - gbase
         x, res, it, ok = self._homotopy(
             0.5, f, x0, lambda x: self._newton(x, sV, gmin=state['gmin']))
+        if ok:
+            return (x, res, it)
+        raise NoConvergenceError('gmin stepping did not converge')
+
+    def solve_homotopy_gmin(self, x0, sV):
+        """gmin stepping"""
+        # gmin from ground to every external node (nodal.py:469-489)
+        state = dict(gmin=0.)
+
+        def f(lam):
+            gbase = 1e-3
+            state['gmin'] = gbase / lam - gbase
+        x, res, it, ok = self._homotopy(
+            0.5, f, x0,
+            lambda x: self._newton(x, sV, gmin_ext=state['gmin']))
         if ok:
             return (x, res, it)
         raise NoConvergenceError('gmin stepping did not converge')
@@ -1070,6 +1134,14 @@ class DCNodal(_NLFunction):
             return
         self.engine = Engine(topo, use_q=False, a0=0.,
                              x_ref=self.get_guess())
+
+    def _replan(self, x_ref):
+        if self.engine.dense:
+            return False
+        self.engine = Engine(self.engine.topo, use_q=False, a0=0.,
+                             x_ref=np.array(x_ref, dtype=float))
+        self.replans = getattr(self, 'replans', 0) + 1
+        return True
 
     def get_guess(self):
         return get_guess(self.ckt)

@@ -246,21 +246,30 @@ extern "C" { int cdn_tune_ac_blocks = 0; int cdn_tune_ac_tpb = 0; }
 // Reference: run_AC (analyses/nodal.py:286-381).  All pointers are device
 // pointers.  G, C: [n*n] row-major; delayed entries (drow, dcol, dg, dc,
 // dtau)[ndel]; frequency-defined entries (frow, fcol)[nfd] with
-// fval[nf][nfd][2]; freqs[nf]; s[n][2] (re, im); work: nf*n*n complex when
-// n > 56 (else unused); x: [nf][n][2]; status: 0 or 1 + index of a frequency
-// whose matrix is singular.  (Only the first min(nf, 2 * SMs) matrices of
-// `work` are used.)
+// fval[nf][nfd][2]; freqs[nf]; s[n][2] (re, im); work: work_matrices n*n
+// complex matrices when n > 56 (else unused), one per CTA in flight -- the grid
+// is clamped to work_matrices; x: [nf][n][2]; status: 0 or 1 + index of a
+// frequency whose matrix is singular.
+extern "C" long cdn_ac_work_matrices(cdn_ctx* ctx, int nf) {
+    if (!ctx || nf <= 0) return 0;
+    long blocks = 2L * ctx->sm_count;
+    if (cdn_tune_ac_blocks > 0) blocks = cdn_tune_ac_blocks;
+    return blocks < nf ? blocks : nf;
+}
+
 extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const double* C, int ndel,
                             const int* drow, const int* dcol, const double* dg, const double* dc,
                             const double* dtau, int nfd, const int* frow, const int* fcol,
                             const double* fval, const double* freqs, const double* s, double* work,
-                            double* x, int* status, void* stream) {
+                            long work_matrices, double* x, int* status, void* stream) {
     if (!ctx) return CDN_ERR_ARG;
+    CDN_USE_DEVICE(ctx);
     if (n <= 0 || nf <= 0) return CDN_OK;
     if (!G || !C || !freqs || !s || !x || !status || (ndel > 0 && (!drow || !dcol || !dg || !dc || !dtau))
         || (nfd > 0 && (!frow || !fcol || !fval)))
         return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: null argument");
-    if (n > AC_SMEM_N && !work) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: workspace required");
+    if (n > AC_SMEM_N && (!work || work_matrices < 1))
+        return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: workspace required");
     if (n > AC_MAX_N) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_ac_solve: more than 2048 unknowns");
     cudaStream_t st = (cudaStream_t)stream;
     if (n <= AC_SMEM_N) {
@@ -285,6 +294,9 @@ extern "C" int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const 
         long blocks = 2L * ctx->sm_count;
         if (cdn_tune_ac_blocks > 0) blocks = cdn_tune_ac_blocks;
         if (blocks > nf) blocks = nf;
+        // one n x n matrix of the workspace per CTA: never more CTAs than the
+        // caller provided matrices for
+        if (blocks > work_matrices) blocks = work_matrices;
         const int smem = (AC_R + 1) * n * (int)sizeof(cplx);
         const bool big = cdn_tune_ac_tpb == 1024;
         if (smem > 48 * 1024) {

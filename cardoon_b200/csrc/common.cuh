@@ -21,6 +21,17 @@ struct cdn_ctx {
         }                                                                      \
     } while (0)
 
+// A context is bound to one GPU: every launching entry point selects it, so
+// that several contexts (one per GPU) can live in one process.
+#define CDN_USE_DEVICE(ctx)                                                    \
+    do {                                                                       \
+        if ((ctx) && (ctx)->device >= 0) {                                     \
+            int cur_ = -1;                                                     \
+            if (cudaGetDevice(&cur_) != cudaSuccess || cur_ != (ctx)->device)  \
+                CDN_CUDA(ctx, cudaSetDevice((ctx)->device));                   \
+        }                                                                      \
+    } while (0)
+
 static inline int cdn_fail(cdn_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
     return code;

@@ -318,6 +318,7 @@ extern "C" int cdn_dev_eval(cdn_ctx* ctx, int model_id, unsigned flags, long n, 
                             const double* xin, double* out, double* jac, void* stream) {
     if (!ctx) return CDN_ERR_ARG;
     if (n <= 0) return CDN_OK;
+    CDN_USE_DEVICE(ctx);
     if (nxin < 1 || nxin > CDN_MAX_XIN) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_dev_eval: bad nxin");
     cudaStream_t st = (cudaStream_t)stream;
     const int lanes = jac ? nxin : 0;

@@ -35,6 +35,7 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     cdn_ctx* ctx = cdn_plan_ctx(P);
     const cdn_plan_dev* D = cdn_plan_host_view(P);
     if (!D) return cdn_fail(ctx, CDN_ERR_STATE, "engine: plan is not bound");
+    CDN_USE_DEVICE(ctx);
     cudaStream_t st = (cudaStream_t)stream;
 
     // model set
@@ -51,6 +52,8 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     static_assert(sizeof(cdn_engine_args) <= 4000, "kernel parameter space");
     A.o.abstol = r->abstol; A.o.reltol = r->reltol; A.o.maxdelta = r->maxdelta;
     A.o.a0 = r->a0; A.o.gmin = r->gmin; A.o.lambda = r->lambda; A.o.h = r->h;
+    A.o.gmin_ext = r->gmin_ext; A.o.n_ext = r->n_ext;
+    if (A.o.n_ext > D->n) A.o.n_ext = D->n;
     A.o.maxiter = r->maxiter; A.o.errfunc = r->errfunc; A.o.use_q = r->use_q; A.o.im = r->im;
     A.op = r->op; A.B = r->B;
     A.x = r->x; A.sv_in = r->sv_in; A.ws = r->ws;
@@ -60,7 +63,7 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     A.nsrc = r->nsrc; A.nsave = r->nsave; A.helpers = r->helpers;
     A.src_rows = r->src_rows; A.src_val = r->src_val; A.src_dc = r->src_dc;
     A.save_rows = r->save_rows; A.wave = r->wave; A.iters = r->iters; A.res = r->res;
-    A.status = r->status; A.red = r->red; A.prof = r->prof;
+    A.status = r->status; A.red = r->red; A.prof = r->prof; A.info = r->info;
     if (A.B <= 0) return CDN_OK;
     if (!A.x) return cdn_fail(ctx, CDN_ERR_ARG, "engine: x is NULL");
 
@@ -75,6 +78,15 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     }
     // the tile kernels keep the state in shared memory only
     if (c.team == CDN_TEAM_TILE && A.ws) c.team = CDN_TEAM_BLOCK;
+    if (c.team == CDN_TEAM_TILE) {
+        // ... for the duration of one launch: nothing may continue from (or
+        // leave behind) per-instance state
+        const bool fresh = A.op == CDN_OP_NEWTON ||
+                           (A.op == CDN_OP_TRAN && A.first <= 1 && A.init_ic);
+        if (!fresh)
+            return cdn_fail(ctx, CDN_ERR_STATE, "engine: this operation continues from kept state; "
+                                                "pass a workspace (ws)");
+    }
     if (c.team == CDN_TEAM_TILE) {
         int T = r->T;
         if (T <= 0) {

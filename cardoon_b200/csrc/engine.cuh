@@ -36,12 +36,14 @@ struct cdn_opts {
     double abstol, reltol, maxdelta;
     double a0;        // integration coefficient (0 in DC)
     double gmin;      // gmin-stepping conductance (multiplies the Gones pattern)
+    double gmin_ext;  // gmin on the diagonal of the first n_ext unknowns (nodal.py:469-489)
     double lambda;    // source-stepping factor (1 = full sources)
     double h;         // time step (delayed control ports)
     int maxiter;
     int errfunc;
     int use_q;        // 0: DC (currents only); 1: transient (charges too)
     int im;           // 0 backward Euler, 1 trapezoidal
+    int n_ext;        // external terminals = first unknowns (0: no such helper)
 };
 
 struct cdn_engine_args {
@@ -73,6 +75,7 @@ struct cdn_engine_args {
                                 // of the plan's gather lists (0: read the global copy)
     long long* prof;            // optional [16]: cycles of instance 0 per phase (device
                                 // sweep, assembly, factor, solve, update, accept, chord)
+    int* info;                  // optional [B][2]: highest helper used, pivot-trouble flag
 };
 
 // status bits or'ed into the negative range are avoided: singular pivots are
@@ -81,7 +84,8 @@ struct cdn_engine_args {
 // ---- per-instance state ----------------------------------------------------------
 struct Ws {
     double *x, *dx, *ivec, *sv, *q, *qprev, *dq, *y, *tmp, *xb, *lu, *out, *jac, *hist;
-    int* piv;       // [n] pivot rows (dense LU); piv[n + 1] = head of the history rings
+    int* piv;       // [n] pivot rows (dense LU); piv[n] = pivot-trouble flag of the static-
+                    // pivot sparse LU; piv[n + 1] = head of the history rings
     unsigned* stage;   // block team: shared-memory staging area for compact solve programs
     long long* dprof;  // optional fine-grained timers of the staged sweeps (slots 8..15)
 };
@@ -550,24 +554,32 @@ __device__ __forceinline__ bool row_heavy(const cdn_plan_dev& P, int r) {
            (CDN_LD(P.r_con_ptr + r + 1) - CDN_LD(P.r_con_ptr + r)) > P.heavy;
 }
 
+// Returns whether the rows this thread wrote are finite (dense plans: input of
+// the non-finite test of newton()).
 template <class Team>
-__device__ __forceinline__ void residual(Team& tm, const cdn_plan_dev& P, const Ws& w,
+__device__ __forceinline__ bool residual(Team& tm, const cdn_plan_dev& P, const Ws& w,
                                          const cdn_opts& o) {
     const double a0 = o.use_q ? o.a0 : 0.0;
+    bool fin = true;
     for (int r = tm.rank(); r < P.n; r += tm.size()) {
         if (P.n_r_heavy && row_heavy(P, r)) continue;
-        const double acc = row_sum<Team>(P, w, o, a0, r, 0, 1);
+        double acc = row_sum<Team>(P, w, o, a0, r, 0, 1);
+        if (o.gmin_ext != 0.0 && r < o.n_ext) acc += o.gmin_ext * w.x[r];   // nodal.py:478
         w.ivec[r] = acc;
-        w.y[r] = o.lambda * w.sv[r] - acc;
+        const double y = o.lambda * w.sv[r] - acc;
+        w.y[r] = y;
+        fin = fin && isfinite(y);
     }
     for (int h = 0; h < P.n_r_heavy; ++h) {
         const int r = CDN_LD(P.r_heavy + h);
-        const double acc = tm.sum(row_sum<Team>(P, w, o, a0, r, tm.rank(), tm.size()));
+        double acc = tm.sum(row_sum<Team>(P, w, o, a0, r, tm.rank(), tm.size()));
         if (tm.rank() == 0) {
+            if (o.gmin_ext != 0.0 && r < o.n_ext) acc += o.gmin_ext * w.x[r];
             w.ivec[r] = acc;
             w.y[r] = o.lambda * w.sv[r] - acc;
         }
     }
+    return fin;
 }
 
 // Jacobian slots: G' + Ti J Tcv + a0 Tq Jq Tcv (+ gmin Gones)
@@ -600,16 +612,23 @@ __device__ __forceinline__ double slot_sum(const cdn_plan_dev& P, const Ws& w, c
 }
 
 template <class Team>
-__device__ __forceinline__ void assemble(Team& tm, const cdn_plan_dev& P, const Ws& w,
+__device__ __forceinline__ bool assemble(Team& tm, const cdn_plan_dev& P, const Ws& w,
                                          const cdn_opts& o) {
     const double a0 = o.use_q ? o.a0 : 0.0;
+    bool fin = true;
     for (int q = tm.rank(); q < P.nlu; q += tm.size()) {
         const int e = P.dense ? CDN_LD(P.e_bal + q) : q;
         if (P.n_e_heavy && CDN_LD(P.e_con_ptr + e + 1) - CDN_LD(P.e_con_ptr + e) > P.heavy) continue;
         double v = CDN_LD(P.e_g + e);
         if (o.use_q) v += a0 * CDN_LD(P.e_c + e);
         if (o.gmin != 0.0) v += o.gmin * CDN_LD(P.e_gones + e);
-        w.lu[e] = v + slot_sum<Team>(P, w, o, a0, e, 0, 1);
+        // gmin from ground to the external nodes (nodal.py:479): dense slot
+        // e = i * n + j is on the diagonal iff e is a multiple of n + 1
+        if (o.gmin_ext != 0.0 && P.dense && e % (P.n + 1) == 0 && e / (P.n + 1) < o.n_ext)
+            v += o.gmin_ext;
+        v += slot_sum<Team>(P, w, o, a0, e, 0, 1);
+        w.lu[e] = v;
+        fin = fin && isfinite(v);
     }
     for (int h = 0; h < P.n_e_heavy; ++h) {
         const int e = CDN_LD(P.e_heavy + h);
@@ -621,6 +640,7 @@ __device__ __forceinline__ void assemble(Team& tm, const cdn_plan_dev& P, const 
             w.lu[e] = v + t;
         }
     }
+    return fin;
 }
 
 // q = C x + Tq q(x)   (device outputs must be current)
@@ -675,7 +695,10 @@ __device__ __forceinline__ void dense_factor(Team& tm, double* a, int* piv, int 
                 a[bi * n + j] = t;
             }
         tm.sync();
-        const double pinv = 1.0 / a[k * n + k];
+        // (dgetf2: a zero pivot is recorded, the column is left unscaled and
+        // the elimination goes on)
+        const double pk = a[k * n + k];
+        const double pinv = (pk != 0.0) ? 1.0 / pk : 1.0;
         for (int i = k + 1 + tm.rank(); i < n; i += tm.size()) a[i * n + k] *= pinv;
         tm.sync();
         const int m = n - k - 1;
@@ -714,8 +737,20 @@ __device__ __forceinline__ void dense_solve(Team& tm, const double* a, const int
 // ---- sparse LU: static pivot order, entry-wise Crout by dependency level ----------------
 // Entries (rows) with more than CDN_HEAVY terms sit at the head of their level
 // and are reduced by the whole team (hub rows/columns).
+// The pivot order was validated on the host at the reference point only
+// (the reference re-pivots on every iteration, nodalSP.py:281-303).  A pivot
+// that has degraded since shows as a zero / non-finite diagonal or a huge
+// multiplier: *flag is set (benign race) and the host re-plans at the current
+// iterate.
+#define CDN_MULT_LIMIT 1e8
+__device__ __forceinline__ void pivot_check(double v, int pv, int* flag) {
+    if (pv >= 0) { if (!(fabs(v) <= CDN_MULT_LIMIT)) *flag = 1; }
+    else if (pv == -2) { if (!(fabs(v) > 0.0) || !isfinite(v)) *flag = 1; }
+}
+
 template <class Team>
-__device__ __forceinline__ void sparse_factor(Team& tm, const cdn_plan_dev& P, double* lu) {
+__device__ __forceinline__ void sparse_factor(Team& tm, const cdn_plan_dev& P, double* lu,
+                                              int* flag) {
     for (int l = 0; l < P.nlev_f; ++l) {
         const int e0 = CDN_LD(P.f_lvl_ptr + l), e1 = CDN_LD(P.f_lvl_ptr + l + 1);
         const int nh = CDN_LD(P.f_lvl_nheavy + l);
@@ -731,6 +766,7 @@ __device__ __forceinline__ void sparse_factor(Team& tm, const cdn_plan_dev& P, d
                 const int pv = CDN_LD(P.e_piv + e);
                 if (pv >= 0) v /= lu[pv];
                 lu[e] = v;
+                pivot_check(v, pv, flag);
             }
         }
         for (int e = e0 + nh + tm.rank(); e < e1; e += tm.size()) {
@@ -741,6 +777,7 @@ __device__ __forceinline__ void sparse_factor(Team& tm, const cdn_plan_dev& P, d
             const int pv = CDN_LD(P.e_piv + e);
             if (pv >= 0) v /= lu[pv];
             lu[e] = v;
+            pivot_check(v, pv, flag);
         }
         tm.sync();
     }
@@ -824,7 +861,8 @@ __device__ __forceinline__ void dense_factor_cols(Team& tm, double* a, int* piv,
         }
         if (j == 0) piv[k] = bi;
         tm.sync();
-        const double pinv = 1.0 / a[k * n + k];
+        const double pk = a[k * n + k];
+        const double pinv = (pk != 0.0) ? 1.0 / pk : 1.0;      // dgetf2: zero pivot
         if (j > k && j < n) {
             const double akj = a[k * n + j];
             for (int i = k + 1; i < n; ++i) a[i * n + j] -= (a[i * n + k] * pinv) * akj;
@@ -893,7 +931,7 @@ __device__ __forceinline__ void dense_factor_reg8(TileTeam<T>& tm, double* a, in
             for (int i = 0; i < 8; ++i)
                 if (i > k && i == bi) { cb = col[i]; vb = v[i]; col[i] = ck; v[i] = vk; }
             col[k] = cb;
-            const double pinv = 1.0 / vb;
+            const double pinv = (vb != 0.0) ? 1.0 / vb : 1.0;   // dgetf2: zero pivot
 #pragma unroll
             for (int i = 0; i < 8; ++i)
                 if (i > k && i < n) {
@@ -986,7 +1024,7 @@ __device__ __forceinline__ void factor(Team& tm, const cdn_plan_dev& P, const Ws
         if (Team::kFlat && P.n <= tm.size()) factor_small(tm, w.lu, w.piv, P.n);
         else dense_factor(tm, w.lu, w.piv, P.n);
     } else {
-        sparse_factor(tm, P, w.lu);
+        sparse_factor(tm, P, w.lu, w.piv + P.n);
     }
 }
 
@@ -1135,7 +1173,10 @@ __device__ __forceinline__ void staged_refactor(BlockTeam& tm, const cdn_plan_de
                 const unsigned tt = term[t0 + t];
                 v -= lu[tt & 0xffffu] * lu[tt >> 16];
             }
-            if (pv != 0xffff) v /= lu[pv];
+            if (pv != 0xffff) {
+                v /= lu[pv];
+                if (!(fabs(v) <= CDN_MULT_LIMIT)) w.piv[P.n] = 1;
+            }
             lu[e] = v;
         }
         __syncthreads();
@@ -1162,13 +1203,21 @@ __device__ __forceinline__ bool try_staged_refactor(BlockTeam& tm, const cdn_pla
     return true;
 }
 
-// dx <- J^{-1} y  (y is consumed)
+// dx <- J^{-1} y  (y is consumed).  `scrub`: condition_array of the dense
+// factor_and_solve / solve_linear_system (nodal.py:385-402, 626, 644): nan ->
+// 10 abstol, +-inf -> +-0.1 maxdelta; get_chord_deltax (:648) does not scrub.
 template <class Team>
-__device__ __forceinline__ void lusolve(Team& tm, const cdn_plan_dev& P, const Ws& w) {
+__device__ __forceinline__ void lusolve(Team& tm, const cdn_plan_dev& P, const Ws& w,
+                                        const cdn_opts& o, bool scrub) {
     if (P.dense) {
         if (Team::kFlat && P.n <= 16) solve_small(tm, w.lu, w.piv, w.y, P.n);
         else dense_solve(tm, w.lu, w.piv, w.y, P.n);
-        for (int r = tm.rank(); r < P.n; r += tm.size()) w.dx[r] = w.y[r];
+        for (int r = tm.rank(); r < P.n; r += tm.size()) {
+            double d = w.y[r];
+            if (scrub && !isfinite(d))
+                d = isnan(d) ? 10.0 * o.abstol : (d > 0.0 ? 0.1 : -0.1) * o.maxdelta;
+            w.dx[r] = d;
+        }
         tm.sync();
     } else if (!try_staged_solve(tm, P, w)) {
         sparse_solve(tm, P, w.lu, w.y, w.tmp, w.dx);
@@ -1206,18 +1255,28 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
         CDN_PROF_T0;
         eval_devices<MS, true>(tm, P, b, w.x, w, true, o.h);
         CDN_PROF(0);
-        residual(tm, P, w, o);
+        bool fin = residual(tm, P, w, o);
         if (fs && try_staged_refactor(tm, P, w, o, *fs)) {
             CDN_PROF(2);
         } else {
-            assemble(tm, P, w, o);
+            fin = assemble(tm, P, w, o) && fin;
+            if (P.dense && !tm.all(fin)) {
+                // NaN/inf in the dense Jacobian or right-hand side: this
+                // Newton solve has failed (oracle/nodal_ref.py
+                // factor_and_solve explains the choice); next helper or
+                // bisection step
+                ++it;
+                res = INFINITY;
+                run = false;
+                continue;
+            }
             tm.sync();
             CDN_PROF(1);
             factor(tm, P, w);
             if (fs) { fs->valid = true; fs->a0 = o.use_q ? o.a0 : 0.0; fs->gmin = o.gmin; }
             CDN_PROF(2);
         }
-        lusolve(tm, P, w);
+        lusolve(tm, P, w, o, true);
         CDN_PROF(3);
         double m = 0.0;
         for (int r = tm.rank(); r < P.n; r += tm.size()) m = fmax(m, fabs(w.dx[r]));
@@ -1257,7 +1316,8 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
 
 // Continuation on lambda with bisection and backtracking (nodal.py:545-604):
 // mode 0 = gmin stepping on the nonlinear ports (gmin = 1e-3/lambda - 1e-3,
-// nodal.py:491-515, 535-543), mode 1 = source stepping (:517-533).  w.xb is
+// nodal.py:491-515, 535-543), mode 1 = source stepping (:517-533), mode 2 =
+// gmin stepping from ground to the external nodes (:469-489).  w.xb is
 // the caller's x0 and, as in the reference, is overwritten by every
 // successful intermediate solution.
 template <int MS, class Team>
@@ -1280,7 +1340,8 @@ __device__ __noinline__ int homotopy(Team& tm, const cdn_plan_dev& P, int b, con
     while (tm.cta_any(run && sp > 0)) {
         const bool go = run && sp > 0;
         if (mode == 0) o.gmin = 1e-3 / lam - 1e-3;
-        else o.lambda = lam;
+        else if (mode == 1) o.lambda = lam;
+        else o.gmin_ext = 1e-3 / lam - 1e-3;
         bool ok1 = false;
         tot += newton<MS>(tm, P, b, w, o, go, &res, &ok1);
         if (!go) continue;
@@ -1302,31 +1363,50 @@ __device__ __noinline__ int homotopy(Team& tm, const cdn_plan_dev& P, int b, con
     return tot;
 }
 
-// fsolve.solve (fsolve.py:23-56) over the helper list of the sparse engine
-// (nodalSP.py:232-235): plain Newton, gmin stepping, source stepping.  x0 is
-// taken from w.x; returns the iteration count of the helper that succeeded.
+// fsolve.solve (fsolve.py:23-56) over the helper lists of the reference: plain
+// Newton, gmin stepping on the nonlinear ports, source stepping (sparse engine,
+// nodalSP.py:232-235) and, for dense plans, gmin stepping on the external nodes
+// (nodal.py:443-447).  x0 is taken from w.x; returns the iteration count of
+// the helper that succeeded and its index in *used.
 template <int MS, class Team>
 __device__ __forceinline__ int solve_helpers(Team& tm, const cdn_plan_dev& P, int b,
                                              const Ws& w, const cdn_opts& o, int helpers,
                                              bool active, double* res_out, bool* ok,
-                                             long long* prof = nullptr, FactState* fs = nullptr) {
+                                             int* used, long long* prof = nullptr,
+                                             FactState* fs = nullptr) {
+    // `helpers`: bit 0 enables the chain; bits 1..3 (tests) skip plain Newton,
+    // gmin stepping on the ports, source stepping
+    *used = 0;
     if (helpers && active) {
         for (int r = tm.rank(); r < P.n; r += tm.size()) w.xb[r] = w.x[r];
         tm.sync();
     }
-    int it = newton<MS>(tm, P, b, w, o, active, res_out, ok, prof, fs);
+    int it = 0;
+    *ok = false;
+    *res_out = 0.0;
+    if (!(helpers & 2)) it = newton<MS>(tm, P, b, w, o, active, res_out, ok, prof, fs);
     if (!helpers) return it;
     bool need = active && !*ok;
     if (!tm.cta_any(need)) return it;
     if (fs) fs->valid = false;              // the helpers refactor in full
     double res2 = 0.0;
     bool ok2 = false;
-    int it2 = homotopy<MS>(tm, P, b, w, o, 0, need, &res2, &ok2);
-    if (need) { it = it2; *res_out = res2; *ok = ok2; }
-    need = need && !ok2;
-    if (!tm.cta_any(need)) return it;
-    it2 = homotopy<MS>(tm, P, b, w, o, 1, need, &res2, &ok2);
-    if (need) { it = it2; *res_out = res2; *ok = ok2; }
+    int it2;
+    if (!(helpers & 4)) {
+        it2 = homotopy<MS>(tm, P, b, w, o, 0, need, &res2, &ok2);
+        if (need) { it = it2; *res_out = res2; *ok = ok2; *used = 1; }
+        need = need && !ok2;
+        if (!tm.cta_any(need)) return it;
+    }
+    if (!(helpers & 8)) {
+        it2 = homotopy<MS>(tm, P, b, w, o, 1, need, &res2, &ok2);
+        if (need) { it = it2; *res_out = res2; *ok = ok2; *used = 2; }
+        need = need && !ok2;
+    }
+    const bool has4 = P.dense && o.n_ext > 0;        // team-uniform
+    if (!has4 || !tm.cta_any(need)) return it;
+    it2 = homotopy<MS>(tm, P, b, w, o, 2, need, &res2, &ok2);
+    if (need) { it = it2; *res_out = res2; *ok = ok2; *used = 3; }
     return it;
 }
 
@@ -1378,7 +1458,7 @@ __device__ __forceinline__ void chord(Team& tm, const cdn_plan_dev& P, const Ws&
                                       const cdn_opts& o) {
     for (int r = tm.rank(); r < P.n; r += tm.size()) w.y[r] = w.sv[r] - w.ivec[r];
     tm.sync();
-    lusolve(tm, P, w);
+    lusolve(tm, P, w, o, false);
 }
 
 // ---- one circuit instance, one operation ------------------------------------------------
@@ -1396,11 +1476,13 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
             for (int r = tm.rank(); r < n; r += tm.size()) w.sv[r] = __ldg(A.sv_in + r);
             tm.sync();
         }
-        double res; bool ok;
-        const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, active, &res, &ok,
+        double res; bool ok; int used;
+        if (active && !P.dense && tm.rank() == 0) w.piv[n] = 0;
+        const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, active, &res, &ok, &used,
                                          b == 0 ? A.prof : nullptr);
         if (active && tm.rank() == 0) {
             A.iters[b] = it; A.res[b] = res; A.status[b] = ok ? 0 : -1;
+            if (A.info) { A.info[2 * b] = used; A.info[2 * b + 1] = P.dense ? 0 : w.piv[n]; }
         }
         break;
     }
@@ -1410,8 +1492,9 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
             integ_init(tm, P, w);
             hist_store(tm, P, w, true);
         }
-        int status = 0;
+        int status = 0, used_max = 0, piv_at = 0;
         bool run = active;
+        if (active && !P.dense && tm.rank() == 0) w.piv[n] = 0;
         FactState fs;
         fs.valid = false; fs.a0 = 0.0; fs.gmin = 0.0;
         for (int i = A.first; i < A.nsamples; ++i) {
@@ -1432,17 +1515,22 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
                 }
                 CDN_PROF(6);
             }
-            double res; bool ok;
-            const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, run, &res, &ok, prof,
-                                             &fs);
+            double res; bool ok; int used;
+            const int it = solve_helpers<MS>(tm, P, b, w, o, A.helpers, run, &res, &ok, &used,
+                                             prof, &fs);
             if (!run) continue;
+            if (used > used_max) used_max = used;
+            if (!P.dense && !piv_at && w.piv[n]) piv_at = i + 1;
             const long at = (long)b * A.nsamples + i;
             if (tm.rank() == 0) { A.iters[at] = it; A.res[at] = res; }
             if (!ok) { status = i; run = false; continue; }
             for (int k = tm.rank(); k < A.nsave; k += tm.size())
                 A.wave[at * A.nsave + k] = w.x[__ldg(A.save_rows + k)];
         }
-        if (active && tm.rank() == 0) A.status[b] = status;
+        if (active && tm.rank() == 0) {
+            A.status[b] = status;
+            if (A.info) { A.info[2 * b] = used_max; A.info[2 * b + 1] = piv_at; }
+        }
         break;
     }
     case CDN_OP_UPDATE_Q:
@@ -1485,7 +1573,7 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
     case CDN_OP_SOLVE:
         if (!active) break;
         factor(tm, P, w);
-        lusolve(tm, P, w);
+        lusolve(tm, P, w, o, true);
         break;
     default: break;
     }

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters) 
 
 extern "C" int cdn_fp64_peak(cdn_ctx* ctx, double* flops_per_s) {
     if (!ctx || !flops_per_s) return CDN_ERR_ARG;
+    CDN_USE_DEVICE(ctx);
     const int blocks = ctx->sm_count * 8, tpb = 256, iters = 4096;
     double* buf = nullptr;
     CDN_CUDA(ctx, cudaMalloc(&buf, sizeof(double) * blocks * tpb));

@@ -792,6 +792,7 @@ extern "C" int cdn_plan_info(cdn_plan* P, long* info) {
 extern "C" int cdn_plan_bind(cdn_plan* P, void* dev_ws, long bytes, void* stream) {
     if (!P || !dev_ws) return CDN_ERR_ARG;
     cdn_ctx* ctx = P->ctx;
+    CDN_USE_DEVICE(ctx);
     char* base = (char*)(((uintptr_t)dev_ws + 255) / 256 * 256);
     const long struct_off = ((long)P->staging.size() + 255) / 256 * 256;
     if ((long)(base - (char*)dev_ws) + struct_off + (long)sizeof(cdn_plan_dev) > bytes)

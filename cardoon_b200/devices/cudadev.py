@@ -62,6 +62,72 @@ class CudaModel(object):
         return (out[:ncs], out[ncs:])
 
 
+# ---- batch mode ---------------------------------------------------------------
+# A Monte-Carlo / corner batch packs the records of B parameter variations of
+# one element at once: the varied attributes are numpy arrays of shape (B,)
+# and ``process_params`` / ``set_temp_vars`` / ``cuda_pack`` run ONCE, with
+# the same FP64 operations element-wise (numpy evaluates +, -, *, /, sqrt,
+# exp, log and pow per element exactly as for a scalar), so every column is
+# bit-identical to the scalar path.  Branches on varied values go through
+# ``sel`` / ``uniform`` below; anything else that cannot be vectorised raises
+# and the caller falls back to the per-instance loop.
+def sel(cond, a, b):
+    """``a if cond else b`` for scalars, ``np.where`` for batches."""
+    if np.ndim(cond) == 0:
+        return a if cond else b
+    return np.where(cond, a, b)
+
+
+def power(x, y):
+    """``pow(x, y)``; in batch mode through the scalar libm ``pow`` element by
+    element (numpy's vectorised power is not bit-identical to it)."""
+    if np.ndim(x) == 0 and np.ndim(y) == 0:
+        return pow(x, y)
+    import math
+    if np.ndim(y) == 0 and y == 1.:
+        return np.asarray(x, dtype=np.float64) + 0.   # pow(x, 1) == x exactly
+    xb, yb = np.broadcast_arrays(np.asarray(x, dtype=np.float64),
+                                 np.asarray(y, dtype=np.float64))
+    return np.array([math.pow(a, b) for a, b in zip(xb.ravel().tolist(),
+                                                    yb.ravel().tolist())]
+                    ).reshape(xb.shape)
+
+
+def uniform(cond, what):
+    """A condition that selects kernel structure must agree over the batch."""
+    if np.ndim(cond) == 0:
+        return bool(cond)
+    if np.all(cond) or not np.any(cond):
+        return bool(cond.flat[0])
+    raise NotImplementedError(
+        'the variation changes the model structure ({0})'.format(what))
+
+
+def stack_record(entries, *tails):
+    """Kernel record from a list of scalar entries (batch mode: some may be
+    arrays [B]) followed by 1-D scalar records: [npar] or [npar, B]."""
+    B = max([np.size(e) for e in entries if np.ndim(e) == 1] + [0])
+    tail = np.concatenate([np.atleast_1d(np.asarray(t, dtype=np.float64))
+                           for t in tails]) if tails else np.zeros(0)
+    if B == 0:
+        return np.concatenate([np.array(entries, dtype=np.float64), tail])
+    out = np.empty((len(entries) + len(tail), B))
+    for k, e in enumerate(entries):
+        out[k] = e
+    out[len(entries):] = tail[:, None]
+    return out
+
+
+def append_rows(rec, *tails):
+    """``np.concatenate([rec] + tails)`` for [npar] and [npar, B] records."""
+    tail = np.concatenate([np.atleast_1d(np.asarray(t, dtype=np.float64))
+                           for t in tails])
+    if rec.ndim == 1:
+        return np.concatenate([rec, tail])
+    return np.concatenate(
+        [rec, np.broadcast_to(tail[:, None], (len(tail), rec.shape[1]))])
+
+
 def delete_tape(dev):
     """Invalidate the cached kernel record (reference cppaddev.py:99)."""
     dev.__dict__.pop('_cuda_spec', None)

@@ -30,9 +30,12 @@ EXP_THRESHOLD = 34.0
 
 def _safe_exp(x):
     """exp with linear continuation above 50 (reference cppaddev.py:56)."""
-    if x < 50.:
-        return np.exp(x)
-    return np.exp(50.) * (x - 50. + 1.)
+    if np.ndim(x) == 0:
+        if x < 50.:
+            return np.exp(x)
+        return np.exp(50.) * (x - 50. + 1.)
+    with np.errstate(over='ignore'):
+        return np.where(x < 50., np.exp(x), np.exp(50.) * (x - 50. + 1.))
 
 
 class BSIM3(ad.CudaModel, cir.Element):
@@ -202,17 +205,17 @@ class BSIM3(ad.CudaModel, cir.Element):
         # effective channel length / width
         self.ldrn = self.l
         self.wdrn = self.w
-        t0 = pow(self.ldrn, self.lln)
-        t1 = pow(self.wdrn, self.lwn)
+        t0 = ad.power(self.ldrn, self.lln)
+        t1 = ad.power(self.wdrn, self.lwn)
         self.dl = self.lint + (self.ll / t0 + self.lw / t1
                                + self.lwl / (t0 * t1))
-        t2 = pow(self.ldrn, self.wln)
-        t3 = pow(self.wdrn, self.wwn)
+        t2 = ad.power(self.ldrn, self.wln)
+        t3 = ad.power(self.wdrn, self.wwn)
         self.dw = self.wint + (self.wl / t2 + self.ww / t3
                                + self.wwl / (t2 * t3))
         self.leff = self.l - 2.0 * self.dl
         self.weff = self.w - 2.0 * self.dw
-        self.AbulkCVfactor = (1. + pow(self.clc / self.leff, self.cle))
+        self.AbulkCVfactor = (1. + ad.power(self.clc / self.leff, self.cle))
         self.cox = const.epOx / self.tox
         self.phi = 2. * self._Vtn * np.log(self.nch / ni)
         self.sqrtPhi = np.sqrt(self.phi)
@@ -253,18 +256,14 @@ class BSIM3(ad.CudaModel, cir.Element):
         t0 = _safe_exp(-0.5 * self.dsub * self.leff / t1)
         self.theta0vb0 = (t0 + 2.0 * t0**2)
         self._Tox = 1e8 * self.tox
-        if self._k2 < 0.:
-            self.vbsc = .9 * (self.phi - (.5 * self._k1 / self._k2)**2)
-            if self.vbsc > -3.:
-                self.vbsc = -3.
-            elif self.vbsc < -30.:
-                self.vbsc = -30.
+        # (ad.sel / ad.uniform: scalar ``if`` or, in batch mode, np.where)
+        if ad.uniform(self._k2 < 0., 'sign of k2'):
+            vbsc = .9 * (self.phi - (.5 * self._k1 / self._k2)**2)
+            self.vbsc = ad.sel(vbsc > -3., -3., ad.sel(vbsc < -30., -30.,
+                                                       vbsc))
         else:
             self.vbsc = -30.
-        if self.u0 > 1.:
-            self._u0 = self.u0 * 1e-4
-        else:
-            self._u0 = self.u0
+        self._u0 = ad.sel(self.u0 > 1., self.u0 * 1e-4, self.u0)
         if not thermal:
             self.set_temp_vars(self.temp)
 
@@ -275,12 +274,12 @@ class BSIM3(ad.CudaModel, cir.Element):
         self._ToTnm1 = absTemp / self._Tn - 1.
         self.vsattemp = self.vsat - self.at * self._ToTnm1
         self.rds0 = (self.rdsw + self.prt * self._ToTnm1) \
-            / pow(self.weff * 1e6, self.wr)
+            / ad.power(self.weff * 1e6, self.wr)
         self.V0 = self.vbi - self.phi
         self._ua = self.ua + self.ua1 * self._ToTnm1
         self._ub = self.ub + self.ub1 * self._ToTnm1
         self._uc = self.uc + self.uc1 * self._ToTnm1
-        self.u0temp = self._u0 * pow(absTemp / self._Tn, self.ute)
+        self.u0temp = self._u0 * ad.power(absTemp / self._Tn, self.ute)
 
     def cuda_pack(self):
         """Kernel record: attributes + folded parameter-only expressions.
@@ -329,17 +328,13 @@ class BSIM3(ad.CudaModel, cir.Element):
         # zero-bias flat-band voltage (:741-766; T5 uses the exponent
         # argument T0 of :751, as the reference does)
         T0 = -.5 * s.dvt1w * s.weff * s.leff / s.factor1 / np.sqrt(s.Xdep0)
-        if T0 + EXP_THRESHOLD > 0.:
-            T2 = _safe_exp(T0) * (1. + 2. * _safe_exp(T0))
-        else:
-            T2 = MIN_1
+        T2 = ad.sel(T0 + EXP_THRESHOLD > 0.,
+                    _safe_exp(T0) * (1. + 2. * _safe_exp(T0)), MIN_1)
         T0 = s.dvt0w * T2
         T2 = T0 * (s.vbi - s.phi)
         T0 = -.5 * s.dvt1 * s.leff / (s.factor1 * np.sqrt(s.Xdep0))
-        if T0 + EXP_THRESHOLD > 0.:
-            T3 = _safe_exp(T0) * (1. + 2. * _safe_exp(T0))
-        else:
-            T3 = MIN_1
+        T3 = ad.sel(T0 + EXP_THRESHOLD > 0.,
+                    _safe_exp(T0) * (1. + 2. * _safe_exp(T0)), MIN_1)
         T3 = s.dvt0 * T3 * (s.vbi - s.phi)
         T4 = s.tox * s.phi / (s.weff + s.w0)
         T5 = s.k1ox * (T0 - 1.) * s.sqrtPhi \
@@ -351,22 +346,21 @@ class BSIM3(ad.CudaModel, cir.Element):
         v['c1tox'] = 1e-3 * s.tox                                 # :798
         v['c2toxldeb'] = 4e-3 * s.tox * s.ldeb                    # :799
         # surface-potential constants (:831-837)
-        if s.k1ox > 0.:
-            v['t2dp'] = s.moin * s._Vt * s.k1ox**2
-            v['t0dp'] = s.k1ox * np.sqrt(s.phi)
-        else:
-            v['t2dp'] = .25 * s.moin * s._Vt
-            v['t0dp'] = .5 * np.sqrt(s.phi)
+        v['t2dp'] = ad.sel(s.k1ox > 0., s.moin * s._Vt * s.k1ox**2,
+                           .25 * s.moin * s._Vt)
+        v['t0dp'] = ad.sel(s.k1ox > 0., s.k1ox * np.sqrt(s.phi),
+                           .5 * np.sqrt(s.phi))
         flags = 0
-        if s.pscbe1 != 0.:
+        if ad.uniform(s.pscbe1 != 0., 'pscbe1'):
             flags |= _F['PSCBE1']
-        if (s.alpha0 + s.alpha1 * s.leff > 0.) and (s.beta0 > 0.):  # :725
+        if ad.uniform((s.alpha0 + s.alpha1 * s.leff > 0.) & (s.beta0 > 0.),
+                      'substrate current'):                        # :725
             flags |= _F['ISUB']
         names = LAYOUTS['bsim3'][0]
         nint = len(names) - 1 - 4 * len(EMPTY)
         rec = [v[n] for n in names[:nint]]
         # intrinsic device: multiplier 1, no junctions
-        return flags, np.concatenate([rec, [1.]] + 4 * [EMPTY])
+        return flags, ad.stack_record(rec, [1.], *(4 * [EMPTY]))
 
     def power(self, vPort, currV):
         vds = vPort[0] - vPort[2]

@@ -153,7 +153,7 @@ def extrinsic_mos(IMOS):
                 if cap != 0.:
                     flags |= F[fcap]
                 recs.append(j.pack())
-            return flags, np.concatenate([p, [self.m]] + recs)
+            return flags, ad.append_rows(p, [self.m], *recs)
 
         def cuda_pack_thermal(self):
             """Electro-thermal record: the isothermal record (placeholders at

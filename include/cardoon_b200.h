@@ -56,16 +56,22 @@ int cdn_dev_eval(cdn_ctx* ctx, int model_id, unsigned flags, long n, int nxin,
  *   (frow, fcol)[nfd], fval[nf][nfd][2]   Y_k[frow,fcol] += fval[k] (Y parameters
  *               of frequency-defined elements, get_Y_matrix, nodal.py:366-370)
  *   freqs[nf] (Hz); s[n][2] (re, im); x[nf][n][2]
- *   work        min(nf, 2 * SMs)*n*n*16 bytes when n > 56 (else may be NULL);
- *               n <= 2048
+ *   work        work_matrices * n*n*16 bytes when n > 56 (else may be NULL):
+ *               one column-major matrix per CTA in flight; the launch uses
+ *               min(nf, 2 * SMs, work_matrices) CTAs, each looping over its
+ *               share of the frequencies (cdn_ac_work_matrices gives the
+ *               count that keeps every SM busy); n <= 2048
  *   status      int: 0, or 1 + index of a frequency with a singular matrix
  * All pointers are device pointers.                                          */
 int cdn_ac_solve(cdn_ctx* ctx, int n, int nf, const double* G, const double* C,
                  int ndel, const int* drow, const int* dcol, const double* dg,
                  const double* dc, const double* dtau, int nfd, const int* frow,
                  const int* fcol, const double* fval, const double* freqs,
-                 const double* s, double* work, double* x, int* status,
-                 void* stream);
+                 const double* s, double* work, long work_matrices, double* x,
+                 int* status, void* stream);
+/* workspace matrices cdn_ac_solve can use for nf frequencies (honours the
+ * tuning knobs)                                                              */
+long cdn_ac_work_matrices(cdn_ctx* ctx, int nf);
 
 /* ---- (a1-a4, a12) formulation plan: symbolic analysis, done once ---------
  * Replaces what the reference redoes on every Newton iteration: COO -> CSC
@@ -151,7 +157,16 @@ int cdn_plan_free(cdn_plan* plan);
  *   CDN_OP_GET_I_JAC  get_i_Jac                 (nodalSP.py:494-523, 838-887)
  *   CDN_OP_SOLVE      factor_and_solve          (nodalSP.py:281-303)
  * Non-convergence is a status, not an error: status[b] = -1 (NEWTON) or the
- * first failed sample (TRAN); the host raises NoConvergenceError.           */
+ * first failed sample (TRAN); the host raises NoConvergenceError.
+ * Dense plans follow factor_and_solve of nodal.py:606-627: LAPACK getrf/getrs
+ * semantics (a zero pivot does not stop the factorisation) followed by
+ * condition_array (nodal.py:385-402) on the step; a Jacobian or right-hand
+ * side that already holds NaN/inf fails that Newton solve at once (next
+ * helper / bisection), see oracle/nodal_ref.py factor_and_solve.
+ * State: with ws == NULL the state of an instance lives in shared memory for
+ * one launch only, so operations that continue from earlier state (TRAN with
+ * first > 1 or init_ic == 0, CHORD, ACCEPT, RHS, SOLVE, UPDATE_Q, SET_IC,
+ * GET_I, GET_I_JAC) return CDN_ERR_STATE.                                    */
 #define CDN_OP_NEWTON 0
 #define CDN_OP_TRAN 1
 #define CDN_OP_UPDATE_Q 2
@@ -168,6 +183,9 @@ typedef struct cdn_run_host {
     double abstol, reltol, maxdelta;
     double a0;           /* integration coefficient: 2/h trap, 1/h BE, 0 DC  */
     double gmin;         /* gmin stepping (multiplies the E pattern)         */
+    double gmin_ext;     /* gmin stepping on the diagonal of the first n_ext
+                            unknowns (solve_homotopy_gmin, nodal.py:469-489;
+                            dense plans only)                                */
     double lambda;       /* source stepping factor (1 = full sources)        */
     double h;            /* time step (delayed-port interpolation)           */
     int maxiter, errfunc;
@@ -175,8 +193,13 @@ typedef struct cdn_run_host {
     int im;              /* 0 backward Euler, 1 trapezoidal                  */
     int op, B;           /* operation, circuit instances in the batch        */
     int team, T;         /* -1 choose / 0 warp tile / 1 CTA / 2 grid; lanes  */
-    int helpers, pad_;   /* 1: on failure continue in-kernel with gmin and
-                            source stepping (fsolve.py:23-56 helper chain)  */
+    int helpers;         /* 1: on failure continue in-kernel with the helper
+                            chain of fsolve.py:23-56: gmin stepping on the
+                            nonlinear ports, source stepping and -- dense
+                            plans with n_ext > 0, nodal.py:443-447 -- gmin
+                            stepping on the external nodes                   */
+    int n_ext;           /* external terminals (ckt.nD_nterms): they are the
+                            first unknowns (nodal.py:472-475)                */
     double* x;           /* [B][n] in/out (device)                           */
     const double* sv_in; /* [n] source vector (device)                       */
     double* ws;          /* [B][cdn_engine_ws_doubles] state, or NULL        */
@@ -193,6 +216,14 @@ typedef struct cdn_run_host {
     long long* prof;         /* optional [16] (device): SM cycles instance 0
                                 spent per phase: device sweep, assembly, factor,
                                 solve, update, accept (+rhs), chord            */
+    int* info;               /* optional [B][2] (device): [0] highest helper
+                                that had to be used (0 plain Newton, 1 gmin on
+                                the nonlinear ports, 2 source stepping, 3 gmin
+                                on the external nodes); [1] 1 + first sample
+                                (TRAN) or 1 (NEWTON) at which the static-pivot
+                                sparse LU saw a zero / non-finite pivot or a
+                                multiplier above 1e8 (the host then re-plans at
+                                the current iterate), else 0                   */
 } cdn_run_host;
 
 long cdn_engine_ws_doubles(cdn_plan* plan);

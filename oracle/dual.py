@@ -104,6 +104,32 @@ class Dual(object):
     def __abs__(self):
         return dabs(self)
 
+    # numpy ufuncs applied to a dual (the reference's device code calls
+    # np.exp / np.sqrt / np.abs ... on pycppad a_float values, which numpy
+    # forwards to the object's methods; here they map to the functions below)
+    def __array_ufunc__(self, ufunc, method, *args, **kwargs):
+        out = kwargs.pop('out', None)          # in-place: vec *= dual
+        if method != '__call__' or kwargs:
+            return NotImplemented
+        if out is not None:
+            res = self.__array_ufunc__(ufunc, method, *args)
+            if res is NotImplemented or not _is_objarr(out[0]):
+                return NotImplemented
+            out[0][...] = res
+            return out[0]
+        f = _UFUNCS.get(ufunc.__name__)
+        if f is None:
+            return NotImplemented
+        if any(_is_objarr(a) for a in args):
+            # dual (op) object array of duals: element by element, as numpy
+            # does for arrays of pycppad a_float
+            shape = [a for a in args if _is_objarr(a)][0].shape
+            out = np.empty(shape, dtype=object)
+            for i in np.ndindex(*shape):
+                out[i] = f(*[a[i] if _is_objarr(a) else a for a in args])
+            return out
+        return f(*args)
+
     # comparisons act on values (used only through condassign in models)
     def __gt__(self, o):
         return self.v > _val(o)
@@ -120,6 +146,26 @@ class Dual(object):
 
 def _val(x):
     return x.v if isinstance(x, Dual) else x
+
+
+def _is_objarr(x):
+    return isinstance(x, np.ndarray) and x.dtype == object
+
+
+def _defer(method):
+    """Binary operators hand object arrays (vectors of duals) back to numpy,
+    which then applies the operation element by element."""
+    def wrapped(self, o):
+        if _is_objarr(o):
+            return NotImplemented
+        return method(self, o)
+    wrapped.__name__ = method.__name__
+    return wrapped
+
+
+for _name in ('__add__', '__radd__', '__sub__', '__rsub__', '__mul__',
+              '__rmul__', '__truediv__', '__rtruediv__'):
+    setattr(Dual, _name, _defer(getattr(Dual, _name)))
 
 
 def seed(x):
@@ -193,6 +239,22 @@ def power(x, p):
             _count(3 + x.P, 1)
             return Dual(z, (p * z / x.v) * x.d)
         return np.power(x, p)
+
+
+_UFUNCS = dict(
+    exp=exp, log=log, sqrt=sqrt, tan=tan, tanh=tanh, cosh=cosh, sin=sin,
+    cos=cos, absolute=dabs, fabs=dabs, negative=lambda a: -a,
+    add=lambda a, b: a + b if isinstance(a, Dual) else b.__radd__(a),
+    subtract=lambda a, b: a - b if isinstance(a, Dual) else b.__rsub__(a),
+    multiply=lambda a, b: a * b if isinstance(a, Dual) else b.__rmul__(a),
+    true_divide=lambda a, b: a / b if isinstance(a, Dual)
+    else b.__rtruediv__(a),
+    divide=lambda a, b: a / b if isinstance(a, Dual) else b.__rtruediv__(a),
+    power=lambda a, b: a ** b if isinstance(a, Dual) else b.__rpow__(a),
+    greater=lambda a, b: _val(a) > _val(b),
+    less=lambda a, b: _val(a) < _val(b),
+    greater_equal=lambda a, b: _val(a) >= _val(b),
+    less_equal=lambda a, b: _val(a) <= _val(b))
 
 
 def condassign(b, c, d):

@@ -12,6 +12,8 @@ function.  Device evaluation goes through oracle.models.device_eval.
 Node numbering uses insertion order (the reference used Python-2 hash order,
 i.e. arbitrary): compare results by terminal name.
 """
+import warnings
+
 import numpy as np
 import scipy.linalg as linalg
 import scipy.sparse as sp
@@ -22,6 +24,21 @@ from .models import device_eval
 
 class NoConvergence(Exception):
     pass
+
+
+class NonFiniteSystem(Exception):
+    """The dense Jacobian or right-hand side handed to factor_and_solve holds
+    a NaN/inf (see ``_NLFunction.factor_and_solve``)."""
+
+
+def condition_array(x, opt):                            # nodal.py:385-402
+    """Removes infs and nans from x in place: nan -> 10 abstol, +inf ->
+    0.1 maxdelta, -inf -> -0.1 maxdelta."""
+    if not np.all(np.isfinite(x)):
+        x[np.isnan(x)] = 10. * opt.abstol
+        x[np.isposinf(x)] = .1 * opt.maxdelta
+        x[np.isneginf(x)] = -.1 * opt.maxdelta
+    return x
 
 
 class Options(object):
@@ -234,7 +251,11 @@ def fsolve_newton(x0, get_deltax, f_eval, opt):
     x = x0
     n2 = True
     for i in range(opt.maxiter):
-        deltax = get_deltax(x)
+        try:
+            deltax = get_deltax(x)
+        except NonFiniteSystem:
+            # see _NLFunction.factor_and_solve: this Newton solve has failed
+            return x, np.inf, i + 1, False
         maxDelta = np.max(np.abs(deltax))
         if maxDelta > opt.maxdelta:
             deltax *= opt.maxdelta / maxDelta
@@ -303,13 +324,38 @@ class _NLFunction(object):
             self._lu = spla.splu(M)
             self.deltaxVec[:] = self._lu.solve(rhs)
             return self.deltaxVec
-        self._lu = linalg.lu_factor(Jac)                # nodal.py:606-627
-        return linalg.lu_solve(self._lu, rhs)
+        # nodal.py:606-627: lu_factor + lu_solve, then condition_array on the
+        # step (:626).  An exactly singular matrix passes through LAPACK
+        # (dgetrf only reports info > 0, scipy warns) and the inf/nan of the
+        # back substitution are scrubbed by condition_array.
+        #
+        # A Jacobian that already holds NaN/inf (BSIM3 far outside its
+        # bias range, e.g. Monte-Carlo instance 31 of the config-5 workload)
+        # has no reproducible meaning in the reference: the scipy of its
+        # time passed the NaNs to dgetrf, whose pivot search on NaNs is
+        # implementation defined, and scrubbed the all-NaN step; today's
+        # scipy raises ValueError from asarray_chkfinite, which nothing in
+        # the reference catches (the run aborts).  The oracle and the CUDA
+        # engine define it as "this Newton solve has failed": solve_simple
+        # raises NoConvergence (next helper, fsolve.py:44-56) and _homotopy
+        # bisects (nodal.py:581-592).
+        if not (np.all(np.isfinite(Jac)) and np.all(np.isfinite(rhs))):
+            raise NonFiniteSystem()
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            self._lu = linalg.lu_factor(Jac)
+            deltax = linalg.lu_solve(self._lu, rhs)
+        return condition_array(deltax, self.opt)
 
     def lu_solve(self, b):
         if self.sparse:
             return self._lu.solve(b)
-        return linalg.lu_solve(self._lu, b)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            return linalg.lu_solve(self._lu, b)
+
+    def solve_linear_system(self, b):           # nodal.py:629-646
+        return condition_array(self.lu_solve(b), self.opt)
 
     def get_chord_deltax(self, sV):             # nodal.py:648, nodalSP:345
         # uses the iVec left by the last get_i_Jac / get_i call

@@ -148,3 +148,37 @@ def test_plugin_batch_of_one(lib):
 def test_fp64_peak(lib):
     peak = lib.fp64_peak()
     assert 5e12 < peak < 8e13
+
+
+# ---- against the reference's own device code -----------------------------------
+from tests import ref_cases as RC                              # noqa: E402
+import os                                                      # noqa: E402
+
+_GOLDEN = os.path.join(os.path.dirname(__file__), 'golden',
+                       'ref_devices.npz')
+
+
+@pytest.mark.parametrize('name', sorted(RC.CASES))
+def test_kernels_vs_reference_golden(lib, name):
+    """CUDA kernels against numbers produced by the reference's unmodified
+    device modules (tests/golden/make_ref_device_golden.py)."""
+    g = np.load(_GOLDEN)
+    elem, xin = RC.build(name)
+    assert np.array_equal(xin, g[name + '/xin'])
+    ro, rj = g[name + '/out'], g[name + '/jac']
+    out, jac = S.cuda_eval(lib, elem, xin)
+    assert out.shape == ro.shape and jac.shape == rj.shape
+    bsim = name.startswith('bsim3')
+    vtol, jtol = (1e-9, 1e-7) if (bsim or 'ekv' in name or '_t' in name) \
+        else (VTOL, JTOL)
+    keep = np.all(np.isfinite(ro), axis=0) & np.all(np.isfinite(rj),
+                                                    axis=(0, 1))
+    if bsim:
+        # exact cancellation to 0 below Vgst ~ -2.4 V: see test_bsim3
+        keep &= np.abs(ro[0]) > 1e-25
+    assert keep.mean() > (0.25 if 'mc31' in name else 0.5)
+    assert S.rel_err(out[:, keep], ro[:, keep], 1e-20) < vtol
+    jac, rj = jac[:, :, keep], rj[:, :, keep]
+    scale = 1e-9 * np.max(np.abs(rj), axis=(1, 2), keepdims=True) + 1e-16
+    ej = float(np.max(np.abs(jac - rj) / (np.abs(rj) + scale)))
+    assert ej < jtol, 'Jacobian differs: {0:g}'.format(ej)

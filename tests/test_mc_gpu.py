@@ -70,3 +70,91 @@ def test_mc_matches_single_circuit(lib):
     for b in range(3):
         assert np.array_equal(wave[b], w1)
         assert np.array_equal(iters[b], it1)
+
+
+# ---- the config-5 workload against the committed oracle runs -------------------
+import os                                                        # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'mc_ring_bsim3.npz')
+TERMS = ['1', '3', '4']
+
+
+def _bt_full(lib):
+    ckt, queue = S.load_circuit(S.net('ring_bsim3.net'))
+    an = queue[0]
+    bt = mc.BatchTransient(ckt, an.tstop, an.tstep, an.im, lib=lib)
+    assert len(bt.timeVec) == 400
+    return ckt, bt
+
+
+def test_mc_golden_instances_full_length(lib):
+    """80 instances at the full 400 samples -- 0..47 plus 32 whose operating
+    point needs the in-kernel gmin stepping (instance 31 among them: its
+    plain Newton runs into a non-finite BSIM3 Jacobian) -- against the oracle
+    run of each (tests/golden/make_mc_golden.py): waveforms within
+    reltol/abstol at every sample, iterations +-1 per sample, same
+    convergence helper.  The batch is ragged and mixes instances that need a
+    helper with instances that do not (inactive neighbours in the tile
+    kernel's lockstep)."""
+    g = np.load(GOLD)
+    inst = g['inst']
+    assert len(inst) >= 64 and 31 in inst
+    ckt, bt = _bt_full(lib)
+    z = mc.bsim3_ring_samples(inst)
+    params = bt.pack_batch(mc.bsim3_ring_overrides(z, ckt.nD_nlinElem))
+    wave, iters, status, opit = bt.run(params, TERMS)
+    helper_op = bt.helper_used[0].cpu().numpy()
+    helper_tr = bt.helper_used[1].cpu().numpy()
+    assert np.all(status == 0)
+    want = g['op_helper'][inst]
+    assert (want != 0).sum() >= 30
+    assert np.array_equal(helper_op, want)
+    assert np.all(helper_tr == 0)
+    plain = want == 0
+    d_it = np.abs(opit - g['op_iters'][inst])
+    assert d_it[plain].max() <= 1
+    # gmin stepping: every inner solve may differ by one iteration
+    assert d_it[~plain].max() <= 4, d_it[~plain]
+    X = g['wave']
+    err = np.abs(wave - X)
+    tol = glVar.reltol * np.abs(X) + glVar.abstol
+    worst = (err / tol).max(axis=(1, 2))
+    assert np.all(worst < 1.), (inst[worst >= 1.], worst.max())
+    assert np.max(np.abs(iters[:, 1:] - g['iters'][:, 1:])) <= 1
+
+
+def test_mc_all_operating_points(lib):
+    """Operating points of all 4096 instances: the helper each one needs and
+    its iteration count equal the oracle's (3979 plain Newton, 117 gmin
+    stepping, none beyond)."""
+    g = np.load(GOLD)
+    ckt, bt = _bt_full(lib)
+    z = mc.bsim3_ring_samples(range(4096))
+    params = bt.pack_batch(mc.bsim3_ring_overrides(z, ckt.nD_nlinElem))
+    dc = bt.operating_points(params, 4096)
+    helper = dc.info[:, 0].cpu().numpy()
+    its = dc.iters.cpu().numpy()
+    assert np.all(dc.status.cpu().numpy() == 0)
+    same = helper == g['op_helper']
+    # (an instance on the edge of plain-Newton convergence may fall on the
+    # other side by rounding)
+    assert same.mean() > 0.998, np.nonzero(~same)[0]
+    plain = same & (helper == 0)
+    assert np.abs(its - g['op_iters'])[plain].max() <= 1
+    hard = same & (helper != 0)
+    assert np.abs(its - g['op_iters'])[hard].max() <= 4
+
+
+def test_mc_strong_scaling_shards_agree(lib):
+    """A shard (the instance range of one rank, mc.shard) gives the same
+    waveforms as those instances inside the full batch."""
+    ckt, bt = _bt_full(lib)
+    ids = list(range(96))
+    z = mc.bsim3_ring_samples(ids)
+    ov = mc.bsim3_ring_overrides(z, ckt.nD_nlinElem)
+    full = bt.run(bt.pack_batch(ov), TERMS)
+    lo, hi = mc.shard(96, 1, 3)
+    part = bt.run(bt.pack_batch(mc.bsim3_ring_overrides(
+        z[lo:hi], ckt.nD_nlinElem)), TERMS)
+    assert np.array_equal(part[0], full[0][lo:hi])
+    assert np.array_equal(part[1], full[1][lo:hi])

@@ -437,3 +437,142 @@ def test_tran_backward_euler_and_errfunc(lib):
             check_tran(wave, iters, status, ref)
         finally:
             glVar.errfunc = old
+
+
+# ---- dense failure semantics of the reference (nodal.py:385-402, 443-489, 606-627) ----
+def test_homotopy_gmin_external_nodes(lib):
+    """The dense engine's fourth helper, solve_homotopy_gmin (gmin from
+    ground to every external node, nodal.py:469-489): host-driven through the
+    nd interface, in-kernel (homotopy mode 2) and the oracle agree."""
+    ckt, _ = S.load_circuit(S.net('bias_npn.net'))
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    assert dc.engine.dense and dc.engine.n_ext == ckt.nD_nterms
+    helpers = dc.convergence_helpers
+    assert [h.__name__ if h else None for h in helpers] == [
+        'solve_simple', 'solve_homotopy_gmin2', 'solve_homotopy_source',
+        'solve_homotopy_gmin', None]            # nodal.py:443-447
+    old = glVar.maxiter
+    glVar.maxiter = 8          # plain Newton needs 17
+    try:
+        x0, sV = dc.get_guess(), dc.get_source()
+        xh, resh, ith = dc.solve_homotopy_gmin(x0.copy(), sV)
+        idx = R.prepare(ckt)
+        rdc = R.RefDC(ckt, idx, R.Options(glVar))
+        xr, resr, itr = rdc.solve_homotopy_gmin(rdc.get_guess(),
+                                                rdc.get_source())
+        assert abs(ith - itr) <= 2
+        assert np.allclose(xh, xr, rtol=1e-6, atol=1e-9)
+        # in-kernel: skip helpers 1-3 (bits 1..3), so that the chain reaches
+        # the fourth one
+        e = dc.engine
+        r = e._run_struct(nd.L.OP_NEWTON, helpers=1 | 2 | 4 | 8)
+        e.x.copy_(e.lib.torch.as_tensor(x0[None, :]))
+        e.sv.copy_(e.lib.torch.as_tensor(sV))
+        e._launch(r)
+        assert int(e.status[0].item()) == 0
+        assert int(e.info[0, 0].item()) == 3
+        assert int(e.iters[0].item()) == ith
+        assert np.allclose(e.x[0].cpu().numpy(), xh, rtol=1e-9, atol=1e-12)
+    finally:
+        glVar.maxiter = old
+    # a sparse engine keeps the three-helper list (nodalSP.py:232-235)
+    ckt2, _ = S.load_circuit(S.net('soliton.net'))
+    nd.make_nodal_circuit(ckt2)
+    dc2 = nd.DCNodal(ckt2)
+    assert not dc2.engine.dense and len(dc2.convergence_helpers) == 4
+
+
+FLOATING = """
+* node 3 floats at DC (between two capacitors): singular dense Jacobian
+vdc:v1 1 gnd vdc=2
+res:r1 1 2 r=1k
+diode:d1 2 gnd isat=1e-14
+cap:c1 2 3 c=1p
+cap:c2 3 gnd c=1p
+.options sparse=0
+.end
+"""
+
+
+def test_singular_matrix_condition_array(lib, tmp_path, capsys):
+    """factor_and_solve on an exactly singular dense matrix: LAPACK goes on
+    past the zero pivot, the back substitution produces inf/nan, and
+    condition_array (nodal.py:385-402) scrubs the step; the oracle (scipy +
+    the same scrub) and the device agree on every entry that is finite, and
+    on which ones were scrubbed."""
+    from cardoon_b200.analyses.fsolve import NoConvergenceError
+    deck = tmp_path / 'floating.net'
+    deck.write_text(FLOATING)
+    ckt, _ = S.load_circuit(str(deck))
+    nd.make_nodal_circuit(ckt)
+    dc = nd.DCNodal(ckt)
+    assert dc.engine.dense
+    idx = R.prepare(ckt)
+    opt = R.Options(glVar)
+    rdc = R.RefDC(ckt, idx, opt)
+    names = idx.name_to_row()
+    x = dc.get_guess()
+    sV = dc.get_source()
+    iVec, Jac = dc.get_i_Jac(x)
+    dx = dc.factor_and_solve(sV - iVec, Jac).copy()
+    # oracle on the same vector (unknown order by terminal name)
+    order = [names[nd_name(t)] for t in ckt.nD_termList]
+    xr = np.zeros(len(x))
+    xr[order] = x
+    sr = rdc.get_source()
+    ir, Jr = rdc.get_i_Jac(xr)
+    dr = rdc.factor_and_solve(sr - ir, Jr)[order]
+    scrub = (10. * glVar.abstol, .1 * glVar.maxdelta, -.1 * glVar.maxdelta)
+    was_scrubbed = np.isin(dr, scrub)
+    assert was_scrubbed.any()
+    assert np.array_equal(np.isin(dx, scrub), was_scrubbed)
+    assert np.allclose(dx[~was_scrubbed], dr[~was_scrubbed], rtol=1e-9)
+    assert np.all(np.isfinite(dx))
+    # no helper can make the floating node converge, here or there
+    with pytest.raises(NoConvergenceError):
+        solve(dc.get_guess(), sV, dc.convergence_helpers)
+    with pytest.raises(R.NoConvergence):
+        R.run_op(ckt, glVar)
+
+
+def nd_name(term):
+    """Terminal label as oracle.nodal_ref.NodalIndex.name_to_row keys it."""
+    if hasattr(term, 'get_label') and not term.get_label().startswith('T:'):
+        return term.connection[0].instanceName + ':' + term.instanceName
+    return term.instanceName
+
+
+def test_stateless_engine_rejects_stateful_ops(lib):
+    """With ws == NULL the state lives for one launch only: operations that
+    continue from kept state are refused (CDN_ERR_STATE), not run on
+    uninitialised shared memory."""
+    from cardoon_b200._lib import CdnError
+    ckt, queue = S.load_circuit(S.net('ring_bsim3.net'))
+    nd.make_nodal_circuit(ckt)
+    topo = nd.get_topology(ckt)
+    e = nd.Engine(topo, use_q=True, a0=2e11, keep_state=False, h=1e-11)
+    assert e.ws is None
+    for op in (nd.L.OP_CHORD, nd.L.OP_ACCEPT, nd.L.OP_RHS, nd.L.OP_SOLVE,
+               nd.L.OP_UPDATE_Q):
+        with pytest.raises(CdnError):
+            e._launch(e._run_struct(op))
+    r = e._run_struct(nd.L.OP_TRAN)
+    r.nsamples, r.first, r.init_ic = 4, 2, 0
+    with pytest.raises(CdnError):
+        e._launch(r)
+    # plain Newton is fine
+    e._launch(e._run_struct(nd.L.OP_NEWTON))
+
+
+def test_two_contexts_select_their_device(lib):
+    """Every launching entry point selects the context's GPU (one box may
+    hold several contexts); with one GPU this only checks the call path."""
+    import torch
+    from cardoon_b200._lib import Lib
+    other = Lib(0)
+    elem = S.make_element('diode', [1, 0])
+    out1, _ = S.cuda_eval(other, elem, np.array([[0.6, 0.7]]))
+    out2, _ = S.cuda_eval(lib, elem, np.array([[0.6, 0.7]]))
+    assert np.array_equal(out1, out2)
+    assert torch.cuda.current_device() == 0
