@@ -187,7 +187,7 @@ class BatchTransient(object):
         plain Newton, then the convergence helpers for the instances that
         need them, all inside one launch (fsolve.py:23-56 helper chain).
         Returns the DC engine: ``x`` [B, n], ``iters``, ``status`` and
-        ``info[:, 0]`` (helper used) are device tensors."""
+        ``hinfo[:, 0]`` (helper used) are device tensors."""
         dc, tr = self.engines(B)
         torch = dc.lib.torch
         dc.set_params(params)
@@ -219,7 +219,7 @@ class BatchTransient(object):
                              status)
         # highest convergence helper each instance needed (operating point,
         # transient): 0 = plain Newton only
-        self.helper_used = (dc.info[:, 0], tr.info[:, 0])
+        self.helper_used = (dc.hinfo[:, 0], tr.hinfo[:, 0])
         return wave, iters, status, dc.iters
 
     def run(self, params, terms):

@@ -708,7 +708,7 @@ class Engine(object):
         self.status = torch.zeros(batch, dtype=torch.int32,
                                   device=lib.device)
         # [:, 0] highest convergence helper used, [:, 1] pivot-trouble flag
-        self.info = torch.zeros((batch, 2), dtype=torch.int32,
+        self.hinfo = torch.zeros((batch, 2), dtype=torch.int32,
                                 device=lib.device)
         # external terminals come first in the unknown vector (nodal.py:472)
         self.n_ext = int(getattr(topo.ckt, 'nD_nterms', 0)) if dense else 0
@@ -770,7 +770,7 @@ class Engine(object):
         r.helpers = helpers
         r.n_ext = self.n_ext
         r.gmin_ext = gmin_ext
-        r.info = self.lib.ptr(self.info)
+        r.info = self.lib.ptr(self.hinfo)
         r.abstol, r.reltol = glVar.abstol, glVar.reltol
         r.maxdelta, r.maxiter = glVar.maxdelta, int(glVar.maxiter)
         r.errfunc = int(bool(glVar.errfunc))
@@ -935,7 +935,7 @@ class _NLFunction(object):
     def _newton(self, x0, sV, gmin=0., lam=1., gmin_ext=0.):
         x, res, it, ok = self.engine.newton(x0, sV, gmin=gmin, lam=lam,
                                             gmin_ext=gmin_ext)
-        if not ok[0] and int(self.engine.info[0, 1].item()):
+        if not ok[0] and int(self.engine.hinfo[0, 1].item()):
             # a static pivot of the sparse plan degraded on the way (the
             # reference re-pivots on every iteration, nodalSP.py:281-303):
             # build a new plan validated at the starting point of this solve

@@ -16,6 +16,7 @@ test covers the in-kernel homotopy.  Arrays written:
   op_helper[4096]   0 plain Newton, 1 gmin2, 2 source, 3 gmin stepping,
                     -1 none converged
   op_iters[4096]    iterations reported by the helper that succeeded
+  op_x_all[4096,7]  the operating points
   inst[K]           instance numbers with full transients
   wave[K,400,3]     nodes 1, 3, 4; iters[K,400]; op_x[K,7]
 """
@@ -86,6 +87,7 @@ def main():
             out = pool.map(op_of, range(TOTAL), chunksize=16)
             old['op_helper'] = np.array([o[1] for o in out], dtype=np.int8)
             old['op_iters'] = np.array([o[2] for o in out], dtype=np.int32)
+            old['op_x_all'] = np.array([o[3] for o in out])
             print('helpers used:', np.bincount(old['op_helper'] + 1))
         else:
             hard = np.nonzero(old['op_helper'] != 0)[0]

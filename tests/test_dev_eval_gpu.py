@@ -171,6 +171,10 @@ def test_kernels_vs_reference_golden(lib, name):
     bsim = name.startswith('bsim3')
     vtol, jtol = (1e-9, 1e-7) if (bsim or 'ekv' in name or '_t' in name) \
         else (VTOL, JTOL)
+    if name == 'mosekv_t':
+        # weak inversion at a hot junction: the inverse of the EKV
+        # interpolation function amplifies last-bit differences of exp/log
+        vtol = 1e-8
     keep = np.all(np.isfinite(ro), axis=0) & np.all(np.isfinite(rj),
                                                     axis=(0, 1))
     if bsim:

@@ -471,7 +471,7 @@ def test_homotopy_gmin_external_nodes(lib):
         e.sv.copy_(e.lib.torch.as_tensor(sV))
         e._launch(r)
         assert int(e.status[0].item()) == 0
-        assert int(e.info[0, 0].item()) == 3
+        assert int(e.hinfo[0, 0].item()) == 3
         assert int(e.iters[0].item()) == ith
         assert np.allclose(e.x[0].cpu().numpy(), xh, rtol=1e-9, atol=1e-12)
     finally:
