@@ -613,7 +613,7 @@ _ARRAY_TYPES = dict(e_g=np.float64, e_c=np.float64, e_gones=np.float64,
                     r_lin_g=np.float64, r_lin_c=np.float64,
                     r_lin_gones=np.float64, e_con_kind=np.int8,
                     r_con_kind=np.int8, e_con_pk=np.uint32,
-                    r_con_pk=np.uint32)
+                    r_con_pk=np.uint32, sd_prog=np.uint32)
 
 
 def plan_array(dll, plan, name):

@@ -10,7 +10,7 @@ extern "C" {
 long cdn_engine_ws_doubles(cdn_plan* P) {
     const cdn_plan_dev* D = cdn_plan_host_view(P);
     if (!D) return -1;
-    return ws_doubles(D->n, D->nlu, D->dev_out_size, D->dev_jac_size, D->hist_size);
+    return ws_doubles(*D);
 }
 
 // offsets (in doubles) of x, dx, ivec, sv, q, qprev, dq, y, tmp, xb, lu, out, jac, hist, piv
@@ -23,7 +23,7 @@ int cdn_engine_layout(cdn_plan* P, long* off) {
     off[11] = off[10] + D->nlu;
     off[12] = off[11] + D->dev_out_size;
     off[13] = off[12] + D->dev_jac_size;
-    off[14] = off[13] + D->hist_size;
+    off[14] = off[13] + D->hist_size + (D->sd ? CDN_SD8_FACT : 0);
     return CDN_OK;
 }
 
@@ -57,7 +57,7 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
     A.o.maxiter = r->maxiter; A.o.errfunc = r->errfunc; A.o.use_q = r->use_q; A.o.im = r->im;
     A.op = r->op; A.B = r->B;
     A.x = r->x; A.sv_in = r->sv_in; A.ws = r->ws;
-    const long per = ws_doubles(D->n, D->nlu, D->dev_out_size, D->dev_jac_size, D->hist_size);
+    const long per = ws_doubles(*D);
     A.ws_stride = per;
     A.nsamples = r->nsamples; A.first = r->first; A.init_ic = r->init_ic;
     A.nsrc = r->nsrc; A.nsave = r->nsave; A.helpers = r->helpers;
@@ -96,13 +96,21 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
         }
         c.T = (T <= 8) ? 8 : (T <= 16) ? 16 : 32;
         T = c.T;
-        // one CTA of 8 warps per SM when the batch fills the GPU: its tiles run
-        // in lockstep and share the instruction cache
+        // one CTA per SM when the batch fills the GPU (its tiles run in lockstep
+        // and share the instruction cache), sized so that every SM gets one:
+        // ceil(B / SMs) instances per CTA, whole warps, at most 256 threads
         c.tpb = ((long)A.B * T >= (long)ctx->sm_count * 128) ? 256 : 128;
-        if (cdn_tune_tile_tpb == 128 || cdn_tune_tile_tpb == 256) c.tpb = cdn_tune_tile_tpb;
+        if ((long)A.B * T >= (long)ctx->sm_count * 128) {
+            const long per_sm = (A.B + ctx->sm_count - 1) / ctx->sm_count;
+            long tpb = (per_sm * T + 31) / 32 * 32;
+            if (tpb < 128) tpb = 128;
+            if (tpb < c.tpb) c.tpb = (int)tpb;
+        }
+        if (cdn_tune_tile_tpb >= 32 && cdn_tune_tile_tpb <= 256 && cdn_tune_tile_tpb % 32 == 0)
+            c.tpb = cdn_tune_tile_tpb;
         if (!A.ws) {
             // state in shared memory: shrink the CTA until it fits
-            while (c.tpb > T && (long)(c.tpb / T) * per * 8 > 200 * 1024) c.tpb /= 2;
+            while (c.tpb > 32 && (long)(c.tpb / T) * per * 8 > 200 * 1024) c.tpb -= 32;
             c.smem = (long)(c.tpb / T) * per * 8;
             // room for the shared-memory copy of the plan's gather lists
             const long pb = plan_smem_bytes(*D);

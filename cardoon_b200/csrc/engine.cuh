@@ -84,28 +84,44 @@ struct cdn_engine_args {
 // ---- per-instance state ----------------------------------------------------------
 struct Ws {
     double *x, *dx, *ivec, *sv, *q, *qprev, *dq, *y, *tmp, *xb, *lu, *out, *jac, *hist;
+    double* fact;   // small dense plans: factors kept for the chord step (sd8_store)
     int* piv;       // [n] pivot rows (dense LU); piv[n] = pivot-trouble flag of the static-
                     // pivot sparse LU; piv[n + 1] = head of the history rings
     unsigned* stage;   // block team: shared-memory staging area for compact solve programs
     long long* dprof;  // optional fine-grained timers of the staged sweeps (slots 8..15)
 };
 
+// doubles of factor storage of a small dense plan (rows, reciprocal pivots, steps)
+// (rows 0..63, reciprocal pivots 64..71, steps and perm 72..76, then the partial
+// accumulators of sd8_gather)
+#define CDN_SD8_PART 77
+#define CDN_SD8_FACT (CDN_SD8_PART + CDN_SD8_NFIX + 1)
+
 __host__ __device__ inline long ws_doubles(int n, long nlu, long out_size, long jac_size,
-                                           long hist_size = 0) {
-    return 10L * n + nlu + out_size + jac_size + hist_size + (n + 1) / 2 + 2;
+                                           long hist_size = 0, long fact_size = 0) {
+    return 10L * n + nlu + out_size + jac_size + hist_size + fact_size + (n + 1) / 2 + 2;
+}
+__host__ __device__ inline long ws_doubles(const cdn_plan_dev& P) {
+    return ws_doubles(P.n, P.nlu, P.dev_out_size, P.dev_jac_size, P.hist_size,
+                      P.sd ? CDN_SD8_FACT : 0);
 }
 
 __device__ inline Ws ws_carve(double* base, int n, long nlu, long out_size, long jac_size,
-                              long hist_size = 0) {
+                              long hist_size = 0, long fact_size = 0) {
     Ws w;
     w.x = base; w.dx = w.x + n; w.ivec = w.dx + n; w.sv = w.ivec + n; w.q = w.sv + n;
     w.qprev = w.q + n; w.dq = w.qprev + n; w.y = w.dq + n; w.tmp = w.y + n; w.xb = w.tmp + n; w.lu = w.xb + n;
     w.out = w.lu + nlu; w.jac = w.out + out_size;
     w.hist = w.jac + jac_size;
-    w.piv = (int*)(w.hist + hist_size);
+    w.fact = w.hist + hist_size;
+    w.piv = (int*)(w.fact + fact_size);
     w.stage = nullptr;
     w.dprof = nullptr;
     return w;
+}
+__device__ inline Ws ws_carve(double* base, const cdn_plan_dev& P) {
+    return ws_carve(base, P.n, P.nlu, P.dev_out_size, P.dev_jac_size, P.hist_size,
+                    P.sd ? CDN_SD8_FACT : 0);
 }
 
 // ---- teams ---------------------------------------------------------------------------
@@ -258,15 +274,19 @@ struct WsSink {
     int ld, i, nxin;
     int ndel;            // the last ndel control ports are delayed:
     double coef[2];      // d v(t - tau) / d v(t) of each (nodalSP.py:872-875)
+    int ncs;             // outputs >= ncs are charges: their Jacobian rows are stored
+    double qs;           // times a0, as the reference stamps them (qJac = a0 * Jac[ncs:],
+                         // nodal.py:1117, nodalSP.py:878); the values stay unscaled
     CDN_HD void put(int slot, const Dual<P>& d) const {
         out[slot * ld + i] = d.v;
         if (P > 0) {
+            const double s = (slot >= ncs) ? qs : 1.0;
 #pragma unroll
             for (int c = 0; c < P; ++c)
                 if (c < nxin) {
                     double t = d.d[c];
                     if (ndel > 0 && c >= nxin - ndel) t *= coef[c - (nxin - ndel)];
-                    jac[(slot * nxin + c) * ld + i] = t;
+                    jac[(slot * nxin + c) * ld + i] = t * s;
                 }
         }
     }
@@ -316,12 +336,13 @@ __device__ __forceinline__ void gather_xin(const cdn_group_dev& G, int i, const 
 template <int MODEL, int P>
 __device__ __forceinline__ void eval_model(const cdn_group_dev& G, const PV& p, int i,
                                            const double* x, const Ws& w, int nhist, double h,
-                                           int head) {
+                                           int head, double qs) {
     Dual<P> v[CDN_MAX_XIN];
     gather_xin<P>(G, i, x, v);
     WsSink<P> sink;
     sink.out = w.out + G.out_off; sink.jac = w.jac + G.jac_off;
     sink.ld = G.n; sink.i = i; sink.nxin = G.nxin;
+    sink.ncs = G.ncs; sink.qs = qs;
     sink.ndel = 0;
     if ((MODEL == CDN_MODEL_MESFETC || MODEL == CDN_MODEL_MESFETC_T) && nhist > 0 && G.ndelay > 0) {
         // delayed copies of control voltages (nodalSP.py:860-875)
@@ -357,7 +378,7 @@ __device__ __forceinline__ void eval_model(const cdn_group_dev& G, const PV& p, 
 // one device: instance i of group G of circuit instance b
 template <int MS, bool DERIV>
 __device__ __noinline__ void eval_one(const cdn_group_dev& G, int b, int i, const double* x,
-                                      const Ws& w, int nhist, double h, int head) {
+                                      const Ws& w, int nhist, double h, int head, double qs) {
     long col = (G.per_inst ? (long)b * G.n : 0L) + i;
     if (G.pidx) col = CDN_LD(G.pidx + col);
     PV p;
@@ -365,58 +386,58 @@ __device__ __noinline__ void eval_one(const cdn_group_dev& G, int b, int i, cons
     p.ld = G.ldp;
     switch (G.model) {
     case CDN_MODEL_DIODE:
-        if (CDN_HAS(MS, CDN_MODEL_DIODE)) eval_model<CDN_MODEL_DIODE, DERIV ? 1 : 0>(G, p, i, x, w, 0, h, 0);
+        if (CDN_HAS(MS, CDN_MODEL_DIODE)) eval_model<CDN_MODEL_DIODE, DERIV ? 1 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_BJT:
-        if (CDN_HAS(MS, CDN_MODEL_BJT)) eval_model<CDN_MODEL_BJT, DERIV ? 4 : 0>(G, p, i, x, w, 0, h, 0);
+        if (CDN_HAS(MS, CDN_MODEL_BJT)) eval_model<CDN_MODEL_BJT, DERIV ? 4 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_SVBJT:
-        if (CDN_HAS(MS, CDN_MODEL_SVBJT)) eval_model<CDN_MODEL_SVBJT, DERIV ? 4 : 0>(G, p, i, x, w, 0, h, 0);
+        if (CDN_HAS(MS, CDN_MODEL_SVBJT)) eval_model<CDN_MODEL_SVBJT, DERIV ? 4 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_BSIM3:
-        if (CDN_HAS(MS, CDN_MODEL_BSIM3)) eval_model<CDN_MODEL_BSIM3, DERIV ? 3 : 0>(G, p, i, x, w, 0, h, 0);
+        if (CDN_HAS(MS, CDN_MODEL_BSIM3)) eval_model<CDN_MODEL_BSIM3, DERIV ? 3 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_EKV:
-        if (CDN_HAS(MS, CDN_MODEL_EKV)) eval_model<CDN_MODEL_EKV, DERIV ? 3 : 0>(G, p, i, x, w, 0, h, 0);
+        if (CDN_HAS(MS, CDN_MODEL_EKV)) eval_model<CDN_MODEL_EKV, DERIV ? 3 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_MEMR:
-        if (CDN_HAS(MS, CDN_MODEL_MEMR)) eval_model<CDN_MODEL_MEMR, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0);
+        if (CDN_HAS(MS, CDN_MODEL_MEMR)) eval_model<CDN_MODEL_MEMR, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_DIODE_T:
         if (CDN_HAS(MS, CDN_MODEL_DIODE_T))
-            eval_model<CDN_MODEL_DIODE_T, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0);
+            eval_model<CDN_MODEL_DIODE_T, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_BJT_T:
         if (CDN_HAS(MS, CDN_MODEL_BJT_T))
-            eval_model<CDN_MODEL_BJT_T, DERIV ? 5 : 0>(G, p, i, x, w, 0, h, 0);
+            eval_model<CDN_MODEL_BJT_T, DERIV ? 5 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_SVBJT_T:
         if (CDN_HAS(MS, CDN_MODEL_SVBJT_T))
-            eval_model<CDN_MODEL_SVBJT_T, DERIV ? 5 : 0>(G, p, i, x, w, 0, h, 0);
+            eval_model<CDN_MODEL_SVBJT_T, DERIV ? 5 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_MESFETC_T:
         if (CDN_HAS(MS, CDN_MODEL_MESFETC_T))
-            eval_model<CDN_MODEL_MESFETC_T, DERIV ? 5 : 0>(G, p, i, x, w, nhist, h, head);
+            eval_model<CDN_MODEL_MESFETC_T, DERIV ? 5 : 0>(G, p, i, x, w, nhist, h, head, qs);
         break;
     case CDN_MODEL_SVDIODE:
         if (CDN_HAS(MS, CDN_MODEL_SVDIODE))
-            eval_model<CDN_MODEL_SVDIODE, DERIV ? 1 : 0>(G, p, i, x, w, 0, h, 0);
+            eval_model<CDN_MODEL_SVDIODE, DERIV ? 1 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_SVDIODE_T:
         if (CDN_HAS(MS, CDN_MODEL_SVDIODE_T))
-            eval_model<CDN_MODEL_SVDIODE_T, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0);
+            eval_model<CDN_MODEL_SVDIODE_T, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_RES_T:
         if (CDN_HAS(MS, CDN_MODEL_RES_T))
-            eval_model<CDN_MODEL_RES_T, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0);
+            eval_model<CDN_MODEL_RES_T, DERIV ? 2 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_EKV_T:
         if (CDN_HAS(MS, CDN_MODEL_EKV_T))
-            eval_model<CDN_MODEL_EKV_T, DERIV ? 4 : 0>(G, p, i, x, w, 0, h, 0);
+            eval_model<CDN_MODEL_EKV_T, DERIV ? 4 : 0>(G, p, i, x, w, 0, h, 0, qs);
         break;
     case CDN_MODEL_MESFETC:
         if (CDN_HAS(MS, CDN_MODEL_MESFETC))
-            eval_model<CDN_MODEL_MESFETC, DERIV ? 4 : 0>(G, p, i, x, w, nhist, h, head);
+            eval_model<CDN_MODEL_MESFETC, DERIV ? 4 : 0>(G, p, i, x, w, nhist, h, head, qs);
         break;
     default: break;
     }
@@ -427,18 +448,18 @@ __device__ __noinline__ void eval_one(const cdn_group_dev& G, int b, int i, cons
 template <int MS, bool DERIV, class Team>
 __device__ __forceinline__ void eval_devices(Team& tm, const cdn_plan_dev& P, int b,
                                              const double* x, const Ws& w, bool delayed = false,
-                                             double h = 0.0) {
+                                             double h = 0.0, double qs = 1.0) {
     const int nhist = delayed ? P.nhist : 0;
     const int head = nhist ? w.piv[P.n + 1] : 0;
     if (Team::kFlat) {
         for (int d = tm.rank(); d < P.ndev; d += tm.size())
             eval_one<MS, DERIV>(P.groups[CDN_LD(P.dev_g + d)], b, CDN_LD(P.dev_i + d), x, w, nhist,
-                                h, head);
+                                h, head, qs);
     } else {
         for (int g = 0; g < P.ngroups; ++g) {
             const cdn_group_dev& G = P.groups[g];
             for (int i = tm.rank(); i < G.n; i += tm.size())
-                eval_one<MS, DERIV>(G, b, i, x, w, nhist, h, head);
+                eval_one<MS, DERIV>(G, b, i, x, w, nhist, h, head, qs);
         }
     }
     tm.sync();
@@ -582,7 +603,11 @@ __device__ __forceinline__ bool residual(Team& tm, const cdn_plan_dev& P, const 
     return fin;
 }
 
-// Jacobian slots: G' + Ti J Tcv + a0 Tq Jq Tcv (+ gmin Gones)
+// Jacobian slots: G' + Ti J Tcv + a0 Tq Jq Tcv (+ gmin Gones).  The charge rows of
+// the device Jacobians arrive already multiplied by a0 (WsSink), so every
+// contribution is +-1 times a stored value.
+__device__ __forceinline__ double pk_sign(unsigned pk) { return (pk & (1u << 29)) ? -1.0 : 1.0; }
+
 template <class Team>
 __device__ __forceinline__ double slot_sum(const cdn_plan_dev& P, const Ws& w, const cdn_opts& o,
                                            double a0, int e, int first, int stride) {
@@ -597,16 +622,16 @@ __device__ __forceinline__ double slot_sum(const cdn_plan_dev& P, const Ws& w, c
             const unsigned p2 = CDN_LD(P.e_con_pk + k + 2), p3 = CDN_LD(P.e_con_pk + k + 3);
             const double j0 = w.jac[p0 & 0x1fffffffu], j1 = w.jac[p1 & 0x1fffffffu];
             const double j2 = w.jac[p2 & 0x1fffffffu], j3 = w.jac[p3 & 0x1fffffffu];
-            v = fma(pk_coef(p0, a0), j0, v);
-            v1 = fma(pk_coef(p1, a0), j1, v1);
-            v2 = fma(pk_coef(p2, a0), j2, v2);
-            v3 = fma(pk_coef(p3, a0), j3, v3);
+            v = fma(pk_sign(p0), j0, v);
+            v1 = fma(pk_sign(p1), j1, v1);
+            v2 = fma(pk_sign(p2), j2, v2);
+            v3 = fma(pk_sign(p3), j3, v3);
         }
         v += (v1 + v2) + v3;
     }
     for (; k < c1; k += stride) {
         const unsigned pk = CDN_LD(P.e_con_pk + k);
-        v = fma(pk_coef(pk, a0), w.jac[pk & 0x1fffffffu], v);
+        v = fma(pk_sign(pk), w.jac[pk & 0x1fffffffu], v);
     }
     return v;
 }
@@ -1224,6 +1249,209 @@ __device__ __forceinline__ void lusolve(Team& tm, const cdn_plan_dev& P, const W
     }
 }
 
+
+// ==== small dense systems (dense plan, n <= 8) on an 8-lane warp tile ==================
+// The Newton linear algebra of a batch instance lives in the registers of its
+// tile, one matrix ROW per lane (lane r: row r of [J | y]):
+//   * the device-Jacobian contributions are summed from flat, equally long
+//     per-lane term lists (plan.h sd_prog) into w.lu, one barrier;
+//   * lane r adds the linear part G' = G + a0 C (+ gmin patterns) of its row,
+//     which at the same time gives the linear part of the residual, G' x;
+//   * Gaussian elimination with partial pivoting (LAPACK getrf arithmetic:
+//     largest |a_ik| of the remaining rows, multipliers by the reciprocal of
+//     the pivot, a zero pivot leaves its column unscaled) runs on the registers
+//     with the right-hand side carried along; rows are not moved -- the lane
+//     that holds the pivot row of step k is remembered instead (`perm`);
+//   * back substitution, damping and the convergence test follow in registers;
+//   * multipliers, U rows and reciprocal pivots are stored (w.fact) so that the
+//     chord predictor of the next time step (tran.py:181) re-uses them.
+// Ties between equal pivot candidates go to the lowest lane (LAPACK: lowest
+// current row position); values agree with getrf/getrs to rounding.
+struct Sd8 {
+    double row[8];
+    double y;        // right-hand side entry, then solution of unknown `step`
+    double pinv;     // 1 / pivot of the step at which this lane held the pivot row
+    int step;        // that step = the unknown this lane solves for (8: none yet)
+    unsigned perm;   // lane holding the pivot row of step k in bits 4k .. 4k + 2
+};
+
+// w.lu[e] = sum of the device-Jacobian contributions of slot e
+__device__ __forceinline__ void sd8_gather(TileTeam<8>& tm, const cdn_plan_dev& P, const Ws& w) {
+    const int l = tm.rank();
+    const int t0 = CDN_LD(P.sd_ptr + l), len = CDN_LD(P.sd_ptr + l + 1) - t0;
+    double acc = 0.0;
+    for (int t = 0; t < P.sd_maxlen; ++t) {
+        if (t < len) {
+            const unsigned pk = CDN_LD(P.sd_prog + t0 + t);
+            const double v = w.jac[pk & 0xfffffu];
+            // +- v: flip the sign bit
+            acc += __hiloint2double(__double2hiint(v) ^ (int)(pk & 0x80000000u), __double2loint(v));
+            if (pk & (1u << 30)) {
+                const int a = (int)((pk >> 20) & 63u);
+                // slot, or partial accumulator of a slot cut between two lanes
+                if (a < P.nlu) w.lu[a] = acc;
+                else w.fact[CDN_SD8_PART + a - P.nlu] = acc;
+                acc = 0.0;
+            }
+        }
+    }
+    tm.sync();
+    if (P.sd_nfix) {
+        if (l == 0)
+            for (int j = 0; j < P.sd_nfix; ++j) w.lu[CDN_LD(P.sd_fix + j)] += w.fact[CDN_SD8_PART + j];
+        tm.sync();
+    }
+}
+
+// Rows of J and the residual: S.row = G' row + device part, w.ivec = i(x),
+// S.y = lambda sv - i(x).  Returns whether this lane's row and rhs are finite.
+__device__ __forceinline__ bool sd8_rows(TileTeam<8>& tm, const cdn_plan_dev& P, const Ws& w,
+                                         const cdn_opts& o, Sd8& S, bool want_jac) {
+    const int n = P.n, l = tm.rank();
+    const int r = l < n ? l : n - 1;              // spare lanes shadow the last row
+    const double a0 = o.use_q ? o.a0 : 0.0;
+    double lin = 0.0;
+    bool fin = true;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        double v = 0.0;
+        if (c < n) {
+            const int e = r * n + c;
+            double b = CDN_LD(P.e_g + e);
+            if (o.use_q) b = fma(a0, CDN_LD(P.e_c + e), b);
+            if (o.gmin != 0.0) b = fma(o.gmin, CDN_LD(P.e_gones + e), b);
+            if (o.gmin_ext != 0.0 && c == r && r < o.n_ext) b += o.gmin_ext;   // nodal.py:478-479
+            lin = fma(b, w.x[c], lin);
+            if (want_jac) {
+                v = w.lu[e] + b;
+                fin = fin && isfinite(v);
+            }
+        }
+        S.row[c] = v;
+    }
+    // device currents and charges of this row (flat: every lane runs sd_rmax trips)
+    const int c0 = CDN_LD(P.r_con_ptr + r), len = CDN_LD(P.r_con_ptr + r + 1) - c0;
+    double acc = lin;
+    for (int t = 0; t < P.sd_rmax; ++t)
+        if (t < len) {
+            const unsigned pk = CDN_LD(P.r_con_pk + c0 + t);
+            acc = fma(pk_coef(pk, a0), w.out[pk & 0x1fffffffu], acc);
+        }
+    const double y = o.lambda * w.sv[r] - acc;
+    if (l < n) { w.ivec[l] = acc; w.y[l] = y; }
+    S.y = y;
+    return (l >= n) || (fin && isfinite(y));
+}
+
+// Elimination with the right-hand side carried along (forward substitution fused).
+__device__ __forceinline__ void sd8_factor(TileTeam<8>& tm, Sd8& S, int n) {
+    const int l = tm.rank();
+    S.step = 8;
+    S.perm = 0u;
+    S.pinv = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k < n) {
+            const bool cand = (l < n) && (S.step == 8);
+            double v = fabs(S.row[k]);
+            if (!(v >= 0.0)) v = -1.0;                 // NaN loses against any number
+            if (!cand) v = -2.0;
+            int p = l;
+#pragma unroll
+            for (int off = 4; off > 0; off >>= 1) {
+                const double v2 = tm.tile.shfl_xor(v, off);
+                const int p2 = tm.tile.shfl_xor(p, off);
+                if (v2 > v || (v2 == v && p2 < p)) { v = v2; p = p2; }
+            }
+            S.perm |= (unsigned)p << (4 * k);
+            const double pv = tm.tile.shfl(S.row[k], p);
+            const double pinv = 1.0 / pv;
+            const double m = S.row[k] * ((pv != 0.0) ? pinv : 1.0);   // dgetf2: zero pivot
+            const bool elim = cand && (l != p);
+            if (l == p) { S.step = k; S.pinv = pinv; }
+            if (elim) S.row[k] = m;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j > k && j < n) {
+                    const double pr = tm.tile.shfl(S.row[j], p);
+                    if (elim) S.row[j] = fma(-m, pr, S.row[j]);
+                }
+            const double py = tm.tile.shfl(S.y, p);
+            if (elim) S.y = fma(-m, py, S.y);
+        }
+    }
+}
+
+// forward substitution of a fresh right-hand side with stored factors
+__device__ __forceinline__ void sd8_forward(TileTeam<8>& tm, Sd8& S, int n) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < n) {
+            const double yk = tm.tile.shfl(S.y, (int)((S.perm >> (4 * k)) & 7u));
+            if (S.step > k && S.step < 8) S.y = fma(-S.row[k], yk, S.y);
+        }
+}
+
+// U x = y; afterwards the lane that held the pivot row of step k holds x_k
+__device__ __forceinline__ void sd8_backward(TileTeam<8>& tm, Sd8& S, int n) {
+    const int l = tm.rank();
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        const int k = 7 - kk;
+        if (k < n) {
+            const int p = (int)((S.perm >> (4 * k)) & 7u);
+            const double xk = tm.tile.shfl(S.y * S.pinv, p);
+            if (S.step < k) S.y = fma(-S.row[k], xk, S.y);
+            if (l == p) S.y = xk;
+        }
+    }
+}
+
+// x_l for lane l (unknown l sits in the lane that held the pivot row of step l)
+__device__ __forceinline__ double sd8_unknown(TileTeam<8>& tm, const Sd8& S) {
+    const int l = tm.rank();
+    return tm.tile.shfl(S.y, (int)((S.perm >> (4 * l)) & 7u));
+}
+
+__device__ __forceinline__ void sd8_store(TileTeam<8>& tm, const Sd8& S, const Ws& w) {
+    const int l = tm.rank();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w.fact[l * 8 + c] = S.row[c];
+    w.fact[64 + l] = S.pinv;
+    int* meta = (int*)(w.fact + 72);
+    meta[l] = S.step;
+    if (l == 0) meta[8] = (int)S.perm;
+}
+
+__device__ __forceinline__ void sd8_load(TileTeam<8>& tm, Sd8& S, const Ws& w) {
+    const int l = tm.rank();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) S.row[c] = w.fact[l * 8 + c];
+    S.pinv = w.fact[64 + l];
+    const int* meta = (const int*)(w.fact + 72);
+    S.step = meta[l];
+    S.perm = (unsigned)meta[8];
+}
+
+__device__ __forceinline__ double sd8_max(TileTeam<8>& tm, double v) {
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) v = fmax(v, tm.tile.shfl_xor(v, off));
+    return v;
+}
+
+// dx = LU \ (sv - iVec) with the stored factors; x += dx (tran.py:181)
+__device__ __forceinline__ void sd8_chord(TileTeam<8>& tm, const cdn_plan_dev& P, const Ws& w) {
+    const int n = P.n, l = tm.rank();
+    Sd8 S;
+    sd8_load(tm, S, w);
+    S.y = (l < n) ? w.sv[l] - w.ivec[l] : 0.0;
+    sd8_forward(tm, S, n);
+    sd8_backward(tm, S, n);
+    const double d = sd8_unknown(tm, S);
+    if (l < n) { w.dx[l] = d; w.x[l] += d; }
+    tm.sync();
+}
+
 // ---- damped Newton (fsolve.py:59-128) -------------------------------------------------
 // Returns the iteration count; *ok tells whether the tolerances were met.
 // On return w.ivec holds the residual evaluated at the LAST-BUT-ONE iterate and
@@ -1253,7 +1481,7 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
     while (tm.cta_any(run && it < o.maxiter)) {
         if (!(run && it < o.maxiter)) continue;
         CDN_PROF_T0;
-        eval_devices<MS, true>(tm, P, b, w.x, w, true, o.h);
+        eval_devices<MS, true>(tm, P, b, w.x, w, true, o.h, o.use_q ? o.a0 : 1.0);
         CDN_PROF(0);
         bool fin = residual(tm, P, w, o);
         if (fs && try_staged_refactor(tm, P, w, o, *fs)) {
@@ -1312,6 +1540,82 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
     *res_out = res;
     *ok = success;
     return it;
+}
+
+
+// The same iteration for small dense plans on 8-lane tiles (sd8_* above).
+template <int MS>
+__device__ __forceinline__ int newton_sd8(TileTeam<8>& tm, const cdn_plan_dev& P, int b,
+                                          const Ws& w, const cdn_opts& o, bool active,
+                                          double* res_out, bool* ok, long long* prof) {
+    const int n = P.n, l = tm.rank();
+    double res = 0.0;
+    bool success = false;
+    int it = 0;
+    bool run = active;
+    while (tm.cta_any(run && it < o.maxiter)) {
+        if (!(run && it < o.maxiter)) continue;
+        CDN_PROF_T0;
+        eval_devices<MS, true>(tm, P, b, w.x, w, true, o.h, o.use_q ? o.a0 : 1.0);
+        CDN_PROF(0);
+        sd8_gather(tm, P, w);
+        Sd8 S;
+        const bool fin = sd8_rows(tm, P, w, o, S, true);
+        if (!tm.all(fin)) {             // see newton(): this solve has failed
+            ++it;
+            res = INFINITY;
+            run = false;
+            continue;
+        }
+        CDN_PROF(1);
+        sd8_factor(tm, S, n);
+        sd8_store(tm, S, w);
+        CDN_PROF(2);
+        sd8_backward(tm, S, n);
+        double d = sd8_unknown(tm, S);
+        if (!isfinite(d))               // condition_array (nodal.py:385-402)
+            d = isnan(d) ? 10.0 * o.abstol : (d > 0.0 ? 0.1 : -0.1) * o.maxdelta;
+        if (l >= n) d = 0.0;
+        CDN_PROF(3);
+        const double m = sd8_max(tm, fabs(d));
+        const bool damp = m > o.maxdelta;
+        const double scale = damp ? o.maxdelta / m : 1.0;
+        if (damp) d *= scale;
+        bool conv = true;
+        if (l < n) {
+            const double xo = w.x[l], xn = xo + d;
+            conv = fabs(d) < o.reltol * fmax(fabs(xo), fabs(xn)) + o.abstol;
+            w.x[l] = xn;
+            w.dx[l] = d;
+        }
+        res = damp ? m * scale : m;
+        const bool n1 = tm.all(conv);
+        tm.sync();
+        bool n2 = true;
+        if (n1 && o.errfunc) {
+            eval_devices<MS, false>(tm, P, b, w.x, w, true, o.h);
+            Sd8 R;
+            sd8_rows(tm, P, w, o, R, false);
+            const double ef = sd8_max(tm, l < n ? fabs(R.y) : 0.0);
+            tm.sync();
+            n2 = ef < o.abstol;
+            res = fmax(ef, res);
+        }
+        ++it;
+        if (n1 && n2) { success = true; run = false; }
+        CDN_PROF(4);
+    }
+    *res_out = res;
+    *ok = success;
+    return it;
+}
+
+template <int MS>
+__device__ __forceinline__ int newton(TileTeam<8>& tm, const cdn_plan_dev& P, int b, const Ws& w,
+                                      const cdn_opts& o, bool active, double* res_out, bool* ok,
+                                      long long* prof = nullptr, FactState* fs = nullptr) {
+    if (P.sd) return newton_sd8<MS>(tm, P, b, w, o, active, res_out, ok, prof);
+    return newton<MS, TileTeam<8> >(tm, P, b, w, o, active, res_out, ok, prof, fs);
 }
 
 // Continuation on lambda with bisection and backtracking (nodal.py:545-604):
@@ -1460,6 +1764,14 @@ __device__ __forceinline__ void chord(Team& tm, const cdn_plan_dev& P, const Ws&
     tm.sync();
     lusolve(tm, P, w, o, false);
 }
+// (tile of 8 on a small dense plan: stored row factors; also applies x += dx)
+__device__ __forceinline__ bool chord_sd8(TileTeam<8>& tm, const cdn_plan_dev& P, const Ws& w) {
+    if (!P.sd) return false;
+    sd8_chord(tm, P, w);
+    return true;
+}
+template <class Team>
+__device__ __forceinline__ bool chord_sd8(Team&, const cdn_plan_dev&, const Ws&) { return false; }
 
 // ---- one circuit instance, one operation ------------------------------------------------
 // `active` is false for the padding tiles of a ragged batch: they only take
@@ -1508,7 +1820,7 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
                 make_rhs(tm, P, w, o, A.src_dc, A.nsrc, A.src_rows,
                          A.src_val + (long)i * A.nsrc);
                 CDN_PROF(5);
-                if (i > 1) {                     // chord predictor (tran.py:181)
+                if (i > 1 && !chord_sd8(tm, P, w)) {   // chord predictor (tran.py:181)
                     chord(tm, P, w, o);
                     for (int r = tm.rank(); r < n; r += tm.size()) w.x[r] += w.dx[r];
                     tm.sync();
@@ -1565,7 +1877,7 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
         break;
     case CDN_OP_GET_I_JAC:
         if (!active) break;
-        eval_devices<MS, true>(tm, P, b, w.x, w, true, o.h);
+        eval_devices<MS, true>(tm, P, b, w.x, w, true, o.h, o.use_q ? o.a0 : 1.0);
         assemble(tm, P, w, o);
         residual(tm, P, w, o);
         tm.sync();
@@ -1588,6 +1900,7 @@ __host__ __device__ inline long plan_smem_bytes(const cdn_plan_dev& P) {
     b += (long)P.nrlin * (4 + 3 * 8);            // r_lin_col, r_lin_g/c/gones
     b += (long)P.nrcon * 4;                      // r_con_pk
     b += (long)P.ndev * 8;                       // dev_g, dev_i
+    if (P.sd) b += 9L * 4 + 4L * P.sd_nterms + 4L * P.sd_nfix;   // sd_ptr, sd_prog, sd_fix
     for (int g = 0; g < P.ngroups; ++g) b += 2L * P.groups[g].nxin * P.groups[g].n * 4;
     return b + 16 * 16;                          // alignment slack
 }
@@ -1625,6 +1938,9 @@ __device__ __forceinline__ void plan_to_smem(const cdn_plan_dev& G, cdn_plan_dev
     const int* e_bal = smem_copy(G.e_bal, G.nlu, cur);
     const int* dev_g = smem_copy(G.dev_g, G.ndev, cur);
     const int* dev_i = smem_copy(G.dev_i, G.ndev, cur);
+    const int* sd_ptr = G.sd ? smem_copy(G.sd_ptr, 9L, cur) : nullptr;
+    const unsigned* sd_prog = G.sd ? smem_copy(G.sd_prog, (long)G.sd_nterms, cur) : nullptr;
+    const int* sd_fix = G.sd ? smem_copy(G.sd_fix, (long)G.sd_nfix, cur) : nullptr;
     const int* vp[CDN_MAX_GROUPS];
     const int* vn[CDN_MAX_GROUPS];
     for (int g = 0; g < G.ngroups; ++g) {
@@ -1639,6 +1955,7 @@ __device__ __forceinline__ void plan_to_smem(const cdn_plan_dev& G, cdn_plan_dev
         S.r_lin_ptr = r_lin_ptr; S.r_lin_col = r_lin_col;
         S.r_con_ptr = r_con_ptr; S.r_con_pk = r_con_pk; S.e_bal = e_bal;
         S.dev_g = dev_g; S.dev_i = dev_i;
+        if (G.sd) { S.sd_ptr = sd_ptr; S.sd_prog = sd_prog; S.sd_fix = sd_fix; }
         for (int g = 0; g < G.ngroups; ++g) { S.groups[g].vpos = vp[g]; S.groups[g].vneg = vn[g]; }
     }
     __syncthreads();
@@ -1660,12 +1977,11 @@ engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
     __shared__ cdn_plan_dev Ps;
     const bool shadow = A.plan_smem > 0;
     if (shadow) {
-        const long per0 = ws_doubles(A.plan.n, A.plan.nlu, A.plan.dev_out_size,
-                                     A.plan.dev_jac_size, A.plan.hist_size);
+        const long per0 = ws_doubles(A.plan);
         plan_to_smem(A.plan, Ps, (char*)(smem + (long)tiles * per0));
     }
     const cdn_plan_dev& P = shadow ? Ps : A.plan;
-    const long per = ws_doubles(P.n, P.nlu, P.dev_out_size, P.dev_jac_size, P.hist_size);
+    const long per = ws_doubles(P);
     // the loop bounds are CTA-uniform: padding tiles run along inactive
     for (int b0 = blockIdx.x * tiles; b0 < A.B; b0 += gridDim.x * tiles) {
         const int b = b0 + tile_id;
@@ -1674,9 +1990,12 @@ engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
         // routed to the block kernel): with the address space known at compile
         // time the state is accessed with LDS/STS, not generic loads and stores
         double* base = smem + (long)tile_id * per;
-        const Ws w = ws_carve(base, P.n, P.nlu, P.dev_out_size, P.dev_jac_size, P.hist_size);
+        const Ws w = ws_carve(base, P);
         if (active) {
             for (int r = tm.rank(); r < P.n; r += T) w.x[r] = A.x[(long)b * P.n + r];
+            // (small dense plans accumulate device contributions per slot in
+            // w.lu: slots without any stay zero)
+            if (P.sd) for (int e = tm.rank(); e < P.nlu; e += T) w.lu[e] = 0.0;
             tm.sync();
         }
         run_instance<MS>(tm, A, P, b, w, active);
@@ -1703,8 +2022,7 @@ engine_block_kernel(const __grid_constant__ cdn_engine_args A) {
     BlockTeam tm;
     tm.sred = sred; tm.ired = ired;
     for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
-        Ws w = ws_carve(A.ws + (long)b * A.ws_stride, P.n, P.nlu, P.dev_out_size,
-                        P.dev_jac_size, P.hist_size);
+        Ws w = ws_carve(A.ws + (long)b * A.ws_stride, P);
         double* const g_lu = w.lu;
         if (A.smem_lu) {
             w.lu = dsm; w.tmp = dsm + P.nlu;
@@ -1733,7 +2051,7 @@ engine_grid_kernel(const __grid_constant__ cdn_engine_args A) {
     const cdn_plan_dev& P = A.plan;
     GridTeam tm;
     tm.sred = sred; tm.gred = A.red;
-    const Ws w = ws_carve(A.ws, P.n, P.nlu, P.dev_out_size, P.dev_jac_size, P.hist_size);
+    const Ws w = ws_carve(A.ws, P);
     if (A.op == CDN_OP_NEWTON || A.op == CDN_OP_TRAN) {
         for (int r = tm.rank(); r < P.n; r += tm.size()) w.x[r] = A.x[r];
         tm.sync();

@@ -11,6 +11,8 @@
 #define CDN_MAX_GROUPS 16
 // gather / term lists longer than this are summed cooperatively by the team
 #define CDN_HEAVY 256
+// partial accumulators of the small dense tile programs (see cdn_plan_dev::sd)
+#define CDN_SD8_NFIX 10
 
 // one homogeneous group of nonlinear devices (same model, flags, port counts)
 struct cdn_group_dev {
@@ -84,6 +86,24 @@ struct cdn_plan_dev {
     int naff;                 // entries in the partial refactorisation
     const int* e_bal;         // [nlu] dense plans: slots by decreasing gather length, so
                               // that a strided walk gives every lane the same work
+    // ---- small dense systems (dense, n <= 8): programs of the 8-lane warp tiles
+    // (engine.cuh sd8_*).  The device-Jacobian contributions of all slots, slot
+    // after slot, are cut into eight equally long pieces, one per lane, so that
+    // every lane walks one flat list of the same length:
+    //   term = index into dev_jac | accumulator << 20 | last term of its
+    //          accumulator in this piece << 30 | minus sign << 31
+    // Accumulator a < nlu is slot a itself; a slot that straddles a cut continues
+    // in the next lane on partial accumulator nlu + j, which lane 0 adds to slot
+    // sd_fix[j] afterwards (at most CDN_SD8_NFIX of them).
+    int sd;                   // 1: programs present
+    int sd_maxlen;            // longest lane list
+    int sd_rmax;              // longest per-row list of device-output contributions
+    int sd_nterms;            // length of sd_prog
+    const int* sd_ptr;        // [9] lane l owns sd_prog[sd_ptr[l] .. sd_ptr[l + 1])
+    const unsigned* sd_prog;
+    int sd_nfix;              // partial accumulators
+    int sd_pad_;
+    const int* sd_fix;        // [sd_nfix] slot each partial belongs to
     // ---- triangular solves (permuted index space) --------------------------
     const int* l_lvl_ptr;     // [nlev_l+1]
     const int* l_rows;        // [n] rows ordered by level

@@ -154,7 +154,7 @@ struct cdn_plan {
             e_con_src, e_con_kind, l_lvl_ptr, l_rows, l_ptr, l_col, l_slot, u_lvl_ptr, u_rows,
             u_ptr, u_col, u_slot, u_diag, rowmap, colmap, r_lin_ptr, r_lin_col, r_lin_g,
             r_lin_c, r_lin_gones, r_con_ptr, r_con_src, r_con_kind, dev_g, dev_i, e_con_pk,
-            r_con_pk, e_bal, cl_prog, cu_prog, cf_prog;
+            r_con_pk, e_bal, cl_prog, cu_prog, cf_prog, sd_ptr, sd_prog, sd_fix;
         long gv[CDN_MAX_GROUPS][2];
         long gd[CDN_MAX_GROUPS];
     } off;
@@ -725,6 +725,53 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
             return (e_con_ptr[a + 1] - e_con_ptr[a]) > (e_con_ptr[b + 1] - e_con_ptr[b]);
         });
     PUT(e_bal);
+    // small dense systems: flat per-lane programs of the device-Jacobian
+    // contributions (plan.h); slot e = row * n + unknown for dense storage
+    ivec sd_ptr(9, 0);
+    std::vector<unsigned> sd_prog;
+    int sd_maxlen = 0, sd_rmax = 0;
+    bool sd = dense && n <= 8 && jac_size < (1L << 20) && e_heavy.empty() && r_heavy.empty();
+    if (sd)
+        for (long e = 0; e < nlu; ++e)
+            if (P->slot_row[e] * n + P->slot_col[e] != e) sd = false;
+    ivec sd_fix;
+    if (sd) {
+        // all terms, slot after slot (longest lists first), cut into 8 pieces
+        struct T { int e; int src; bool minus; };
+        std::vector<T> all;
+        for (long q = 0; q < nlu; ++q) {
+            const int e = e_bal[q];
+            for (int k = e_con_ptr[e]; k < e_con_ptr[e + 1]; ++k)
+                all.push_back(T{e, e_con_src[k], e_con_kind[k] < 0});
+        }
+        const long total = (long)all.size();
+        const long chunk = (total + 7) / 8;
+        for (int l = 0; l < 8; ++l) {
+            const long t0 = std::min(total, l * chunk), t1 = std::min(total, (l + 1) * chunk);
+            for (long t = t0; t < t1; ++t) {
+                const int e = all[t].e;
+                // the slot's first term lies in an earlier piece: partial accumulator
+                const bool cont = t0 > 0 && all[t0 - 1].e == e;
+                int acc = e;
+                if (cont) {
+                    if (t == t0) sd_fix.push_back(e);
+                    acc = (int)nlu + (int)sd_fix.size() - 1;
+                }
+                unsigned w = (unsigned)all[t].src | ((unsigned)acc << 20);
+                if (all[t].minus) w |= 1u << 31;
+                if (t + 1 == t1 || all[t + 1].e != e) w |= 1u << 30;
+                sd_prog.push_back(w);
+            }
+            sd_ptr[l + 1] = (int)sd_prog.size();
+            sd_maxlen = std::max(sd_maxlen, sd_ptr[l + 1] - sd_ptr[l]);
+        }
+        if ((long)sd_fix.size() > CDN_SD8_NFIX || nlu + (long)sd_fix.size() > 64) {
+            sd = false; sd_prog.clear(); sd_fix.clear(); sd_maxlen = 0;
+            for (int l = 0; l < 9; ++l) sd_ptr[l] = 0;
+        }
+        for (int r = 0; r < n; ++r) sd_rmax = std::max(sd_rmax, r_con_ptr[r + 1] - r_con_ptr[r]);
+    }
+    PUT(sd_ptr); PUT(sd_prog); PUT(sd_fix);
     {
         ivec dg, di;
         for (int g = 0; g < c->ngroups; ++g)
@@ -735,6 +782,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     }
     cdn_plan_dev& D = P->dev;
     D.dense = dense ? 1 : 0;
+    D.sd = sd ? 1 : 0; D.sd_maxlen = sd_maxlen; D.sd_rmax = sd_rmax; D.sd_nterms = (int)sd_prog.size(); D.sd_nfix = (int)sd_fix.size(); D.sd_pad_ = 0;
     D.compact = compact ? 1 : 0; D.nnzl = (int)l_col.size(); D.nnzu = (int)u_col.size();
     D.cl_words = (int)cl_prog.size(); D.cu_words = (int)cu_prog.size();
     D.cf_words = (int)cf_prog.size(); D.naff = naff;
@@ -817,6 +865,7 @@ extern "C" int cdn_plan_bind(cdn_plan* P, void* dev_ws, long bytes, void* stream
     BIND(dev_g, int); BIND(dev_i, int);
     BIND(e_con_pk, unsigned); BIND(r_con_pk, unsigned); BIND(e_bal, int);
     BIND(cl_prog, unsigned); BIND(cu_prog, unsigned); BIND(cf_prog, unsigned);
+    BIND(sd_ptr, int); BIND(sd_prog, unsigned); BIND(sd_fix, int);
 #undef BIND
     for (int g = 0; g < D.ngroups; ++g) {
         D.groups[g].vpos = (const int*)(base + O.gv[g][0]);

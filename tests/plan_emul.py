@@ -159,3 +159,105 @@ class HostPlan(object):
                 dx[a['colmap'][i]] = v
             done[rows] = True
         return dx
+
+
+# ---------------------------------------------------------------------------
+# small dense systems on 8-lane tiles (csrc/engine.cuh sd8_*)
+# ---------------------------------------------------------------------------
+def sd8_program(hp):
+    """(sd_ptr, sd_prog) of a dense plan with n <= 8, or None."""
+    ptr = nd.plan_array(hp.dll, hp.plan, 'sd_ptr')
+    prog = nd.plan_array(hp.dll, hp.plan, 'sd_prog')
+    return (ptr, prog) if ptr[-1] > 0 else None
+
+
+def sd8_gather(hp, jac_scaled):
+    """w.lu after sd8_gather: per-slot sums of the device contributions
+    (``jac_scaled``: charge rows already times a0, as WsSink stores them)."""
+    ptr, prog = sd8_program(hp)
+    fix = nd.plan_array(hp.dll, hp.plan, 'sd_fix')
+    lu = np.zeros(hp.nlu)
+    part = np.zeros(len(fix))
+    for lane in range(8):
+        acc = 0.
+        for t in range(ptr[lane], ptr[lane + 1]):
+            pk = int(prog[t])
+            v = jac_scaled[pk & 0xfffff]
+            acc += -v if pk & 0x80000000 else v
+            if pk & (1 << 30):
+                a = (pk >> 20) & 63
+                if a < hp.nlu:
+                    lu[a] = acc
+                else:
+                    part[a - hp.nlu] = acc
+                acc = 0.
+        assert acc == 0.          # every piece ends with a flush
+    for j, e in enumerate(fix):
+        lu[e] += part[j]
+    return lu
+
+
+def sd8_solve(J, y):
+    """sd8_factor + sd8_backward + sd8_unknown on rows J[r] / rhs y (n <= 8):
+    lane-parallel elimination without row moves, emulated lane by lane.
+    Returns (x, factors) where factors = (rows, pinv, step, perm)."""
+    n = len(y)
+    row = np.zeros((8, 8))
+    row[:n, :n] = J
+    yy = np.zeros(8)
+    yy[:n] = y
+    step = np.full(8, 8)
+    pinv = np.zeros(8)
+    perm = []
+    for k in range(n):
+        v = np.abs(row[:, k])
+        v = np.where(np.isnan(v), -1., v)
+        cand = (np.arange(8) < n) & (step == 8)
+        v = np.where(cand, v, -2.)
+        p = int(np.argmax(v))                 # first maximum: lowest lane
+        perm.append(p)
+        pv = row[p, k]
+        with np.errstate(divide='ignore'):
+            pi = 1. / pv
+        m = row[:, k] * (pi if pv != 0. else 1.)
+        elim = cand.copy()
+        elim[p] = False
+        step[p] = k
+        pinv[p] = pi
+        pr = row[p].copy()
+        py = yy[p]
+        for l in range(8):
+            if elim[l]:
+                row[l, k] = m[l]
+                row[l, k + 1:n] = row[l, k + 1:n] - m[l] * pr[k + 1:n]
+                yy[l] = yy[l] - m[l] * py
+    fact = (row.copy(), pinv.copy(), step.copy(), list(perm))
+    x = sd8_backward(fact, yy, n)
+    return x, fact
+
+
+def sd8_backward(fact, yy, n):
+    row, pinv, step, perm = fact
+    yy = yy.copy()
+    for k in range(n - 1, -1, -1):
+        p = perm[k]
+        xk = yy[p] * pinv[p]
+        for l in range(8):
+            if step[l] < k:
+                yy[l] -= row[l, k] * xk
+        yy[p] = xk
+    return np.array([yy[perm[l]] for l in range(n)])
+
+
+def sd8_resolve(fact, y):
+    """sd8_forward + sd8_backward with stored factors (the chord step)."""
+    row, pinv, step, perm = fact
+    n = len(y)
+    yy = np.zeros(8)
+    yy[:n] = y
+    for k in range(n):
+        yk = yy[perm[k]]
+        for l in range(8):
+            if k < step[l] < 8:
+                yy[l] -= row[l, k] * yk
+    return sd8_backward(fact, yy, n)

@@ -136,3 +136,67 @@ def test_sparse_plan_chain_with_hub(monkeypatch):
         assert info['max_con'] > 16 and info['max_terms'] > 16
     finally:
         os.remove(path)
+
+
+@pytest.mark.parametrize('deck,use_q', [('ring_bsim3.net', True),
+                                        ('ring_bsim3.net', False),
+                                        ('ring_osc_ahkab.net', True),
+                                        ('memristor.net', True)])
+def test_small_dense_tile_programs(deck, use_q):
+    """Dense plans with n <= 8 carry the programs of the register-resident
+    8-lane solver (engine.cuh sd8_*): the flat per-lane term lists rebuild
+    the assembled Jacobian, and the lane-parallel elimination without row
+    moves solves like LAPACK, also for a second right-hand side (chord)."""
+    from tests import plan_emul as E
+    ckt, _, topo, idx = setup(deck)
+    assert topo.n <= 8
+    a0 = 2. / 1e-11 if use_q else 0.
+    x = np.random.default_rng(7).uniform(0., 2.5, topo.n)
+    hp = HostPlan(topo, use_q, True)
+    sd = E.sd8_program(hp)
+    assert sd is not None
+    ptr, prog = sd
+    lens = np.diff(ptr)
+    assert lens.max() - lens.min() <= max(1, lens.max() - lens[-1])  # equal pieces, short tail
+    outs, jacs = oracle_device_buffers(topo, x)
+    out, jac = hp.pack_device(outs, jacs)
+    lu_ref = hp.assemble(jac, a0, use_q)
+    # charge rows of the device Jacobians times a0 (WsSink)
+    scaled = []
+    for g, j in zip(topo.groups, jacs):
+        j = j.copy()
+        j[g['ncs']:] *= (a0 if use_q else 1.)
+        scaled.append(j)
+    _, jac_s = hp.pack_device(outs, scaled)
+    base = hp.a['e_g'] + (a0 * hp.a['e_c'] if use_q else 0.)
+    lu = base + E.sd8_gather(hp, jac_s)
+    assert np.allclose(lu, lu_ref, rtol=1e-13,
+                       atol=1e-15 * np.abs(lu_ref).max())
+    n = topo.n
+    J = hp.matrix(lu)
+    assert np.array_equal(J, lu.reshape(n, n))      # slot e = row * n + col
+    rng = np.random.default_rng(8)
+    y = rng.standard_normal(n)
+    xs, fact = E.sd8_solve(J, y)
+    ref = np.linalg.solve(J, y)
+    assert np.allclose(xs, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max())
+    y2 = rng.standard_normal(n)
+    ref2 = np.linalg.solve(J, y2)
+    assert np.allclose(E.sd8_resolve(fact, y2), ref2, rtol=1e-9,
+                       atol=1e-12 * np.abs(ref2).max())
+    # a singular system goes through (zero pivot: column left unscaled)
+    Js = J.copy()
+    Js[:, 2] = 0.
+    Js[2, :] = 0.
+    with np.errstate(all='ignore'):
+        xz, _ = E.sd8_solve(Js, y)
+    assert not np.all(np.isfinite(xz))
+    hp.close()
+
+
+def test_larger_dense_plan_has_no_tile_program():
+    from tests import plan_emul as E
+    ckt, _, topo, idx = setup('bias_npn.net')
+    hp = HostPlan(topo, False, True)
+    assert topo.n > 8 and E.sd8_program(hp) is None
+    hp.close()
