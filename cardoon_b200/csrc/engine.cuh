@@ -85,6 +85,8 @@ struct cdn_engine_args {
 struct Ws {
     double *x, *dx, *ivec, *sv, *q, *qprev, *dq, *y, *tmp, *xb, *lu, *out, *jac, *hist;
     double* fact;   // small dense plans: factors kept for the chord step (sd8_store)
+    unsigned sd_plan;  // shared-memory address of the CTA's Sd8Plan (0: generic path)
+    unsigned sd_base;  // shared-memory address of this instance's state
     int* piv;       // [n] pivot rows (dense LU); piv[n] = pivot-trouble flag of the static-
                     // pivot sparse LU; piv[n + 1] = head of the history rings
     unsigned* stage;   // block team: shared-memory staging area for compact solve programs
@@ -92,10 +94,7 @@ struct Ws {
 };
 
 // doubles of factor storage of a small dense plan (rows, reciprocal pivots, steps)
-// (rows 0..63, reciprocal pivots 64..71, steps and perm 72..76, then the partial
-// accumulators of sd8_gather)
-#define CDN_SD8_PART 77
-#define CDN_SD8_FACT (CDN_SD8_PART + CDN_SD8_NFIX + 1)
+// (layout: plan.h)
 
 __host__ __device__ inline long ws_doubles(int n, long nlu, long out_size, long jac_size,
                                            long hist_size = 0, long fact_size = 0) {
@@ -117,6 +116,8 @@ __device__ inline Ws ws_carve(double* base, int n, long nlu, long out_size, long
     w.piv = (int*)(w.fact + fact_size);
     w.stage = nullptr;
     w.dprof = nullptr;
+    w.sd_plan = 0u;
+    w.sd_base = 0u;
     return w;
 }
 __device__ inline Ws ws_carve(double* base, const cdn_plan_dev& P) {
@@ -1275,72 +1276,176 @@ struct Sd8 {
     unsigned perm;   // lane holding the pivot row of step k in bits 4k .. 4k + 2
 };
 
-// w.lu[e] = sum of the device-Jacobian contributions of slot e
-__device__ __forceinline__ void sd8_gather(TileTeam<8>& tm, const cdn_plan_dev& P, const Ws& w) {
+// The state and the plan copy of these kernels live in shared memory.  They
+// are addressed with explicit ld/st.shared on 32-bit addresses: the generic
+// pointers of `Ws` / `cdn_plan_dev` lose their address space once the structs
+// are spilled (255 registers), and every access became a generic LD.E/ST.E
+// behind a pointer re-load.
+__device__ __forceinline__ unsigned saddr(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ double lds_f64(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(unsigned a, unsigned v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ double flip_sign(double v, unsigned signbit) {   // signbit: 0 / 0x80000000
+    return __hiloint2double(__double2hiint(v) ^ (int)signbit, __double2loint(v));
+}
+
+// shared-memory addresses of the plan copy and byte offsets of the state
+// vectors inside one instance's state (one per CTA, filled by sd8_plan_init)
+struct Sd8Plan {
+    unsigned e_g, e_c, e_ee, rptr, rpk, sptr, sprog, sfix;
+    unsigned lu, out, fact;          // byte offsets from the instance base (x)
+    int n, nlu, maxlen, rmax, nfix;
+};
+
+__device__ __forceinline__ void sd8_plan_init(Sd8Plan& sp, const cdn_plan_dev& P) {
+    sp.e_g = saddr(P.e_g); sp.e_c = saddr(P.e_c); sp.e_ee = saddr(P.e_gones);
+    sp.rptr = saddr(P.r_con_ptr); sp.rpk = saddr(P.r_con_pk);
+    sp.sptr = saddr(P.sd_ptr); sp.sprog = saddr(P.sd_prog); sp.sfix = saddr(P.sd_fix);
+    sp.lu = 8u * 10u * (unsigned)P.n;
+    sp.out = sp.lu + 8u * (unsigned)P.nlu;
+    sp.fact = sp.out + 8u * (unsigned)(P.dev_out_size + P.dev_jac_size + P.hist_size);
+    sp.n = P.n; sp.nlu = P.nlu; sp.maxlen = P.sd_maxlen; sp.rmax = P.sd_rmax; sp.nfix = P.sd_nfix;
+}
+
+__device__ __forceinline__ Sd8Plan sd8_plan_load(unsigned a) {
+    Sd8Plan sp;
+    unsigned* d = (unsigned*)&sp;
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(Sd8Plan) / 4); ++k) d[k] = lds_u32(a + 4u * k);
+    return sp;
+}
+
+// offsets (doubles) of the state vectors: x 0, dx n, ivec 2n, sv 3n, q 4n, y 7n
+#define SD8_X(base, n, r) ((base) + 8u * (unsigned)(r))
+#define SD8_DX(base, n, r) ((base) + 8u * (unsigned)((n) + (r)))
+#define SD8_IVEC(base, n, r) ((base) + 8u * (unsigned)(2 * (n) + (r)))
+#define SD8_SV(base, n, r) ((base) + 8u * (unsigned)(3 * (n) + (r)))
+#define SD8_Q(base, n, r) ((base) + 8u * (unsigned)(4 * (n) + (r)))
+#define SD8_Y(base, n, r) ((base) + 8u * (unsigned)(7 * (n) + (r)))
+
+// lu[e] = sum of the device-Jacobian contributions of slot e.  Every lane
+// walks `maxlen` terms (padded with terms that add an always-zero location):
+//   term = source (doubles from the instance base) | target << 14 |
+//          store-and-reset << 30 | minus << 31
+__device__ __forceinline__ void sd8_gather(TileTeam<8>& tm, const Sd8Plan& sp, unsigned base) {
     const int l = tm.rank();
-    const int t0 = CDN_LD(P.sd_ptr + l), len = CDN_LD(P.sd_ptr + l + 1) - t0;
+    const int maxlen = sp.maxlen, nfix = sp.nfix;
+    unsigned pa = sp.sprog + 4u * (unsigned)(l * maxlen);
     double acc = 0.0;
-    for (int t = 0; t < P.sd_maxlen; ++t) {
-        if (t < len) {
-            const unsigned pk = CDN_LD(P.sd_prog + t0 + t);
-            const double v = w.jac[pk & 0xfffffu];
-            // +- v: flip the sign bit
-            acc += __hiloint2double(__double2hiint(v) ^ (int)(pk & 0x80000000u), __double2loint(v));
-            if (pk & (1u << 30)) {
-                const int a = (int)((pk >> 20) & 63u);
-                // slot, or partial accumulator of a slot cut between two lanes
-                if (a < P.nlu) w.lu[a] = acc;
-                else w.fact[CDN_SD8_PART + a - P.nlu] = acc;
-                acc = 0.0;
-            }
+    unsigned pk = (maxlen > 0) ? lds_u32(pa) : 0u;
+    for (int t = 0; t < maxlen; ++t) {
+        pa += 4u;
+        const unsigned nx = (t + 1 < maxlen) ? lds_u32(pa) : 0u;    // one trip ahead
+        const double v = lds_f64(base + 8u * (pk & 0x3fffu));
+        acc += flip_sign(v, pk & 0x80000000u);
+        if (pk & (1u << 30)) {
+            sts_f64(base + 8u * ((pk >> 14) & 0x3fffu), acc);
+            acc = 0.0;
         }
+        pk = nx;
     }
     tm.sync();
-    if (P.sd_nfix) {
+    if (nfix) {
+        // partial accumulators of slots cut between two lanes
         if (l == 0)
-            for (int j = 0; j < P.sd_nfix; ++j) w.lu[CDN_LD(P.sd_fix + j)] += w.fact[CDN_SD8_PART + j];
+            for (int j = 0; j < nfix; ++j) {
+                const unsigned tgt = base + sp.lu + 8u * lds_u32(sp.sfix + 4u * j);
+                const unsigned src = base + sp.fact + 8u * (unsigned)(CDN_SD8_PART + j);
+                sts_f64(tgt, lds_f64(tgt) + lds_f64(src));
+            }
         tm.sync();
     }
 }
 
-// Rows of J and the residual: S.row = G' row + device part, w.ivec = i(x),
+// Rows of J and the residual: S.row = G' row + device part, ivec = i(x),
 // S.y = lambda sv - i(x).  Returns whether this lane's row and rhs are finite.
-__device__ __forceinline__ bool sd8_rows(TileTeam<8>& tm, const cdn_plan_dev& P, const Ws& w,
+__device__ __forceinline__ bool sd8_rows(TileTeam<8>& tm, const Sd8Plan& sp, unsigned base,
                                          const cdn_opts& o, Sd8& S, bool want_jac) {
-    const int n = P.n, l = tm.rank();
+    const int n = sp.n, l = tm.rank();
     const int r = l < n ? l : n - 1;              // spare lanes shadow the last row
     const double a0 = o.use_q ? o.a0 : 0.0;
+    const unsigned ro = 8u * (unsigned)(r * n);
+    const unsigned eg = sp.e_g + ro, ec = sp.e_c + ro, ee = sp.e_ee + ro, lu = base + sp.lu + ro;
+    const bool use_q = o.use_q != 0, use_g = o.gmin != 0.0;
+    const bool use_ext = o.gmin_ext != 0.0 && r < o.n_ext;
+    // device-output list of this row, first words in flight early
+    const unsigned c0 = lds_u32(sp.rptr + 4u * r), c1 = lds_u32(sp.rptr + 4u * r + 4u);
     double lin = 0.0;
     bool fin = true;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         double v = 0.0;
         if (c < n) {
-            const int e = r * n + c;
-            double b = CDN_LD(P.e_g + e);
-            if (o.use_q) b = fma(a0, CDN_LD(P.e_c + e), b);
-            if (o.gmin != 0.0) b = fma(o.gmin, CDN_LD(P.e_gones + e), b);
-            if (o.gmin_ext != 0.0 && c == r && r < o.n_ext) b += o.gmin_ext;   // nodal.py:478-479
-            lin = fma(b, w.x[c], lin);
+            double b = lds_f64(eg + 8u * c);
+            if (use_q) b = fma(a0, lds_f64(ec + 8u * c), b);
+            if (use_g) b = fma(o.gmin, lds_f64(ee + 8u * c), b);
+            if (use_ext && c == r) b += o.gmin_ext;               // nodal.py:478-479
+            lin = fma(b, lds_f64(SD8_X(base, n, c)), lin);
             if (want_jac) {
-                v = w.lu[e] + b;
+                v = lds_f64(lu + 8u * c) + b;
                 fin = fin && isfinite(v);
             }
         }
         S.row[c] = v;
     }
-    // device currents and charges of this row (flat: every lane runs sd_rmax trips)
-    const int c0 = CDN_LD(P.r_con_ptr + r), len = CDN_LD(P.r_con_ptr + r + 1) - c0;
-    double acc = lin;
-    for (int t = 0; t < P.sd_rmax; ++t)
-        if (t < len) {
-            const unsigned pk = CDN_LD(P.r_con_pk + c0 + t);
-            acc = fma(pk_coef(pk, a0), w.out[pk & 0x1fffffffu], acc);
-        }
-    const double y = o.lambda * w.sv[r] - acc;
-    if (l < n) { w.ivec[l] = acc; w.y[l] = y; }
+    // device currents and charges of this row: +-i and a0 * (+-q) on separate
+    // accumulators; every lane runs rmax trips (the list is re-read at its
+    // last entry with a zero weight past the end)
+    const int len = (int)(c1 - c0), rmax = sp.rmax;
+    const unsigned rpk = sp.rpk + 4u * c0, out = base + sp.out;
+    double ai = 0.0, aq = 0.0;
+    for (int t = 0; t < rmax; ++t) {
+        const bool live = t < len;
+        const unsigned pk = lds_u32(rpk + 4u * (unsigned)(live ? t : 0));
+        const double v = lds_f64(out + 8u * (pk & 0x1fffffffu));
+        const double sv = flip_sign(v, (pk << 2) & 0x80000000u);   // bit 29: minus
+        const bool chg = (pk & (1u << 30)) != 0u;
+        if (live && chg) aq += sv;
+        if (live && !chg) ai += sv;
+    }
+    const double acc = (lin + ai) + a0 * aq;
+    const double y = o.lambda * lds_f64(SD8_SV(base, n, r)) - acc;
+    if (l < n) { sts_f64(SD8_IVEC(base, n, l), acc); sts_f64(SD8_Y(base, n, l), y); }
     S.y = y;
     return (l >= n) || (fin && isfinite(y));
+}
+
+// q = C x + Tq q(x) of this lane's row (device outputs must be current)
+__device__ __forceinline__ void sd8_charge(TileTeam<8>& tm, const Sd8Plan& sp, unsigned base) {
+    const int n = sp.n, l = tm.rank();
+    const int r = l < n ? l : n - 1;
+    const unsigned ec = sp.e_c + 8u * (unsigned)(r * n);
+    const unsigned c0 = lds_u32(sp.rptr + 4u * r), c1 = lds_u32(sp.rptr + 4u * r + 4u);
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        if (c < n) acc = fma(lds_f64(ec + 8u * c), lds_f64(SD8_X(base, n, c)), acc);
+    const int len = (int)(c1 - c0), rmax = sp.rmax;
+    const unsigned rpk = sp.rpk + 4u * c0, out = base + sp.out;
+    double aq = 0.0;
+    for (int t = 0; t < rmax; ++t) {
+        const bool live = t < len;
+        const unsigned pk = lds_u32(rpk + 4u * (unsigned)(live ? t : 0));
+        const double v = lds_f64(out + 8u * (pk & 0x1fffffffu));
+        if (live && (pk & (1u << 30))) aq += flip_sign(v, (pk << 2) & 0x80000000u);
+    }
+    if (l < n) sts_f64(SD8_Q(base, n, l), acc + aq);
+    tm.sync();
 }
 
 // Elimination with the right-hand side carried along (forward substitution fused).
@@ -1413,24 +1518,26 @@ __device__ __forceinline__ double sd8_unknown(TileTeam<8>& tm, const Sd8& S) {
     return tm.tile.shfl(S.y, (int)((S.perm >> (4 * l)) & 7u));
 }
 
-__device__ __forceinline__ void sd8_store(TileTeam<8>& tm, const Sd8& S, const Ws& w) {
+__device__ __forceinline__ void sd8_store(TileTeam<8>& tm, const Sd8& S, const Sd8Plan& sp,
+                                          unsigned base) {
     const int l = tm.rank();
+    const unsigned f = base + sp.fact;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) w.fact[l * 8 + c] = S.row[c];
-    w.fact[64 + l] = S.pinv;
-    int* meta = (int*)(w.fact + 72);
-    meta[l] = S.step;
-    if (l == 0) meta[8] = (int)S.perm;
+    for (int c = 0; c < 8; ++c) sts_f64(f + 8u * (unsigned)(l * 8 + c), S.row[c]);
+    sts_f64(f + 8u * (unsigned)(64 + l), S.pinv);
+    sts_u32(f + 8u * 72u + 4u * (unsigned)l, (unsigned)S.step);
+    if (l == 0) sts_u32(f + 8u * 72u + 32u, S.perm);
 }
 
-__device__ __forceinline__ void sd8_load(TileTeam<8>& tm, Sd8& S, const Ws& w) {
+__device__ __forceinline__ void sd8_load(TileTeam<8>& tm, Sd8& S, const Sd8Plan& sp,
+                                         unsigned base) {
     const int l = tm.rank();
+    const unsigned f = base + sp.fact;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) S.row[c] = w.fact[l * 8 + c];
-    S.pinv = w.fact[64 + l];
-    const int* meta = (const int*)(w.fact + 72);
-    S.step = meta[l];
-    S.perm = (unsigned)meta[8];
+    for (int c = 0; c < 8; ++c) S.row[c] = lds_f64(f + 8u * (unsigned)(l * 8 + c));
+    S.pinv = lds_f64(f + 8u * (unsigned)(64 + l));
+    S.step = (int)lds_u32(f + 8u * 72u + 4u * (unsigned)l);
+    S.perm = lds_u32(f + 8u * 72u + 32u);
 }
 
 __device__ __forceinline__ double sd8_max(TileTeam<8>& tm, double v) {
@@ -1440,15 +1547,19 @@ __device__ __forceinline__ double sd8_max(TileTeam<8>& tm, double v) {
 }
 
 // dx = LU \ (sv - iVec) with the stored factors; x += dx (tran.py:181)
-__device__ __forceinline__ void sd8_chord(TileTeam<8>& tm, const cdn_plan_dev& P, const Ws& w) {
-    const int n = P.n, l = tm.rank();
+__device__ __forceinline__ void sd8_chord(TileTeam<8>& tm, const Sd8Plan& sp, unsigned base) {
+    const int n = sp.n, l = tm.rank();
+    const int r = l < n ? l : n - 1;
     Sd8 S;
-    sd8_load(tm, S, w);
-    S.y = (l < n) ? w.sv[l] - w.ivec[l] : 0.0;
+    sd8_load(tm, S, sp, base);
+    S.y = (l < n) ? lds_f64(SD8_SV(base, n, r)) - lds_f64(SD8_IVEC(base, n, r)) : 0.0;
     sd8_forward(tm, S, n);
     sd8_backward(tm, S, n);
     const double d = sd8_unknown(tm, S);
-    if (l < n) { w.dx[l] = d; w.x[l] += d; }
+    if (l < n) {
+        sts_f64(SD8_DX(base, n, l), d);
+        sts_f64(SD8_X(base, n, l), lds_f64(SD8_X(base, n, l)) + d);
+    }
     tm.sync();
 }
 
@@ -1549,6 +1660,7 @@ __device__ __forceinline__ int newton_sd8(TileTeam<8>& tm, const cdn_plan_dev& P
                                           const Ws& w, const cdn_opts& o, bool active,
                                           double* res_out, bool* ok, long long* prof) {
     const int n = P.n, l = tm.rank();
+    const unsigned base = w.sd_base;
     double res = 0.0;
     bool success = false;
     int it = 0;
@@ -1558,9 +1670,10 @@ __device__ __forceinline__ int newton_sd8(TileTeam<8>& tm, const cdn_plan_dev& P
         CDN_PROF_T0;
         eval_devices<MS, true>(tm, P, b, w.x, w, true, o.h, o.use_q ? o.a0 : 1.0);
         CDN_PROF(0);
-        sd8_gather(tm, P, w);
+        const Sd8Plan sp = sd8_plan_load(w.sd_plan);
+        sd8_gather(tm, sp, base);
         Sd8 S;
-        const bool fin = sd8_rows(tm, P, w, o, S, true);
+        const bool fin = sd8_rows(tm, sp, base, o, S, true);
         if (!tm.all(fin)) {             // see newton(): this solve has failed
             ++it;
             res = INFINITY;
@@ -1569,7 +1682,7 @@ __device__ __forceinline__ int newton_sd8(TileTeam<8>& tm, const cdn_plan_dev& P
         }
         CDN_PROF(1);
         sd8_factor(tm, S, n);
-        sd8_store(tm, S, w);
+        sd8_store(tm, S, sp, base);
         CDN_PROF(2);
         sd8_backward(tm, S, n);
         double d = sd8_unknown(tm, S);
@@ -1583,10 +1696,10 @@ __device__ __forceinline__ int newton_sd8(TileTeam<8>& tm, const cdn_plan_dev& P
         if (damp) d *= scale;
         bool conv = true;
         if (l < n) {
-            const double xo = w.x[l], xn = xo + d;
+            const double xo = lds_f64(SD8_X(base, n, l)), xn = xo + d;
             conv = fabs(d) < o.reltol * fmax(fabs(xo), fabs(xn)) + o.abstol;
-            w.x[l] = xn;
-            w.dx[l] = d;
+            sts_f64(SD8_X(base, n, l), xn);
+            sts_f64(SD8_DX(base, n, l), d);
         }
         res = damp ? m * scale : m;
         const bool n1 = tm.all(conv);
@@ -1595,7 +1708,7 @@ __device__ __forceinline__ int newton_sd8(TileTeam<8>& tm, const cdn_plan_dev& P
         if (n1 && o.errfunc) {
             eval_devices<MS, false>(tm, P, b, w.x, w, true, o.h);
             Sd8 R;
-            sd8_rows(tm, P, w, o, R, false);
+            sd8_rows(tm, sp, base, o, R, false);
             const double ef = sd8_max(tm, l < n ? fabs(R.y) : 0.0);
             tm.sync();
             n2 = ef < o.abstol;
@@ -1614,7 +1727,7 @@ template <int MS>
 __device__ __forceinline__ int newton(TileTeam<8>& tm, const cdn_plan_dev& P, int b, const Ws& w,
                                       const cdn_opts& o, bool active, double* res_out, bool* ok,
                                       long long* prof = nullptr, FactState* fs = nullptr) {
-    if (P.sd) return newton_sd8<MS>(tm, P, b, w, o, active, res_out, ok, prof);
+    if (w.sd_plan) return newton_sd8<MS>(tm, P, b, w, o, active, res_out, ok, prof);
     return newton<MS, TileTeam<8> >(tm, P, b, w, o, active, res_out, ok, prof, fs);
 }
 
@@ -1715,9 +1828,18 @@ __device__ __forceinline__ int solve_helpers(Team& tm, const cdn_plan_dev& P, in
 }
 
 // q(x) with a values-only device sweep (nodalSP.py:719-733)
+template <class Team>
+__device__ __forceinline__ bool charge_sd8(Team&, const cdn_plan_dev&, const Ws&) { return false; }
+__device__ __forceinline__ bool charge_sd8(TileTeam<8>& tm, const cdn_plan_dev& P, const Ws& w) {
+    if (!w.sd_plan) return false;
+    sd8_charge(tm, sd8_plan_load(w.sd_plan), w.sd_base);
+    return true;
+}
+
 template <int MS, class Team>
 __device__ __forceinline__ void update_q(Team& tm, const cdn_plan_dev& P, int b, const Ws& w) {
     eval_devices<MS, false>(tm, P, b, w.x, w);
+    if (charge_sd8(tm, P, w)) return;
     charge(tm, P, w);
     tm.sync();
 }
@@ -1766,8 +1888,8 @@ __device__ __forceinline__ void chord(Team& tm, const cdn_plan_dev& P, const Ws&
 }
 // (tile of 8 on a small dense plan: stored row factors; also applies x += dx)
 __device__ __forceinline__ bool chord_sd8(TileTeam<8>& tm, const cdn_plan_dev& P, const Ws& w) {
-    if (!P.sd) return false;
-    sd8_chord(tm, P, w);
+    if (!w.sd_plan) return false;
+    sd8_chord(tm, sd8_plan_load(w.sd_plan), w.sd_base);
     return true;
 }
 template <class Team>
@@ -1975,12 +2097,20 @@ engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
     // instance in every Newton iteration: keep a copy in shared memory (the
     // per-instance device records streaming through L1 evict the global copy).
     __shared__ cdn_plan_dev Ps;
+    __shared__ Sd8Plan sdp;
     const bool shadow = A.plan_smem > 0;
     if (shadow) {
         const long per0 = ws_doubles(A.plan);
         plan_to_smem(A.plan, Ps, (char*)(smem + (long)tiles * per0));
     }
     const cdn_plan_dev& P = shadow ? Ps : A.plan;
+    // small dense plans on 8-lane tiles: register-resident Newton linear algebra
+    // (sd8_*), which addresses the shared-memory plan copy directly
+    const bool use_sd8 = (T == 8) && shadow && P.sd;
+    if (use_sd8) {
+        if (threadIdx.x == 0) sd8_plan_init(sdp, P);
+        __syncthreads();
+    }
     const long per = ws_doubles(P);
     // the loop bounds are CTA-uniform: padding tiles run along inactive
     for (int b0 = blockIdx.x * tiles; b0 < A.B; b0 += gridDim.x * tiles) {
@@ -1990,12 +2120,16 @@ engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
         // routed to the block kernel): with the address space known at compile
         // time the state is accessed with LDS/STS, not generic loads and stores
         double* base = smem + (long)tile_id * per;
-        const Ws w = ws_carve(base, P);
+        Ws w = ws_carve(base, P);
+        if (use_sd8) { w.sd_plan = saddr(&sdp); w.sd_base = saddr(base); }
         if (active) {
             for (int r = tm.rank(); r < P.n; r += T) w.x[r] = A.x[(long)b * P.n + r];
             // (small dense plans accumulate device contributions per slot in
-            // w.lu: slots without any stay zero)
-            if (P.sd) for (int e = tm.rank(); e < P.nlu; e += T) w.lu[e] = 0.0;
+            // w.lu: slots without any stay zero; so does the padding source)
+            if (P.sd) {
+                for (int e = tm.rank(); e < P.nlu; e += T) w.lu[e] = 0.0;
+                if (tm.rank() == 0) w.fact[CDN_SD8_PART + CDN_SD8_NFIX] = 0.0;
+            }
             tm.sync();
         }
         run_instance<MS>(tm, A, P, b, w, active);

@@ -11,8 +11,12 @@
 #define CDN_MAX_GROUPS 16
 // gather / term lists longer than this are summed cooperatively by the team
 #define CDN_HEAVY 256
-// partial accumulators of the small dense tile programs (see cdn_plan_dev::sd)
+// small dense tile programs (see cdn_plan_dev::sd): the factor storage of one
+// instance (rows 0..63, reciprocal pivots 64..71, steps and perm 72..76) is
+// followed by CDN_SD8_NFIX partial accumulators and one always-zero double
 #define CDN_SD8_NFIX 10
+#define CDN_SD8_PART 77
+#define CDN_SD8_FACT (CDN_SD8_PART + CDN_SD8_NFIX + 1)
 
 // one homogeneous group of nonlinear devices (same model, flags, port counts)
 struct cdn_group_dev {
@@ -88,13 +92,16 @@ struct cdn_plan_dev {
                               // that a strided walk gives every lane the same work
     // ---- small dense systems (dense, n <= 8): programs of the 8-lane warp tiles
     // (engine.cuh sd8_*).  The device-Jacobian contributions of all slots, slot
-    // after slot, are cut into eight equally long pieces, one per lane, so that
-    // every lane walks one flat list of the same length:
-    //   term = index into dev_jac | accumulator << 20 | last term of its
-    //          accumulator in this piece << 30 | minus sign << 31
-    // Accumulator a < nlu is slot a itself; a slot that straddles a cut continues
-    // in the next lane on partial accumulator nlu + j, which lane 0 adds to slot
-    // sd_fix[j] afterwards (at most CDN_SD8_NFIX of them).
+    // after slot, are cut into eight equally long pieces, one per lane (lane l:
+    // sd_prog[l * sd_maxlen .. (l + 1) * sd_maxlen), padded), so that every lane
+    // walks one flat list of the same length:
+    //   term = source | target << 14 | store target and reset << 30 | minus << 31
+    // Source and target are positions (in doubles) inside one instance's state
+    // (engine.cuh ws_carve): a device-Jacobian entry, and the slot of w.lu the
+    // running sum belongs to.  A slot that straddles a cut continues in the next
+    // lane on partial accumulator j (in the factor storage), which lane 0 adds
+    // to slot sd_fix[j] afterwards (at most CDN_SD8_NFIX of them); padding terms
+    // add the always-zero double.
     int sd;                   // 1: programs present
     int sd_maxlen;            // longest lane list
     int sd_rmax;              // longest per-row list of device-output contributions

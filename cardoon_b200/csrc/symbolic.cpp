@@ -735,7 +735,14 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
         for (long e = 0; e < nlu; ++e)
             if (P->slot_row[e] * n + P->slot_col[e] != e) sd = false;
     ivec sd_fix;
+    if (c->nhist > 0) sd = false;                    // (delayed ports: general path)
     if (sd) {
+        // positions (doubles) inside one instance's state, engine.cuh ws_carve:
+        // 10 n-vectors, lu, device outputs, device Jacobians, factor storage
+        const long lu_off = 10L * n, jac_off = lu_off + nlu + out_size;
+        const long fact_off = jac_off + jac_size;
+        const long zero_at = fact_off + CDN_SD8_PART + CDN_SD8_NFIX;
+        if (zero_at >= (1L << 14)) sd = false;
         // all terms, slot after slot (longest lists first), cut into 8 pieces
         struct T { int e; int src; bool minus; };
         std::vector<T> all;
@@ -746,26 +753,27 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
         }
         const long total = (long)all.size();
         const long chunk = (total + 7) / 8;
-        for (int l = 0; l < 8; ++l) {
+        sd_maxlen = (int)chunk;
+        for (int l = 0; l < 8 && sd; ++l) {
             const long t0 = std::min(total, l * chunk), t1 = std::min(total, (l + 1) * chunk);
             for (long t = t0; t < t1; ++t) {
                 const int e = all[t].e;
                 // the slot's first term lies in an earlier piece: partial accumulator
                 const bool cont = t0 > 0 && all[t0 - 1].e == e;
-                int acc = e;
+                long tgt = lu_off + e;
                 if (cont) {
                     if (t == t0) sd_fix.push_back(e);
-                    acc = (int)nlu + (int)sd_fix.size() - 1;
+                    tgt = fact_off + CDN_SD8_PART + (long)sd_fix.size() - 1;
                 }
-                unsigned w = (unsigned)all[t].src | ((unsigned)acc << 20);
+                unsigned w = (unsigned)(jac_off + all[t].src) | ((unsigned)tgt << 14);
                 if (all[t].minus) w |= 1u << 31;
                 if (t + 1 == t1 || all[t + 1].e != e) w |= 1u << 30;
                 sd_prog.push_back(w);
             }
+            for (long t = t1 - t0; t < chunk; ++t) sd_prog.push_back((unsigned)zero_at);
             sd_ptr[l + 1] = (int)sd_prog.size();
-            sd_maxlen = std::max(sd_maxlen, sd_ptr[l + 1] - sd_ptr[l]);
         }
-        if ((long)sd_fix.size() > CDN_SD8_NFIX || nlu + (long)sd_fix.size() > 64) {
+        if (!sd || (long)sd_fix.size() > CDN_SD8_NFIX) {
             sd = false; sd_prog.clear(); sd_fix.clear(); sd_maxlen = 0;
             for (int l = 0; l < 9; ++l) sd_ptr[l] = 0;
         }

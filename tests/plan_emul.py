@@ -173,27 +173,33 @@ def sd8_program(hp):
 
 def sd8_gather(hp, jac_scaled):
     """w.lu after sd8_gather: per-slot sums of the device contributions
-    (``jac_scaled``: charge rows already times a0, as WsSink stores them)."""
+    (``jac_scaled``: charge rows already times a0, as WsSink stores them).
+    Emulates the instance state the terms address: 10 n-vectors, lu, device
+    outputs, device Jacobians, factor storage (engine.cuh ws_carve)."""
     ptr, prog = sd8_program(hp)
     fix = nd.plan_array(hp.dll, hp.plan, 'sd_fix')
-    lu = np.zeros(hp.nlu)
-    part = np.zeros(len(fix))
+    n, nlu = hp.n, hp.nlu
+    lu_off = 10 * n
+    jac_off = lu_off + nlu + hp.info['dev_out']
+    fact_off = jac_off + hp.info['dev_jac']
+    PART, NFIX = 77, 10
+    state = np.zeros(fact_off + PART + NFIX + 1)
+    state[jac_off:jac_off + len(jac_scaled)] = jac_scaled
+    maxlen = ptr[1] - ptr[0]
+    assert np.all(np.diff(ptr) == maxlen)
     for lane in range(8):
         acc = 0.
         for t in range(ptr[lane], ptr[lane + 1]):
             pk = int(prog[t])
-            v = jac_scaled[pk & 0xfffff]
+            v = state[pk & 0x3fff]
             acc += -v if pk & 0x80000000 else v
             if pk & (1 << 30):
-                a = (pk >> 20) & 63
-                if a < hp.nlu:
-                    lu[a] = acc
-                else:
-                    part[a - hp.nlu] = acc
+                state[(pk >> 14) & 0x3fff] = acc
                 acc = 0.
-        assert acc == 0.          # every piece ends with a flush
+        assert acc == 0.          # every piece ends with a store (or padding)
+    lu = state[lu_off:lu_off + nlu].copy()
     for j, e in enumerate(fix):
-        lu[e] += part[j]
+        lu[e] += state[fact_off + PART + j]
     return lu
 
 
