@@ -1251,318 +1251,6 @@ __device__ __forceinline__ void lusolve(Team& tm, const cdn_plan_dev& P, const W
 }
 
 
-// ==== small dense systems (dense plan, n <= 8) on an 8-lane warp tile ==================
-// The Newton linear algebra of a batch instance lives in the registers of its
-// tile, one matrix ROW per lane (lane r: row r of [J | y]):
-//   * the device-Jacobian contributions are summed from flat, equally long
-//     per-lane term lists (plan.h sd_prog) into w.lu, one barrier;
-//   * lane r adds the linear part G' = G + a0 C (+ gmin patterns) of its row,
-//     which at the same time gives the linear part of the residual, G' x;
-//   * Gaussian elimination with partial pivoting (LAPACK getrf arithmetic:
-//     largest |a_ik| of the remaining rows, multipliers by the reciprocal of
-//     the pivot, a zero pivot leaves its column unscaled) runs on the registers
-//     with the right-hand side carried along; rows are not moved -- the lane
-//     that holds the pivot row of step k is remembered instead (`perm`);
-//   * back substitution, damping and the convergence test follow in registers;
-//   * multipliers, U rows and reciprocal pivots are stored (w.fact) so that the
-//     chord predictor of the next time step (tran.py:181) re-uses them.
-// Ties between equal pivot candidates go to the lowest lane (LAPACK: lowest
-// current row position); values agree with getrf/getrs to rounding.
-struct Sd8 {
-    double row[8];
-    double y;        // right-hand side entry, then solution of unknown `step`
-    double pinv;     // 1 / pivot of the step at which this lane held the pivot row
-    int step;        // that step = the unknown this lane solves for (8: none yet)
-    unsigned perm;   // lane holding the pivot row of step k in bits 4k .. 4k + 2
-};
-
-// The state and the plan copy of these kernels live in shared memory.  They
-// are addressed with explicit ld/st.shared on 32-bit addresses: the generic
-// pointers of `Ws` / `cdn_plan_dev` lose their address space once the structs
-// are spilled (255 registers), and every access became a generic LD.E/ST.E
-// behind a pointer re-load.
-__device__ __forceinline__ unsigned saddr(const void* p) {
-    return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ double lds_f64(unsigned a) {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts_f64(unsigned a, double v) {
-    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
-}
-__device__ __forceinline__ unsigned lds_u32(unsigned a) {
-    unsigned v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts_u32(unsigned a, unsigned v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ double flip_sign(double v, unsigned signbit) {   // signbit: 0 / 0x80000000
-    return __hiloint2double(__double2hiint(v) ^ (int)signbit, __double2loint(v));
-}
-
-// shared-memory addresses of the plan copy and byte offsets of the state
-// vectors inside one instance's state (one per CTA, filled by sd8_plan_init)
-struct Sd8Plan {
-    unsigned e_g, e_c, e_ee, rptr, rpk, sptr, sprog, sfix;
-    unsigned lu, out, fact;          // byte offsets from the instance base (x)
-    int n, nlu, maxlen, rmax, nfix;
-};
-
-__device__ __forceinline__ void sd8_plan_init(Sd8Plan& sp, const cdn_plan_dev& P) {
-    sp.e_g = saddr(P.e_g); sp.e_c = saddr(P.e_c); sp.e_ee = saddr(P.e_gones);
-    sp.rptr = saddr(P.r_con_ptr); sp.rpk = saddr(P.r_con_pk);
-    sp.sptr = saddr(P.sd_ptr); sp.sprog = saddr(P.sd_prog); sp.sfix = saddr(P.sd_fix);
-    sp.lu = 8u * 10u * (unsigned)P.n;
-    sp.out = sp.lu + 8u * (unsigned)P.nlu;
-    sp.fact = sp.out + 8u * (unsigned)(P.dev_out_size + P.dev_jac_size + P.hist_size);
-    sp.n = P.n; sp.nlu = P.nlu; sp.maxlen = P.sd_maxlen; sp.rmax = P.sd_rmax; sp.nfix = P.sd_nfix;
-}
-
-__device__ __forceinline__ Sd8Plan sd8_plan_load(unsigned a) {
-    Sd8Plan sp;
-    unsigned* d = (unsigned*)&sp;
-#pragma unroll
-    for (int k = 0; k < (int)(sizeof(Sd8Plan) / 4); ++k) d[k] = lds_u32(a + 4u * k);
-    return sp;
-}
-
-// offsets (doubles) of the state vectors: x 0, dx n, ivec 2n, sv 3n, q 4n, y 7n
-#define SD8_X(base, n, r) ((base) + 8u * (unsigned)(r))
-#define SD8_DX(base, n, r) ((base) + 8u * (unsigned)((n) + (r)))
-#define SD8_IVEC(base, n, r) ((base) + 8u * (unsigned)(2 * (n) + (r)))
-#define SD8_SV(base, n, r) ((base) + 8u * (unsigned)(3 * (n) + (r)))
-#define SD8_Q(base, n, r) ((base) + 8u * (unsigned)(4 * (n) + (r)))
-#define SD8_Y(base, n, r) ((base) + 8u * (unsigned)(7 * (n) + (r)))
-
-// lu[e] = sum of the device-Jacobian contributions of slot e.  Every lane
-// walks `maxlen` terms (padded with terms that add an always-zero location):
-//   term = source (doubles from the instance base) | target << 14 |
-//          store-and-reset << 30 | minus << 31
-__device__ __forceinline__ void sd8_gather(TileTeam<8>& tm, const Sd8Plan& sp, unsigned base) {
-    const int l = tm.rank();
-    const int maxlen = sp.maxlen, nfix = sp.nfix;
-    unsigned pa = sp.sprog + 4u * (unsigned)(l * maxlen);
-    double acc = 0.0;
-    unsigned pk = (maxlen > 0) ? lds_u32(pa) : 0u;
-    for (int t = 0; t < maxlen; ++t) {
-        pa += 4u;
-        const unsigned nx = (t + 1 < maxlen) ? lds_u32(pa) : 0u;    // one trip ahead
-        const double v = lds_f64(base + 8u * (pk & 0x3fffu));
-        acc += flip_sign(v, pk & 0x80000000u);
-        if (pk & (1u << 30)) {
-            sts_f64(base + 8u * ((pk >> 14) & 0x3fffu), acc);
-            acc = 0.0;
-        }
-        pk = nx;
-    }
-    tm.sync();
-    if (nfix) {
-        // partial accumulators of slots cut between two lanes
-        if (l == 0)
-            for (int j = 0; j < nfix; ++j) {
-                const unsigned tgt = base + sp.lu + 8u * lds_u32(sp.sfix + 4u * j);
-                const unsigned src = base + sp.fact + 8u * (unsigned)(CDN_SD8_PART + j);
-                sts_f64(tgt, lds_f64(tgt) + lds_f64(src));
-            }
-        tm.sync();
-    }
-}
-
-// Rows of J and the residual: S.row = G' row + device part, ivec = i(x),
-// S.y = lambda sv - i(x).  Returns whether this lane's row and rhs are finite.
-__device__ __forceinline__ bool sd8_rows(TileTeam<8>& tm, const Sd8Plan& sp, unsigned base,
-                                         const cdn_opts& o, Sd8& S, bool want_jac) {
-    const int n = sp.n, l = tm.rank();
-    const int r = l < n ? l : n - 1;              // spare lanes shadow the last row
-    const double a0 = o.use_q ? o.a0 : 0.0;
-    const unsigned ro = 8u * (unsigned)(r * n);
-    const unsigned eg = sp.e_g + ro, ec = sp.e_c + ro, ee = sp.e_ee + ro, lu = base + sp.lu + ro;
-    const bool use_q = o.use_q != 0, use_g = o.gmin != 0.0;
-    const bool use_ext = o.gmin_ext != 0.0 && r < o.n_ext;
-    // device-output list of this row, first words in flight early
-    const unsigned c0 = lds_u32(sp.rptr + 4u * r), c1 = lds_u32(sp.rptr + 4u * r + 4u);
-    double lin = 0.0;
-    bool fin = true;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        double v = 0.0;
-        if (c < n) {
-            double b = lds_f64(eg + 8u * c);
-            if (use_q) b = fma(a0, lds_f64(ec + 8u * c), b);
-            if (use_g) b = fma(o.gmin, lds_f64(ee + 8u * c), b);
-            if (use_ext && c == r) b += o.gmin_ext;               // nodal.py:478-479
-            lin = fma(b, lds_f64(SD8_X(base, n, c)), lin);
-            if (want_jac) {
-                v = lds_f64(lu + 8u * c) + b;
-                fin = fin && isfinite(v);
-            }
-        }
-        S.row[c] = v;
-    }
-    // device currents and charges of this row: +-i and a0 * (+-q) on separate
-    // accumulators; every lane runs rmax trips (the list is re-read at its
-    // last entry with a zero weight past the end)
-    const int len = (int)(c1 - c0), rmax = sp.rmax;
-    const unsigned rpk = sp.rpk + 4u * c0, out = base + sp.out;
-    double ai = 0.0, aq = 0.0;
-    for (int t = 0; t < rmax; ++t) {
-        const bool live = t < len;
-        const unsigned pk = lds_u32(rpk + 4u * (unsigned)(live ? t : 0));
-        const double v = lds_f64(out + 8u * (pk & 0x1fffffffu));
-        const double sv = flip_sign(v, (pk << 2) & 0x80000000u);   // bit 29: minus
-        const bool chg = (pk & (1u << 30)) != 0u;
-        if (live && chg) aq += sv;
-        if (live && !chg) ai += sv;
-    }
-    const double acc = (lin + ai) + a0 * aq;
-    const double y = o.lambda * lds_f64(SD8_SV(base, n, r)) - acc;
-    if (l < n) { sts_f64(SD8_IVEC(base, n, l), acc); sts_f64(SD8_Y(base, n, l), y); }
-    S.y = y;
-    return (l >= n) || (fin && isfinite(y));
-}
-
-// q = C x + Tq q(x) of this lane's row (device outputs must be current)
-__device__ __forceinline__ void sd8_charge(TileTeam<8>& tm, const Sd8Plan& sp, unsigned base) {
-    const int n = sp.n, l = tm.rank();
-    const int r = l < n ? l : n - 1;
-    const unsigned ec = sp.e_c + 8u * (unsigned)(r * n);
-    const unsigned c0 = lds_u32(sp.rptr + 4u * r), c1 = lds_u32(sp.rptr + 4u * r + 4u);
-    double acc = 0.0;
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        if (c < n) acc = fma(lds_f64(ec + 8u * c), lds_f64(SD8_X(base, n, c)), acc);
-    const int len = (int)(c1 - c0), rmax = sp.rmax;
-    const unsigned rpk = sp.rpk + 4u * c0, out = base + sp.out;
-    double aq = 0.0;
-    for (int t = 0; t < rmax; ++t) {
-        const bool live = t < len;
-        const unsigned pk = lds_u32(rpk + 4u * (unsigned)(live ? t : 0));
-        const double v = lds_f64(out + 8u * (pk & 0x1fffffffu));
-        if (live && (pk & (1u << 30))) aq += flip_sign(v, (pk << 2) & 0x80000000u);
-    }
-    if (l < n) sts_f64(SD8_Q(base, n, l), acc + aq);
-    tm.sync();
-}
-
-// Elimination with the right-hand side carried along (forward substitution fused).
-__device__ __forceinline__ void sd8_factor(TileTeam<8>& tm, Sd8& S, int n) {
-    const int l = tm.rank();
-    S.step = 8;
-    S.perm = 0u;
-    S.pinv = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (k < n) {
-            const bool cand = (l < n) && (S.step == 8);
-            double v = fabs(S.row[k]);
-            if (!(v >= 0.0)) v = -1.0;                 // NaN loses against any number
-            if (!cand) v = -2.0;
-            int p = l;
-#pragma unroll
-            for (int off = 4; off > 0; off >>= 1) {
-                const double v2 = tm.tile.shfl_xor(v, off);
-                const int p2 = tm.tile.shfl_xor(p, off);
-                if (v2 > v || (v2 == v && p2 < p)) { v = v2; p = p2; }
-            }
-            S.perm |= (unsigned)p << (4 * k);
-            const double pv = tm.tile.shfl(S.row[k], p);
-            const double pinv = 1.0 / pv;
-            const double m = S.row[k] * ((pv != 0.0) ? pinv : 1.0);   // dgetf2: zero pivot
-            const bool elim = cand && (l != p);
-            if (l == p) { S.step = k; S.pinv = pinv; }
-            if (elim) S.row[k] = m;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j > k && j < n) {
-                    const double pr = tm.tile.shfl(S.row[j], p);
-                    if (elim) S.row[j] = fma(-m, pr, S.row[j]);
-                }
-            const double py = tm.tile.shfl(S.y, p);
-            if (elim) S.y = fma(-m, py, S.y);
-        }
-    }
-}
-
-// forward substitution of a fresh right-hand side with stored factors
-__device__ __forceinline__ void sd8_forward(TileTeam<8>& tm, Sd8& S, int n) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (k < n) {
-            const double yk = tm.tile.shfl(S.y, (int)((S.perm >> (4 * k)) & 7u));
-            if (S.step > k && S.step < 8) S.y = fma(-S.row[k], yk, S.y);
-        }
-}
-
-// U x = y; afterwards the lane that held the pivot row of step k holds x_k
-__device__ __forceinline__ void sd8_backward(TileTeam<8>& tm, Sd8& S, int n) {
-    const int l = tm.rank();
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-        const int k = 7 - kk;
-        if (k < n) {
-            const int p = (int)((S.perm >> (4 * k)) & 7u);
-            const double xk = tm.tile.shfl(S.y * S.pinv, p);
-            if (S.step < k) S.y = fma(-S.row[k], xk, S.y);
-            if (l == p) S.y = xk;
-        }
-    }
-}
-
-// x_l for lane l (unknown l sits in the lane that held the pivot row of step l)
-__device__ __forceinline__ double sd8_unknown(TileTeam<8>& tm, const Sd8& S) {
-    const int l = tm.rank();
-    return tm.tile.shfl(S.y, (int)((S.perm >> (4 * l)) & 7u));
-}
-
-__device__ __forceinline__ void sd8_store(TileTeam<8>& tm, const Sd8& S, const Sd8Plan& sp,
-                                          unsigned base) {
-    const int l = tm.rank();
-    const unsigned f = base + sp.fact;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) sts_f64(f + 8u * (unsigned)(l * 8 + c), S.row[c]);
-    sts_f64(f + 8u * (unsigned)(64 + l), S.pinv);
-    sts_u32(f + 8u * 72u + 4u * (unsigned)l, (unsigned)S.step);
-    if (l == 0) sts_u32(f + 8u * 72u + 32u, S.perm);
-}
-
-__device__ __forceinline__ void sd8_load(TileTeam<8>& tm, Sd8& S, const Sd8Plan& sp,
-                                         unsigned base) {
-    const int l = tm.rank();
-    const unsigned f = base + sp.fact;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) S.row[c] = lds_f64(f + 8u * (unsigned)(l * 8 + c));
-    S.pinv = lds_f64(f + 8u * (unsigned)(64 + l));
-    S.step = (int)lds_u32(f + 8u * 72u + 4u * (unsigned)l);
-    S.perm = lds_u32(f + 8u * 72u + 32u);
-}
-
-__device__ __forceinline__ double sd8_max(TileTeam<8>& tm, double v) {
-#pragma unroll
-    for (int off = 4; off > 0; off >>= 1) v = fmax(v, tm.tile.shfl_xor(v, off));
-    return v;
-}
-
-// dx = LU \ (sv - iVec) with the stored factors; x += dx (tran.py:181)
-__device__ __forceinline__ void sd8_chord(TileTeam<8>& tm, const Sd8Plan& sp, unsigned base) {
-    const int n = sp.n, l = tm.rank();
-    const int r = l < n ? l : n - 1;
-    Sd8 S;
-    sd8_load(tm, S, sp, base);
-    S.y = (l < n) ? lds_f64(SD8_SV(base, n, r)) - lds_f64(SD8_IVEC(base, n, r)) : 0.0;
-    sd8_forward(tm, S, n);
-    sd8_backward(tm, S, n);
-    const double d = sd8_unknown(tm, S);
-    if (l < n) {
-        sts_f64(SD8_DX(base, n, l), d);
-        sts_f64(SD8_X(base, n, l), lds_f64(SD8_X(base, n, l)) + d);
-    }
-    tm.sync();
-}
-
 // ---- damped Newton (fsolve.py:59-128) -------------------------------------------------
 // Returns the iteration count; *ok tells whether the tolerances were met.
 // On return w.ivec holds the residual evaluated at the LAST-BUT-ONE iterate and
@@ -1653,83 +1341,6 @@ __device__ __forceinline__ int newton(Team& tm, const cdn_plan_dev& P, int b, co
     return it;
 }
 
-
-// The same iteration for small dense plans on 8-lane tiles (sd8_* above).
-template <int MS>
-__device__ __forceinline__ int newton_sd8(TileTeam<8>& tm, const cdn_plan_dev& P, int b,
-                                          const Ws& w, const cdn_opts& o, bool active,
-                                          double* res_out, bool* ok, long long* prof) {
-    const int n = P.n, l = tm.rank();
-    const unsigned base = w.sd_base;
-    double res = 0.0;
-    bool success = false;
-    int it = 0;
-    bool run = active;
-    while (tm.cta_any(run && it < o.maxiter)) {
-        if (!(run && it < o.maxiter)) continue;
-        CDN_PROF_T0;
-        eval_devices<MS, true>(tm, P, b, w.x, w, true, o.h, o.use_q ? o.a0 : 1.0);
-        CDN_PROF(0);
-        const Sd8Plan sp = sd8_plan_load(w.sd_plan);
-        sd8_gather(tm, sp, base);
-        Sd8 S;
-        const bool fin = sd8_rows(tm, sp, base, o, S, true);
-        if (!tm.all(fin)) {             // see newton(): this solve has failed
-            ++it;
-            res = INFINITY;
-            run = false;
-            continue;
-        }
-        CDN_PROF(1);
-        sd8_factor(tm, S, n);
-        sd8_store(tm, S, sp, base);
-        CDN_PROF(2);
-        sd8_backward(tm, S, n);
-        double d = sd8_unknown(tm, S);
-        if (!isfinite(d))               // condition_array (nodal.py:385-402)
-            d = isnan(d) ? 10.0 * o.abstol : (d > 0.0 ? 0.1 : -0.1) * o.maxdelta;
-        if (l >= n) d = 0.0;
-        CDN_PROF(3);
-        const double m = sd8_max(tm, fabs(d));
-        const bool damp = m > o.maxdelta;
-        const double scale = damp ? o.maxdelta / m : 1.0;
-        if (damp) d *= scale;
-        bool conv = true;
-        if (l < n) {
-            const double xo = lds_f64(SD8_X(base, n, l)), xn = xo + d;
-            conv = fabs(d) < o.reltol * fmax(fabs(xo), fabs(xn)) + o.abstol;
-            sts_f64(SD8_X(base, n, l), xn);
-            sts_f64(SD8_DX(base, n, l), d);
-        }
-        res = damp ? m * scale : m;
-        const bool n1 = tm.all(conv);
-        tm.sync();
-        bool n2 = true;
-        if (n1 && o.errfunc) {
-            eval_devices<MS, false>(tm, P, b, w.x, w, true, o.h);
-            Sd8 R;
-            sd8_rows(tm, sp, base, o, R, false);
-            const double ef = sd8_max(tm, l < n ? fabs(R.y) : 0.0);
-            tm.sync();
-            n2 = ef < o.abstol;
-            res = fmax(ef, res);
-        }
-        ++it;
-        if (n1 && n2) { success = true; run = false; }
-        CDN_PROF(4);
-    }
-    *res_out = res;
-    *ok = success;
-    return it;
-}
-
-template <int MS>
-__device__ __forceinline__ int newton(TileTeam<8>& tm, const cdn_plan_dev& P, int b, const Ws& w,
-                                      const cdn_opts& o, bool active, double* res_out, bool* ok,
-                                      long long* prof = nullptr, FactState* fs = nullptr) {
-    if (w.sd_plan) return newton_sd8<MS>(tm, P, b, w, o, active, res_out, ok, prof);
-    return newton<MS, TileTeam<8> >(tm, P, b, w, o, active, res_out, ok, prof, fs);
-}
 
 // Continuation on lambda with bisection and backtracking (nodal.py:545-604):
 // mode 0 = gmin stepping on the nonlinear ports (gmin = 1e-3/lambda - 1e-3,
@@ -1828,18 +1439,9 @@ __device__ __forceinline__ int solve_helpers(Team& tm, const cdn_plan_dev& P, in
 }
 
 // q(x) with a values-only device sweep (nodalSP.py:719-733)
-template <class Team>
-__device__ __forceinline__ bool charge_sd8(Team&, const cdn_plan_dev&, const Ws&) { return false; }
-__device__ __forceinline__ bool charge_sd8(TileTeam<8>& tm, const cdn_plan_dev& P, const Ws& w) {
-    if (!w.sd_plan) return false;
-    sd8_charge(tm, sd8_plan_load(w.sd_plan), w.sd_base);
-    return true;
-}
-
 template <int MS, class Team>
 __device__ __forceinline__ void update_q(Team& tm, const cdn_plan_dev& P, int b, const Ws& w) {
     eval_devices<MS, false>(tm, P, b, w.x, w);
-    if (charge_sd8(tm, P, w)) return;
     charge(tm, P, w);
     tm.sync();
 }
@@ -1886,14 +1488,7 @@ __device__ __forceinline__ void chord(Team& tm, const cdn_plan_dev& P, const Ws&
     tm.sync();
     lusolve(tm, P, w, o, false);
 }
-// (tile of 8 on a small dense plan: stored row factors; also applies x += dx)
-__device__ __forceinline__ bool chord_sd8(TileTeam<8>& tm, const cdn_plan_dev& P, const Ws& w) {
-    if (!w.sd_plan) return false;
-    sd8_chord(tm, sd8_plan_load(w.sd_plan), w.sd_base);
-    return true;
-}
-template <class Team>
-__device__ __forceinline__ bool chord_sd8(Team&, const cdn_plan_dev&, const Ws&) { return false; }
+
 
 // ---- one circuit instance, one operation ------------------------------------------------
 // `active` is false for the padding tiles of a ragged batch: they only take
@@ -1942,7 +1537,7 @@ __device__ __forceinline__ void run_instance(Team& tm, const cdn_engine_args& A,
                 make_rhs(tm, P, w, o, A.src_dc, A.nsrc, A.src_rows,
                          A.src_val + (long)i * A.nsrc);
                 CDN_PROF(5);
-                if (i > 1 && !chord_sd8(tm, P, w)) {   // chord predictor (tran.py:181)
+                if (i > 1) {                     // chord predictor (tran.py:181)
                     chord(tm, P, w, o);
                     for (int r = tm.rank(); r < n; r += tm.size()) w.x[r] += w.dx[r];
                     tm.sync();
@@ -2083,6 +1678,20 @@ __device__ __forceinline__ void plan_to_smem(const cdn_plan_dev& G, cdn_plan_dev
     __syncthreads();
 }
 
+#include "engine_sd8.cuh"
+
+template <int MS, int T>
+__device__ __forceinline__ void run_tile(TileTeam<T>& tm, const cdn_engine_args& A,
+                                         const cdn_plan_dev& P, int b, const Ws& w, bool active) {
+    run_instance<MS>(tm, A, P, b, w, active);
+}
+template <int MS>
+__device__ __forceinline__ void run_tile(TileTeam<8>& tm, const cdn_engine_args& A,
+                                         const cdn_plan_dev& P, int b, const Ws& w, bool active) {
+    if (w.sd_plan) sd8_run<MS>(tm, A, P, b, w, active);
+    else run_instance<MS>(tm, A, P, b, w, active);
+}
+
 // ---- kernels --------------------------------------------------------------------------------
 // Batches of small circuits: T lanes per instance; the state lives in shared
 // memory unless the caller wants it kept (A.ws != NULL).
@@ -2132,7 +1741,7 @@ engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
             }
             tm.sync();
         }
-        run_instance<MS>(tm, A, P, b, w, active);
+        run_tile<MS>(tm, A, P, b, w, active);
         if (active) {
             tm.sync();
             for (int r = tm.rank(); r < P.n; r += T) A.x[(long)b * P.n + r] = w.x[r];
