@@ -40,6 +40,11 @@ struct Sd8 {
 };
 
 #define SD8_FULL 0xffffffffu
+// experiment: evaluate q(x) of the accept step with the Jacobian variant of the
+// device code (one code path in the hot loop: instruction-cache footprint)
+#ifndef SD8_ACCEPT_JAC
+#define SD8_ACCEPT_JAC true
+#endif
 __device__ __forceinline__ double sd8_shfl(double v, int src) { return __shfl_sync(SD8_FULL, v, src, 8); }
 __device__ __forceinline__ int sd8_shfl(int v, int src) { return __shfl_sync(SD8_FULL, v, src, 8); }
 __device__ __forceinline__ double sd8_shfl_xor(double v, int off) {
@@ -54,6 +59,22 @@ __device__ __forceinline__ bool sd8_all(bool p) {
     return ((bal >> (threadIdx.x & 24u)) & 0xffu) == 0xffu;
 }
 __device__ __forceinline__ bool sd8_warp_any(bool p) { return __any_sync(SD8_FULL, p) != 0; }
+// Loop control: the warps of a CTA iterate in lockstep (every thread of the CTA
+// passes the same sequence of sd8_any calls), so that they walk the ~110 KB of
+// hot code together and share instruction fetches.  Measured on B200, 4096
+// ring_bsim3 instances: 27.9 ms in lockstep, 49.8 ms with independent warps
+// (SD8_LOCKSTEP 0), although a warp then only waits for the slowest of its own
+// four instances instead of the slowest of the CTA's 28.
+#ifndef SD8_LOCKSTEP
+#define SD8_LOCKSTEP 1
+#endif
+__device__ __forceinline__ bool sd8_any(TileTeam<8>& tm, bool p) {
+#if SD8_LOCKSTEP
+    return tm.cta_any(p);
+#else
+    return sd8_warp_any(p);
+#endif
+}
 
 // The state and the plan copy of these kernels live in shared memory.  They
 // are addressed with explicit ld/st.shared on 32-bit addresses: the generic
@@ -243,19 +264,24 @@ __device__ __forceinline__ void sd8_factor(Sd8& S, int n) {
     for (int k = 0; k < 8; ++k) {
         if (k < n) {
             const bool cand = (l < n) && (S.step == 8);
+            // argmax over the tile in one 64-bit key per lane: |a_ik| with its
+            // three lowest mantissa bits replaced by 7 - lane, so that the
+            // larger key is the larger magnitude and, among magnitudes equal to
+            // 2^-49 relative, the lower lane (keys of non-negative doubles order
+            // like the doubles themselves); NaN loses against any number,
+            // lanes without a candidate row lose against everything
             double v = fabs(S.row[k]);
-            if (!(v >= 0.0)) v = -1.0;                 // NaN loses against any number
+            if (!(v >= 0.0)) v = -1.0;
             if (!cand) v = -2.0;
-            int p = l;
+            v = __hiloint2double(__double2hiint(v), (__double2loint(v) & ~7) | (7 - l));
 #pragma unroll
-            for (int off = 4; off > 0; off >>= 1) {
-                const double v2 = sd8_shfl_xor(v, off);
-                const int p2 = sd8_shfl_xor(p, off);
-                if (v2 > v || (v2 == v && p2 < p)) { v = v2; p = p2; }
-            }
+            for (int off = 4; off > 0; off >>= 1) v = fmax(v, sd8_shfl_xor(v, off));
+            const int p = 7 - (__double2loint(v) & 7);
             S.perm |= (unsigned)p << (4 * k);
             const double pv = sd8_shfl(S.row[k], p);
-            const double pinv = 1.0 / pv;
+            // reciprocal of the pivot: MUFU seed + two Newton steps (dual.cuh
+            // cdn_rcp: within an ulp of 1 / pv, inf for a zero pivot, branch-free)
+            const double pinv = cdn_rcp(pv);
             const double m = S.row[k] * ((pv != 0.0) ? pinv : 1.0);   // dgetf2: zero pivot
             const bool elim = cand && (l != p);
             if (l == p) { S.step = k; S.pinv = pinv; }
@@ -356,7 +382,8 @@ __device__ __forceinline__ void sd8_eval(const cdn_plan_dev& P, int b, const Ws&
 }
 
 // ---- damped Newton (fsolve.py:59-128; engine.cuh newton() is the general version) -------
-// Every thread of the CTA calls this the same number of times (TileTeam::cta_any).
+// Every thread of the warp (of the CTA with SD8_LOCKSTEP) calls this the same number of
+// times.
 template <int MS>
 __device__ __forceinline__ int sd8_newton(TileTeam<8>& tm, const cdn_plan_dev& P, int b,
                                           const Ws& w, const cdn_opts& o, bool active,
@@ -367,7 +394,7 @@ __device__ __forceinline__ int sd8_newton(TileTeam<8>& tm, const cdn_plan_dev& P
     bool success = false;
     int it = 0;
     bool run = active;
-    while (tm.cta_any(run && it < o.maxiter)) {
+    while (sd8_any(tm, run && it < o.maxiter)) {
         bool live = run && it < o.maxiter;
         if (!sd8_warp_any(live)) continue;              // warp-uniform from here on
         CDN_PROF_T0;
@@ -458,7 +485,7 @@ __device__ __noinline__ int sd8_homotopy(TileTeam<8>& tm, const cdn_plan_dev& P,
     if (active && l < n) sts_f64(SD8_X(base, n, l), lds_f64(SD8_XB(base, n, l)));
     __syncwarp();
     bool run = active;
-    while (tm.cta_any(run && sp > 0)) {
+    while (sd8_any(tm, run && sp > 0)) {
         const bool go = run && sp > 0;
         if (mode == 0) o.gmin = 1e-3 / lam - 1e-3;
         else if (mode == 1) o.lambda = lam;
@@ -502,7 +529,7 @@ __device__ __forceinline__ int sd8_solve_helpers(TileTeam<8>& tm, const cdn_plan
     if (!(helpers & 2)) it = sd8_newton<MS>(tm, P, b, w, o, active, res_out, ok, prof);
     if (!helpers) return it;
     bool need = active && !*ok;
-    if (!tm.cta_any(need)) return it;
+    if (!sd8_any(tm, need)) return it;
     double res2 = 0.0;
     bool ok2 = false;
     int it2;
@@ -510,14 +537,14 @@ __device__ __forceinline__ int sd8_solve_helpers(TileTeam<8>& tm, const cdn_plan
         it2 = sd8_homotopy<MS>(tm, P, b, w, o, 0, need, &res2, &ok2);
         if (need) { it = it2; *res_out = res2; *ok = ok2; *used = 1; }
         need = need && !ok2;
-        if (!tm.cta_any(need)) return it;
+        if (!sd8_any(tm, need)) return it;
     }
     if (!(helpers & 8)) {
         it2 = sd8_homotopy<MS>(tm, P, b, w, o, 1, need, &res2, &ok2);
         if (need) { it = it2; *res_out = res2; *ok = ok2; *used = 2; }
         need = need && !ok2;
     }
-    if (o.n_ext <= 0 || !tm.cta_any(need)) return it;
+    if (o.n_ext <= 0 || !sd8_any(tm, need)) return it;
     it2 = sd8_homotopy<MS>(tm, P, b, w, o, 2, need, &res2, &ok2);
     if (need) { it = it2; *res_out = res2; *ok = ok2; *used = 3; }
     return it;
@@ -560,12 +587,12 @@ __device__ __forceinline__ void sd8_run(TileTeam<8>& tm, const cdn_engine_args& 
     bool run = active;
     long long* prof = (b == 0) ? A.prof : nullptr;
     for (int i = A.first; i < A.nsamples; ++i) {
-        if (!tm.cta_any(run)) break;
+        if (!sd8_any(tm, run)) break;
         if (sd8_warp_any(run)) {
             CDN_PROF_T0;
             // accept(xOld): q(x) with a values-only sweep (nodalSP.py:719-758),
             // integration.py:36-38 / :83-91, then sv = f_n1() + s (:47-49, :93-97)
-            if (run) sd8_eval<MS, false>(P, b, w, 0.0, 1.0);
+            if (run) sd8_eval<MS, SD8_ACCEPT_JAC>(P, b, w, 0.0, 1.0);
             __syncwarp();
             sd8_charge(sp, base, run);
             if (run && l < n) {
