@@ -641,44 +641,109 @@ def oracle_mc_instance(args):
     return dt, len(r['t']), nfull, int(r['iters'].sum())
 
 
-def cpu_baseline_mc(procs=1, per_proc=1, max_samples=100):
-    """CPU oracle on a bounded sample: `procs` worker processes, each running
-    `per_proc` instances for `max_samples` of the samples; circuits/s is
-    scaled to complete transients."""
+def oracle_mc_instance_safe(args):
+    try:
+        return oracle_mc_instance(args)
+    except Exception as err:                  # reported, never fatal
+        return ('failed', args[0], '{0}: {1}'.format(type(err).__name__, err))
+
+
+def cpu_baseline_mc(procs=1, instances=(0,), max_samples=100):
+    """CPU oracle on a bounded sample: the listed instances (a fixed list,
+    whatever the core count) for the first ``max_samples`` samples, on
+    ``procs`` worker processes; circuits/s is EXTRAPOLATED to complete
+    transients (the time loop costs the same per sample)."""
     import multiprocessing as mp
-    jobs = [(j, max_samples) for j in range(procs * per_proc)]
+    jobs = [(int(j), max_samples) for j in instances]
+    procs = max(1, min(procs, len(jobs)))
     t0 = time.time()
     if procs > 1:
         with mp.get_context('spawn').Pool(procs) as pool:
-            out = pool.map(oracle_mc_instance, jobs)
+            out = pool.map(oracle_mc_instance_safe, jobs)
     else:
-        out = [oracle_mc_instance(j) for j in jobs]
+        out = [oracle_mc_instance_safe(j) for j in jobs]
     wall = time.time() - t0
-    busy = sum(o[0] for o in out)
-    frac = out[0][1] / float(out[0][2])
+    good = [o for o in out if o[0] != 'failed']
+    bad = [o for o in out if o[0] == 'failed']
+    if not good:
+        return dict(value=0., unit='circuits/s', cores=procs, kind='port',
+                    sample='all {0} oracle instances failed: {1}'.format(
+                        len(jobs), bad[0][2]))
+    busy = sum(o[0] for o in good)
+    frac = good[0][1] / float(good[0][2])
     # complete-transient equivalents finished per second by `procs` workers
-    value = len(jobs) * frac / (busy / procs)
+    value = len(good) * frac / (busy / procs)
     return dict(value=value, unit='circuits/s', cores=procs, kind='port',
-                sample='{0} instances x first {1} of {2} samples on {3} '
+                sample='instances {0}..{1} x first {2} of {3} samples on {4} '
                        'worker process(es) (numpy oracle restatement of the '
-                       'reference tran loop; scaled to complete transients; '
-                       'wall {4:.1f} s)'.format(len(jobs), out[0][1],
-                                                out[0][2], procs, wall))
+                       'reference tran loop; EXTRAPOLATED to complete '
+                       'transients; wall {5:.1f} s; {6} failed)'.format(
+                           jobs[0][0], jobs[-1][0], good[0][1], good[0][2],
+                           procs, wall, len(bad)),
+                failed_instances=[[o[1], o[2]] for o in bad])
+
+
+MC_TOTAL = 4096
+
+
+def mc_roofline(lib, ckt, bt, B, nsamples, iters_sum, opit_sum, t_step):
+    elems = ckt.nD_nlinElem
+    xs = np.array([[2.5, 1.2, 0.]]).T
+    fd = np.mean([count_flops(e, xs * e._tf, True)[0] for e in elems])
+    fv = np.mean([count_flops(e, xs * e._tf, False)[0] for e in elems])
+    n = bt.topo.n
+    ndev = len(elems)
+    it_total = iters_sum + opit_sum
+    lu_flop = 2. / 3. * n ** 3 + 2. * n * n
+    # algorithmic work (the accept step needs values only, whatever code
+    # variant computes them)
+    flop = it_total * (ndev * fd + lu_flop) \
+        + B * nsamples * (ndev * fv + 2. * n * n)
+    peak = lib.fp64_peak()
+    ach = flop / t_step / 1e12
+    tr = measured_traffic('mc')
+    return dict(bound='fp64', achieved=ach, peak=peak / 1e12,
+                unit='TFLOP/s', frac=ach / (peak / 1e12),
+                traffic=tr['bytes_per_instance'] * B if tr else None,
+                traffic_source=(tr or {}).get('source'),
+                pipe_fp64_active_pct_ncu=(tr or {}).get(
+                    'pipe_fp64_active_pct'),
+                kernel='engine_tile_kernel<BSIM3, 8> (whole time loop, '
+                       'sd8 path)',
+                peak_source='cdn_fp64_peak (DFMA microbenchmark, this run)',
+                flop_per_eval_jac=fd, flop_per_eval_values=fv,
+                newton_iterations=it_total)
 
 
 def run_mc(args, D):
+    """MC circuits/s.  Default = the configuration BASELINE.json names: 4096
+    instances in total, sharded over the ranks (strong scaling, mc.shard);
+    ``--weak`` gives every rank 4096 instances of its own."""
     torch = D.torch
     from cardoon_b200._lib import get_lib
     lib = get_lib(D.local)
     ckt, an, bt, mc = mc_setup(lib)
     lib.dll.cdn_set_tuning(3, args.tile_tpb)
-    B = args.n or 4096
-    lo = D.rank * B
-    params_h = bt.pack_instances(B, mc.bsim3_ring_variation(), first=lo)
-    pinned = [torch.as_tensor(p).pin_memory() for p in params_h]
-    params_d = [p.to(lib.device) for p in pinned]
+    total = args.n or MC_TOTAL
+    if args.weak:
+        lo, hi = D.rank * total, (D.rank + 1) * total
+        job = total * D.world
+    else:
+        lo, hi = mc.shard(total, D.rank, D.world)
+        job = total
+    B = hi - lo
+    elems = ckt.nD_nlinElem
+    # the Monte-Carlo sample (standard-normal draws of every instance) is the
+    # input data set; records are packed from it on the host
+    z = mc.bsim3_ring_samples(range(lo, hi))
+    over = mc.bsim3_ring_overrides(z, elems)
     rows = bt.save_rows(MC_TERMS)
     nsamples = len(bt.timeVec)
+    shapes = [o.shape for o in bt.pack_batch(over, device_major=True)]
+    pinned = [[torch.empty(sh, dtype=torch.float64).pin_memory()
+               for sh in shapes] for _ in range(2)]
+    bt.pack_batch(over, out=[t.numpy() for t in pinned[0]], device_major=True)
+    params_d = [t.to(lib.device) for t in pinned[0]]
     dc, tr = bt.engines(B)
     state = {}
 
@@ -693,82 +758,123 @@ def run_mc(args, D):
         * args.steps // (args.steps + args.warmup)
     clocks = clk.stop(t0, t1)
     wave, iters, status, opit = state['out']
-    nfail = int((status != 0).sum().item())
+    nfail = int(D.sum_over_ranks((status != 0).sum().item()))
     phases = phase_shares(D, tr, step)
-    total = D.sum_over_ranks(B) * args.steps
-    value = total / (ms * 1e-3)
+    value = job * args.steps / (ms * 1e-3)
+    it_sum = D.sum_over_ranks(float(iters.sum().item()))
+    op_sum = D.sum_over_ranks(float(opit.sum().item()))
+    helper_op = int(D.sum_over_ranks((bt.helper_used[0] != 0).sum().item()))
 
-    # ---- end to end: host records -> device, run, waveforms -> host --------
-    wave_h = torch.empty(wave.shape, dtype=torch.float64).pin_memory()
-    iters_h = torch.empty(iters.shape, dtype=torch.int32).pin_memory()
+    # ---- end to end through the public API --------------------------------
+    # host: raw parameter samples -> BatchTransient.pack_batch (the
+    # process_params arithmetic of every instance) into pinned memory ->
+    # H2D -> operating points + transients -> one gather over the ranks
+    # (NCCL) -> D2H of waveforms and iteration counts.  Double-buffered:
+    # while the GPU runs step k the host packs step k + 1.
+    gshape = (job,) + tuple(wave.shape[1:])
+    wave_h = torch.empty(gshape, dtype=torch.float64).pin_memory()
+    iters_h = torch.empty((job, iters.shape[1]), dtype=torch.int32).pin_memory()
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
-        for d, h in zip(params_d, pinned):
-            d.copy_(h, non_blocking=True)
-        w, it, st, _ = bt.run_device(params_d, rows, B)
-        wave_h.copy_(w, non_blocking=True)
-        iters_h.copy_(it, non_blocking=True)
+    def e2e_run(K):
+        for k in range(K):
+            buf = pinned[k % 2]
+            if k >= 2:
+                copied[k % 2].synchronize()     # its H2D has been consumed
+            bt.pack_batch(over, out=[t.numpy() for t in buf],
+                          device_major=True)
+            for d, h in zip(params_d, buf):
+                d.copy_(h, non_blocking=True)
+            copied[k % 2].record()
+            w, it, st, _ = bt.run_device(params_d, rows, B)
+            w, it, st = mc.gather_results(w, it, st, D.dist)
+            wave_h.copy_(w, non_blocking=True)
+            iters_h.copy_(it, non_blocking=True)
+        torch.cuda.synchronize()
 
-    e2e_steps = max(2, min(args.steps, 5))
-    ms_e, _, _ = timed_steps(D, e2e_step, e2e_steps, 1)
-    e2e = dict(value=D.sum_over_ranks(B) * e2e_steps / (ms_e * 1e-3),
-               unit='circuits/s',
-               h2d_bytes_per_step=int(sum(p.numel() for p in pinned) * 8),
+    e2e_steps = max(3, min(args.steps, 6))
+    e2e_run(2)
+    D.barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
+    e0.record()
+    e2e_run(e2e_steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e = D.max_over_ranks(max(e0.elapsed_time(e1),
+                                (time.time() - tw0) * 1e3))
+    D.barrier()
+    e2e = dict(value=job * e2e_steps / (ms_e * 1e-3), unit='circuits/s',
+               h2d_bytes_per_step=int(sum(t.numel() for t in pinned[0]) * 8),
                d2h_bytes_per_step=int(wave_h.numel() * 8
-                                      + iters_h.numel() * 4))
-    # results of all ranks gathered once (NCCL), outside the timed region
-    allw, alli, alls = mc.gather_results(wave, iters, status, D.dist)
+                                      + iters_h.numel() * 4),
+               steps=e2e_steps,
+               path='raw samples (host) -> BatchTransient.pack_batch -> '
+                    'pinned -> H2D -> run_device -> gather_results (NCCL) '
+                    '-> D2H; host packing of step k+1 overlaps the GPU run '
+                    'of step k; time = max(CUDA events, wall clock)')
+    # one un-overlapped pass: what each stage costs
+    tp = time.time()
+    bt.pack_batch(over, out=[t.numpy() for t in pinned[0]],
+                  device_major=True)
+    e2e['host_pack_ms'] = (time.time() - tp) * 1e3
+
+    weak = None
+    if D.world > 1 and not args.weak:
+        # secondary: every rank runs 4096 instances of its own
+        zw = mc.bsim3_ring_samples(range(D.rank * total,
+                                         (D.rank + 1) * total))
+        pw = [lib.dev(p) for p in bt.pack_batch(
+            mc.bsim3_ring_overrides(zw, elems), device_major=True)]
+
+        def wstep():
+            bt.run_device(pw, rows, total)
+        msw, _, _ = timed_steps(D, wstep, 3, 2)
+        weak = dict(instances_per_gpu=total,
+                    value=total * D.world * 3 / (msw * 1e-3),
+                    unit='circuits/s', ms_per_step=msw / 3)
 
     line = None
     if D.rank == 0:
-        elems = ckt.nD_nlinElem
-        xs = np.array([[2.5, 1.2, 0.]]).T
-        fd = np.mean([count_flops(e, xs * e._tf, True)[0] for e in elems])
-        fv = np.mean([count_flops(e, xs * e._tf, False)[0] for e in elems])
-        n = bt.topo.n
-        ndev = len(elems)
-        it_total = float(iters.sum().item()) + float(opit.sum().item())
-        lu_flop = 2. / 3. * n ** 3 + 2. * n * n
-        flop = it_total * (ndev * fd + lu_flop) \
-            + B * nsamples * (ndev * fv + 2. * n * n)
-        t_step = ms * 1e-3 / args.steps
-        peak = lib.fp64_peak()
-        ach = flop / t_step / 1e12
-        tr = measured_traffic('mc')
-        roof = dict(bound='fp64', achieved=ach, peak=peak / 1e12,
-                    unit='TFLOP/s', frac=ach / (peak / 1e12),
-                    traffic=tr['bytes_per_instance'] * B if tr else None,
-                    traffic_source=(tr or {}).get('source'),
-                    pipe_fp64_active_pct_ncu=(tr or {}).get(
-                        'pipe_fp64_active_pct'),
-                    kernel='engine_tile_kernel<BSIM3, 8> (whole time loop)',
-                    peak_source='cdn_fp64_peak (DFMA microbenchmark, this '
-                                'run)',
-                    flop_per_eval_jac=fd, flop_per_eval_values=fv,
-                    newton_iterations=it_total)
-        cpu = cpu_baseline_mc(procs=1, per_proc=1, max_samples=120)
+        roof = mc_roofline(lib, ckt, bt, job, nsamples, it_sum, op_sum,
+                           ms * 1e-3 / args.steps * (1 if args.weak else 1))
+        if D.world > 1:
+            # per-GPU fraction: the job's flops over N GPUs' peak
+            roof['frac'] /= D.world
+            roof['peak'] *= D.world
+            roof['note'] = 'peak = {0} x one GPU'.format(D.world)
+        cpu = cpu_baseline_mc(procs=1, instances=(0,), max_samples=120)
         line = dict(metric='MC circuits/s (complete ring_bsim3 transients)',
                     value=value, unit='circuits/s', n_gpus=D.world,
                     steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True,
-                    scaling='weak', vs_baseline=None, dtype='f64',
-                    data='synthetic',
-                    config=dict(workload='mc: Monte Carlo of workspace/'
-                                'ring_bsim3.net (N=7, 6 mosbsim3, {0} '
-                                'samples, trapezoidal), {1} instances per '
-                                'GPU with per-instance BSIM3 records; one '
-                                'step = operating points + transients of all '
-                                'instances'.format(nsamples, B),
-                                instances_per_gpu=B, samples=nsamples,
+                    scaling='weak' if args.weak else 'strong',
+                    vs_baseline=None, dtype='f64', data='synthetic',
+                    config=dict(workload='mc: {0}-instance Monte Carlo of '
+                                'workspace/ring_bsim3.net (N=7, 6 mosbsim3, '
+                                '{1} samples, trapezoidal) with per-instance '
+                                'BSIM3 records, {2}; one step = operating '
+                                'points + transients of all instances'
+                                .format(job, nsamples,
+                                        '{0} per GPU'.format(total)
+                                        if args.weak else
+                                        'sharded over the GPUs '
+                                        '(rank r: [r*{0}/G, (r+1)*{0}/G))'
+                                        .format(total)),
+                                instances_total=job,
+                                instances_this_rank=B, samples=nsamples,
                                 failed_instances=nfail,
+                                op_instances_using_helpers=helper_op,
                                 phase_shares_instance0=phases,
-                                avg_newton_iterations_per_sample=float(
-                                    iters.sum().item()) / (B * nsamples),
-                                l2='per-instance records ({0:.1f} MB) are '
-                                   'L2-resident by nature of the workload; '
-                                   'every step re-reads them'.format(
-                                       sum(p.numel() for p in pinned) * 8
-                                       / 1e6)),
+                                avg_newton_iterations_per_sample=it_sum
+                                / (job * nsamples),
+                                weak_scaling=weak,
+                                l2='per-instance records ({0:.1f} MB per '
+                                   'rank) are L2-resident by nature of the '
+                                   'workload; every step re-reads them'
+                                   .format(sum(t.numel() for t in pinned[0])
+                                           * 8 / 1e6)),
                     clocks=clocks, e2e=e2e, gpu_launches=launches,
                     roofline=roof, cpu_baseline=cpu)
     return line
@@ -1066,9 +1172,24 @@ def run_reference(args):
         metric = 'device evals/s (BSIM3v3 mosbsim3, value + Jacobian)'
         wl = 'deveval'
     elif args.workload == 'mc':
-        cpu = cpu_baseline_mc(procs=cores, per_proc=1, max_samples=120)
+        # a fixed instance list (independent of the core count), every step
+        # the same bounded sample; per-instance failures are reported, never
+        # fatal
+        procs = min(cores, 16)
+        steps = []
+        for k in range(max(0, args.warmup) + max(1, args.steps)):
+            c = cpu_baseline_mc(procs=procs, instances=range(16),
+                                max_samples=120)
+            if k >= max(0, args.warmup):
+                steps.append(c)
+        cpu = dict(steps[-1])
+        cpu['value'] = float(np.mean([c['value'] for c in steps]))
+        cpu['sample'] += '; mean of {0} such steps'.format(len(steps))
         metric = 'MC circuits/s (complete ring_bsim3 transients)'
-        wl = 'mc: Monte Carlo of workspace/ring_bsim3.net'
+        wl = ('mc: {0}-instance Monte Carlo of workspace/ring_bsim3.net '
+              '(N=7, 6 mosbsim3, 400 samples, trapezoidal) with '
+              'per-instance BSIM3 records'.format(args.n or MC_TOTAL))
+        common['scaling'] = 'strong'
     elif args.workload == 'chain':
         cpu = cpu_baseline_chain(args.n or 100000, K=300, max_samples=10)
         metric = 'inverter-chain tran timepoints/s'
@@ -1119,7 +1240,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native',
                     choices=['native', 'reference'])
-    ap.add_argument('--workload', default='mc',
+    ap.add_argument('--workload', default=None,
                     choices=['deveval', 'mc', 'soliton', 'chain', 'ac'])
     ap.add_argument('--minblocks', type=int, default=0,
                     help='deveval tuning: CTAs/SM register limit (0 = default)')
@@ -1136,8 +1257,20 @@ def main():
                     help='mc tuning: threads per CTA of the tile kernel '
                          '(128 | 256, 0 = automatic)')
     ap.add_argument('--n', type=int, default=0,
-                    help='instances per GPU (0 = workload default)')
+                    help='problem size (0 = workload default; mc: instances '
+                         'of the whole job)')
+    ap.add_argument('--weak', action='store_true',
+                    help='mc: --n instances per GPU instead of in total')
+    ap.add_argument('--legs', type=int, default=-1,
+                    help='mc on one GPU: also run short deveval and soliton '
+                         'legs (the other two parts of BASELINE.json\'s '
+                         'metric) and report them under config (-1 = when '
+                         'the workload flag is not given)')
     args = ap.parse_args()
+    if args.legs < 0:
+        args.legs = 1 if args.workload is None else 0
+    if args.workload is None:
+        args.workload = 'mc'
     args.warmup = max(args.warmup, 3) if args.impl == 'native' \
         else args.warmup
     if args.impl == 'reference':
@@ -1152,6 +1285,23 @@ def main():
     D.barrier()
     line = dict(deveval=run_deveval, mc=run_mc, soliton=run_soliton, ac=run_ac,
                 chain=run_chain)[args.workload](args, D)
+    if args.workload == 'mc' and args.legs and D.world == 1:
+        # the other two parts of BASELINE.json's metric, short runs
+        import copy
+        keep = ('metric', 'value', 'unit', 'ms_per_step', 'steps', 'warmup',
+                'e2e', 'roofline', 'cpu_baseline', 'gpu_launches', 'clocks')
+        for name, fn, n in (('deveval', run_deveval, 1 << 21),
+                            ('soliton', run_soliton, 0)):
+            a2 = copy.copy(args)
+            a2.workload, a2.n = name, n
+            a2.steps = max(3, min(args.steps, 5))
+            sub = fn(a2, D)
+            leg = {k: sub[k] for k in keep if k in sub}
+            leg['workload'] = sub['config']['workload']
+            if name == 'deveval':
+                leg['gummel_poon'] = sub['config']['gummel_poon']
+            line['config'][name] = leg
+            line['gpu_launches'] += sub.get('gpu_launches', 0)
     if D.rank == 0:
         emit(line)
     D.close()

@@ -48,7 +48,7 @@ class BatchTransient(object):
         self._engines = {}
 
     # ---- host: per-instance device records ------------------------------------
-    def pack_batch(self, overrides):
+    def pack_batch(self, overrides, out=None, device_major=False):
         """Records of B instances in one vectorised pass.
 
         ``overrides``: one dict per nonlinear element (order of
@@ -60,16 +60,27 @@ class BatchTransient(object):
         per thousand instances instead of Python per-element calls.  Raises
         ``NotImplementedError`` when a device class or the variation cannot
         be vectorised (callers fall back to ``pack_instances``).
+
+        ``device_major=True`` returns ``[npar, n_g, B]`` arrays (contiguous
+        per element: the fastest to fill on the host, e.g. straight into
+        pinned memory passed as ``out``); ``run_device`` re-orders them to the
+        kernels' instance-major columns on the GPU.
         """
         ckt, topo = self.ckt, self.topo
         elems = ckt.nD_nlinElem
         B = max(np.size(v) for o in overrides for v in o.values())
         saved = [dict(e.__dict__) for e in elems]
-        out = [None] * len(topo.groups)
+        given = out is not None
+        out = list(out) if given else [None] * len(topo.groups)
         where = {}
         for gi, g in enumerate(topo.groups):
             npar = len(g['elems'][0].cuda_spec()['params'])
-            out[gi] = np.empty((npar, B, g['n']))
+            shape = (npar, g['n'], B) if device_major else (npar, B, g['n'])
+            if not given:
+                out[gi] = np.empty(shape)
+            elif out[gi].shape != shape:
+                raise ValueError('out[{0}]: shape {1}, expected {2}'.format(
+                    gi, out[gi].shape, shape))
             for i, e in enumerate(g['elems']):
                 where[id(e)] = (gi, i)
         try:
@@ -99,13 +110,18 @@ class BatchTransient(object):
                     raise NotImplementedError(
                         '{0}: the variation changes the model structure '
                         '(kernel flags)'.format(e.instanceName))
-                params = np.asarray(params)
-                out[gi][:, :, i] = params if params.ndim == 2 \
-                    else params[:, None]
+                dest = out[gi][:, i, :] if device_major \
+                    else out[gi][:, :, i]
+                if hasattr(params, 'write_into'):      # batch record
+                    params.write_into(dest)
+                else:                                  # nothing varied
+                    dest[...] = np.asarray(params)[:, None]
         finally:
             for e, d in zip(elems, saved):
                 e.__dict__.clear()
                 e.__dict__.update(d)
+        if device_major:
+            return out
         # columns instance-major: b * n_g + i
         return [o.reshape(o.shape[0], -1) for o in out]
 
@@ -190,6 +206,23 @@ class BatchTransient(object):
         ``hinfo[:, 0]`` (helper used) are device tensors."""
         dc, tr = self.engines(B)
         torch = dc.lib.torch
+        if any(p.dim() == 3 if hasattr(p, 'dim') else p.ndim == 3
+               for p in params):
+            # device-major [npar, n_g, B] -> instance-major columns, on the
+            # GPU, into buffers kept for the batch size
+            bufs = self.__dict__.setdefault('_pbuf', {})
+            cols = []
+            for gi, p in enumerate(params):
+                t = p if hasattr(p, 'data_ptr') else dc.lib.dev(p)
+                npar, ng, nb = t.shape
+                key = (gi, npar, ng, nb)
+                if key not in bufs:
+                    bufs[key] = torch.empty((npar, nb * ng),
+                                            dtype=torch.float64,
+                                            device=dc.lib.device)
+                bufs[key].view(npar, nb, ng).copy_(t.permute(0, 2, 1))
+                cols.append(bufs[key])
+            params = cols
         dc.set_params(params)
         if getattr(self, '_x0_dev', None) is None or \
                 self._x0_dev.shape[0] != B:

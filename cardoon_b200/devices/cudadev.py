@@ -103,29 +103,61 @@ def uniform(cond, what):
         'the variation changes the model structure ({0})'.format(what))
 
 
-def stack_record(entries, *tails):
-    """Kernel record from a list of scalar entries (batch mode: some may be
-    arrays [B]) followed by 1-D scalar records: [npar] or [npar, B]."""
-    B = max([np.size(e) for e in entries if np.ndim(e) == 1] + [0])
-    tail = np.concatenate([np.atleast_1d(np.asarray(t, dtype=np.float64))
-                           for t in tails]) if tails else np.zeros(0)
-    if B == 0:
-        return np.concatenate([np.array(entries, dtype=np.float64), tail])
-    out = np.empty((len(entries) + len(tail), B))
-    for k, e in enumerate(entries):
-        out[k] = e
-    out[len(entries):] = tail[:, None]
+class BatchRecord(object):
+    """Kernel record of a batch: a list of rows, each a scalar or an array
+    [B]; materialised once, straight into its destination (``write_into``)."""
+
+    def __init__(self, rows, B):
+        self.rows = rows
+        self.B = B
+        self.ndim = 2
+
+    def __len__(self):
+        return len(self.rows)
+
+    @property
+    def shape(self):
+        return (len(self.rows), self.B)
+
+    def __getitem__(self, key):
+        if not isinstance(key, slice):
+            raise TypeError('BatchRecord supports row slices only')
+        return BatchRecord(self.rows[key], self.B)
+
+    def write_into(self, dest):
+        for k, r in enumerate(self.rows):
+            dest[k] = r
+        return dest
+
+    def __array__(self, dtype=None, copy=None):
+        return self.write_into(np.empty(self.shape))
+
+
+def _rows(tails):
+    out = []
+    for t in tails:
+        out.extend(np.atleast_1d(np.asarray(t, dtype=np.float64)).tolist())
     return out
 
 
+def stack_record(entries, *tails):
+    """Kernel record from a list of scalar entries (batch mode: some may be
+    arrays [B]) followed by 1-D scalar records: an array [npar], or a
+    ``BatchRecord`` [npar, B]."""
+    B = max([np.size(e) for e in entries if np.ndim(e) == 1] + [0])
+    if B == 0:
+        tail = np.concatenate([np.atleast_1d(np.asarray(t, dtype=np.float64))
+                               for t in tails]) if tails else np.zeros(0)
+        return np.concatenate([np.array(entries, dtype=np.float64), tail])
+    return BatchRecord(list(entries) + _rows(tails), B)
+
+
 def append_rows(rec, *tails):
-    """``np.concatenate([rec] + tails)`` for [npar] and [npar, B] records."""
-    tail = np.concatenate([np.atleast_1d(np.asarray(t, dtype=np.float64))
-                           for t in tails])
-    if rec.ndim == 1:
-        return np.concatenate([rec, tail])
-    return np.concatenate(
-        [rec, np.broadcast_to(tail[:, None], (len(tail), rec.shape[1]))])
+    """``np.concatenate([rec] + tails)`` for [npar] records and batches."""
+    if isinstance(rec, BatchRecord):
+        return BatchRecord(rec.rows + _rows(tails), rec.B)
+    return np.concatenate([rec] + [np.atleast_1d(np.asarray(
+        t, dtype=np.float64)) for t in tails])
 
 
 def delete_tape(dev):
