@@ -373,12 +373,30 @@ def run_deveval(args, D):
                                         dtype=torch.float64).pin_memory()))
     npar = G[0]['params'].shape[0]
     pbytes = sum(g['params'].numel() for g in G) * 8
+    # devices of a group share a model card: only the rows that depend on
+    # w and l differ between instances (split once, outside the timed region:
+    # it is part of loading the circuit)
+    for g in G:
+        g['split'] = lib.split_record(g['params'])
+    nvar = float(np.mean([(g['split'][1] >= 0).sum() for g in G]))
+    lib.dll.cdn_set_tuning(6, args.split_minb)
 
-    def step():
+    def step_full():
         for g in G:
             lib.dev_eval(g['model'], g['flags'], g['params'], g['xin'], nout,
                          want_jac=True, out=g['out'], jac=g['jac'])
 
+    def step():
+        for g in G:
+            lib.dev_eval_split(g['model'], g['flags'], g['split'], g['xin'],
+                               nout, out=g['out'], jac=g['jac'])
+
+    if args.full_record:
+        step = step_full
+    # outputs + inputs of one step (~1 GB at 4 M instances) exceed the L2
+    ms_full, _, _ = timed_steps(D, step_full, max(2, args.steps // 2),
+                                args.warmup)
+    ms_full /= max(2, args.steps // 2)
     clk = ClockSampler(D.local)
     clk.start()
     ms, t0, t1 = timed_steps(D, step, args.steps, args.warmup)
@@ -391,8 +409,12 @@ def run_deveval(args, D):
     def e2e_step():
         for g in G:
             g['xin'].copy_(g['xin_h'], non_blocking=True)
-            lib.dev_eval(g['model'], g['flags'], g['params'], g['xin'], nout,
-                         want_jac=True, out=g['out'], jac=g['jac'])
+            if args.full_record:
+                lib.dev_eval(g['model'], g['flags'], g['params'], g['xin'],
+                             nout, want_jac=True, out=g['out'], jac=g['jac'])
+            else:
+                lib.dev_eval_split(g['model'], g['flags'], g['split'],
+                                   g['xin'], nout, out=g['out'], jac=g['jac'])
             g['out_h'].copy_(g['out'], non_blocking=True)
             g['jac_h'].copy_(g['jac'], non_blocking=True)
 
@@ -419,7 +441,9 @@ def run_deveval(args, D):
         nrows = np.mean([npar - NJ * sum(1 for f in ('AD', 'PD', 'ASRC', 'PS')
                                          if not g['flags'] & fb[f])
                          for g in G])
-        bytes_eval = 8. * (nrows + nxin + nout + nout * nxin)
+        bytes_full = 8. * (nrows + nxin + nout + nout * nxin)
+        bytes_eval = bytes_full if args.full_record else \
+            8. * (nvar + nxin + nout + nout * nxin)
         t_step = ms * 1e-3 / args.steps
         ach = n * flop / t_step / 1e12
         tr = measured_traffic('deveval')
@@ -445,8 +469,9 @@ def run_deveval(args, D):
                     traffic=(tr['bytes_per_instance'] * n / len(G)
                              if tr else None),
                     traffic_source=(tr or {}).get('source'),
-                    kernel='bsim3_ring_kernel<128,3,48> (one launch per '
-                           'channel type)', fp64=fp64, hbm=hbm_r)
+                    kernel=('bsim3_ring_kernel<128,3,48>' if args.full_record
+                            else 'bsim3_split_kernel<256,2>')
+                    + ' (one launch per channel type)', fp64=fp64, hbm=hbm_r)
         cpu = cpu_baseline_deveval(inp)
         gp['fp64_frac'] = gp['evals_per_s'] * gp['flop_per_eval'] / peak
         th['fp64_frac'] = th['evals_per_s'] * th['flop_per_eval'] / peak
@@ -457,9 +482,23 @@ def run_deveval(args, D):
                     scaling='weak', vs_baseline=None, dtype='f64',
                     data='synthetic',
                     config=dict(workload='deveval: {0} mosbsim3 instances per '
-                                'GPU (half nch, half pch), per-instance '
-                                'parameter columns ({1} doubles each) in HBM'
-                                .format(n, npar), instances_per_gpu=n,
+                                'GPU (half nch, half pch of inverter_chain_'
+                                'bsim.net, w and l per instance); record of '
+                                '{1} doubles: {2}'.format(
+                                    n, npar,
+                                    'every row per instance in HBM'
+                                    if args.full_record else
+                                    '{0:.0f} rows per instance in HBM, the '
+                                    'rest once per model card'.format(nvar)),
+                                instances_per_gpu=n,
+                                full_record=dict(
+                                    evals_per_s=n / (ms_full * 1e-3),
+                                    bytes_per_eval=bytes_full,
+                                    hbm_frac=n * bytes_full / (ms_full * 1e-3)
+                                    / 1e9 / hbm,
+                                    note='every record row per instance '
+                                         '(bsim3_ring_kernel), the round-1 '
+                                         'configuration'),
                                 gummel_poon=gp, electro_thermal=th,
                                 l2='inputs larger than L2 ({0:.1f} GB of '
                                    'parameters per step)'.format(pbytes
@@ -1249,6 +1288,11 @@ def main():
     ap.add_argument('--ring', type=int, default=1,
                     help='deveval tuning: BSIM3 record through the '
                          'shared-memory ring (0 = on-demand loads)')
+    ap.add_argument('--full-record', action='store_true',
+                    help='deveval: every record row per instance (round-1 '
+                         'configuration) instead of the split record')
+    ap.add_argument('--split-minb', type=int, default=5,
+                    help='deveval tuning: CTAs/SM of the split-record kernel')
     ap.add_argument('--ac-blocks', type=int, default=0,
                     help='ac tuning: CTAs (matrices) in flight, 0 = automatic')
     ap.add_argument('--ac-tpb', type=int, default=0,

@@ -86,6 +86,9 @@ def _declare(dll):
     dll.cdn_model_nparams.argtypes = [C.c_int]
     dll.cdn_dev_eval.argtypes = [_vp, C.c_int, C.c_uint, C.c_long, C.c_int,
                                  _vp, C.c_long, _vp, _vp, _vp, _vp, _vp]
+    dll.cdn_dev_eval_split.argtypes = [_vp, C.c_int, C.c_uint, C.c_long, _vp,
+                                       C.c_int, _vp, _vp, C.c_long, _vp, _vp,
+                                       _vp, _vp]
     dll.cdn_ac_solve.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int,
                                  _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp,
                                  _vp, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp]
@@ -198,6 +201,37 @@ class Lib(object):
             self.stream())
         self.check(rc)
         return out, (jac if want_jac else None)
+
+    def split_record(self, params):
+        """Split packed records [npar, n] (device tensor) of devices that
+        share model cards: returns ``(card[npar], vrow[npar] int16 host,
+        inst[nvar, n])`` -- the rows all instances agree on once, the others
+        per instance -- for ``dev_eval_split``."""
+        torch = self.torch
+        uniform = params.max(dim=1).values == params.min(dim=1).values
+        u = uniform.cpu().numpy()
+        vrow = np.full(params.shape[0], -1, dtype=np.int16)
+        vrow[~u] = np.arange(int((~u).sum()), dtype=np.int16)
+        card = params[:, 0].contiguous()
+        inst = params[~uniform].contiguous() if (~u).any() else None
+        return card, vrow, inst
+
+    def dev_eval_split(self, model, flags, split, xin, nout, out=None,
+                       jac=None):
+        """Value + Jacobian from a split record (``split_record``)."""
+        card, vrow, inst = split
+        nxin, n = xin.shape
+        if out is None:
+            out = self.empty((nout, n))
+        if jac is None:
+            jac = self.empty((nout * nxin, n))
+        rc = self.dll.cdn_dev_eval_split(
+            self.ctx, int(model), int(flags), int(n), self.ptr(card),
+            int(card.shape[0]), vrow.ctypes.data_as(_vp), self.ptr(inst),
+            int(inst.stride(0)) if inst is not None else 0, self.ptr(xin),
+            self.ptr(out), self.ptr(jac), self.stream())
+        self.check(rc)
+        return out, jac
 
     def dev_eval_host(self, model, flags, params, xin, nout, want_jac=True):
         """numpy in / numpy out convenience (plugin batch-of-one path)."""

@@ -183,6 +183,136 @@ static void launch_ring(long n, unsigned flags, const double* params, long ldp,
         n, flags, params, ldp, pidx, xin, out, jac);
 }
 
+// ---- split records: model-card rows shared, instance rows per device ----------------
+// Devices that share a `.model` card differ in a few record rows only (BSIM3:
+// the ~25 rows that depend on w and l).  The caller splits the record once
+// (cdn_dev_eval_split): `card[k]` holds row k of the rows all instances agree
+// on, `inst[vrow[k] * ld + i]` the others.  The map row -> instance row travels
+// in the kernel parameters (constant bank): at every access the row number is
+// a literal, so the choice is one uniform-datapath test and both loads are
+// predicated; card rows are warp-wide broadcasts served by L1.  HBM traffic per
+// evaluation falls from ~1.1 KB to ~0.4 KB and the kernel is bound by the FP64
+// pipe instead.
+struct cdn_rowmap {
+    short vrow[NP_BSIM3 + 1];      // -1: card row; else row of `inst`
+};
+
+// Accessor of the split kernel: both kinds of rows are read from shared
+// memory -- the card rows as warp-wide broadcasts, the instance rows from the
+// thread's own column, staged by one burst of cp.async at kernel start -- so
+// that no global-memory latency sits on the model's dependent chain.
+template <int TPB>
+struct PVSplit {
+    const double* smc;             // card rows [nrows] (shared)
+    const double* smi;             // this thread's column: instance row v at smi[v * TPB]
+    const cdn_rowmap* map;         // kernel parameter
+    int off;
+    __device__ __forceinline__ double operator[](int k) const {
+        const int v = map->vrow[off + k];
+        return (v >= 0) ? smi[v * TPB] : smc[off + k];
+    }
+    __device__ __forceinline__ PVSplit sub(int o) const { PVSplit r = *this; r.off = off + o; return r; }
+    __device__ __forceinline__ void mark(int) {}
+};
+
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+bsim3_split_kernel(long n, unsigned flags, const double* __restrict__ card,
+                   const double* __restrict__ inst, long ld, int nvar,
+                   const __grid_constant__ cdn_rowmap map,
+                   const double* __restrict__ xin, double* __restrict__ out,
+                   double* __restrict__ jac) {
+    extern __shared__ double sm[];                    // card[NP_BSIM3 + 1] | inst[nvar][TPB]
+    long i = (long)blockIdx.x * TPB + threadIdx.x;
+    const bool live = i < n;
+    if (!live) i = n - 1;                             // (keeps the barrier; stores nothing)
+    double* smi = sm + NP_BSIM3 + 1 + threadIdx.x;
+    for (int v = 0; v < nvar; ++v) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(smi + v * TPB);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst),
+                     "l"(inst + (long)v * ld + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int k = threadIdx.x; k < NP_BSIM3; k += TPB) sm[k] = __ldg(card + k);
+    Dual<3> v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = make_var<3>(xin[(long)c * n + i], c);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    PVSplit<TPB> p;
+    p.smc = sm; p.smi = smi; p.map = &map; p.off = 0;
+    Dual<3> iv[3], qv[3];
+    const double tf = p[P_BSIM3_tf];
+    bsim3_intrinsic(p, flags, v, iv, qv);
+    mosext_apply(p, P_BSIM3_m, flags, tf, v, iv, qv);
+    if (!live) return;
+    GlobalSink<3> sink;
+    sink.out = out; sink.jac = jac; sink.ld = n; sink.i = i; sink.nxin = 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sink.put(k, iv[k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sink.put(3 + k, qv[k]);
+}
+
+template <int TPB, int MINB>
+static cudaError_t launch_split(long n, unsigned flags, const double* card, const double* inst,
+                                long ld, int nvar, const cdn_rowmap& map, const double* xin,
+                                double* out, double* jac, cudaStream_t st) {
+    const int smem = (NP_BSIM3 + 1 + nvar * TPB) * (int)sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(bsim3_split_kernel<TPB, MINB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem > 48 * 1024 ? smem : 48 * 1024);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)((n + TPB - 1) / TPB);
+    bsim3_split_kernel<TPB, MINB><<<blocks, TPB, smem, st>>>(n, flags, card, inst, ld, nvar, map,
+                                                              xin, out, jac);
+    return cudaGetLastError();
+}
+
+// tuning (cdn_set_tuning key 6): CTA shape of the split kernel.  Measured on
+// B200, 2 x 2M mosbsim3 evaluations (G evals/s): 128 thr x 2/SM 3.18, x 3 3.52,
+// x 4 3.38; 256 x 2 4.07 (default), 256 x 3 3.25; 384 x 1 3.55; 512 x 1 3.74;
+// 640 x 1 3.49; 768 x 1 3.13 -- 16 warps per SM at 128 registers, in CTAs
+// large enough for their warps to share instruction fetches.
+static int g_split_minb = 5;
+
+extern "C" int cdn_dev_eval_split(cdn_ctx* ctx, int model_id, unsigned flags, long n,
+                                  const double* card, int nrows, const short* vrow,
+                                  const double* inst, long ld, const double* xin, double* out,
+                                  double* jac, void* stream) {
+    if (!ctx) return CDN_ERR_ARG;
+    if (n <= 0) return CDN_OK;
+    CDN_USE_DEVICE(ctx);
+    if (model_id != CDN_MODEL_BSIM3)
+        return cdn_fail(ctx, CDN_ERR_ARG, "cdn_dev_eval_split: only mosbsim3 / bsim3_i records are split");
+    if (nrows != NP_BSIM3 || !card || !vrow || !xin || !out || !jac)
+        return cdn_fail(ctx, CDN_ERR_ARG, "cdn_dev_eval_split: bad arguments");
+    cdn_rowmap map;
+    int nvar = 0;
+    for (int k = 0; k < NP_BSIM3; ++k) {
+        map.vrow[k] = vrow[k];
+        if (vrow[k] >= nvar) nvar = vrow[k] + 1;
+    }
+    map.vrow[NP_BSIM3] = -1;
+    if (nvar && !inst) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_dev_eval_split: instance rows missing");
+    if (nvar > 64) return cdn_fail(ctx, CDN_ERR_ARG, "cdn_dev_eval_split: more than 64 instance rows; use cdn_dev_eval");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    switch (g_split_minb) {
+    case 2: e = launch_split<128, 2>(n, flags, card, inst, ld, nvar, map, xin, out, jac, st); break;
+    case 4: e = launch_split<128, 4>(n, flags, card, inst, ld, nvar, map, xin, out, jac, st); break;
+    case 5: e = launch_split<256, 2>(n, flags, card, inst, ld, nvar, map, xin, out, jac, st); break;
+    case 6: e = launch_split<512, 1>(n, flags, card, inst, ld, nvar, map, xin, out, jac, st); break;
+    case 7: e = launch_split<384, 1>(n, flags, card, inst, ld, nvar, map, xin, out, jac, st); break;
+    case 8: e = launch_split<640, 1>(n, flags, card, inst, ld, nvar, map, xin, out, jac, st); break;
+    case 9: e = launch_split<768, 1>(n, flags, card, inst, ld, nvar, map, xin, out, jac, st); break;
+    case 10: e = launch_split<256, 3>(n, flags, card, inst, ld, nvar, map, xin, out, jac, st); break;
+    case 3: e = launch_split<128, 3>(n, flags, card, inst, ld, nvar, map, xin, out, jac, st); break;
+    default: e = launch_split<256, 2>(n, flags, card, inst, ld, nvar, map, xin, out, jac, st); break;
+    }
+    if (e != cudaSuccess) return cdn_fail(ctx, CDN_ERR_CUDA, std::string("cdn_dev_eval_split launch: ") + cudaGetErrorString(e));
+    return CDN_OK;
+}
+
 // MINB = resident CTAs per SM the register allocation is limited for
 template <int MODEL, int P, int MINB = 1>
 __global__ void __launch_bounds__(128, MINB)
@@ -222,6 +352,7 @@ extern "C" int cdn_set_tuning(int key, int value) {
     if (key == 3) { cdn_tune_tile_tpb = value; return CDN_OK; }
     if (key == 4) { cdn_tune_ac_blocks = value; return CDN_OK; }
     if (key == 5) { cdn_tune_ac_tpb = value; return CDN_OK; }
+    if (key == 6) { g_split_minb = value; return CDN_OK; }
     return CDN_ERR_ARG;
 }
 

@@ -47,6 +47,17 @@ int cdn_dev_eval(cdn_ctx* ctx, int model_id, unsigned flags, long n, int nxin,
                  const double* params, long ldp, const int* pidx,
                  const double* xin, double* out, double* jac, void* stream);
 
+/* Same evaluation for mosbsim3 / bsim3_i devices that share model cards: the
+ * rows of the packed record on which all n instances agree are passed once
+ * (card[nrows], device), the others per instance (inst[vrow[k]*ld + i],
+ * device); vrow[nrows] (host): row of `inst` holding record row k, or -1 for
+ * a card row.  Values and Jacobian are those of cdn_dev_eval on the expanded
+ * record, bit for bit.                                                       */
+int cdn_dev_eval_split(cdn_ctx* ctx, int model_id, unsigned flags, long n,
+                       const double* card, int nrows, const short* vrow,
+                       const double* inst, long ld, const double* xin,
+                       double* out, double* jac, void* stream);
+
 /* ---- (f2) small-signal AC sweep -------------------------------------------
  * Replaces the per-frequency loop of run_AC (cardoon/analyses/nodal.py:286-381):
  * Y = G + j w C, set_Jac of the device Jacobians with exp(-j w tau) on

@@ -186,3 +186,48 @@ def test_kernels_vs_reference_golden(lib, name):
     scale = 1e-9 * np.max(np.abs(rj), axis=(1, 2), keepdims=True) + 1e-16
     ej = float(np.max(np.abs(jac - rj) / (np.abs(rj) + scale)))
     assert ej < jtol, 'Jacobian differs: {0:g}'.format(ej)
+
+
+def test_bsim3_split_record(lib):
+    """Devices sharing a model card: the split-record kernel (card rows once,
+    w/l-dependent rows per instance) returns exactly what the full-record
+    kernels return."""
+    import bench
+    torch = lib.torch
+    inp = bench.deveval_inputs(1 << 14, ncols=64)
+    for g in inp['groups']:
+        cols = torch.as_tensor(g['cols']).to(lib.device)
+        params = cols.index_select(
+            1, torch.as_tensor(g['col'], device=lib.device)).contiguous()
+        xin = lib.dev(g['xin'])
+        split = lib.split_record(params)
+        card, vrow, inst = split
+        nvar = int((vrow >= 0).sum())
+        assert 5 < nvar < 45 and inst.shape == (nvar, g['n'])
+        o1, j1 = lib.dev_eval(g['model'], g['flags'], params, xin, 6)
+        o2, j2 = lib.dev_eval_split(g['model'], g['flags'], split, xin, 6)
+        lib.dll.cdn_set_tuning(2, 0)            # on-demand kernel
+        o3, j3 = lib.dev_eval(g['model'], g['flags'], params, xin, 6)
+        lib.dll.cdn_set_tuning(2, 1)
+        torch.cuda.synchronize()
+        # (different instantiations of the same source: FMA contraction may
+        # differ in the last bits; Jacobians compared where Ids is not an
+        # exact cancellation, see test_bsim3)
+        keep = (o2[0].abs() > 1e-25).cpu().numpy()
+        for oa, ja in ((o1, j1), (o3, j3)):
+            assert S.rel_err(oa.cpu().numpy(), o2.cpu().numpy(), 1e-20) < 1e-9
+            ra = ja.cpu().numpy().reshape(6, 3, -1)[:, :, keep]
+            rb = j2.cpu().numpy().reshape(6, 3, -1)[:, :, keep]
+            scale = 1e-9 * np.max(np.abs(rb), axis=(1, 2), keepdims=True) \
+                + 1e-16
+            assert np.max(np.abs(ra - rb) / (np.abs(rb) + scale)) < 1e-7
+    # one shared record: nothing per instance
+    params1 = params[:, :1].expand(-1, 512).contiguous()
+    split1 = lib.split_record(params1)
+    assert split1[2] is None
+    o4, j4 = lib.dev_eval_split(g['model'], g['flags'], split1, xin[:, :512]
+                                .contiguous(), 6)
+    o5, j5 = lib.dev_eval(g['model'], g['flags'], params1,
+                          xin[:, :512].contiguous(), 6)
+    torch.cuda.synchronize()
+    assert S.rel_err(o4.cpu().numpy(), o5.cpu().numpy(), 1e-20) < 1e-9
