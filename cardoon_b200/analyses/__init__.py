@@ -40,7 +40,7 @@ def _placeholder(name, params):
 
         def run(self, circuit):
             print('\n"{0}" analysis is not provided by the B200 back-end '
-                  '(only op and tran are); skipped.\n'.format(name))
+                  '(op, dc, ac and tran are); skipped.\n'.format(name))
 
     NotProvided.__name__ = 'NotProvided_' + name
     return NotProvided

@@ -6,6 +6,13 @@ cardoon/analyses/ac.py (:22-146): operating point first (device Newton), then
 ``nd.run_AC`` -- here one launch that factors and solves every frequency of
 the sweep (csrc/ac.cu) -- then the output requests ``ac``, ``ac_mag``,
 ``ac_phase``, ``ac_dB``.
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 import sys
 

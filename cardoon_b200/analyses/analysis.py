@@ -4,6 +4,13 @@ Shared analysis helpers (reference cardoon/analyses/analysis.py:20-116).
 Plots need matplotlib, which is optional here: ``.plot`` requests are
 skipped with a note when it is missing; ``.save`` requests write the same
 ``<netlist>_<reqtype>.npz`` files (keys ``xaxis`` + terminal names).
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 import numpy as np
 

@@ -10,6 +10,13 @@ reference's mechanism (:167-205): ``setattr`` the parameter (or
 then ``solve`` starting from the previous point's solution.  Every solve is a
 device Newton launch; ``refresh`` keeps the symbolic plan when only device
 records or source values changed.
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 import numpy as np
 

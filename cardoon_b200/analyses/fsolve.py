@@ -7,6 +7,13 @@ own ``get_deltax`` (e.g. homotopy helpers working through the ``nd``
 interface); the CUDA back-end's own helpers run the identical iteration on
 the device (csrc/engine_common.cuh ``newton_update``) and only report
 ``(x, res, iterations, success)``.
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 import numpy as np
 

@@ -7,6 +7,13 @@ BEuler :13, Trapezoidal :52).
 Host copies used by the ``nd`` interface (``set_IC``/``accept``/``get_rhs``
 called from Python).  The device-resident time loop implements the same two
 recurrences inside the kernels (csrc/engine_common.cuh, ``integ_accept``).
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 import numpy as np
 

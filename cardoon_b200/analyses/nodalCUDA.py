@@ -1073,12 +1073,30 @@ class _NLFunction(object):
         return x.reshape(b.shape)
 
     def get_adjoint_voltages(self, d):
-        """Transposed solve for sensitivities (nodal.py:661-670).  No
-        analysis of the reference's main tree calls it and the device engine
-        keeps no transposed triangular schedules."""
-        raise NotImplementedError(
-            'get_adjoint_voltages: transposed solves are not provided by the '
-            'CUDA back-end')
+        """Adjoint voltages for sensitivity calculations: solves
+        ``Jac^T lambda = d`` with the Jacobian of the last ``get_i_Jac``
+        (reference nodal.py:661-672, ``lu_solve(..., trans=1)``).
+
+        Dense engines only: the transposed matrix is written into the
+        device's Jacobian slots and factored and solved there (CDN_OP_SOLVE);
+        the static-pivot sparse plan has no schedule for the transposed
+        pattern.  The factors kept for ``solve_linear_system`` / the chord
+        step are those of the transpose afterwards; assemble again
+        (``get_i_Jac``) before going on with the forward system."""
+        e = self.engine
+        if not e.dense:
+            raise NotImplementedError(
+                'get_adjoint_voltages: the sparse plan of the CUDA back-end '
+                'has no transposed schedule (use sparse=0)')
+        torch = e.lib.torch
+        n = e.n
+        lu = e.view('lu')
+        J = lu.view(n, n).clone()
+        lu.copy_(J.t().contiguous().view(-1))
+        e.view('y').copy_(torch.as_tensor(np.ascontiguousarray(
+            d, dtype=np.float64)))
+        e.simple_op(L.OP_SOLVE)
+        return e.view('dx').cpu().numpy()
 
     def get_chord_deltax(self, sV, iVec=None):
         e = self.engine

@@ -5,6 +5,13 @@ Driver with the interface and printed report of the reference's
 cardoon/analyses/op.py (DCOP :21-155).  The solve itself runs on the GPU:
 ``nodalCUDA.DCNodal`` evaluates devices, assembles, factors and iterates
 Newton inside one kernel launch per convergence helper.
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 from ..paramset import ParamSet
 from ..globalVars import glVar

@@ -10,6 +10,13 @@ capture) runs as ONE kernel launch for all samples
 (``nodalCUDA.TransientNodal.run``), so a Newton iteration never returns to
 the host.  Source waveforms are evaluated on the host for all samples
 beforehand (a few scalar function calls per sample) and uploaded once.
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 import sys
 

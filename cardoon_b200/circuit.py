@@ -10,6 +10,13 @@ the port lists the device plugins publish.
 Differences that do not change results: dictionaries keep insertion order
 (the reference relied on Python-2 hash order, so its node numbering was
 arbitrary; compare by terminal *name*).
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 import copy
 

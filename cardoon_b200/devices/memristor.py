@@ -8,6 +8,13 @@ on the GPU from the compiled form of the ``m`` expression (exprcode.py).
 
 Terminals 0, 1; internal ``im`` (current/gyr), ``vc`` (q/C) and a local
 reference.
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 import numpy as np
 

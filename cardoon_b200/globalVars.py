@@ -5,6 +5,13 @@ Mirrors the reference's cardoon/globalVars.py:26-60 (same names, units,
 defaults) so that netlists and device plugins written for cardoon keep
 working.  Values only; nothing here runs on the hot path, the Newton
 kernels receive the tolerances as launch arguments.
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 import math
 from .paramset import ParamSet

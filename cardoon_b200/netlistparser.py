@@ -11,6 +11,13 @@ Supported lines: comments (``*``, ``#``, ``//``), ``\\`` continuation,
 ``<dev>:<name> nodes.. [par=val ..]``, ``x<name> nodes.. <subckt>``,
 ``.model``, ``.options``, ``.vars``, ``.subckt``/``.ends``, ``.include``,
 ``.analysis``, ``.plot``, ``.save``, ``.end``.
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 import os
 import re

@@ -7,6 +7,13 @@ values given in the netlist live in ``valueDict``, references to ``.vars``
 variables in ``varDict``; ``set_attributes`` turns them into instance
 attributes with the precedence element > model > default
 (reference circuit.py:318-336).
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 
 

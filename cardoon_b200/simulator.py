@@ -3,6 +3,13 @@ Library façade: parse netlists and run the analyses they request.
 
 Mirror of the reference's cardoon/simulator.py (reset_all :43, parse_net :54,
 run_analyses :66, new_elem :90, run_netlist :109).
+
+Provenance and licence: this file follows the structure, messages and
+behaviour of the corresponding module of cardoon (cechrist/cardoon,
+Copyright Carlos Christoffersen <c.christoffersen@ieee.org>), which is free
+software under the GNU General Public License version 3 or later
+(http://www.gnu.org/licenses/gpl.html); this Python-3 restatement is
+distributed under the same terms.
 """
 import time
 

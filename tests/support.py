@@ -8,7 +8,14 @@ NETS = os.path.join(HERE, 'netlists')
 
 
 def net(name):
-    return os.path.join(NETS, name)
+    """Path of a deck: tests/netlists/, else the reference's own regression
+    decks under tests/netlists/reference_tests/ (verbatim copies, kept once)."""
+    p = os.path.join(NETS, name)
+    if not os.path.exists(p):
+        q = os.path.join(NETS, 'reference_tests', name)
+        if os.path.exists(q):
+            return q
+    return p
 
 
 def load_circuit(path, init=True):

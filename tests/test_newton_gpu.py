@@ -576,3 +576,16 @@ def test_two_contexts_select_their_device(lib):
     out2, _ = S.cuda_eval(lib, elem, np.array([[0.6, 0.7]]))
     assert np.array_equal(out1, out2)
     assert torch.cuda.current_device() == 0
+
+
+def test_adjoint_voltages_dense(lib):
+    """get_adjoint_voltages (nodal.py:661-672): Jac^T lambda = d at the
+    operating point, against numpy on the device's own Jacobian."""
+    ckt, _ = S.load_circuit(S.net('bias_npn.net'))
+    (x, res, it), dc = run_op(ckt)
+    iVec, Jac = dc.get_i_Jac(x)
+    J = Jac.toarray()
+    d = np.random.default_rng(3).standard_normal(len(x))
+    lam = dc.get_adjoint_voltages(d)
+    ref = np.linalg.solve(J.T, d)
+    assert np.allclose(lam, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max())
