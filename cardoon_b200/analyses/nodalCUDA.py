@@ -1077,12 +1077,14 @@ class _NLFunction(object):
         ``Jac^T lambda = d`` with the Jacobian of the last ``get_i_Jac``
         (reference nodal.py:661-672, ``lu_solve(..., trans=1)``).
 
-        Dense engines only: the transposed matrix is written into the
-        device's Jacobian slots and factored and solved there (CDN_OP_SOLVE);
-        the static-pivot sparse plan has no schedule for the transposed
-        pattern.  The factors kept for ``solve_linear_system`` / the chord
-        step are those of the transpose afterwards; assemble again
-        (``get_i_Jac``) before going on with the forward system."""
+        Dense engines only: the Jacobian is assembled again at the vector of
+        the last ``get_i_Jac`` / ``get_i`` (the in-place factorisation has
+        overwritten it), its transpose is written into the device's Jacobian
+        slots and factored and solved there (CDN_OP_SOLVE); the static-pivot
+        sparse plan has no schedule for the transposed pattern.  The factors
+        kept for ``solve_linear_system`` / the chord step are those of the
+        transpose afterwards: call ``get_i_Jac`` + ``factor_and_solve`` again
+        before going on with the forward system."""
         e = self.engine
         if not e.dense:
             raise NotImplementedError(
@@ -1090,6 +1092,9 @@ class _NLFunction(object):
                 'has no transposed schedule (use sparse=0)')
         torch = e.lib.torch
         n = e.n
+        keep = e.view('ivec').clone()
+        e.simple_op(L.OP_GET_I_JAC)
+        e.view('ivec').copy_(keep)
         lu = e.view('lu')
         J = lu.view(n, n).clone()
         lu.copy_(J.t().contiguous().view(-1))

@@ -208,8 +208,10 @@ def test_nd_interface_stepwise(lib):
     assert np.array_equal(nd.get_submatrix(J_r, 2), J_r[:, :2])
     assert np.allclose(nd.add_to_diagonal(np.zeros((3, 3)), [1., 2.]),
                        np.diag([1., 2., 0.]))
-    with pytest.raises(NotImplementedError):
-        dc.get_adjoint_voltages(B[:, 0])
+    lam = dc.get_adjoint_voltages(B[:, 0])          # nodal.py:661-672
+    assert np.allclose(lam, np.linalg.solve(J_r.T, B[:, 0]), rtol=1e-6,
+                       atol=1e-10)
+    dc.get_i_Jac(x)          # (the adjoint solve left transposed factors)
     # stepwise transient, host loop as in tran.py:171-206
     timeVec = np.arange(0., an.tstop, an.tstep)[:30]
     tran.set_IC(an.tstep)
