@@ -267,6 +267,15 @@ def set_xin(xin, posCols, negCols, xVec):
         xin[i] -= xVec[j]
 
 
+def set_i(iVec, posRows, negRows, current):
+    """iVec += T_i current (nodal.py:55-63; used by the sensitivity module,
+    the engines assemble on the device)."""
+    for i, j in posRows:
+        iVec[j] += current[i]
+    for i, j in negRows:
+        iVec[j] -= current[i]
+
+
 # ---------------------------------------------------------------------------
 # topology -> plan input
 # ---------------------------------------------------------------------------
