@@ -11,7 +11,10 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(_HERE, 'libcardoon_b200.so')
+# (CARDOON_B200_LIB: a differently tuned build of the same library, used by
+# tools/build_variant.py experiments)
+LIBPATH = os.environ.get('CARDOON_B200_LIB') or os.path.join(
+    _HERE, 'libcardoon_b200.so')
 
 
 class CudaUnavailable(RuntimeError):

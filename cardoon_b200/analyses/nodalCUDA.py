@@ -708,7 +708,7 @@ class Engine(object):
                                   device=lib.device)
         keep = []
         self.profile = False
-        self.prof = torch.zeros(16, dtype=torch.int64, device=lib.device)
+        self.prof = torch.zeros(128, dtype=torch.int64, device=lib.device)
         self.red = torch.zeros(4096, dtype=torch.float64, device=lib.device)
         self.x = torch.zeros((batch, n), dtype=torch.float64,
                              device=lib.device)

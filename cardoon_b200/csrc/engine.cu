@@ -99,14 +99,18 @@ int cdn_engine_run(cdn_plan* P, const cdn_run_host* r, void* stream) {
         // one CTA per SM when the batch fills the GPU (its tiles run in lockstep
         // and share the instruction cache), sized so that every SM gets one:
         // ceil(B / SMs) instances per CTA, whole warps, at most 256 threads
-        c.tpb = ((long)A.B * T >= (long)ctx->sm_count * 128) ? 256 : 128;
-        if ((long)A.B * T >= (long)ctx->sm_count * 128) {
+        // (an instance's chain of dependent instructions is what a launch
+        // costs -- a warp alone on an SM needs 23 ms for 400 ring_bsim3 samples,
+        // seven warps sharing it 28 ms -- so small batches spread over all SMs:
+        // 512 instances 25.7 ms with 128-thread CTAs, 23.0 ms with 32)
+        c.tpb = 256;
+        {
             const long per_sm = (A.B + ctx->sm_count - 1) / ctx->sm_count;
             long tpb = (per_sm * T + 31) / 32 * 32;
-            if (tpb < 128) tpb = 128;
+            if (tpb < 32) tpb = 32;
             if (tpb < c.tpb) c.tpb = (int)tpb;
         }
-        if (cdn_tune_tile_tpb >= 32 && cdn_tune_tile_tpb <= 256 && cdn_tune_tile_tpb % 32 == 0)
+        if (cdn_tune_tile_tpb >= 32 && cdn_tune_tile_tpb <= 1024 && cdn_tune_tile_tpb % 32 == 0)
             c.tpb = cdn_tune_tile_tpb;
         if (!A.ws) {
             // state in shared memory: shrink the CTA until it fits

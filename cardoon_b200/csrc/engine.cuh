@@ -1082,6 +1082,23 @@ __device__ __forceinline__ unsigned* stage_area(double* dsm, const cdn_plan_dev&
     return (unsigned*)(dsm + ((P.nlu + P.n + 1) & ~1));
 }
 
+// One level of a staged sweep: 2^lg lanes share a row (plan.h; the host picks lg
+// per level).  The row loop is uniform over each warp -- lanes past the end
+// of the level run along with an empty row -- so that the shuffles of
+// group_sum can name the whole warp.
+//   CDN_GROUP_ROWS(r0, r1, lg) { CDN_GROUP_ROW(r1, lg); ... }   defines g, sub, q, ok
+#define CDN_GROUP_ROWS(r0, r1, lg)                                                           \
+    for (int qw_ = (r0) + (int)((threadIdx.x & ~31u) >> (lg)); qw_ < (r1);                   \
+         qw_ += (int)(blockDim.x >> (lg)))
+#define CDN_GROUP_ROW(r1, lg)                                                                \
+    const int g = 1 << (lg), sub = (int)(threadIdx.x & (unsigned)(g - 1));                   \
+    const int q = qw_ + (int)((threadIdx.x & 31u) >> (lg));                                  \
+    const bool ok = q < (r1)
+__device__ __forceinline__ double group_sum(double s, int g) {
+    for (int off = g >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    return s;
+}
+
 __device__ __forceinline__ void staged_solve(BlockTeam& tm, const cdn_plan_dev& P, const Ws& w) {
     extern __shared__ double dsm[];
     const int n = P.n;
@@ -1105,16 +1122,21 @@ __device__ __forceinline__ void staged_solve(BlockTeam& tm, const cdn_plan_dev& 
         __syncthreads();
         CDN_DP(9);
         const int nlev = P.nlev_l;
+        const int* glg = lvl + nlev + 1;
         for (int l = 0; l < nlev; ++l) {
-            const int r1 = lvl[l + 1];
-            for (int q = lvl[l] + threadIdx.x; q < r1; q += blockDim.x) {
-                const uint2 r = rec[q];
+            const int r0 = lvl[l], r1 = lvl[l + 1], lg = glg[l];
+            CDN_GROUP_ROWS(r0, r1, lg) {
+                CDN_GROUP_ROW(r1, lg);
+                const uint2 r = ok ? rec[q] : make_uint2(0u, 0u);
                 const int i = r.x & 0xffffu, cnt = r.x >> 16, k0 = r.y;
-                double v = tmp[i];
-                for (int k = 0; k < cnt; ++k) v -= lu[slot[k0 + k]] * tmp[col[k0 + k]];
-                tmp[i] = v;
+                double s = 0.0;
+#pragma unroll 2
+                for (int k = sub; k < cnt; k += g) s = fma(lu[slot[k0 + k]], tmp[col[k0 + k]], s);
+                s = group_sum(s, g);
+                if (ok && sub == 0) tmp[i] -= s;
             }
             __syncthreads();
+            if (l < 32) CDN_DP(16 + l);
         }
     }
     CDN_DP(10);
@@ -1129,17 +1151,22 @@ __device__ __forceinline__ void staged_solve(BlockTeam& tm, const cdn_plan_dev& 
         const unsigned short* slot = (const unsigned short*)(blob + P.cu_off[3]);
         const unsigned short* cmap = (const unsigned short*)(blob + P.cu_off[4]);
         const int nlev = P.nlev_u;
+        const int* glg = lvl + nlev + 1;
         for (int l = 0; l < nlev; ++l) {
-            const int r1 = lvl[l + 1];
-            for (int q = lvl[l] + threadIdx.x; q < r1; q += blockDim.x) {
-                const uint2 r = rec[q];
+            const int r0 = lvl[l], r1 = lvl[l + 1], lg = glg[l];
+            CDN_GROUP_ROWS(r0, r1, lg) {
+                CDN_GROUP_ROW(r1, lg);
+                const uint2 r = ok ? rec[q] : make_uint2(0u, 0u);
                 const int i = r.x & 0xffffu, cnt = r.x >> 16;
                 const int k0 = r.y & 0xffffu, dg = r.y >> 16;
-                double v = tmp[i];
-                for (int k = 0; k < cnt; ++k) v -= lu[slot[k0 + k]] * tmp[col[k0 + k]];
-                tmp[i] = v / lu[dg];
+                double s = 0.0;
+#pragma unroll 2
+                for (int k = sub; k < cnt; k += g) s = fma(lu[slot[k0 + k]], tmp[col[k0 + k]], s);
+                s = group_sum(s, g);
+                if (ok && sub == 0) tmp[i] = (tmp[i] - s) / lu[dg];
             }
             __syncthreads();
+            if (l < 32) CDN_DP(48 + l);
         }
         CDN_DP(12);
         for (int i = threadIdx.x; i < n; i += blockDim.x) w.dx[cmap[i]] = tmp[i];
@@ -1187,23 +1214,30 @@ __device__ __forceinline__ void staged_refactor(BlockTeam& tm, const cdn_plan_de
     }
     __syncthreads();
     const int nlev = P.nlev_f;
+    const int* glg = lvl + nlev + 1;
     for (int l = 0; l < nlev; ++l) {
-        const int q0 = lvl[l], q1 = lvl[l + 1];
+        const int q0 = lvl[l], q1 = lvl[l + 1], lg = glg[l];
         if (q0 == q1) continue;                    // nothing changes on this level
-        for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-            const uint2 r = rec[q];
+        CDN_GROUP_ROWS(q0, q1, lg) {
+            CDN_GROUP_ROW(q1, lg);
+            const uint2 r = ok ? rec[q] : make_uint2(0u, 0xffff0000u);
             const int e = r.x & 0xffffu, cnt = r.x >> 16;
             const int t0 = r.y & 0xffffu, pv = r.y >> 16;
-            double v = lu[e];
-            for (int t = 0; t < cnt; ++t) {
+            double s = 0.0;
+#pragma unroll 2
+            for (int t = sub; t < cnt; t += g) {
                 const unsigned tt = term[t0 + t];
-                v -= lu[tt & 0xffffu] * lu[tt >> 16];
+                s = fma(lu[tt & 0xffffu], lu[tt >> 16], s);
             }
-            if (pv != 0xffff) {
-                v /= lu[pv];
-                if (!(fabs(v) <= CDN_MULT_LIMIT)) w.piv[P.n] = 1;
+            s = group_sum(s, g);
+            if (ok && sub == 0) {
+                double v = lu[e] - s;
+                if (pv != 0xffff) {
+                    v /= lu[pv];
+                    if (!(fabs(v) <= CDN_MULT_LIMIT)) w.piv[P.n] = 1;
+                }
+                lu[e] = v;
             }
-            lu[e] = v;
         }
         __syncthreads();
     }
@@ -1695,8 +1729,14 @@ __device__ __forceinline__ void run_tile(TileTeam<8>& tm, const cdn_engine_args&
 // ---- kernels --------------------------------------------------------------------------------
 // Batches of small circuits: T lanes per instance; the state lives in shared
 // memory unless the caller wants it kept (A.ws != NULL).
+#ifndef CDN_TILE_MAXT
+#define CDN_TILE_MAXT 256
+#endif
+#ifndef CDN_TILE_MINB
+#define CDN_TILE_MINB 1
+#endif
 template <int MS, int T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(CDN_TILE_MAXT, CDN_TILE_MINB)
 engine_tile_kernel(const __grid_constant__ cdn_engine_args A) {
     extern __shared__ double smem[];
     TileTeam<T> tm;

@@ -45,6 +45,9 @@ static cudaError_t launch_tile(const cdn_engine_args& A, const cdn_launch_cfg& c
     return cudaGetLastError();
 }
 
+#ifndef CDN_BLOCK_TPB_LIGHT
+#define CDN_BLOCK_TPB_LIGHT 1024
+#endif
 template <int MS, int KIND>
 static cudaError_t launch_kind(const cdn_engine_args& A, const cdn_launch_cfg& c, cudaStream_t st) {
     // (if constexpr: a translation unit instantiates exactly one kernel)
@@ -57,7 +60,7 @@ static cudaError_t launch_kind(const cdn_engine_args& A, const cdn_launch_cfg& c
     } else if constexpr (KIND == CDN_KIND_BLOCK) {
         // light model sets run 1024 threads per CTA (64 registers each); the
         // heavy models need their 255 registers
-        constexpr int TPB = (MS == CDN_MS_DIODE) ? 1024 : 256;
+        constexpr int TPB = (MS == CDN_MS_DIODE) ? CDN_BLOCK_TPB_LIGHT : 256;
         cudaError_t e = set_smem(engine_block_kernel<MS, TPB>, c.smem);
         if (e != cudaSuccess) return e;
         engine_block_kernel<MS, TPB><<<c.blocks, TPB, c.smem, st>>>(A);

@@ -77,9 +77,11 @@ struct cdn_plan_dev {
     // shared memory next to the LU values (block team)
     int compact, nnzl, nnzu;
     // one contiguous blob of 32-bit words per sweep (copied with 16-byte loads):
-    //   L / U solve: [level ptr | row records (2 words) | columns (16 bit) |
+    //   L / U solve: [level ptr, then log2 of the lanes per row of each level
+    //                 | row records (2 words) | columns (16 bit) |
     //                 slots (16 bit) | rowmap / colmap (16 bit)]
-    //   partial refactorisation: [level ptr | entry records (2 words: slot |
+    //   partial refactorisation: [level ptr, lanes per entry as above | entry
+    //                 records (2 words: slot |
     //                 terms << 16, first term | pivot slot << 16) | terms
     //                 (L slot | U slot << 16)] over the entries that depend on a
     //                 device contribution; all other entries keep the values of the

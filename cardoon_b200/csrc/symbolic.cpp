@@ -603,6 +603,23 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
     for (int col = 0; col < n; ++col) colmap[ip[col]] = col;
 
     // compact programs (see plan.h)
+    // Lanes that share one row (entry) of a level: a level costs what its longest
+    // row costs, one term after the other (two dependent shared-memory loads
+    // and a multiply-add, ~70 cycles); 2^lg lanes take every 2^lg-th term and
+    // add up with lg shuffles.  Picked per level for a 512-thread CTA from a
+    // cycle estimate: passes over the level x (fixed + longest share + shuffles).
+    auto group_log2 = [](int nitems, int maxcnt) {
+        int best = 0;
+        long best_cost = -1;
+        for (int lg = 0; lg <= 5; ++lg) {
+            const int g = 1 << lg;
+            if (lg > 0 && g > 2 * maxcnt) break;
+            const long passes = ((long)nitems * g + 511) / 512;
+            const long cost = std::max(1L, passes) * (150 + 70L * ((maxcnt + g - 1) / g) + 30L * lg);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = lg; }
+        }
+        return best;
+    };
     std::vector<unsigned> cl_prog, cu_prog, cf_prog;
     int cl_off[5] = {0, 0, 0, 0, 0}, cu_off[5] = {0, 0, 0, 0, 0}, cf_off[3] = {0, 0, 0};
     int naff = 0;
@@ -626,6 +643,15 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
             const ivec& ptr = pass ? u_ptr : l_ptr;
             off[0] = 0;
             for (int v : lvl) pr.push_back((unsigned)v);
+            // lanes per row, level by level (log2)
+            for (size_t l = 0; l + 1 < lvl.size(); ++l) {
+                int maxcnt = 0;
+                for (int q = lvl[l]; q < lvl[l + 1]; ++q) {
+                    const int i = rows[q];
+                    maxcnt = std::max(maxcnt, ptr[i + 1] - ptr[i]);
+                }
+                pr.push_back((unsigned)group_log2(lvl[l + 1] - lvl[l], maxcnt));
+            }
             pad4(pr);
             off[1] = (int)pr.size();
             for (int q = 0; q < n; ++q) {
@@ -650,9 +676,16 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
             if (!f && e_piv[e] >= 0) f = aff[e_piv[e]];
             aff[e] = f ? 1 : 0;
         }
-        ivec flvl(nlev_f + 1, 0);
+        ivec flvl(nlev_f + 1, 0), fgrp(nlev_f, 0);
         std::vector<unsigned> frec, fterm;
         for (int l = 0; l < nlev_f; ++l) {
+            int maxcnt = 0, cnt_l = 0;
+            for (int e = f_lvl_ptr[l]; e < f_lvl_ptr[l + 1]; ++e)
+                if (aff[e]) {
+                    maxcnt = std::max(maxcnt, e_term_ptr[e + 1] - e_term_ptr[e]);
+                    ++cnt_l;
+                }
+            fgrp[l] = group_log2(cnt_l, maxcnt);
             for (int e = f_lvl_ptr[l]; e < f_lvl_ptr[l + 1]; ++e) {
                 if (!aff[e]) continue;
                 const int cnt = e_term_ptr[e + 1] - e_term_ptr[e];
@@ -669,6 +702,7 @@ extern "C" int cdn_plan_create(cdn_ctx* ctx, const cdn_circuit_host* c, cdn_plan
             compact = false;             // first-term offsets are 16 bit
         } else {
             for (int v : flvl) cf_prog.push_back((unsigned)v);
+            for (int v : fgrp) cf_prog.push_back((unsigned)v);
             pad4(cf_prog);
             cf_off[1] = (int)cf_prog.size();
             cf_prog.insert(cf_prog.end(), frec.begin(), frec.end());

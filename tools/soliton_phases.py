@@ -19,9 +19,14 @@ t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=T
 t0.record()
 w, it, rs, st = e.tran(x, src, rows, im='trap', sync=False)
 t1.record(); torch.cuda.synchronize()
+raw = e.prof.cpu().numpy().copy()
 c = e.phase_cycles()
 tot = sum(v for k, v in c.items() if k in e.PHASES[:7])
 print('ms', t0.elapsed_time(t1), 'steps', len(timeVec), 'info', e.info)
 for k, v in c.items():
     print('%-14s %12d cycles  %6.2f us/step' % (k, v, v / 1.965e3 / (len(timeVec) - 1)))
 print('sum main', tot / 1.965e3 / (len(timeVec) - 1), 'us/step')
+# cycles per level of the staged L / U sweeps (slots 16.., 48..), per sweep
+nsweep = 2 * (len(timeVec) - 1) - 1
+print('L levels:', ' '.join('%d' % (v / nsweep) for v in raw[16:16 + e.info['nlev_l']]))
+print('U levels:', ' '.join('%d' % (v / nsweep) for v in raw[48:48 + e.info['nlev_u']]))
