@@ -1,0 +1,351 @@
+"""
+Host analysis for the *boundary / interior* transient engine (csrc/schur.cuh).
+
+The sparse engine of the reference refactors the whole Jacobian on every
+Newton iteration (SuperLU, nodalSP.py:281-303, :838-887).  With a fixed time
+step only the entries stamped by nonlinear devices change: J = A + D(x) with
+A = G + a0 C constant (nodalSP.py:603-612 builds it once per step size) and D
+confined to the rows/columns of the device ports (nodal.py:66-80).  This
+module splits the unknowns into
+
+  * a small *boundary* set B = device port unknowns + a few cut nodes that
+    separate the rest into independent pieces, and
+  * the *interior* I, dealt to the CTAs of one thread-block cluster piece by
+    piece,
+
+and precomputes, per CTA c with interior rows Ic, the constant operators
+
+  Linv_c, Uinv_c   explicit inverses of the LU factors of A[Ic, Ic]
+                   (so that a solve is two sparse matrix-vector products
+                   instead of level-scheduled triangular sweeps),
+  X_c   = A[Ic, Ic]^-1 A[Ic, B],   Asi_c = A[B, Ic],   Csi_c = C[B, Ic],
+  A_c, C_c         rows Ic of A and C (residual and charge),
+
+and the replicated boundary data: A[B, B], C[B, B], the Schur complement
+T0 = A[B, B] - sum_c Asi_c X_c in band storage, and gather lists of the device
+outputs / Jacobians into the boundary rows and the band of T = T0 + D(x).
+
+One Newton step  J dx = y  is then
+  t_I = Uinv (Linv y_I);  r_B = y_B - A[B, I] t_I;  T dx_B = r_B (banded LU,
+  no pivoting);  dx_I = t_I - X dx_B,
+with one exchange of boundary partial sums between the CTAs.
+
+Entries of T0 below 2**-60 of both diagonals they couple are dropped before
+the bandwidth is measured: they cannot change a double-precision pivot.  A
+circuit whose boundary system is not narrow-banded after that is not eligible
+(`analyse` returns None) and runs on the general kernels.
+"""
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+from scipy.sparse.csgraph import (breadth_first_order, connected_components,
+                                  reverse_cuthill_mckee)
+
+MAX_BOUNDARY = 96          # unknowns of the replicated boundary system
+MAX_BAND = 4               # half bandwidth of T the kernel handles
+DROP = 2. ** -60
+
+
+def _levels(adj, nodes, start):
+    """BFS level of every node of the sub-graph ``nodes`` from ``start``."""
+    sub = adj[nodes][:, nodes]
+    order, pred = breadth_first_order(sub, start, directed=False)
+    lev = np.full(len(nodes), -1)
+    lev[start] = 0
+    for v in order[1:]:
+        lev[v] = lev[pred[v]] + 1
+    return lev, order
+
+
+def _bisect(adj, nodes):
+    """Vertex separator of the sub-graph ``nodes`` (a connected piece) from
+    its BFS level structure: (part1, part2, separator) as node arrays."""
+    if len(nodes) < 3:
+        return nodes, nodes[:0], nodes[:0]
+    lev, order = _levels(adj, nodes, 0)
+    lev, order = _levels(adj, nodes, order[-1])      # pseudo-peripheral start
+    if lev.max() < 2:
+        return nodes, nodes[:0], nodes[:0]
+    cnt = np.bincount(lev[lev >= 0])
+    half = np.searchsorted(np.cumsum(cnt), len(nodes) / 2.)
+    half = min(max(half, 1), len(cnt) - 2)
+    unreached = lev < 0
+    return (nodes[(lev < half) & ~unreached],
+            nodes[(lev > half) | unreached], nodes[lev == half])
+
+
+def _nd_order(adj, nodes, leaf=4):
+    """Nested-dissection elimination order of the sub-graph ``nodes``."""
+    if len(nodes) <= leaf:
+        return list(nodes)
+    ncomp, lab = connected_components(adj[nodes][:, nodes], directed=False)
+    if ncomp > 1:
+        out = []
+        for k in range(ncomp):
+            out += _nd_order(adj, nodes[lab == k], leaf)
+        return out
+    p1, p2, s = _bisect(adj, nodes)
+    if len(s) == 0:
+        return list(nodes)
+    return _nd_order(adj, p1, leaf) + _nd_order(adj, p2, leaf) + list(s)
+
+
+def _cut_nodes(adj, interior, parts):
+    """Separators that cut the interior graph into at least ``parts`` pieces
+    of comparable size."""
+    pieces = []
+    ncomp, lab = connected_components(adj[interior][:, interior],
+                                      directed=False)
+    for k in range(ncomp):
+        pieces.append(interior[lab == k])
+    cuts = []
+    target = max(8, int(1.15 * len(interior) / parts))
+    for _ in range(4 * parts):
+        pieces.sort(key=len)
+        big = pieces[-1]
+        if len(pieces) >= parts and len(big) <= target:
+            break
+        p1, p2, s = _bisect(adj, big)
+        if len(s) == 0:
+            break
+        pieces.pop()
+        cuts += list(s)
+        for p in (p1, p2):
+            if len(p):
+                nc, lb = connected_components(adj[p][:, p], directed=False)
+                for k in range(nc):
+                    pieces.append(p[lb == k])
+    return np.array(sorted(cuts), dtype=np.int64), pieces
+
+
+class Csr(object):
+    """CSR operator with 16-bit column indices (what the kernel stages)."""
+
+    def __init__(self, M, drop_zeros=True):
+        M = sp.csr_matrix(M)
+        if drop_zeros:
+            M.eliminate_zeros()
+        M.sort_indices()
+        self.shape = M.shape
+        self.ptr = M.indptr.astype(np.int32)
+        self.col = M.indices.astype(np.uint16)
+        self.val = M.data.astype(np.float64)
+        assert M.shape[1] < 65536
+
+    @property
+    def nnz(self):
+        return len(self.val)
+
+    def dot(self, v):
+        out = np.zeros(self.shape[0])
+        for r in range(self.shape[0]):
+            a, b = self.ptr[r], self.ptr[r + 1]
+            out[r] = np.dot(self.val[a:b], v[self.col[a:b]])
+        return out
+
+    def tosp(self):
+        return sp.csr_matrix((self.val, self.col.astype(np.int32), self.ptr),
+                             shape=self.shape)
+
+
+def device_port_unknowns(topo):
+    s = set()
+    for g in topo.groups:
+        for k in ('vpos', 'vneg', 'cpos', 'cneg', 'qpos', 'qneg'):
+            s.update(int(v) for v in np.asarray(g[k]).ravel() if v >= 0)
+    return np.array(sorted(s), dtype=np.int64)
+
+
+def device_gathers(topo, bpos, out_off, jac_off):
+    """Gather lists of the device buffers into the boundary system.
+
+    ``bpos[u]`` = position of unknown u in B (-1: interior); ``out_off`` /
+    ``jac_off``: offsets of every group inside the device-output / Jacobian
+    buffers (layout of csrc/engine.cuh WsSink: out[slot * n + i],
+    jac[(slot * nxin + c) * n + i]).  Returns COO lists
+    (row, out index, sign) for currents and for charges, and
+    (row, col, jac index, sign) for the Jacobian (charge rows of the
+    Jacobian buffer arrive multiplied by a0)."""
+    cur, chg, jac = [], [], []
+    for g, oo, jo in zip(topo.groups, out_off, jac_off):
+        n, ncs, nqs, nxin = g['n'], g['ncs'], g['nqs'], g['nxin']
+        for o in range(ncs + nqs):
+            rp = g['cpos'][o] if o < ncs else g['qpos'][o - ncs]
+            rn = g['cneg'][o] if o < ncs else g['qneg'][o - ncs]
+            dst = cur if o < ncs else chg
+            for i in range(n):
+                for r, sg in ((rp[i], 1.), (rn[i], -1.)):
+                    if r >= 0:
+                        dst.append((bpos[r], oo + o * n + i, sg))
+                for k in range(nxin):
+                    cp, cn = g['vpos'][k][i], g['vneg'][k][i]
+                    src = jo + (o * nxin + k) * n + i
+                    for r, c, sg in ((rp[i], cp, 1.), (rn[i], cn, 1.),
+                                     (rp[i], cn, -1.), (rn[i], cp, -1.)):
+                        if r >= 0 and c >= 0:
+                            jac.append((bpos[r], bpos[c], src, sg))
+    return cur, chg, jac
+
+
+class SchurPlan(object):
+    pass
+
+
+def analyse(topo, a0, ncta=8, stamps=None, out_off=None, jac_off=None,
+            max_band=MAX_BAND):
+    """Boundary/interior plan of the transient Jacobian of ``topo`` with
+    integration coefficient ``a0``, for a cluster of ``ncta`` CTAs.
+    ``stamps``: nodal stamps (rows, cols, dI/dv, dQ/dv) of the device
+    Jacobians at a reference point (Topology.device_stamps); they only serve
+    to scale the drop test of the boundary system.  Returns None when the
+    circuit is not eligible."""
+    n = topo.n
+    if any(g['ndelay'] for g in topo.groups) or n >= 60000:
+        return None
+    G = sp.coo_matrix((topo.G[2], (topo.G[0], topo.G[1])), shape=(n, n)).tocsr()
+    Cm = sp.coo_matrix((topo.C[2], (topo.C[0], topo.C[1])), shape=(n, n)).tocsr()
+    A = (G + a0 * Cm).tocsr()
+    adj = (abs(A) + abs(A.T)).tocsr()
+    S = device_port_unknowns(topo)
+    if len(S) == 0 or len(S) > MAX_BOUNDARY:
+        return None
+    mask = np.ones(n, bool)
+    mask[S] = False
+    interior = np.nonzero(mask)[0]
+    cuts, pieces = _cut_nodes(adj, interior, ncta)
+    B = np.array(sorted(set(S) | set(cuts)), dtype=np.int64)
+    if len(B) > MAX_BOUNDARY:
+        return None
+    # ---- deal the pieces to the CTAs (largest first, least loaded CTA) ---------
+    pieces.sort(key=len, reverse=True)
+    load = [0] * ncta
+    owned = [[] for _ in range(ncta)]
+    for p in pieces:
+        c = int(np.argmin(load))
+        load[c] += len(p)
+        owned[c].append(p)
+    # ---- boundary order: reverse Cuthill-McKee of the pattern of T0 -----------
+    ctas = []
+    ABB = A[B][:, B].toarray()
+    T0 = ABB.copy()
+    for c in range(ncta):
+        Ic = []
+        for p in owned[c]:
+            Ic += _nd_order(adj, np.asarray(p))
+        Ic = np.array(Ic, dtype=np.int64)
+        m = len(Ic)
+        d = dict(Ic=Ic, m=m)
+        if m:
+            Acc = A[Ic][:, Ic].tocsc()
+            try:
+                lu = spla.splu(Acc, permc_spec='NATURAL', diag_pivot_thresh=0.01,
+                               options=dict(SymmetricMode=False))
+            except RuntimeError:
+                return None
+            eye = np.eye(m)
+            Linv = spla.spsolve_triangular(lu.L.tocsr(), eye, lower=True)
+            Uinv = spla.spsolve_triangular(lu.U.tocsr(), eye, lower=False)
+            # Pr A Pc = L U  =>  A^-1 = Pc U^-1 L^-1 Pr
+            Pr = sp.csc_matrix((np.ones(m), (lu.perm_r, np.arange(m))), shape=(m, m))
+            Pc = sp.csc_matrix((np.ones(m), (np.arange(m), lu.perm_c)), shape=(m, m))
+            d['Linv'] = sp.csr_matrix(Linv) @ Pr
+            d['Uinv'] = Pc @ sp.csr_matrix(Uinv)
+            AiB = A[Ic][:, B].toarray()
+            Xc = d['Uinv'] @ (d['Linv'] @ AiB)
+            Xc[AiB.any(axis=0)[None, :].repeat(m, 0) == 0] = 0.
+            d['X'] = Xc
+            d['Asi'] = A[B][:, Ic]
+            d['Csi'] = Cm[B][:, Ic]
+            T0 -= d['Asi'] @ Xc
+        ctas.append(d)
+    # the boundary matrix at the reference point scales the drop test (T0
+    # alone may have zero diagonals: gyrator equations of device branches)
+    Tref = T0.copy()
+    if stamps is not None:
+        bp = np.full(n, -1, dtype=np.int64)
+        bp[B] = np.arange(len(B))
+        sr, sc, si, sq = stamps
+        np.add.at(Tref, (bp[sr], bp[sc]), si + a0 * sq)
+    dg = np.abs(np.diag(Tref))
+    if not (np.all(np.isfinite(Tref)) and np.all(dg > 0.)):
+        return None
+    keep = np.abs(T0) > DROP * np.minimum(dg[:, None], dg[None, :])
+    keep |= np.eye(len(B), dtype=bool)
+    perm = np.asarray(reverse_cuthill_mckee(sp.csr_matrix(keep | keep.T),
+                                            symmetric_mode=True))
+    kp = keep[perm][:, perm]
+    ii, jj = np.nonzero(kp)
+    band = int(np.abs(ii - jj).max()) if len(ii) else 0
+    if band > max_band:
+        return None
+    # ---- renumber the boundary -------------------------------------------------
+    B = B[perm]
+    nB = len(B)
+    bpos = np.full(n, -1, dtype=np.int64)
+    bpos[B] = np.arange(nB)
+    T0 = T0[perm][:, perm] * kp
+    P = SchurPlan()
+    P.n, P.nB, P.band, P.ncta, P.a0 = n, nB, band, ncta, float(a0)
+    P.B, P.bpos = B, bpos
+    P.T0 = T0
+    P.Abb = Csr(A[B][:, B])
+    P.Cbb = Csr(Cm[B][:, B])
+    P.ctas = []
+    for d in ctas:
+        m, Ic = d['m'], d['Ic']
+        c = SchurPlan()
+        c.m, c.Ic = m, Ic
+        # local vector space of a CTA: [x_B (nB) | x_Ic (m)]
+        loc = np.concatenate([B, Ic])
+        if m:
+            c.Linv, c.Uinv = Csr(d['Linv']), Csr(d['Uinv'])
+            c.X = Csr(d['X'][:, perm])
+            c.Asi = Csr(d['Asi'][perm])
+            c.Csi = Csr(d['Csi'][perm])
+            c.Arow = Csr(A[Ic][:, loc])
+            c.Crow = Csr(Cm[Ic][:, loc])
+        else:
+            z = sp.csr_matrix((0, 0))
+            c.Linv = c.Uinv = Csr(z)
+            c.X = Csr(sp.csr_matrix((0, nB)))
+            c.Asi = c.Csi = Csr(sp.csr_matrix((nB, 0)))
+            c.Arow = c.Crow = Csr(sp.csr_matrix((0, nB)))
+        P.ctas.append(c)
+    P.has_csi = any(c.Csi.nnz for c in P.ctas)
+    # ---- device gathers ------------------------------------------------------------
+    if out_off is None:
+        out_off, jac_off, o, j = [], [], 0, 0
+        for g in topo.groups:
+            out_off.append(o), jac_off.append(j)
+            o += (g['ncs'] + g['nqs']) * g['n']
+            j += (g['ncs'] + g['nqs']) * g['nxin'] * g['n']
+        P.out_size, P.jac_size = o, j
+    cur, chg, jac = device_gathers(topo, bpos, out_off, jac_off)
+    P.out_size = sum((g['ncs'] + g['nqs']) * g['n'] for g in topo.groups)
+    P.jac_size = sum((g['ncs'] + g['nqs']) * g['nxin'] * g['n']
+                     for g in topo.groups)
+    if P.out_size >= 65536 or P.jac_size >= 65536:
+        return None
+
+    def coo(lst, nrow, ncol):
+        if not lst:
+            return Csr(sp.csr_matrix((nrow, ncol)))
+        r, c, v = zip(*lst)
+        return Csr(sp.coo_matrix((v, (r, c)), shape=(nrow, ncol)), False)
+    P.Dcur = coo(cur, nB, P.out_size)
+    P.Dchg = coo(chg, nB, P.out_size)
+    # Jacobian contributions must stay inside the band
+    W = 2 * band + 1
+    tj = []
+    for r, c_, src, sg in jac:
+        if abs(r - c_) > band:
+            return None
+        tj.append((r * W + (c_ - r + band), src, sg))
+    P.Tjac = coo(tj, nB * W, P.jac_size)
+    # band storage of T0: Tb[r, band + (c - r)]
+    Tb = np.zeros((nB, W))
+    for r in range(nB):
+        for c_ in range(max(0, r - band), min(nB, r + band + 1)):
+            Tb[r, c_ - r + band] = T0[r, c_]
+    P.Tb = Tb
+    return P
