@@ -73,6 +73,15 @@ class RunHost(C.Structure):
                 ('info', _vp)]
 
 
+class SchurHost(C.Structure):
+    """cdn_schur_host (csrc/schur.cu)."""
+    _fields_ = [('ncta', C.c_int), ('nB', C.c_int), ('band', C.c_int),
+                ('blob', _vp), ('cta_off', _vp), ('m', _vp),
+                ('vpos_b', _vp), ('vneg_b', _vp),
+                ('src_own', _vp), ('src_loc', _vp),
+                ('save_ptr', _vp), ('save_k', _vp), ('save_loc', _vp)]
+
+
 OP_NEWTON, OP_TRAN, OP_UPDATE_Q, OP_SET_IC, OP_ACCEPT, OP_RHS, OP_CHORD, \
     OP_GET_I, OP_GET_I_JAC, OP_SOLVE = range(10)
 TEAM_AUTO, TEAM_TILE, TEAM_BLOCK, TEAM_GRID = -1, 0, 1, 2
@@ -116,6 +125,10 @@ def _declare(dll):
     dll.cdn_engine_ws_doubles.restype = C.c_long
     dll.cdn_engine_layout.argtypes = [_vp, C.POINTER(C.c_long)]
     dll.cdn_engine_run.argtypes = [_vp, C.POINTER(RunHost), _vp]
+    dll.cdn_schur_tran.argtypes = [_vp, C.POINTER(RunHost),
+                                   C.POINTER(SchurHost), _vp]
+    dll.cdn_schur_smem_bytes.argtypes = [C.c_long] + [C.c_int] * 6
+    dll.cdn_schur_smem_bytes.restype = C.c_long
 
 
 def load_dll():

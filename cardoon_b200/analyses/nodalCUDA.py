@@ -644,6 +644,9 @@ def plan_array(dll, plan, name):
 # engine wrapper
 # ---------------------------------------------------------------------------
 DENSE_MAX = 64
+# transients of one sparse circuit try the boundary/interior kernel first
+# (analyses/schur.py); tests switch it off to compare the two paths
+SCHUR_ENABLED = True
 
 
 class Engine(object):
@@ -676,6 +679,9 @@ class Engine(object):
         self.dense = dense
         self.team = team
         self.match = None
+        self._ref_stamps = None
+        self._schur = None      # boundary/interior plan: None = not tried yet
+        self.last_path = None   # 'schur' or 'engine': what the last tran() ran on
         if dense:
             self.plan, self.info = create_plan(
                 lib.dll, lib.ctx, topo, use_q, True, check=lib.check,
@@ -683,6 +689,7 @@ class Engine(object):
         else:
             xr = np.zeros(n) if x_ref is None else np.asarray(x_ref)
             stamps = topo.device_stamps(topo.device_jacobians(lib, xr))
+            self._ref_stamps = stamps
             A_ref = reference_matrix(topo, use_q, a0, stamps)
             self.plan, self.info, self.match = sparse_plan(
                 lib.dll, lib.ctx, topo, use_q, A_ref, ordering, lib.check,
@@ -854,6 +861,87 @@ class Engine(object):
             self.sv.copy_(torch.as_tensor(np.ascontiguousarray(sV)))
         self._launch(self._run_struct(op, a0=a0))
 
+    # ---- boundary / interior transient path ---------------------------------
+    SCHUR_CTAS = 8          # CTAs of the cluster (8 is the portable maximum)
+
+    def _schur_plan(self):
+        """Boundary/interior plan (analyses/schur.py) of this engine, built on
+        first use; None when the circuit is not eligible."""
+        if self._schur is not None:
+            return self._schur or None
+        self._schur = False
+        if (self.dense or self.B != 1 or not self.use_q or self.nhist
+                or glVar.errfunc or not SCHUR_ENABLED
+                or self._ref_stamps is None):
+            return None
+        from . import schur
+        lib = self.lib
+        P = schur.analyse(self.topo, self.a0, self.SCHUR_CTAS,
+                          self._ref_stamps)
+        if P is None:
+            return None
+        if (P.out_size != self.info['dev_out']
+                or P.jac_size != self.info['dev_jac']):
+            return None
+        blob, off = schur.pack(P)
+        need = max(lib.dll.cdn_schur_smem_bytes(
+            int(off[k + 1] - off[k]), int(c.m), P.nB, P.band, P.out_size,
+            P.jac_size, P.ncta) for k, c in enumerate(P.ctas))
+        if need > 227 * 1024:
+            return None
+        keep = dict(P=P, schur=schur)
+        keep['blob'] = lib.dev(np.frombuffer(blob, dtype=np.uint8).copy())
+        keep['off'] = np.ascontiguousarray(off, dtype=np.int64)
+        keep['m'] = np.array([c.m for c in P.ctas], dtype=np.int32)
+        ports = [schur.remap_ports(P, g) for g in self.topo.groups]
+        keep['ports'] = [(lib.dev(a), lib.dev(b)) for a, b in ports]
+        ng = len(ports)
+        keep['vp'] = (C.c_void_p * max(1, ng))(
+            *[t[0].data_ptr() for t in keep['ports']])
+        keep['vn'] = (C.c_void_p * max(1, ng))(
+            *[t[1].data_ptr() for t in keep['ports']])
+        self._schur = keep
+        return keep
+
+    def _schur_tran(self, r, var, save_rows, check):
+        """Launch the boundary/interior kernel for the run described by ``r``;
+        False when it asks for the general kernels (status / pivot flag; only
+        looked at if ``check``, which synchronises)."""
+        lib = self.lib
+        k = self._schur
+        P, schur = k['P'], k['schur']
+        key = (np.asarray(var).tobytes(),
+               np.asarray(save_rows, dtype=np.int32).tobytes())
+        if k.get('key') != key:
+            own, loc = schur.locate(P, var) if len(var) else (
+                np.zeros(0, np.int32), np.zeros(0, np.int32))
+            sp, sk, sl = schur.save_lists(P, save_rows)
+            k['maps'] = [lib.dev(a) if len(a) else None for a in (own, loc)] \
+                + [lib.dev(sp), lib.dev(sk) if len(sk) else None,
+                   lib.dev(sl) if len(sl) else None]
+            k['key'] = key
+        dev = k['maps']
+        h = L.SchurHost()
+        h.ncta, h.nB, h.band = P.ncta, P.nB, P.band
+        h.blob = lib.ptr(k['blob'])
+        h.cta_off = k['off'].ctypes.data_as(L._vp)
+        h.m = k['m'].ctypes.data_as(L._vp)
+        h.vpos_b = C.cast(k['vp'], L._vp)
+        h.vneg_b = C.cast(k['vn'], L._vp)
+        h.src_own, h.src_loc = lib.ptr(dev[0]), lib.ptr(dev[1])
+        h.save_ptr, h.save_k, h.save_loc = (lib.ptr(dev[2]), lib.ptr(dev[3]),
+                                            lib.ptr(dev[4]))
+        self._x_keep = self.x.clone()
+        self.hinfo.zero_()
+        lib.check(lib.dll.cdn_schur_tran(self.plan, C.byref(r), C.byref(h),
+                                         lib.stream()))
+        self.launches += 1
+        if not check:
+            return True
+        st = int(self.status[0].item())
+        piv = int(self.hinfo[0, 1].item())
+        return st == 0 and piv == 0
+
     def jacobian_coords(self):
         rows = np.empty(self.info['nlu'], dtype=np.int32)
         cols = np.empty(self.info['nlu'], dtype=np.int32)
@@ -906,7 +994,18 @@ class Engine(object):
         r.src_rows, r.src_val = lib.ptr(self._src[0]), lib.ptr(self._src[1])
         r.src_dc, r.save_rows = lib.ptr(self._src[2]), lib.ptr(self._src[3])
         r.wave, r.iters, r.res = lib.ptr(wave), lib.ptr(iters), lib.ptr(res)
-        self._launch(r)
+        self.last_path = 'engine'
+        if first == 1 and init_ic and self._schur_plan() is not None:
+            # one sparse circuit with few device ports: boundary/interior
+            # kernel on a thread-block cluster (analyses/schur.py); Newton
+            # failures and degraded pivots fall back to the general kernels,
+            # which have the helper chain
+            if self._schur_tran(r, var, save_rows, sync):
+                self.last_path = 'schur'
+            else:
+                self.x.copy_(self._x_keep)
+        if self.last_path == 'engine':
+            self._launch(r)
         if not sync:
             return wave, iters, res, self.status
         return (wave.cpu().numpy(), iters.cpu().numpy(), res.cpu().numpy(),

@@ -349,3 +349,91 @@ def analyse(topo, a0, ncta=8, stamps=None, out_off=None, jac_off=None,
             Tb[r, c_ - r + band] = T0[r, c_]
     P.Tb = Tb
     return P
+
+
+# ---------------------------------------------------------------------------
+# device packaging (layout: csrc/schur.cuh, enums SOP_* / SH_*)
+# ---------------------------------------------------------------------------
+NOPS = 12
+LONG_ROW = 32
+SH_OPS, SH_WORDS = 8, 64
+SH_TB = SH_OPS + 4 * NOPS
+
+
+def pack_blob(P, c):
+    """Operator blob of CTA ``c``: 64 header words, then per operator row
+    pointers (int32), columns (uint16) and values (float64), the band of T0 and
+    the unknown numbers of the interior rows and of the boundary."""
+    ops = [c.Linv, c.Uinv, c.X, c.Asi, c.Csi, c.Arow, c.Crow, P.Abb, P.Cbb,
+           P.Dcur, P.Dchg, P.Tjac]
+    hdr = np.zeros(SH_WORDS, dtype=np.int32)
+    hdr[0:6] = (c.m, P.nB, P.band, P.out_size, P.jac_size, int(P.has_csi))
+    parts = [None]
+    pos = [SH_WORDS * 4]
+
+    def put(arr):
+        b = np.ascontiguousarray(arr).tobytes()
+        pad = (-len(b)) % 8
+        off = pos[0]
+        parts.append(b + b'\0' * pad)
+        pos[0] += len(b) + pad
+        return off
+    for k, op in enumerate(ops):
+        hdr[SH_OPS + 4 * k] = op.shape[0]
+        hdr[SH_OPS + 4 * k + 1] = put(op.ptr.astype(np.int32))
+        hdr[SH_OPS + 4 * k + 2] = put(op.col.astype(np.uint16))
+        hdr[SH_OPS + 4 * k + 3] = put(op.val.astype(np.float64))
+    hdr[SH_TB] = put(P.Tb.astype(np.float64).ravel())
+    hdr[SH_TB + 1] = put(c.Ic.astype(np.int32))
+    hdr[SH_TB + 2] = put(P.B.astype(np.int32))
+    # rows of Linv a warp sums together (csrc/schur.cuh CDN_SCHUR_LONG)
+    llong = np.nonzero(np.diff(c.Linv.ptr) > LONG_ROW)[0].astype(np.int32)
+    hdr[6] = put(llong)
+    hdr[7] = len(llong)
+    pad = (-pos[0]) % 16
+    parts.append(b'\0' * pad)
+    pos[0] += pad
+    hdr[SH_TB + 3] = pos[0]
+    parts[0] = hdr.tobytes()
+    return b''.join(parts)
+
+
+def pack(P):
+    """All CTA blobs back to back: (bytes, offsets[ncta + 1])."""
+    blobs = [pack_blob(P, c) for c in P.ctas]
+    off = np.zeros(len(blobs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(b) for b in blobs])
+    return b''.join(blobs), off
+
+
+def locate(P, rows):
+    """Owner CTA (-1: boundary) and position in the owner's local vector
+    [x_B | x_Ic] of the unknowns ``rows``."""
+    own = np.full(P.n, -1, dtype=np.int32)
+    loc = np.zeros(P.n, dtype=np.int32)
+    loc[P.B] = np.arange(P.nB)
+    for k, c in enumerate(P.ctas):
+        own[c.Ic] = k
+        loc[c.Ic] = P.nB + np.arange(c.m)
+    rows = np.asarray(rows, dtype=np.int64)
+    return own[rows], loc[rows]
+
+
+def save_lists(P, save_rows):
+    """Per CTA the columns of ``wave`` it writes and where it finds them
+    (boundary unknowns are written by CTA 0)."""
+    own, loc = locate(P, save_rows)
+    own = np.where(own < 0, 0, own)
+    order = np.argsort(own, kind='stable')
+    ptr = np.zeros(P.ncta + 1, dtype=np.int32)
+    ptr[1:] = np.cumsum(np.bincount(own, minlength=P.ncta))
+    return ptr, order.astype(np.int32), loc[order].astype(np.int32)
+
+
+def remap_ports(P, g):
+    """Control-port rows of group ``g`` as boundary positions."""
+    def m(a):
+        a = np.asarray(a, dtype=np.int64)
+        return np.ascontiguousarray(
+            np.where(a >= 0, P.bpos[np.maximum(a, 0)], -1).astype(np.int32))
+    return m(g['vpos']), m(g['vneg'])

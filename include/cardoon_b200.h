@@ -243,6 +243,40 @@ long cdn_engine_ws_doubles(cdn_plan* plan);
 int cdn_engine_layout(cdn_plan* plan, long* off);
 int cdn_engine_run(cdn_plan* plan, const cdn_run_host* run, void* stream);
 
+/* ---- boundary / interior transient engine (one sparse circuit on a thread-
+ * block cluster) ------------------------------------------------------------------
+ * Replaces, for circuits whose nonlinear devices touch few unknowns, the
+ * refactor-everything-per-iteration time loop of the sparse back-end
+ * (cardoon/analyses/tran.py:171-206 over nodalSP.py:281-354, :666-887): the
+ * linear interior is solved with precomputed inverse factors, only the banded
+ * boundary system on the device ports is assembled and factored per Newton
+ * iteration.  The operator blobs come from cardoon_b200/analyses/schur.py
+ * (pack_blob); `run` is the same structure cdn_engine_run takes (op
+ * CDN_OP_TRAN, B = 1, first = 1, init_ic = 1; src_rows is replaced by
+ * src_own / src_loc, save_rows by save_ptr / save_k / save_loc).  status[0] != 0
+ * (Newton failed at that sample: the helper chain is not available here) or
+ * info[1] != 0 (a pivot of the boundary system degraded) tell the caller to
+ * run cdn_engine_run instead.                                                  */
+typedef struct cdn_schur_host {
+    int ncta;                 /* CTAs of the cluster (1..16)                       */
+    int nB, band;             /* boundary unknowns, half bandwidth of T            */
+    const void* blob;         /* device: per-CTA operator blobs                    */
+    const long* cta_off;      /* host [ncta + 1]: byte offsets into blob           */
+    const int* m;             /* host [ncta]: interior unknowns per CTA            */
+    const int* const* vpos_b; /* host [ngroups] of device [nxin][n]: control-port
+                                 rows as boundary positions (-1 ground)            */
+    const int* const* vneg_b;
+    const int* src_own;       /* device [nsrc]: owner CTA of a source row (-1: B)  */
+    const int* src_loc;       /* device [nsrc]: position in the local vector       */
+    const int* save_ptr;      /* device [ncta + 1]                                 */
+    const int* save_k;        /* device: column of wave                            */
+    const int* save_loc;      /* device: position in the CTA's local vector        */
+} cdn_schur_host;
+long cdn_schur_smem_bytes(long blob_bytes, int m, int nB, int band, int nout,
+                          int njac, int ncta);
+int cdn_schur_tran(cdn_plan* plan, const cdn_run_host* run,
+                   const cdn_schur_host* s, void* stream);
+
 /* tuning knobs for experiments (key 0: resident CTAs per SM the BSIM3
  * evaluation kernel is register-limited for; 0 = default)                    */
 int cdn_set_tuning(int key, int value);

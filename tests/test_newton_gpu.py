@@ -117,12 +117,26 @@ def test_tran_ring_bsim3(lib):
 
 def test_tran_soliton(lib):
     """BASELINE config 2: N = 3022 sparse, 47 diodes, 500 samples
-    (block team, level-scheduled static-pivot LU)."""
+    (thread-block cluster, boundary/interior kernel of csrc/schur.cuh)."""
     wave, iters, status, ref, tran = tran_both('soliton.net')
     assert wave.shape[1] == 3022 and wave.shape[0] in (500, 501)
     check_tran(wave, iters, status, ref)
     assert tran.engine.launches == 1
     assert not tran.engine.dense
+    assert tran.engine.last_path == 'schur'
+    # ~1 Newton iteration per step thanks to the chord predictor
+    # (reference doc/design.rst:243-256: 505 solves for 501 steps)
+    assert iters.sum() < 1.2 * len(iters)
+
+
+def test_tran_soliton_general_kernel(lib, monkeypatch):
+    """Same run on the general sparse path (block team, level-scheduled
+    static-pivot LU), which the boundary/interior kernel falls back to."""
+    monkeypatch.setattr(nd, 'SCHUR_ENABLED', False)
+    wave, iters, status, ref, tran = tran_both('soliton.net')
+    check_tran(wave, iters, status, ref)
+    assert tran.engine.launches == 1
+    assert tran.engine.last_path == 'engine'
     # ~1 Newton iteration per step thanks to the chord predictor
     # (reference doc/design.rst:243-256: 505 solves for 501 steps)
     assert iters.sum() < 1.2 * len(iters)
