@@ -82,16 +82,29 @@ __device__ __forceinline__ SOp sop_get(const unsigned char* blob, int k) {
     return o;
 }
 
+// one row: eight entries in flight (index and value loads, then the gathers,
+// then four independent accumulators) -- every one of these is a shared-memory
+// or FP64 latency, and a row is short
 __device__ __forceinline__ double sop_row(const SOp& op, int r, const double* in) {
     const int a = op.ptr[r], b = op.ptr[r + 1];
-    double s0 = 0.0, s1 = 0.0;
-    int k = a;
-    for (; k + 1 < b; k += 2) {
-        s0 = fma(op.val[k], in[op.col[k]], s0);
-        s1 = fma(op.val[k + 1], in[op.col[k + 1]], s1);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int k = a; k < b; k += 8) {
+        int c[8];
+        double v[8], x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool ok = k + j < b;
+            c[j] = ok ? (int)op.col[k + j] : 0;
+            v[j] = ok ? op.val[k + j] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = in[c[j]];
+        s0 = fma(v[0], x[0], s0); s1 = fma(v[1], x[1], s1);
+        s2 = fma(v[2], x[2], s2); s3 = fma(v[3], x[3], s3);
+        s0 = fma(v[4], x[4], s0); s1 = fma(v[5], x[5], s1);
+        s2 = fma(v[6], x[6], s2); s3 = fma(v[7], x[7], s3);
     }
-    if (k < b) s0 = fma(op.val[k], in[op.col[k]], s0);
-    return s0 + s1;
+    return (s0 + s1) + (s2 + s3);
 }
 
 // per-CTA state in shared memory
@@ -107,11 +120,15 @@ __host__ __device__ inline long schur_vec_doubles(int m, int nB, int band, int n
                                                   int ncta) {
     const int W = 2 * band + 1, MB = 2 * nB + 2;
     return (long)(nB + m) + 8L * m + 8L * nB + MB + (long)nB * W + nB + nout + njac +
-           2L * ncta * MB + 64;
+           2L * ncta * MB + 64 + 5 * W + 8;
 }
 
 
 // ---- boundary system: band LU without pivoting, one thread ---------------------------
+// (a single warp issues these loops, so what counts is the number of
+// instructions per row: the band storage is padded with BAND + 1 identity rows
+// and zero right-hand sides, positions outside the matrix hold zeros, and no
+// access needs a guard)
 // T is stored by rows, Tf[r * W + BAND + (c - r)], W = 2 BAND + 1.  The rows and
 // right-hand side entries the elimination is working on sit in registers (a
 // sliding (BAND+1) x (BAND+1) window), so that the chain of dependent
@@ -127,10 +144,10 @@ __device__ __forceinline__ int band_factor_solve(double* Tf, double* rB, double*
     for (int i = 0; i <= BAND; ++i) {
 #pragma unroll
         for (int j = 0; j <= BAND; ++j)
-            win[i][j] = (i < nB && j < nB) ? Tf[i * W + BAND + (j - i)] : 0.0;
-        y[i] = (i < nB) ? rB[i] : 0.0;
+            win[i][j] = Tf[i * W + BAND + (j - i)];
+        y[i] = rB[i];
     }
-#pragma unroll 2
+#pragma unroll 4
     for (int k = 0; k < nB; ++k) {
         // entries entering the window after this step (untouched so far)
         double ncol[BAND + 1], nrow[BAND + 1], ny;
@@ -138,24 +155,24 @@ __device__ __forceinline__ int band_factor_solve(double* Tf, double* rB, double*
 #pragma unroll
         for (int i = 0; i <= BAND; ++i) {
             const int r = k + 1 + i;
-            ncol[i] = (r < nB && q < nB) ? Tf[r * W + BAND + (q - r)] : 0.0;
-            nrow[i] = (q < nB) ? Tf[q * W + i] : 0.0;      // columns k+1+i, i < BAND
+            ncol[i] = Tf[r * W + BAND + (q - r)];
+            nrow[i] = Tf[q * W + i];                       // columns k+1+i, i < BAND
         }
-        ny = (q < nB) ? rB[q] : 0.0;
+        ny = rB[q];
         const double piv = win[0][0];
         const double pinv = cdn_rcp(piv);
         if (!(fabs(piv) > 0.0) || !isfinite(pinv)) bad = 1;
         Dinv[k] = pinv;
 #pragma unroll
         for (int j = 1; j <= BAND; ++j)
-            if (k + j < nB) Tf[k * W + BAND + j] = win[0][j];
+            Tf[k * W + BAND + j] = win[0][j];
         Tf[k * W + BAND] = piv;
         rB[k] = y[0];
 #pragma unroll
         for (int i = 1; i <= BAND; ++i) {
             const double mlt = win[i][0] * pinv;
             if (fabs(mlt) > CDN_MULT_LIMIT) bad = 1;
-            if (k + i < nB) Tf[(k + i) * W + BAND - i] = mlt;
+            Tf[(k + i) * W + BAND - i] = mlt;
 #pragma unroll
             for (int j = 1; j <= BAND; ++j) win[i][j] = fma(-mlt, win[0][j], win[i][j]);
             y[i] = fma(-mlt, y[0], y[i]);
@@ -182,7 +199,7 @@ __device__ __forceinline__ int band_factor_solve(double* Tf, double* rB, double*
         double sacc = rB[i];
 #pragma unroll
         for (int j = 1; j <= BAND; ++j) {
-            const double u = (i + j < nB) ? Tf[i * W + BAND + j] : 0.0;
+            const double u = Tf[i * W + BAND + j];
             sacc = fma(-u, xr[j - 1], sacc);
         }
         const double xv = sacc * Dinv[i];
@@ -194,7 +211,11 @@ __device__ __forceinline__ int band_factor_solve(double* Tf, double* rB, double*
     return bad;
 }
 
-// dx_B from r_B with stored factors
+// dx_B from r_B with stored factors.  The term with the newest solution entry
+// is added last, and the backward sweep multiplies by the reciprocal pivot
+// before that: one dependent operation per row on either sweep.
+// dx_B from r_B with stored factors; the term with the newest solution entry is
+// added last: one dependent operation per row on either sweep
 template <int BAND>
 __device__ __forceinline__ void band_resolve(const double* Tf, const double* rB, const double* Dinv,
                                              double* dB, int nB) {
@@ -206,8 +227,8 @@ __device__ __forceinline__ void band_resolve(const double* Tf, const double* rB,
     for (int i = 0; i < nB; ++i) {
         double sacc = rB[i];
 #pragma unroll
-        for (int j = 1; j <= BAND; ++j) {
-            const double l = (i - j >= 0) ? Tf[i * W + BAND - j] : 0.0;
+        for (int j = BAND; j >= 1; --j) {
+            const double l = Tf[i * W + BAND - j];
             sacc = fma(-l, yr[j - 1], sacc);
         }
         dB[i] = sacc;
@@ -219,13 +240,18 @@ __device__ __forceinline__ void band_resolve(const double* Tf, const double* rB,
     for (int j = 0; j <= BAND; ++j) yr[j] = 0.0;
 #pragma unroll 4
     for (int i = nB - 1; i >= 0; --i) {
+        const double dinv = Dinv[i];
         double sacc = dB[i];
 #pragma unroll
-        for (int j = 1; j <= BAND; ++j) {
-            const double u = (i + j < nB) ? Tf[i * W + BAND + j] : 0.0;
+        for (int j = BAND; j >= 2; --j) {
+            const double u = Tf[i * W + BAND + j];
             sacc = fma(-u, yr[j - 1], sacc);
         }
-        const double xv = sacc * Dinv[i];
+        double xv = sacc * dinv;
+        if (BAND >= 1) {
+            const double u1 = Tf[i * W + BAND + 1];
+            xv = fma(-(u1 * dinv), yr[0], xv);
+        }
         dB[i] = xv;
 #pragma unroll
         for (int j = BAND; j > 0; --j) yr[j] = yr[j - 1];
@@ -272,9 +298,9 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
         s.ivI = p; p += m; s.svI = p; p += m; s.qI = p; p += m; s.qpI = p; p += m;
         s.dqI = p; p += m; s.uI = p; p += m; s.tI = p; p += m; s.srcI = p; p += m;
         s.ivB = p; p += nB; s.svB = p; p += nB; s.qB = p; p += nB; s.qpB = p; p += nB;
-        s.dqB = p; p += nB; s.rB = p; p += nB; s.dB = p; p += nB; s.srcB = p; p += nB;
+        s.dqB = p; p += nB; s.rB = p; p += nB + 8; s.dB = p; p += nB; s.srcB = p; p += nB;
         s.snd = p; p += MB;
-        s.Tf = p; p += nB * W; s.Dinv = p; p += nB;
+        s.Tf = p; p += (nB + 5) * W; s.Dinv = p; p += nB;
         s.out = p; p += s.nout; s.jac = p; p += s.njac;
         s.red = p; p += 64;
     }
@@ -314,8 +340,26 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
         s.srcI[r] = A.src_dc ? __ldg(A.src_dc + Ic[r]) : 0.0;
         s.ivI[r] = 0.0;
     }
+    for (int e = tid; e < 5 * W; e += TPB) s.Tf[nB * W + e] = (e % W == band) ? 1.0 : 0.0;
+    if (tid < 8) s.rB[nB + tid] = 0.0;
     __syncthreads();
     int xc = 0;      // exchange counter (parity of the mailbox in use)
+
+    // Warp roles: the device sweep (a chain of dependent FP64 operations per
+    // device, few threads) runs on the last warps of the CTA while the others do
+    // the interior work of the same phase, which never needs device outputs
+    // (interior rows carry no device stamps).  The workers meet at named barrier
+    // 1, everybody at barrier 0.
+    int evw = (A.ndev + 31) / 32;
+    if (evw * 64 > TPB) evw = 0;                         // too many devices: no split
+    const int NWK = TPB - 32 * evw;                      // worker threads
+    const bool is_worker = tid < NWK;
+    const int etid = tid - NWK;                          // rank among the sweep threads
+    const int ENT = evw ? 32 * evw : TPB;
+    auto wbar = [&]() {
+        if (evw) asm volatile("bar.sync 1, %0;" ::"r"(NWK) : "memory");
+        else __syncthreads();
+    };
 
     // all CTAs: mail[par][src][0 .. count) <- snd[0 .. count) of CTA src
     auto exchange = [&](int count) {
@@ -331,29 +375,13 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
         cluster.sync();
         return s.mail + (long)par * ncta * MB;
     };
-    auto eval = [&](bool deriv) {
-        for (int d = tid; d < A.ndev; d += TPB) {
+    // device sweep by the sweep warps (by everybody without the split)
+    auto sweep = [&](bool deriv) {
+        for (int d = (evw ? etid : tid); d < A.ndev; d += ENT) {
             const cdn_group_dev& G = A.groups[__ldg(A.dev_g + d)];
             if (deriv) eval_one<MS, true>(G, 0, __ldg(A.dev_i + d), xB, w, 0, o.h, 0, a0);
             else eval_one<MS, false>(G, 0, __ldg(A.dev_i + d), xB, w, 0, o.h, 0, 1.0);
         }
-        __syncthreads();
-    };
-    // q = C x + Tq q(x) (nodalSP.py:719-733); device outputs must be current
-    auto charge = [&]() {
-        for (int r = tid; r < m; r += TPB) s.qI[r] = sop_row(oCrow, r, s.xloc);
-        const double* mb = nullptr;
-        if (s.has_csi) {
-            for (int j = tid; j < nB; j += TPB) s.snd[j] = sop_row(oCsi, j, xI);
-            mb = exchange(nB);
-        }
-        for (int j = tid; j < nB; j += TPB) {
-            double q = sop_row(oCbb, j, xB) + sop_row(oDchg, j, s.out);
-            if (mb)
-                for (int c = 0; c < ncta; ++c) q += mb[c * MB + j];
-            s.qB[j] = q;
-        }
-        __syncthreads();
     };
     // dx_B from r_B with the stored factors (one thread; band is 0..4)
     auto band_solve = [&]() {
@@ -368,81 +396,125 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
         }
         __syncthreads();
     };
-    // interior part of a solve: t_I = Uinv Linv y_I (y_I in uI on entry is overwritten)
-    // (the rows of Linv that belong to the top separators of a piece are long --
-    // they depend on the whole piece -- and are summed by a warp each)
+    // workers: t_I = Uinv Linv y_I (the rows of Linv that belong to the top
+    // separators of a piece are long -- they depend on the whole piece -- and are
+    // summed by a warp each)
     auto interior_solve = [&](const double* yI) {
-        for (int q = tid >> 5; q < nlong; q += TPB / 32) {
+        wbar();
+        for (int q = tid >> 5; q < nlong; q += NWK / 32) {
             const int r = llong[q];
             const int a = oLinv.ptr[r], b = oLinv.ptr[r + 1];
-            double acc = 0.0;
-            for (int k = a + (tid & 31); k < b; k += 32) acc = fma(oLinv.val[k], yI[oLinv.col[k]], acc);
+            double acc = 0.0, acc2 = 0.0;
+            for (int k = a + (tid & 31); k < b; k += 64) {
+                const bool ok2 = k + 32 < b;
+                const int c1 = oLinv.col[k], c2 = ok2 ? (int)oLinv.col[k + 32] : 0;
+                const double v1 = oLinv.val[k], v2 = ok2 ? oLinv.val[k + 32] : 0.0;
+                acc = fma(v1, yI[c1], acc);
+                acc2 = fma(v2, yI[c2], acc2);
+            }
+            acc += acc2;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
             if ((tid & 31) == 0) s.uI[r] = acc;
         }
-        for (int r = tid; r < m; r += TPB)
+        for (int r = tid; r < m; r += NWK)
             if (oLinv.ptr[r + 1] - oLinv.ptr[r] <= CDN_SCHUR_LONG) s.uI[r] = sop_row(oLinv, r, yI);
-        __syncthreads();
-        for (int r = tid; r < m; r += TPB) s.tI[r] = sop_row(oUinv, r, s.uI);
-        __syncthreads();
+        wbar();
+        for (int r = tid; r < m; r += NWK) s.tI[r] = sop_row(oUinv, r, s.uI);
+        wbar();
+    };
+    // time-varying sources of sample i on the rows this thread just wrote
+    auto add_sources_I = [&](int i, int r, double f) {
+        for (int k = 0; k < A.nsrc; ++k)
+            if (__ldg(A.src_own + k) == rank && __ldg(A.src_loc + k) - nB == r)
+                f += __ldg(A.src_val + (long)i * A.nsrc + k);
+        return f;
+    };
+    auto add_sources_B = [&](int i, int j, double f) {
+        for (int k = 0; k < A.nsrc; ++k)
+            if (__ldg(A.src_own + k) < 0 && __ldg(A.src_loc + k) == j)
+                f += __ldg(A.src_val + (long)i * A.nsrc + k);
+        return f;
     };
 
     // ---- set_IC (nodalSP.py:666-696), integration.py init ------------------------------
-    eval(false);
-    charge();
-    for (int r = tid; r < m; r += TPB) { s.qpI[r] = s.qI[r]; s.dqI[r] = 0.0; }
-    for (int j = tid; j < nB; j += TPB) { s.qpB[j] = s.qB[j]; s.dqB[j] = 0.0; }
-    __syncthreads();
+    // q = C x + Tq q(x) (nodalSP.py:719-733)
+    if (!evw || !is_worker) sweep(false);
+    if (!evw || is_worker) {
+        for (int r = tid; r < m; r += NWK) { s.qpI[r] = sop_row(oCrow, r, s.xloc); s.dqI[r] = 0.0; }
+        if (s.has_csi)
+            for (int j = tid; j < nB; j += NWK) s.snd[j] = sop_row(oCsi, j, xI);
+    }
+    {
+        const double* mb = nullptr;
+        if (s.has_csi) mb = exchange(nB);
+        else __syncthreads();
+        for (int j = tid; j < nB; j += TPB) {
+            double q = sop_row(oCbb, j, xB) + sop_row(oDchg, j, s.out);
+            if (mb)
+                for (int c = 0; c < ncta; ++c) q += mb[c * MB + j];
+            s.qpB[j] = q;
+            s.dqB[j] = 0.0;
+        }
+        __syncthreads();
+    }
 
     int status = 0, piv_at = 0;
     for (int i = 1; i < A.nsamples; ++i) {
         SCH_T0;
-        // ---- accept(xOld) + rhs (nodalSP.py:735-802, integration.py:36-49, :83-97) -----
-        eval(false);
-        charge();
-        for (int r = tid; r < m; r += TPB) {
-            const double q = s.qI[r];
-            double dq = s.dqI[r];
-            if (trap) { dq = -dq + a0 * (q - s.qpI[r]); s.dqI[r] = dq; }
-            s.qpI[r] = q;
-            double f = a0 * q;
-            if (trap) f += dq;
-            s.svI[r] = f + s.srcI[r];
-        }
-        for (int j = tid; j < nB; j += TPB) {
-            const double q = s.qB[j];
-            double dq = s.dqB[j];
-            if (trap) { dq = -dq + a0 * (q - s.qpB[j]); s.dqB[j] = dq; }
-            s.qpB[j] = q;
-            double f = a0 * q;
-            if (trap) f += dq;
-            s.svB[j] = f + s.srcB[j];
-        }
-        __syncthreads();
-        if (tid == 0)
-            for (int k = 0; k < A.nsrc; ++k) {
-                const int own = __ldg(A.src_own + k), loc = __ldg(A.src_loc + k);
-                const double v = __ldg(A.src_val + (long)i * A.nsrc + k);
-                if (own < 0) s.svB[loc] += v;
-                else if (own == rank) s.svI[loc - nB] += v;
+        // ---- accept(xOld) + rhs (nodalSP.py:735-802, integration.py:36-49, :83-97) and the
+        // interior part of the chord predictor (tran.py:181: last factors, last residual);
+        // the values-only device sweep runs beside them
+        const bool chord = i > 1;
+        if (!evw || !is_worker) sweep(false);
+        if (!evw || is_worker) {
+            for (int r = tid; r < m; r += NWK) {
+                const double q = sop_row(oCrow, r, s.xloc);
+                double dq = s.dqI[r];
+                if (trap) { dq = -dq + a0 * (q - s.qpI[r]); s.dqI[r] = dq; }
+                s.qpI[r] = q;
+                double f = a0 * q;
+                if (trap) f += dq;
+                f = add_sources_I(i, r, f + s.srcI[r]);
+                s.svI[r] = f;
+                s.qI[r] = f - s.ivI[r];                  // y_I of the chord step
             }
-        __syncthreads();
-        SCH_P(5);
-        // ---- chord predictor (tran.py:181): last factors, last residual ----------------
-        if (i > 1) {
-            for (int r = tid; r < m; r += TPB) s.qI[r] = s.svI[r] - s.ivI[r];   // (qI is free)
-            __syncthreads();
-            interior_solve(s.qI);
-            for (int j = tid; j < nB; j += TPB) s.snd[j] = sop_row(oAsi, j, s.tI);
-            const double* mb = exchange(nB);
+            if (chord) {
+                interior_solve(s.qI);
+                for (int j = tid; j < nB; j += NWK) s.snd[j] = sop_row(oAsi, j, s.tI);
+            }
+            if (s.has_csi)
+                for (int j = tid; j < nB; j += NWK) s.snd[nB + j] = sop_row(oCsi, j, xI);
+        }
+        SCH_P(8);
+        {
+            const double* mb = nullptr;
+            if (chord || s.has_csi) mb = exchange(2 * nB);
+            else __syncthreads();
+            SCH_P(9);
             for (int j = tid; j < nB; j += TPB) {
-                double r = s.svB[j] - s.ivB[j];
-                for (int c = 0; c < ncta; ++c) r -= mb[c * MB + j];
-                s.rB[j] = r;
+                double q = sop_row(oCbb, j, xB) + sop_row(oDchg, j, s.out);
+                if (s.has_csi)
+                    for (int c = 0; c < ncta; ++c) q += mb[c * MB + nB + j];
+                double dq = s.dqB[j];
+                if (trap) { dq = -dq + a0 * (q - s.qpB[j]); s.dqB[j] = dq; }
+                s.qpB[j] = q;
+                double f = a0 * q;
+                if (trap) f += dq;
+                f = add_sources_B(i, j, f + s.srcB[j]);
+                s.svB[j] = f;
+                if (chord) {
+                    double r = f - s.ivB[j];
+                    for (int c = 0; c < ncta; ++c) r -= mb[c * MB + j];
+                    s.rB[j] = r;
+                }
             }
             __syncthreads();
+        }
+        SCH_P(5);
+        if (chord) {
             band_solve();
+            SCH_P(10);
             for (int r = tid; r < m; r += TPB) xI[r] += s.tI[r] - sop_row(oX, r, s.dB);
             for (int j = tid; j < nB; j += TPB) xB[j] += s.dB[j];
             __syncthreads();
@@ -454,18 +526,19 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
         double res = 0.0;
         while (it < o.maxiter) {
             SCH_T0;
-            eval(true);
-            SCH_P(0);
-            for (int r = tid; r < m; r += TPB) {
-                const double v = sop_row(oArow, r, s.xloc);
-                s.ivI[r] = v;
-                s.qI[r] = s.svI[r] - v;
-            }
-            __syncthreads();
-            interior_solve(s.qI);
-            for (int j = tid; j < nB; j += TPB) {
-                s.snd[j] = sop_row(oAsi, j, xI);
-                s.snd[nB + j] = sop_row(oAsi, j, s.tI);
+            // device sweep with derivatives beside the interior residual and solve
+            if (!evw || !is_worker) sweep(true);
+            if (!evw || is_worker) {
+                for (int r = tid; r < m; r += NWK) {
+                    const double v = sop_row(oArow, r, s.xloc);
+                    s.ivI[r] = v;
+                    s.qI[r] = s.svI[r] - v;
+                }
+                interior_solve(s.qI);
+                for (int j = tid; j < nB; j += NWK) {
+                    s.snd[j] = sop_row(oAsi, j, xI);
+                    s.snd[nB + j] = sop_row(oAsi, j, s.tI);
+                }
             }
             SCH_P(1);
             const double* mb = exchange(2 * nB);
@@ -480,6 +553,7 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
             }
             for (int e = tid; e < nB * W; e += TPB) s.Tf[e] = Tb[e] + sop_row(oTjac, e, s.jac);
             __syncthreads();
+            SCH_P(11);
             // banded LU without pivoting, right-hand side carried along
             if (tid == 0) {
                 int bad;
@@ -524,6 +598,7 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
             }
             SCH_P(3);
             const double* mb2 = exchange(2);
+            SCH_P(12);
             double mg = 0.0;
             bool cg_ = true;
             for (int c = 0; c < ncta; ++c) {
@@ -591,8 +666,9 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
 
 template <int MS>
 static cudaError_t launch_schur(const cdn_schur_args& A, long smem, cudaStream_t st) {
-    // light model sets: one thread per interior row of a typical piece
-    constexpr int TPB = (MS == CDN_MS(CDN_MODEL_DIODE)) ? 384 : 256;
+    // light model sets: one thread per interior row of a typical piece plus the
+    // warps of the device sweep
+    constexpr int TPB = (MS == CDN_MS(CDN_MODEL_DIODE)) ? 512 : 256;
     auto kern = engine_schur_kernel<MS, TPB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

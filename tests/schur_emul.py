@@ -160,3 +160,4 @@ class SchurEmul(object):
                 return X[:i], iters[:i], resv[:i]
             X[i] = self._full_x()
         return X, iters, resv
+

@@ -26,6 +26,18 @@ print('ms', t0.elapsed_time(t1), 'steps', len(timeVec), 'info', e.info)
 for k, v in c.items():
     print('%-14s %12d cycles  %6.2f us/step' % (k, v, v / 1.965e3 / (len(timeVec) - 1)))
 print('sum main', tot / 1.965e3 / (len(timeVec) - 1), 'us/step')
+if e.last_path == 'schur':
+    names = ['-', 'newton: rows + interior solve | device sweep', 'boundary factor+solve',
+             'X dx + max', 'update', 'accept: boundary rows', 'chord: x update',
+             'exchange 1 (newton)', 'accept + chord interior | device sweep',
+             'accept/chord: exchange', 'chord: boundary resolve', 'boundary assembly',
+             'exchange 2 (newton)']
+    tot = 0
+    for k, nm in enumerate(names):
+        print('%-48s %8.2f us/step' % (nm, raw[k] / 1.965e3 / (len(timeVec) - 1)))
+        tot += raw[k]
+    print('sum', tot / 1.965e3 / (len(timeVec) - 1), 'us/step')
+    sys.exit(0)
 # cycles per level of the staged L / U sweeps (slots 16.., 48..), per sweep
 nsweep = 2 * (len(timeVec) - 1) - 1
 print('L levels:', ' '.join('%d' % (v / nsweep) for v in raw[16:16 + e.info['nlev_l']]))
