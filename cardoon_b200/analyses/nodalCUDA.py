@@ -816,13 +816,21 @@ class Engine(object):
               'accept_rhs', 'chord', 'spare', 'stage_L', 'permute_rhs',
               'levels_L', 'stage_U', 'levels_U', 'scatter_dx')
 
+    # timers of the boundary/interior kernel (csrc/schur.cuh SCH_P slots)
+    SCHUR_PHASES = ('unused', 'newton_rows_interior_solve', 'boundary_lu',
+                    'interior_update_max', 'update', 'accept_boundary_rows',
+                    'chord_update', 'newton_exchange', 'accept_chord_interior',
+                    'accept_chord_exchange', 'chord_boundary_resolve',
+                    'boundary_assembly', 'convergence_exchange')
+
     def phase_cycles(self, reset=True):
         """SM cycles instance 0 spent per phase since the last reset (set
         ``engine.profile = True`` before launching)."""
         c = self.prof.cpu().numpy()
         if reset:
             self.prof.zero_()
-        return dict(zip(self.PHASES, (int(v) for v in c)))
+        names = self.SCHUR_PHASES if self.last_path == 'schur' else self.PHASES
+        return dict(zip(names, (int(v) for v in c)))
 
     def last_team(self):
         """Thread team of the last launch: 'tile', 'block' or 'grid'."""
@@ -951,14 +959,15 @@ class Engine(object):
         return rows, cols
 
     def tran(self, x0, src, save_rows, im='trap', first=1, init_ic=True,
-             wave=None, iters=None, res=None, sync=True):
+             wave=None, iters=None, res=None, sync=True, reuse_src=False):
         """Whole fixed-step time loop on the device (tran.py:171-206).
 
         ``x0``: operating point [n] or [B, n] (None: keep self.x);
         ``src``: source vectors [nsamples, n] (tran.get_source(t_i));
         ``save_rows``: unknowns to record.  Returns (wave[B, nsamples, nsave],
         iters[B, nsamples], res[B, nsamples], status[B]) as device tensors
-        (numpy if ``sync``).
+        (numpy if ``sync``).  ``reuse_src``: ``src`` and ``save_rows`` are the
+        arrays of the previous call and their device copies are kept.
         """
         lib = self.lib
         torch = lib.torch
@@ -968,13 +977,19 @@ class Engine(object):
             self.x.copy_(torch.as_tensor(np.broadcast_to(
                 x0, (self.B, self.n)).copy()))
         # constant rows go to src_dc, time-varying rows to a compact table
-        var = np.nonzero(np.any(src != src[0], axis=0))[0].astype(np.int32)
-        dc = src[0].copy()
-        dc[var] = 0.
-        self._src = (lib.dev(var) if len(var) else None,
-                     lib.dev(np.ascontiguousarray(src[:, var]))
-                     if len(var) else None, lib.dev(dc),
-                     lib.dev(np.asarray(save_rows, dtype=np.int32)))
+        if reuse_src and getattr(self, '_src_key', None) == (id(src),
+                                                             src.shape):
+            var = self._src_var
+        else:
+            var = np.nonzero(np.any(src != src[0], axis=0))[0].astype(np.int32)
+            dc = src[0].copy()
+            dc[var] = 0.
+            self._src = (lib.dev(var) if len(var) else None,
+                         lib.dev(np.ascontiguousarray(src[:, var]))
+                         if len(var) else None, lib.dev(dc),
+                         lib.dev(np.asarray(save_rows, dtype=np.int32)))
+            self._src_var = var
+            self._src_key = (id(src), src.shape)
         nsave = len(save_rows)
         if wave is None:
             wave = torch.zeros((self.B, nsamples, nsave),

@@ -142,6 +142,74 @@ def test_tran_soliton_general_kernel(lib, monkeypatch):
     assert iters.sum() < 1.2 * len(iters)
 
 
+def ladder_deck(nsec=150, every=25, im='trap', tstep='2p'):
+    """Synthetic deck for the boundary/interior kernel: an RC ladder with a
+    series inductor now and then and diode clamps every ``every`` sections
+    (the diodes have series resistance and junction capacitance, so each adds
+    an internal node)."""
+    import tempfile
+    lines = ['# RC ladder with diode clamps (synthetic)',
+             '.options sparse=1',
+             '.analysis tran tstop=0.6n tstep={0} im={1} verbose=0'.format(
+                 tstep, im),
+             'ipulse:iin gnd n0 i1=0 i2=40mA pw=.2n per=1n tr=50p tf=50p '
+             'td=20p',
+             'res:rin n0 gnd r=50.']
+    for k in range(nsec):
+        if k % 10 == 5:
+            lines.append('ind:l{0} n{0} n{1} l=20p'.format(k, k + 1))
+        else:
+            lines.append('res:r{0} n{0} n{1} r=2.'.format(k, k + 1))
+        lines.append('cap:c{0} n{1} gnd c=20f'.format(k, k + 1))
+        if k % 7 == 3:
+            # capacitive coupling across a section (C[B, I] != 0 next to a clamp)
+            lines.append('cap:cc{0} n{0} n{1} c=5f'.format(k, k + 1))
+        if k % every == every - 1:
+            lines.append('diode:d{0} n{1} gnd isat=1e-14 rs=10. cj0=30f '
+                         'tt=1p'.format(k, k + 1))
+    lines += ['res:rl n{0} gnd r=50.'.format(nsec), '.end', '']
+    fd, path = tempfile.mkstemp(suffix='.net', prefix='ladder_')
+    os.close(fd)
+    with open(path, 'w') as f:
+        f.write('\n'.join(lines))
+    return path
+
+
+@pytest.mark.parametrize('im', ['trap', 'BE'])
+def test_tran_ladder_cluster_kernel(lib, im):
+    """A second circuit on the boundary/interior kernel (both integration
+    methods, a band wider than soliton's, inductor branches in the interior)
+    against the oracle's refactor-per-iteration loop."""
+    path = ladder_deck(im=im)
+    try:
+        wave, iters, status, ref, tran = tran_both(path)
+    finally:
+        os.remove(path)
+    assert tran.engine.last_path == 'schur'
+    assert wave.shape[1] > 150 and wave.shape[0] >= 300
+    check_tran(wave, iters, status, ref)
+    assert iters.max() >= 2          # the clamps do conduct
+
+
+def test_tran_cluster_kernel_falls_back(lib, monkeypatch):
+    """A run the boundary/interior kernel gives up on (status / pivot flag) is
+    repeated on the general kernels from the same operating point."""
+    orig = nd.Engine._schur_tran
+    seen = []
+
+    def refuse(self, *a):
+        seen.append(orig(self, *a))
+        return False
+    monkeypatch.setattr(nd.Engine, '_schur_tran', refuse)
+    path = ladder_deck(nsec=90)
+    try:
+        wave, iters, status, ref, tran = tran_both(path)
+    finally:
+        os.remove(path)
+    assert seen == [True] and tran.engine.last_path == 'engine'
+    check_tran(wave, iters, status, ref)
+
+
 @pytest.mark.parametrize('deck', ['rctransient.net', 'oscillator.net',
                                   'ring_osc_ahkab.net', 'memristor.net',
                                   'inverter_chain_bsim.net'])

@@ -21,17 +21,13 @@ w, it, rs, st = e.tran(x, src, rows, im='trap', sync=False)
 t1.record(); torch.cuda.synchronize()
 raw = e.prof.cpu().numpy().copy()
 c = e.phase_cycles()
-tot = sum(v for k, v in c.items() if k in e.PHASES[:7])
+tot = sum(v for k, v in c.items() if k in e.PHASES[:7] or e.last_path == 'schur')
 print('ms', t0.elapsed_time(t1), 'steps', len(timeVec), 'info', e.info)
 for k, v in c.items():
     print('%-14s %12d cycles  %6.2f us/step' % (k, v, v / 1.965e3 / (len(timeVec) - 1)))
 print('sum main', tot / 1.965e3 / (len(timeVec) - 1), 'us/step')
 if e.last_path == 'schur':
-    names = ['-', 'newton: rows + interior solve | device sweep', 'boundary factor+solve',
-             'X dx + max', 'update', 'accept: boundary rows', 'chord: x update',
-             'exchange 1 (newton)', 'accept + chord interior | device sweep',
-             'accept/chord: exchange', 'chord: boundary resolve', 'boundary assembly',
-             'exchange 2 (newton)']
+    names = e.SCHUR_PHASES
     tot = 0
     for k, nm in enumerate(names):
         print('%-48s %8.2f us/step' % (nm, raw[k] / 1.965e3 / (len(timeVec) - 1)))
