@@ -218,40 +218,7 @@ struct GridTeam {
     __device__ GridTeam() : grid(cg::this_grid()), phase(0) {}
     __device__ int rank() const { return blockIdx.x * blockDim.x + threadIdx.x; }
     __device__ int size() const { return gridDim.x * blockDim.x; }
-    // Grid barrier: one atomic per CTA on a counter that the last arriver
-    // resets before it releases the next generation (the words sit behind the
-    // reduction scratch, zero before the first launch and again after every
-    // barrier).  The cooperative launch guarantees that all CTAs are resident.
-    // CDN_GRID_CG_SYNC=1 selects cooperative-groups' grid.sync() for A/B runs.
-#ifndef CDN_GRID_CG_SYNC
-#define CDN_GRID_CG_SYNC 0
-#endif
-    __device__ void sync() const {
-#if CDN_GRID_CG_SYNC
-        grid.sync();
-#else
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned* cnt = (unsigned*)(gred + 2 * gridDim.x + 2);
-            unsigned* gen = cnt + 32;                  // its own 128-byte line
-            unsigned g;
-            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(g) : "l"(gen) : "memory");
-            __threadfence();
-            if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
-                *cnt = 0u;
-                __threadfence();
-                asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(gen), "r"(g + 1u) : "memory");
-            } else {
-                unsigned now;
-                do {
-                    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(now) : "l"(gen) : "memory");
-                } while (now == g);
-            }
-            __threadfence();
-        }
-        __syncthreads();
-#endif
-    }
+    __device__ void sync() const { grid.sync(); }
     __device__ double max(double v) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -263,7 +230,7 @@ struct GridTeam {
             for (int k = 1; k < nw; ++k) r = fmax(r, sred[k]);
             gred[phase * gridDim.x + blockIdx.x] = r;
         }
-        sync();
+        grid.sync();
         double r = -INFINITY;
         for (int k = threadIdx.x & 31; k < (int)gridDim.x; k += 32)
             r = fmax(r, __ldcg(gred + phase * gridDim.x + k));
@@ -283,7 +250,7 @@ struct GridTeam {
             for (int k = 1; k < nw; ++k) r += sred[k];
             gred[phase * gridDim.x + blockIdx.x] = r;
         }
-        sync();
+        grid.sync();
         double r = 0.0;
         for (int k = threadIdx.x & 31; k < (int)gridDim.x; k += 32)
             r += __ldcg(gred + phase * gridDim.x + k);
