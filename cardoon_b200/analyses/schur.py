@@ -41,6 +41,7 @@ import scipy.sparse.linalg as spla
 from scipy.sparse.csgraph import (breadth_first_order, connected_components,
                                   reverse_cuthill_mckee)
 
+LONG_ROW = 32              # rows of Linv longer than this are summed by a warp
 MAX_BOUNDARY = 96          # unknowns of the replicated boundary system
 MAX_BAND = 4               # half bandwidth of T the kernel handles
 DROP = 2. ** -60
@@ -146,6 +147,61 @@ class Csr(object):
     def tosp(self):
         return sp.csr_matrix((self.val, self.col.astype(np.int32), self.ptr),
                              shape=self.shape)
+
+
+class Ell(object):
+    """Sliced ELLPACK copy of the short rows of a CSR operator, for the
+    one-thread-per-row products of the kernel: rows sorted by length, slices
+    of 32 rows, every slice stored column-major (entry j of lane l at
+    sbase[s] + 32 j + l) and padded to a multiple of four entries per row with
+    (column 0, value 0).  A warp then reads consecutive shared-memory words
+    (no bank conflicts on the value and column streams) and needs no
+    predicates.  ``rowid[slot]`` = row a slot computes (-1: padding slot);
+    rows longer than ``long_row`` are left to the caller (a warp sums each)."""
+
+    def __init__(self, op, long_row=None):
+        ln = np.diff(op.ptr)
+        rows = np.arange(op.shape[0])
+        if long_row is not None:
+            rows = rows[ln <= long_row]
+        order = rows[np.argsort(-ln[rows], kind='stable')]
+        nsl = (len(order) + 31) // 32
+        self.nslots = 32 * nsl
+        self.rowid = np.full(self.nslots, -1, dtype=np.int16)
+        self.rowid[:len(order)] = order
+        self.sbase = np.zeros(nsl + 1, dtype=np.int32)
+        vals, cols = [], []
+        for s_ in range(nsl):
+            rs = order[32 * s_:32 * s_ + 32]
+            w = int(ln[rs].max()) if len(rs) else 0
+            w = (w + 3) // 4 * 4
+            v = np.zeros((w, 32))
+            c = np.zeros((w, 32), dtype=np.uint16)
+            for lane, r in enumerate(rs):
+                a, b = op.ptr[r], op.ptr[r + 1]
+                v[:b - a, lane] = op.val[a:b]
+                c[:b - a, lane] = op.col[a:b]
+            vals.append(v.ravel())
+            cols.append(c.ravel())
+            self.sbase[s_ + 1] = self.sbase[s_] + 32 * w
+        self.val = np.concatenate(vals) if vals else np.zeros(0)
+        self.col = np.concatenate(cols) if cols else np.zeros(0, np.uint16)
+        self.shape = op.shape
+
+    def dot(self, v, out=None):
+        """Product of the rows held here (numpy statement of the kernel's
+        loop); rows not held keep the value of ``out``."""
+        out = np.zeros(self.shape[0]) if out is None else out
+        for slot in range(self.nslots):
+            r = self.rowid[slot]
+            if r < 0:
+                continue
+            s_, lane = slot >> 5, slot & 31
+            base = self.sbase[s_]
+            w = (self.sbase[s_ + 1] - base) >> 5
+            idx = base + 32 * np.arange(w) + lane
+            out[r] = np.dot(self.val[idx], v[self.col[idx]])
+        return out
 
 
 def device_port_unknowns(topo):
@@ -310,6 +366,11 @@ def analyse(topo, a0, ncta=8, stamps=None, out_off=None, jac_off=None,
             c.X = Csr(sp.csr_matrix((0, nB)))
             c.Asi = c.Csi = Csr(sp.csr_matrix((nB, 0)))
             c.Arow = c.Crow = Csr(sp.csr_matrix((0, nB)))
+        # what the kernel's row products read (the CSR copies stay for the
+        # emulation and the long rows of Linv)
+        c.eLinv = Ell(c.Linv, LONG_ROW)
+        c.eUinv, c.eX = Ell(c.Uinv), Ell(c.X)
+        c.eArow = Ell(c.Arow)
         P.ctas.append(c)
     P.has_csi = any(c.Csi.nnz for c in P.ctas)
     # ---- device gathers ------------------------------------------------------------
@@ -355,17 +416,25 @@ def analyse(topo, a0, ncta=8, stamps=None, out_off=None, jac_off=None,
 # device packaging (layout: csrc/schur.cuh, enums SOP_* / SH_*)
 # ---------------------------------------------------------------------------
 NOPS = 12
-LONG_ROW = 32
-SH_OPS, SH_WORDS = 8, 64
+NELL = 4
+SH_OPS, SH_WORDS = 8, 96
 SH_TB = SH_OPS + 4 * NOPS
+SH_ELL = 64
 
 
 def pack_blob(P, c):
     """Operator blob of CTA ``c``: 64 header words, then per operator row
     pointers (int32), columns (uint16) and values (float64), the band of T0 and
     the unknown numbers of the interior rows and of the boundary."""
-    ops = [c.Linv, c.Uinv, c.X, c.Asi, c.Csi, c.Arow, c.Crow, P.Abb, P.Cbb,
-           P.Dcur, P.Dchg, P.Tjac]
+    # CSR part: the long rows of Linv (by decreasing length, so that dealing them
+    # to the warps round-robin balances), the boundary operators
+    ln = np.diff(c.Linv.ptr)
+    llong = np.nonzero(ln > LONG_ROW)[0]
+    llong = llong[np.argsort(-ln[llong], kind='stable')].astype(np.int32)
+    Llong = c.Linv.tosp()[llong] if len(llong) else sp.csr_matrix((0, max(1, c.m)))
+    empty = Csr(sp.csr_matrix((0, 1)))
+    ops = [Csr(Llong, False), empty, empty, c.Asi, c.Csi, empty, c.Crow, P.Abb,
+           P.Cbb, P.Dcur, P.Dchg, P.Tjac]
     hdr = np.zeros(SH_WORDS, dtype=np.int32)
     hdr[0:6] = (c.m, P.nB, P.band, P.out_size, P.jac_size, int(P.has_csi))
     parts = [None]
@@ -386,10 +455,17 @@ def pack_blob(P, c):
     hdr[SH_TB] = put(P.Tb.astype(np.float64).ravel())
     hdr[SH_TB + 1] = put(c.Ic.astype(np.int32))
     hdr[SH_TB + 2] = put(P.B.astype(np.int32))
-    # rows of Linv a warp sums together (csrc/schur.cuh CDN_SCHUR_LONG)
-    llong = np.nonzero(np.diff(c.Linv.ptr) > LONG_ROW)[0].astype(np.int32)
+    # rows of Linv a warp sums together: row k of the CSR operator SOP_LINV is
+    # row llong[k] of the piece
     hdr[6] = put(llong)
     hdr[7] = len(llong)
+    for k, e in enumerate((c.eLinv, c.eUinv, c.eX, c.eArow)):
+        w0 = SH_ELL + 5 * k
+        hdr[w0] = e.nslots
+        hdr[w0 + 1] = put(e.sbase.astype(np.int32))
+        hdr[w0 + 2] = put(e.col.astype(np.uint16))
+        hdr[w0 + 3] = put(e.val.astype(np.float64))
+        hdr[w0 + 4] = put(e.rowid.astype(np.int16))
     pad = (-pos[0]) % 16
     parts.append(b'\0' * pad)
     pos[0] += pad

@@ -37,7 +37,9 @@ enum { SOP_LINV = 0, SOP_UINV, SOP_X, SOP_ASI, SOP_CSI, SOP_AROW, SOP_CROW, SOP_
        SOP_DCUR, SOP_DCHG, SOP_TJAC };
 // blob header (32-bit words): see schur.py pack_blob
 enum { SH_M = 0, SH_NB, SH_BAND, SH_OUT, SH_JAC, SH_HASCSI, SH_LLONG, SH_NLONG, SH_OPS = 8,
-       SH_TB = SH_OPS + 4 * CDN_SCHUR_NOPS, SH_IC, SH_B, SH_BYTES, SH_WORDS = 64 };
+       SH_TB = SH_OPS + 4 * CDN_SCHUR_NOPS, SH_IC, SH_B, SH_BYTES, SH_ELL = 64, SH_WORDS = 96 };
+// sliced-ELLPACK copies (schur.py Ell) of the operators applied one thread per row
+enum { EOP_LINV = 0, EOP_UINV, EOP_X, EOP_AROW };
 
 struct cdn_schur_args {
     cdn_group_dev groups[CDN_MAX_GROUPS];   // vpos / vneg re-mapped to boundary positions
@@ -103,6 +105,49 @@ __device__ __forceinline__ double sop_row(const SOp& op, int r, const double* in
         s2 = fma(v[2], x[2], s2); s3 = fma(v[3], x[3], s3);
         s0 = fma(v[4], x[4], s0); s1 = fma(v[5], x[5], s1);
         s2 = fma(v[6], x[6], s2); s3 = fma(v[7], x[7], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+// Sliced ELLPACK operator: slices of 32 rows sorted by length, column-major
+// inside a slice, rows padded to a multiple of four entries (value 0, column 0):
+// a warp reads consecutive shared-memory words for values and columns (the CSR
+// walk was bound by bank conflicts: rows of different length start at scattered
+// addresses) and needs no predicates.
+struct EOp {
+    int nslots;
+    const int* sbase;
+    const unsigned short* col;
+    const double* val;
+    const short* rowid;
+};
+
+__device__ __forceinline__ EOp eop_get(const unsigned char* blob, int k) {
+    const int* h = (const int*)blob + SH_ELL + 5 * k;
+    EOp o;
+    o.nslots = h[0];
+    o.sbase = (const int*)(blob + h[1]);
+    o.col = (const unsigned short*)(blob + h[2]);
+    o.val = (const double*)(blob + h[3]);
+    o.rowid = (const short*)(blob + h[4]);
+    return o;
+}
+
+__device__ __forceinline__ double ell_slot(const EOp& op, int slot, const double* in) {
+    const int sl = slot >> 5;
+    const int base = op.sbase[sl];
+    const int w = (op.sbase[sl + 1] - base) >> 5;
+    const double* v = op.val + base + (slot & 31);
+    const unsigned short* c = op.col + base + (slot & 31);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 2
+    for (int j = 0; j < w; j += 4) {
+        const int c0 = c[32 * j], c1 = c[32 * j + 32], c2 = c[32 * j + 64], c3 = c[32 * j + 96];
+        const double v0 = v[32 * j], v1 = v[32 * j + 32], v2 = v[32 * j + 64], v3 = v[32 * j + 96];
+        s0 = fma(v0, in[c0], s0);
+        s1 = fma(v1, in[c1], s1);
+        s2 = fma(v2, in[c2], s2);
+        s3 = fma(v3, in[c3], s3);
     }
     return (s0 + s1) + (s2 + s3);
 }
@@ -333,6 +378,8 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
     const SOp oCrow = sop_get(s.blob, SOP_CROW), oAbb = sop_get(s.blob, SOP_ABB);
     const SOp oCbb = sop_get(s.blob, SOP_CBB), oDcur = sop_get(s.blob, SOP_DCUR);
     const SOp oDchg = sop_get(s.blob, SOP_DCHG), oTjac = sop_get(s.blob, SOP_TJAC);
+    const EOp eLinv = eop_get(s.blob, EOP_LINV), eUinv = eop_get(s.blob, EOP_UINV);
+    const EOp eX = eop_get(s.blob, EOP_X), eArow = eop_get(s.blob, EOP_AROW);
     const double* Tb = (const double*)(s.blob + ((const int*)s.blob)[SH_TB]);
     const int* Ic = (const int*)(s.blob + ((const int*)s.blob)[SH_IC]);
     const int* Bl = (const int*)(s.blob + ((const int*)s.blob)[SH_B]);
@@ -443,26 +490,38 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
     // summed by a warp each)
     auto interior_solve = [&](const double* yI) {
         wbar();
+        // (row q of the CSR operator SOP_LINV is row llong[q] of the piece, longest
+        // first; four entries per lane in flight)
         for (int q = tid >> 5; q < nlong; q += NWK / 32) {
-            const int r = llong[q];
-            const int a = oLinv.ptr[r], b = oLinv.ptr[r + 1];
-            double acc = 0.0, acc2 = 0.0;
-            for (int k = a + (tid & 31); k < b; k += 64) {
-                const bool ok2 = k + 32 < b;
-                const int c1 = oLinv.col[k], c2 = ok2 ? (int)oLinv.col[k + 32] : 0;
-                const double v1 = oLinv.val[k], v2 = ok2 ? oLinv.val[k + 32] : 0.0;
-                acc = fma(v1, yI[c1], acc);
-                acc2 = fma(v2, yI[c2], acc2);
+            const int a = oLinv.ptr[q], b = oLinv.ptr[q + 1];
+            double a0_ = 0.0, a1_ = 0.0, a2_ = 0.0, a3_ = 0.0;
+            for (int k = a + (tid & 31); k < b; k += 128) {
+                const bool k1 = k + 32 < b, k2 = k + 64 < b, k3 = k + 96 < b;
+                const int c0 = oLinv.col[k], c1 = k1 ? (int)oLinv.col[k + 32] : 0;
+                const int c2 = k2 ? (int)oLinv.col[k + 64] : 0, c3 = k3 ? (int)oLinv.col[k + 96] : 0;
+                const double v0 = oLinv.val[k], v1 = k1 ? oLinv.val[k + 32] : 0.0;
+                const double v2 = k2 ? oLinv.val[k + 64] : 0.0, v3 = k3 ? oLinv.val[k + 96] : 0.0;
+                a0_ = fma(v0, yI[c0], a0_);
+                a1_ = fma(v1, yI[c1], a1_);
+                a2_ = fma(v2, yI[c2], a2_);
+                a3_ = fma(v3, yI[c3], a3_);
             }
-            acc += acc2;
+            double acc = (a0_ + a1_) + (a2_ + a3_);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-            if ((tid & 31) == 0) s.uI[r] = acc;
+            if ((tid & 31) == 0) s.uI[llong[q]] = acc;
         }
-        for (int r = tid; r < m; r += NWK)
-            if (oLinv.ptr[r + 1] - oLinv.ptr[r] <= CDN_SCHUR_LONG) s.uI[r] = sop_row(oLinv, r, yI);
+        for (int slot = tid; slot < eLinv.nslots; slot += NWK) {
+            const int r = eLinv.rowid[slot];
+            const double acc = ell_slot(eLinv, slot, yI);
+            if (r >= 0) s.uI[r] = acc;
+        }
         wbar();
-        for (int r = tid; r < m; r += NWK) s.tI[r] = sop_row(oUinv, r, s.uI);
+        for (int slot = tid; slot < eUinv.nslots; slot += NWK) {
+            const int r = eUinv.rowid[slot];
+            const double acc = ell_slot(eUinv, slot, s.uI);
+            if (r >= 0) s.tI[r] = acc;
+        }
         wbar();
     };
     // time-varying sources of sample i on the rows this thread just wrote
@@ -561,7 +620,11 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
         if (chord) {
             band_solve();
             SCH_P(10);
-            for (int r = tid; r < m; r += TPB) xI[r] += s.tI[r] - sop_row(oX, r, s.dB);
+            for (int slot = tid; slot < eX.nslots; slot += TPB) {
+                const int r = eX.rowid[slot];
+                const double acc = ell_slot(eX, slot, s.dB);
+                if (r >= 0) xI[r] += s.tI[r] - acc;
+            }
             for (int j = tid; j < nB; j += TPB) xB[j] += s.dB[j];
             __syncthreads();
         }
@@ -575,10 +638,10 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
             // device sweep with derivatives beside the interior residual and solve
             if (!evw || !is_worker) sweep(true);
             if (!evw || is_worker) {
-                for (int r = tid; r < m; r += NWK) {
-                    const double v = sop_row(oArow, r, s.xloc);
-                    s.ivI[r] = v;
-                    s.qI[r] = s.svI[r] - v;
+                for (int slot = tid; slot < eArow.nslots; slot += NWK) {
+                    const int r = eArow.rowid[slot];
+                    const double v = ell_slot(eArow, slot, s.xloc);
+                    if (r >= 0) { s.ivI[r] = v; s.qI[r] = s.svI[r] - v; }
                 }
                 interior_solve(s.qI);
                 for (int j = tid; j < nB; j += NWK) {
@@ -624,12 +687,16 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
             // no damping
             double mloc = 0.0;
             bool conv = true;
-            for (int r = tid; r < m; r += TPB) {
-                const double d = s.tI[r] - sop_row(oX, r, s.dB);
-                s.tI[r] = d;
-                mloc = fmax(mloc, fabs(d));
-                const double xo = xI[r], xn = xo + d;
-                conv = conv && (fabs(d) < o.reltol * fmax(fabs(xo), fabs(xn)) + o.abstol);
+            for (int slot = tid; slot < eX.nslots; slot += TPB) {
+                const int r = eX.rowid[slot];
+                const double acc = ell_slot(eX, slot, s.dB);
+                if (r >= 0) {
+                    const double d = s.tI[r] - acc;
+                    s.tI[r] = d;
+                    mloc = fmax(mloc, fabs(d));
+                    const double xo = xI[r], xn = xo + d;
+                    conv = conv && (fabs(d) < o.reltol * fmax(fabs(xo), fabs(xn)) + o.abstol);
+                }
             }
             for (int j = tid; j < nB; j += TPB) {
                 const double d = s.dB[j];

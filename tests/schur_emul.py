@@ -161,3 +161,95 @@ class SchurEmul(object):
             X[i] = self._full_x()
         return X, iters, resv
 
+
+
+class SchurEmulSlaved(SchurEmul):
+    """The same time loop with the interior eliminated analytically: the
+    interior equations are linear, so with z_I = A_II^-1 sv_I (ONE interior solve
+    per time step) every solve of that step needs only
+        t_I = z_I - (x_I + X x_B)          (interior part of J^-1 y)
+        r_B = (sv_B - A_BI z_I) - T0 x_B - dev(x_B)
+    and the chord predictor the stored x'_B, dev(x'_B) and w'_I = x'_I + X x'_B
+    of the last residual evaluation.  One exchange of boundary partial sums per
+    time step instead of one per solve."""
+
+    def run(self, x0, src, qscale_jac):
+        P = self.P
+        a0 = P.a0
+        W = 2 * P.band + 1
+        ns = src.shape[0]
+        self.xB = x0[P.B].copy()
+        self.xI = [x0[c.Ic].copy() for c in P.ctas]
+        X = np.zeros((ns, P.n))
+        X[0] = x0
+        iters = np.zeros(ns, dtype=int)
+        resv = np.zeros(ns)
+        T0 = np.zeros((P.nB, P.nB))
+        for r in range(P.nB):
+            for c_ in range(max(0, r - P.band), min(P.nB, r + P.band + 1)):
+                T0[r, c_] = P.Tb[r, c_ - r + P.band]
+        self._eval(False)
+        qB, qI = self._charge()
+        qpB, qpI = qB.copy(), [q.copy() for q in qI]
+        dqB, dqI = np.zeros_like(qB), [np.zeros_like(q) for q in qI]
+        xBp = devp = wIp = None
+        for i in range(1, ns):
+            self._eval(False)
+            qB, qI = self._charge()
+            if self.trap:
+                dqB = -dqB + a0 * (qB - qpB)
+                dqI = [-d + a0 * (q - qp) for d, q, qp in zip(dqI, qI, qpI)]
+            qpB, qpI = qB, qI
+            svB = a0 * qpB + (dqB if self.trap else 0.) + src[i][P.B]
+            svI = [a0 * qp + (d if self.trap else 0.) + src[i][c.Ic]
+                   for qp, d, c in zip(qpI, dqI, P.ctas)]
+            zI = [c.Uinv.dot(c.Linv.dot(s)) for c, s in zip(P.ctas, svI)]
+            gB = np.zeros(P.nB)
+            for c, z in zip(P.ctas, zI):
+                gB += c.Asi.dot(z)                     # (the exchange of the step)
+            bB = svB - gB
+            if i > 1:
+                rB = bB - T0 @ xBp - devp
+                dB = band_solve(self.Tf, P.band, rB)
+                dI = [z - w - c.X.dot(dB) for c, z, w in zip(P.ctas, zI, wIp)]
+                self.xB = self.xB + dB
+                self.xI = [x + d for x, d in zip(self.xI, dI)]
+            ok = False
+            it = 0
+            while it < self.maxiter:
+                out, jac = self.dev_eval(self._full_x(), True)
+                jac_a0 = qscale_jac(jac, a0)
+                devB = P.Dcur.dot(out) + a0 * P.Dchg.dot(out)
+                wI = [xi + c.X.dot(self.xB) for c, xi in zip(P.ctas, self.xI)]
+                xBp, devp, wIp = self.xB.copy(), devB, wI
+                rB = bB - T0 @ self.xB - devB
+                Tb = P.Tb + P.Tjac.dot(jac_a0).reshape(P.nB, W)
+                self.Tf = band_factor(Tb, P.band)
+                dB = band_solve(self.Tf, P.band, rB)
+                dI = [z - w - c.X.dot(dB) for c, z, w in zip(P.ctas, zI, wI)]
+                m = max([np.abs(dB).max()] + [np.abs(d).max() for d in dI if len(d)])
+                scale = self.maxdelta / m if m > self.maxdelta else 1.
+                conv = True
+                d = dB * scale
+                xn = self.xB + d
+                conv &= bool(np.all(np.abs(d) < self.reltol * np.maximum(
+                    np.abs(self.xB), np.abs(xn)) + self.abstol))
+                self.xB = xn
+                newI = []
+                for xi, di in zip(self.xI, dI):
+                    d = di * scale
+                    xn = xi + d
+                    conv &= bool(np.all(np.abs(d) < self.reltol * np.maximum(
+                        np.abs(xi), np.abs(xn)) + self.abstol))
+                    newI.append(xn)
+                self.xI = newI
+                res = m * scale
+                it += 1
+                if conv:
+                    ok = True
+                    break
+            iters[i], resv[i] = it, res
+            if not ok:
+                return X[:i], iters[:i], resv[:i]
+            X[i] = self._full_x()
+        return X, iters, resv

@@ -109,3 +109,23 @@ def test_schur_time_loop_soliton_vs_oracle():
     tol = glVar.reltol * np.abs(r['X']) + glVar.abstol
     assert np.all(np.abs(X - r['X']) <= tol)
     assert np.all(np.abs(iters - r['iters']) <= 1)
+
+
+def test_ell_copies_match_csr():
+    """The sliced-ELLPACK copies the kernel walks give the products of the CSR
+    operators they were made from (long rows of Linv excluded: a warp sums
+    those from the CSR part of the blob)."""
+    ckt, an, topo, idx, P = _soliton_plan()
+    rng = np.random.default_rng(3)
+    for c in P.ctas[:3]:
+        for nm in ('Linv', 'Uinv', 'X', 'Arow'):
+            op, e = getattr(c, nm), getattr(c, 'e' + nm)
+            v = rng.standard_normal(op.shape[1])
+            held = e.rowid[e.rowid >= 0]
+            ref, got = op.dot(v), e.dot(v)
+            assert np.allclose(got[held], ref[held], rtol=1e-13,
+                               atol=1e-13 * np.abs(ref).max())
+            if nm != 'Linv':
+                assert len(held) == op.shape[0]
+        blob = schur.pack_blob(P, c)
+        assert len(blob) % 16 == 0
