@@ -816,25 +816,44 @@ def run_mc(args, D):
     gshape = (job,) + tuple(wave.shape[1:])
     wave_h = torch.empty(gshape, dtype=torch.float64).pin_memory()
     iters_h = torch.empty((job, iters.shape[1]), dtype=torch.int32).pin_memory()
-    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    # three streams: H2D of step k + 1 and D2H of step k - 1 run beside the
+    # kernels of step k (records and results are double-buffered on the device)
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    params_dd = [params_d, [t.clone() for t in params_d]]
+    h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+    run_done = [torch.cuda.Event(), torch.cuda.Event()]
+    keep = [None, None]
 
     def e2e_run(K):
+        main = torch.cuda.current_stream()
         for k in range(K):
-            buf = pinned[k % 2]
+            buf, pd = pinned[k % 2], params_dd[k % 2]
             if k >= 2:
-                copied[k % 2].synchronize()     # its H2D has been consumed
+                h2d_done[k % 2].synchronize()   # pinned buffer consumed
             bt.pack_batch(over, out=[t.numpy() for t in buf],
                           device_major=True)
-            for d, h in zip(params_d, buf):
-                d.copy_(h, non_blocking=True)
-            copied[k % 2].record()
-            w, it, st, _ = bt.run_device(params_d, rows, B)
+            with torch.cuda.stream(s_h2d):
+                if k >= 2:
+                    s_h2d.wait_event(run_done[k % 2])   # run k - 2 has read pd
+                for d, h in zip(pd, buf):
+                    d.copy_(h, non_blocking=True)
+                h2d_done[k % 2].record(s_h2d)
+            main.wait_event(h2d_done[k % 2])
+            w, it, st, _ = bt.run_device(pd, rows, B)
             w, it, st = mc.gather_results(w, it, st, D.dist)
-            wave_h.copy_(w, non_blocking=True)
-            iters_h.copy_(it, non_blocking=True)
+            run_done[k % 2].record(main)
+            keep[k % 2] = (w, it, st)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(run_done[k % 2])
+                wave_h.copy_(w, non_blocking=True)
+                iters_h.copy_(it, non_blocking=True)
+                w.record_stream(s_d2h)
+                it.record_stream(s_d2h)
         torch.cuda.synchronize()
 
-    e2e_steps = max(3, min(args.steps, 6))
+    # enough steps that filling and draining the pipeline (one un-overlapped
+    # pack + H2D, one D2H) do not dominate
+    e2e_steps = max(3, min(2 * args.steps, 20))
     e2e_run(2)
     D.barrier()
     e0 = torch.cuda.Event(enable_timing=True)
@@ -854,8 +873,9 @@ def run_mc(args, D):
                steps=e2e_steps,
                path='raw samples (host) -> BatchTransient.pack_batch -> '
                     'pinned -> H2D -> run_device -> gather_results (NCCL) '
-                    '-> D2H; host packing of step k+1 overlaps the GPU run '
-                    'of step k; time = max(CUDA events, wall clock)')
+                    '-> D2H; host packing and H2D of step k+1 and D2H of '
+                    'step k-1 overlap the kernels of step k (three streams, '
+                    'double buffers); time = max(CUDA events, wall clock)')
     # one un-overlapped pass: what each stage costs
     tp = time.time()
     bt.pack_batch(over, out=[t.numpy() for t in pinned[0]],
