@@ -209,7 +209,7 @@ __device__ __forceinline__ int band_factor_solve(double* Tf, double* rB, double*
         }
         ny = rB[q];
         const double piv = win[0][0];
-        const double pinv = cdn_rcp(piv);
+        const double pinv = cdn_rcp1(piv);   // 2^-46: a Newton step is not sensitive to it
         if (!(fabs(piv) > 0.0) || !isfinite(pinv)) bad = 1;
         Dinv[k] = pinv;
 #pragma unroll
