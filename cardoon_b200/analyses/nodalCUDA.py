@@ -962,7 +962,8 @@ class Engine(object):
              wave=None, iters=None, res=None, sync=True, reuse_src=False):
         """Whole fixed-step time loop on the device (tran.py:171-206).
 
-        ``x0``: operating point [n] or [B, n] (None: keep self.x);
+        ``x0``: operating point [n] or [B, n], numpy or a device tensor (None:
+        keep self.x);
         ``src``: source vectors [nsamples, n] (tran.get_source(t_i));
         ``save_rows``: unknowns to record.  Returns (wave[B, nsamples, nsave],
         iters[B, nsamples], res[B, nsamples], status[B]) as device tensors
@@ -973,9 +974,12 @@ class Engine(object):
         torch = lib.torch
         nsamples = src.shape[0]
         if x0 is not None:
-            x0 = np.asarray(x0, dtype=np.float64)
-            self.x.copy_(torch.as_tensor(np.broadcast_to(
-                x0, (self.B, self.n)).copy()))
+            if hasattr(x0, 'data_ptr'):          # already on the device
+                self.x.copy_(x0.reshape(-1, self.n).expand(self.B, self.n))
+            else:
+                x0 = np.asarray(x0, dtype=np.float64)
+                self.x.copy_(torch.as_tensor(np.broadcast_to(
+                    x0, (self.B, self.n)).copy()))
         # constant rows go to src_dc, time-varying rows to a compact table
         if reuse_src and getattr(self, '_src_key', None) == (id(src),
                                                              src.shape):
