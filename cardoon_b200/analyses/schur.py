@@ -205,11 +205,12 @@ class Ell(object):
 
 
 def device_port_unknowns(topo):
-    s = set()
-    for g in topo.groups:
-        for k in ('vpos', 'vneg', 'cpos', 'cneg', 'qpos', 'qneg'):
-            s.update(int(v) for v in np.asarray(g[k]).ravel() if v >= 0)
-    return np.array(sorted(s), dtype=np.int64)
+    parts = [np.asarray(g[k]).ravel() for g in topo.groups
+             for k in ('vpos', 'vneg', 'cpos', 'cneg', 'qpos', 'qneg')]
+    if not parts:
+        return np.zeros(0, dtype=np.int64)
+    a = np.unique(np.concatenate(parts))
+    return a[a >= 0].astype(np.int64)
 
 
 def device_gathers(topo, bpos, out_off, jac_off):
@@ -258,6 +259,8 @@ def analyse(topo, a0, ncta=8, stamps=None, out_off=None, jac_off=None,
     n = topo.n
     if any(g['ndelay'] for g in topo.groups) or n >= 60000:
         return None
+    if sum(g['n'] for g in topo.groups) > 4 * MAX_BOUNDARY:
+        return None                    # (cannot have few port unknowns)
     G = sp.coo_matrix((topo.G[2], (topo.G[0], topo.G[1])), shape=(n, n)).tocsr()
     Cm = sp.coo_matrix((topo.C[2], (topo.C[0], topo.C[1])), shape=(n, n)).tocsr()
     A = (G + a0 * Cm).tocsr()
