@@ -684,7 +684,9 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
             if (s.red[32] != 0.0 && !piv_at) piv_at = i + 1;
             SCH_P(2);
             // dx_I = t_I - X dx_B (kept in tI), local max |dx|, convergence assuming
-            // no damping
+            // no damping -- and x is updated on that assumption right away (the old
+            // values are kept in qI / yB); a damped step, known after the exchange,
+            // re-does its update
             double mloc = 0.0;
             bool conv = true;
             for (int slot = tid; slot < eX.nslots; slot += TPB) {
@@ -696,6 +698,8 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
                     mloc = fmax(mloc, fabs(d));
                     const double xo = xI[r], xn = xo + d;
                     conv = conv && (fabs(d) < o.reltol * fmax(fabs(xo), fabs(xn)) + o.abstol);
+                    s.qI[r] = xo;
+                    xI[r] = xn;
                 }
             }
             for (int j = tid; j < nB; j += TPB) {
@@ -703,6 +707,8 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
                 mloc = fmax(mloc, fabs(d));
                 const double xo = xB[j], xn = xo + d;
                 conv = conv && (fabs(d) < o.reltol * fmax(fabs(xo), fabs(xn)) + o.abstol);
+                s.yB[j] = xo;
+                xB[j] = xn;
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) mloc = fmax(mloc, __shfl_xor_sync(0xffffffffu, mloc, off));
@@ -730,13 +736,15 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
                 conv = true;
                 for (int r = tid; r < m; r += TPB) {
                     const double d = s.tI[r] * scale;
-                    const double xo = xI[r], xn = xo + d;
+                    const double xo = s.qI[r], xn = xo + d;
                     conv = conv && (fabs(d) < o.reltol * fmax(fabs(xo), fabs(xn)) + o.abstol);
+                    xI[r] = xn;
                 }
                 for (int j = tid; j < nB; j += TPB) {
                     const double d = s.dB[j] * scale;
-                    const double xo = xB[j], xn = xo + d;
+                    const double xo = s.yB[j], xn = xo + d;
                     conv = conv && (fabs(d) < o.reltol * fmax(fabs(xo), fabs(xn)) + o.abstol);
+                    xB[j] = xn;
                 }
                 const int c2 = __syncthreads_and(conv ? 1 : 0);
                 if (tid == 0) s.snd[0] = c2 ? 1.0 : 0.0;
@@ -744,17 +752,6 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
                 cg_ = true;
                 for (int c = 0; c < ncta; ++c) cg_ = cg_ && (mb3[c * MB] != 0.0);
             }
-            for (int r = tid; r < m; r += TPB) {
-                double d = s.tI[r];
-                if (damp) d *= scale;
-                xI[r] += d;
-            }
-            for (int j = tid; j < nB; j += TPB) {
-                double d = s.dB[j];
-                if (damp) d *= scale;
-                xB[j] += d;
-            }
-            __syncthreads();
             res = damp ? mg * scale : mg;
             ++it;
             SCH_P(4);
