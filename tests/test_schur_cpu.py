@@ -7,9 +7,11 @@ refactors the whole matrix with SuperLU on every iteration as the reference
 does, nodalSP.py:281-303).
 """
 import numpy as np
+import pytest
 
 from tests import support as S
-from tests.schur_emul import SchurEmul, band_factor, band_solve
+from tests.schur_emul import (SchurEmul, SchurEmulSlaved, band_factor,
+                              band_solve)
 from tests.test_plan_cpu import setup, oracle_device_buffers
 from cardoon_b200.analyses import schur
 from cardoon_b200.globalVars import glVar
@@ -78,9 +80,15 @@ def test_schur_operators_soliton():
     assert np.allclose(dx, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max())
 
 
-def test_schur_time_loop_soliton_vs_oracle():
+@pytest.mark.parametrize('variant', [SchurEmul, SchurEmulSlaved])
+def test_schur_time_loop_soliton_vs_oracle(variant):
+    """The kernel's phase order (SchurEmul) and the variant with the interior
+    eliminated analytically (SchurEmulSlaved: one interior solve and one
+    exchange per time step; not built on the device -- after the operators moved
+    to sliced ELLPACK both interior phases are hidden behind the device sweeps)
+    against the oracle's refactor-per-iteration loop."""
     ckt, an, topo, idx, P = _soliton_plan()
-    nsamp = 40
+    nsamp = 40 if variant is SchurEmul else 25
     r = R.run_tran(ckt, glVar, an.tstop, an.tstep, an.im, idx=idx,
                    max_samples=nsamp)
     opt = R.Options(glVar)
@@ -102,8 +110,8 @@ def test_schur_time_loop_soliton_vs_oracle():
             off += nout * nx * n
         return jac
 
-    em = SchurEmul(P, dev_eval, glVar.abstol, glVar.reltol, glVar.maxdelta,
-                   int(glVar.maxiter), an.im == 'trap')
+    em = variant(P, dev_eval, glVar.abstol, glVar.reltol, glVar.maxdelta,
+                 int(glVar.maxiter), an.im == 'trap')
     X, iters, res = em.run(r['X'][0], src, qscale)
     assert len(X) == nsamp
     tol = glVar.reltol * np.abs(r['X']) + glVar.abstol
