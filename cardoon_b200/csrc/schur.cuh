@@ -437,10 +437,12 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
         const int par = xc & 1;
         ++xc;
         double* mine = s.mail + ((long)par * ncta + rank) * MB;
-        for (int t = tid; t < count * ncta; t += TPB) {
-            const int dst = t / count, j = t - dst * count;
-            double* remote = cluster.map_shared_rank(mine, dst);
-            remote[j] = s.snd[j];
+        for (int t = tid; t < 256 * ncta; t += TPB) {       // (count <= 2 * 96 + 2)
+            const int dst = t >> 8, j = t & 255;
+            if (j < count) {
+                double* remote = cluster.map_shared_rank(mine, dst);
+                remote[j] = s.snd[j];
+            }
         }
         cluster.sync();
         return s.mail + (long)par * ncta * MB;
@@ -451,10 +453,12 @@ __global__ void __launch_bounds__(TPB) engine_schur_kernel(const cdn_schur_args 
         __syncthreads();
         const int par = xc & 1;
         double* mine = s.mail + ((long)par * ncta + rank) * MB;
-        for (int t = tid; t < count * ncta; t += TPB) {
-            const int dst = t / count, j = t - dst * count;
-            double* remote = cluster.map_shared_rank(mine, dst);
-            remote[j] = s.snd[j];
+        for (int t = tid; t < 256 * ncta; t += TPB) {
+            const int dst = t >> 8, j = t & 255;
+            if (j < count) {
+                double* remote = cluster.map_shared_rank(mine, dst);
+                remote[j] = s.snd[j];
+            }
         }
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     };
