@@ -268,6 +268,10 @@ def analyse(topo, a0, ncta=8, stamps=None, out_off=None, jac_off=None,
     S = device_port_unknowns(topo)
     if len(S) == 0 or len(S) > MAX_BOUNDARY:
         return None
+    # operators of a piece must fit the shared memory of one CTA (>= ~200 bytes
+    # per interior row): do not even try pieces of thousands of rows
+    if (n - len(S)) > 1200 * ncta:
+        return None
     mask = np.ones(n, bool)
     mask[S] = False
     interior = np.nonzero(mask)[0]
