@@ -144,7 +144,7 @@ def test_tran_soliton_general_kernel(lib, monkeypatch):
     assert iters.sum() < 1.2 * len(iters)
 
 
-def ladder_deck(nsec=150, every=25, im='trap', tstep='2p'):
+def ladder_deck(nsec=150, every=25, im='trap', tstep='2p', clamp='diode'):
     """Synthetic deck for the boundary/interior kernel: an RC ladder with a
     series inductor now and then and diode clamps every ``every`` sections
     (the diodes have series resistance and junction capacitance, so each adds
@@ -167,8 +167,23 @@ def ladder_deck(nsec=150, every=25, im='trap', tstep='2p'):
             # capacitive coupling across a section (C[B, I] != 0 next to a clamp)
             lines.append('cap:cc{0} n{0} n{1} c=5f'.format(k, k + 1))
         if k % every == every - 1:
-            lines.append('diode:d{0} n{1} gnd isat=1e-14 rs=10. cj0=30f '
-                         'tt=1p'.format(k, k + 1))
+            kind = 'diode' if clamp == 'diode' else \
+                ('bjt', 'mos', 'diode')[(k // every) % 3]
+            if kind == 'diode':
+                lines.append('diode:d{0} n{1} gnd isat=1e-14 rs=10. cj0=30f '
+                             'tt=1p'.format(k, k + 1))
+            elif kind == 'bjt':          # diode-connected Gummel-Poon npn
+                lines.append('bjt:q{0} n{1} n{1} gnd model=t122'.format(
+                    k, k + 1))
+            else:                        # diode-connected BSIM3 n-channel
+                lines.append('mosbsim3:m{0} n{1} n{1} gnd gnd model=nch '
+                             'w=20u l=1u'.format(k, k + 1))
+    if clamp != 'diode':
+        lines += ['.model t122 bjt (type=npn isat=0.480e-15 nf=1.008 '
+                  'bf=99.655 vaf=90.000 ikf=0.190 ise=7.490e-15 ne=1.762 '
+                  'nr=1.010 br=38.400 var=7.000 ikr=93.200e-3 isc=0.200e-15 '
+                  'nc=1.042 cje=1.e-12 cjc=1.e-12 tf=10p)',
+                  '.model nch mosbsim3 (type=n)']
     lines += ['res:rl n{0} gnd r=50.'.format(nsec), '.end', '']
     fd, path = tempfile.mkstemp(suffix='.net', prefix='ladder_')
     os.close(fd)
@@ -191,6 +206,18 @@ def test_tran_ladder_cluster_kernel(lib, im):
     assert wave.shape[1] > 150 and wave.shape[0] >= 300
     check_tran(wave, iters, status, ref)
     assert iters.max() >= 2          # the clamps do conduct
+
+
+def test_tran_ladder_cluster_kernel_mixed_models(lib):
+    """The all-models instantiation of the cluster kernel (256 threads, device
+    sweeps of Gummel-Poon, BSIM3 and diode clamps on one warp)."""
+    path = ladder_deck(nsec=120, every=20, clamp='mixed')
+    try:
+        wave, iters, status, ref, tran = tran_both(path)
+    finally:
+        os.remove(path)
+    assert tran.engine.last_path == 'schur'
+    check_tran(wave, iters, status, ref)
 
 
 def test_tran_cluster_kernel_falls_back(lib, monkeypatch):
