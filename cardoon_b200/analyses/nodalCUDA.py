@@ -941,8 +941,13 @@ class Engine(object):
                                             lib.ptr(dev[4]))
         self._x_keep = self.x.clone()
         self.hinfo.zero_()
-        lib.check(lib.dll.cdn_schur_tran(self.plan, C.byref(r), C.byref(h),
-                                         lib.stream()))
+        rc = lib.dll.cdn_schur_tran(self.plan, C.byref(r), C.byref(h),
+                                    lib.stream())
+        if rc != 0:
+            # (a launch the device refuses -- cluster size, shared memory --
+            # must not cost the run: the general kernels take over for good)
+            self._schur = False
+            return False
         self.launches += 1
         if not check:
             return True
