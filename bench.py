@@ -1010,8 +1010,11 @@ def run_soliton(args, D):
     phases = phase_shares(D, e, step)
     value = D.world * (nsamples - 1) * args.steps / (ms * 1e-3)
 
+    var_rows = tran.source_rows()
+
     def e2e_step():
-        w, it, rs, st = e.tran(x, src, rows, im='trap', sync=True)
+        w, it, rs, st = e.tran(x, src, rows, im='trap', sync=True,
+                               var_rows=var_rows)
 
     ms_e, _, _ = timed_steps(D, e2e_step, max(2, min(args.steps, 5)), 1)
     e2e = dict(value=D.world * (nsamples - 1) * max(2, min(args.steps, 5))

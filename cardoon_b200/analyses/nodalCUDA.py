@@ -964,7 +964,8 @@ class Engine(object):
         return rows, cols
 
     def tran(self, x0, src, save_rows, im='trap', first=1, init_ic=True,
-             wave=None, iters=None, res=None, sync=True, reuse_src=False):
+             wave=None, iters=None, res=None, sync=True, reuse_src=False,
+             var_rows=None):
         """Whole fixed-step time loop on the device (tran.py:171-206).
 
         ``x0``: operating point [n] or [B, n], numpy or a device tensor (None:
@@ -973,7 +974,10 @@ class Engine(object):
         ``save_rows``: unknowns to record.  Returns (wave[B, nsamples, nsave],
         iters[B, nsamples], res[B, nsamples], status[B]) as device tensors
         (numpy if ``sync``).  ``reuse_src``: ``src`` and ``save_rows`` are the
-        arrays of the previous call and their device copies are kept.
+        arrays of the previous call and their device copies are kept;
+        ``var_rows``: the rows of ``src`` that vary with time, when the caller
+        knows them (TransientNodal.source_rows), else they are found by
+        comparing the samples.
         """
         lib = self.lib
         torch = lib.torch
@@ -990,7 +994,11 @@ class Engine(object):
                                                              src.shape):
             var = self._src_var
         else:
-            var = np.nonzero(np.any(src != src[0], axis=0))[0].astype(np.int32)
+            if var_rows is not None:
+                var = np.asarray(var_rows, dtype=np.int32)
+            else:
+                var = np.nonzero(np.any(src != src[0],
+                                        axis=0))[0].astype(np.int32)
             dc = src[0].copy()
             dc[var] = 0.
             self._src = (lib.dev(var) if len(var) else None,
@@ -1405,6 +1413,13 @@ class TransientNodal(_NLFunction):
         self.rhs = e.view('sv').cpu().numpy()
         return self.rhs
 
+    def source_rows(self):
+        """Rows of the source vector that time-dependent sources stamp."""
+        rows = set()
+        for elem in self.ckt.nD_sourceTDElem:
+            rows.update(r for r in elem.nD_sourceOut if r >= 0)
+        return np.array(sorted(rows), dtype=np.int32)
+
     def source_table(self, timeVec):
         """get_source(t) for every sample: [nsamples, n]."""
         return np.array([self.get_source(t).copy() for t in timeVec])
@@ -1420,5 +1435,6 @@ class TransientNodal(_NLFunction):
             self._make_engine(h, x0)
         src = self.source_table(timeVec)
         wave, iters, res, status = self.engine.tran(
-            x0, src, save_rows, im='trap' if self._imcode() else 'BE')
+            x0, src, save_rows, im='trap' if self._imcode() else 'BE',
+            var_rows=self.source_rows())
         return wave[0], iters[0], res[0], int(status[0])
