@@ -24,6 +24,18 @@
 // The chord predictor (tran.py:181) re-uses the last factors of T and the last
 // residual, with one exchange.
 //
+// What the time goes to is latency, so the kernel is organised around it
+// (measurements: profiles/README.md, tools/fp64_latency.cu):
+//   * the device sweep runs on the last warps of the CTA beside the interior
+//     work of the same phase (named barriers), which never needs device outputs;
+//   * operators applied one thread per row are stored as sliced ELLPACK, the
+//     long rows of Linv are summed by a warp each;
+//   * the cluster barrier is split into arrive / wait around the work that
+//     needs no remote data; x is updated on the undamped assumption before the
+//     convergence exchange;
+//   * the boundary LU runs on one thread in a register window, its triangular
+//     sweeps in blocks of eight rows with all loads ahead of the dependent chain.
+//
 // Anything this kernel cannot do (Newton failure -> helper chain, a pivot of T
 // that degrades) is reported through status / info and the host re-runs the
 // analysis on the general kernels (nodalCUDA.Engine.tran).
